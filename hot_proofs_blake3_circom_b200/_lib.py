@@ -1,0 +1,70 @@
+"""ctypes binding of libblake3wit.so (include/blake3wit.h).  Fails loudly when the library is absent."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+B3W_OK, B3W_ERR_INVALID, B3W_ERR_CUDA, B3W_ERR_NOMEM, B3W_ERR_DOMAIN, B3W_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+B3W_CIRCOM_ASSERT = 4
+
+EXPORTS = ("b3w_version", "b3w_last_error", "b3w_create", "b3w_destroy", "b3w_circuit_info", "b3w_wtns_header",
+           "b3w_input_signal", "b3w_witness_one", "b3w_witness_batch", "b3w_witness_batch_device",
+           "b3w_checksum_device", "b3w_calib_fill", "b3w_host_alloc", "b3w_host_free")
+
+
+class B3WError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(msg)
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [("circuit", C.c_uint32), ("device", C.c_int32), ("chunk", C.c_uint32), ("flags", C.c_uint32)]
+
+
+class Info(C.Structure):
+    _fields_ = [("witness_size", C.c_uint32), ("n_inputs", C.c_uint32), ("n32", C.c_uint32), ("n_public", C.c_uint32),
+                ("version", C.c_uint32 * 3), ("prime", C.c_uint8 * 32)]
+
+
+def lib_path():
+    return os.path.join(_HERE, "libblake3wit.so")
+
+
+def lib():
+    """Load the CUDA library.  There is no fallback: a missing build is an error."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    p = lib_path()
+    if not os.path.exists(p):
+        raise B3WError(B3W_ERR_CUDA, "%s is missing -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(there is no CPU fallback)" % p)
+    L = C.CDLL(p)
+    vp, u64, u32p = C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32)
+    L.b3w_version.restype = C.c_int
+    L.b3w_last_error.restype = C.c_char_p
+    L.b3w_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.b3w_destroy.argtypes = [vp]
+    L.b3w_destroy.restype = None
+    L.b3w_circuit_info.argtypes = [C.c_uint32, C.POINTER(Info)]
+    L.b3w_wtns_header.argtypes = [C.c_uint32, vp]
+    L.b3w_input_signal.argtypes = [C.c_uint32, C.c_char_p, u32p, u32p]
+    L.b3w_witness_one.argtypes = [vp, vp, vp]
+    L.b3w_witness_batch.argtypes = [vp, vp, u64, vp, vp, vp]
+    L.b3w_witness_batch_device.argtypes = [vp, vp, u64, vp, vp, vp, vp]
+    L.b3w_checksum_device.argtypes = [vp, vp, u64, vp, vp]
+    L.b3w_calib_fill.argtypes = [vp, vp, u64, vp]
+    L.b3w_host_alloc.argtypes = [C.c_size_t]
+    L.b3w_host_alloc.restype = vp
+    L.b3w_host_free.argtypes = [vp]
+    L.b3w_host_free.restype = None
+    _LIB = L
+    return L
+
+
+def check(rc, allow=()):
+    if rc != 0 and rc not in allow:
+        raise B3WError(rc, "libblake3wit error %d: %s" % (rc, lib().b3w_last_error().decode(errors="replace")))
+    return rc

@@ -1,0 +1,461 @@
+// blake3wit.cu -- sm_100a kernels + C ABI of libblake3wit.so (see include/blake3wit.h).
+//
+// Replaces the reference's wasm witness programs (build/**/**.wasm driven by
+// blake3_nova_js/witness_calculator.js:131-272).  Per instance:
+//   phase 1 (trace):  native u32 BLAKE3 compression, 4 lanes = 4 G functions in parallel, every
+//                     intermediate the circuit exposes is written to a ~4 KB shared-memory trace
+//                     (layout: trace_layout.h; semantics: circuits/blake3_compression.circom:72-228);
+//   phase 2 (expand): each lane turns one slot descriptor into one canonical 32-byte field element and
+//                     writes it with a single 256-bit streaming store (STG.E.256), so one warp
+//                     instruction covers 1 KiB of contiguous .wtns body.
+// The kernel is HBM-write bound: 770 976 B written per compression witness vs 112 B read.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <stdlib.h>
+#include <new>
+
+#include "../../include/blake3wit.h"
+#include "trace_layout.h"
+#include "slot_tables.h"
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512];
+static int fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CK(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess) return fail(B3W_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t rotr32(uint32_t x, int r) { return __funnelshift_r(x, x, r); }
+
+// 256-bit streaming store of one witness slot {w0..w7}: written once, never re-read by this kernel.
+__device__ __forceinline__ void st_slot(void *p, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4,
+                                        uint32_t w5, uint32_t w6, uint32_t w7) {
+  asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w0), "r"(w1), "r"(w2),
+               "r"(w3), "r"(w4), "r"(w5), "r"(w6), "r"(w7)
+               : "memory");
+}
+
+// BLAKE3 message schedule: MSG_SCHED[r][j] = index into the original m[] of the word that round r
+// sees at position j, i.e. sigma applied r times (circuits/blake3_common.circom:20-24,
+// circuits/blake3_compression.circom:198-209).
+__constant__ uint8_t MSG_SCHED[7][16] = {
+    {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15},
+    {2, 6, 3, 10, 7, 0, 4, 13, 1, 11, 12, 5, 9, 14, 15, 8},
+    {3, 4, 10, 12, 13, 2, 7, 14, 6, 5, 9, 0, 11, 15, 8, 1},
+    {10, 7, 12, 9, 14, 3, 13, 15, 4, 0, 11, 2, 5, 8, 1, 6},
+    {12, 13, 9, 11, 15, 10, 14, 8, 7, 2, 5, 3, 0, 1, 6, 4},
+    {9, 14, 11, 5, 8, 12, 15, 1, 13, 3, 0, 10, 2, 6, 4, 7},
+    {11, 15, 5, 0, 1, 9, 8, 6, 14, 10, 2, 12, 3, 4, 7, 13}};
+
+// One HalfFunG (circuits/blake3_compression.circom:72-100) on this lane's (a,b,c,d); lanes 0..3 record it.
+template <int R1, int R2>
+__device__ __forceinline__ void half_g(uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &d, uint32_t xy, uint32_t *rec,
+                                       bool writer) {
+  uint32_t s = a + b;
+  uint32_t hi1 = (s < a);
+  uint32_t s2 = s + xy;
+  hi1 += (s2 < s);                       // add1 = Bits34(v[a]+v[b]+xy): carries u = bit0, v = bit1   (:83,:88)
+  uint32_t d_old = d;
+  d = rotr32(d ^ s2, R1);                // rxor2 = RotXorWordBits(R1)(v[d], add1.out_bits)            (:89-90)
+  uint32_t t = c + d;
+  uint32_t hi3 = (t < c);                // add3 = Bits33(v[c] + rxor2.out_word)                        (:91)
+  uint32_t b_old = b;
+  b = rotr32(b ^ t, R2);                 // rxor4 = RotXorWordBits(R2)(v[b], add3.out_bits)            (:92-93)
+  a = s2;
+  c = t;
+  if (writer) {
+    *reinterpret_cast<uint4 *>(rec) = make_uint4(a, hi1, d_old, d);
+    *reinterpret_cast<uint4 *>(rec + 4) = make_uint4(c, hi3, b_old, b);
+  }
+}
+
+// Phase 1 for the compression circuit.  trace[TR_IN..TR_IN+28) must already hold h,m,t,b,d.
+// All 32 lanes execute (8 redundant groups of 4); lanes 0..3 write.
+__device__ __forceinline__ void compression_trace(uint32_t *trace, int lane) {
+  const int q = lane & 3;
+  const bool writer = lane < 4;
+  const uint32_t IVq[4] = {0x6A09E667u, 0xBB67AE85u, 0x3C6EF372u, 0xA54FF53Au};
+  uint32_t a = trace[TR_IN + q];                 // v[q]     = h[q]
+  uint32_t b = trace[TR_IN + 4 + q];             // v[4+q]   = h[4+q]
+  uint32_t c = q == 0 ? IVq[0] : q == 1 ? IVq[1] : q == 2 ? IVq[2] : IVq[3];   // v[8+q] = IV[q]
+  uint32_t d = trace[TR_IN + 24 + q];            // v[12+q]  = t0,t1,b,d               (:184-187)
+  const uint32_t h_lo = a, h_hi = b;
+  const uint32_t *m = trace + TR_IN + 8;
+#pragma unroll 1
+  for (int r = 0; r < 7; r++) {
+    uint32_t *rec = trace + TR_HG + 128 * r + 16 * q;
+    // columns: G(q, 4+q, 8+q, 12+q) with msg[2q], msg[2q+1]                              (:145-148)
+    half_g<16, 12>(a, b, c, d, m[MSG_SCHED[r][2 * q]], rec, writer);
+    half_g<8, 7>(a, b, c, d, m[MSG_SCHED[r][2 * q + 1]], rec + 8, writer);
+    // diagonals: lane q takes b from column q+1, c from q+2, d from q+3                  (:150-153)
+    b = __shfl_sync(0xffffffffu, b, (q + 1) & 3, 4);
+    c = __shfl_sync(0xffffffffu, c, (q + 2) & 3, 4);
+    d = __shfl_sync(0xffffffffu, d, (q + 3) & 3, 4);
+    half_g<16, 12>(a, b, c, d, m[MSG_SCHED[r][8 + 2 * q]], rec + 64, writer);
+    half_g<8, 7>(a, b, c, d, m[MSG_SCHED[r][9 + 2 * q]], rec + 72, writer);
+    b = __shfl_sync(0xffffffffu, b, (q + 3) & 3, 4);
+    c = __shfl_sync(0xffffffffu, c, (q + 2) & 3, 4);
+    d = __shfl_sync(0xffffffffu, d, (q + 1) & 3, 4);
+  }
+  if (writer) {                                  // out[i] = v[i]^v[i+8], out[i+8] = v[i+8]^h[i]  (:213-227)
+    trace[TR_OUT + q] = a ^ c;
+    trace[TR_OUT + 4 + q] = b ^ d;
+    trace[TR_OUT + 8 + q] = c ^ h_lo;
+    trace[TR_OUT + 12 + q] = d ^ h_hi;
+  }
+}
+
+// Phase 2: expand the trace into witness slots [0, ws) at `dst` (32 B per slot).
+template <bool HAS_FIELD>
+__device__ __forceinline__ void expand_slots(const uint32_t *trace, const uint32_t *__restrict__ desc, uint32_t ws,
+                                             uint8_t *dst, int lane, const uint32_t *prime) {
+#pragma unroll 4
+  for (uint32_t s = lane; s < ws; s += 32) {
+    const uint32_t dsc = __ldg(desc + s);
+    const uint32_t t = dsc & 0xFFFFu, k = (dsc >> 16) & 31u, kind = dsc >> 24;
+    const uint32_t w = trace[t];
+    uint32_t lo = kind == DK_BIT ? ((w >> k) & 1u) : w;
+    uint32_t hi = kind == DK_W64 ? trace[t + 1] : 0u;
+    if (HAS_FIELD && kind >= DK_FR) {
+      uint32_t v[8];
+      if (kind == DK_FR) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = trace[t + j];
+      } else {  // DK_NEG: p - w (0 stays 0)
+        uint32_t borrow = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          uint64_t x = (uint64_t)prime[j] - (j == 0 ? w : 0u) - borrow;
+          v[j] = w ? (uint32_t)x : 0u;
+          borrow = (uint32_t)(x >> 63);
+        }
+      }
+      st_slot(dst + (size_t)s * 32, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+    } else {
+      st_slot(dst + (size_t)s * 32, lo, hi, 0u, 0u, 0u, 0u, 0u, 0u);
+    }
+  }
+}
+
+#define WARPS_PER_CTA 8
+#define TRACE_STRIDE 960   // u32 words per warp (>= 944, 16-byte multiple)
+
+// k_blake3_comp_witness: one warp per instance, grid-stride over instances.
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+k_blake3_comp_witness(const uint32_t *__restrict__ in, uint64_t n, const uint32_t *__restrict__ desc, uint32_t ws,
+                      uint8_t *__restrict__ out, uint8_t *__restrict__ status, uint32_t *__restrict__ pub) {
+  __shared__ __align__(16) uint32_t s_trace[WARPS_PER_CTA][TRACE_STRIDE];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  uint32_t *trace = s_trace[wib];
+  const uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
+  if (lane == 0) { trace[TR_ZERO] = 0u; trace[TR_ONE] = 1u; }
+  for (uint64_t i = (uint64_t)blockIdx.x * WARPS_PER_CTA + wib; i < n; i += nwarps) {
+    __syncwarp();
+    if (lane < 28) trace[TR_IN + lane] = __ldg(in + i * 28 + lane);
+    __syncwarp();
+    compression_trace(trace, lane);
+    __syncwarp();
+    if (pub && lane < 16) pub[i * 16 + lane] = trace[TR_OUT + lane];
+    if (status && lane == 0) status[i] = 0;   // u32 inputs can never violate a constraint of this circuit
+    expand_slots<false>(trace, desc, ws, out + i * (uint64_t)ws * 32, lane, nullptr);
+  }
+}
+
+// ---- checksum of resident witnesses (verification helper; reads HBM) ----
+__device__ __forceinline__ uint64_t mix64(uint64_t x) { return (x + 1) * 0x9E3779B97F4A7C15ull; }
+__global__ void __launch_bounds__(256) k_checksum(const uint64_t *__restrict__ wit, uint64_t n, uint32_t ws,
+                                                  uint64_t *__restrict__ sums) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t i = warp; i < n; i += nwarps) {
+    const uint64_t *w = wit + i * (uint64_t)ws * 4;
+    uint64_t acc = 0;
+    for (uint32_t e = lane; e < ws * 4; e += 32) acc += (w[e] + 1) * mix64(e);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) sums[i] = acc;
+  }
+}
+
+// ---- pure-store calibration ----
+__global__ void __launch_bounds__(256) k_fill(uint8_t *buf, uint64_t nslots) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nslots; s += stride)
+    st_slot(buf + s * 32, (uint32_t)s & 1u, 0u, 0u, 0u, 0u, 0u, 0u, 0u);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct circuit_def {
+  const char *name;
+  uint32_t ws, n_inputs, n_public, trace_words;
+  const b3w_seg *segs;
+  size_t n_segs;
+  const uint8_t *prime;
+  int n_sig;
+  struct { const char *name; uint32_t off, size; } sig[12];
+};
+
+static const uint8_t PRIME_BN254[32] = {0x01, 0x00, 0x00, 0xf0, 0x93, 0xf5, 0xe1, 0x43, 0x91, 0x70, 0xb9,
+                                        0x79, 0x48, 0xe8, 0x33, 0x28, 0x5d, 0x58, 0x81, 0x81, 0xb6, 0x45,
+                                        0x50, 0xb8, 0x29, 0xa0, 0x31, 0xe1, 0x72, 0x4e, 0x64, 0x30};
+
+static const circuit_def CIRCUITS[] = {
+    {"blake3_compression", B3W_WS_COMPRESSION, 28, 16, B3W_TRACE_WORDS_COMPRESSION, B3W_SEGS_COMPRESSION,
+     sizeof(B3W_SEGS_COMPRESSION) / sizeof(b3w_seg), PRIME_BN254, 5,
+     {{"h", 0, 8}, {"m", 8, 16}, {"t", 24, 2}, {"b", 26, 1}, {"d", 27, 1}}},
+};
+static const int N_CIRCUITS = sizeof(CIRCUITS) / sizeof(CIRCUITS[0]);
+
+struct b3w_ctx {
+  const circuit_def *def;
+  int device;
+  int sm_count;
+  uint32_t chunk;
+  uint32_t *d_desc;
+  // staging for host-buffer batches: 2 ring slots
+  cudaStream_t st[2];
+  cudaEvent_t ev[2];
+  uint8_t *d_ring[2];
+  uint32_t *d_in[2];
+  uint8_t *d_status[2];
+  uint32_t *d_pub[2];
+  bool ring_ready;
+};
+
+extern "C" int b3w_version(void) { return B3W_VERSION; }
+extern "C" const char *b3w_last_error(void) { return g_err; }
+
+extern "C" int b3w_create(const b3w_config *cfg, b3w_ctx **out) {
+  if (!cfg || !out) return fail(B3W_ERR_INVALID, "b3w_create: null argument");
+  if (cfg->circuit >= (uint32_t)N_CIRCUITS) return fail(B3W_ERR_UNSUPPORTED, "b3w_create: circuit %u not built", cfg->circuit);
+  if (cfg->flags) return fail(B3W_ERR_INVALID, "b3w_create: flags must be 0");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(B3W_ERR_CUDA, "no CUDA device: %s (libblake3wit has no CPU path)", cudaGetErrorString(e));
+  int dev = cfg->device;
+  if (dev < 0) CK(cudaGetDevice(&dev));
+  if (dev >= ndev) return fail(B3W_ERR_INVALID, "device %d out of range (%d devices)", dev, ndev);
+  CK(cudaSetDevice(dev));
+  b3w_ctx *c = new (std::nothrow) b3w_ctx();
+  if (!c) return fail(B3W_ERR_NOMEM, "out of host memory");
+  memset(c, 0, sizeof *c);
+  c->def = &CIRCUITS[cfg->circuit];
+  c->device = dev;
+  c->chunk = cfg->chunk ? cfg->chunk : 1024;
+  CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, dev));
+  // expand the run-length table to one descriptor per slot and upload it
+  const circuit_def *d = c->def;
+  uint32_t *h = (uint32_t *)malloc((size_t)d->ws * 4);
+  if (!h) { delete c; return fail(B3W_ERR_NOMEM, "out of host memory"); }
+  uint32_t pos = 0;
+  for (size_t i = 0; i < d->n_segs; i++)
+    for (uint32_t j = 0; j < d->segs[i].count; j++) h[pos++] = d->segs[i].desc0 + j * d->segs[i].delta;
+  if (pos != d->ws) { free(h); delete c; return fail(B3W_ERR_INVALID, "slot table of %s is corrupt", d->name); }
+  cudaError_t e1 = cudaMalloc(&c->d_desc, (size_t)d->ws * 4);
+  if (e1 == cudaSuccess) e1 = cudaMemcpy(c->d_desc, h, (size_t)d->ws * 4, cudaMemcpyHostToDevice);
+  free(h);
+  if (e1 != cudaSuccess) { delete c; return fail(B3W_ERR_CUDA, "descriptor upload: %s", cudaGetErrorString(e1)); }
+  *out = c;
+  return B3W_OK;
+}
+
+static void free_ring(b3w_ctx *c) {
+  for (int k = 0; k < 2; k++) {
+    if (c->d_ring[k]) cudaFree(c->d_ring[k]);
+    if (c->d_in[k]) cudaFree(c->d_in[k]);
+    if (c->d_status[k]) cudaFree(c->d_status[k]);
+    if (c->d_pub[k]) cudaFree(c->d_pub[k]);
+    if (c->st[k]) cudaStreamDestroy(c->st[k]);
+    if (c->ev[k]) cudaEventDestroy(c->ev[k]);
+    c->d_ring[k] = nullptr; c->d_in[k] = nullptr; c->d_status[k] = nullptr; c->d_pub[k] = nullptr;
+    c->st[k] = nullptr; c->ev[k] = nullptr;
+  }
+  c->ring_ready = false;
+}
+
+extern "C" void b3w_destroy(b3w_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  free_ring(c);
+  if (c->d_desc) cudaFree(c->d_desc);
+  delete c;
+}
+
+static const circuit_def *find_def(uint32_t circuit) {
+  if (circuit >= (uint32_t)N_CIRCUITS) {
+    fail(B3W_ERR_UNSUPPORTED, "circuit %u not built", circuit);
+    return nullptr;
+  }
+  return &CIRCUITS[circuit];
+}
+
+extern "C" int b3w_circuit_info(uint32_t circuit, b3w_info *info) {
+  const circuit_def *d = find_def(circuit);
+  if (!d) return B3W_ERR_UNSUPPORTED;
+  if (!info) return fail(B3W_ERR_INVALID, "b3w_circuit_info: null argument");
+  info->witness_size = d->ws;
+  info->n_inputs = d->n_inputs;
+  info->n32 = 8;
+  info->n_public = d->n_public;
+  info->version[0] = 2; info->version[1] = 1; info->version[2] = 6;
+  memcpy(info->prime, d->prime, 32);
+  return B3W_OK;
+}
+
+extern "C" int b3w_wtns_header(uint32_t circuit, uint8_t hdr[76]) {
+  const circuit_def *d = find_def(circuit);
+  if (!d) return B3W_ERR_UNSUPPORTED;
+  if (!hdr) return fail(B3W_ERR_INVALID, "b3w_wtns_header: null argument");
+  // witness_calculator.js:214-262 with n32 = 8
+  uint32_t w[19];
+  memcpy(&w[0], "wtns", 4);
+  w[1] = 2;                     // version
+  w[2] = 2;                     // sections
+  w[3] = 1;                     // section 1 id
+  w[4] = 40; w[5] = 0;          // section 1 length (u64) = 8 + n8
+  w[6] = 32;                    // n8
+  memcpy(&w[7], d->prime, 32);
+  w[15] = d->ws;
+  w[16] = 2;                    // section 2 id
+  uint64_t len2 = 32ull * d->ws;
+  w[17] = (uint32_t)len2; w[18] = (uint32_t)(len2 >> 32);
+  memcpy(hdr, w, 76);
+  return B3W_OK;
+}
+
+extern "C" int b3w_input_signal(uint32_t circuit, const char *name, uint32_t *offset, uint32_t *size) {
+  const circuit_def *d = find_def(circuit);
+  if (!d) return B3W_ERR_UNSUPPORTED;
+  if (!name) return fail(B3W_ERR_INVALID, "b3w_input_signal: null argument");
+  for (int i = 0; i < d->n_sig; i++)
+    if (strcmp(d->sig[i].name, name) == 0) {
+      if (offset) *offset = d->sig[i].off;
+      if (size) *size = d->sig[i].size;
+      return B3W_OK;
+    }
+  return fail(B3W_ERR_INVALID, "Signal %s not found", name);
+}
+
+static int launch_witness(b3w_ctx *c, const uint32_t *d_in, uint64_t n, uint8_t *d_out, uint8_t *d_status,
+                          uint32_t *d_pub, cudaStream_t s) {
+  if (n == 0) return B3W_OK;
+  // grid: a multiple of the SM count; 8 CTAs of 8 warps fit per SM (30 KB smem, 256 threads each)
+  uint64_t ctas_needed = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+  uint64_t max_ctas = (uint64_t)c->sm_count * 8;
+  unsigned grid = (unsigned)(ctas_needed < max_ctas ? ctas_needed : max_ctas);
+  k_blake3_comp_witness<<<grid, WARPS_PER_CTA * 32, 0, s>>>(d_in, n, c->d_desc, c->def->ws, d_out, d_status, d_pub);
+  CK(cudaGetLastError());
+  return B3W_OK;
+}
+
+extern "C" int b3w_witness_batch_device(b3w_ctx *c, const uint32_t *d_in, uint64_t n, uint8_t *d_out,
+                                        uint8_t *d_status, uint32_t *d_pub, void *stream) {
+  if (!c || !d_in || !d_out) return fail(B3W_ERR_INVALID, "b3w_witness_batch_device: null argument");
+  if (((uintptr_t)d_out & 31) != 0) return fail(B3W_ERR_INVALID, "d_out must be 32-byte aligned");
+  CK(cudaSetDevice(c->device));
+  return launch_witness(c, d_in, n, d_out, d_status, d_pub, (cudaStream_t)stream);
+}
+
+static int ensure_ring(b3w_ctx *c) {
+  if (c->ring_ready) return B3W_OK;
+  const circuit_def *d = c->def;
+  for (int k = 0; k < 2; k++) {
+    CK(cudaStreamCreateWithFlags(&c->st[k], cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev[k], cudaEventDisableTiming));
+    CK(cudaMalloc(&c->d_ring[k], (size_t)c->chunk * d->ws * 32));
+    CK(cudaMalloc(&c->d_in[k], (size_t)c->chunk * d->n_inputs * 4));
+    CK(cudaMalloc(&c->d_status[k], (size_t)c->chunk));
+    CK(cudaMalloc(&c->d_pub[k], (size_t)c->chunk * d->n_public * 4));
+  }
+  c->ring_ready = true;
+  return B3W_OK;
+}
+
+extern "C" int b3w_witness_batch(b3w_ctx *c, const uint32_t *in, uint64_t n, uint8_t *out, uint8_t *status,
+                                 uint32_t *pub) {
+  if (!c || (!in && n)) return fail(B3W_ERR_INVALID, "b3w_witness_batch: null argument");
+  CK(cudaSetDevice(c->device));
+  int rc = ensure_ring(c);
+  if (rc) { free_ring(c); return rc; }
+  const circuit_def *d = c->def;
+  const size_t wbytes = (size_t)d->ws * 32;
+  // two ring slots: chunk j runs on stream j&1; its D2H overlaps the next chunk's kernel
+  uint64_t done = 0;
+  int k = 0;
+  while (done < n) {
+    uint64_t m = n - done < c->chunk ? n - done : c->chunk;
+    cudaStream_t s = c->st[k];
+    CK(cudaMemcpyAsync(c->d_in[k], in + done * d->n_inputs, (size_t)m * d->n_inputs * 4, cudaMemcpyHostToDevice, s));
+    rc = launch_witness(c, c->d_in[k], m, c->d_ring[k], c->d_status[k], c->d_pub[k], s);
+    if (rc) return rc;
+    if (out) CK(cudaMemcpyAsync(out + done * wbytes, c->d_ring[k], (size_t)m * wbytes, cudaMemcpyDeviceToHost, s));
+    if (status) CK(cudaMemcpyAsync(status + done, c->d_status[k], (size_t)m, cudaMemcpyDeviceToHost, s));
+    if (pub) CK(cudaMemcpyAsync(pub + done * d->n_public, c->d_pub[k], (size_t)m * d->n_public * 4, cudaMemcpyDeviceToHost, s));
+    done += m;
+    k ^= 1;
+    // before reusing slot k (two chunks ago) its stream must have drained
+    if (done < n) CK(cudaStreamSynchronize(c->st[k]));
+  }
+  CK(cudaStreamSynchronize(c->st[0]));
+  CK(cudaStreamSynchronize(c->st[1]));
+  return B3W_OK;
+}
+
+extern "C" int b3w_witness_one(b3w_ctx *c, const uint32_t *in, uint8_t *out) {
+  if (!c || !in || !out) return fail(B3W_ERR_INVALID, "b3w_witness_one: null argument");
+  uint8_t status = 0;
+  int rc = b3w_witness_batch(c, in, 1, out, &status, nullptr);
+  if (rc) return rc;
+  if (status) return fail((int)status, "Assert Failed.");
+  return B3W_OK;
+}
+
+extern "C" int b3w_checksum_device(b3w_ctx *c, const uint8_t *d_wit, uint64_t n, uint64_t *d_sums, void *stream) {
+  if (!c || !d_wit || !d_sums) return fail(B3W_ERR_INVALID, "b3w_checksum_device: null argument");
+  CK(cudaSetDevice(c->device));
+  if (n == 0) return B3W_OK;
+  uint64_t ctas = (n + 7) / 8, cap = (uint64_t)c->sm_count * 8;
+  k_checksum<<<(unsigned)(ctas < cap ? ctas : cap), 256, 0, (cudaStream_t)stream>>>((const uint64_t *)d_wit, n, c->def->ws, d_sums);
+  CK(cudaGetLastError());
+  return B3W_OK;
+}
+
+extern "C" int b3w_calib_fill(b3w_ctx *c, uint8_t *d_buf, uint64_t bytes, void *stream) {
+  if (!c || !d_buf) return fail(B3W_ERR_INVALID, "b3w_calib_fill: null argument");
+  CK(cudaSetDevice(c->device));
+  k_fill<<<c->sm_count * 8, 256, 0, (cudaStream_t)stream>>>(d_buf, bytes / 32);
+  CK(cudaGetLastError());
+  return B3W_OK;
+}
+
+extern "C" void *b3w_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+    fail(B3W_ERR_NOMEM, "cudaHostAlloc(%zu) failed", bytes);
+    return nullptr;
+  }
+  return p;
+}
+extern "C" void b3w_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}

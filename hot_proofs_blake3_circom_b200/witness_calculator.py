@@ -1,0 +1,216 @@
+"""witness_calculator.py -- host-side mirror of the reference's witness_calculator.js, backed by
+libblake3wit.so (CUDA, sm_100a) instead of the circom wasm program.
+
+Reference interface mirrored (paths under /root/reference):
+    builder(code, options)                  blake3_nova_js/witness_calculator.js:1-106
+    WitnessCalculator fields                :108-125  (version, n32, prime, witnessSize, sanityCheck)
+    circom_version()                        :127-129
+    _doCalculateWitness(input, sanityCheck) :131-169  (same checks, same error messages)
+    calculateWitness / calculateBinWitness / calculateWTNSBin   :171-272
+plus the NEW batched entry point calculateWitnessBatch().  Node is not available in this image, so the
+N-API addon of INTEGRATION.md cannot be built here; this module is the executable host layer and the
+parity tests are written against it the way the reference's tests use witness_calculator.js.
+
+Differences that are deliberate and loud:
+  * `code` (the .wasm bytes) only selects the circuit (by sha256); an unknown wasm raises -- there is no
+    WebAssembly engine here to fall back to.
+  * input values must lie in the circuits' honest domain [0, 2^32) after reduction mod p; anything else
+    raises B3WError(B3W_ERR_DOMAIN) instead of being computed in the field.
+  * methods are plain (synchronous) functions.
+"""
+import ctypes as C
+import hashlib
+
+import numpy as np
+
+from . import _lib
+from ._lib import B3WError
+
+# sha256 of the reference's committed witness programs -> (circuit id, name)
+CIRCUITS = {
+    "6faf23ddfd697bbb7e8e922577589c2c06486258968a5a14f96fb5a16091b142": (0, "blake3_compression"),
+    "020bd11f289864c54c7d02cd05723dcf8323e31fa5c77d8700c618232685978e": (1, "blake3_nova (bn128, O2)"),
+    "b982f960ebbfcabe957fe13857ea47adfeee30e18fbe05474e9b982eab187f46": (2, "blake3_nova_pasta (vesta prime, O2)"),
+    "8d6317b72eab34d34e12dfd7bd310dce40f4190768669772f992a9510c441fca": (3, "blake3_nova (bn128, O1, circomkit)"),
+}
+CIRCUIT_IDS = {"blake3_compression": 0, "blake3_nova": 1, "blake3_nova_pasta": 2, "blake3_nova_o1": 3}
+
+
+def circuit_from_wasm(code):
+    h = hashlib.sha256(bytes(code)).hexdigest()
+    if h not in CIRCUITS:
+        raise B3WError(_lib.B3W_ERR_UNSUPPORTED,
+                       "unknown witness program (sha256 %s...): only the reference's BLAKE3 circuits are built in" % h[:16])
+    return CIRCUITS[h][0]
+
+
+def builder(code, options=None, device=-1, chunk=0, lazy=False):
+    """builder(code, options) -> WitnessCalculator   (witness_calculator.js:1).
+    `code`: bytes of one of the reference's .wasm files, or a circuit name / id.
+    lazy=True defers the creation of the GPU context to the first witness call (host-logic tests)."""
+    if isinstance(code, int):
+        cid = code
+    elif isinstance(code, str):
+        cid = CIRCUIT_IDS[code]
+    else:
+        cid = circuit_from_wasm(code)
+    return WitnessCalculator(cid, options or {}, device=device, chunk=chunk, lazy=lazy)
+
+
+def _flat_array(a):
+    """flatArray (witness_calculator.js:303-317)"""
+    res = []
+
+    def fill(x):
+        if isinstance(x, (list, tuple, np.ndarray)):
+            for y in x:
+                fill(y)
+        else:
+            res.append(x)
+    fill(a)
+    return res
+
+
+def _to_bigint(n):
+    """BigInt(n) for the value types JSON / JS callers pass."""
+    if isinstance(n, (bool, np.bool_)):
+        return int(n)
+    if isinstance(n, (int, np.integer)):
+        return int(n)
+    if isinstance(n, str):
+        s = n.strip()
+        return int(s, 0) if s.lower().startswith(("0x", "-0x", "0b", "0o")) else int(s)
+    if isinstance(n, float) and n == int(n):
+        return int(n)
+    raise TypeError("Cannot convert %r to a BigInt" % (n,))
+
+
+class WitnessCalculator:
+    def __init__(self, circuit, sanity_check, device=-1, chunk=0, lazy=False):
+        L = _lib.lib()
+        self._L, self._ctx, self._cfg = L, None, _lib.Config(circuit, device, chunk, 0)
+        info = _lib.Info()
+        _lib.check(L.b3w_circuit_info(circuit, C.byref(info)))
+        if not lazy:
+            self._h                               # instantiate now, like WebAssembly.instantiate in builder()
+        self.instance = self                      # the reference exposes the wasm instance here
+        self.circuit = circuit
+        self.version = info.version[0]
+        self.n32 = info.n32
+        self.prime = int.from_bytes(bytes(info.prime), "little")
+        self.witnessSize = info.witness_size
+        self.nInputs = info.n_inputs
+        self.nPublic = info.n_public
+        self.sanityCheck = sanity_check
+
+    @property
+    def _h(self):
+        """The GPU context (created on first use)."""
+        if self._ctx is None:
+            h = C.c_void_p()
+            _lib.check(self._L.b3w_create(C.byref(self._cfg), C.byref(h)))
+            self._ctx = h
+        return self._ctx
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._L.b3w_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def circom_version(self):
+        return self.version
+
+    # ---- input normalisation: _doCalculateWitness (witness_calculator.js:131-169) ----
+    def _input_signal_size(self, name):
+        off, size = C.c_uint32(), C.c_uint32()
+        rc = self._L.b3w_input_signal(self.circuit, name.encode(), C.byref(off), C.byref(size))
+        if rc != 0:
+            return 0, 0          # the wasm's getInputSignalSize returns 0 for an unknown name
+        return off.value, size.value
+
+    def _row(self, inp):
+        row = np.zeros(self.nInputs, np.uint32)
+        input_counter = 0
+        for k in inp.keys():
+            f_arr = _flat_array(inp[k])
+            off, signal_size = self._input_signal_size(k)
+            if signal_size < 0:
+                raise RuntimeError("Signal %s not found\n" % k)
+            if len(f_arr) < signal_size:
+                raise RuntimeError("Not enough values for input signal %s\n" % k)
+            if len(f_arr) > signal_size:
+                raise RuntimeError("Too many values for input signal %s\n" % k)
+            for i, v in enumerate(f_arr):
+                x = _to_bigint(v) % self.prime        # normalize(): BigInt(n) % prime, made non-negative
+                if x >> 32:
+                    raise B3WError(_lib.B3W_ERR_DOMAIN,
+                                   "input %s[%d] = %d is outside the supported u32 domain" % (k, i, x))
+                row[off + i] = x
+                input_counter += 1
+        if input_counter < self.nInputs:
+            raise RuntimeError("Not all inputs have been set. Only %d out of %d" % (input_counter, self.nInputs))
+        return row
+
+    def _do_calculate(self, inp):
+        row = self._row(inp)
+        out = np.empty(self.witnessSize * 32, np.uint8)
+        rc = self._L.b3w_witness_one(self._h, row.ctypes.data, out.ctypes.data)
+        if rc == _lib.B3W_CIRCOM_ASSERT:
+            raise RuntimeError("Error: Assert Failed.\n")
+        _lib.check(rc)
+        return out
+
+    # ---- the three reference read-outs ----
+    def calculateWitness(self, inp, sanityCheck=0):
+        """-> list of witnessSize Python ints (the reference returns BigInt[])."""
+        b = self._do_calculate(inp).tobytes()
+        return [int.from_bytes(b[32 * i:32 * i + 32], "little") for i in range(self.witnessSize)]
+
+    def calculateBinWitness(self, inp, sanityCheck=0):
+        """-> np.uint8[witnessSize*32], little-endian limbs."""
+        return self._do_calculate(inp)
+
+    def calculateWTNSBin(self, inp, sanityCheck=0):
+        """-> np.uint8[76 + witnessSize*32]: the .wtns file image."""
+        body = self._do_calculate(inp)
+        hdr = np.empty(76, np.uint8)
+        _lib.check(self._L.b3w_wtns_header(self.circuit, hdr.ctypes.data))
+        return np.concatenate([hdr, body])
+
+    # ---- NEW: batched entry point ----
+    def calculateWitnessBatch(self, inputs, want_witness=True, out=None):
+        """inputs: list of input objects (as for calculateWitness) or an (n, nInputs) uint32 array in
+        circuit declaration order.  Returns dict(witness=(n, witnessSize*32) u8 | None, status=u8[n],
+        pub=(n, nPublic) u32)."""
+        if isinstance(inputs, np.ndarray):
+            rows = np.ascontiguousarray(inputs, np.uint32)
+            if rows.ndim != 2 or rows.shape[1] != self.nInputs:
+                raise ValueError("expected an (n, %d) uint32 array" % self.nInputs)
+        else:
+            rows = np.stack([self._row(i) for i in inputs]) if len(inputs) else np.zeros((0, self.nInputs), np.uint32)
+        n = rows.shape[0]
+        if want_witness and out is None:
+            out = np.empty((n, self.witnessSize * 32), np.uint8)
+        status = np.zeros(n, np.uint8)
+        pub = np.zeros((n, self.nPublic), np.uint32)
+        _lib.check(self._L.b3w_witness_batch(self._h, rows.ctypes.data, n,
+                                             out.ctypes.data if want_witness else None,
+                                             status.ctypes.data, pub.ctypes.data))
+        return {"witness": out if want_witness else None, "status": status, "pub": pub}
+
+    # ---- device-pointer plumbing used by bench.py / tests (torch supplies memory and streams) ----
+    def witness_batch_device(self, d_in, n, d_out, d_status=0, d_pub=0, stream=0):
+        _lib.check(self._L.b3w_witness_batch_device(self._h, d_in, n, d_out, d_status or None, d_pub or None,
+                                                    stream or None))
+
+    def checksum_device(self, d_wit, n, d_sums, stream=0):
+        _lib.check(self._L.b3w_checksum_device(self._h, d_wit, n, d_sums, stream or None))
+
+    def calib_fill(self, d_buf, nbytes, stream=0):
+        _lib.check(self._L.b3w_calib_fill(self._h, d_buf, nbytes, stream or None))

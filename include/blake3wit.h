@@ -1,0 +1,113 @@
+/* blake3wit.h -- C ABI of libblake3wit.so: B200-native batched circom witness generation for the
+ * BLAKE3 compression circuit and the blake3_nova / blake3_nova_pasta step circuits.
+ *
+ * This library replaces ONE path of banyancomputer/hot-proofs-blake3-circom: everything that happens
+ * between `WitnessCalculator._doCalculateWitness` and the witness read-out, i.e. the circom-generated
+ * wasm program and its Fr library (reference: blake3_nova_js/witness_calculator.js:131-272 and
+ * build/ ** / *.wasm).  Plain pointers and sizes only; no torch / CUDA types in the signatures (a CUDA
+ * stream is passed as an opaque void*).  All functions return 0 on success, a NEGATIVE library error
+ * (B3W_ERR_*) or a POSITIVE circom runtime code (the `exceptionHandler` codes of
+ * witness_calculator.js:21-39; only 4 = "Assert Failed." can be produced by a witness run).
+ * The library never aborts and never falls back to a CPU implementation: without a usable CUDA device
+ * every compute entry point fails with B3W_ERR_CUDA.
+ */
+#ifndef BLAKE3WIT_H
+#define BLAKE3WIT_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B3W_VERSION 0x000100
+
+#define B3W_OK 0
+#define B3W_ERR_INVALID (-1)     /* bad argument */
+#define B3W_ERR_CUDA (-2)        /* CUDA runtime error or no device; text in b3w_last_error() */
+#define B3W_ERR_NOMEM (-3)
+#define B3W_ERR_DOMAIN (-4)      /* an input is outside the supported (u32) domain */
+#define B3W_ERR_UNSUPPORTED (-5)
+#define B3W_CIRCOM_ASSERT 4      /* "Assert Failed." (witness_calculator.js:29-30) */
+
+/* Circuit variants = the reference's committed witness programs:
+ *   COMPRESSION   build/blake3_compression/blake3_compression_js/blake3_compression.wasm (BN254, O1)
+ *   NOVA_BN_O2    build/blake3_nova_js/blake3_nova.wasm                                  (BN254, O2)
+ *   NOVA_PASTA_O2 build/blake3_nova_pasta_js/blake3_nova_pasta.wasm                      (Pallas scalar, O2)
+ *   NOVA_BN_O1    build/blake3_nova/blake3_nova_js/blake3_nova.wasm (== build/blake3_nova_pasta/...) (BN254, O1) */
+typedef enum {
+  B3W_COMPRESSION = 0,
+  B3W_NOVA_BN_O2 = 1,
+  B3W_NOVA_PASTA_O2 = 2,
+  B3W_NOVA_BN_O1 = 3
+} b3w_circuit;
+
+typedef struct {
+  uint32_t circuit;        /* b3w_circuit */
+  int32_t device;          /* CUDA device ordinal; -1 = current device */
+  uint32_t chunk;          /* instances per internal HBM ring slot for host-buffer batches; 0 = default */
+  uint32_t flags;          /* reserved, must be 0 */
+} b3w_config;
+
+/* What the WitnessCalculator constructor caches (witness_calculator.js:108-125). */
+typedef struct {
+  uint32_t witness_size;   /* getWitnessSize(): slots per witness, slot 0 is the constant 1 */
+  uint32_t n_inputs;       /* getInputSize(): input values, in circuit declaration order */
+  uint32_t n32;            /* getFieldNumLen32() = 8 */
+  uint32_t n_public;       /* values copied to `pub`: 16 (compression out[16]) / 15 (nova z_{i+1}) */
+  uint32_t version[3];     /* circom version the reference artefact was built with: 2,1,6 */
+  uint8_t prime[32];       /* getRawPrime(), little-endian */
+} b3w_info;
+
+typedef struct b3w_ctx b3w_ctx;
+
+int b3w_version(void);
+const char *b3w_last_error(void);                       /* thread-local text of the last failure */
+
+/* replaces builder() + new WitnessCalculator (witness_calculator.js:1-125): one ctx per GPU, not re-entrant */
+int b3w_create(const b3w_config *cfg, b3w_ctx **out);
+void b3w_destroy(b3w_ctx *ctx);
+
+/* Static circuit metadata; these three need no GPU (circuit = b3w_circuit). */
+int b3w_circuit_info(uint32_t circuit, b3w_info *info);
+
+/* the 76-byte .wtns header that calculateWTNSBin writes before the body (witness_calculator.js:214-262) */
+int b3w_wtns_header(uint32_t circuit, uint8_t hdr[76]);
+
+/* Name -> (offset, size) of an input signal inside the u32 input row; replaces getInputSignalSize
+ * (witness_calculator.js:141).  Returns B3W_ERR_INVALID for an unknown name. */
+int b3w_input_signal(uint32_t circuit, const char *name, uint32_t *offset, uint32_t *size);
+
+/* replaces _doCalculateWitness + calculateBinWitness for ONE input (witness_calculator.js:131-205).
+ * in: n_inputs u32 (host).  out: witness_size*32 bytes (host), canonical little-endian Fr256.
+ * Returns 0 or B3W_CIRCOM_ASSERT (out is then untouched beyond what was written). */
+int b3w_witness_one(b3w_ctx *ctx, const uint32_t *in, uint8_t *out);
+
+/* NEW batched entry point, HOST buffers.  in: n rows of n_inputs u32.  out: n*witness_size*32 bytes or
+ * NULL (witnesses are then only streamed through the HBM ring: generate + compact results).
+ * status: n bytes (0 ok, 4 assert) or NULL.  pub: n rows of n_public u32 or NULL.
+ * Host buffers from b3w_host_alloc() are pinned and copy at full PCIe rate. */
+int b3w_witness_batch(b3w_ctx *ctx, const uint32_t *in, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub);
+
+/* NEW batched entry point, DEVICE buffers (same layouts), asynchronous on `stream` (a cudaStream_t, may
+ * be NULL for the default stream).  d_out must hold n*witness_size*32 bytes, 32-byte aligned. */
+int b3w_witness_batch_device(b3w_ctx *ctx, const uint32_t *d_in, uint64_t n, uint8_t *d_out, uint8_t *d_status,
+                             uint32_t *d_pub, void *stream);
+
+/* Per-instance 64-bit checksum of witnesses resident in device memory (reads them back from HBM):
+ *   sum_i = SUM over slots s, limbs j of  (limb64[s][j] + 1) * mix(4*s + j)   (mod 2^64),
+ *   mix(x) = (x + 1) * 0x9E3779B97F4A7C15  (mod 2^64).  d_sums: n u64. */
+int b3w_checksum_device(b3w_ctx *ctx, const uint8_t *d_wit, uint64_t n, uint64_t *d_sums, void *stream);
+
+/* Pure-store calibration kernel (the write roofline of this GPU): fills `bytes` of device memory with
+ * 256-bit streaming stores; asynchronous on `stream`. */
+int b3w_calib_fill(b3w_ctx *ctx, uint8_t *d_buf, uint64_t bytes, void *stream);
+
+/* pinned host memory for batch buffers */
+void *b3w_host_alloc(size_t bytes);
+void b3w_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
