@@ -1,0 +1,86 @@
+"""CPU tests of the drop-in boundary: the C ABI library loads, exports what include/blake3wit.h declares,
+needs no GPU for metadata, and refuses loudly to compute without one."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import hot_proofs_blake3_circom_b200 as pkg
+from hot_proofs_blake3_circom_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "blake3wit.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(b3w_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    L = pkg.lib()
+    syms = declared_symbols()
+    assert len(syms) >= 14
+    for s in syms:
+        assert hasattr(L, s), "libblake3wit.so does not export %s" % s
+    assert set(syms) == set(_lib.EXPORTS)
+    assert L.b3w_version() == 0x000100
+
+
+def test_no_torch_types_in_header():
+    hdr = open(os.path.join(ROOT, "include", "blake3wit.h")).read()
+    assert "torch" not in re.sub(r"/\*.*?\*/", "", hdr, flags=re.S).lower()
+    assert "at::" not in hdr and "c10" not in hdr
+
+
+def test_circuit_info_matches_reference_constants(built):
+    L = pkg.lib()
+    info = _lib.Info()
+    assert L.b3w_circuit_info(0, C.byref(info)) == 0
+    assert (info.witness_size, info.n_inputs, info.n32, info.n_public) == (24093, 28, 8, 16)
+    assert list(info.version) == [2, 1, 6]
+    # test/blake3_hash.test.ts:10-12
+    assert int.from_bytes(bytes(info.prime), "little") == \
+        21888242871839275222246405745257275088548364400416034343698204186575808495617
+    assert L.b3w_circuit_info(99, C.byref(info)) == _lib.B3W_ERR_UNSUPPORTED
+
+
+def test_wtns_header_equals_reference_golden(golden, built):
+    hdr = np.zeros(76, np.uint8)
+    assert pkg.lib().b3w_wtns_header(0, hdr.ctypes.data) == 0
+    assert hdr.tobytes() == golden["wtns"].tobytes()[:76]
+
+
+def test_input_signal_table(built):
+    L = pkg.lib()
+    off, size = C.c_uint32(), C.c_uint32()
+    want = {"h": (0, 8), "m": (8, 16), "t": (24, 2), "b": (26, 1), "d": (27, 1)}
+    for k, v in want.items():
+        assert L.b3w_input_signal(0, k.encode(), C.byref(off), C.byref(size)) == 0
+        assert (off.value, size.value) == v
+    assert L.b3w_input_signal(0, b"nope", C.byref(off), C.byref(size)) == _lib.B3W_ERR_INVALID
+    assert b"nope" in L.b3w_last_error()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_compute_fails_loudly_without_gpu(built):
+    with pytest.raises(pkg.B3WError) as e:
+        pkg.builder("blake3_compression")
+    assert e.value.code == _lib.B3W_ERR_CUDA
+    assert "no CPU path" in str(e.value)
+    wc = pkg.builder("blake3_compression", lazy=True)
+    with pytest.raises(pkg.B3WError):
+        wc.calculateWitness({"h": [0] * 8, "m": [0] * 16, "t": [0, 0], "b": 0, "d": 0})
+
+
+def test_product_does_not_import_oracle():
+    # the product path must never route through oracle/
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "hot_proofs_blake3_circom_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cuh", ".cpp", ".c")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "oracle/" not in src.replace("tools/", ""), f

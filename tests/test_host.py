@@ -1,0 +1,77 @@
+"""CPU tests of the host layer that mirrors witness_calculator.js:131-169 (input handling and errors)."""
+import numpy as np
+import pytest
+
+import hot_proofs_blake3_circom_b200 as pkg
+from hot_proofs_blake3_circom_b200 import _lib
+from hot_proofs_blake3_circom_b200 import inputs as gen
+from oracle import blake3_ref
+
+P = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+
+
+@pytest.fixture(scope="module")
+def wc(built):
+    return pkg.builder("blake3_compression", lazy=True)
+
+
+def good():
+    return {"h": list(blake3_ref.IV), "m": list(range(16)), "t": [0, 0], "b": 64, "d": 0}
+
+
+def test_constructor_fields(wc):
+    assert (wc.version, wc.n32, wc.prime, wc.witnessSize) == (2, 8, P, 24093)
+    assert wc.circom_version() == 2
+
+
+def test_row_layout_and_value_forms(wc):
+    inp = good()
+    inp["m"] = [[str(i) for i in range(8)], [hex(i) for i in range(8, 16)]]     # nested arrays are flattened (:303-317)
+    inp["b"] = "64"
+    inp["t"] = [P, -P]                                                          # reduced mod p (:319-323)
+    inp["d"] = -(P - 3)                                                         # negative -> wrapped
+    row = wc._row(inp)
+    assert list(row) == list(blake3_ref.IV) + list(range(16)) + [0, 0, 64, 3]
+
+
+def test_error_messages_match_reference(wc):
+    inp = good(); inp["m"] = list(range(15))
+    with pytest.raises(RuntimeError, match="Not enough values for input signal m"):
+        wc._row(inp)
+    inp = good(); inp["h"] = list(range(9))
+    with pytest.raises(RuntimeError, match="Too many values for input signal h"):
+        wc._row(inp)
+    inp = good(); inp["bogus"] = 1          # the wasm reports size 0 for unknown names
+    with pytest.raises(RuntimeError, match="Too many values for input signal bogus"):
+        wc._row(inp)
+    inp = good(); del inp["d"]
+    with pytest.raises(RuntimeError, match="Not all inputs have been set. Only 27 out of 28"):
+        wc._row(inp)
+
+
+def test_out_of_domain_is_loud(wc):
+    inp = good(); inp["m"][0] = 2 ** 32
+    with pytest.raises(pkg.B3WError) as e:
+        wc._row(inp)
+    assert e.value.code == _lib.B3W_ERR_DOMAIN
+
+
+def test_wasm_identification():
+    with pytest.raises(pkg.B3WError):
+        pkg.circuit_from_wasm(b"\0asm\x01\0\0\0")
+    assert len(pkg.CIRCUITS) == 4
+
+
+def test_input_generators():
+    a = gen.lcg_compression_inputs(5)
+    lcg = blake3_ref.LCG(6429)
+    for i in range(5):
+        c = blake3_ref.gen_random_chunk(lcg)
+        assert list(a[i]) == c["h"] + c["m"] + c["t"] + [c["b"], c["d"]]
+    assert (gen.lcg_compression_inputs(3, first=2) == a[2:]).all()
+    b = gen.splitmix_compression_inputs(4096)
+    assert (b[:, 26] % 4 == 0).all() and b[:, 26].max() == 64 and b[:, 26].min() == 0
+    assert b[:, 27].max() == 15
+    nz = (np.arange(16)[None, :] >= (b[:, 26] // 4)[:, None])
+    assert not b[:, 8:24][nz].any()
+    assert (gen.splitmix_compression_inputs(10, first=100) == gen.splitmix_compression_inputs(110)[100:]).all()

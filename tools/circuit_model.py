@@ -9,8 +9,8 @@ This is a build-time tool, not the product path and not the oracle.  It re-deriv
           ("W", t)        the 32-bit trace word t
           ("Q", t)        the 64-bit value trace[t] | trace[t+1] << 32
           ("B", t, k)     bit k of trace word t
-          ("F", t)        the 256-bit field element trace[t..t+8)
-          ("N", t)        the field element  p - trace[t]  (0 if trace[t] == 0)      [nova O1 only]
+          ("S", t)        the signed 64-bit integer trace[t] | trace[t+1] << 32, as a field element (x mod p)
+          ("I", t)        the inverse mod p of that signed integer (0 for 0)   [circomlib IsZero.inv, nova only]
 Every template below mirrors one template of the reference; the file:line it follows is cited
 (paths under /root/reference).  The model also carries concrete integer values so that the numbering
 and semantics can be validated signal-by-signal against the reference wasm's memory (tests do this
@@ -452,3 +452,435 @@ class CompressionModel:
         main.run(iv[0:8], iv[8:24], iv[24:26], iv[26], iv[27])
         b.finish()
         self.ok = main.ok
+
+
+# ================================================================================================
+# Nova step circuit  (circuits/blake3_nova.circom, AS BUILT into the committed wasm files: without the two
+# Num2Bits(8) range checks of lines 25-30) + circomlib 2.0.5 templates
+# (not vendored in the reference; semantics per SURVEY.md appendix B, validated against the wasm).
+# ================================================================================================
+# Nova trace words, relative to TR_NOVA.  Emitted to csrc/nova_trace.h by tools/gen_tables.py.
+NV = {}
+_nv_next = [0]
+
+
+def _nv(name, count=1):
+    NV[name] = TR_NOVA + _nv_next[0]
+    _nv_next[0] += count
+    return NV[name]
+
+
+_nv("IN", 32)            # the 32 inputs in declaration order: n_blocks block_count h[8] chunk_idx_low chunk_idx_high
+#                          leaf_depth total_depth depth m[16] b      (circuits/blake3_nova.circom:173-191)
+_nv("V1")                # check_parent.n2b.in  = depth + 256 - (leaf_depth - 1)
+_nv("V2")                # exceed_depth.lt.n2b.in = leaf_depth + 256 - (depth + 1)
+_nv("LDM1")              # leaf_depth - 1
+_nv("DP1")               # depth + 1
+_nv("IS_PARENT")
+_nv("EXCEED")            # exceed_depth.out (0 whenever the witness exists)
+_nv("IS_ROOT")
+_nv("NOT_ROOT")
+_nv("NOT_PARENT")
+_nv("BC_FIRST")          # check_block_counts[0].out
+_nv("BC_LAST")           # check_block_counts[1].out
+_nv("IS_LAST")           # is_last_block = BC_LAST * not_parent (= last_block_flag_set.out)
+_nv("FIRST_SET")         # first_block_flag_set.out
+_nv("URF_TMP")           # use_root_flag_tmp.out
+_nv("URF")               # use_root_flag
+_nv("DLP")               # down_left_path.out
+_nv("CDD")               # check_decr_depth.out
+_nv("DECR")              # decr_depth
+_nv("DEPTH_OUT")
+_nv("PAD0")
+_nv("NEG_DEPTH", 2)      # signed 64: 0 - depth                      (check_root.isz.in)
+_nv("NEG_BC", 2)         # signed 64: 0 - block_count                (check_block_counts[0].isz.in)
+_nv("NBM1", 2)           # signed 64: n_blocks - 1                   (check_block_counts[1].in[1])
+_nv("BC_DIFF", 2)        # signed 64: n_blocks - 1 - block_count     (check_block_counts[1].isz.in)
+_nv("BC_OUT", 2)         # block_count + (1 - is_parent)  (up to 2^32)
+_nv("EQ_OUT", 2)         # bit i = eqs[i].out
+_nv("BAD", 2)            # bit i = bit_at_depth[i]
+_nv("TMPIV", 8)
+_nv("TMP_DOWN", 16)
+_nv("M_IS_PAR", 16)
+_nv("TMP_IS_PAR", 16)
+_nv("EQ_IN1", 128)       # signed 64 x 64: total_depth - i - 2        (eqs[i].in[1])
+_nv("EQ_D", 128)         # signed 64 x 64: total_depth - i - 2 - depth (eqs[i].isz.in)
+NOVA_TRACE_WORDS = TR_NOVA + _nv_next[0]
+
+
+def s64_words(x):
+    """two's complement 64-bit -> (lo, hi) u32"""
+    x &= (1 << 64) - 1
+    return x & M32, x >> 32
+
+
+class NovaBuilder(Builder):
+    def ts64(self, t, x):
+        """Define trace[t], trace[t+1] := signed 64-bit x; returns the field-valued V (kind S)."""
+        lo, hi = s64_words(x)
+        self.tw(t, lo), self.tw(t + 1, hi)
+        return V(x % self.p, ("S", t))
+
+    def inv_of(self, s):
+        """IsZero's inv of an S-kind value: kind I refers to the same signed argument."""
+        assert s.s[0] == "S"
+        return V(pow(s.v, -1, self.p) if s.v else 0, ("I", s.s[1]))
+
+
+class IsZero(Comp):
+    """circomlib comparators.circom IsZero: signals out; in; inv."""
+
+    def __init__(self, b, name):
+        super().__init__(b, name)
+        self.out, self.inp, self.inv = self.sig("out"), self.sig("in"), self.sig("inv")
+
+    def run(self, x, out):
+        """x: S-kind value; out: V for the result word/bit (caller decides where it lives)."""
+        self.S(self.inp, x)
+        self.S(self.inv, self.b.inv_of(x))
+        assert out.v == (1 if x.v == 0 else 0)
+        self.S(self.out, out)
+        return out
+
+
+class IsEqual(Comp):
+    """circomlib IsEqual: out; in[2]; sub isz.   isz.in = in[1] - in[0]."""
+
+    def __init__(self, b, name):
+        super().__init__(b, name)
+        self.out, self.inp = self.sig("out"), self.sig("in", 2)
+        self.subs(isz=lambda b, n: IsZero(b, n))
+
+    def run(self, in0, in1, diff, out):
+        self.S(self.inp[0], in0), self.S(self.inp[1], in1)
+        assert diff.v == (in1.v - in0.v) % self.b.p
+        self.isz.run(diff, out)
+        self.S(self.out, out)
+        return out
+
+
+class Num2Bits(Comp):
+    """circomlib bitify.circom Num2Bits(n): out[n]; in."""
+
+    def __init__(self, b, name, n):
+        super().__init__(b, name)
+        self.n = n
+        self.out, self.inp = self.sig("out", n), self.sig("in")
+
+    def run(self, x):
+        self.S(self.inp, x)
+        bits = []
+        for i in range(self.n):
+            bt = x.bit(i) if i < 64 else const(0)
+            bits.append(bt)
+            self.S(self.out[i], bt)
+        self.ok = x.v == sum(bt.v << i for i, bt in enumerate(bits))
+        return bits
+
+
+class LessThan(Comp):
+    """circomlib LessThan(n): out; in[2]; sub n2b = Num2Bits(n+1).  n2b.in = in[0] + 2^n - in[1]; out = 1 - n2b.out[n]."""
+
+    def __init__(self, b, name, n):
+        super().__init__(b, name)
+        self.n = n
+        self.out, self.inp = self.sig("out"), self.sig("in", 2)
+        self.subs(n2b=lambda b, nm: Num2Bits(b, nm, n + 1))
+
+    def run(self, in0, in1, vword, out):
+        self.S(self.inp[0], in0), self.S(self.inp[1], in1)
+        bits = self.n2b.run(vword)
+        assert out.v == 1 - bits[self.n].v
+        self.S(self.out, out)
+        self.ok = self.n2b.ok
+        return out
+
+
+class GreaterEqThan(Comp):
+    """circomlib GreaterEqThan(n): out; in[2]; sub lt = LessThan(n) with lt.in = (in[1], in[0]+1)."""
+
+    def __init__(self, b, name, n):
+        super().__init__(b, name)
+        self.out, self.inp = self.sig("out"), self.sig("in", 2)
+        self.subs(lt=lambda b, nm: LessThan(b, nm, n))
+
+    def run(self, in0, in1, in0p1, vword, out):
+        self.S(self.inp[0], in0), self.S(self.inp[1], in1)
+        self.lt.run(in1, in0p1, vword, out)
+        self.S(self.out, out)
+        self.ok = self.lt.ok
+        return out
+
+
+class Gate2(Comp):
+    """circomlib gates.circom AND / OR: out; a; b."""
+
+    def __init__(self, b, name):
+        super().__init__(b, name)
+        self.out, self.a, self.bb = self.sig("out"), self.sig("a"), self.sig("b")
+
+    def run(self, a, b, out):
+        self.S(self.a, a), self.S(self.bb, b), self.S(self.out, out)
+        return out
+
+
+class NOT(Comp):
+    """circomlib NOT: out; in.   out = 1 + in - 2*in"""
+
+    def __init__(self, b, name):
+        super().__init__(b, name)
+        self.out, self.inp = self.sig("out"), self.sig("in")
+
+    def run(self, x, out):
+        assert out.v == 1 - x.v
+        self.S(self.inp, x), self.S(self.out, out)
+        return out
+
+
+class CheckDepth(Comp):
+    """Blake3NovaTreePath_CheckDepth -- circuits/blake3_nova.circom:13-45 minus lines 25-30 (as built)."""
+
+    def __init__(self, b, name):
+        super().__init__(b, name)
+        self.is_root, self.is_parent = self.sig("is_root"), self.sig("is_parent")
+        self.depth, self.leaf_depth = self.sig("depth"), self.sig("leaf_depth")
+        self.subs(check_root=lambda b, n: IsEqual(b, n), check_parent=lambda b, n: LessThan(b, n, 8),
+                  exceed_depth=lambda b, n: GreaterEqThan(b, n, 8))
+
+    def run(self, depth, leaf_depth):
+        b = self.b
+        self.S(self.depth, depth), self.S(self.leaf_depth, leaf_depth)
+        is_root = b.tw(NV["IS_ROOT"], 1 if depth.v == 0 else 0)
+        self.check_root.run(depth, const(0), b.ts64(NV["NEG_DEPTH"], -depth.v), is_root)          # :19-23
+        self.S(self.is_root, is_root)
+        v1 = depth.v + 256 - (leaf_depth.v - 1)
+        v2 = leaf_depth.v + 256 - (depth.v + 1)
+        self.ok = 0 <= v1 < 512 and 0 <= v2 < 512
+        if not self.ok:
+            return None, None
+        V1, V2 = b.tw(NV["V1"], v1), b.tw(NV["V2"], v2)
+        is_parent = b.tw(NV["IS_PARENT"], 1 - ((v1 >> 8) & 1))
+        self.check_parent.run(depth, b.tw(NV["LDM1"], leaf_depth.v - 1), V1, is_parent)           # :31-33
+        self.S(self.is_parent, is_parent)                                                        # :38
+        exceed = b.tw(NV["EXCEED"], 1 - ((v2 >> 8) & 1))
+        self.exceed_depth.run(depth, leaf_depth, b.tw(NV["DP1"], depth.v + 1), V2, exceed)        # :41-43
+        self.ok = self.ok and exceed.v == 0                                                      # :44
+        return is_root, is_parent
+
+
+class DownLeftPath(Comp):
+    """Blake3GetDownLeftPath -- circuits/blake3_nova.circom:47-84"""
+
+    def __init__(self, b, name):
+        super().__init__(b, name)
+        self.out = self.sig("out")
+        self.depth, self.leaf_idx = self.sig("depth"), self.sig("leaf_idx")
+        self.is_parent, self.total_depth = self.sig("is_parent"), self.sig("total_depth")
+        self.bit_at_depth = self.sig("bit_at_depth", 65)
+        self.subs(eqs=[lambda b, n: IsEqual(b, n)] * 64, n2b=lambda b, n: Num2Bits(b, n, 65))
+
+    def run(self, depth, leaf_idx, is_parent, total_depth):
+        b = self.b
+        self.S(self.depth, depth), self.S(self.leaf_idx, leaf_idx)
+        self.S(self.is_parent, is_parent), self.S(self.total_depth, total_depth)
+        bits = self.n2b.run(leaf_idx)                                                            # :57-59
+        eq_mask = 0
+        for i in range(64):
+            if total_depth.v - i - 2 == depth.v:
+                eq_mask |= 1 << i
+        eqw = [b.tw(NV["EQ_OUT"], eq_mask & M32), b.tw(NV["EQ_OUT"] + 1, eq_mask >> 32)]
+        acc, bad_mask = 0, 0
+        for i in range(64):
+            acc += (1 - bits[i].v) * ((eq_mask >> i) & 1)                                        # :65, :70
+            assert acc in (0, 1)
+            bad_mask |= acc << i
+        badw = [b.tw(NV["BAD"], bad_mask & M32), b.tw(NV["BAD"] + 1, bad_mask >> 32)]
+        for i in range(64):
+            in1 = b.ts64(NV["EQ_IN1"] + 2 * i, total_depth.v - i - 2)                            # :64, :69
+            d = b.ts64(NV["EQ_D"] + 2 * i, total_depth.v - i - 2 - depth.v)
+            self.eqs[i].run(depth, in1, d, eqw[i >> 5].bit(i & 31))
+            self.S(self.bit_at_depth[i], badw[i >> 5].bit(i & 31))
+        out = b.tw(NV["DLP"], (1 - is_parent.v) + is_parent.v * ((bad_mask >> 63) & 1))           # :79
+        self.S(self.out, out)
+        self.ok = out.v in (0, 1) and self.n2b.ok                                                # :81
+        return out
+
+
+class FinalM(Comp):
+    """Blake3GetFinal_m -- circuits/blake3_nova.circom:86-120.  out_m lives in the compression input words."""
+
+    def __init__(self, b, name):
+        super().__init__(b, name)
+        self.out_m = self.sig("out_m", 16)
+        self.h, self.m = self.sig("h", 8), self.sig("m", 16)
+        self.is_parent, self.depth = self.sig("is_parent"), self.sig("depth")
+        self.total_depth, self.chunk_idx = self.sig("total_depth"), self.sig("chunk_idx")
+        self.m_is_parent, self.tmp_down, self.tmp_is_par = self.sig("m_is_parent", 16), self.sig("tmp_down", 16), self.sig("tmp_is_par", 16)
+        self.subs(down_left_path=lambda b, n: DownLeftPath(b, n))
+
+    def run(self, h, m, is_parent, depth, total_depth, chunk_idx):
+        b = self.b
+        for i in range(8):
+            self.S(self.h[i], h[i])
+        for i in range(16):
+            self.S(self.m[i], m[i])
+        self.S(self.is_parent, is_parent), self.S(self.depth, depth)
+        self.S(self.total_depth, total_depth), self.S(self.chunk_idx, chunk_idx)
+        dlp = self.down_left_path.run(depth, chunk_idx, is_parent, total_depth)                  # :97-101
+        out = []
+        for i in range(16):
+            if i < 8:
+                td = h[i].v * dlp.v                                                              # :109
+                mp = m[i].v * (1 - dlp.v) + td                                                   # :111
+            else:
+                td = h[i - 8].v * (1 - dlp.v)                                                    # :113
+                mp = m[i - 8].v * dlp.v + td                                                     # :114
+            tp = mp * is_parent.v                                                                # :116
+            om = m[i].v * (1 - is_parent.v) + tp                                                 # :117
+            self.S(self.tmp_down[i], b.tw(NV["TMP_DOWN"] + i, td))
+            self.S(self.m_is_parent[i], b.tw(NV["M_IS_PAR"] + i, mp))
+            self.S(self.tmp_is_par[i], b.tw(NV["TMP_IS_PAR"] + i, tp))
+            o = b.tw(TR_IN + 8 + i, om)
+            self.S(self.out_m[i], o)
+            out.append(o)
+        self.ok = self.down_left_path.ok
+        return out
+
+
+class GetFlag(Comp):
+    """Blake3GetFlag(D_FLAGS = 0) -- circuits/blake3_nova.circom:122-167"""
+
+    def __init__(self, b, name):
+        super().__init__(b, name)
+        self.out, self.is_last_block = self.sig("out"), self.sig("is_last_block")
+        self.is_parent, self.is_root = self.sig("is_parent"), self.sig("is_root")
+        self.block_count, self.n_blocks = self.sig("block_count"), self.sig("n_blocks")
+        self.use_root_flag = self.sig("use_root_flag")
+        self.subs(not_root=lambda b, n: NOT(b, n), not_parent=lambda b, n: NOT(b, n),
+                  check_block_counts=[lambda b, n: IsEqual(b, n)] * 2,
+                  first_block_flag_set=lambda b, n: Gate2(b, n), last_block_flag_set=lambda b, n: Gate2(b, n),
+                  use_root_flag_tmp=lambda b, n: Gate2(b, n))
+
+    def run(self, is_parent, is_root, block_count, n_blocks):
+        b = self.b
+        self.S(self.is_parent, is_parent), self.S(self.is_root, is_root)
+        self.S(self.block_count, block_count), self.S(self.n_blocks, n_blocks)
+        self.not_root.run(is_root, b.tw(NV["NOT_ROOT"], 1 - is_root.v))                           # :136
+        not_parent = self.not_parent.run(is_parent, b.tw(NV["NOT_PARENT"], 1 - is_parent.v))      # :137
+        first = b.tw(NV["BC_FIRST"], 1 if block_count.v == 0 else 0)
+        self.check_block_counts[0].run(block_count, const(0), b.ts64(NV["NEG_BC"], -block_count.v), first)     # :141-142
+        last = b.tw(NV["BC_LAST"], 1 if block_count.v == n_blocks.v - 1 else 0)
+        self.check_block_counts[1].run(block_count, b.ts64(NV["NBM1"], n_blocks.v - 1),
+                                       b.ts64(NV["BC_DIFF"], n_blocks.v - 1 - block_count.v), last)           # :144-145
+        is_last = b.tw(NV["IS_LAST"], last.v * not_parent.v)                                      # :148
+        self.S(self.is_last_block, is_last)
+        fs = self.first_block_flag_set.run(first, not_parent, b.tw(NV["FIRST_SET"], first.v * not_parent.v))   # :151
+        ls = self.last_block_flag_set.run(last, not_parent, is_last)                              # :152
+        tmp = self.use_root_flag_tmp.run(is_parent, last, b.tw(NV["URF_TMP"], is_parent.v + last.v - is_parent.v * last.v))   # :157
+        urf = b.tw(NV["URF"], tmp.v * is_root.v)                                                  # :158
+        self.S(self.use_root_flag, urf)
+        out = b.tw(TR_IN + 27, fs.v + 2 * ls.v + 8 * urf.v + 4 * is_parent.v)                     # :161-165
+        self.S(self.out, out)
+        return out, is_last
+
+
+class Blake3Nova(Comp):
+    """Blake3Nova(0) -- circuits/blake3_nova.circom:169-267"""
+
+    def __init__(self, b, name):
+        super().__init__(b, name)
+        s = self.sig
+        self.n_blocks_out, self.block_count_out, self.h_out = s("n_blocks_out"), s("block_count_out"), s("h_out", 8)
+        self.total_depth_out, self.depth_out = s("total_depth_out"), s("depth_out")
+        self.chunk_idx_low_out, self.chunk_idx_high_out, self.leaf_depth_out = s("chunk_idx_low_out"), s("chunk_idx_high_out"), s("leaf_depth_out")
+        self.n_blocks, self.block_count, self.h = s("n_blocks"), s("block_count"), s("h", 8)
+        self.chunk_idx_low, self.chunk_idx_high = s("chunk_idx_low"), s("chunk_idx_high")
+        self.leaf_depth, self.total_depth, self.depth = s("leaf_depth"), s("total_depth"), s("depth")
+        self.m, self.bb = s("m", 16), s("b")
+        self.tmpIV, self.h_compression, self.decr_depth = s("tmpIV", 8), s("h_compression", 8), s("decr_depth")
+        self.subs(blake3Compression=lambda b, n: Blake3Compression(b, n), check_decr_depth=lambda b, n: Gate2(b, n),
+                  check_depth=lambda b, n: CheckDepth(b, n), comp_d=lambda b, n: GetFlag(b, n),
+                  final_m=lambda b, n: FinalM(b, n), iv=lambda b, n: IVc(b, n))
+
+    def run(self, w):
+        """w: the 32 input words as V (trace words NV_IN..)."""
+        b = self.b
+        n_blocks, block_count, h = w[0], w[1], w[2:10]
+        low, high, leaf_depth, total_depth, depth, m, bb = w[10], w[11], w[12], w[13], w[14], w[15:31], w[31]
+        for sidx, val in ((self.n_blocks, n_blocks), (self.block_count, block_count), (self.chunk_idx_low, low),
+                          (self.chunk_idx_high, high), (self.leaf_depth, leaf_depth), (self.total_depth, total_depth),
+                          (self.depth, depth), (self.bb, bb)):
+            self.S(sidx, val)
+        for i in range(8):
+            self.S(self.h[i], h[i])
+        for i in range(16):
+            self.S(self.m[i], m[i])
+        is_root, is_parent = self.check_depth.run(depth, leaf_depth)                              # :205-207
+        self.ok = self.check_depth.ok
+        if not self.ok:
+            return
+        d, is_last = self.comp_d.run(is_parent, is_root, block_count, n_blocks)                   # :210-214
+        iv = self.iv.run()
+        chunk_idx = V(low.v + (high.v << 32), ("Q", NV["IN"] + 10))                               # :227
+        out_m = self.final_m.run(h, m, is_parent, depth, total_depth, chunk_idx)                  # :222-227
+        hc = []
+        for i in range(8):
+            tiv = b.tw(NV["TMPIV"] + i, IV[i] * is_parent.v)                                      # :231
+            self.S(self.tmpIV[i], tiv)
+            x = b.tw(TR_IN + i, h[i].v * (1 - is_parent.v) + tiv.v)                               # :232
+            self.S(self.h_compression[i], x)
+            hc.append(x)
+        t1 = b.tw(TR_IN + 25, high.v * (1 - is_parent.v))                                         # :244
+        t0 = b.tw(TR_IN + 24, low.v * (1 - is_parent.v))                                          # :245
+        bw = b.tw(TR_IN + 26, bb.v)
+        out = self.blake3Compression.run(hc, out_m, [t0, t1], bw, d)                              # :235-245
+        for i in range(8):
+            self.S(self.h_out[i], out[i])                                                        # :248
+        bco = block_count.v + (1 - is_parent.v)                                                  # :251
+        lo, hi = s64_words(bco)
+        b.tw(NV["BC_OUT"], lo), b.tw(NV["BC_OUT"] + 1, hi)
+        self.S(self.block_count_out, V(bco, ("Q", NV["BC_OUT"])))
+        self.S(self.n_blocks_out, n_blocks)                                                      # :252
+        cdd = self.check_decr_depth.run(is_last, is_parent, b.tw(NV["CDD"], is_last.v + is_parent.v - is_last.v * is_parent.v))   # :254-256
+        decr = b.tw(NV["DECR"], cdd.v * (1 - is_root.v))                                          # :258
+        self.S(self.decr_depth, decr)
+        self.S(self.depth_out, b.tw(NV["DEPTH_OUT"], depth.v - decr.v))                           # :262
+        self.S(self.total_depth_out, total_depth), self.S(self.chunk_idx_low_out, low)           # :263-265
+        self.S(self.chunk_idx_high_out, high), self.S(self.leaf_depth_out, leaf_depth)
+        self.ok = (self.ok and self.final_m.ok and self.blake3Compression.ok and decr.v in (0, 1))
+
+
+class NovaModel:
+    """main = Blake3Nova(0)  (circuits/main/blake3_nova.circom:6)."""
+    n_inputs = 32
+
+    def __init__(self, inputs, prime=BN254_R, o1=False):
+        assert len(inputs) == 32
+        b = self.b = NovaBuilder(prime)
+        b.tw(TR_ZERO, 0), b.tw(TR_ONE, 1)
+        w = [b.tw(NV["IN"] + i, x) for i, x in enumerate(inputs)]
+        main = self.main = Blake3Nova(b, "main")
+        main.run(w)
+        b.finish()
+        self.ok = main.ok
+
+
+def random_nova_inputs(rng, edge=0):
+    """Step inputs covering leaf / first / last / parent / root cases."""
+    r32 = lambda: rng.getrandbits(32)
+    leaf_depth = rng.randrange(1, 65)
+    total_depth = leaf_depth if rng.random() < 0.8 else rng.randrange(1, 65)
+    depth = rng.randrange(0, leaf_depth)
+    if edge == 1:
+        leaf_depth = total_depth = 1
+        depth = 0
+    elif edge == 2:
+        leaf_depth = total_depth = 64
+        depth = 63
+    n_blocks = rng.randrange(1, 17)
+    block_count = rng.randrange(0, n_blocks) if rng.random() < 0.9 else rng.randrange(0, 17)
+    if rng.random() < 0.3:
+        block_count = n_blocks - 1
+    b = rng.choice([0, 1, 4, 63, 64, rng.randrange(0, 65)])
+    return ([n_blocks, block_count] + [r32() for _ in range(8)] + [r32(), r32() if rng.random() < 0.5 else 0] +
+            [leaf_depth, total_depth, depth] + [r32() for _ in range(16)] + [b])

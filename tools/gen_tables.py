@@ -15,8 +15,8 @@ Descriptor (u32):  bits 0..15 trace index | bits 16..20 bit index | bits 24..26 
    kind 0 BIT   value = (trace[t] >> k) & 1
    kind 1 W32   value = trace[t]
    kind 2 W64   value = trace[t] | trace[t+1] << 32
-   kind 3 FR    value = 256-bit trace[t..t+8)
-   kind 4 NEG   value = trace[t] ? p - trace[t] : 0
+   kind 3 S64   value = (int64)(trace[t] | trace[t+1] << 32) mod p          (negative -> p - |x|)
+   kind 4 INV   value = inverse mod p of that signed value (0 for 0)        (circomlib IsZero.inv)
 Run-length record {desc0, count, delta}: slot j of the run has descriptor desc0 + j*delta.
 
 Usage: python tools/gen_tables.py [--check-only] [--trials N]
@@ -35,7 +35,7 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 import circuit_model as cm  # noqa: E402
 
-KIND = {"B": 0, "W": 1, "Q": 2, "F": 3, "N": 4}
+KIND = {"B": 0, "W": 1, "Q": 2, "S": 3, "I": 4}
 W2S_OFFSET = {"compression": 6244, "nova_bn_o2": 6260, "nova_pasta_o2": 6260, "nova_bn_o1": 6260}
 
 
@@ -79,10 +79,10 @@ def expand(trace, descs, prime):
             out.append(trace[t])
         elif kind == 2:
             out.append(trace[t] | (trace[t + 1] << 32))
-        elif kind == 3:
-            out.append(sum(trace[t + j] << (32 * j) for j in range(8)))
-        elif kind == 4:
-            out.append((prime - trace[t]) % prime)
+        elif kind in (3, 4):
+            x = trace[t] | (trace[t + 1] << 32)
+            x = x - (1 << 64) if x >> 63 else x
+            out.append(x % prime if kind == 3 else (pow(x % prime, -1, prime) if x else 0))
     return out
 
 
@@ -225,7 +225,14 @@ def emit(results, check_only):
         orc.append(line)
         orc.append("};")
         orc.append("")
-    outs = [(os.path.join(ROOT, "hot_proofs_blake3_circom_b200", "csrc", "slot_tables.h"), "\n".join(prod) + "\n"),
+    nv = ["/* GENERATED by tools/gen_tables.py from tools/circuit_model.py -- do not edit.",
+          " * Trace indices (u32 words) of the nova step circuit's values; see circuit_model.py for their meaning. */",
+          "#pragma once"]
+    for k, v in cm.NV.items():
+        nv.append("#define NV_%s %du" % (k, v))
+    nv.append("#define NOVA_TRACE_WORDS %du" % cm.NOVA_TRACE_WORDS)
+    outs = [(os.path.join(ROOT, "hot_proofs_blake3_circom_b200", "csrc", "nova_trace.h"), "\n".join(nv) + "\n"),
+            (os.path.join(ROOT, "hot_proofs_blake3_circom_b200", "csrc", "slot_tables.h"), "\n".join(prod) + "\n"),
             (os.path.join(ROOT, "oracle", "w2s_tables.h"), "\n".join(orc) + "\n")]
     for path, text in outs:
         if check_only:
