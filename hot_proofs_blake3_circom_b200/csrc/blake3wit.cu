@@ -20,6 +20,8 @@
 #include "../../include/blake3wit.h"
 #include "trace_layout.h"
 #include "slot_tables.h"
+#include "nova_trace.h"
+#include "fr.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // error plumbing
@@ -121,32 +123,114 @@ __device__ __forceinline__ void compression_trace(uint32_t *trace, int lane) {
   }
 }
 
+// Phase 1 for the nova step circuit Blake3Nova(0) (circuits/blake3_nova.circom:169-267, as built: without
+// the Num2Bits(8) range checks of :25-30).  trace[NV_IN..NV_IN+32) holds the 32 inputs.  Computes every
+// nova-level value (trace indices: nova_trace.h, generated from tools/circuit_model.py) and the inputs of
+// the embedded compression (TR_IN..).  Returns false when a constraint fails ("Assert Failed.").
+__device__ __forceinline__ bool nova_trace(uint32_t *trace, int lane) {
+  const uint32_t *in = trace + NV_IN;
+  const uint32_t n_blocks = in[0], block_count = in[1], low = in[10], high = in[11];
+  const uint32_t leaf_depth = in[12], total_depth = in[13], depth = in[14], bb = in[31];
+  // Blake3NovaTreePath_CheckDepth (:13-45)
+  const int64_t v1 = (int64_t)depth + 256 - ((int64_t)leaf_depth - 1);      // check_parent = LessThan(8)(depth, leaf_depth-1)
+  const int64_t v2 = (int64_t)leaf_depth + 256 - ((int64_t)depth + 1);      // exceed_depth = GreaterEqThan(8)(depth, leaf_depth)
+  // Num2Bits(9) recomposition must hold for both, and exceed_depth.out === 0 (:44)
+  if (v1 < 0 || v1 >= 512 || v2 < 0 || v2 >= 512 || ((v2 >> 8) & 1) == 0) return false;
+  const uint32_t is_parent = 1u - (uint32_t)((v1 >> 8) & 1);
+  const uint32_t is_root = depth == 0;
+  // Blake3GetFlag (:122-167)
+  const uint32_t not_root = 1u - is_root, not_parent = 1u - is_parent;
+  const uint32_t first = block_count == 0;
+  const uint32_t last = (int64_t)block_count == (int64_t)n_blocks - 1;
+  const uint32_t is_last = last & not_parent, first_set = first & not_parent;
+  const uint32_t urf_tmp = is_parent | last, urf = urf_tmp & is_root;
+  const uint32_t dflags = first_set + 2u * is_last + 8u * urf + 4u * is_parent;
+  // Blake3GetDownLeftPath (:47-84): eqs[i] = IsEqual(depth, total_depth - i - 2), i = lane and lane + 32
+  const int64_t in1a = (int64_t)total_depth - lane - 2, in1b = in1a - 32;
+  const int64_t da = in1a - depth, db = in1b - depth;
+  uint2 *eq_in1 = reinterpret_cast<uint2 *>(trace + NV_EQ_IN1), *eq_d = reinterpret_cast<uint2 *>(trace + NV_EQ_D);
+  eq_in1[lane] = make_uint2((uint32_t)in1a, (uint32_t)((uint64_t)in1a >> 32));
+  eq_in1[lane + 32] = make_uint2((uint32_t)in1b, (uint32_t)((uint64_t)in1b >> 32));
+  eq_d[lane] = make_uint2((uint32_t)da, (uint32_t)((uint64_t)da >> 32));
+  eq_d[lane + 32] = make_uint2((uint32_t)db, (uint32_t)((uint64_t)db >> 32));
+  const uint32_t eq_lo = __ballot_sync(0xffffffffu, da == 0), eq_hi = __ballot_sync(0xffffffffu, db == 0);
+  // bit_at_depth[i] = sum_{j<=i} (1 - n2b.out[j]) * eqs[j].out: at most one term is non-zero  (:65,:70)
+  const uint64_t mask = (((uint64_t)eq_hi << 32) | eq_lo) & ~(((uint64_t)high << 32) | low);
+  const uint64_t bad = mask ? ~((mask & (0 - mask)) - 1) : 0;
+  const uint32_t dlp = not_parent + is_parent * (uint32_t)(bad >> 63);      // out (:79); boolean by construction (:81)
+  // Blake3GetFinal_m (:86-120)
+  if (lane < 16) {
+    const uint32_t hw = in[2 + (lane & 7)], mw = in[15 + lane], mo = in[15 + (lane & 7)];
+    const uint32_t td = lane < 8 ? hw * dlp : hw * (1u - dlp);
+    const uint32_t mp = (lane < 8 ? mw * (1u - dlp) : mo * dlp) + td;
+    const uint32_t tp = mp * is_parent;
+    trace[NV_TMP_DOWN + lane] = td;
+    trace[NV_M_IS_PAR + lane] = mp;
+    trace[NV_TMP_IS_PAR + lane] = tp;
+    trace[TR_IN + 8 + lane] = mw * not_parent + tp;                          // out_m -> compression m
+  }
+  if (lane < 8) {                                                           // :229-233
+    const uint32_t IVc[8] = {0x6A09E667u, 0xBB67AE85u, 0x3C6EF372u, 0xA54FF53Au, 0x510E527Fu, 0x9B05688Cu, 0x1F83D9ABu, 0x5BE0CD19u};
+    uint32_t ivw = IVc[0];
+#pragma unroll
+    for (int j = 1; j < 8; j++) ivw = lane == j ? IVc[j] : ivw;
+    const uint32_t tiv = ivw * is_parent;
+    trace[NV_TMPIV + lane] = tiv;
+    trace[TR_IN + lane] = in[2 + lane] * not_parent + tiv;                   // h_compression
+  }
+  if (lane == 0) {
+    const uint32_t cdd = is_last | is_parent, decr = cdd & not_root;        // :254-258
+    const int64_t neg_depth = -(int64_t)depth, neg_bc = -(int64_t)block_count;
+    const int64_t nbm1 = (int64_t)n_blocks - 1, bc_diff = nbm1 - block_count;
+    const uint64_t bc_out = (uint64_t)block_count + not_parent;             // :251
+    trace[NV_V1] = (uint32_t)v1; trace[NV_V2] = (uint32_t)v2;
+    trace[NV_LDM1] = leaf_depth - 1u; trace[NV_DP1] = depth + 1u;
+    trace[NV_IS_PARENT] = is_parent; trace[NV_EXCEED] = 0u; trace[NV_IS_ROOT] = is_root;
+    trace[NV_NOT_ROOT] = not_root; trace[NV_NOT_PARENT] = not_parent;
+    trace[NV_BC_FIRST] = first; trace[NV_BC_LAST] = last; trace[NV_IS_LAST] = is_last; trace[NV_FIRST_SET] = first_set;
+    trace[NV_URF_TMP] = urf_tmp; trace[NV_URF] = urf; trace[NV_DLP] = dlp;
+    trace[NV_CDD] = cdd; trace[NV_DECR] = decr; trace[NV_DEPTH_OUT] = depth - decr;   // :262
+    trace[NV_NEG_DEPTH] = (uint32_t)neg_depth; trace[NV_NEG_DEPTH + 1] = (uint32_t)((uint64_t)neg_depth >> 32);
+    trace[NV_NEG_BC] = (uint32_t)neg_bc; trace[NV_NEG_BC + 1] = (uint32_t)((uint64_t)neg_bc >> 32);
+    trace[NV_NBM1] = (uint32_t)nbm1; trace[NV_NBM1 + 1] = (uint32_t)((uint64_t)nbm1 >> 32);
+    trace[NV_BC_DIFF] = (uint32_t)bc_diff; trace[NV_BC_DIFF + 1] = (uint32_t)((uint64_t)bc_diff >> 32);
+    trace[NV_BC_OUT] = (uint32_t)bc_out; trace[NV_BC_OUT + 1] = (uint32_t)(bc_out >> 32);
+    trace[NV_EQ_OUT] = eq_lo; trace[NV_EQ_OUT + 1] = eq_hi;
+    trace[NV_BAD] = (uint32_t)bad; trace[NV_BAD + 1] = (uint32_t)(bad >> 32);
+    trace[TR_IN + 24] = low * not_parent;                                   // t[0] (:245)
+    trace[TR_IN + 25] = high * not_parent;                                  // t[1] (:244)
+    trace[TR_IN + 26] = bb;
+    trace[TR_IN + 27] = dflags;                                             // comp_d.out (:161-165)
+  }
+  return true;
+}
+
+// Slow path of phase 2 (nova only): a slot that holds a true field element.  Kept out of line so that the hot
+// loop keeps its small register footprint.
+__device__ __noinline__ void store_field_slot(uint8_t *p, uint32_t kind, uint32_t lo, uint32_t hi,
+                                              const field_consts *__restrict__ F) {
+  const int64_t x = (int64_t)(((uint64_t)hi << 32) | lo);
+  fr_t v;
+  if (kind == DK_S64) v = fr_from_s64(x, F->p);
+  else v = fr_inv_s64(x, *F);
+  st_slot(p, v.l[0], v.l[1], v.l[2], v.l[3], v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+
 // Phase 2: expand the trace into witness slots [0, ws) at `dst` (32 B per slot).
+// kinds BIT / W32 / W64 are the hot path (single 256-bit store, upper 6 words from RZ); S64 / INV (nova only,
+// 67 .. 260 slots per witness) materialise a full field element.
 template <bool HAS_FIELD>
 __device__ __forceinline__ void expand_slots(const uint32_t *trace, const uint32_t *__restrict__ desc, uint32_t ws,
-                                             uint8_t *dst, int lane, const uint32_t *prime) {
+                                             uint8_t *dst, int lane, const field_consts *__restrict__ F) {
 #pragma unroll 4
   for (uint32_t s = lane; s < ws; s += 32) {
     const uint32_t dsc = __ldg(desc + s);
     const uint32_t t = dsc & 0xFFFFu, k = (dsc >> 16) & 31u, kind = dsc >> 24;
     const uint32_t w = trace[t];
     uint32_t lo = kind == DK_BIT ? ((w >> k) & 1u) : w;
-    uint32_t hi = kind == DK_W64 ? trace[t + 1] : 0u;
-    if (HAS_FIELD && kind >= DK_FR) {
-      uint32_t v[8];
-      if (kind == DK_FR) {
-#pragma unroll
-        for (int j = 0; j < 8; j++) v[j] = trace[t + j];
-      } else {  // DK_NEG: p - w (0 stays 0)
-        uint32_t borrow = 0;
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-          uint64_t x = (uint64_t)prime[j] - (j == 0 ? w : 0u) - borrow;
-          v[j] = w ? (uint32_t)x : 0u;
-          borrow = (uint32_t)(x >> 63);
-        }
-      }
-      st_slot(dst + (size_t)s * 32, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+    uint32_t hi = kind >= DK_W64 ? trace[t + 1] : 0u;
+    if (HAS_FIELD && kind >= DK_S64) {
+      store_field_slot(dst + (size_t)s * 32, kind, w, hi, F);
     } else {
       st_slot(dst + (size_t)s * 32, lo, hi, 0u, 0u, 0u, 0u, 0u, 0u);
     }
@@ -154,7 +238,10 @@ __device__ __forceinline__ void expand_slots(const uint32_t *trace, const uint32
 }
 
 #define WARPS_PER_CTA 8
-#define TRACE_STRIDE 960   // u32 words per warp (>= 944, 16-byte multiple)
+#define TRACE_STRIDE 960          // u32 words per warp, compression (>= 944, 16-byte multiple)
+#define NOVA_TRACE_STRIDE 1344    // u32 words per warp, nova (>= NOVA_TRACE_WORDS)
+static_assert(NOVA_TRACE_WORDS <= NOVA_TRACE_STRIDE, "nova trace does not fit its stride");
+#define NOVA_SMEM (WARPS_PER_CTA * NOVA_TRACE_STRIDE * 4)
 
 // k_blake3_comp_witness: one warp per instance, grid-stride over instances.
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
@@ -174,6 +261,47 @@ k_blake3_comp_witness(const uint32_t *__restrict__ in, uint64_t n, const uint32_
     if (pub && lane < 16) pub[i * 16 + lane] = trace[TR_OUT + lane];
     if (status && lane == 0) status[i] = 0;   // u32 inputs can never violate a constraint of this circuit
     expand_slots<false>(trace, desc, ws, out + i * (uint64_t)ws * 32, lane, nullptr);
+  }
+}
+
+// k_blake3_nova_witness: the nova step circuit (all three committed builds share it; they differ in the
+// slot table and the prime).  pub = z_{i+1} = the 15 outputs (low 32 bits each).
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+k_blake3_nova_witness(const uint32_t *__restrict__ in, uint64_t n, const uint32_t *__restrict__ desc, uint32_t ws,
+                      const field_consts *__restrict__ F, uint8_t *__restrict__ out, uint8_t *__restrict__ status,
+                      uint32_t *__restrict__ pub) {
+  extern __shared__ __align__(16) uint32_t s_dyn[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  uint32_t *trace = s_dyn + wib * NOVA_TRACE_STRIDE;
+  const uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
+  if (lane == 0) { trace[TR_ZERO] = 0u; trace[TR_ONE] = 1u; }
+  for (uint64_t i = (uint64_t)blockIdx.x * WARPS_PER_CTA + wib; i < n; i += nwarps) {
+    __syncwarp();
+    trace[NV_IN + lane] = __ldg(in + i * 32 + lane);
+    __syncwarp();
+    const bool ok = nova_trace(trace, lane);
+    if (status && lane == 0) status[i] = ok ? 0 : B3W_CIRCOM_ASSERT;
+    if (!ok) {                                  // the reference throws "Assert Failed.": no witness exists
+      if (pub && lane < 15) pub[i * 15 + lane] = 0u;
+      continue;
+    }
+    __syncwarp();
+    compression_trace(trace, lane);
+    __syncwarp();
+    if (pub && lane < 15) {
+      // n_blocks_out, block_count_out, h_out[8], total_depth_out, depth_out, chunk_idx_low/high_out, leaf_depth_out (:195-202)
+      uint32_t v;
+      if (lane == 0) v = trace[NV_IN + 0];
+      else if (lane == 1) v = trace[NV_BC_OUT];
+      else if (lane < 10) v = trace[TR_OUT + lane - 2];
+      else if (lane == 10) v = trace[NV_IN + 13];
+      else if (lane == 11) v = trace[NV_DEPTH_OUT];
+      else if (lane == 12) v = trace[NV_IN + 10];
+      else if (lane == 13) v = trace[NV_IN + 11];
+      else v = trace[NV_IN + 12];
+      pub[i * 15 + lane] = v;
+    }
+    expand_slots<true>(trace, desc, ws, out + i * (uint64_t)ws * 32, lane, F);
   }
 }
 
@@ -206,6 +334,7 @@ __global__ void __launch_bounds__(256) k_fill(uint8_t *buf, uint64_t nslots) {
 // ------------------------------------------------------------------------------------------------
 struct circuit_def {
   const char *name;
+  bool nova;
   uint32_t ws, n_inputs, n_public, trace_words;
   const b3w_seg *segs;
   size_t n_segs;
@@ -218,10 +347,20 @@ static const uint8_t PRIME_BN254[32] = {0x01, 0x00, 0x00, 0xf0, 0x93, 0xf5, 0xe1
                                         0x79, 0x48, 0xe8, 0x33, 0x28, 0x5d, 0x58, 0x81, 0x81, 0xb6, 0x45,
                                         0x50, 0xb8, 0x29, 0xa0, 0x31, 0xe1, 0x72, 0x4e, 0x64, 0x30};
 
+static const uint8_t PRIME_PALLAS_SCALAR[32] = {0x01, 0x00, 0x00, 0x00, 0x21, 0xeb, 0x46, 0x8c, 0xdd, 0xa8, 0x94, 0x09, 0xfc, 0x98, 0x46, 0x22, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x40};
+
+#define NOVA_SIGS                                                                                              \
+  10, {{"n_blocks", 0, 1}, {"block_count", 1, 1}, {"h", 2, 8}, {"chunk_idx_low", 10, 1}, {"chunk_idx_high", 11, 1}, \
+       {"leaf_depth", 12, 1}, {"total_depth", 13, 1}, {"depth", 14, 1}, {"m", 15, 16}, {"b", 31, 1}}
+#define SEGS(v) B3W_SEGS_##v, sizeof(B3W_SEGS_##v) / sizeof(b3w_seg)
+
 static const circuit_def CIRCUITS[] = {
-    {"blake3_compression", B3W_WS_COMPRESSION, 28, 16, B3W_TRACE_WORDS_COMPRESSION, B3W_SEGS_COMPRESSION,
-     sizeof(B3W_SEGS_COMPRESSION) / sizeof(b3w_seg), PRIME_BN254, 5,
+    {"blake3_compression", false, B3W_WS_COMPRESSION, 28, 16, B3W_TRACE_WORDS_COMPRESSION, SEGS(COMPRESSION), PRIME_BN254, 5,
      {{"h", 0, 8}, {"m", 8, 16}, {"t", 24, 2}, {"b", 26, 1}, {"d", 27, 1}}},
+    {"blake3_nova (bn128, O2)", true, B3W_WS_NOVA_BN_O2, 32, 15, B3W_TRACE_WORDS_NOVA_BN_O2, SEGS(NOVA_BN_O2), PRIME_BN254, NOVA_SIGS},
+    {"blake3_nova_pasta (vesta prime = Pallas scalar, O2)", true, B3W_WS_NOVA_PASTA_O2, 32, 15, B3W_TRACE_WORDS_NOVA_PASTA_O2,
+     SEGS(NOVA_PASTA_O2), PRIME_PALLAS_SCALAR, NOVA_SIGS},
+    {"blake3_nova (bn128, O1)", true, B3W_WS_NOVA_BN_O1, 32, 15, B3W_TRACE_WORDS_NOVA_BN_O1, SEGS(NOVA_BN_O1), PRIME_BN254, NOVA_SIGS},
 };
 static const int N_CIRCUITS = sizeof(CIRCUITS) / sizeof(CIRCUITS[0]);
 
@@ -230,7 +369,9 @@ struct b3w_ctx {
   int device;
   int sm_count;
   uint32_t chunk;
+  int ctas_per_sm;          // resident CTAs of this circuit's kernel (occupancy query)
   uint32_t *d_desc;
+  field_consts *d_field;    // nova only
   // staging for host-buffer batches: 2 ring slots
   cudaStream_t st[2];
   cudaEvent_t ev[2];
@@ -275,6 +416,21 @@ extern "C" int b3w_create(const b3w_config *cfg, b3w_ctx **out) {
   if (e1 == cudaSuccess) e1 = cudaMemcpy(c->d_desc, h, (size_t)d->ws * 4, cudaMemcpyHostToDevice);
   free(h);
   if (e1 != cudaSuccess) { delete c; return fail(B3W_ERR_CUDA, "descriptor upload: %s", cudaGetErrorString(e1)); }
+  if (d->nova) {
+    field_consts *F = new (std::nothrow) field_consts();
+    if (!F) { b3w_destroy(c); return fail(B3W_ERR_NOMEM, "out of host memory"); }
+    uint32_t pl[8];
+    memcpy(pl, d->prime, 32);
+    field_consts_init(*F, pl);
+    e1 = cudaMalloc(&c->d_field, sizeof(field_consts));
+    if (e1 == cudaSuccess) e1 = cudaMemcpy(c->d_field, F, sizeof(field_consts), cudaMemcpyHostToDevice);
+    delete F;
+    if (e1 != cudaSuccess) { b3w_destroy(c); return fail(B3W_ERR_CUDA, "field table upload: %s", cudaGetErrorString(e1)); }
+    e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, k_blake3_nova_witness, WARPS_PER_CTA * 32, NOVA_SMEM);
+  } else {
+    e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, k_blake3_comp_witness, WARPS_PER_CTA * 32, 0);
+  }
+  if (e1 != cudaSuccess || c->ctas_per_sm < 1) { b3w_destroy(c); return fail(B3W_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e1)); }
   *out = c;
   return B3W_OK;
 }
@@ -298,6 +454,7 @@ extern "C" void b3w_destroy(b3w_ctx *c) {
   cudaSetDevice(c->device);
   free_ring(c);
   if (c->d_desc) cudaFree(c->d_desc);
+  if (c->d_field) cudaFree(c->d_field);
   delete c;
 }
 
@@ -359,11 +516,15 @@ extern "C" int b3w_input_signal(uint32_t circuit, const char *name, uint32_t *of
 static int launch_witness(b3w_ctx *c, const uint32_t *d_in, uint64_t n, uint8_t *d_out, uint8_t *d_status,
                           uint32_t *d_pub, cudaStream_t s) {
   if (n == 0) return B3W_OK;
-  // grid: a multiple of the SM count; 8 CTAs of 8 warps fit per SM (30 KB smem, 256 threads each)
+  // persistent grid: exactly the CTAs that are resident at once (SM count x occupancy), grid-stride over instances
   uint64_t ctas_needed = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-  uint64_t max_ctas = (uint64_t)c->sm_count * 8;
+  uint64_t max_ctas = (uint64_t)c->sm_count * c->ctas_per_sm;
   unsigned grid = (unsigned)(ctas_needed < max_ctas ? ctas_needed : max_ctas);
-  k_blake3_comp_witness<<<grid, WARPS_PER_CTA * 32, 0, s>>>(d_in, n, c->d_desc, c->def->ws, d_out, d_status, d_pub);
+  if (c->def->nova)
+    k_blake3_nova_witness<<<grid, WARPS_PER_CTA * 32, NOVA_SMEM, s>>>(d_in, n, c->d_desc, c->def->ws, c->d_field, d_out,
+                                                                       d_status, d_pub);
+  else
+    k_blake3_comp_witness<<<grid, WARPS_PER_CTA * 32, 0, s>>>(d_in, n, c->d_desc, c->def->ws, d_out, d_status, d_pub);
   CK(cudaGetLastError());
   return B3W_OK;
 }

@@ -23,5 +23,5 @@
 #define DK_BIT 0u
 #define DK_W32 1u
 #define DK_W64 2u
-#define DK_FR 3u
-#define DK_NEG 4u
+#define DK_S64 3u         /* signed 64-bit integer trace[t] | trace[t+1] << 32, as a field element */
+#define DK_INV 4u         /* inverse mod p of that signed integer (0 for 0): circomlib IsZero.inv */

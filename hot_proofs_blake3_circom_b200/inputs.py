@@ -69,3 +69,24 @@ def splitmix_compression_inputs(n, seed=0xB3B30001, first=0):
     rows[:, 26] = (4 * b_words).astype(np.uint32)
     rows[:, 27] = w[:, 29] % 16
     return rows
+
+
+def splitmix_nova_inputs(n, seed=0xB3B30004, first=0):
+    """Independent blake3_nova step inputs: leaf_depth = total_depth in [1,64],
+    depth in [0, leaf_depth), n_blocks in [1,16], block_count in [0, n_blocks), 64-bit chunk_idx, random u32 h / m,
+    b in [0,64].  Rows are u32 in circuit declaration order (circuits/blake3_nova.circom:173-191):
+    n_blocks block_count h[8] chunk_idx_low chunk_idx_high leaf_depth total_depth depth m[16] b."""
+    w = splitmix_words(seed, np.arange(first, first + n, dtype=np.uint64), 40)
+    rows = np.zeros((n, 32), np.uint32)
+    n_blocks = w[:, 32] % 16 + 1
+    leaf_depth = w[:, 34] % 64 + 1
+    rows[:, 0] = n_blocks
+    rows[:, 1] = w[:, 33] % n_blocks
+    rows[:, 2:10] = w[:, 0:8]
+    rows[:, 10:12] = w[:, 8:10]
+    rows[:, 12] = leaf_depth
+    rows[:, 13] = leaf_depth
+    rows[:, 14] = w[:, 35] % leaf_depth
+    rows[:, 15:31] = w[:, 10:26]
+    rows[:, 31] = w[:, 36] % 65
+    return rows

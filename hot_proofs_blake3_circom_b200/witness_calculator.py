@@ -159,6 +159,10 @@ class WitnessCalculator:
 
     def _do_calculate(self, inp):
         row = self._row(inp)
+        if self.circuit != 0:
+            # the nova circuits execute log("D_FLAGS: ", D_FLAGS) once per witness (circuits/blake3_nova.circom:166);
+            # witness_calculator.js:44-61 prints it with console.log.  The batched entry point stays silent.
+            print("D_FLAGS:  0")
         out = np.empty(self.witnessSize * 32, np.uint8)
         rc = self._L.b3w_witness_one(self._h, row.ctypes.data, out.ctypes.data)
         if rc == _lib.B3W_CIRCOM_ASSERT:

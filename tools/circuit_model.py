@@ -882,5 +882,15 @@ def random_nova_inputs(rng, edge=0):
     if rng.random() < 0.3:
         block_count = n_blocks - 1
     b = rng.choice([0, 1, 4, 63, 64, rng.randrange(0, 65)])
+    if edge == 3:                      # depth == leaf_depth: exceed_depth.out === 0 fails  (blake3_nova.circom:44)
+        depth = leaf_depth
+    elif edge == 4:                    # legal but far outside the honest domain: huge depth, generic inverses
+        depth = 4000000000 + rng.randrange(1000)
+        leaf_depth = depth + rng.randrange(1, 258)
+        total_depth = rng.getrandbits(32)
+    elif edge == 5:                    # n_blocks = 0, block_count = 2^32 - 1 (block_count_out = 2^32)
+        n_blocks, block_count, depth = 0, 0xFFFFFFFF, leaf_depth - 1
+    elif edge == 6:                    # Num2Bits(9) range assert: leaf_depth - depth > 257
+        depth, leaf_depth = 3, 300
     return ([n_blocks, block_count] + [r32() for _ in range(8)] + [r32(), r32() if rng.random() < 0.5 else 0] +
             [leaf_depth, total_depth, depth] + [r32() for _ in range(16)] + [b])

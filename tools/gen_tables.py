@@ -145,7 +145,7 @@ def build_variant(variant, trials, verbose=True):
     sizes = [sz for _, sz in ref.plan]
     n_checked = 0
     for trial in range(trials):
-        inputs = random_inputs(variant, rng, edge=trial if trial < 3 else 0)
+        inputs = random_inputs(variant, rng, edge=trial if trial < 7 else 0)
         mdl = model_for(variant, inputs, ref.prime)
         d = {}
         pos = 0
@@ -184,7 +184,7 @@ def emit(results, check_only):
     prod = ["/* GENERATED by tools/gen_tables.py -- do not edit.",
             " * Slot-descriptor tables: where each witness slot's value lives in the kernel's trace.",
             " * Witness order = the reference wasm's own witness->signal table (SURVEY.md 8(a) A7). */",
-            "#pragma once", "#include <stdint.h>", "typedef struct { uint32_t desc0, count, delta; } b3w_seg;", ""]
+            "#pragma once", "#include <stdint.h>", "typedef struct { uint32_t desc0, count; int32_t delta; } b3w_seg;", ""]
     orc = ["/* GENERATED by tools/gen_tables.py -- do not edit.  TEST INFRASTRUCTURE (oracle).",
            " * witness slot -> circom signal index, run-length encoded {first signal, count} (consecutive signals). */",
            "#pragma once", "#include <stdint.h>", ""]
@@ -196,7 +196,7 @@ def emit(results, check_only):
         prod.append("static const b3w_seg B3W_SEGS_%s[%d] = {" % (v.upper(), len(segs)))
         line = "  "
         for s in segs:
-            item = "{0x%x,%d,0x%x}," % s
+            item = "{0x%x,%d,%d}," % s
             if len(line) + len(item) > 118:
                 prod.append(line)
                 line = "  "
