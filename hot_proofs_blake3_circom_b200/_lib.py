@@ -7,10 +7,14 @@ _LIB = None
 
 B3W_OK, B3W_ERR_INVALID, B3W_ERR_CUDA, B3W_ERR_NOMEM, B3W_ERR_DOMAIN, B3W_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 B3W_CIRCOM_ASSERT = 4
+B3W_R1CS_VIOLATION = 7
+B3W_NO_ROW = 0xFFFFFFFF
+B3W_FLAG_FUSED_CHECK = 1
 
 EXPORTS = ("b3w_version", "b3w_last_error", "b3w_create", "b3w_destroy", "b3w_circuit_info", "b3w_wtns_header",
            "b3w_input_signal", "b3w_witness_one", "b3w_witness_batch", "b3w_witness_batch_device",
-           "b3w_checksum_device", "b3w_calib_fill", "b3w_host_alloc", "b3w_host_free")
+           "b3w_checksum_device", "b3w_calib_fill", "b3w_host_alloc", "b3w_host_free",
+           "b3w_witness_batch_device_checked", "b3w_r1cs_check_device", "b3w_r1cs_info", "b3w_debug_inject_fault")
 
 
 class B3WError(RuntimeError):
@@ -55,6 +59,10 @@ def lib():
     L.b3w_witness_batch.argtypes = [vp, vp, u64, vp, vp, vp]
     L.b3w_witness_batch_device.argtypes = [vp, vp, u64, vp, vp, vp, vp]
     L.b3w_checksum_device.argtypes = [vp, vp, u64, vp, vp]
+    L.b3w_witness_batch_device_checked.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp]
+    L.b3w_r1cs_check_device.argtypes = [vp, vp, u64, vp, vp, vp]
+    L.b3w_r1cs_info.argtypes = [C.c_uint32, u32p, u32p]
+    L.b3w_debug_inject_fault.argtypes = [vp, C.c_uint32, C.c_uint32]
     L.b3w_calib_fill.argtypes = [vp, vp, u64, vp]
     L.b3w_host_alloc.argtypes = [C.c_size_t]
     L.b3w_host_alloc.restype = vp

@@ -22,6 +22,8 @@
 #include "slot_tables.h"
 #include "nova_trace.h"
 #include "fr.cuh"
+#include "r1cs_tables.h"
+#include "r1cs.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // error plumbing
@@ -51,6 +53,14 @@ __device__ __forceinline__ void st_slot(void *p, uint32_t w0, uint32_t w1, uint3
   asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w0), "r"(w1), "r"(w2),
                "r"(w3), "r"(w4), "r"(w5), "r"(w6), "r"(w7)
                : "memory");
+}
+
+// A full 8-limb field element goes out as two 128-bit stores.  (ptxas 12.9 mis-handles the live ranges of a
+// v8.b32 store whose eight operands are all computed values inside a non-inlined function and keeps only the first
+// limb -- seen in SASS as a 32-bit STG; the {lo, hi, 0...} form above is not affected.  tests/test_gpu_nova.py pins it.)
+__device__ __forceinline__ void st_slot_fr(void *p, const uint32_t *l) {
+  asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+  asm volatile("st.global.L1::no_allocate.v4.b32 [%0+16], {%1,%2,%3,%4};" ::"l"(p), "r"(l[4]), "r"(l[5]), "r"(l[6]), "r"(l[7]) : "memory");
 }
 
 // BLAKE3 message schedule: MSG_SCHED[r][j] = index into the original m[] of the word that round r
@@ -213,7 +223,7 @@ __device__ __noinline__ void store_field_slot(uint8_t *p, uint32_t kind, uint32_
   fr_t v;
   if (kind == DK_S64) v = fr_from_s64(x, F->p);
   else v = fr_inv_s64(x, *F);
-  st_slot(p, v.l[0], v.l[1], v.l[2], v.l[3], v.l[4], v.l[5], v.l[6], v.l[7]);
+  st_slot_fr(p, v.l);
 }
 
 // Phase 2: expand the trace into witness slots [0, ws) at `dst` (32 B per slot).
@@ -243,10 +253,22 @@ __device__ __forceinline__ void expand_slots(const uint32_t *trace, const uint32
 static_assert(NOVA_TRACE_WORDS <= NOVA_TRACE_STRIDE, "nova trace does not fit its stride");
 #define NOVA_SMEM (WARPS_PER_CTA * NOVA_TRACE_STRIDE * 4)
 
+// Optional extras of the checked kernel variants: the fused R1CS check (rows evaluated on the shared-memory trace,
+// nothing re-read from HBM) and a fault-injection hook for its negative tests.
+struct check_args {
+  r1cs_tables_dev T;
+  const field_consts *F;
+  uint32_t *first_bad;       // per instance: smallest violated row id or B3W_NO_ROW (may be NULL)
+  uint32_t fault_word;       // trace word to corrupt (B3W_NO_ROW = none) ...
+  uint32_t fault_mask;       // ... by xor with this mask, after the trace phase
+};
+
 // k_blake3_comp_witness: one warp per instance, grid-stride over instances.
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+template <bool CHECK>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, CHECK ? 4 : 7)
 k_blake3_comp_witness(const uint32_t *__restrict__ in, uint64_t n, const uint32_t *__restrict__ desc, uint32_t ws,
-                      uint8_t *__restrict__ out, uint8_t *__restrict__ status, uint32_t *__restrict__ pub) {
+                      uint8_t *__restrict__ out, uint8_t *__restrict__ status, uint32_t *__restrict__ pub,
+                      const check_args ck) {
   __shared__ __align__(16) uint32_t s_trace[WARPS_PER_CTA][TRACE_STRIDE];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   uint32_t *trace = s_trace[wib];
@@ -259,17 +281,26 @@ k_blake3_comp_witness(const uint32_t *__restrict__ in, uint64_t n, const uint32_
     compression_trace(trace, lane);
     __syncwarp();
     if (pub && lane < 16) pub[i * 16 + lane] = trace[TR_OUT + lane];
-    if (status && lane == 0) status[i] = 0;   // u32 inputs can never violate a constraint of this circuit
+    uint8_t st = 0;                           // u32 inputs can never violate a constraint of this circuit ...
+    if (CHECK) {                              // ... which the fused check confirms row by row
+      if (ck.fault_word != B3W_NO_ROW && lane == 0) trace[ck.fault_word] ^= ck.fault_mask;
+      __syncwarp();
+      const uint32_t bad = r1cs_check_instance(TraceSrc{trace, ck.F}, ck.T, lane);
+      if (bad != B3W_NO_ROW) st = B3W_R1CS_VIOLATION;
+      if (ck.first_bad && lane == 0) ck.first_bad[i] = bad;
+    }
+    if (status && lane == 0) status[i] = st;
     expand_slots<false>(trace, desc, ws, out + i * (uint64_t)ws * 32, lane, nullptr);
   }
 }
 
 // k_blake3_nova_witness: the nova step circuit (all three committed builds share it; they differ in the
 // slot table and the prime).  pub = z_{i+1} = the 15 outputs (low 32 bits each).
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+template <bool CHECK>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
 k_blake3_nova_witness(const uint32_t *__restrict__ in, uint64_t n, const uint32_t *__restrict__ desc, uint32_t ws,
                       const field_consts *__restrict__ F, uint8_t *__restrict__ out, uint8_t *__restrict__ status,
-                      uint32_t *__restrict__ pub) {
+                      uint32_t *__restrict__ pub, const check_args ck) {
   extern __shared__ __align__(16) uint32_t s_dyn[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   uint32_t *trace = s_dyn + wib * NOVA_TRACE_STRIDE;
@@ -280,14 +311,24 @@ k_blake3_nova_witness(const uint32_t *__restrict__ in, uint64_t n, const uint32_
     trace[NV_IN + lane] = __ldg(in + i * 32 + lane);
     __syncwarp();
     const bool ok = nova_trace(trace, lane);
-    if (status && lane == 0) status[i] = ok ? 0 : B3W_CIRCOM_ASSERT;
     if (!ok) {                                  // the reference throws "Assert Failed.": no witness exists
+      if (status && lane == 0) status[i] = B3W_CIRCOM_ASSERT;
       if (pub && lane < 15) pub[i * 15 + lane] = 0u;
+      if (CHECK && ck.first_bad && lane == 0) ck.first_bad[i] = B3W_NO_ROW;
       continue;
     }
     __syncwarp();
     compression_trace(trace, lane);
     __syncwarp();
+    uint8_t st = 0;
+    if (CHECK) {
+      if (ck.fault_word != B3W_NO_ROW && lane == 0) trace[ck.fault_word] ^= ck.fault_mask;
+      __syncwarp();
+      const uint32_t bad = r1cs_check_instance(TraceSrc{trace, ck.F}, ck.T, lane);
+      if (bad != B3W_NO_ROW) st = B3W_R1CS_VIOLATION;
+      if (ck.first_bad && lane == 0) ck.first_bad[i] = bad;
+    }
+    if (status && lane == 0) status[i] = st;
     if (pub && lane < 15) {
       // n_blocks_out, block_count_out, h_out[8], total_depth_out, depth_out, chunk_idx_low/high_out, leaf_depth_out (:195-202)
       uint32_t v;
@@ -302,6 +343,23 @@ k_blake3_nova_witness(const uint32_t *__restrict__ in, uint64_t n, const uint32_
       pub[i * 15 + lane] = v;
     }
     expand_slots<true>(trace, desc, ws, out + i * (uint64_t)ws * 32, lane, F);
+  }
+}
+
+// k_r1cs_check_witness: stand-alone check of witnesses resident in HBM (one warp per instance).
+__global__ void __launch_bounds__(256)
+k_r1cs_check_witness(const uint8_t *__restrict__ wit, uint64_t n, uint32_t ws, const r1cs_tables_dev T,
+                     const field_consts *__restrict__ F, uint8_t *__restrict__ status, uint32_t *__restrict__ first_bad) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t i = warp; i < n; i += nwarps) {
+    SlotSrc src{reinterpret_cast<const uint32_t *>(wit + i * (uint64_t)ws * 32), F};
+    const uint32_t bad = r1cs_check_instance(src, T, lane);
+    if (lane == 0) {
+      if (status) status[i] = bad == B3W_NO_ROW ? 0 : B3W_R1CS_VIOLATION;
+      if (first_bad) first_bad[i] = bad;
+    }
   }
 }
 
@@ -339,6 +397,12 @@ struct circuit_def {
   const b3w_seg *segs;
   size_t n_segs;
   const uint8_t *prime;
+  struct r1cs_set {
+    const b3w_r1cs_class *cls; size_t ncls;
+    const uint64_t (*coef)[2]; size_t ncoef;
+    const b3w_seg *cols; size_t ncols;
+    uint32_t rows, terms;
+  } r_fused, r_slots;    // reduced trace-space set (fused check) / all rows in witness-slot space (O1 builds; else empty)
   int n_sig;
   struct { const char *name; uint32_t off, size; } sig[12];
 };
@@ -353,14 +417,18 @@ static const uint8_t PRIME_PALLAS_SCALAR[32] = {0x01, 0x00, 0x00, 0x00, 0x21, 0x
   10, {{"n_blocks", 0, 1}, {"block_count", 1, 1}, {"h", 2, 8}, {"chunk_idx_low", 10, 1}, {"chunk_idx_high", 11, 1}, \
        {"leaf_depth", 12, 1}, {"total_depth", 13, 1}, {"depth", 14, 1}, {"m", 15, 16}, {"b", 31, 1}}
 #define SEGS(v) B3W_SEGS_##v, sizeof(B3W_SEGS_##v) / sizeof(b3w_seg)
+#define R1CS1(v)                                                                                                  \
+  {R1CS_CLASSES_##v, sizeof(R1CS_CLASSES_##v) / sizeof(b3w_r1cs_class), R1CS_COEFS_##v, sizeof(R1CS_COEFS_##v) / 16, \
+   R1CS_COLS_##v, sizeof(R1CS_COLS_##v) / sizeof(b3w_seg), R1CS_ROWS_##v, R1CS_TERMS_##v}
+#define R1CS_NONE {nullptr, 0, nullptr, 0, nullptr, 0, 0, 0}
 
 static const circuit_def CIRCUITS[] = {
-    {"blake3_compression", false, B3W_WS_COMPRESSION, 28, 16, B3W_TRACE_WORDS_COMPRESSION, SEGS(COMPRESSION), PRIME_BN254, 5,
+    {"blake3_compression", false, B3W_WS_COMPRESSION, 28, 16, B3W_TRACE_WORDS_COMPRESSION, SEGS(COMPRESSION), PRIME_BN254, R1CS1(COMPRESSION_FUSED), R1CS1(COMPRESSION_SLOTS), 5,
      {{"h", 0, 8}, {"m", 8, 16}, {"t", 24, 2}, {"b", 26, 1}, {"d", 27, 1}}},
-    {"blake3_nova (bn128, O2)", true, B3W_WS_NOVA_BN_O2, 32, 15, B3W_TRACE_WORDS_NOVA_BN_O2, SEGS(NOVA_BN_O2), PRIME_BN254, NOVA_SIGS},
+    {"blake3_nova (bn128, O2)", true, B3W_WS_NOVA_BN_O2, 32, 15, B3W_TRACE_WORDS_NOVA_BN_O2, SEGS(NOVA_BN_O2), PRIME_BN254, R1CS1(NOVA_FUSED), R1CS_NONE, NOVA_SIGS},
     {"blake3_nova_pasta (vesta prime = Pallas scalar, O2)", true, B3W_WS_NOVA_PASTA_O2, 32, 15, B3W_TRACE_WORDS_NOVA_PASTA_O2,
-     SEGS(NOVA_PASTA_O2), PRIME_PALLAS_SCALAR, NOVA_SIGS},
-    {"blake3_nova (bn128, O1)", true, B3W_WS_NOVA_BN_O1, 32, 15, B3W_TRACE_WORDS_NOVA_BN_O1, SEGS(NOVA_BN_O1), PRIME_BN254, NOVA_SIGS},
+     SEGS(NOVA_PASTA_O2), PRIME_PALLAS_SCALAR, R1CS1(NOVA_FUSED), R1CS_NONE, NOVA_SIGS},
+    {"blake3_nova (bn128, O1)", true, B3W_WS_NOVA_BN_O1, 32, 15, B3W_TRACE_WORDS_NOVA_BN_O1, SEGS(NOVA_BN_O1), PRIME_BN254, R1CS1(NOVA_FUSED), R1CS1(NOVA_BN_O1_SLOTS), NOVA_SIGS},
 };
 static const int N_CIRCUITS = sizeof(CIRCUITS) / sizeof(CIRCUITS[0]);
 
@@ -370,8 +438,15 @@ struct b3w_ctx {
   int sm_count;
   uint32_t chunk;
   int ctas_per_sm;          // resident CTAs of this circuit's kernel (occupancy query)
+  int ctas_per_sm_checked;  // ... of its *_checked variant
   uint32_t *d_desc;
-  field_consts *d_field;    // nova only
+  field_consts *d_field;
+  uint32_t *h_desc;         // host copy of the per-slot descriptors
+  uint32_t flags;
+  // R1CS tables (built on first use)
+  bool r1cs_ready;
+  struct r1cs_dev { r1cs_class_dev *cls; int64_t *lo, *hi; uint32_t *terms; uint32_t ncls; } r_fused, r_slots;
+  uint32_t fault_word, fault_mask;
   // staging for host-buffer batches: 2 ring slots
   cudaStream_t st[2];
   cudaEvent_t ev[2];
@@ -388,7 +463,7 @@ extern "C" const char *b3w_last_error(void) { return g_err; }
 extern "C" int b3w_create(const b3w_config *cfg, b3w_ctx **out) {
   if (!cfg || !out) return fail(B3W_ERR_INVALID, "b3w_create: null argument");
   if (cfg->circuit >= (uint32_t)N_CIRCUITS) return fail(B3W_ERR_UNSUPPORTED, "b3w_create: circuit %u not built", cfg->circuit);
-  if (cfg->flags) return fail(B3W_ERR_INVALID, "b3w_create: flags must be 0");
+  if (cfg->flags & ~(uint32_t)B3W_FLAG_FUSED_CHECK) return fail(B3W_ERR_INVALID, "b3w_create: unknown flags 0x%x", cfg->flags);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -403,6 +478,8 @@ extern "C" int b3w_create(const b3w_config *cfg, b3w_ctx **out) {
   c->def = &CIRCUITS[cfg->circuit];
   c->device = dev;
   c->chunk = cfg->chunk ? cfg->chunk : 1024;
+  c->flags = cfg->flags;
+  c->fault_word = B3W_NO_ROW;
   CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, dev));
   // expand the run-length table to one descriptor per slot and upload it
   const circuit_def *d = c->def;
@@ -414,9 +491,9 @@ extern "C" int b3w_create(const b3w_config *cfg, b3w_ctx **out) {
   if (pos != d->ws) { free(h); delete c; return fail(B3W_ERR_INVALID, "slot table of %s is corrupt", d->name); }
   cudaError_t e1 = cudaMalloc(&c->d_desc, (size_t)d->ws * 4);
   if (e1 == cudaSuccess) e1 = cudaMemcpy(c->d_desc, h, (size_t)d->ws * 4, cudaMemcpyHostToDevice);
-  free(h);
-  if (e1 != cudaSuccess) { delete c; return fail(B3W_ERR_CUDA, "descriptor upload: %s", cudaGetErrorString(e1)); }
-  if (d->nova) {
+  c->h_desc = h;
+  if (e1 != cudaSuccess) { b3w_destroy(c); return fail(B3W_ERR_CUDA, "descriptor upload: %s", cudaGetErrorString(e1)); }
+  {
     field_consts *F = new (std::nothrow) field_consts();
     if (!F) { b3w_destroy(c); return fail(B3W_ERR_NOMEM, "out of host memory"); }
     uint32_t pl[8];
@@ -426,11 +503,17 @@ extern "C" int b3w_create(const b3w_config *cfg, b3w_ctx **out) {
     if (e1 == cudaSuccess) e1 = cudaMemcpy(c->d_field, F, sizeof(field_consts), cudaMemcpyHostToDevice);
     delete F;
     if (e1 != cudaSuccess) { b3w_destroy(c); return fail(B3W_ERR_CUDA, "field table upload: %s", cudaGetErrorString(e1)); }
-    e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, k_blake3_nova_witness, WARPS_PER_CTA * 32, NOVA_SMEM);
-  } else {
-    e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, k_blake3_comp_witness, WARPS_PER_CTA * 32, 0);
   }
-  if (e1 != cudaSuccess || c->ctas_per_sm < 1) { b3w_destroy(c); return fail(B3W_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e1)); }
+  if (d->nova) {
+    e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, k_blake3_nova_witness<false>, WARPS_PER_CTA * 32, NOVA_SMEM);
+    if (e1 == cudaSuccess)
+      e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm_checked, k_blake3_nova_witness<true>, WARPS_PER_CTA * 32, NOVA_SMEM);
+  } else {
+    e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, k_blake3_comp_witness<false>, WARPS_PER_CTA * 32, 0);
+    if (e1 == cudaSuccess)
+      e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm_checked, k_blake3_comp_witness<true>, WARPS_PER_CTA * 32, 0);
+  }
+  if (e1 != cudaSuccess || c->ctas_per_sm < 1 || c->ctas_per_sm_checked < 1) { b3w_destroy(c); return fail(B3W_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e1)); }
   *out = c;
   return B3W_OK;
 }
@@ -455,6 +538,13 @@ extern "C" void b3w_destroy(b3w_ctx *c) {
   free_ring(c);
   if (c->d_desc) cudaFree(c->d_desc);
   if (c->d_field) cudaFree(c->d_field);
+  for (b3w_ctx::r1cs_dev *r : {&c->r_slots, &c->r_fused}) {
+    if (r->cls) cudaFree(r->cls);
+    if (r->lo) cudaFree(r->lo);
+    if (r->hi) cudaFree(r->hi);
+    if (r->terms) cudaFree(r->terms);
+  }
+  free(c->h_desc);
   delete c;
 }
 
@@ -513,18 +603,85 @@ extern "C" int b3w_input_signal(uint32_t circuit, const char *name, uint32_t *of
   return fail(B3W_ERR_INVALID, "Signal %s not found", name);
 }
 
+// Expand the class / coefficient / column tables of one R1CS row set (r1cs_tables.h) and upload them.
+static int upload_r1cs_set(b3w_ctx *c, const circuit_def::r1cs_set &set, b3w_ctx::r1cs_dev *out) {
+  const size_t ncls = set.ncls;
+  if (ncls == 0) return B3W_OK;
+  r1cs_class_dev *cls = (r1cs_class_dev *)calloc(ncls, sizeof *cls);
+  int64_t *lo = (int64_t *)calloc(set.ncoef, 8), *hi = (int64_t *)calloc(set.ncoef, 8);
+  uint32_t *td = (uint32_t *)calloc(set.terms, 4);
+  int rc = B3W_OK;
+  auto done = [&](int code) { free(cls); free(lo); free(hi); free(td); return code; };
+  if (!cls || !lo || !hi || !td) return done(fail(B3W_ERR_NOMEM, "out of host memory"));
+  for (size_t i = 0; i < set.ncoef; i++) { lo[i] = (int64_t)set.coef[i][0]; hi[i] = (int64_t)set.coef[i][1]; }
+  uint32_t term_off = 0, row_off = 0;
+  bool corrupt = false;
+  for (size_t k = 0; k < ncls && !corrupt; k++) {
+    const b3w_r1cs_class &s = set.cls[k];
+    cls[k] = r1cs_class_dev{s.nA, s.nB, s.nC, s.flags, s.count, s.coef_off, term_off, row_off};
+    size_t pos = s.col_off;
+    for (uint32_t t = 0; t < (uint32_t)(s.nA + s.nB + s.nC) && !corrupt; t++) {
+      if (pos >= set.ncols || set.cols[pos].desc0 != 0xFFFFFFFFu || term_off + s.count > set.terms) { corrupt = true; break; }
+      uint32_t nruns = set.cols[pos++].count, w = 0;
+      for (uint32_t r = 0; r < nruns && !corrupt; r++, pos++)
+        for (uint32_t j = 0; j < set.cols[pos].count; j++) {
+          if (w >= s.count) { corrupt = true; break; }
+          td[term_off + w++] = set.cols[pos].desc0 + j * (uint32_t)set.cols[pos].delta;
+        }
+      if (w != s.count) corrupt = true;
+      term_off += s.count;
+    }
+    row_off += s.count;
+  }
+  if (corrupt || term_off != set.terms || row_off != set.rows) return done(fail(B3W_ERR_INVALID, "R1CS tables of %s are corrupt", c->def->name));
+  cudaError_t e = cudaMalloc(&out->cls, ncls * sizeof *cls);
+  if (e == cudaSuccess) e = cudaMalloc(&out->lo, set.ncoef * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&out->hi, set.ncoef * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&out->terms, (size_t)set.terms * 4);
+  if (e == cudaSuccess) e = cudaMemcpy(out->cls, cls, ncls * sizeof *cls, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(out->lo, lo, set.ncoef * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(out->hi, hi, set.ncoef * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(out->terms, td, (size_t)set.terms * 4, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) rc = fail(B3W_ERR_CUDA, "R1CS table upload: %s", cudaGetErrorString(e));
+  out->ncls = (uint32_t)ncls;
+  return done(rc);
+}
+
+static int ensure_r1cs(b3w_ctx *c) {
+  if (c->r1cs_ready) return B3W_OK;
+  int rc = upload_r1cs_set(c, c->def->r_fused, &c->r_fused);
+  if (rc == B3W_OK) rc = upload_r1cs_set(c, c->def->r_slots, &c->r_slots);
+  if (rc == B3W_OK) c->r1cs_ready = true;
+  return rc;
+}
+
 static int launch_witness(b3w_ctx *c, const uint32_t *d_in, uint64_t n, uint8_t *d_out, uint8_t *d_status,
-                          uint32_t *d_pub, cudaStream_t s) {
+                          uint32_t *d_pub, cudaStream_t s, bool check = false, uint32_t *d_first_bad = nullptr) {
   if (n == 0) return B3W_OK;
   // persistent grid: exactly the CTAs that are resident at once (SM count x occupancy), grid-stride over instances
   uint64_t ctas_needed = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-  uint64_t max_ctas = (uint64_t)c->sm_count * c->ctas_per_sm;
+  uint64_t max_ctas = (uint64_t)c->sm_count * (check ? c->ctas_per_sm_checked : c->ctas_per_sm);
   unsigned grid = (unsigned)(ctas_needed < max_ctas ? ctas_needed : max_ctas);
-  if (c->def->nova)
-    k_blake3_nova_witness<<<grid, WARPS_PER_CTA * 32, NOVA_SMEM, s>>>(d_in, n, c->d_desc, c->def->ws, c->d_field, d_out,
-                                                                       d_status, d_pub);
-  else
-    k_blake3_comp_witness<<<grid, WARPS_PER_CTA * 32, 0, s>>>(d_in, n, c->d_desc, c->def->ws, d_out, d_status, d_pub);
+  check_args ck;
+  memset(&ck, 0, sizeof ck);
+  ck.fault_word = B3W_NO_ROW;
+  if (check) {
+    int rc = ensure_r1cs(c);
+    if (rc) return rc;
+    ck.T = r1cs_tables_dev{c->r_fused.cls, c->r_fused.lo, c->r_fused.hi, c->r_fused.terms, c->r_fused.ncls};
+    ck.F = c->d_field;
+    ck.first_bad = d_first_bad;
+    ck.fault_word = c->fault_word;
+    ck.fault_mask = c->fault_mask;
+  }
+  const unsigned bs = WARPS_PER_CTA * 32;
+  if (c->def->nova) {
+    if (check) k_blake3_nova_witness<true><<<grid, bs, NOVA_SMEM, s>>>(d_in, n, c->d_desc, c->def->ws, c->d_field, d_out, d_status, d_pub, ck);
+    else k_blake3_nova_witness<false><<<grid, bs, NOVA_SMEM, s>>>(d_in, n, c->d_desc, c->def->ws, c->d_field, d_out, d_status, d_pub, ck);
+  } else {
+    if (check) k_blake3_comp_witness<true><<<grid, bs, 0, s>>>(d_in, n, c->d_desc, c->def->ws, d_out, d_status, d_pub, ck);
+    else k_blake3_comp_witness<false><<<grid, bs, 0, s>>>(d_in, n, c->d_desc, c->def->ws, d_out, d_status, d_pub, ck);
+  }
   CK(cudaGetLastError());
   return B3W_OK;
 }
@@ -534,7 +691,51 @@ extern "C" int b3w_witness_batch_device(b3w_ctx *c, const uint32_t *d_in, uint64
   if (!c || !d_in || !d_out) return fail(B3W_ERR_INVALID, "b3w_witness_batch_device: null argument");
   if (((uintptr_t)d_out & 31) != 0) return fail(B3W_ERR_INVALID, "d_out must be 32-byte aligned");
   CK(cudaSetDevice(c->device));
-  return launch_witness(c, d_in, n, d_out, d_status, d_pub, (cudaStream_t)stream);
+  return launch_witness(c, d_in, n, d_out, d_status, d_pub, (cudaStream_t)stream, (c->flags & B3W_FLAG_FUSED_CHECK) != 0);
+}
+
+extern "C" int b3w_witness_batch_device_checked(b3w_ctx *c, const uint32_t *d_in, uint64_t n, uint8_t *d_out,
+                                                uint8_t *d_status, uint32_t *d_pub, uint32_t *d_first_bad, void *stream) {
+  if (!c || !d_in || !d_out) return fail(B3W_ERR_INVALID, "b3w_witness_batch_device_checked: null argument");
+  if (((uintptr_t)d_out & 31) != 0) return fail(B3W_ERR_INVALID, "d_out must be 32-byte aligned");
+  CK(cudaSetDevice(c->device));
+  return launch_witness(c, d_in, n, d_out, d_status, d_pub, (cudaStream_t)stream, true, d_first_bad);
+}
+
+extern "C" int b3w_r1cs_info(uint32_t circuit, uint32_t *n_rows, uint32_t *n_terms) {
+  const circuit_def *d = find_def(circuit);
+  if (!d) return B3W_ERR_UNSUPPORTED;
+  if (n_rows) *n_rows = d->nova ? R1CS_ROWS_NOVA_BN_O1_SLOTS : R1CS_ROWS_COMPRESSION_SLOTS;
+  if (n_terms) *n_terms = d->nova ? R1CS_TERMS_NOVA_BN_O1_SLOTS : R1CS_TERMS_COMPRESSION_SLOTS;
+  return B3W_OK;
+}
+
+extern "C" int b3w_r1cs_check_device(b3w_ctx *c, const uint8_t *d_wit, uint64_t n, uint8_t *d_status,
+                                     uint32_t *d_first_bad, void *stream) {
+  if (!c || !d_wit) return fail(B3W_ERR_INVALID, "b3w_r1cs_check_device: null argument");
+  if (((uintptr_t)d_wit & 15) != 0) return fail(B3W_ERR_INVALID, "d_wit must be 16-byte aligned");
+  CK(cudaSetDevice(c->device));
+  int rc = ensure_r1cs(c);
+  if (rc) return rc;
+  if (c->r_slots.ncls == 0)
+    return fail(B3W_ERR_UNSUPPORTED, "%s: circom's O2 pass removed signals that the template-level rows refer to; use the "
+                "fused check (b3w_witness_batch_device_checked) for this build", c->def->name);
+  if (n == 0) return B3W_OK;
+  r1cs_tables_dev T{c->r_slots.cls, c->r_slots.lo, c->r_slots.hi, c->r_slots.terms, c->r_slots.ncls};
+  uint64_t ctas = (n + 7) / 8, cap = (uint64_t)c->sm_count * 8;
+  k_r1cs_check_witness<<<(unsigned)(ctas < cap ? ctas : cap), 256, 0, (cudaStream_t)stream>>>(d_wit, n, c->def->ws, T, c->d_field,
+                                                                                            d_status, d_first_bad);
+  CK(cudaGetLastError());
+  return B3W_OK;
+}
+
+extern "C" int b3w_debug_inject_fault(b3w_ctx *c, uint32_t trace_word, uint32_t xor_mask) {
+  if (!c) return fail(B3W_ERR_INVALID, "b3w_debug_inject_fault: null argument");
+  if (trace_word != B3W_NO_ROW && trace_word >= (c->def->nova ? (uint32_t)NOVA_TRACE_WORDS : (uint32_t)TR_NOVA))
+    return fail(B3W_ERR_INVALID, "trace word %u out of range", trace_word);
+  c->fault_word = trace_word;
+  c->fault_mask = xor_mask;
+  return B3W_OK;
 }
 
 static int ensure_ring(b3w_ctx *c) {
@@ -567,7 +768,7 @@ extern "C" int b3w_witness_batch(b3w_ctx *c, const uint32_t *in, uint64_t n, uin
     uint64_t m = n - done < c->chunk ? n - done : c->chunk;
     cudaStream_t s = c->st[k];
     CK(cudaMemcpyAsync(c->d_in[k], in + done * d->n_inputs, (size_t)m * d->n_inputs * 4, cudaMemcpyHostToDevice, s));
-    rc = launch_witness(c, c->d_in[k], m, c->d_ring[k], c->d_status[k], c->d_pub[k], s);
+    rc = launch_witness(c, c->d_in[k], m, c->d_ring[k], c->d_status[k], c->d_pub[k], s, (c->flags & B3W_FLAG_FUSED_CHECK) != 0);
     if (rc) return rc;
     if (out) CK(cudaMemcpyAsync(out + done * wbytes, c->d_ring[k], (size_t)m * wbytes, cudaMemcpyDeviceToHost, s));
     if (status) CK(cudaMemcpyAsync(status + done, c->d_status[k], (size_t)m, cudaMemcpyDeviceToHost, s));

@@ -1,0 +1,168 @@
+// r1cs.cuh -- on-device R1CS satisfiability check:  (A.z) * (B.z) - C.z == 0 for every row, over Fr.
+//
+// The reference never checks constraints in the witness path itself; its tests do, through circom_tester
+// (`expectPass`, test/blake3_hash.test.ts:36,57) and the Rust side through bellpepper
+// (rust_fold/src/utils.rs:78-85 enforces every row).  The rows here are re-derived from the circom templates
+// by tools/gen_r1cs.py (r1cs_tables.h), grouped into shape classes: the 32 lanes of a warp evaluate 32 rows of
+// identical shape, term columns are term-major so that lane loads coalesce.
+//
+// Two value sources share the evaluator:
+//   TraceSrc  -- the fused check: a term is a slot DESCRIPTOR and its value is taken from the shared-memory trace
+//                that the expansion is about to read (nothing is re-read from HBM).  In trace space the rows that are
+//                identities for ANY trace content (booleanity of a bit extracted by shift-and-mask; w == sum 2^i
+//                bit_i(w)) need no evaluation, and the 32 rows 2*x_i*y_i = x_i + y_i - o_i over the bits of one word
+//                triple are evaluated bit-sliced as ONE word comparison (class flag XORW): the *_FUSED row sets;
+//   SlotSrc   -- the stand-alone check of witnesses resident in HBM: a term is a witness SLOT index and its value
+//                is the 32-byte field element found there.
+// Arithmetic: every row of these circuits except IsZero's `in*inv = 1 - out` is an identity between integers far
+// below p (bits, u32 words, <= 66-bit sums, small negatives), so it is evaluated exactly in signed 64-bit (NARROW
+// classes) or signed 128-bit (WIDE) integers; the 67 IsZero rows per nova witness go through Montgomery
+// multiplication in Fr (FIELD classes).  A slot that holds anything but a small (|x| < 2^63) integer inside an
+// integer row cannot satisfy it and is reported as a violation.
+#pragma once
+#include <stdint.h>
+#include "fr.cuh"
+#include "trace_layout.h"
+
+#define R1CS_FLAG_FIELD 1u
+#define R1CS_FLAG_WIDE 2u
+#define R1CS_FLAG_XORW 4u     /* fused set only: 32 XOR rows of one word triple, X ^ rotr(Y, dy) == rotr(O, do) */
+#define B3W_NO_ROW 0xFFFFFFFFu
+
+struct r1cs_class_dev {
+  uint16_t nA, nB, nC, flags;
+  uint32_t count, coef_off, term_off, row_off;     // term_off: start of this class's term matrix; row_off: first row id
+};
+
+struct r1cs_tables_dev {
+  const r1cs_class_dev *cls;
+  const int64_t *coef_lo;      // low 64 bits of each coefficient (two's complement)
+  const int64_t *coef_hi;      // high 64 bits
+  const uint32_t *terms;       // descriptors (TraceSrc) or slot indices (SlotSrc), [class][term][row]
+  uint32_t n_classes;
+};
+
+typedef __int128 i128;
+
+struct TraceSrc {
+  const uint32_t *trace;
+  const field_consts *F;
+  __device__ __forceinline__ bool xorw(const r1cs_class_dev &c, const r1cs_tables_dev &T, uint32_t r) const;
+  __device__ __forceinline__ bool small(uint32_t d, i128 &v) const {
+    const uint32_t t = d & 0xFFFFu, k = (d >> 16) & 31u, kind = d >> 24;
+    const uint32_t w = trace[t];
+    if (kind == DK_BIT) v = (w >> k) & 1u;
+    else if (kind == DK_W32) v = w;
+    else if (kind == DK_W64) v = (i128)(((uint64_t)trace[t + 1] << 32) | w);
+    else if (kind == DK_S64) v = (i128)(int64_t)(((uint64_t)trace[t + 1] << 32) | w);
+    else return false;
+    return true;
+  }
+  __device__ __forceinline__ fr_t field(uint32_t d) const {
+    const uint32_t t = d & 0xFFFFu, kind = d >> 24;
+    const int64_t x = (int64_t)(((uint64_t)trace[t + 1] << 32) | trace[t]);
+    if (kind == DK_INV) return fr_inv_s64(x, *F);
+    i128 v;
+    small(d, v);
+    return fr_from_s64((int64_t)v, F->p);      // FIELD rows only hold S64 / INV / bit terms
+  }
+};
+
+// XORW row: for bits, 2xy = x + y - o  <=>  o = x ^ y; all 32 rows of the word triple at once.
+__device__ __forceinline__ bool r1cs_xorw_row(const uint32_t *trace, const r1cs_class_dev &c, const r1cs_tables_dev &T, uint32_t r) {
+  const uint32_t *tm = T.terms + c.term_off;
+  const uint32_t dx = tm[r], dy = tm[c.count + r], dz = tm[2 * c.count + r];
+  const uint32_t X = trace[dx & 0xFFFFu], Y = trace[dy & 0xFFFFu], O = trace[dz & 0xFFFFu];
+  return (X ^ __funnelshift_r(Y, Y, (dy >> 16) & 31u)) == __funnelshift_r(O, O, (dz >> 16) & 31u);
+}
+
+struct SlotSrc {
+  const uint32_t *wit;          // this instance's witness, 8 u32 per slot
+  const field_consts *F;
+  __device__ __forceinline__ fr_t load(uint32_t s) const {
+    fr_t v;
+    const uint4 a = *reinterpret_cast<const uint4 *>(wit + 8 * (size_t)s);
+    const uint4 b = *reinterpret_cast<const uint4 *>(wit + 8 * (size_t)s + 4);
+    v.l[0] = a.x; v.l[1] = a.y; v.l[2] = a.z; v.l[3] = a.w; v.l[4] = b.x; v.l[5] = b.y; v.l[6] = b.z; v.l[7] = b.w;
+    return v;
+  }
+  __device__ __forceinline__ bool small(uint32_t s, i128 &v) const {
+    fr_t x = load(s);
+    if ((x.l[2] | x.l[3] | x.l[4] | x.l[5] | x.l[6] | x.l[7]) == 0) {
+      v = (i128)(((uint64_t)x.l[1] << 32) | x.l[0]);
+      return true;
+    }
+    fr_t n;                     // p - x: a small negative integer stored canonically?
+    if (fr_raw_sub(n, F->p, x)) return false;          // x > p: not canonical
+    if ((n.l[2] | n.l[3] | n.l[4] | n.l[5] | n.l[6] | n.l[7]) != 0 || (n.l[1] >> 31)) return false;
+    v = -(i128)(((uint64_t)n.l[1] << 32) | n.l[0]);
+    return true;
+  }
+  __device__ __forceinline__ fr_t field(uint32_t s) const { return load(s); }
+  __device__ __forceinline__ bool xorw(const r1cs_class_dev &, const r1cs_tables_dev &, uint32_t) const { return false; }
+};
+__device__ __forceinline__ bool TraceSrc::xorw(const r1cs_class_dev &c, const r1cs_tables_dev &T, uint32_t r) const {
+  return r1cs_xorw_row(trace, c, T, r);
+}
+
+// FIELD row (IsZero):  a * b == C.z  with single unit-coefficient A and B terms.
+template <class Src>
+__device__ __noinline__ bool r1cs_field_row(const Src &src, const r1cs_class_dev &c, const r1cs_tables_dev &T, uint32_t r) {
+  const uint32_t *tm = T.terms + c.term_off;
+  const fr_t a = src.field(tm[r]), b = src.field(tm[c.count + r]);
+  const field_consts &F = *src.F;
+  const fr_t ab = fr_montmul(fr_montmul(a, b, F.p, F.n0), F.r2, F.p, F.n0);
+  i128 lc = 0;
+  for (uint32_t t = 0; t < c.nC; t++) {
+    i128 v;
+    if (!src.small(tm[(2 + t) * c.count + r], v)) return false;
+    lc += (i128)T.coef_lo[c.coef_off + 2 + t] * v;
+  }
+  const fr_t want = fr_from_s64((int64_t)lc, F.p);
+  bool eq = true;
+#pragma unroll
+  for (int j = 0; j < 8; j++) eq = eq && (ab.l[j] == want.l[j]);
+  return eq;
+}
+
+template <class Src, typename acc_t>
+__device__ __forceinline__ bool r1cs_int_row(const Src &src, const r1cs_class_dev &c, const r1cs_tables_dev &T, uint32_t r) {
+  const uint32_t *tm = T.terms + c.term_off;
+  acc_t L[3] = {0, 0, 0};
+  const uint32_t n[3] = {c.nA, c.nB, c.nC};
+  uint32_t t = 0;
+  bool ok = true;
+#pragma unroll
+  for (int part = 0; part < 3; part++) {
+    for (uint32_t j = 0; j < n[part]; j++, t++) {
+      i128 v;
+      ok = src.small(tm[t * c.count + r], v) && ok;
+      acc_t co = sizeof(acc_t) == 16 ? (acc_t)(((i128)T.coef_hi[c.coef_off + t] << 64) | (i128)(uint64_t)T.coef_lo[c.coef_off + t])
+                                      : (acc_t)T.coef_lo[c.coef_off + t];
+      L[part] += co * (acc_t)v;
+    }
+  }
+  if (!ok) return false;
+  return c.nA == 0 ? L[2] == 0 : L[0] * L[1] == L[2];
+}
+
+// Evaluate every row of one instance with one warp.  Returns the smallest violated row id over the warp's lanes
+// (B3W_NO_ROW if the instance satisfies the system); all lanes return the same value.
+template <class Src>
+__device__ __forceinline__ uint32_t r1cs_check_instance(const Src &src, const r1cs_tables_dev &T, int lane) {
+  uint32_t bad = B3W_NO_ROW;
+  for (uint32_t ci = 0; ci < T.n_classes; ci++) {
+    const r1cs_class_dev c = T.cls[ci];
+    for (uint32_t r = lane; r < c.count; r += 32) {
+      bool ok;
+      if (c.flags & R1CS_FLAG_XORW) ok = src.xorw(c, T, r);
+      else if (c.flags & R1CS_FLAG_FIELD) ok = r1cs_field_row(src, c, T, r);
+      else if (c.flags & R1CS_FLAG_WIDE) ok = r1cs_int_row<Src, i128>(src, c, T, r);
+      else ok = r1cs_int_row<Src, int64_t>(src, c, T, r);
+      if (!ok) bad = min(bad, c.row_off + r);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) bad = min(bad, __shfl_xor_sync(0xffffffffu, bad, o));
+  return bad;
+}

@@ -44,17 +44,18 @@ def circuit_from_wasm(code):
     return CIRCUITS[h][0]
 
 
-def builder(code, options=None, device=-1, chunk=0, lazy=False):
+def builder(code, options=None, device=-1, chunk=0, lazy=False, fused_check=False):
     """builder(code, options) -> WitnessCalculator   (witness_calculator.js:1).
     `code`: bytes of one of the reference's .wasm files, or a circuit name / id.
-    lazy=True defers the creation of the GPU context to the first witness call (host-logic tests)."""
+    lazy=True defers the creation of the GPU context to the first witness call (host-logic tests).
+    fused_check=True makes every batch call also run the fused on-device R1CS check (status 7 = violation)."""
     if isinstance(code, int):
         cid = code
     elif isinstance(code, str):
         cid = CIRCUIT_IDS[code]
     else:
         cid = circuit_from_wasm(code)
-    return WitnessCalculator(cid, options or {}, device=device, chunk=chunk, lazy=lazy)
+    return WitnessCalculator(cid, options or {}, device=device, chunk=chunk, lazy=lazy, fused_check=fused_check)
 
 
 def _flat_array(a):
@@ -86,9 +87,10 @@ def _to_bigint(n):
 
 
 class WitnessCalculator:
-    def __init__(self, circuit, sanity_check, device=-1, chunk=0, lazy=False):
+    def __init__(self, circuit, sanity_check, device=-1, chunk=0, lazy=False, fused_check=False):
         L = _lib.lib()
-        self._L, self._ctx, self._cfg = L, None, _lib.Config(circuit, device, chunk, 0)
+        self._L, self._ctx = L, None
+        self._cfg = _lib.Config(circuit, device, chunk, _lib.B3W_FLAG_FUSED_CHECK if fused_check else 0)
         info = _lib.Info()
         _lib.check(L.b3w_circuit_info(circuit, C.byref(info)))
         if not lazy:
@@ -212,6 +214,23 @@ class WitnessCalculator:
     def witness_batch_device(self, d_in, n, d_out, d_status=0, d_pub=0, stream=0):
         _lib.check(self._L.b3w_witness_batch_device(self._h, d_in, n, d_out, d_status or None, d_pub or None,
                                                     stream or None))
+
+    def witness_batch_device_checked(self, d_in, n, d_out, d_status=0, d_pub=0, d_first_bad=0, stream=0):
+        """generation + fused R1CS check (rows evaluated on the shared-memory trace)"""
+        _lib.check(self._L.b3w_witness_batch_device_checked(self._h, d_in, n, d_out, d_status or None, d_pub or None,
+                                                            d_first_bad or None, stream or None))
+
+    def r1cs_check_device(self, d_wit, n, d_status=0, d_first_bad=0, stream=0):
+        """stand-alone R1CS check of witnesses resident in device memory (O1 builds)"""
+        _lib.check(self._L.b3w_r1cs_check_device(self._h, d_wit, n, d_status or None, d_first_bad or None, stream or None))
+
+    def r1cs_info(self):
+        rows, terms = C.c_uint32(), C.c_uint32()
+        _lib.check(self._L.b3w_r1cs_info(self.circuit, C.byref(rows), C.byref(terms)))
+        return rows.value, terms.value
+
+    def inject_fault(self, trace_word=0xFFFFFFFF, xor_mask=0):
+        _lib.check(self._L.b3w_debug_inject_fault(self._h, trace_word, xor_mask))
 
     def checksum_device(self, d_wit, n, d_sums, stream=0):
         _lib.check(self._L.b3w_checksum_device(self._h, d_wit, n, d_sums, stream or None))

@@ -29,6 +29,10 @@ extern "C" {
 #define B3W_ERR_DOMAIN (-4)      /* an input is outside the supported (u32) domain */
 #define B3W_ERR_UNSUPPORTED (-5)
 #define B3W_CIRCOM_ASSERT 4      /* "Assert Failed." (witness_calculator.js:29-30) */
+#define B3W_R1CS_VIOLATION 7     /* per-instance status of the on-device R1CS check: some row has A.z * B.z != C.z */
+#define B3W_NO_ROW 0xFFFFFFFFu   /* "no violated row" in first_bad[] */
+
+#define B3W_FLAG_FUSED_CHECK 1u  /* b3w_config.flags: every batch call also runs the fused R1CS check */
 
 /* Circuit variants = the reference's committed witness programs:
  *   COMPRESSION   build/blake3_compression/blake3_compression_js/blake3_compression.wasm (BN254, O1)
@@ -46,7 +50,7 @@ typedef struct {
   uint32_t circuit;        /* b3w_circuit */
   int32_t device;          /* CUDA device ordinal; -1 = current device */
   uint32_t chunk;          /* instances per internal HBM ring slot for host-buffer batches; 0 = default */
-  uint32_t flags;          /* reserved, must be 0 */
+  uint32_t flags;          /* 0 or B3W_FLAG_FUSED_CHECK */
 } b3w_config;
 
 /* What the WitnessCalculator constructor caches (witness_calculator.js:108-125). */
@@ -93,6 +97,29 @@ int b3w_witness_batch(b3w_ctx *ctx, const uint32_t *in, uint64_t n, uint8_t *out
  * be NULL for the default stream).  d_out must hold n*witness_size*32 bytes, 32-byte aligned. */
 int b3w_witness_batch_device(b3w_ctx *ctx, const uint32_t *d_in, uint64_t n, uint8_t *d_out, uint8_t *d_status,
                              uint32_t *d_pub, void *stream);
+
+/* As b3w_witness_batch_device, plus the FUSED R1CS satisfiability check: before the witness of an instance is expanded,
+ * every row of the circuit's constraint system (re-derived from the circom templates, the .r1cs files being absent from
+ * the reference tree) is evaluated on the values the expansion is about to write, straight from shared memory -- nothing
+ * is re-read from HBM.  d_status[i] = 0, B3W_CIRCOM_ASSERT or B3W_R1CS_VIOLATION; d_first_bad[i] (may be NULL) = the
+ * smallest violated row id or B3W_NO_ROW.  What the reference's tests do with circom_tester's expectPass
+ * (test/blake3_hash.test.ts:36) and bellpepper's enforce (rust_fold/src/utils.rs:78-85). */
+int b3w_witness_batch_device_checked(b3w_ctx *ctx, const uint32_t *d_in, uint64_t n, uint8_t *d_out, uint8_t *d_status,
+                                     uint32_t *d_pub, uint32_t *d_first_bad, void *stream);
+
+/* Stand-alone R1CS check of witnesses that are RESIDENT IN DEVICE MEMORY (re-reads them): sparse A.z * B.z - C.z over
+ * Fr, one warp per instance.  Available for the O1 builds (blake3_compression, NOVA_BN_O1), whose witness still holds
+ * every value the template-level rows mention; B3W_ERR_UNSUPPORTED for the O2 builds. */
+int b3w_r1cs_check_device(b3w_ctx *ctx, const uint8_t *d_wit, uint64_t n, uint8_t *d_status, uint32_t *d_first_bad,
+                          void *stream);
+
+/* rows / non-zero terms of the circuit's template-level constraint system in O1 form
+ * (blake3_compression: 24 544 rows = 23 376 quadratic + 1 168 linear; nova: 25 064) */
+int b3w_r1cs_info(uint32_t circuit, uint32_t *n_rows, uint32_t *n_terms);
+
+/* Test hook for the fused check: xor `xor_mask` into trace word `trace_word` of every instance after the trace phase
+ * of the *_checked kernels (B3W_NO_ROW disables it). */
+int b3w_debug_inject_fault(b3w_ctx *ctx, uint32_t trace_word, uint32_t xor_mask);
 
 /* Per-instance 64-bit checksum of witnesses resident in device memory (reads them back from HBM):
  *   sum_i = SUM over slots s, limbs j of  (limb64[s][j] + 1) * mix(4*s + j)   (mod 2^64),

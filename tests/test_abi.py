@@ -84,3 +84,19 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "oracle/" not in src.replace("tools/", ""), f
+
+
+def test_sass_streaming_stores_are_wide(built):
+    """ptxas 12.9 once turned a v8.b32 store with eight computed operands into a 32-bit STG inside a non-inlined
+    function (only limb 0 of nova's field slots reached memory).  Every no-allocate store in the library must be a
+    256-bit or 128-bit STG; the hot path must have the 256-bit form."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", pkg.lib_path()], capture_output=True, text=True, check=True).stdout
+    na = [l for l in sass.splitlines() if "STG.E.NA" in l]
+    assert len(na) > 10
+    assert all(".256" in l or ".128" in l for l in na), [l for l in na if ".256" not in l and ".128" not in l][:3]
+    assert sum(".256" in l for l in na) > 10

@@ -1,0 +1,121 @@
+"""GPU tests of the on-device R1CS satisfiability checks (stand-alone over HBM, and fused on the trace).
+The reference's own tests check constraints through circom_tester's expectPass (test/blake3_hash.test.ts:36,57);
+its .r1cs files are absent, so the rows are re-derived from the templates (tools/gen_r1cs.py): R1CS parity with the
+reference's files is NOT pinned, satisfaction is."""
+import numpy as np
+import pytest
+import torch
+
+import hot_proofs_blake3_circom_b200 as pkg
+from hot_proofs_blake3_circom_b200 import _lib
+from hot_proofs_blake3_circom_b200 import inputs as gen
+
+pytestmark = pytest.mark.gpu
+
+
+def run(wc, rows, checked=False):
+    n, ws = rows.shape[0], wc.witnessSize
+    d_in = torch.from_numpy(rows.view(np.int32)).cuda()
+    d_out = torch.zeros(n * ws * 32, dtype=torch.uint8, device="cuda")
+    d_st = torch.full((n,), 255, dtype=torch.uint8, device="cuda")
+    d_bad = torch.zeros(n, dtype=torch.int32, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    if checked:
+        wc.witness_batch_device_checked(d_in.data_ptr(), n, d_out.data_ptr(), d_st.data_ptr(), 0, d_bad.data_ptr(), s)
+    else:
+        wc.witness_batch_device(d_in.data_ptr(), n, d_out.data_ptr(), d_st.data_ptr(), 0, s)
+    torch.cuda.synchronize()
+    return d_out, d_st, d_bad
+
+
+def hbm_check(wc, d_out, n):
+    d_st = torch.full((n,), 255, dtype=torch.uint8, device="cuda")
+    d_bad = torch.zeros(n, dtype=torch.int32, device="cuda")
+    wc.r1cs_check_device(d_out.data_ptr(), n, d_st.data_ptr(), d_bad.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return d_st.cpu().numpy(), d_bad.cpu().numpy().view(np.uint32)
+
+
+def test_row_counts(built):
+    wc = pkg.builder("blake3_compression", lazy=True)
+    rows, terms = wc.r1cs_info()
+    # 24 544 template-level rows = 23 376 quadratic + 1 168 linear: the O1 constraint count of SURVEY 8(a) A6
+    assert (rows, terms) == (24544, 117760)
+    assert pkg.builder("blake3_nova", lazy=True).r1cs_info()[0] == 25064
+
+
+@pytest.mark.parametrize("name,rows_fn", [("blake3_compression", gen.splitmix_compression_inputs),
+                                          ("blake3_nova_o1", gen.splitmix_nova_inputs)])
+def test_hbm_check_accepts_valid_and_rejects_single_slot_corruption(built, name, rows_fn):
+    wc = pkg.builder(name, device=0)
+    n, ws = 512, wc.witnessSize
+    rows = rows_fn(n, first=1)
+    d_out, st, _ = run(wc, rows)
+    assert int(st.max()) == 0
+    status, bad = hbm_check(wc, d_out, n)
+    assert (status == 0).all() and (bad == _lib.B3W_NO_ROW).all()
+    # corrupt ONE slot per instance (a different slot in every instance): +1 on the low word
+    w = d_out.view(n, ws, 32)
+    rng = np.random.default_rng(7)
+    slots = rng.integers(0, ws, n)
+    slots[:4] = [0, 1, ws - 1, 17]
+    idx = torch.arange(n, device="cuda")
+    sl = torch.from_numpy(slots).cuda()
+    w[idx, sl, 0] += 1
+    status, bad = hbm_check(wc, d_out, n)
+    assert (status == _lib.B3W_R1CS_VIOLATION).all(), "undetected corruption in slots %s" % slots[status == 0][:10]
+    assert (bad != _lib.B3W_NO_ROW).all()
+    # a slot turned into a large field element is a violation too
+    w[idx, sl, 0] -= 1
+    w[0, 100, 31] = 0x10
+    status, _ = hbm_check(wc, d_out, n)
+    assert status[0] == _lib.B3W_R1CS_VIOLATION and (status[1:] == 0).all()
+    wc.close()
+
+
+def test_hbm_check_unsupported_for_o2_builds(built):
+    wc = pkg.builder("blake3_nova", device=0)
+    d = torch.zeros(wc.witnessSize * 32, dtype=torch.uint8, device="cuda")
+    with pytest.raises(pkg.B3WError) as e:
+        wc.r1cs_check_device(d.data_ptr(), 1)
+    assert e.value.code == _lib.B3W_ERR_UNSUPPORTED
+    wc.close()
+
+
+@pytest.mark.parametrize("name,rows_fn,word", [("blake3_compression", gen.splitmix_compression_inputs, 48 + 8 * 37 + 3),
+                                               ("blake3_nova", gen.splitmix_nova_inputs, 48 + 8 * 5 + 4),
+                                               ("blake3_nova_pasta", gen.splitmix_nova_inputs, 2 + 9),
+                                               ("blake3_nova_o1", gen.splitmix_nova_inputs, 30 + 2)])
+def test_fused_check_and_fault_injection(built, name, rows_fn, word):
+    wc = pkg.builder(name, device=0)
+    n = 2048
+    rows = rows_fn(n, first=3)
+    if name != "blake3_compression":
+        rows[5, 14] = rows[5, 12]                       # one instance that fails a circuit assert
+    plain, st0, _ = run(wc, rows)
+    fused, st1, bad1 = run(wc, rows, checked=True)
+    assert torch.equal(plain, fused)                    # the check does not disturb the witness
+    assert torch.equal(st0, st1)
+    assert int((st1 == 0).sum()) == (n if name == "blake3_compression" else n - 1)
+    assert bool((bad1.cpu().numpy().view(np.uint32) == _lib.B3W_NO_ROW).all())
+    # flip one bit of one trace word in every instance: every witness must be flagged
+    wc.inject_fault(word, 1 << 7)
+    _, st2, bad2 = run(wc, rows, checked=True)
+    ok = st1.cpu().numpy() == 0
+    assert (st2.cpu().numpy()[ok] == _lib.B3W_R1CS_VIOLATION).all()
+    assert (bad2.cpu().numpy().view(np.uint32)[ok] != _lib.B3W_NO_ROW).all()
+    wc.inject_fault()                                   # disable
+    _, st3, _ = run(wc, rows, checked=True)
+    assert torch.equal(st3, st1)
+    wc.close()
+
+
+def test_fused_check_flag_on_host_batches(built):
+    wc = pkg.builder("blake3_compression", device=0, fused_check=True)
+    rows = gen.lcg_compression_inputs(100)
+    res = wc.calculateWitnessBatch(rows, want_witness=False)
+    assert (res["status"] == 0).all()
+    wc.inject_fault(48 + 3, 1)
+    res = wc.calculateWitnessBatch(rows, want_witness=False)
+    assert (res["status"] == _lib.B3W_R1CS_VIOLATION).all()
+    wc.close()

@@ -78,6 +78,7 @@ class Builder:
         self.names = ["one"]
         self.vals = [const(1)]
         self.trace = {}          # trace index -> u32 value (sparse while building)
+        self.cons = []           # R1CS rows (A, B, C): dicts signal index -> integer coefficient; (A.z)*(B.z) = C.z
 
     # --- signal allocation ---
     def alloc(self, name, *dims):
@@ -136,6 +137,26 @@ class Comp:
     def S(self, idx, val):
         self.b.set(idx, val)
 
+    # --- constraints (signal level, before any circom simplification); signal 0 is the constant 1 ---
+    def c_mul(self, A, B, C):
+        self.b.cons.append((dict(A), dict(B), dict(C)))
+
+    def c_lin(self, terms):
+        """sum coeff*signal = 0"""
+        self.b.cons.append(({}, {}, dict(terms)))
+
+    def c_alias(self, a, b):
+        """a <== b between plain signals (lists are zipped)"""
+        if isinstance(a, list):
+            assert len(a) == len(b)
+            for x, y in zip(a, b):
+                self.c_alias(x, y)
+        else:
+            self.c_lin({a: 1, b: -1})
+
+    def c_bool(self, x):
+        self.c_mul({x: 1}, {0: 1, x: -1}, {})
+
     def G(self, idx):
         return self.b.get(idx)
 
@@ -151,6 +172,9 @@ class ToBits(Comp):
         self.n = n
         self.out = self.sig("out", n)
         self.inp = self.sig("inp")
+        for i in range(n):
+            self.c_bool(self.out[i])                                        # :149
+        self.c_lin({self.inp: 1, **{self.out[i]: -(1 << i) for i in range(n)}})   # :153
 
     def run(self, x):
         self.S(self.inp, x)
@@ -167,6 +191,7 @@ class XOR2(Comp):
     def __init__(self, b, name):
         super().__init__(b, name)
         self.out, self.x, self.y = self.sig("out"), self.sig("x"), self.sig("y")
+        self.c_mul({self.x: 2}, {self.y: 1}, {self.x: 1, self.y: 1, self.out: -1})   # out <== x + y - 2*x*y (:49)
 
     def run(self, x, y, o):
         self.S(self.x, x), self.S(self.y, y), self.S(self.out, o)
@@ -182,6 +207,11 @@ class XorWord2(Comp):
         self.out_bits = self.sig("out_bits", 32)
         self.subs(tb_x=lambda b, n: ToBits(b, n), tb_y=lambda b, n: ToBits(b, n),
                   xor=[(lambda b, n: XOR2(b, n))] * 32)
+        self.c_alias(self.tb_x.inp, self.x), self.c_alias(self.tb_y.inp, self.y)      # :65-66
+        for i in range(32):
+            self.c_alias(self.xor[i].x, self.tb_x.out[i]), self.c_alias(self.xor[i].y, self.tb_y.out[i])   # :72-73
+            self.c_alias(self.out_bits[i], self.xor[i].out)                          # :74
+        self.c_lin({self.out_word: 1, **{self.out_bits[i]: -(1 << i) for i in range(32)}})   # :79
 
     def run(self, x, y, t_out):
         self.S(self.x, x), self.S(self.y, y)
@@ -208,6 +238,15 @@ class Bits3x(Comp):
         self.u = self.sig("u")
         if extra == 2:
             self.v = self.sig("v")
+        for i in range(32):
+            self.c_bool(self.out_bits[i])
+        self.c_bool(self.u)
+        rec = {self.inp: 1, self.u: -(1 << 32), **{self.out_bits[i]: -(1 << i) for i in range(32)}}
+        if extra == 2:
+            self.c_bool(self.v)
+            rec[self.v] = -(1 << 33)
+        self.c_lin(rec)                                                             # inp === sum + ... (:176 / :201)
+        self.c_lin({self.out_word: 1, **{self.out_bits[i]: -(1 << i) for i in range(32)}})   # out_word <== sum
 
     def run(self, total, t_lo):
         """total = the integer sum; trace[t_lo] = low word, trace[t_lo+1] = carries."""
@@ -236,6 +275,11 @@ class RotXorBits(Comp):
         self.inp1_bits = self.sig("inp1_bits", 32)
         self.inp2_bits = self.sig("inp2_bits", 32)
         self.aux = self.sig("aux", 32)
+        for i in range(32):
+            self.c_mul({self.inp1_bits[i]: 2}, {self.inp2_bits[i]: 1},
+                       {self.inp1_bits[i]: 1, self.inp2_bits[i]: 1, self.aux[i]: -1})   # :37
+            self.c_alias(self.out_bits[i], self.aux[(i + R) % 32])                   # :42
+        self.c_lin({self.out_word: 1, **{self.out_bits[i]: -(1 << i) for i in range(32)}})   # :46
 
     def run(self, b1, b2, w_out):
         R = self.R
@@ -263,6 +307,11 @@ class RotXorWordBits(Comp):
         self.inp1_word = self.sig("inp1_word")
         self.inp2_bits = self.sig("inp2_bits", 32)
         self.subs(rx=lambda b, n: RotXorBits(b, n, R), tb=lambda b, n: ToBits(b, n))
+        self.c_alias(self.tb.inp, self.inp1_word)                                    # :61
+        self.c_alias(self.rx.inp1_bits, self.tb.out)                                # :62
+        self.c_alias(self.rx.inp2_bits, self.inp2_bits)                             # :63
+        self.c_alias(self.out_bits, self.rx.out_bits)                               # :64
+        self.c_alias(self.out_word, self.rx.out_word)                               # :65
 
     def run(self, word, bits2, w_out):
         self.S(self.inp1_word, word)
@@ -290,6 +339,18 @@ class HalfFunG(Comp):
         self.xy = self.sig("xy")
         self.subs(add1=lambda b, n: Bits3x(b, n, 2), add3=lambda b, n: Bits3x(b, n, 1),
                   rxor2=lambda b, n: RotXorWordBits(b, n, R1), rxor4=lambda b, n: RotXorWordBits(b, n, R2))
+        a, bb, c, d = idx4
+        for i in range(16):
+            if i not in idx4:
+                self.c_alias(self.out[i], self.v[i])                                 # :77-81
+        self.c_lin({self.add1.inp: 1, self.v[a]: -1, self.v[bb]: -1, self.xy: -1})  # :88
+        self.c_alias(self.rxor2.inp1_word, self.v[d])                               # :89
+        self.c_alias(self.rxor2.inp2_bits, self.add1.out_bits)                      # :90
+        self.c_lin({self.add3.inp: 1, self.v[c]: -1, self.rxor2.out_word: -1})      # :91
+        self.c_alias(self.rxor4.inp1_word, self.v[bb])                              # :92
+        self.c_alias(self.rxor4.inp2_bits, self.add3.out_bits)                      # :93
+        self.c_alias(self.out[a], self.add1.out_word), self.c_alias(self.out[d], self.rxor2.out_word)   # :95-96
+        self.c_alias(self.out[c], self.add3.out_word), self.c_alias(self.out[bb], self.rxor4.out_word)  # :97-98
 
     def run(self, v, xy, t_rec):
         """v: list of 16 V; xy: V; t_rec: trace index of this half's 8-word record."""
@@ -325,6 +386,9 @@ class MixFunG(Comp):
         self.inp = self.sig("inp", 16)
         self.x, self.y = self.sig("x"), self.sig("y")
         self.subs(half1=lambda b, n: HalfFunG(b, n, idx4, 16, 12), half2=lambda b, n: HalfFunG(b, n, idx4, 8, 7))
+        self.c_alias(self.half1.v, self.inp), self.c_alias(self.half1.xy, self.x)    # :115-116
+        self.c_alias(self.half2.v, self.half1.out), self.c_alias(self.half2.xy, self.y)   # :119-120
+        self.c_alias(self.out, self.half2.out)                                      # :121
 
     def run(self, inp, x, y, t_rec):
         for i in range(16):
@@ -352,6 +416,11 @@ class SingleRound(Comp):
         self.msg = self.sig("msg", 16)
         self.vs = self.sig("vs", 9, 16)
         self.subs(GS=[(lambda b, n, q=q: MixFunG(b, n, q)) for q in G_IDX])
+        self.c_alias(self.vs[0], self.inp)                                           # :141
+        for g in range(8):
+            self.c_alias(self.GS[g].x, self.msg[2 * g]), self.c_alias(self.GS[g].y, self.msg[2 * g + 1])   # :145-153
+            self.c_alias(self.GS[g].inp, self.vs[g]), self.c_alias(self.vs[g + 1], self.GS[g].out)         # :156-157
+        self.c_alias(self.out, self.vs[8])                                          # :160
 
     def run(self, inp, msg, t_rec):
         for i in range(16):
@@ -375,6 +444,8 @@ class Blake3Permute(Comp):
         super().__init__(b, name)
         self.out = self.sig("out", 16)
         self.inp = self.sig("inp", 16)
+        for j in range(16):
+            self.c_alias(self.out[j], self.inp[SIGMA[j]])                            # :24
 
     def run(self, inp):
         out = [inp[SIGMA[j]] for j in range(16)]
@@ -389,6 +460,8 @@ class IVc(Comp):
     def __init__(self, b, name):
         super().__init__(b, name)
         self.out = self.sig("out", 8)
+        for j in range(8):
+            self.c_lin({self.out[j]: 1, 0: -IV[j]})                                  # :23
 
     def run(self):
         o = [const(x) for x in IV]
@@ -408,6 +481,19 @@ class Blake3Compression(Comp):
         self.init = self.sig("init", 16)
         self.subs(iv=lambda b, n: IVc(b, n), outXor=[lambda b, n: XorWord2(b, n)] * 16,
                   permuters=[lambda b, n: Blake3Permute(b, n)] * 6, rounds=[lambda b, n: SingleRound(b, n)] * 7)
+        self.c_alias(self.init[0:8], self.h)                                         # :184
+        self.c_alias(self.init[8:12], self.iv.out[0:4])                             # :185
+        self.c_alias(self.init[12:14], self.t)                                      # :186
+        self.c_alias(self.init[14], self.bb), self.c_alias(self.init[15], self.d)   # :187
+        self.c_alias(self.rounds[0].msg, self.m), self.c_alias(self.rounds[0].inp, self.init)   # :194-195
+        for i in range(6):
+            self.c_alias(self.permuters[i].inp, self.m if i == 0 else self.permuters[i - 1].out)   # :203-207
+            self.c_alias(self.rounds[i + 1].msg, self.permuters[i].out)              # :208
+            self.c_alias(self.rounds[i + 1].inp, self.rounds[i].out)                 # :209
+        for i in range(16):
+            self.c_alias(self.outXor[i].x, self.rounds[6].out[i])                    # :217, :224
+            self.c_alias(self.outXor[i].y, self.rounds[6].out[i + 8] if i < 8 else self.h[i - 8])   # :218, :226
+            self.c_alias(self.out[i], self.outXor[i].out_word)                       # :219, :227
 
     def run(self, h, m, t, bb, d):
         """h[8], m[16], t[2], bb, d: V (their sources decided by the caller)."""
@@ -533,6 +619,8 @@ class IsZero(Comp):
     def __init__(self, b, name):
         super().__init__(b, name)
         self.out, self.inp, self.inv = self.sig("out"), self.sig("in"), self.sig("inv")
+        self.c_mul({self.inp: 1}, {self.inv: 1}, {0: 1, self.out: -1})               # out <== -in*inv + 1
+        self.c_mul({self.inp: 1}, {self.out: 1}, {})                                # in*out === 0
 
     def run(self, x, out):
         """x: S-kind value; out: V for the result word/bit (caller decides where it lives)."""
@@ -550,6 +638,8 @@ class IsEqual(Comp):
         super().__init__(b, name)
         self.out, self.inp = self.sig("out"), self.sig("in", 2)
         self.subs(isz=lambda b, n: IsZero(b, n))
+        self.c_lin({self.isz.inp: 1, self.inp[1]: -1, self.inp[0]: 1})               # isz.in <== in[1] - in[0]
+        self.c_alias(self.out, self.isz.out)
 
     def run(self, in0, in1, diff, out):
         self.S(self.inp[0], in0), self.S(self.inp[1], in1)
@@ -566,6 +656,9 @@ class Num2Bits(Comp):
         super().__init__(b, name)
         self.n = n
         self.out, self.inp = self.sig("out", n), self.sig("in")
+        for i in range(n):
+            self.c_bool(self.out[i])
+        self.c_lin({self.inp: 1, **{self.out[i]: -(1 << i) for i in range(n)}})
 
     def run(self, x):
         self.S(self.inp, x)
@@ -586,6 +679,8 @@ class LessThan(Comp):
         self.n = n
         self.out, self.inp = self.sig("out"), self.sig("in", 2)
         self.subs(n2b=lambda b, nm: Num2Bits(b, nm, n + 1))
+        self.c_lin({self.n2b.inp: 1, self.inp[0]: -1, 0: -(1 << n), self.inp[1]: 1})   # n2b.in <== in[0] + (1<<n) - in[1]
+        self.c_lin({self.out: 1, 0: -1, self.n2b.out[n]: 1})                        # out <== 1 - n2b.out[n]
 
     def run(self, in0, in1, vword, out):
         self.S(self.inp[0], in0), self.S(self.inp[1], in1)
@@ -603,6 +698,9 @@ class GreaterEqThan(Comp):
         super().__init__(b, name)
         self.out, self.inp = self.sig("out"), self.sig("in", 2)
         self.subs(lt=lambda b, nm: LessThan(b, nm, n))
+        self.c_alias(self.lt.inp[0], self.inp[1])
+        self.c_lin({self.lt.inp[1]: 1, self.inp[0]: -1, 0: -1})                      # lt.in[1] <== in[0] + 1
+        self.c_alias(self.out, self.lt.out)
 
     def run(self, in0, in1, in0p1, vword, out):
         self.S(self.inp[0], in0), self.S(self.inp[1], in1)
@@ -613,11 +711,15 @@ class GreaterEqThan(Comp):
 
 
 class Gate2(Comp):
-    """circomlib gates.circom AND / OR: out; a; b."""
+    """circomlib gates.circom AND / OR: out; a; b.   AND: out <== a*b;  OR: out <== a + b - a*b"""
 
-    def __init__(self, b, name):
+    def __init__(self, b, name, kind="AND"):
         super().__init__(b, name)
         self.out, self.a, self.bb = self.sig("out"), self.sig("a"), self.sig("b")
+        if kind == "AND":
+            self.c_mul({self.a: 1}, {self.bb: 1}, {self.out: 1})
+        else:
+            self.c_mul({self.a: 1}, {self.bb: 1}, {self.a: 1, self.bb: 1, self.out: -1})
 
     def run(self, a, b, out):
         self.S(self.a, a), self.S(self.bb, b), self.S(self.out, out)
@@ -630,6 +732,7 @@ class NOT(Comp):
     def __init__(self, b, name):
         super().__init__(b, name)
         self.out, self.inp = self.sig("out"), self.sig("in")
+        self.c_lin({self.out: 1, 0: -1, self.inp: 1})                               # out <== 1 + in - 2*in
 
     def run(self, x, out):
         assert out.v == 1 - x.v
@@ -646,6 +749,13 @@ class CheckDepth(Comp):
         self.depth, self.leaf_depth = self.sig("depth"), self.sig("leaf_depth")
         self.subs(check_root=lambda b, n: IsEqual(b, n), check_parent=lambda b, n: LessThan(b, n, 8),
                   exceed_depth=lambda b, n: GreaterEqThan(b, n, 8))
+        self.c_alias(self.check_root.inp[0], self.depth), self.c_lin({self.check_root.inp[1]: 1})   # :20-21
+        self.c_alias(self.is_root, self.check_root.out)                             # :23
+        self.c_alias(self.check_parent.inp[0], self.depth)                          # :32
+        self.c_lin({self.check_parent.inp[1]: 1, self.leaf_depth: -1, 0: 1})        # :33
+        self.c_alias(self.is_parent, self.check_parent.out)                         # :38
+        self.c_alias(self.exceed_depth.inp[0], self.depth), self.c_alias(self.exceed_depth.inp[1], self.leaf_depth)   # :42-43
+        self.c_lin({self.exceed_depth.out: 1})                                      # exceed_depth.out === 0 (:44)
 
     def run(self, depth, leaf_depth):
         b = self.b
@@ -662,9 +772,12 @@ class CheckDepth(Comp):
         is_parent = b.tw(NV["IS_PARENT"], 1 - ((v1 >> 8) & 1))
         self.check_parent.run(depth, b.tw(NV["LDM1"], leaf_depth.v - 1), V1, is_parent)           # :31-33
         self.S(self.is_parent, is_parent)                                                        # :38
-        exceed = b.tw(NV["EXCEED"], 1 - ((v2 >> 8) & 1))
-        self.exceed_depth.run(depth, leaf_depth, b.tw(NV["DP1"], depth.v + 1), V2, exceed)        # :41-43
-        self.ok = self.ok and exceed.v == 0                                                      # :44
+        b.tw(NV["EXCEED"], 1 - ((v2 >> 8) & 1))
+        self.ok = self.ok and ((v2 >> 8) & 1) == 1                                               # exceed_depth.out === 0 (:44)
+        if not self.ok:
+            return None, None
+        # the constraint pins the signal to the constant 0 (circom drops it from the witness), so it is modelled as one
+        self.exceed_depth.run(depth, leaf_depth, b.tw(NV["DP1"], depth.v + 1), V2, const(0))      # :41-43
         return is_root, is_parent
 
 
@@ -678,6 +791,14 @@ class DownLeftPath(Comp):
         self.is_parent, self.total_depth = self.sig("is_parent"), self.sig("total_depth")
         self.bit_at_depth = self.sig("bit_at_depth", 65)
         self.subs(eqs=[lambda b, n: IsEqual(b, n)] * 64, n2b=lambda b, n: Num2Bits(b, n, 65))
+        self.c_alias(self.n2b.inp, self.leaf_idx)                                    # :59
+        for i in range(64):
+            self.c_alias(self.eqs[i].inp[0], self.depth)                             # :64, :69
+            self.c_lin({self.eqs[i].inp[1]: 1, self.total_depth: -1, 0: i + 2})
+            prev = {self.bit_at_depth[i - 1]: -1} if i else {}
+            self.c_mul({0: 1, self.n2b.out[i]: -1}, {self.eqs[i].out: 1}, {self.bit_at_depth[i]: 1, **prev})   # :65, :70
+        self.c_mul({self.is_parent: 1}, {self.bit_at_depth[63]: 1}, {self.out: 1, 0: -1, self.is_parent: 1})   # :79
+        self.c_bool(self.out)                                                       # :81
 
     def run(self, depth, leaf_idx, is_parent, total_depth):
         b = self.b
@@ -717,6 +838,18 @@ class FinalM(Comp):
         self.total_depth, self.chunk_idx = self.sig("total_depth"), self.sig("chunk_idx")
         self.m_is_parent, self.tmp_down, self.tmp_is_par = self.sig("m_is_parent", 16), self.sig("tmp_down", 16), self.sig("tmp_is_par", 16)
         self.subs(down_left_path=lambda b, n: DownLeftPath(b, n))
+        dl = self.down_left_path
+        self.c_alias(dl.depth, self.depth), self.c_alias(dl.leaf_idx, self.chunk_idx)   # :98-99
+        self.c_alias(dl.is_parent, self.is_parent), self.c_alias(dl.total_depth, self.total_depth)   # :100-101
+        for i in range(16):
+            if i < 8:
+                self.c_mul({self.h[i]: 1}, {dl.out: 1}, {self.tmp_down[i]: 1})                            # :109
+                self.c_mul({self.m[i]: 1}, {0: 1, dl.out: -1}, {self.m_is_parent[i]: 1, self.tmp_down[i]: -1})   # :111
+            else:
+                self.c_mul({self.h[i - 8]: 1}, {0: 1, dl.out: -1}, {self.tmp_down[i]: 1})                  # :113
+                self.c_mul({self.m[i - 8]: 1}, {dl.out: 1}, {self.m_is_parent[i]: 1, self.tmp_down[i]: -1})   # :114
+            self.c_mul({self.m_is_parent[i]: 1}, {self.is_parent: 1}, {self.tmp_is_par[i]: 1})            # :116
+            self.c_mul({self.m[i]: 1}, {0: 1, self.is_parent: -1}, {self.out_m[i]: 1, self.tmp_is_par[i]: -1})   # :117
 
     def run(self, h, m, is_parent, depth, total_depth, chunk_idx):
         b = self.b
@@ -758,8 +891,20 @@ class GetFlag(Comp):
         self.use_root_flag = self.sig("use_root_flag")
         self.subs(not_root=lambda b, n: NOT(b, n), not_parent=lambda b, n: NOT(b, n),
                   check_block_counts=[lambda b, n: IsEqual(b, n)] * 2,
-                  first_block_flag_set=lambda b, n: Gate2(b, n), last_block_flag_set=lambda b, n: Gate2(b, n),
-                  use_root_flag_tmp=lambda b, n: Gate2(b, n))
+                  first_block_flag_set=lambda b, n: Gate2(b, n, "AND"), last_block_flag_set=lambda b, n: Gate2(b, n, "AND"),
+                  use_root_flag_tmp=lambda b, n: Gate2(b, n, "OR"))
+        cb = self.check_block_counts
+        self.c_alias(self.not_root.inp, self.is_root), self.c_alias(self.not_parent.inp, self.is_parent)   # :136-137
+        self.c_alias(cb[0].inp[0], self.block_count), self.c_lin({cb[0].inp[1]: 1})                       # :141-142
+        self.c_alias(cb[1].inp[0], self.block_count)                                                     # :144
+        self.c_lin({cb[1].inp[1]: 1, self.n_blocks: -1, 0: 1})                                           # :145
+        self.c_mul({cb[1].out: 1}, {self.not_parent.out: 1}, {self.is_last_block: 1})                    # :148
+        self.c_alias(self.first_block_flag_set.a, cb[0].out), self.c_alias(self.first_block_flag_set.bb, self.not_parent.out)   # :151
+        self.c_alias(self.last_block_flag_set.a, cb[1].out), self.c_alias(self.last_block_flag_set.bb, self.not_parent.out)     # :152
+        self.c_alias(self.use_root_flag_tmp.a, self.is_parent), self.c_alias(self.use_root_flag_tmp.bb, cb[1].out)             # :157
+        self.c_mul({self.use_root_flag_tmp.out: 1}, {self.is_root: 1}, {self.use_root_flag: 1})          # :158
+        self.c_lin({self.out: 1, self.first_block_flag_set.out: -1, self.last_block_flag_set.out: -2,
+                    self.use_root_flag: -8, self.is_parent: -4})                                         # :161-165 (D_FLAGS = 0)
 
     def run(self, is_parent, is_root, block_count, n_blocks):
         b = self.b
@@ -798,9 +943,32 @@ class Blake3Nova(Comp):
         self.leaf_depth, self.total_depth, self.depth = s("leaf_depth"), s("total_depth"), s("depth")
         self.m, self.bb = s("m", 16), s("b")
         self.tmpIV, self.h_compression, self.decr_depth = s("tmpIV", 8), s("h_compression", 8), s("decr_depth")
-        self.subs(blake3Compression=lambda b, n: Blake3Compression(b, n), check_decr_depth=lambda b, n: Gate2(b, n),
+        self.subs(blake3Compression=lambda b, n: Blake3Compression(b, n), check_decr_depth=lambda b, n: Gate2(b, n, "OR"),
                   check_depth=lambda b, n: CheckDepth(b, n), comp_d=lambda b, n: GetFlag(b, n),
                   final_m=lambda b, n: FinalM(b, n), iv=lambda b, n: IVc(b, n))
+        cd, fl, fm, bc = self.check_depth, self.comp_d, self.final_m, self.blake3Compression
+        self.c_alias(cd.depth, self.depth), self.c_alias(cd.leaf_depth, self.leaf_depth)                 # :206-207
+        self.c_alias(fl.is_parent, cd.is_parent), self.c_alias(fl.is_root, cd.is_root)                   # :211-212
+        self.c_alias(fl.block_count, self.block_count), self.c_alias(fl.n_blocks, self.n_blocks)         # :213-214
+        self.c_alias(fm.h, self.h), self.c_alias(fm.m, self.m), self.c_alias(fm.is_parent, cd.is_parent)  # :222-224
+        self.c_alias(fm.depth, self.depth), self.c_alias(fm.total_depth, self.total_depth)               # :225-226
+        self.c_lin({fm.chunk_idx: 1, self.chunk_idx_low: -1, self.chunk_idx_high: -(1 << 32)})           # :227
+        for i in range(8):
+            self.c_mul({self.iv.out[i]: 1}, {cd.is_parent: 1}, {self.tmpIV[i]: 1})                        # :231
+            self.c_mul({self.h[i]: 1}, {0: 1, cd.is_parent: -1}, {self.h_compression[i]: 1, self.tmpIV[i]: -1})   # :232
+            self.c_alias(self.h_out[i], bc.out[i])                                                       # :248
+        self.c_alias(bc.m, fm.out_m), self.c_alias(bc.h, self.h_compression)                             # :236-237
+        self.c_alias(bc.d, fl.out), self.c_alias(bc.bb, self.bb)                                         # :238-239
+        self.c_mul({self.chunk_idx_high: 1}, {0: 1, cd.is_parent: -1}, {bc.t[1]: 1})                      # :244
+        self.c_mul({self.chunk_idx_low: 1}, {0: 1, cd.is_parent: -1}, {bc.t[0]: 1})                       # :245
+        self.c_lin({self.block_count_out: 1, self.block_count: -1, 0: -1, cd.is_parent: 1})              # :251
+        self.c_alias(self.n_blocks_out, self.n_blocks)                                                   # :252
+        self.c_alias(self.check_decr_depth.a, fl.is_last_block), self.c_alias(self.check_decr_depth.bb, cd.is_parent)   # :255-256
+        self.c_mul({self.check_decr_depth.out: 1}, {0: 1, cd.is_root: -1}, {self.decr_depth: 1})          # :258
+        self.c_bool(self.decr_depth)                                                                     # :259
+        self.c_lin({self.depth_out: 1, self.depth: -1, self.decr_depth: 1})                              # :262
+        self.c_alias(self.total_depth_out, self.total_depth), self.c_alias(self.chunk_idx_low_out, self.chunk_idx_low)   # :263-264
+        self.c_alias(self.chunk_idx_high_out, self.chunk_idx_high), self.c_alias(self.leaf_depth_out, self.leaf_depth)   # :265-266
 
     def run(self, w):
         """w: the 32 input words as V (trace words NV_IN..)."""
@@ -832,8 +1000,8 @@ class Blake3Nova(Comp):
             hc.append(x)
         t1 = b.tw(TR_IN + 25, high.v * (1 - is_parent.v))                                         # :244
         t0 = b.tw(TR_IN + 24, low.v * (1 - is_parent.v))                                          # :245
-        bw = b.tw(TR_IN + 26, bb.v)
-        out = self.blake3Compression.run(hc, out_m, [t0, t1], bw, d)                              # :235-245
+        b.tw(TR_IN + 26, bb.v)          # the kernel copies b next to the other compression inputs; the signal IS main.b
+        out = self.blake3Compression.run(hc, out_m, [t0, t1], bb, d)                              # :235-245
         for i in range(8):
             self.S(self.h_out[i], out[i])                                                        # :248
         bco = block_count.v + (1 - is_parent.v)                                                  # :251
