@@ -16,6 +16,8 @@
 #include <string.h>
 #include <stdlib.h>
 #include <new>
+#include <vector>
+#include <algorithm>
 
 #include "../../include/blake3wit.h"
 #include "trace_layout.h"
@@ -377,6 +379,140 @@ __global__ void __launch_bounds__(256) k_checksum(const uint64_t *__restrict__ w
 #pragma unroll
     for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) sums[i] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Chained-chunk driver (BASELINE config 3): the step schedule of the reference's Nova driver
+// (rust_fold/src/main.rs:71-94,130-142,166-171 and rust_fold/src/blake3_circuit.rs:160-290), batched.
+// Step i+1 consumes step i's outputs (h, block_count, depth), but those are plain BLAKE3 chaining values, so the
+// whole chain of every chunk is pre-computed with native u32 compressions and all step witnesses are then
+// generated independently by k_blake3_nova_witness.  The sibling chaining values that the reference gets from
+// bao slice extraction (rust_fold/src/blake3_hash.rs:17-93) come from a BLAKE3 tree hashed on the device.
+// ------------------------------------------------------------------------------------------------
+#define B3_CHUNK_START 1u
+#define B3_CHUNK_END 2u
+#define B3_PARENT 4u
+#define B3_ROOT 8u
+
+__device__ __forceinline__ void b3_g(uint32_t *v, int a, int b, int c, int d, uint32_t x, uint32_t y) {
+  v[a] = v[a] + v[b] + x; v[d] = rotr32(v[d] ^ v[a], 16);
+  v[c] = v[c] + v[d];     v[b] = rotr32(v[b] ^ v[c], 12);
+  v[a] = v[a] + v[b] + y; v[d] = rotr32(v[d] ^ v[a], 8);
+  v[c] = v[c] + v[d];     v[b] = rotr32(v[b] ^ v[c], 7);
+}
+// plain BLAKE3 compression, first 8 output words (the chaining value)
+__device__ void b3_compress_cv(const uint32_t h[8], const uint32_t m[16], uint32_t t0, uint32_t t1, uint32_t blen,
+                               uint32_t flags, uint32_t out[8]) {
+  uint32_t v[16] = {h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7],
+                    0x6A09E667u, 0xBB67AE85u, 0x3C6EF372u, 0xA54FF53Au, t0, t1, blen, flags};
+#pragma unroll 1
+  for (int r = 0; r < 7; r++) {
+    const uint8_t *s = MSG_SCHED[r];
+    b3_g(v, 0, 4, 8, 12, m[s[0]], m[s[1]]);   b3_g(v, 1, 5, 9, 13, m[s[2]], m[s[3]]);
+    b3_g(v, 2, 6, 10, 14, m[s[4]], m[s[5]]);  b3_g(v, 3, 7, 11, 15, m[s[6]], m[s[7]]);
+    b3_g(v, 0, 5, 10, 15, m[s[8]], m[s[9]]);  b3_g(v, 1, 6, 11, 12, m[s[10]], m[s[11]]);
+    b3_g(v, 2, 7, 8, 13, m[s[12]], m[s[13]]); b3_g(v, 3, 4, 9, 14, m[s[14]], m[s[15]]);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) out[i] = v[i] ^ v[i + 8];
+}
+__constant__ uint32_t B3_IV[8] = {0x6A09E667u, 0xBB67AE85u, 0x3C6EF372u, 0xA54FF53Au, 0x510E527Fu, 0x9B05688Cu, 0x1F83D9ABu, 0x5BE0CD19u};
+
+// bytes [off, off+64) of the (zero padded) input as 16 little-endian words + the count of real bytes
+__device__ __forceinline__ uint32_t load_block(const uint8_t *data, uint64_t len, uint64_t off, uint32_t m[16]) {
+  const uint32_t *w = reinterpret_cast<const uint32_t *>(data + off);     // the device copy is padded to 64 B
+#pragma unroll
+  for (int i = 0; i < 16; i++) m[i] = w[i];
+  return off >= len ? 0u : (uint32_t)(len - off < 64 ? len - off : 64);
+}
+__device__ __forceinline__ uint32_t chunk_blocks(uint64_t len, uint64_t c) {
+  const uint64_t cb = len - c * 1024 < 1024 ? len - c * 1024 : 1024;   // bytes in chunk c
+  const uint32_t nb = (uint32_t)((cb + 63) / 64);                          // utils.rs:112-114
+  return nb ? nb : 1;                                                      // the empty input is one empty block
+}
+
+// chunk chaining values: cv[c] for c < n_chunks (one thread per chunk)
+__global__ void k_chunk_cvs(const uint8_t *__restrict__ data, uint64_t len, uint64_t n_chunks, uint32_t *__restrict__ cv) {
+  const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_chunks) return;
+  uint32_t h[8], m[16];
+#pragma unroll
+  for (int i = 0; i < 8; i++) h[i] = B3_IV[i];
+  const uint32_t nb = chunk_blocks(len, c);
+  for (uint32_t k = 0; k < nb; k++) {
+    const uint32_t bl = load_block(data, len, c * 1024 + 64ull * k, m);
+    b3_compress_cv(h, m, (uint32_t)c, (uint32_t)(c >> 32), bl, (k == 0 ? B3_CHUNK_START : 0u) | (k == nb - 1 ? B3_CHUNK_END : 0u), h);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) cv[c * 8 + i] = h[i];
+}
+// one tree level: parent j = compress(IV, cv[left] || cv[right], PARENT)
+__global__ void k_parent_cvs(const uint32_t *__restrict__ nodes /* [first..first+count) x {left, right} */, uint32_t first,
+                             uint32_t count, uint64_t n_chunks, uint32_t *__restrict__ cv) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= count) return;
+  const uint32_t l = nodes[2 * (first + j)], r = nodes[2 * (first + j) + 1];
+  uint32_t m[16], h[8], o[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { m[i] = cv[(uint64_t)l * 8 + i]; m[8 + i] = cv[(uint64_t)r * 8 + i]; h[i] = B3_IV[i]; }
+  b3_compress_cv(h, m, 0, 0, 64, B3_PARENT, o);
+#pragma unroll
+  for (int i = 0; i < 8; i++) cv[(n_chunks + first + j) * 8 + i] = o[i];
+}
+// Step rows of every chunk (one thread per chunk): blake3_circuit.rs format_input() (:197-289) applied along
+// update_for_step() (:185-195), with z0 from main.rs:130-142 and z_{i+1} = the circuit's outputs.
+__global__ void k_chain_rows(const uint8_t *__restrict__ data, uint64_t len, uint64_t n_chunks,
+                             const uint32_t *__restrict__ cv, const uint32_t *__restrict__ path /* [chunk][max_depth] sibling refs */,
+                             const uint32_t *__restrict__ depth_of /* parents above chunk c */, uint32_t max_depth,
+                             const uint64_t *__restrict__ step_off, uint32_t *__restrict__ rows) {
+  const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_chunks) return;
+  const uint32_t n_par = depth_of[c];                 // parent_path.len()
+  const uint32_t total_depth = n_par + 1;             // = leaf_depth (blake3_circuit.rs:169, main.rs:71)
+  const uint32_t nb = chunk_blocks(len, c);
+  uint32_t h[8], m[16];
+#pragma unroll
+  for (int i = 0; i < 8; i++) h[i] = B3_IV[i];
+  uint32_t block_count = 0, depth = total_depth - 1;
+  uint32_t *row = rows + step_off[c] * 32;
+  const uint32_t steps = nb + total_depth - 1;        // main.rs:94
+  for (uint32_t st = 0; st < steps; st++, row += 32) {
+    const bool leaf = st < nb;
+    uint32_t bl;
+    if (leaf) {
+      bl = load_block(data, len, c * 1024 + 64ull * st, m);                 // :207-224
+    } else {
+      const uint32_t sib = path[c * max_depth + depth];                    // parent_path[current_depth] (:234)
+#pragma unroll
+      for (int i = 0; i < 8; i++) { m[i] = cv[(uint64_t)sib * 8 + i]; m[8 + i] = 0; }
+      bl = 64;                                                             // :229
+    }
+    row[0] = nb; row[1] = block_count;
+#pragma unroll
+    for (int i = 0; i < 8; i++) row[2 + i] = h[i];
+    row[10] = (uint32_t)c; row[11] = (uint32_t)(c >> 32);
+    row[12] = total_depth; row[13] = total_depth; row[14] = depth;
+#pragma unroll
+    for (int i = 0; i < 16; i++) row[15 + i] = m[i];
+    row[31] = bl;
+    // what the circuit will output (circuits/blake3_nova.circom:122-167, 229-266), natively
+    const bool is_parent = depth + 1 < total_depth, is_root = depth == 0;
+    const bool last = block_count + 1 == nb;
+    uint32_t mm[16], hh[8];
+    uint32_t flags;
+    if (is_parent) {
+      const bool left = ((c >> (total_depth - 2 - depth)) & 1) == 0;       // Blake3GetDownLeftPath (:47-84)
+#pragma unroll
+      for (int i = 0; i < 8; i++) { mm[i] = left ? h[i] : m[i]; mm[8 + i] = left ? m[i] : h[i]; hh[i] = B3_IV[i]; }
+      flags = B3_PARENT | (is_root ? B3_ROOT : 0u);
+      b3_compress_cv(hh, mm, 0, 0, bl, flags, h);
+    } else {
+      flags = (block_count == 0 ? B3_CHUNK_START : 0u) | (last ? B3_CHUNK_END : 0u) | (last && is_root ? B3_ROOT : 0u);
+      b3_compress_cv(h, m, (uint32_t)c, (uint32_t)(c >> 32), bl, flags, h);
+      block_count += 1;
+    }
+    if ((is_parent || last) && !is_root) depth -= 1;
   }
 }
 
@@ -808,6 +944,175 @@ extern "C" int b3w_calib_fill(b3w_ctx *c, uint8_t *d_buf, uint64_t bytes, void *
   k_fill<<<c->sm_count * 8, 256, 0, (cudaStream_t)stream>>>(d_buf, bytes / 32);
   CK(cudaGetLastError());
   return B3W_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// chained-chunk driver, host side
+// ------------------------------------------------------------------------------------------------
+static uint64_t chunk_count_of(uint64_t len) { return len == 0 ? 1 : (len + 1023) / 1024; }
+static uint32_t blocks_of_chunk(uint64_t len, uint64_t c) {
+  uint64_t cb = len - c * 1024 < 1024 ? len - c * 1024 : 1024;
+  uint32_t nb = (uint32_t)((cb + 63) / 64);
+  return nb ? nb : 1;
+}
+
+struct tree_plan {
+  std::vector<uint32_t> nodes;        // parents in creation (post-) order: {left ref, right ref}; ref < n_chunks = chunk
+  std::vector<uint32_t> height;       // per parent
+  std::vector<uint32_t> depth_of;     // per chunk: number of parents above it
+  std::vector<uint32_t> path;         // per chunk: sibling refs, root first, max_depth entries
+  uint32_t max_depth = 1;
+  uint32_t root = 0;
+};
+// BLAKE3 tree shape: the left subtree takes the largest power of two of chunks that leaves >= 1 on the right
+static uint32_t build_tree(tree_plan &t, uint64_t first, uint64_t n, uint64_t n_chunks, uint32_t &h_out) {
+  if (n == 1) { h_out = 0; return (uint32_t)first; }
+  uint64_t left = 1;
+  while (left * 2 < n) left *= 2;
+  uint32_t hl, hr;
+  uint32_t l = build_tree(t, first, left, n_chunks, hl), r = build_tree(t, first + left, n - left, n_chunks, hr);
+  t.nodes.push_back(l);
+  t.nodes.push_back(r);
+  h_out = (hl > hr ? hl : hr) + 1;
+  t.height.push_back(h_out);
+  return (uint32_t)(n_chunks + t.height.size() - 1);
+}
+static void fill_paths(tree_plan &t, uint32_t ref, uint64_t n_chunks, std::vector<uint32_t> &stack) {
+  if (ref < n_chunks) {
+    t.depth_of[ref] = (uint32_t)stack.size();
+    for (size_t i = 0; i < stack.size(); i++) t.path[(size_t)ref * t.max_depth + i] = stack[i];
+    return;
+  }
+  uint32_t j = ref - (uint32_t)n_chunks, l = t.nodes[2 * j], r = t.nodes[2 * j + 1];
+  stack.push_back(r); fill_paths(t, l, n_chunks, stack); stack.pop_back();
+  stack.push_back(l); fill_paths(t, r, n_chunks, stack); stack.pop_back();
+}
+
+extern "C" int b3w_nova_chain_size(uint64_t len, uint64_t *n_chunks, uint64_t *total_steps) {
+  const uint64_t nc = chunk_count_of(len);
+  if (nc > 0x7FFFFFFFull) return fail(B3W_ERR_INVALID, "input too large for the chain driver (%llu chunks)", (unsigned long long)nc);
+  tree_plan t;
+  uint32_t h;
+  t.root = build_tree(t, 0, nc, nc, h);
+  t.max_depth = h ? h : 1;
+  t.depth_of.assign(nc, 0);
+  t.path.assign((size_t)nc * t.max_depth, 0);
+  std::vector<uint32_t> st;
+  fill_paths(t, t.root, nc, st);
+  uint64_t steps = 0;
+  for (uint64_t c = 0; c < nc; c++) steps += blocks_of_chunk(len, c) + t.depth_of[c];
+  if (n_chunks) *n_chunks = nc;
+  if (total_steps) *total_steps = steps;
+  return B3W_OK;
+}
+
+extern "C" int b3w_nova_chain(b3w_ctx *c, const uint8_t *data, uint64_t len, uint8_t *out, uint8_t *status, uint32_t *pub,
+                              uint32_t *rows_out, uint64_t *step_off_out, uint8_t root_out[32]) {
+  if (!c || (!data && len)) return fail(B3W_ERR_INVALID, "b3w_nova_chain: null argument");
+  if (!c->def->nova) return fail(B3W_ERR_INVALID, "b3w_nova_chain needs a nova circuit context");
+  CK(cudaSetDevice(c->device));
+  const uint64_t nc = chunk_count_of(len);
+  if (nc > 0x7FFFFFFFull) return fail(B3W_ERR_INVALID, "input too large for the chain driver");
+  tree_plan t;
+  uint32_t hgt;
+  t.root = build_tree(t, 0, nc, nc, hgt);
+  t.max_depth = hgt ? hgt : 1;
+  t.depth_of.assign(nc, 0);
+  t.path.assign((size_t)nc * t.max_depth, 0);
+  { std::vector<uint32_t> st; fill_paths(t, t.root, nc, st); }
+  std::vector<uint64_t> step_off(nc + 1, 0);
+  for (uint64_t k = 0; k < nc; k++) step_off[k + 1] = step_off[k] + blocks_of_chunk(len, k) + t.depth_of[k];
+  const uint64_t total = step_off[nc];
+  const size_t n_par = t.height.size();
+  // parents ordered by height so that one launch handles one level
+  std::vector<uint32_t> order(n_par), remap(n_par);
+  for (size_t i = 0; i < n_par; i++) order[i] = (uint32_t)i;
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return t.height[a] < t.height[b]; });
+  for (size_t i = 0; i < n_par; i++) remap[order[i]] = (uint32_t)i;
+  auto fix = [&](uint32_t ref) { return ref < nc ? ref : (uint32_t)(nc + remap[ref - nc]); };
+  std::vector<uint32_t> nodes(2 * n_par + 2);
+  for (size_t i = 0; i < n_par; i++) { nodes[2 * i] = fix(t.nodes[2 * order[i]]); nodes[2 * i + 1] = fix(t.nodes[2 * order[i] + 1]); }
+  for (auto &r : t.path) r = fix(r);
+  const uint32_t root_ref = fix(t.root);
+
+  uint8_t *d_data = nullptr; uint32_t *d_cv = nullptr, *d_nodes = nullptr, *d_path = nullptr, *d_depth = nullptr, *d_rows = nullptr;
+  uint64_t *d_off = nullptr;
+  const size_t padded = (size_t)nc * 1024;
+  int rc = B3W_OK;
+  cudaError_t e = cudaMalloc(&d_data, padded);
+  if (e == cudaSuccess) e = cudaMemset(d_data, 0, padded);
+  if (e == cudaSuccess && len) e = cudaMemcpy(d_data, data, len, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&d_cv, (nc + n_par) * 32);
+  if (e == cudaSuccess) e = cudaMalloc(&d_nodes, nodes.size() * 4);
+  if (e == cudaSuccess) e = cudaMemcpy(d_nodes, nodes.data(), nodes.size() * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&d_path, t.path.size() * 4);
+  if (e == cudaSuccess) e = cudaMemcpy(d_path, t.path.data(), t.path.size() * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&d_depth, nc * 4);
+  if (e == cudaSuccess) e = cudaMemcpy(d_depth, t.depth_of.data(), nc * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&d_off, (nc + 1) * 8);
+  if (e == cudaSuccess) e = cudaMemcpy(d_off, step_off.data(), (nc + 1) * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&d_rows, total * 128);
+  if (e == cudaSuccess) {
+    k_chunk_cvs<<<(unsigned)((nc + 127) / 128), 128>>>(d_data, len, nc, d_cv);
+    size_t i = 0;
+    while (i < n_par) {                                   // one launch per tree level
+      size_t j = i;
+      while (j < n_par && t.height[order[j]] == t.height[order[i]]) j++;
+      k_parent_cvs<<<(unsigned)((j - i + 127) / 128), 128>>>(d_nodes, (uint32_t)i, (uint32_t)(j - i), nc, d_cv);
+      i = j;
+    }
+    k_chain_rows<<<(unsigned)((nc + 63) / 64), 64>>>(d_data, len, nc, d_cv, d_path, d_depth, t.max_depth, d_off, d_rows);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess && rows_out) e = cudaMemcpy(rows_out, d_rows, total * 128, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && step_off_out) memcpy(step_off_out, step_off.data(), (nc + 1) * 8);
+  if (e != cudaSuccess) rc = fail(B3W_ERR_CUDA, "b3w_nova_chain: %s", cudaGetErrorString(e));
+  // all step witnesses, chunk by chunk through the ring (or straight to `out`)
+  if (rc == B3W_OK) {
+    rc = ensure_ring(c);
+    const size_t wbytes = (size_t)c->def->ws * 32;
+    uint64_t done = 0;
+    int k = 0;
+    while (rc == B3W_OK && done < total) {
+      uint64_t m = total - done < c->chunk ? total - done : c->chunk;
+      cudaStream_t s = c->st[k];
+      rc = launch_witness(c, d_rows + done * 32, m, c->d_ring[k], c->d_status[k], c->d_pub[k], s, (c->flags & B3W_FLAG_FUSED_CHECK) != 0);
+      if (rc) break;
+      cudaError_t e2 = cudaSuccess;
+      if (out) e2 = cudaMemcpyAsync(out + done * wbytes, c->d_ring[k], (size_t)m * wbytes, cudaMemcpyDeviceToHost, s);
+      if (e2 == cudaSuccess && status) e2 = cudaMemcpyAsync(status + done, c->d_status[k], (size_t)m, cudaMemcpyDeviceToHost, s);
+      if (e2 == cudaSuccess && pub) e2 = cudaMemcpyAsync(pub + done * 15, c->d_pub[k], (size_t)m * 60, cudaMemcpyDeviceToHost, s);
+      done += m;
+      k ^= 1;
+      if (e2 == cudaSuccess && done < total) e2 = cudaStreamSynchronize(c->st[k]);
+      if (e2 != cudaSuccess) rc = fail(B3W_ERR_CUDA, "b3w_nova_chain: %s", cudaGetErrorString(e2));
+    }
+    if (rc == B3W_OK) {
+      cudaError_t e2 = cudaStreamSynchronize(c->st[0]);
+      if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(c->st[1]);
+      if (e2 != cudaSuccess) rc = fail(B3W_ERR_CUDA, "b3w_nova_chain: %s", cudaGetErrorString(e2));
+    }
+  }
+  // the BLAKE3 root: root parent (or the lone chunk) re-compressed with the ROOT flag = the last step's h_out of any chunk
+  if (rc == B3W_OK && root_out) {
+    (void)root_ref;
+    std::vector<uint32_t> last(15);
+    // the last step of chunk 0 outputs the root chaining value (z_{i+1}[2..10]); it is in `pub` when given, else recompute
+    uint32_t *d_p1 = nullptr; uint8_t *d_o1 = nullptr, *d_s1 = nullptr;
+    cudaError_t e3 = cudaMalloc(&d_p1, 64);
+    if (e3 == cudaSuccess) e3 = cudaMalloc(&d_o1, (size_t)c->def->ws * 32);
+    if (e3 == cudaSuccess) e3 = cudaMalloc(&d_s1, 1);
+    if (e3 == cudaSuccess) {
+      rc = launch_witness(c, d_rows + (step_off[1] - 1) * 32, 1, d_o1, d_s1, d_p1, 0);
+      if (rc == B3W_OK) e3 = cudaMemcpy(last.data(), d_p1, 60, cudaMemcpyDeviceToHost);
+    }
+    if (e3 != cudaSuccess) rc = fail(B3W_ERR_CUDA, "b3w_nova_chain: %s", cudaGetErrorString(e3));
+    if (rc == B3W_OK) memcpy(root_out, &last[2], 32);
+    cudaFree(d_p1); cudaFree(d_o1); cudaFree(d_s1);
+  }
+  cudaFree(d_data); cudaFree(d_cv); cudaFree(d_nodes); cudaFree(d_path); cudaFree(d_depth); cudaFree(d_off); cudaFree(d_rows);
+  return rc;
 }
 
 extern "C" void *b3w_host_alloc(size_t bytes) {

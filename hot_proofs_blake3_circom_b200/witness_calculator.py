@@ -210,6 +210,27 @@ class WitnessCalculator:
                                              status.ctypes.data, pub.ctypes.data))
         return {"witness": out if want_witness else None, "status": status, "pub": pub}
 
+    # ---- NEW: all Nova step witnesses of a file (the batched form of rust_fold's prove_step loop) ----
+    def novaChain(self, data, want_witness=False):
+        """data: bytes.  Returns dict(n_chunks, total_steps, step_off=u64[n_chunks+1], rows=(steps,32) u32 step inputs,
+        status=u8[steps], pub=(steps,15) u32 = z_{i+1}, witness=(steps, witnessSize*32) u8 | None, root=32 bytes)."""
+        data = bytes(data)
+        nc, ns = C.c_uint64(), C.c_uint64()
+        _lib.check(self._L.b3w_nova_chain_size(len(data), C.byref(nc), C.byref(ns)))
+        nc, ns = nc.value, ns.value
+        buf = np.frombuffer(data, np.uint8) if data else np.zeros(1, np.uint8)
+        rows = np.zeros((ns, 32), np.uint32)
+        step_off = np.zeros(nc + 1, np.uint64)
+        status = np.zeros(ns, np.uint8)
+        pub = np.zeros((ns, 15), np.uint32)
+        out = np.empty((ns, self.witnessSize * 32), np.uint8) if want_witness else None
+        root = np.zeros(32, np.uint8)
+        _lib.check(self._L.b3w_nova_chain(self._h, buf.ctypes.data, len(data), out.ctypes.data if want_witness else None,
+                                          status.ctypes.data, pub.ctypes.data, rows.ctypes.data, step_off.ctypes.data,
+                                          root.ctypes.data))
+        return {"n_chunks": nc, "total_steps": ns, "step_off": step_off, "rows": rows, "status": status, "pub": pub,
+                "witness": out, "root": root.tobytes()}
+
     # ---- device-pointer plumbing used by bench.py / tests (torch supplies memory and streams) ----
     def witness_batch_device(self, d_in, n, d_out, d_status=0, d_pub=0, stream=0):
         _lib.check(self._L.b3w_witness_batch_device(self._h, d_in, n, d_out, d_status or None, d_pub or None,

@@ -130,6 +130,22 @@ int b3w_checksum_device(b3w_ctx *ctx, const uint8_t *d_wit, uint64_t n, uint64_t
  * 256-bit streaming stores; asynchronous on `stream`. */
 int b3w_calib_fill(b3w_ctx *ctx, uint8_t *d_buf, uint64_t bytes, void *stream);
 
+/* Chained-chunk driver (BASELINE config 3): all Nova step witnesses of a file, the batched form of the reference's
+ * rust_fold loop (main.rs:71-94,166-171 around blake3_circuit.rs:160-290: update_for_step / format_input / synthesize).
+ * For every 1024-byte chunk c the schedule is n_blocks leaf steps + (depth of the chunk in the BLAKE3 tree) parent steps,
+ * z0 = [n_blocks, 0, IV, total_depth, leaf_depth-1, chunk_idx_low, chunk_idx_high, leaf_depth]; the chaining between steps and
+ * the sibling chaining values (bao slice extraction in rust_fold/src/blake3_hash.rs:17-93) are computed on the device.
+ * ctx must be one of the nova circuits.  Buffers are HOST buffers sized from b3w_nova_chain_size():
+ *   out      total_steps * witness_size * 32 bytes, or NULL (witnesses only stream through the HBM ring)
+ *   status   total_steps bytes or NULL;   pub  total_steps * 15 u32 (z_{i+1} of every step) or NULL
+ *   rows     total_steps * 32 u32: the step inputs in circuit declaration order, or NULL
+ *   step_off n_chunks + 1 u64: first step of each chunk, or NULL
+ *   root     32 bytes: h_out of the last step of chunk 0 (= the BLAKE3 hash of the input for tree shapes on which the
+ *            circuit's left/right rule, bit i of chunk_idx, agrees with the BLAKE3 tree: always for 2^k chunks). */
+int b3w_nova_chain_size(uint64_t len, uint64_t *n_chunks, uint64_t *total_steps);
+int b3w_nova_chain(b3w_ctx *ctx, const uint8_t *data, uint64_t len, uint8_t *out, uint8_t *status, uint32_t *pub,
+                   uint32_t *rows, uint64_t *step_off, uint8_t root[32]);
+
 /* pinned host memory for batch buffers */
 void *b3w_host_alloc(size_t bytes);
 void b3w_host_free(void *p);

@@ -1,0 +1,89 @@
+"""GPU tests of the chained-chunk driver b3w_nova_chain (BASELINE config 3): the batched form of the reference's
+rust_fold prove_step loop.  Checker: oracle/nova_chain_ref.py (restatement of the Rust driver) + Oracle B / A for the
+witness bytes + the blake3 package for the final hash (what rust_fold's tests assert, main.rs:392,410,439,474)."""
+import os
+
+import numpy as np
+import pytest
+
+import hot_proofs_blake3_circom_b200 as pkg
+from hot_proofs_blake3_circom_b200 import inputs as gen
+from oracle import nova_chain_ref, port, ref_wasm
+
+pytestmark = pytest.mark.gpu
+NCPU = os.cpu_count() or 1
+blake3 = pytest.importorskip("blake3")
+
+
+def synth(n, seed=0xB3B30003):
+    w = gen.splitmix_words(seed, np.arange((n + 3) // 4, dtype=np.uint64), 1)[:, 0]
+    return w.tobytes()[:n]
+
+
+@pytest.fixture(scope="module")
+def wc(built):
+    w = pkg.builder("blake3_nova", device=0)
+    yield w
+    w.close()
+
+
+@pytest.mark.parametrize("n", [0, 4, 17, 64, 68, 1023, 1024, 1025, 2048, 3000, 4096, 5123, 7168, 8192, 16 * 1024 + 1])
+def test_rows_match_the_rust_driver_restatement(wc, n):
+    data = synth(n)
+    res = wc.novaChain(data)
+    rows, off, finals = nova_chain_ref.chain_rows(data)
+    assert res["total_steps"] == len(rows) and list(res["step_off"]) == off
+    assert np.array_equal(res["rows"], np.array(rows, np.uint32))
+    assert (res["status"] == 0).all()
+    assert res["root"] == finals[0]
+    # h_out of every chunk's last step = that chunk's final value in the restatement
+    for c in range(res["n_chunks"]):
+        last = int(res["step_off"][c + 1]) - 1
+        assert res["pub"][last, 2:10].tobytes() == finals[c]
+    nchunks = max(1, (n + 1023) // 1024)
+    if nchunks & (nchunks - 1) == 0:                      # perfect tree: every chunk folds to the real BLAKE3 hash
+        assert all(f == blake3.blake3(data).digest() for f in finals)
+
+
+@pytest.mark.parametrize("name,variant", [("blake3_nova", "nova_bn_o2"), ("blake3_nova_pasta", "nova_pasta_o2"),
+                                          ("blake3_nova_o1", "nova_bn_o1")])
+def test_witness_bytes_of_a_small_file(built, name, variant):
+    w = pkg.builder(name, device=0, chunk=16)             # 16 steps per ring slot: exercises the ring
+    data = synth(3000)
+    res = w.novaChain(data, want_witness=True)
+    want, _, st = port.witness_batch(variant, res["rows"], nthreads=NCPU, want="both")
+    assert (st == 0).all()
+    assert np.array_equal(res["witness"], want)
+    z = want.view(np.uint32).reshape(res["total_steps"], w.witnessSize, 8)[:, 1:16, 0]
+    assert np.array_equal(res["pub"], z)
+    w.close()
+
+
+def test_config3_one_mebibyte(wc):
+    data = synth(1 << 20)
+    res = wc.novaChain(data)
+    assert res["n_chunks"] == 1024 and res["total_steps"] == 26624       # 1024 x (16 + 10), SURVEY 8(a) A13
+    assert (res["status"] == 0).all()
+    digest = blake3.blake3(data).digest()
+    assert res["root"] == digest
+    rows, pub, off = res["rows"], res["pub"], res["step_off"]
+    last = (off[1:] - 1).astype(np.int64)
+    assert all(pub[i, 2:10].tobytes() == digest for i in last)           # every chunk folds to blake3(file)
+    # z chaining: outputs of step i are the public inputs of step i+1 inside a chunk
+    inner = np.ones(res["total_steps"], bool)
+    inner[last] = False
+    i = np.nonzero(inner)[0]
+    nxt = rows[i + 1]
+    z = pub[i]
+    assert np.array_equal(z[:, 0], nxt[:, 0]) and np.array_equal(z[:, 1], nxt[:, 1])          # n_blocks, block_count
+    assert np.array_equal(z[:, 2:10], nxt[:, 2:10])                                           # h
+    assert np.array_equal(z[:, 10], nxt[:, 13]) and np.array_equal(z[:, 11], nxt[:, 14])      # total_depth, depth
+    assert np.array_equal(z[:, 12:14], nxt[:, 10:12]) and np.array_equal(z[:, 14], nxt[:, 12])  # chunk_idx, leaf_depth
+    # witness bytes of a sample of chunks against the reference wasm (Oracle A) / the C oracle
+    sel = np.concatenate([np.arange(off[c], off[c + 1]) for c in (0, 517, 1023)]).astype(np.int64)
+    got = wc.calculateWitnessBatch(rows[sel])["witness"]
+    assert np.array_equal(got, port.witness_batch("nova_bn_o2", rows[sel], nthreads=NCPU))
+    if ref_wasm.available("nova_bn_o2"):
+        ref = ref_wasm.RefWasm("nova_bn_o2")
+        want, st, _ = ref.batch_u32(rows[sel[:26]], nthreads=min(NCPU, 26))
+        assert (st == 0).all() and np.array_equal(got[:26], want)
