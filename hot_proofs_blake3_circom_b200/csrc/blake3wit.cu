@@ -229,22 +229,28 @@ __device__ __noinline__ void store_field_slot(uint8_t *p, uint32_t kind, uint32_
 }
 
 // Phase 2: expand the trace into witness slots [0, ws) at `dst` (32 B per slot).
-// kinds BIT / W32 / W64 are the hot path (single 256-bit store, upper 6 words from RZ); S64 / INV (nova only,
-// 67 .. 260 slots per witness) materialise a full field element.
+// kinds BIT / W32 / W64 are the hot path (single 256-bit store, upper 6 words from RZ).  Nova's true field elements
+// (kinds S64 / INV; 67 .. 260 slots per witness) are skipped here and written by a second pass over the list of field
+// slots (`fslots`: {slot, descriptor} pairs), in which all 32 lanes do field arithmetic together instead of one lane
+// diverging inside the hot loop.
 template <bool HAS_FIELD>
 __device__ __forceinline__ void expand_slots(const uint32_t *trace, const uint32_t *__restrict__ desc, uint32_t ws,
-                                             uint8_t *dst, int lane, const field_consts *__restrict__ F) {
+                                             uint8_t *dst, int lane, const field_consts *__restrict__ F,
+                                             const uint2 *__restrict__ fslots, uint32_t n_fslots) {
 #pragma unroll 4
   for (uint32_t s = lane; s < ws; s += 32) {
     const uint32_t dsc = __ldg(desc + s);
     const uint32_t t = dsc & 0xFFFFu, k = (dsc >> 16) & 31u, kind = dsc >> 24;
     const uint32_t w = trace[t];
     uint32_t lo = kind == DK_BIT ? ((w >> k) & 1u) : w;
-    uint32_t hi = kind >= DK_W64 ? trace[t + 1] : 0u;
-    if (HAS_FIELD && kind >= DK_S64) {
-      store_field_slot(dst + (size_t)s * 32, kind, w, hi, F);
-    } else {
-      st_slot(dst + (size_t)s * 32, lo, hi, 0u, 0u, 0u, 0u, 0u, 0u);
+    uint32_t hi = kind == DK_W64 ? trace[t + 1] : 0u;
+    if (!HAS_FIELD || kind < DK_S64) st_slot(dst + (size_t)s * 32, lo, hi, 0u, 0u, 0u, 0u, 0u, 0u);
+  }
+  if (HAS_FIELD) {
+    for (uint32_t j = lane; j < n_fslots; j += 32) {
+      const uint2 fs = __ldg(fslots + j);
+      const uint32_t t = fs.y & 0xFFFFu;
+      store_field_slot(dst + (size_t)fs.x * 32, fs.y >> 24, trace[t], trace[t + 1], F);
     }
   }
 }
@@ -292,7 +298,7 @@ k_blake3_comp_witness(const uint32_t *__restrict__ in, uint64_t n, const uint32_
       if (ck.first_bad && lane == 0) ck.first_bad[i] = bad;
     }
     if (status && lane == 0) status[i] = st;
-    expand_slots<false>(trace, desc, ws, out + i * (uint64_t)ws * 32, lane, nullptr);
+    expand_slots<false>(trace, desc, ws, out + i * (uint64_t)ws * 32, lane, nullptr, nullptr, 0);
   }
 }
 
@@ -301,8 +307,9 @@ k_blake3_comp_witness(const uint32_t *__restrict__ in, uint64_t n, const uint32_
 template <bool CHECK>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
 k_blake3_nova_witness(const uint32_t *__restrict__ in, uint64_t n, const uint32_t *__restrict__ desc, uint32_t ws,
-                      const field_consts *__restrict__ F, uint8_t *__restrict__ out, uint8_t *__restrict__ status,
-                      uint32_t *__restrict__ pub, const check_args ck) {
+                      const field_consts *__restrict__ F, const uint2 *__restrict__ fslots, uint32_t n_fslots,
+                      uint8_t *__restrict__ out, uint8_t *__restrict__ status, uint32_t *__restrict__ pub,
+                      const check_args ck) {
   extern __shared__ __align__(16) uint32_t s_dyn[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   uint32_t *trace = s_dyn + wib * NOVA_TRACE_STRIDE;
@@ -344,7 +351,7 @@ k_blake3_nova_witness(const uint32_t *__restrict__ in, uint64_t n, const uint32_
       else v = trace[NV_IN + 12];
       pub[i * 15 + lane] = v;
     }
-    expand_slots<true>(trace, desc, ws, out + i * (uint64_t)ws * 32, lane, F);
+    expand_slots<true>(trace, desc, ws, out + i * (uint64_t)ws * 32, lane, F, fslots, n_fslots);
   }
 }
 
@@ -577,6 +584,8 @@ struct b3w_ctx {
   int ctas_per_sm_checked;  // ... of its *_checked variant
   uint32_t *d_desc;
   field_consts *d_field;
+  uint2 *d_fslots;          // {slot, descriptor} of every slot that holds a true field element (nova)
+  uint32_t n_fslots;
   uint32_t *h_desc;         // host copy of the per-slot descriptors
   uint32_t flags;
   // R1CS tables (built on first use)
@@ -630,6 +639,17 @@ extern "C" int b3w_create(const b3w_config *cfg, b3w_ctx **out) {
   c->h_desc = h;
   if (e1 != cudaSuccess) { b3w_destroy(c); return fail(B3W_ERR_CUDA, "descriptor upload: %s", cudaGetErrorString(e1)); }
   {
+    std::vector<uint2> fs;
+    for (uint32_t sl = 0; sl < d->ws; sl++)
+      if ((h[sl] >> 24) >= DK_S64) fs.push_back(make_uint2(sl, h[sl]));
+    c->n_fslots = (uint32_t)fs.size();
+    if (c->n_fslots) {
+      e1 = cudaMalloc(&c->d_fslots, fs.size() * sizeof(uint2));
+      if (e1 == cudaSuccess) e1 = cudaMemcpy(c->d_fslots, fs.data(), fs.size() * sizeof(uint2), cudaMemcpyHostToDevice);
+      if (e1 != cudaSuccess) { b3w_destroy(c); return fail(B3W_ERR_CUDA, "field slot list upload: %s", cudaGetErrorString(e1)); }
+    }
+  }
+  {
     field_consts *F = new (std::nothrow) field_consts();
     if (!F) { b3w_destroy(c); return fail(B3W_ERR_NOMEM, "out of host memory"); }
     uint32_t pl[8];
@@ -674,6 +694,7 @@ extern "C" void b3w_destroy(b3w_ctx *c) {
   free_ring(c);
   if (c->d_desc) cudaFree(c->d_desc);
   if (c->d_field) cudaFree(c->d_field);
+  if (c->d_fslots) cudaFree(c->d_fslots);
   for (b3w_ctx::r1cs_dev *r : {&c->r_slots, &c->r_fused}) {
     if (r->cls) cudaFree(r->cls);
     if (r->lo) cudaFree(r->lo);
@@ -812,8 +833,8 @@ static int launch_witness(b3w_ctx *c, const uint32_t *d_in, uint64_t n, uint8_t 
   }
   const unsigned bs = WARPS_PER_CTA * 32;
   if (c->def->nova) {
-    if (check) k_blake3_nova_witness<true><<<grid, bs, NOVA_SMEM, s>>>(d_in, n, c->d_desc, c->def->ws, c->d_field, d_out, d_status, d_pub, ck);
-    else k_blake3_nova_witness<false><<<grid, bs, NOVA_SMEM, s>>>(d_in, n, c->d_desc, c->def->ws, c->d_field, d_out, d_status, d_pub, ck);
+    if (check) k_blake3_nova_witness<true><<<grid, bs, NOVA_SMEM, s>>>(d_in, n, c->d_desc, c->def->ws, c->d_field, c->d_fslots, c->n_fslots, d_out, d_status, d_pub, ck);
+    else k_blake3_nova_witness<false><<<grid, bs, NOVA_SMEM, s>>>(d_in, n, c->d_desc, c->def->ws, c->d_field, c->d_fslots, c->n_fslots, d_out, d_status, d_pub, ck);
   } else {
     if (check) k_blake3_comp_witness<true><<<grid, bs, 0, s>>>(d_in, n, c->d_desc, c->def->ws, d_out, d_status, d_pub, ck);
     else k_blake3_comp_witness<false><<<grid, bs, 0, s>>>(d_in, n, c->d_desc, c->def->ws, d_out, d_status, d_pub, ck);

@@ -1,0 +1,105 @@
+"""bench_configs.py -- measurements for the BASELINE configs that bench.py's single JSON line does not carry
+(configs[2..4]); one JSON line each, written for profiles/.  Not the driver's benchmark (that is bench.py)."""
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+import hot_proofs_blake3_circom_b200 as pkg
+from hot_proofs_blake3_circom_b200 import _lib
+from hot_proofs_blake3_circom_b200 import inputs as gen
+
+L = pkg.lib()
+
+
+def pinned(arr):
+    p = L.b3w_host_alloc(arr.nbytes)
+    C.memmove(p, arr.ctypes.data, arr.nbytes)
+    return p
+
+
+def timed(f, reps=3, warm=1):
+    for _ in range(warm):
+        f()
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    for _ in range(reps):
+        f()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t) / reps
+
+
+def config3():
+    wc = pkg.builder("blake3_nova", device=0, chunk=8192)
+    data = gen.splitmix_words(0xB3B30003, np.arange(1 << 18, dtype=np.uint64), 1)[:, 0].tobytes()
+    res = wc.novaChain(data)
+    import blake3
+    assert res["root"] == blake3.blake3(data).digest() and (res["status"] == 0).all()
+    dt = timed(lambda: wc.novaChain(data), reps=3)
+    print(json.dumps({"config": "configs[2]: blake3_nova (BN254, O2) chained-chunk witnesses, synthetic 1 MiB input",
+                      "chunks": res["n_chunks"], "step_witnesses": res["total_steps"], "witness_bytes": wc.witnessSize * 32,
+                      "seconds": dt, "step_witnesses_per_s": res["total_steps"] / dt,
+                      "GB_generated": res["total_steps"] * wc.witnessSize * 32 / 1e9,
+                      "note": "b3w_nova_chain end to end from host bytes: H2D, device BLAKE3 tree, chain rows, all step witnesses "
+                              "through the HBM ring, z_{i+1}/status/rows D2H; root == blake3(file)"}), flush=True)
+    wc.close()
+
+
+def config4():
+    n = 1 << 20
+    wc = pkg.builder("blake3_nova_pasta", device=0, chunk=32768)
+    rows = gen.splitmix_nova_inputs(n)
+    h_in = pinned(rows)
+    h_st = L.b3w_host_alloc(n)
+    h_pub = L.b3w_host_alloc(n * 60)
+    f = lambda: _lib.check(L.b3w_witness_batch(wc._h, h_in, n, None, h_st, h_pub))
+    dt = timed(f, reps=3)
+    st = np.ctypeslib.as_array(C.cast(h_st, C.POINTER(C.c_uint8)), shape=(n,))
+    assert not st.any()
+    print(json.dumps({"config": "configs[3]: blake3_nova_pasta (Pallas Fr) batch 2^20, streamed through the HBM ring",
+                      "instances": n, "witness_bytes": wc.witnessSize * 32, "seconds": dt, "witnesses_per_s": n / dt,
+                      "GB_generated": n * wc.witnessSize * 32 / 1e9, "hbm_write_GBps": n * wc.witnessSize * 32 / dt / 1e9,
+                      "note": "b3w_witness_batch(out=NULL): host pinned inputs H2D, 781 GB of witnesses written to a 2-slot HBM ring, "
+                              "status + z_{i+1} D2H"}), flush=True)
+    for p in (h_in, h_st, h_pub):
+        L.b3w_host_free(p)
+    wc.close()
+
+
+def config5():
+    n = 1 << 24
+    for fused in (False, True):
+        wc = pkg.builder("blake3_compression", device=0, chunk=32768, fused_check=fused)
+        rows = gen.splitmix_compression_inputs(n)
+        h_in = pinned(rows)
+        del rows
+        h_st = L.b3w_host_alloc(n)
+        h_pub = L.b3w_host_alloc(n * 64)
+        f = lambda: _lib.check(L.b3w_witness_batch(wc._h, h_in, n, None, h_st, h_pub))
+        dt = timed(f, reps=2)
+        st = np.ctypeslib.as_array(C.cast(h_st, C.POINTER(C.c_uint8)), shape=(n,))
+        assert not st.any()
+        print(json.dumps({"config": "configs[4]: blake3_compression 2^24 instances, %s, ONE B200 (shards are independent)"
+                          % ("fused on-device R1CS check" if fused else "no check"),
+                          "instances": n, "seconds": dt, "witnesses_per_s": n / dt, "TB_generated": n * 770976 / 1e12,
+                          "hbm_write_GBps": n * 770976 / dt / 1e9,
+                          "note": "b3w_witness_batch(out=NULL) with splitmix inputs (random h,t,d, ragged b): 12.9 TB streamed through "
+                                  "the HBM ring, status + out[16] D2H"}), flush=True)
+        for p in (h_in, h_st, h_pub):
+            L.b3w_host_free(p)
+        wc.close()
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["3", "4", "5"]
+    if "3" in which:
+        config3()
+    if "4" in which:
+        config4()
+    if "5" in which:
+        config5()
