@@ -15,7 +15,7 @@ EXPORTS = ("b3w_version", "b3w_last_error", "b3w_create", "b3w_destroy", "b3w_ci
            "b3w_input_signal", "b3w_witness_one", "b3w_witness_batch", "b3w_witness_batch_device",
            "b3w_checksum_device", "b3w_calib_fill", "b3w_host_alloc", "b3w_host_free",
            "b3w_witness_batch_device_checked", "b3w_r1cs_check_device", "b3w_r1cs_info", "b3w_debug_inject_fault",
-           "b3w_nova_chain_size", "b3w_nova_chain")
+           "b3w_nova_chain_size", "b3w_nova_chain", "b3w_debug_set_launch")
 
 
 class B3WError(RuntimeError):
@@ -64,6 +64,7 @@ def lib():
     L.b3w_r1cs_check_device.argtypes = [vp, vp, u64, vp, vp, vp]
     L.b3w_r1cs_info.argtypes = [C.c_uint32, u32p, u32p]
     L.b3w_debug_inject_fault.argtypes = [vp, C.c_uint32, C.c_uint32]
+    L.b3w_debug_set_launch.argtypes = [vp, C.c_int, C.c_uint32]
     L.b3w_nova_chain_size.argtypes = [u64, C.POINTER(u64), C.POINTER(u64)]
     L.b3w_nova_chain.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp, vp]
     L.b3w_calib_fill.argtypes = [vp, vp, u64, vp]

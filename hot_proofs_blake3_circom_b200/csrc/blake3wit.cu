@@ -49,10 +49,23 @@ static int fail(int code, const char *fmt, ...) {
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t rotr32(uint32_t x, int r) { return __funnelshift_r(x, x, r); }
 
+// Cache policy of the witness stores: written once and never re-read by this kernel, so they bypass L1 and are marked
+// evict-first in L2 (keeps the descriptor / field tables resident there; +5 % on the nova kernel, +0.3 % on compression).
+// B3W_ST_HINT is an experiment switch; 1 is what ships.
+#ifndef B3W_ST_HINT
+#define B3W_ST_HINT 1
+#endif
+#if B3W_ST_HINT == 0
+#define B3W_ST_QUAL ".L1::no_allocate"
+#elif B3W_ST_HINT == 1
+#define B3W_ST_QUAL ".L1::no_allocate.L2::evict_first"
+#else
+#define B3W_ST_QUAL ".cs"
+#endif
 // 256-bit streaming store of one witness slot {w0..w7}: written once, never re-read by this kernel.
 __device__ __forceinline__ void st_slot(void *p, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4,
                                         uint32_t w5, uint32_t w6, uint32_t w7) {
-  asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w0), "r"(w1), "r"(w2),
+  asm volatile("st.global" B3W_ST_QUAL ".v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w0), "r"(w1), "r"(w2),
                "r"(w3), "r"(w4), "r"(w5), "r"(w6), "r"(w7)
                : "memory");
 }
@@ -99,9 +112,22 @@ __device__ __forceinline__ void half_g(uint32_t &a, uint32_t &b, uint32_t &c, ui
   }
 }
 
+// This lane's slice of the message schedule, packed for registers: word r holds the four m[] indices that lane
+// q = lane & 3 needs in round r (columns: msg[2q], msg[2q+1]; diagonals: msg[8+2q], msg[9+2q]), one byte each.
+struct lane_sched { uint32_t w[7]; };
+__device__ __forceinline__ lane_sched load_lane_sched(int lane) {
+  const int q = lane & 3;
+  lane_sched ls;
+#pragma unroll
+  for (int r = 0; r < 7; r++)
+    ls.w[r] = (uint32_t)MSG_SCHED[r][2 * q] | ((uint32_t)MSG_SCHED[r][2 * q + 1] << 8) | ((uint32_t)MSG_SCHED[r][8 + 2 * q] << 16) |
+              ((uint32_t)MSG_SCHED[r][9 + 2 * q] << 24);
+  return ls;
+}
+
 // Phase 1 for the compression circuit.  trace[TR_IN..TR_IN+28) must already hold h,m,t,b,d.
 // All 32 lanes execute (8 redundant groups of 4); lanes 0..3 write.
-__device__ __forceinline__ void compression_trace(uint32_t *trace, int lane) {
+__device__ __forceinline__ void compression_trace(uint32_t *trace, int lane, const lane_sched &ls) {
   const int q = lane & 3;
   const bool writer = lane < 4;
   const uint32_t IVq[4] = {0x6A09E667u, 0xBB67AE85u, 0x3C6EF372u, 0xA54FF53Au};
@@ -111,18 +137,20 @@ __device__ __forceinline__ void compression_trace(uint32_t *trace, int lane) {
   uint32_t d = trace[TR_IN + 24 + q];            // v[12+q]  = t0,t1,b,d               (:184-187)
   const uint32_t h_lo = a, h_hi = b;
   const uint32_t *m = trace + TR_IN + 8;
-#pragma unroll 1
+#pragma unroll
   for (int r = 0; r < 7; r++) {
     uint32_t *rec = trace + TR_HG + 128 * r + 16 * q;
+    const uint32_t sw = ls.w[r];
+    const uint32_t m0 = m[sw & 15u], m1 = m[(sw >> 8) & 15u], m2 = m[(sw >> 16) & 15u], m3 = m[sw >> 24];
     // columns: G(q, 4+q, 8+q, 12+q) with msg[2q], msg[2q+1]                              (:145-148)
-    half_g<16, 12>(a, b, c, d, m[MSG_SCHED[r][2 * q]], rec, writer);
-    half_g<8, 7>(a, b, c, d, m[MSG_SCHED[r][2 * q + 1]], rec + 8, writer);
+    half_g<16, 12>(a, b, c, d, m0, rec, writer);
+    half_g<8, 7>(a, b, c, d, m1, rec + 8, writer);
     // diagonals: lane q takes b from column q+1, c from q+2, d from q+3                  (:150-153)
     b = __shfl_sync(0xffffffffu, b, (q + 1) & 3, 4);
     c = __shfl_sync(0xffffffffu, c, (q + 2) & 3, 4);
     d = __shfl_sync(0xffffffffu, d, (q + 3) & 3, 4);
-    half_g<16, 12>(a, b, c, d, m[MSG_SCHED[r][8 + 2 * q]], rec + 64, writer);
-    half_g<8, 7>(a, b, c, d, m[MSG_SCHED[r][9 + 2 * q]], rec + 72, writer);
+    half_g<16, 12>(a, b, c, d, m2, rec + 64, writer);
+    half_g<8, 7>(a, b, c, d, m3, rec + 72, writer);
     b = __shfl_sync(0xffffffffu, b, (q + 3) & 3, 4);
     c = __shfl_sync(0xffffffffu, c, (q + 2) & 3, 4);
     d = __shfl_sync(0xffffffffu, d, (q + 1) & 3, 4);
@@ -219,7 +247,7 @@ __device__ __forceinline__ bool nova_trace(uint32_t *trace, int lane) {
 
 // Slow path of phase 2 (nova only): a slot that holds a true field element.  Kept out of line so that the hot
 // loop keeps its small register footprint.
-__device__ __noinline__ void store_field_slot(uint8_t *p, uint32_t kind, uint32_t lo, uint32_t hi,
+__device__ __forceinline__ void store_field_slot(uint8_t *p, uint32_t kind, uint32_t lo, uint32_t hi,
                                               const field_consts *__restrict__ F) {
   const int64_t x = (int64_t)(((uint64_t)hi << 32) | lo);
   fr_t v;
@@ -228,17 +256,17 @@ __device__ __noinline__ void store_field_slot(uint8_t *p, uint32_t kind, uint32_
   st_slot_fr(p, v.l);
 }
 
-// Phase 2: expand the trace into witness slots [0, ws) at `dst` (32 B per slot).
+// Phase 2: expand the trace into witness slots [s0, s1) at `dst` (32 B per slot).
 // kinds BIT / W32 / W64 are the hot path (single 256-bit store, upper 6 words from RZ).  Nova's true field elements
 // (kinds S64 / INV; 67 .. 260 slots per witness) are skipped here and written by a second pass over the list of field
 // slots (`fslots`: {slot, descriptor} pairs), in which all 32 lanes do field arithmetic together instead of one lane
 // diverging inside the hot loop.
 template <bool HAS_FIELD>
-__device__ __forceinline__ void expand_slots(const uint32_t *trace, const uint32_t *__restrict__ desc, uint32_t ws,
+__device__ __forceinline__ void expand_slots(const uint32_t *trace, const uint32_t *__restrict__ desc, uint32_t s0, uint32_t s1,
                                              uint8_t *dst, int lane, const field_consts *__restrict__ F,
                                              const uint2 *__restrict__ fslots, uint32_t n_fslots) {
 #pragma unroll 4
-  for (uint32_t s = lane; s < ws; s += 32) {
+  for (uint32_t s = s0 + lane; s < s1; s += 32) {
     const uint32_t dsc = __ldg(desc + s);
     const uint32_t t = dsc & 0xFFFFu, k = (dsc >> 16) & 31u, kind = dsc >> 24;
     const uint32_t w = trace[t];
@@ -250,7 +278,7 @@ __device__ __forceinline__ void expand_slots(const uint32_t *trace, const uint32
     for (uint32_t j = lane; j < n_fslots; j += 32) {
       const uint2 fs = __ldg(fslots + j);
       const uint32_t t = fs.y & 0xFFFFu;
-      store_field_slot(dst + (size_t)fs.x * 32, fs.y >> 24, trace[t], trace[t + 1], F);
+      if (fs.x >= s0 && fs.x < s1) store_field_slot(dst + (size_t)fs.x * 32, fs.y >> 24, trace[t], trace[t + 1], F);
     }
   }
 }
@@ -271,87 +299,174 @@ struct check_args {
   uint32_t fault_mask;       // ... by xor with this mask, after the trace phase
 };
 
-// k_blake3_comp_witness: one warp per instance, grid-stride over instances.
+// Work distribution.  A work item is one PART of one instance: slots [part * part_len, (part + 1) * part_len) of its
+// witness.  Warps of the persistent grid take items from a global counter (dynamic scheduling): SMs do not all see the
+// same HBM bandwidth, and with a static split the launch ends with a long tail of slow warps; measured on B200
+// (2^16 compression instances) 5.9 TB/s static vs 7.2 TB/s dynamic.  A warp computes the (cheap) trace of the
+// item's instance and expands only the item's slots; part 0 also writes status / public outputs / the check result.
+#define SCHED_LANES 8             // sub-counters per launch: same-address atomics serialise in one L2 slice (~2.4 ns each)
+#define SCHED_STRIDE 16           // u64 between sub-counters (128 B: one L2 line each)
+struct sched_args {
+  unsigned long long *counter;     // SCHED_LANES sub-counters, zeroed before the launch; sub-counter c hands out the
+                                   // items {v * SCHED_LANES + c}
+  unsigned int parts;              // items per instance
+  unsigned int part_len;           // slots per item, a multiple of 32
+};
+
+// Software pipeline over work items: while item k is traced and expanded, the input row of item k+1 is already on its
+// way from HBM and the counter grab for item k+2 is in flight, so neither latency sits between two expansions.
+template <int N_IN>
+struct item_pipe {
+  const sched_args &sc;
+  const uint32_t *__restrict__ in;
+  uint64_t n, total;
+  int lane;
+  uint32_t sub, tries;                    // current sub-counter, exhausted sub-counters seen so far
+  unsigned long long cur, nxt, grabbed;   // item ids: being processed / input row loading / grab in flight (lane 0)
+  uint32_t cur_in, nxt_in;                // this lane's word of the input rows
+
+  __device__ __forceinline__ unsigned long long grab() {
+    return lane == 0 ? atomicAdd(sc.counter + sub * SCHED_STRIDE, 1ull) * SCHED_LANES + sub : 0ull;
+  }
+  // the grabbed id, or -- when its sub-counter has run dry -- an id from the next sub-counter that still has work
+  // (a dry result that was grabbed before the last switch says nothing about the current sub-counter)
+  __device__ __forceinline__ unsigned long long resolve(unsigned long long g) {
+    unsigned long long id = __shfl_sync(0xffffffffu, g, 0);
+    while (id >= total && tries < SCHED_LANES) {
+      if (id % SCHED_LANES == sub) {
+        tries++;
+        sub = (sub + 1) % SCHED_LANES;
+      }
+      id = __shfl_sync(0xffffffffu, grab(), 0);
+    }
+    return id;
+  }
+  __device__ __forceinline__ uint32_t load_row(unsigned long long item) {
+    return (item < total && lane < N_IN) ? __ldg(in + (item / sc.parts) * N_IN + lane) : 0u;
+  }
+  __device__ __forceinline__ item_pipe(const sched_args &sc_, const uint32_t *in_, uint64_t n_, int lane_, uint64_t gwarp)
+      : sc(sc_), in(in_), n(n_), total(n_ * sc_.parts), lane(lane_), sub((uint32_t)(gwarp % SCHED_LANES)), tries(0) {
+    cur = resolve(grab());
+    nxt = resolve(grab());
+    cur_in = load_row(cur);
+    nxt_in = load_row(nxt);
+    grabbed = grab();
+  }
+  __device__ __forceinline__ bool valid() const { return cur < total; }
+  __device__ __forceinline__ uint64_t inst() const { return cur / sc.parts; }
+  __device__ __forceinline__ uint32_t part() const { return (uint32_t)(cur % sc.parts); }
+  // call once the current item's input word has been consumed: shifts the pipeline and refills its far end
+  __device__ __forceinline__ void advance() {
+    cur = nxt;
+    cur_in = nxt_in;
+    nxt = resolve(grabbed);
+    nxt_in = load_row(nxt);
+    grabbed = grab();
+  }
+};
+
+// k_blake3_comp_witness: compression circuit, one warp per range (see above).
 template <bool CHECK>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, CHECK ? 4 : 7)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
 k_blake3_comp_witness(const uint32_t *__restrict__ in, uint64_t n, const uint32_t *__restrict__ desc, uint32_t ws,
                       uint8_t *__restrict__ out, uint8_t *__restrict__ status, uint32_t *__restrict__ pub,
-                      const check_args ck) {
+                      const check_args ck, const sched_args sc) {
   __shared__ __align__(16) uint32_t s_trace[WARPS_PER_CTA][TRACE_STRIDE];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   uint32_t *trace = s_trace[wib];
-  const uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
   if (lane == 0) { trace[TR_ZERO] = 0u; trace[TR_ONE] = 1u; }
-  for (uint64_t i = (uint64_t)blockIdx.x * WARPS_PER_CTA + wib; i < n; i += nwarps) {
+  const lane_sched ls = load_lane_sched(lane);
+  for (item_pipe<28> pipe(sc, in, n, lane, (uint64_t)blockIdx.x * WARPS_PER_CTA + wib); pipe.valid();) {
+    const uint64_t i = pipe.inst();
+    const uint32_t part = pipe.part();
+    const uint32_t a = part * sc.part_len, b = a + sc.part_len < ws ? a + sc.part_len : ws;
+    __syncwarp();                               // the previous expansion has finished reading the trace
+    if (lane < 28) trace[TR_IN + lane] = pipe.cur_in;
+    pipe.advance();
     __syncwarp();
-    if (lane < 28) trace[TR_IN + lane] = __ldg(in + i * 28 + lane);
+    compression_trace(trace, lane, ls);
     __syncwarp();
-    compression_trace(trace, lane);
-    __syncwarp();
-    if (pub && lane < 16) pub[i * 16 + lane] = trace[TR_OUT + lane];
-    uint8_t st = 0;                           // u32 inputs can never violate a constraint of this circuit ...
-    if (CHECK) {                              // ... which the fused check confirms row by row
-      if (ck.fault_word != B3W_NO_ROW && lane == 0) trace[ck.fault_word] ^= ck.fault_mask;
+    if (part == 0) {                            // this warp owns the instance's head
+      if (pub && lane < 16) pub[i * 16 + lane] = trace[TR_OUT + lane];
+      uint8_t st = 0;                           // u32 inputs can never violate a constraint of this circuit ...
+      if (CHECK) {                              // ... which the fused check confirms row by row
+        if (ck.fault_word != B3W_NO_ROW && lane == 0) trace[ck.fault_word] ^= ck.fault_mask;
+        __syncwarp();
+        const uint32_t bad = r1cs_check_instance(TraceSrc{trace, ck.F}, ck.T, lane);
+        if (bad != B3W_NO_ROW) st = B3W_R1CS_VIOLATION;
+        if (ck.first_bad && lane == 0) ck.first_bad[i] = bad;
+      }
+      if (status && lane == 0) status[i] = st;
+    } else if (CHECK && ck.fault_word != B3W_NO_ROW) {   // keep the injected fault visible in every part of the witness
+      if (lane == 0) trace[ck.fault_word] ^= ck.fault_mask;
       __syncwarp();
-      const uint32_t bad = r1cs_check_instance(TraceSrc{trace, ck.F}, ck.T, lane);
-      if (bad != B3W_NO_ROW) st = B3W_R1CS_VIOLATION;
-      if (ck.first_bad && lane == 0) ck.first_bad[i] = bad;
     }
-    if (status && lane == 0) status[i] = st;
-    expand_slots<false>(trace, desc, ws, out + i * (uint64_t)ws * 32, lane, nullptr, nullptr, 0);
+    expand_slots<false>(trace, desc, a, b, out + i * (uint64_t)ws * 32, lane, nullptr, nullptr, 0);
   }
 }
 
 // k_blake3_nova_witness: the nova step circuit (all three committed builds share it; they differ in the
 // slot table and the prime).  pub = z_{i+1} = the 15 outputs (low 32 bits each).
 template <bool CHECK>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3)
 k_blake3_nova_witness(const uint32_t *__restrict__ in, uint64_t n, const uint32_t *__restrict__ desc, uint32_t ws,
                       const field_consts *__restrict__ F, const uint2 *__restrict__ fslots, uint32_t n_fslots,
                       uint8_t *__restrict__ out, uint8_t *__restrict__ status, uint32_t *__restrict__ pub,
-                      const check_args ck) {
+                      const check_args ck, const sched_args sc) {
   extern __shared__ __align__(16) uint32_t s_dyn[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   uint32_t *trace = s_dyn + wib * NOVA_TRACE_STRIDE;
-  const uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
   if (lane == 0) { trace[TR_ZERO] = 0u; trace[TR_ONE] = 1u; }
-  for (uint64_t i = (uint64_t)blockIdx.x * WARPS_PER_CTA + wib; i < n; i += nwarps) {
+  const lane_sched ls = load_lane_sched(lane);
+  for (item_pipe<32> pipe(sc, in, n, lane, (uint64_t)blockIdx.x * WARPS_PER_CTA + wib); pipe.valid();) {
+    const uint64_t i = pipe.inst();
+    const uint32_t part = pipe.part();
+    const uint32_t a = part * sc.part_len, b = a + sc.part_len < ws ? a + sc.part_len : ws;
+    const bool head = part == 0;
     __syncwarp();
-    trace[NV_IN + lane] = __ldg(in + i * 32 + lane);
+    trace[NV_IN + lane] = pipe.cur_in;
+    pipe.advance();
     __syncwarp();
     const bool ok = nova_trace(trace, lane);
     if (!ok) {                                  // the reference throws "Assert Failed.": no witness exists
-      if (status && lane == 0) status[i] = B3W_CIRCOM_ASSERT;
-      if (pub && lane < 15) pub[i * 15 + lane] = 0u;
-      if (CHECK && ck.first_bad && lane == 0) ck.first_bad[i] = B3W_NO_ROW;
+      if (head) {
+        if (status && lane == 0) status[i] = B3W_CIRCOM_ASSERT;
+        if (pub && lane < 15) pub[i * 15 + lane] = 0u;
+        if (CHECK && ck.first_bad && lane == 0) ck.first_bad[i] = B3W_NO_ROW;
+      }
       continue;
     }
     __syncwarp();
-    compression_trace(trace, lane);
+    compression_trace(trace, lane, ls);
     __syncwarp();
-    uint8_t st = 0;
-    if (CHECK) {
-      if (ck.fault_word != B3W_NO_ROW && lane == 0) trace[ck.fault_word] ^= ck.fault_mask;
+    if (head) {
+      uint8_t st = 0;
+      if (CHECK) {
+        if (ck.fault_word != B3W_NO_ROW && lane == 0) trace[ck.fault_word] ^= ck.fault_mask;
+        __syncwarp();
+        const uint32_t bad = r1cs_check_instance(TraceSrc{trace, ck.F}, ck.T, lane);
+        if (bad != B3W_NO_ROW) st = B3W_R1CS_VIOLATION;
+        if (ck.first_bad && lane == 0) ck.first_bad[i] = bad;
+      }
+      if (status && lane == 0) status[i] = st;
+      if (pub && lane < 15) {
+        // n_blocks_out, block_count_out, h_out[8], total_depth_out, depth_out, chunk_idx_low/high_out, leaf_depth_out (:195-202)
+        uint32_t v;
+        if (lane == 0) v = trace[NV_IN + 0];
+        else if (lane == 1) v = trace[NV_BC_OUT];
+        else if (lane < 10) v = trace[TR_OUT + lane - 2];
+        else if (lane == 10) v = trace[NV_IN + 13];
+        else if (lane == 11) v = trace[NV_DEPTH_OUT];
+        else if (lane == 12) v = trace[NV_IN + 10];
+        else if (lane == 13) v = trace[NV_IN + 11];
+        else v = trace[NV_IN + 12];
+        pub[i * 15 + lane] = v;
+      }
+    } else if (CHECK && ck.fault_word != B3W_NO_ROW) {
+      if (lane == 0) trace[ck.fault_word] ^= ck.fault_mask;
       __syncwarp();
-      const uint32_t bad = r1cs_check_instance(TraceSrc{trace, ck.F}, ck.T, lane);
-      if (bad != B3W_NO_ROW) st = B3W_R1CS_VIOLATION;
-      if (ck.first_bad && lane == 0) ck.first_bad[i] = bad;
     }
-    if (status && lane == 0) status[i] = st;
-    if (pub && lane < 15) {
-      // n_blocks_out, block_count_out, h_out[8], total_depth_out, depth_out, chunk_idx_low/high_out, leaf_depth_out (:195-202)
-      uint32_t v;
-      if (lane == 0) v = trace[NV_IN + 0];
-      else if (lane == 1) v = trace[NV_BC_OUT];
-      else if (lane < 10) v = trace[TR_OUT + lane - 2];
-      else if (lane == 10) v = trace[NV_IN + 13];
-      else if (lane == 11) v = trace[NV_DEPTH_OUT];
-      else if (lane == 12) v = trace[NV_IN + 10];
-      else if (lane == 13) v = trace[NV_IN + 11];
-      else v = trace[NV_IN + 12];
-      pub[i * 15 + lane] = v;
-    }
-    expand_slots<true>(trace, desc, ws, out + i * (uint64_t)ws * 32, lane, F, fslots, n_fslots);
+    expand_slots<true>(trace, desc, a, b, out + i * (uint64_t)ws * 32, lane, F, fslots, n_fslots);
   }
 }
 
@@ -575,6 +690,8 @@ static const circuit_def CIRCUITS[] = {
 };
 static const int N_CIRCUITS = sizeof(CIRCUITS) / sizeof(CIRCUITS[0]);
 
+#define N_SCHED_COUNTERS 64       // launches in flight on different streams each need their own counter set
+#define SCHED_SET_U64 (SCHED_LANES * SCHED_STRIDE)
 struct b3w_ctx {
   const circuit_def *def;
   int device;
@@ -592,6 +709,10 @@ struct b3w_ctx {
   bool r1cs_ready;
   struct r1cs_dev { r1cs_class_dev *cls; int64_t *lo, *hi; uint32_t *terms; uint32_t ncls; } r_fused, r_slots;
   uint32_t fault_word, fault_mask;
+  int ctas_limit;           // tuning hook: cap on resident CTAs per SM (0 = occupancy limit)
+  uint32_t sched_parts;     // work items per instance (0 = default)
+  unsigned long long *d_counters;   // rotating pool of work-item counters (launches on different streams may overlap)
+  uint32_t next_counter;
   // staging for host-buffer batches: 2 ring slots
   cudaStream_t st[2];
   cudaEvent_t ev[2];
@@ -695,6 +816,7 @@ extern "C" void b3w_destroy(b3w_ctx *c) {
   if (c->d_desc) cudaFree(c->d_desc);
   if (c->d_field) cudaFree(c->d_field);
   if (c->d_fslots) cudaFree(c->d_fslots);
+  if (c->d_counters) cudaFree(c->d_counters);
   for (b3w_ctx::r1cs_dev *r : {&c->r_slots, &c->r_fused}) {
     if (r->cls) cudaFree(r->cls);
     if (r->lo) cudaFree(r->lo);
@@ -815,9 +937,15 @@ static int ensure_r1cs(b3w_ctx *c) {
 static int launch_witness(b3w_ctx *c, const uint32_t *d_in, uint64_t n, uint8_t *d_out, uint8_t *d_status,
                           uint32_t *d_pub, cudaStream_t s, bool check = false, uint32_t *d_first_bad = nullptr) {
   if (n == 0) return B3W_OK;
-  // persistent grid: exactly the CTAs that are resident at once (SM count x occupancy), grid-stride over instances
-  uint64_t ctas_needed = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-  uint64_t max_ctas = (uint64_t)c->sm_count * (check ? c->ctas_per_sm_checked : c->ctas_per_sm);
+  // Persistent grid, work items handed out dynamically (see sched_args).  Defaults from sweeps on B200 (profiles/):
+  // the plain kernels are fastest with only 2 CTAs (16 warps) per SM and 24 items per witness (32 KiB each: the
+  // GPU-wide write front stays compact); the checked kernels need every warp they can get to hide the check's arithmetic.
+  const uint32_t parts = c->sched_parts ? c->sched_parts : (check ? 4u : 24u);
+  uint64_t ctas_needed = (n * parts + WARPS_PER_CTA - 1) / WARPS_PER_CTA;      // one warp per work item
+  int per_sm = check ? c->ctas_per_sm_checked : c->ctas_per_sm;
+  const int cap = c->ctas_limit > 0 ? c->ctas_limit : (check ? per_sm : 2);
+  if (cap < per_sm) per_sm = cap;
+  uint64_t max_ctas = (uint64_t)c->sm_count * per_sm;
   unsigned grid = (unsigned)(ctas_needed < max_ctas ? ctas_needed : max_ctas);
   check_args ck;
   memset(&ck, 0, sizeof ck);
@@ -832,12 +960,19 @@ static int launch_witness(b3w_ctx *c, const uint32_t *d_in, uint64_t n, uint8_t 
     ck.fault_mask = c->fault_mask;
   }
   const unsigned bs = WARPS_PER_CTA * 32;
+  // work distribution (see sched_args)
+  sched_args sc;
+  if (!c->d_counters) CK(cudaMalloc(&c->d_counters, (size_t)N_SCHED_COUNTERS * SCHED_SET_U64 * sizeof(unsigned long long)));
+  sc.counter = c->d_counters + (size_t)(c->next_counter++ % N_SCHED_COUNTERS) * SCHED_SET_U64;
+  sc.parts = parts;
+  sc.part_len = ((c->def->ws + sc.parts - 1) / sc.parts + 31) / 32 * 32;
+  CK(cudaMemsetAsync(sc.counter, 0, SCHED_SET_U64 * sizeof(unsigned long long), s));
   if (c->def->nova) {
-    if (check) k_blake3_nova_witness<true><<<grid, bs, NOVA_SMEM, s>>>(d_in, n, c->d_desc, c->def->ws, c->d_field, c->d_fslots, c->n_fslots, d_out, d_status, d_pub, ck);
-    else k_blake3_nova_witness<false><<<grid, bs, NOVA_SMEM, s>>>(d_in, n, c->d_desc, c->def->ws, c->d_field, c->d_fslots, c->n_fslots, d_out, d_status, d_pub, ck);
+    if (check) k_blake3_nova_witness<true><<<grid, bs, NOVA_SMEM, s>>>(d_in, n, c->d_desc, c->def->ws, c->d_field, c->d_fslots, c->n_fslots, d_out, d_status, d_pub, ck, sc);
+    else k_blake3_nova_witness<false><<<grid, bs, NOVA_SMEM, s>>>(d_in, n, c->d_desc, c->def->ws, c->d_field, c->d_fslots, c->n_fslots, d_out, d_status, d_pub, ck, sc);
   } else {
-    if (check) k_blake3_comp_witness<true><<<grid, bs, 0, s>>>(d_in, n, c->d_desc, c->def->ws, d_out, d_status, d_pub, ck);
-    else k_blake3_comp_witness<false><<<grid, bs, 0, s>>>(d_in, n, c->d_desc, c->def->ws, d_out, d_status, d_pub, ck);
+    if (check) k_blake3_comp_witness<true><<<grid, bs, 0, s>>>(d_in, n, c->d_desc, c->def->ws, d_out, d_status, d_pub, ck, sc);
+    else k_blake3_comp_witness<false><<<grid, bs, 0, s>>>(d_in, n, c->d_desc, c->def->ws, d_out, d_status, d_pub, ck, sc);
   }
   CK(cudaGetLastError());
   return B3W_OK;
@@ -892,6 +1027,13 @@ extern "C" int b3w_debug_inject_fault(b3w_ctx *c, uint32_t trace_word, uint32_t 
     return fail(B3W_ERR_INVALID, "trace word %u out of range", trace_word);
   c->fault_word = trace_word;
   c->fault_mask = xor_mask;
+  return B3W_OK;
+}
+
+extern "C" int b3w_debug_set_launch(b3w_ctx *c, int ctas_per_sm, uint32_t parts) {
+  if (!c || ctas_per_sm < 0 || parts > 1024) return fail(B3W_ERR_INVALID, "b3w_debug_set_launch: bad argument");
+  c->ctas_limit = ctas_per_sm;
+  c->sched_parts = parts;
   return B3W_OK;
 }
 

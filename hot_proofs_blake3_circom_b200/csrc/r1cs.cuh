@@ -27,6 +27,7 @@
 #define R1CS_FLAG_FIELD 1u
 #define R1CS_FLAG_WIDE 2u
 #define R1CS_FLAG_XORW 4u     /* fused set only: 32 XOR rows of one word triple, X ^ rotr(Y, dy) == rotr(O, do) */
+#define R1CS_FLAG_ROWCOEF 8u  /* coefficients are stored per row (term-major) instead of once per class */
 #define B3W_NO_ROW 0xFFFFFFFFu
 
 struct r1cs_class_dev {
@@ -116,7 +117,7 @@ __device__ __noinline__ bool r1cs_field_row(const Src &src, const r1cs_class_dev
   for (uint32_t t = 0; t < c.nC; t++) {
     i128 v;
     if (!src.small(tm[(2 + t) * c.count + r], v)) return false;
-    lc += (i128)T.coef_lo[c.coef_off + 2 + t] * v;
+    lc += (i128)T.coef_lo[(c.flags & R1CS_FLAG_ROWCOEF) ? c.coef_off + (2 + t) * c.count + r : c.coef_off + 2 + t] * v;
   }
   const fr_t want = fr_from_s64((int64_t)lc, F.p);
   bool eq = true;
@@ -137,8 +138,8 @@ __device__ __forceinline__ bool r1cs_int_row(const Src &src, const r1cs_class_de
     for (uint32_t j = 0; j < n[part]; j++, t++) {
       i128 v;
       ok = src.small(tm[t * c.count + r], v) && ok;
-      acc_t co = sizeof(acc_t) == 16 ? (acc_t)(((i128)T.coef_hi[c.coef_off + t] << 64) | (i128)(uint64_t)T.coef_lo[c.coef_off + t])
-                                      : (acc_t)T.coef_lo[c.coef_off + t];
+      const uint32_t ci = (c.flags & R1CS_FLAG_ROWCOEF) ? c.coef_off + t * c.count + r : c.coef_off + t;
+      acc_t co = sizeof(acc_t) == 16 ? (acc_t)(((i128)T.coef_hi[ci] << 64) | (i128)(uint64_t)T.coef_lo[ci]) : (acc_t)T.coef_lo[ci];
       L[part] += co * (acc_t)v;
     }
   }

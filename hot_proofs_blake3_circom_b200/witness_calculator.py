@@ -253,6 +253,10 @@ class WitnessCalculator:
     def inject_fault(self, trace_word=0xFFFFFFFF, xor_mask=0):
         _lib.check(self._L.b3w_debug_inject_fault(self._h, trace_word, xor_mask))
 
+    def set_launch(self, ctas_per_sm=0, parts=0):
+        """tuning hook: cap on resident CTAs per SM, work items per instance (0 = defaults)"""
+        _lib.check(self._L.b3w_debug_set_launch(self._h, int(ctas_per_sm), int(parts)))
+
     def checksum_device(self, d_wit, n, d_sums, stream=0):
         _lib.check(self._L.b3w_checksum_device(self._h, d_wit, n, d_sums, stream or None))
 

@@ -121,6 +121,10 @@ int b3w_r1cs_info(uint32_t circuit, uint32_t *n_rows, uint32_t *n_terms);
  * of the *_checked kernels (B3W_NO_ROW disables it). */
 int b3w_debug_inject_fault(b3w_ctx *ctx, uint32_t trace_word, uint32_t xor_mask);
 
+/* Tuning hook: cap the persistent grid at `ctas_per_sm` resident CTAs per SM (0 = the per-kernel default) and set the
+ * number of work items an instance's witness is split into (0 = default; the items are scheduled dynamically). */
+int b3w_debug_set_launch(b3w_ctx *ctx, int ctas_per_sm, uint32_t parts);
+
 /* Per-instance 64-bit checksum of witnesses resident in device memory (reads them back from HBM):
  *   sum_i = SUM over slots s, limbs j of  (limb64[s][j] + 1) * mix(4*s + j)   (mod 2^64),
  *   mix(x) = (x + 1) * 0x9E3779B97F4A7C15  (mod 2^64).  d_sums: n u64. */

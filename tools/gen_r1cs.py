@@ -238,8 +238,24 @@ def check_xorw(model, xorw):
         assert X ^ rot(Y, _bit(y)) == rot(O, _bit(o)), (x, y, o)
 
 
+MERGE_BELOW = 16        # shape classes with fewer rows than this are merged into per-row-coefficient classes
+FLAG_FIELD, FLAG_WIDE, FLAG_XORW, FLAG_ROWCOEF = 1, 2, 4, 8
+_BOUND = {0: 1, 1: (1 << 32) - 1, 2: (1 << 64) - 1, 3: 1 << 63, 4: 1 << 255}
+
+
+def _is_wide(nA, nB, nC, coefs, ones, kinds):
+    """value bounds per kind decide whether 64-bit signed arithmetic is exact for a row of this shape"""
+    mx = lambda lo, hi: sum(abs(coefs[t]) * (1 if ones[t] else _BOUND[kinds[t]]) for t in range(lo, hi))
+    la, lb, lc = mx(0, nA), mx(nA, nA + nB), mx(nA + nB, nA + nB + nC)
+    return la >= 1 << 62 or lb >= 1 << 62 or lc >= 1 << 62 or la * lb >= 1 << 62
+
+
 def classify(rows, xorw=(), one=ONE):
-    """-> list of classes: dict(nA, nB, nC, flags, coefs, cols) with cols[t] = list of descs (one per row)."""
+    """-> list of classes: dict(nA, nB, nC, flags, coefs, cols) with cols[t] = list of descs (one per row).
+    Rows of identical shape AND coefficients share one coefficient vector; the many small groups that remain (rows whose
+    coefficients are all different: IV[i] * is_parent, 2^k recompositions split by circom, ...) are merged by (nA, nB,
+    nC) into classes whose coefficients are stored per row (flag ROWCOEF, coefs term-major), so that a warp still
+    evaluates 32 of them per step instead of one."""
     groups = {}
     for a, bb, c in rows:
         # order terms inside each part by coefficient, then kind, so that equal shapes line up; ONE first
@@ -252,23 +268,32 @@ def classify(rows, xorw=(), one=ONE):
                  tuple(d >> 24 for d, _ in a2 + b2 + c2))
         groups.setdefault(shape, []).append([d for d, _ in a2 + b2 + c2])
     classes = []
+    merged = {}
     for shape, members in sorted(groups.items(), key=lambda kv: (-len(kv[1]), kv[0])):
-        members.sort(key=lambda m: [((d >> 24), d & 0xFFFF, (d >> 16) & 31) for d in m])   # (kind, word, bit): long runs
         nA, nB, nC, coefs, ones, field, kinds = shape
         if field:
             assert nA == 1 and nB == 1 and coefs[0] == 1 and coefs[1] == 1, shape
         assert all(abs(x) < (1 << 100) for x in coefs)
-        # value bounds per kind decide whether 64-bit signed arithmetic is exact for the whole class
-        bound = {0: 1, 1: (1 << 32) - 1, 2: (1 << 64) - 1, 3: 1 << 63, 4: 1 << 255}
-        mx = lambda lo, hi: sum(abs(coefs[t]) * (1 if ones[t] else bound[kinds[t]]) for t in range(lo, hi))
-        la, lb, lc = mx(0, nA), mx(nA, nA + nB), mx(nA + nB, nA + nB + nC)
-        wide = not field and (la >= 1 << 62 or lb >= 1 << 62 or lc >= 1 << 62 or la * lb >= 1 << 62)
+        wide = not field and _is_wide(nA, nB, nC, coefs, ones, kinds)
+        if len(members) < MERGE_BELOW:
+            g = merged.setdefault((nA, nB, nC, field), dict(rows=[], wide=False))
+            g["rows"].extend((m, coefs) for m in members)
+            g["wide"] = g["wide"] or wide
+            continue
+        members.sort(key=lambda m: [((d >> 24), d & 0xFFFF, (d >> 16) & 31) for d in m])   # (kind, word, bit): long runs
         cols = [[m[t] for m in members] for t in range(nA + nB + nC)]
-        classes.append(dict(nA=nA, nB=nB, nC=nC, flags=(1 if field else 0) | (2 if wide else 0), coefs=coefs, cols=cols,
-                            count=len(members)))
+        classes.append(dict(nA=nA, nB=nB, nC=nC, flags=(FLAG_FIELD if field else 0) | (FLAG_WIDE if wide else 0), coefs=coefs,
+                            cols=cols, count=len(members)))
+    for (nA, nB, nC, field), g in sorted(merged.items()):
+        rws = sorted(g["rows"], key=lambda mc: [((d >> 24), d & 0xFFFF, (d >> 16) & 31) for d in mc[0]])
+        nt = nA + nB + nC
+        cols = [[m[t] for m, _ in rws] for t in range(nt)]
+        coefs = tuple(co[t] for t in range(nt) for _, co in rws)          # term-major, one per row
+        classes.append(dict(nA=nA, nB=nB, nC=nC, flags=FLAG_ROWCOEF | (FLAG_FIELD if field else 0) | (FLAG_WIDE if g["wide"] else 0),
+                            coefs=coefs, cols=cols, count=len(rws)))
     if xorw:
         members = sorted(xorw, key=lambda m: [(d & 0xFFFF) for d in m])
-        classes.insert(0, dict(nA=1, nB=1, nC=1, flags=4, coefs=(1, 1, 1), cols=[[m[t] for m in members] for t in range(3)],
+        classes.insert(0, dict(nA=1, nB=1, nC=1, flags=FLAG_XORW, coefs=(1, 1, 1), cols=[[m[t] for m in members] for t in range(3)],
                                count=len(members)))
     return classes
 
