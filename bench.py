@@ -203,7 +203,7 @@ def run_own(args, rank, world, local_rank):
     total_ms = max_over_ranks(ev[0].elapsed_time(ev[-1]))
     launch_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
     kernel_ms = max_over_ranks(sum(launch_ms) / len(launch_ms))
-    gpu_launches = args.steps
+    gpu_launches = world * args.steps                         # one witness kernel per step per rank
     assert int(d_st.max()) == 0
     pub0 = d_pub[:16].cpu().numpy().view(np.uint32)
 

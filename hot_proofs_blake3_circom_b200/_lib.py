@@ -15,7 +15,7 @@ EXPORTS = ("b3w_version", "b3w_last_error", "b3w_create", "b3w_destroy", "b3w_ci
            "b3w_input_signal", "b3w_witness_one", "b3w_witness_batch", "b3w_witness_batch_device",
            "b3w_checksum_device", "b3w_calib_fill", "b3w_host_alloc", "b3w_host_free",
            "b3w_witness_batch_device_checked", "b3w_r1cs_check_device", "b3w_r1cs_info", "b3w_debug_inject_fault",
-           "b3w_nova_chain_size", "b3w_nova_chain", "b3w_debug_set_launch")
+           "b3w_nova_chain_size", "b3w_nova_chain", "b3w_debug_set_launch", "b3w_assert_trace")
 
 
 class B3WError(RuntimeError):
@@ -57,6 +57,7 @@ def lib():
     L.b3w_wtns_header.argtypes = [C.c_uint32, vp]
     L.b3w_input_signal.argtypes = [C.c_uint32, C.c_char_p, u32p, u32p]
     L.b3w_witness_one.argtypes = [vp, vp, vp]
+    L.b3w_assert_trace.argtypes = [C.c_uint32, vp, C.c_char_p, C.c_size_t]
     L.b3w_witness_batch.argtypes = [vp, vp, u64, vp, vp, vp]
     L.b3w_witness_batch_device.argtypes = [vp, vp, u64, vp, vp, vp, vp]
     L.b3w_checksum_device.argtypes = [vp, vp, u64, vp, vp]

@@ -287,7 +287,7 @@ __device__ __forceinline__ void expand_slots(const uint32_t *trace, const uint32
 #define TRACE_STRIDE 960          // u32 words per warp, compression (>= 944, 16-byte multiple)
 #define NOVA_TRACE_STRIDE 1344    // u32 words per warp, nova (>= NOVA_TRACE_WORDS)
 static_assert(NOVA_TRACE_WORDS <= NOVA_TRACE_STRIDE, "nova trace does not fit its stride");
-#define NOVA_SMEM (WARPS_PER_CTA * NOVA_TRACE_STRIDE * 4)
+#define NOVA_SMEM(warps) ((warps) * NOVA_TRACE_STRIDE * 4)
 
 // Optional extras of the checked kernel variants: the fused R1CS check (rows evaluated on the shared-memory trace,
 // nothing re-read from HBM) and a fault-injection hook for its negative tests.
@@ -365,108 +365,163 @@ struct item_pipe {
   }
 };
 
-// k_blake3_comp_witness: compression circuit, one warp per range (see above).
+// The *_checked variants add CHECK_WARPS "checker" warps to every CTA.  The 8 expansion warps run exactly the loop of the
+// plain kernel (so the store stream keeps the shape that reaches the write roofline); the checker warps take whole
+// instances from a second set of counters, recompute the trace and evaluate the R1CS rows on it, filling issue slots the
+// store-bound expansion leaves idle.  A warp whose own queue has run dry helps with the other queue (phase 1), so the
+// launch has no tail of one kind of work.  With the check inside the expansion warps (4 items per witness, every
+// resident CTA) the fused kernels ran at 6.3 (compression) / 4.95 TB/s (nova); see profiles/.
+#ifdef B3W_EXP_NOCHECK              /* experiment builds only: checker warps trace but do not evaluate rows */
+#define B3W_EXP_CHECK(x) B3W_NO_ROW
+#else
+#define B3W_EXP_CHECK(x) (x)
+#endif
+#ifndef CHECK_WARPS
+#define CHECK_WARPS 4
+#endif
+
+// k_blake3_comp_witness: compression circuit, one warp per work item (see above).
 template <bool CHECK>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
+__global__ void __launch_bounds__((WARPS_PER_CTA + (CHECK ? CHECK_WARPS : 0)) * 32, CHECK ? 2 : 4)
 k_blake3_comp_witness(const uint32_t *__restrict__ in, uint64_t n, const uint32_t *__restrict__ desc, uint32_t ws,
                       uint8_t *__restrict__ out, uint8_t *__restrict__ status, uint32_t *__restrict__ pub,
-                      const check_args ck, const sched_args sc) {
-  __shared__ __align__(16) uint32_t s_trace[WARPS_PER_CTA][TRACE_STRIDE];
+                      const check_args ck, const sched_args sc, const sched_args sck) {
+  constexpr int WARPS = WARPS_PER_CTA + (CHECK ? CHECK_WARPS : 0);
+  __shared__ __align__(16) uint32_t s_trace[WARPS][TRACE_STRIDE];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   uint32_t *trace = s_trace[wib];
   if (lane == 0) { trace[TR_ZERO] = 0u; trace[TR_ONE] = 1u; }
   const lane_sched ls = load_lane_sched(lane);
-  for (item_pipe<28> pipe(sc, in, n, lane, (uint64_t)blockIdx.x * WARPS_PER_CTA + wib); pipe.valid();) {
-    const uint64_t i = pipe.inst();
-    const uint32_t part = pipe.part();
-    const uint32_t a = part * sc.part_len, b = a + sc.part_len < ws ? a + sc.part_len : ws;
-    __syncwarp();                               // the previous expansion has finished reading the trace
-    if (lane < 28) trace[TR_IN + lane] = pipe.cur_in;
-    pipe.advance();
-    __syncwarp();
-    compression_trace(trace, lane, ls);
-    __syncwarp();
-    if (part == 0) {                            // this warp owns the instance's head
-      if (pub && lane < 16) pub[i * 16 + lane] = trace[TR_OUT + lane];
-      uint8_t st = 0;                           // u32 inputs can never violate a constraint of this circuit ...
-      if (CHECK) {                              // ... which the fused check confirms row by row
-        if (ck.fault_word != B3W_NO_ROW && lane == 0) trace[ck.fault_word] ^= ck.fault_mask;
+  const bool checker = CHECK && wib >= WARPS_PER_CTA;
+  const bool fault = CHECK && ck.fault_word != B3W_NO_ROW;
+#pragma unroll 1
+  for (int phase = 0; phase < (CHECK ? 2 : 1); phase++) {
+    if (CHECK && checker == (phase == 0)) {
+      // ---- check items: one instance each ----
+      for (item_pipe<28> pipe(sck, in, n, lane, (uint64_t)blockIdx.x * WARPS + wib); pipe.valid();) {
+        const uint64_t i = pipe.inst();
         __syncwarp();
-        const uint32_t bad = r1cs_check_instance(TraceSrc{trace, ck.F}, ck.T, lane);
-        if (bad != B3W_NO_ROW) st = B3W_R1CS_VIOLATION;
+        if (lane < 28) trace[TR_IN + lane] = pipe.cur_in;
+        pipe.advance();
+        __syncwarp();
+        compression_trace(trace, lane, ls);
+        __syncwarp();
+        if (fault && lane == 0) trace[ck.fault_word] ^= ck.fault_mask;
+        __syncwarp();
+        const uint32_t bad = B3W_EXP_CHECK(r1cs_check_instance(TraceSrc{trace, ck.F}, ck.T, lane));
         if (ck.first_bad && lane == 0) ck.first_bad[i] = bad;
+        if (status && lane == 0) status[i] = bad != B3W_NO_ROW ? B3W_R1CS_VIOLATION : 0;
       }
-      if (status && lane == 0) status[i] = st;
-    } else if (CHECK && ck.fault_word != B3W_NO_ROW) {   // keep the injected fault visible in every part of the witness
-      if (lane == 0) trace[ck.fault_word] ^= ck.fault_mask;
-      __syncwarp();
+    } else {
+      // ---- expansion items: 1/parts of one witness each ----
+      for (item_pipe<28> pipe(sc, in, n, lane, (uint64_t)blockIdx.x * WARPS + wib); pipe.valid();) {
+        const uint64_t i = pipe.inst();
+        const uint32_t part = pipe.part();
+        const uint32_t a = part * sc.part_len, b = a + sc.part_len < ws ? a + sc.part_len : ws;
+        __syncwarp();                               // the previous expansion has finished reading the trace
+        if (lane < 28) trace[TR_IN + lane] = pipe.cur_in;
+        pipe.advance();
+        __syncwarp();
+        compression_trace(trace, lane, ls);
+        __syncwarp();
+        if (part == 0) {                            // this warp owns the instance's head
+          if (pub && lane < 16) pub[i * 16 + lane] = trace[TR_OUT + lane];
+          // u32 inputs can never violate a constraint of this circuit (which the fused check confirms row by row)
+          if (!CHECK && status && lane == 0) status[i] = 0;
+        }
+        if (fault) {                                // keep the injected fault visible in the witness
+          if (lane == 0) trace[ck.fault_word] ^= ck.fault_mask;
+          __syncwarp();
+        }
+        expand_slots<false>(trace, desc, a, b, out + i * (uint64_t)ws * 32, lane, nullptr, nullptr, 0);
+      }
     }
-    expand_slots<false>(trace, desc, a, b, out + i * (uint64_t)ws * 32, lane, nullptr, nullptr, 0);
   }
+}
+
+// The 15 outputs z_{i+1} of a nova step, one per lane < 15: n_blocks_out, block_count_out, h_out[8], total_depth_out,
+// depth_out, chunk_idx_low/high_out, leaf_depth_out (circuits/blake3_nova.circom:195-202).
+__device__ __forceinline__ uint32_t nova_public_output(const uint32_t *trace, int lane) {
+  if (lane == 0) return trace[NV_IN + 0];
+  if (lane == 1) return trace[NV_BC_OUT];
+  if (lane < 10) return trace[TR_OUT + lane - 2];
+  if (lane == 10) return trace[NV_IN + 13];
+  if (lane == 11) return trace[NV_DEPTH_OUT];
+  if (lane == 12) return trace[NV_IN + 10];
+  if (lane == 13) return trace[NV_IN + 11];
+  return trace[NV_IN + 12];
 }
 
 // k_blake3_nova_witness: the nova step circuit (all three committed builds share it; they differ in the
 // slot table and the prime).  pub = z_{i+1} = the 15 outputs (low 32 bits each).
 template <bool CHECK>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3)
+__global__ void __launch_bounds__((WARPS_PER_CTA + (CHECK ? CHECK_WARPS : 0)) * 32, CHECK ? 2 : 3)
 k_blake3_nova_witness(const uint32_t *__restrict__ in, uint64_t n, const uint32_t *__restrict__ desc, uint32_t ws,
                       const field_consts *__restrict__ F, const uint2 *__restrict__ fslots, uint32_t n_fslots,
                       uint8_t *__restrict__ out, uint8_t *__restrict__ status, uint32_t *__restrict__ pub,
-                      const check_args ck, const sched_args sc) {
+                      const check_args ck, const sched_args sc, const sched_args sck) {
+  constexpr int WARPS = WARPS_PER_CTA + (CHECK ? CHECK_WARPS : 0);
   extern __shared__ __align__(16) uint32_t s_dyn[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   uint32_t *trace = s_dyn + wib * NOVA_TRACE_STRIDE;
   if (lane == 0) { trace[TR_ZERO] = 0u; trace[TR_ONE] = 1u; }
   const lane_sched ls = load_lane_sched(lane);
-  for (item_pipe<32> pipe(sc, in, n, lane, (uint64_t)blockIdx.x * WARPS_PER_CTA + wib); pipe.valid();) {
-    const uint64_t i = pipe.inst();
-    const uint32_t part = pipe.part();
-    const uint32_t a = part * sc.part_len, b = a + sc.part_len < ws ? a + sc.part_len : ws;
-    const bool head = part == 0;
-    __syncwarp();
-    trace[NV_IN + lane] = pipe.cur_in;
-    pipe.advance();
-    __syncwarp();
-    const bool ok = nova_trace(trace, lane);
-    if (!ok) {                                  // the reference throws "Assert Failed.": no witness exists
-      if (head) {
-        if (status && lane == 0) status[i] = B3W_CIRCOM_ASSERT;
-        if (pub && lane < 15) pub[i * 15 + lane] = 0u;
-        if (CHECK && ck.first_bad && lane == 0) ck.first_bad[i] = B3W_NO_ROW;
-      }
-      continue;
-    }
-    __syncwarp();
-    compression_trace(trace, lane, ls);
-    __syncwarp();
-    if (head) {
-      uint8_t st = 0;
-      if (CHECK) {
-        if (ck.fault_word != B3W_NO_ROW && lane == 0) trace[ck.fault_word] ^= ck.fault_mask;
+  const bool checker = CHECK && wib >= WARPS_PER_CTA;
+  const bool fault = CHECK && ck.fault_word != B3W_NO_ROW;
+#pragma unroll 1
+  for (int phase = 0; phase < (CHECK ? 2 : 1); phase++) {
+    if (CHECK && checker == (phase == 0)) {
+      for (item_pipe<32> pipe(sck, in, n, lane, (uint64_t)blockIdx.x * WARPS + wib); pipe.valid();) {
+        const uint64_t i = pipe.inst();
         __syncwarp();
-        const uint32_t bad = r1cs_check_instance(TraceSrc{trace, ck.F}, ck.T, lane);
-        if (bad != B3W_NO_ROW) st = B3W_R1CS_VIOLATION;
+        trace[NV_IN + lane] = pipe.cur_in;
+        pipe.advance();
+        __syncwarp();
+        if (!nova_trace(trace, lane)) {           // the reference throws "Assert Failed.": no witness exists
+          if (status && lane == 0) status[i] = B3W_CIRCOM_ASSERT;
+          if (ck.first_bad && lane == 0) ck.first_bad[i] = B3W_NO_ROW;
+          continue;
+        }
+        __syncwarp();
+        compression_trace(trace, lane, ls);
+        __syncwarp();
+        if (fault && lane == 0) trace[ck.fault_word] ^= ck.fault_mask;
+        __syncwarp();
+        const uint32_t bad = B3W_EXP_CHECK(r1cs_check_instance(TraceSrc{trace, ck.F}, ck.T, lane));
         if (ck.first_bad && lane == 0) ck.first_bad[i] = bad;
+        if (status && lane == 0) status[i] = bad != B3W_NO_ROW ? B3W_R1CS_VIOLATION : 0;
       }
-      if (status && lane == 0) status[i] = st;
-      if (pub && lane < 15) {
-        // n_blocks_out, block_count_out, h_out[8], total_depth_out, depth_out, chunk_idx_low/high_out, leaf_depth_out (:195-202)
-        uint32_t v;
-        if (lane == 0) v = trace[NV_IN + 0];
-        else if (lane == 1) v = trace[NV_BC_OUT];
-        else if (lane < 10) v = trace[TR_OUT + lane - 2];
-        else if (lane == 10) v = trace[NV_IN + 13];
-        else if (lane == 11) v = trace[NV_DEPTH_OUT];
-        else if (lane == 12) v = trace[NV_IN + 10];
-        else if (lane == 13) v = trace[NV_IN + 11];
-        else v = trace[NV_IN + 12];
-        pub[i * 15 + lane] = v;
+    } else {
+      for (item_pipe<32> pipe(sc, in, n, lane, (uint64_t)blockIdx.x * WARPS + wib); pipe.valid();) {
+        const uint64_t i = pipe.inst();
+        const uint32_t part = pipe.part();
+        const uint32_t a = part * sc.part_len, b = a + sc.part_len < ws ? a + sc.part_len : ws;
+        const bool head = part == 0;
+        __syncwarp();
+        trace[NV_IN + lane] = pipe.cur_in;
+        pipe.advance();
+        __syncwarp();
+        if (!nova_trace(trace, lane)) {
+          if (head) {
+            if (!CHECK && status && lane == 0) status[i] = B3W_CIRCOM_ASSERT;
+            if (pub && lane < 15) pub[i * 15 + lane] = 0u;
+          }
+          continue;
+        }
+        __syncwarp();
+        compression_trace(trace, lane, ls);
+        __syncwarp();
+        if (head) {
+          if (!CHECK && status && lane == 0) status[i] = 0;
+          if (pub && lane < 15) pub[i * 15 + lane] = nova_public_output(trace, lane);
+        }
+        if (fault) {
+          if (lane == 0) trace[ck.fault_word] ^= ck.fault_mask;
+          __syncwarp();
+        }
+        expand_slots<true>(trace, desc, a, b, out + i * (uint64_t)ws * 32, lane, F, fslots, n_fslots);
       }
-    } else if (CHECK && ck.fault_word != B3W_NO_ROW) {
-      if (lane == 0) trace[ck.fault_word] ^= ck.fault_mask;
-      __syncwarp();
     }
-    expand_slots<true>(trace, desc, a, b, out + i * (uint64_t)ws * 32, lane, F, fslots, n_fslots);
   }
 }
 
@@ -781,14 +836,18 @@ extern "C" int b3w_create(const b3w_config *cfg, b3w_ctx **out) {
     delete F;
     if (e1 != cudaSuccess) { b3w_destroy(c); return fail(B3W_ERR_CUDA, "field table upload: %s", cudaGetErrorString(e1)); }
   }
+  const int bs_plain = WARPS_PER_CTA * 32, bs_checked = (WARPS_PER_CTA + CHECK_WARPS) * 32;
   if (d->nova) {
-    e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, k_blake3_nova_witness<false>, WARPS_PER_CTA * 32, NOVA_SMEM);
+    e1 = cudaFuncSetAttribute(k_blake3_nova_witness<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NOVA_SMEM(WARPS_PER_CTA + CHECK_WARPS));
     if (e1 == cudaSuccess)
-      e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm_checked, k_blake3_nova_witness<true>, WARPS_PER_CTA * 32, NOVA_SMEM);
+      e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, k_blake3_nova_witness<false>, bs_plain, NOVA_SMEM(WARPS_PER_CTA));
+    if (e1 == cudaSuccess)
+      e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm_checked, k_blake3_nova_witness<true>, bs_checked,
+                                                         NOVA_SMEM(WARPS_PER_CTA + CHECK_WARPS));
   } else {
-    e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, k_blake3_comp_witness<false>, WARPS_PER_CTA * 32, 0);
+    e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, k_blake3_comp_witness<false>, bs_plain, 0);
     if (e1 == cudaSuccess)
-      e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm_checked, k_blake3_comp_witness<true>, WARPS_PER_CTA * 32, 0);
+      e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm_checked, k_blake3_comp_witness<true>, bs_checked, 0);
   }
   if (e1 != cudaSuccess || c->ctas_per_sm < 1 || c->ctas_per_sm_checked < 1) { b3w_destroy(c); return fail(B3W_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e1)); }
   *out = c;
@@ -882,6 +941,33 @@ extern "C" int b3w_input_signal(uint32_t circuit, const char *name, uint32_t *of
   return fail(B3W_ERR_INVALID, "Signal %s not found", name);
 }
 
+// The text the reference's wasm emits through printErrorMessage when an assert of the nova step circuit fires
+// (witness_calculator.js:21-43 appends it to "Assert Failed.\n"): one line per template on the call stack, innermost
+// first.  Line numbers are those of the circuit AS BUILT into the committed wasm files (circuits/blake3_nova.circom
+// without :25-30, circomlib 2.0.5 bitify/comparators); identical in all three nova builds.  Host-only, needs no GPU.
+extern "C" int b3w_assert_trace(uint32_t circuit, const uint32_t *in, char *buf, size_t cap) {
+  const circuit_def *d = find_def(circuit);
+  if (!d) return B3W_ERR_UNSUPPORTED;
+  if (!in || (!buf && cap)) return fail(B3W_ERR_INVALID, "b3w_assert_trace: null argument");
+  if (cap) buf[0] = 0;
+  if (!d->nova) return B3W_OK;                   // u32 inputs cannot violate a constraint of Blake3Compression
+  const int64_t leaf_depth = in[12], depth = in[14];
+  const int64_t v1 = depth + 256 - (leaf_depth - 1);     // check_parent = LessThan(8)(depth, leaf_depth - 1)   (:31-33 -> :27 as built)
+  const int64_t v2 = leaf_depth + 256 - (depth + 1);     // exceed_depth = GreaterEqThan(8)(depth, leaf_depth)  (:41-43 -> :37)
+  const char *msg = nullptr;
+  if (v1 < 0 || v1 >= 512)
+    msg = "Error in template Num2Bits_2 line: 38\nError in template LessThan_3 line: 96\n"
+          "Error in template Blake3NovaTreePath_CheckDepth_5 line: 27\nError in template Blake3Nova_54 line: 201\n";
+  else if (v2 < 0 || v2 >= 512)
+    msg = "Error in template Num2Bits_2 line: 38\nError in template LessThan_3 line: 96\nError in template GreaterEqThan_4 line: 138\n"
+          "Error in template Blake3NovaTreePath_CheckDepth_5 line: 37\nError in template Blake3Nova_54 line: 201\n";
+  else if (((v2 >> 8) & 1) == 0)                         // exceed_depth.out === 0                              (:44 -> :38)
+    msg = "Error in template Blake3NovaTreePath_CheckDepth_5 line: 38\nError in template Blake3Nova_54 line: 201\n";
+  if (!msg) return B3W_OK;
+  if (cap) snprintf(buf, cap, "%s", msg);
+  return B3W_CIRCOM_ASSERT;
+}
+
 // Expand the class / coefficient / column tables of one R1CS row set (r1cs_tables.h) and upload them.
 static int upload_r1cs_set(b3w_ctx *c, const circuit_def::r1cs_set &set, b3w_ctx::r1cs_dev *out) {
   const size_t ncls = set.ncls;
@@ -938,12 +1024,12 @@ static int launch_witness(b3w_ctx *c, const uint32_t *d_in, uint64_t n, uint8_t 
                           uint32_t *d_pub, cudaStream_t s, bool check = false, uint32_t *d_first_bad = nullptr) {
   if (n == 0) return B3W_OK;
   // Persistent grid, work items handed out dynamically (see sched_args).  Defaults from sweeps on B200 (profiles/):
-  // the plain kernels are fastest with only 2 CTAs (16 warps) per SM and 24 items per witness (32 KiB each: the
-  // GPU-wide write front stays compact); the checked kernels need every warp they can get to hide the check's arithmetic.
-  const uint32_t parts = c->sched_parts ? c->sched_parts : (check ? 4u : 24u);
+  // fastest with only 2 CTAs per SM (16 expansion warps) and 24 items per witness (32 KiB each: the GPU-wide write front
+  // stays compact).  The checked kernels have the same expansion shape plus CHECK_WARPS checker warps per CTA.
+  const uint32_t parts = c->sched_parts ? c->sched_parts : 24u;
   uint64_t ctas_needed = (n * parts + WARPS_PER_CTA - 1) / WARPS_PER_CTA;      // one warp per work item
   int per_sm = check ? c->ctas_per_sm_checked : c->ctas_per_sm;
-  const int cap = c->ctas_limit > 0 ? c->ctas_limit : (check ? per_sm : 2);
+  const int cap = c->ctas_limit > 0 ? c->ctas_limit : 2;
   if (cap < per_sm) per_sm = cap;
   uint64_t max_ctas = (uint64_t)c->sm_count * per_sm;
   unsigned grid = (unsigned)(ctas_needed < max_ctas ? ctas_needed : max_ctas);
@@ -959,20 +1045,25 @@ static int launch_witness(b3w_ctx *c, const uint32_t *d_in, uint64_t n, uint8_t 
     ck.fault_word = c->fault_word;
     ck.fault_mask = c->fault_mask;
   }
-  const unsigned bs = WARPS_PER_CTA * 32;
-  // work distribution (see sched_args)
-  sched_args sc;
+  const unsigned bs = (WARPS_PER_CTA + (check ? CHECK_WARPS : 0)) * 32;
+  // work distribution (see sched_args): expansion items, and -- checked kernels -- one check item per instance
+  sched_args sc, sck;
   if (!c->d_counters) CK(cudaMalloc(&c->d_counters, (size_t)N_SCHED_COUNTERS * SCHED_SET_U64 * sizeof(unsigned long long)));
-  sc.counter = c->d_counters + (size_t)(c->next_counter++ % N_SCHED_COUNTERS) * SCHED_SET_U64;
+  const uint32_t set0 = c->next_counter % N_SCHED_COUNTERS;         // two consecutive counter sets (N_SCHED_COUNTERS is even)
+  c->next_counter += 2;
+  sc.counter = c->d_counters + (size_t)set0 * SCHED_SET_U64;
   sc.parts = parts;
   sc.part_len = ((c->def->ws + sc.parts - 1) / sc.parts + 31) / 32 * 32;
-  CK(cudaMemsetAsync(sc.counter, 0, SCHED_SET_U64 * sizeof(unsigned long long), s));
+  sck.counter = sc.counter + SCHED_SET_U64;
+  sck.parts = 1;
+  sck.part_len = 0;
+  CK(cudaMemsetAsync(sc.counter, 0, 2 * SCHED_SET_U64 * sizeof(unsigned long long), s));
   if (c->def->nova) {
-    if (check) k_blake3_nova_witness<true><<<grid, bs, NOVA_SMEM, s>>>(d_in, n, c->d_desc, c->def->ws, c->d_field, c->d_fslots, c->n_fslots, d_out, d_status, d_pub, ck, sc);
-    else k_blake3_nova_witness<false><<<grid, bs, NOVA_SMEM, s>>>(d_in, n, c->d_desc, c->def->ws, c->d_field, c->d_fslots, c->n_fslots, d_out, d_status, d_pub, ck, sc);
+    if (check) k_blake3_nova_witness<true><<<grid, bs, NOVA_SMEM(WARPS_PER_CTA + CHECK_WARPS), s>>>(d_in, n, c->d_desc, c->def->ws, c->d_field, c->d_fslots, c->n_fslots, d_out, d_status, d_pub, ck, sc, sck);
+    else k_blake3_nova_witness<false><<<grid, bs, NOVA_SMEM(WARPS_PER_CTA), s>>>(d_in, n, c->d_desc, c->def->ws, c->d_field, c->d_fslots, c->n_fslots, d_out, d_status, d_pub, ck, sc, sck);
   } else {
-    if (check) k_blake3_comp_witness<true><<<grid, bs, 0, s>>>(d_in, n, c->d_desc, c->def->ws, d_out, d_status, d_pub, ck, sc);
-    else k_blake3_comp_witness<false><<<grid, bs, 0, s>>>(d_in, n, c->d_desc, c->def->ws, d_out, d_status, d_pub, ck, sc);
+    if (check) k_blake3_comp_witness<true><<<grid, bs, 0, s>>>(d_in, n, c->d_desc, c->def->ws, d_out, d_status, d_pub, ck, sc, sck);
+    else k_blake3_comp_witness<false><<<grid, bs, 0, s>>>(d_in, n, c->d_desc, c->def->ws, d_out, d_status, d_pub, ck, sc, sck);
   }
   CK(cudaGetLastError());
   return B3W_OK;

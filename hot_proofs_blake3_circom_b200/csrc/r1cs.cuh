@@ -11,13 +11,15 @@
 //                that the expansion is about to read (nothing is re-read from HBM).  In trace space the rows that are
 //                identities for ANY trace content (booleanity of a bit extracted by shift-and-mask; w == sum 2^i
 //                bit_i(w)) need no evaluation, and the 32 rows 2*x_i*y_i = x_i + y_i - o_i over the bits of one word
-//                triple are evaluated bit-sliced as ONE word comparison (class flag XORW): the *_FUSED row sets;
+//                triple are evaluated bit-sliced as ONE word comparison (class flag XORW), and a recomposition row
+//                whose only content in trace space is "these bits of that word are 0" (e.g. Bits34: the carry word
+//                of a 34-bit sum is < 4) is evaluated as ONE mask test (class flag ZMASK): the *_FUSED row sets;
 //   SlotSrc   -- the stand-alone check of witnesses resident in HBM: a term is a witness SLOT index and its value
 //                is the 32-byte field element found there.
 // Arithmetic: every row of these circuits except IsZero's `in*inv = 1 - out` is an identity between integers far
 // below p (bits, u32 words, <= 66-bit sums, small negatives), so it is evaluated exactly in signed 64-bit (NARROW
 // classes) or signed 128-bit (WIDE) integers; the 67 IsZero rows per nova witness go through Montgomery
-// multiplication in Fr (FIELD classes).  A slot that holds anything but a small (|x| < 2^63) integer inside an
+// multiplication in Fr (FIELD classes) in the stand-alone check and are folded to integer tests (ISZ) in the fused one.  A slot that holds anything but a small (|x| < 2^63) integer inside an
 // integer row cannot satisfy it and is reported as a violation.
 #pragma once
 #include <stdint.h>
@@ -28,6 +30,8 @@
 #define R1CS_FLAG_WIDE 2u
 #define R1CS_FLAG_XORW 4u     /* fused set only: 32 XOR rows of one word triple, X ^ rotr(Y, dy) == rotr(O, do) */
 #define R1CS_FLAG_ROWCOEF 8u  /* coefficients are stored per row (term-major) instead of once per class */
+#define R1CS_FLAG_ZMASK 16u   /* fused set only: a bit-recomposition row, folded to  trace[word] & mask == 0 */
+#define R1CS_FLAG_ISZ 32u     /* fused set only: IsZero's in * inv = C.z with inv = INV(in), folded to  C.z == (in != 0) */
 #define B3W_NO_ROW 0xFFFFFFFFu
 
 struct r1cs_class_dev {
@@ -49,6 +53,10 @@ struct TraceSrc {
   const uint32_t *trace;
   const field_consts *F;
   __device__ __forceinline__ bool xorw(const r1cs_class_dev &c, const r1cs_tables_dev &T, uint32_t r) const;
+  __device__ __forceinline__ bool zmask(const r1cs_class_dev &c, const r1cs_tables_dev &T, uint32_t r) const {
+    const uint32_t *tm = T.terms + c.term_off;
+    return (trace[tm[r] & 0xFFFFu] & tm[c.count + r]) == 0u;
+  }
   __device__ __forceinline__ bool small(uint32_t d, i128 &v) const {
     const uint32_t t = d & 0xFFFFu, k = (d >> 16) & 31u, kind = d >> 24;
     const uint32_t w = trace[t];
@@ -101,6 +109,7 @@ struct SlotSrc {
   }
   __device__ __forceinline__ fr_t field(uint32_t s) const { return load(s); }
   __device__ __forceinline__ bool xorw(const r1cs_class_dev &, const r1cs_tables_dev &, uint32_t) const { return false; }
+  __device__ __forceinline__ bool zmask(const r1cs_class_dev &, const r1cs_tables_dev &, uint32_t) const { return false; }
 };
 __device__ __forceinline__ bool TraceSrc::xorw(const r1cs_class_dev &c, const r1cs_tables_dev &T, uint32_t r) const {
   return r1cs_xorw_row(trace, c, T, r);
@@ -126,25 +135,65 @@ __device__ __noinline__ bool r1cs_field_row(const Src &src, const r1cs_class_dev
   return eq;
 }
 
-template <class Src, typename acc_t>
-__device__ __forceinline__ bool r1cs_int_row(const Src &src, const r1cs_class_dev &c, const r1cs_tables_dev &T, uint32_t r) {
+// ISZ row (fused set): A = the IsZero input (a small integer), no B, C.z must equal (in != 0).
+template <class Src>
+__device__ __forceinline__ bool r1cs_isz_row(const Src &src, const r1cs_class_dev &c, const r1cs_tables_dev &T, uint32_t r) {
   const uint32_t *tm = T.terms + c.term_off;
-  acc_t L[3] = {0, 0, 0};
+  i128 x, lc = 0;
+  bool ok = src.small(tm[r], x);
+  for (uint32_t t = 1; t <= c.nC; t++) {
+    i128 v;
+    ok = src.small(tm[t * c.count + r], v) && ok;
+    lc += (i128)T.coef_lo[(c.flags & R1CS_FLAG_ROWCOEF) ? c.coef_off + t * c.count + r : c.coef_off + t] * v;
+  }
+  return ok && lc == (x != 0 ? 1 : 0);
+}
+
+// Integer rows, U rows per lane at a time (rows r0, r0 + 32, ...): the U accumulator chains are independent, so the
+// descriptor / coefficient / value loads of U rows are in flight together -- the check is latency-bound, not issue-bound
+// (profiles/: one row per lane left the fused nova kernel at 4.95 TB/s with 35 % of the issue slots used).  Rows past
+// the end of the class are clamped to its last row and their verdict ignored, which keeps every load unconditional.
+// Returns the smallest violated row id of this lane's group, or B3W_NO_ROW.
+template <class Src, typename acc_t, int U>
+__device__ __forceinline__ uint32_t r1cs_int_rows(const Src &src, const r1cs_class_dev &c, const r1cs_tables_dev &T, uint32_t r0) {
+  const uint32_t *tm = T.terms + c.term_off;
+  const uint32_t last = c.count - 1;
+  uint32_t r[U];
+  acc_t L[U][3];
+  bool ok[U];
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    r[u] = min(r0 + 32u * u, last);
+    L[u][0] = L[u][1] = L[u][2] = 0;
+    ok[u] = true;
+  }
   const uint32_t n[3] = {c.nA, c.nB, c.nC};
+  const bool rowcoef = (c.flags & R1CS_FLAG_ROWCOEF) != 0;
   uint32_t t = 0;
-  bool ok = true;
 #pragma unroll
   for (int part = 0; part < 3; part++) {
     for (uint32_t j = 0; j < n[part]; j++, t++) {
-      i128 v;
-      ok = src.small(tm[t * c.count + r], v) && ok;
-      const uint32_t ci = (c.flags & R1CS_FLAG_ROWCOEF) ? c.coef_off + t * c.count + r : c.coef_off + t;
-      acc_t co = sizeof(acc_t) == 16 ? (acc_t)(((i128)T.coef_hi[ci] << 64) | (i128)(uint64_t)T.coef_lo[ci]) : (acc_t)T.coef_lo[ci];
-      L[part] += co * (acc_t)v;
+      const uint32_t *col = tm + t * c.count;
+      uint32_t d[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) d[u] = col[r[u]];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const uint32_t ci = rowcoef ? c.coef_off + t * c.count + r[u] : c.coef_off + t;
+        const acc_t co = sizeof(acc_t) == 16 ? (acc_t)(((i128)T.coef_hi[ci] << 64) | (i128)(uint64_t)T.coef_lo[ci]) : (acc_t)T.coef_lo[ci];
+        i128 v;
+        ok[u] = src.small(d[u], v) && ok[u];
+        L[u][part] += co * (acc_t)v;
+      }
     }
   }
-  if (!ok) return false;
-  return c.nA == 0 ? L[2] == 0 : L[0] * L[1] == L[2];
+  uint32_t bad = B3W_NO_ROW;
+#pragma unroll
+  for (int u = U - 1; u >= 0; u--) {
+    const bool holds = ok[u] && (c.nA == 0 ? L[u][2] == 0 : L[u][0] * L[u][1] == L[u][2]);
+    if (!holds && r0 + 32u * u <= last) bad = c.row_off + r[u];
+  }
+  return bad;
 }
 
 // Evaluate every row of one instance with one warp.  Returns the smallest violated row id over the warp's lanes
@@ -154,13 +203,21 @@ __device__ __forceinline__ uint32_t r1cs_check_instance(const Src &src, const r1
   uint32_t bad = B3W_NO_ROW;
   for (uint32_t ci = 0; ci < T.n_classes; ci++) {
     const r1cs_class_dev c = T.cls[ci];
-    for (uint32_t r = lane; r < c.count; r += 32) {
-      bool ok;
-      if (c.flags & R1CS_FLAG_XORW) ok = src.xorw(c, T, r);
-      else if (c.flags & R1CS_FLAG_FIELD) ok = r1cs_field_row(src, c, T, r);
-      else if (c.flags & R1CS_FLAG_WIDE) ok = r1cs_int_row<Src, i128>(src, c, T, r);
-      else ok = r1cs_int_row<Src, int64_t>(src, c, T, r);
-      if (!ok) bad = min(bad, c.row_off + r);
+    if (c.flags & R1CS_FLAG_ZMASK) {
+      for (uint32_t r = lane; r < c.count; r += 32)
+        if (!src.zmask(c, T, r)) bad = min(bad, c.row_off + r);
+    } else if (c.flags & R1CS_FLAG_ISZ) {
+      for (uint32_t r = lane; r < c.count; r += 32)
+        if (!r1cs_isz_row(src, c, T, r)) bad = min(bad, c.row_off + r);
+    } else if (c.flags & (R1CS_FLAG_XORW | R1CS_FLAG_FIELD)) {
+      for (uint32_t r = lane; r < c.count; r += 32) {
+        const bool ok = (c.flags & R1CS_FLAG_XORW) ? src.xorw(c, T, r) : r1cs_field_row(src, c, T, r);
+        if (!ok) bad = min(bad, c.row_off + r);
+      }
+    } else if (c.flags & R1CS_FLAG_WIDE) {
+      for (uint32_t r = lane; r < c.count; r += 64) bad = min(bad, r1cs_int_rows<Src, i128, 2>(src, c, T, r));
+    } else {
+      for (uint32_t r = lane; r < c.count; r += 128) bad = min(bad, r1cs_int_rows<Src, int64_t, 4>(src, c, T, r));
     }
   }
 #pragma unroll

@@ -168,9 +168,19 @@ class WitnessCalculator:
         out = np.empty(self.witnessSize * 32, np.uint8)
         rc = self._L.b3w_witness_one(self._h, row.ctypes.data, out.ctypes.data)
         if rc == _lib.B3W_CIRCOM_ASSERT:
-            raise RuntimeError("Error: Assert Failed.\n")
+            # witness_calculator.js:21-39,159-162: Error("Assert Failed.\n" + the printErrorMessage lines), re-wrapped
+            raise RuntimeError("Error: Assert Failed.\n" + self.assertTrace(row))
         _lib.check(rc)
         return out
+
+    def assertTrace(self, row):
+        """The per-template error trace of the reference for an input row that asserts ("" if it does not)."""
+        row = np.ascontiguousarray(row, np.uint32)
+        buf = C.create_string_buffer(1024)
+        rc = self._L.b3w_assert_trace(self.circuit, row.ctypes.data, buf, len(buf))
+        if rc not in (0, _lib.B3W_CIRCOM_ASSERT):
+            _lib.check(rc)
+        return buf.value.decode()
 
     # ---- the three reference read-outs ----
     def calculateWitness(self, inp, sanityCheck=0):

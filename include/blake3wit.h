@@ -82,6 +82,12 @@ int b3w_wtns_header(uint32_t circuit, uint8_t hdr[76]);
  * (witness_calculator.js:141).  Returns B3W_ERR_INVALID for an unknown name. */
 int b3w_input_signal(uint32_t circuit, const char *name, uint32_t *offset, uint32_t *size);
 
+/* The per-template trace that the reference appends to "Assert Failed.\n" when a constraint of the circuit fails
+ * (printErrorMessage, witness_calculator.js:40-43; e.g. "Error in template Blake3NovaTreePath_CheckDepth_5 line: 38\n
+ * Error in template Blake3Nova_54 line: 201\n").  in: n_inputs u32 (host).  Returns 0 (buf = "") when the input asserts
+ * nowhere, else B3W_CIRCOM_ASSERT with the trace text in buf (truncated to cap).  Host-only, needs no GPU. */
+int b3w_assert_trace(uint32_t circuit, const uint32_t *in, char *buf, size_t cap);
+
 /* replaces _doCalculateWitness + calculateBinWitness for ONE input (witness_calculator.js:131-205).
  * in: n_inputs u32 (host).  out: witness_size*32 bytes (host), canonical little-endian Fr256.
  * Returns 0 or B3W_CIRCOM_ASSERT (out is then untouched beyond what was written). */

@@ -75,3 +75,36 @@ def test_input_generators():
     nz = (np.arange(16)[None, :] >= (b[:, 26] // 4)[:, None])
     assert not b[:, 8:24][nz].any()
     assert (gen.splitmix_compression_inputs(10, first=100) == gen.splitmix_compression_inputs(110)[100:]).all()
+
+
+# ---- the assert trace text of the nova circuits (witness_calculator.js:21-43), against the reference's own wasm ----
+@pytest.mark.parametrize("variant,cid", [("nova_bn_o2", 1), ("nova_pasta_o2", 2), ("nova_bn_o1", 3)])
+def test_assert_trace_matches_reference_wasm(built, variant, cid):
+    import ctypes as C
+    from oracle import ref_wasm
+    if not ref_wasm.available(variant):
+        pytest.skip("oracle/_ref not built")
+    ref = ref_wasm.RefWasm(variant)
+    L = pkg.lib()
+    buf = C.create_string_buffer(1024)
+    seen = set()
+    cases = [(3, 3), (3, 300), (600, 1), (0, 0), (3, 1), (257, 0), (258, 1), (256, 0), (1, 0), (64, 63), (64, 64),
+             (0xFFFFFFFF, 0), (0, 0xFFFFFFFF), (300, 43), (300, 44), (5, 260), (5, 261)]
+    for leaf, depth in cases:
+        row = np.zeros(32, np.uint32)
+        row[0], row[2:10], row[12], row[13], row[14], row[31] = 2, 1, leaf, 3, depth, 64
+        rc = L.b3w_assert_trace(cid, row.ctypes.data, buf, len(buf))
+        d = dict(n_blocks=2, block_count=0, h=[1] * 8, chunk_idx_low=0, chunk_idx_high=0, leaf_depth=leaf, total_depth=3,
+                 depth=depth, m=[0] * 16, b=64)
+        rc_ref, _ = ref.calculate(d)
+        assert rc == rc_ref, (leaf, depth)
+        assert buf.value.decode() == ref.err_msg(), (leaf, depth)
+        seen.add(buf.value.decode())
+    assert len(seen) == 4          # no assert + the three assert sites reachable with u32 inputs
+
+
+def test_assert_trace_empty_for_compression(built):
+    import ctypes as C
+    buf = C.create_string_buffer(64)
+    row = np.full(28, 0xFFFFFFFF, np.uint32)
+    assert pkg.lib().b3w_assert_trace(0, row.ctypes.data, buf, len(buf)) == 0 and buf.value == b""

@@ -1,0 +1,289 @@
+#!/usr/bin/env python3
+"""export_r1cs.py -- regenerate the `.r1cs` / `.sym` artefacts that are missing from the reference tree
+(/root/reference/.MISSING_LARGE_BLOBS: every build/**/*.r1cs and the nova .sym files) from the template-derived
+constraint system of tools/circuit_model.py.  SURVEY.md 8(f) rank 4.
+
+    python tools/export_r1cs.py <variant> <out_dir>      variant: compression | nova_bn_o2 | nova_pasta_o2 | nova_bn_o1 | all
+
+What is reproduced and how it is pinned
+  * wire order      = the witness -> signal table inside the reference's committed wasm (authoritative);
+  * labels (.sym)   = circom's signal numbering re-derived by the model (validated against all 69 380 rows of the
+                      committed build/blake3_compression/blake3_compression.sym and against wasm signal memory);
+  * constraints     = one row per `<==` / `===` of the circom source, then the simplification circom applies:
+        O1 builds (blake3_compression, circomkit nova): aliases `a <== b` merged, constants folded;
+        O2 builds (blake3_nova_js, blake3_nova_pasta_js): additionally every linear constraint is solved for the one
+        signal that the reference's O2 witness no longer contains and substituted into the remaining rows.
+    Row ORDER and per-row scaling are circom-internal and not recoverable without the original files, so the output is
+    an EQUIVALENT system (same wires, same solution set), not a byte-identical file.  Every exported system is checked
+    here against witnesses computed by the reference's own wasm programs (Oracle A): all rows hold.
+
+File format: iden3 r1cs binary v1 (magic "r1cs", sections 1 header / 2 constraints / 3 wire->label map), the format
+snarkjs, circom_tester and circom-scotia (rust_fold/src/blake3_circuit.rs:303 `CircomConfig::new(wasm, r1cs)`) read.
+`.sym` rows: `labelIdx,wireIdx,componentIdx,name` (wireIdx -1 for signals without a wire; componentIdx is not
+re-derived for the nova circuits and is written as -1 there).
+"""
+import os
+import random
+import struct
+import sys
+from fractions import Fraction
+from math import lcm
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import numpy as np  # noqa: E402
+import circuit_model as cm  # noqa: E402
+import gen_tables as gt  # noqa: E402
+
+VARIANTS = ("compression", "nova_bn_o2", "nova_pasta_o2", "nova_bn_o1")
+# (public outputs, public inputs, private inputs): circuits/main/*.circom:6, circuits.json:1-18
+IO_COUNTS = {"compression": (16, 0, 28), "nova": (15, 12, 20)}
+
+
+def _is_alias(A, B, C):
+    if A or B or len(C) != 2 or 0 in C:
+        return False
+    v = list(C.values())
+    return v[0] == -v[1] and abs(v[0]) == 1
+
+
+def derive(model, w2s):
+    """-> (rows, wire_of_signal).  rows: list of (A, B, C) dicts wire -> int coefficient over the wires of `w2s`
+    (wire 0 = the constant 1); linear rows have empty A and B."""
+    b = model.b
+    n = len(b.names)
+    parent = list(range(n))
+
+    def find(x):
+        while parent[x] != x:
+            parent[x] = parent[parent[x]]
+            x = parent[x]
+        return x
+
+    for A, B, C in b.cons:
+        if _is_alias(A, B, C):
+            x, y = (find(k) for k in C)
+            if x != y:
+                parent[max(x, y)] = min(x, y)
+    wire_of, extra_eq = {0: 0}, []
+    for wire, sig in enumerate(w2s):
+        r = find(int(sig))
+        if r in wire_of and wire_of[r] != wire:
+            extra_eq.append((wire_of[r], wire))          # two wires carry one alias class: keep them tied together
+        else:
+            wire_of[r] = wire
+    # substitutions for classes without a wire: class -> {key: Fraction}, key = wire index
+    subst = {}
+
+    def lc_of(D):
+        """signal-level linear combination -> {wire: Fraction}, or None while a class in it is still unresolved"""
+        out = {}
+        for k, co in D.items():
+            r = 0 if k == 0 else find(k)
+            if r in wire_of:
+                out[wire_of[r]] = out.get(wire_of[r], 0) + Fraction(co)
+            elif r in subst:
+                for w, c2 in subst[r].items():
+                    out[w] = out.get(w, 0) + co * c2
+            else:
+                return None
+        return {w: c for w, c in out.items() if c}
+
+    def const_of_lc(D):
+        """value of a signal-level linear combination if it is a resolved constant, else None"""
+        lc = lc_of(D)
+        if lc is None or any(w != 0 for w in lc):
+            return None
+        return lc.get(0, Fraction(0))
+
+    # Fixpoint: a linear row with exactly one class that has no wire defines that class (circom's O2 substitution; in
+    # the O1 builds only constants are resolved this way).  A product whose A or B side has become a constant is
+    # linear too (e.g. tmpIV[i] <== iv.out[i] * is_parent once iv.out[i] is known to be IV[i]).
+    pending = [({}, {}, C) for A, B, C in b.cons if not A and not B and not _is_alias(A, B, C)]
+    pending += [(A, B, C) for A, B, C in b.cons if A or B]
+    kept_linear, quadratic = [], []
+    while pending:
+        progress, nxt = False, []
+        for A, B, C in pending:
+            if A or B:
+                ca, cb = const_of_lc(A), const_of_lc(B)
+                if ca is None and cb is None:
+                    if lc_of(A) is not None and lc_of(B) is not None and lc_of(C) is not None:
+                        quadratic.append((A, B, C))
+                        progress = True
+                    else:
+                        nxt.append((A, B, C))
+                    continue
+                k, other = (ca, B) if ca is not None else (cb, A)         # k * other - C = 0
+                assert k.denominator == 1
+                lin = {s_: -co for s_, co in C.items()}
+                for s_, co in other.items():
+                    lin[s_] = lin.get(s_, 0) + int(k) * co
+                C = {s_: co for s_, co in lin.items() if co}
+                progress = True
+                if not C:
+                    continue
+            missing = {find(k) for k in C if k != 0 and find(k) not in wire_of and find(k) not in subst}
+            if len(missing) > 1:
+                nxt.append(({}, {}, C))
+                continue
+            progress = True
+            if not missing:
+                lc = lc_of(C)
+                if lc:                                    # a linear row between surviving wires stays a constraint
+                    kept_linear.append(lc)
+                continue
+            x = missing.pop()
+            cx = sum(co for k, co in C.items() if k != 0 and find(k) == x)
+            assert cx != 0
+            rest = lc_of({k: co for k, co in C.items() if k == 0 or find(k) != x})
+            subst[x] = {w: -c / cx for w, c in rest.items()}
+        assert progress, "constraints cannot be solved for the dropped signals one at a time"
+        pending = nxt
+
+    def integral(parts):
+        """scale A, B, C (Fraction coefficients) to integers keeping A*B = C"""
+        A, B, C = parts
+        da = lcm(*[c.denominator for c in A.values()]) if A else 1
+        db = lcm(*[c.denominator for c in B.values()]) if B else 1
+        A = {w: c * da for w, c in A.items()}
+        B = {w: c * db for w, c in B.items()}
+        C = {w: c * da * db for w, c in C.items()}
+        dc = lcm(*[c.denominator for c in C.values()]) if C else 1
+        if dc != 1:
+            C = {w: c * dc for w, c in C.items()}
+            if A:
+                A = {w: c * dc for w, c in A.items()}
+            # a linear row (no A, B) is simply scaled
+        return tuple({w: int(c) for w, c in P.items()} for P in (A, B, C))
+
+    rows, seen = [], set()
+
+    def add(A, B, C):
+        A, B, C = integral((A, B, C))
+        if not A or not B:
+            A, B = {}, {}
+            if not C:
+                return
+        key = (tuple(sorted(A.items())), tuple(sorted(B.items())), tuple(sorted(C.items())))
+        if key not in seen:
+            seen.add(key)
+            rows.append((A, B, C))
+
+    for A, B, C in quadratic:
+        add(lc_of(A), lc_of(B), lc_of(C))
+    for lc in kept_linear:
+        add({}, {}, lc)
+    for w0, w1 in extra_eq:
+        add({}, {}, {w0: Fraction(1), w1: Fraction(-1)})
+    wire_of_signal = [wire_of.get(find(i), -1) if find(i) in wire_of else -1 for i in range(n)]
+    return rows, wire_of_signal
+
+
+def check_rows(rows, witness_ints, p):
+    for A, B, C in rows:
+        la = sum(co * witness_ints[w] for w, co in A.items()) % p
+        lb = sum(co * witness_ints[w] for w, co in B.items()) % p
+        lc = sum(co * witness_ints[w] for w, co in C.items()) % p
+        if (la * lb - lc) % p:
+            return (A, B, C)
+    return None
+
+
+def write_r1cs(path, rows, prime, n_wires, n_pub_out, n_pub_in, n_prv_in, labels):
+    def lc_bytes(D):
+        out = [struct.pack("<I", len(D))]
+        for w in sorted(D):
+            out.append(struct.pack("<I", w) + (D[w] % prime).to_bytes(32, "little"))
+        return b"".join(out)
+    header = struct.pack("<I", 32) + prime.to_bytes(32, "little") + struct.pack("<IIIIQI", n_wires, n_pub_out, n_pub_in, n_prv_in,
+                                                                               len(labels), len(rows))
+    cons = b"".join(lc_bytes(A) + lc_bytes(B) + lc_bytes(C) for A, B, C in rows)
+    w2l = b"".join(struct.pack("<Q", int(x)) for x in labels[:0]) if False else np.asarray(labels, "<u8").tobytes()
+    with open(path, "wb") as f:
+        f.write(b"r1cs" + struct.pack("<II", 1, 3))
+        for sec_type, body in ((1, header), (2, cons), (3, w2l)):
+            f.write(struct.pack("<IQ", sec_type, len(body)) + body)
+
+
+def read_r1cs(path):
+    """-> dict(prime, n_wires, n_pub_out, n_pub_in, n_prv_in, n_labels, rows=[(A, B, C)], wire2label)"""
+    data = open(path, "rb").read()
+    assert data[:4] == b"r1cs"
+    version, n_sec = struct.unpack_from("<II", data, 4)
+    assert version == 1
+    pos, secs = 12, {}
+    for _ in range(n_sec):
+        t, ln = struct.unpack_from("<IQ", data, pos)
+        secs[t] = data[pos + 12: pos + 12 + ln]
+        pos += 12 + ln
+    h = secs[1]
+    fs = struct.unpack_from("<I", h, 0)[0]
+    prime = int.from_bytes(h[4:4 + fs], "little")
+    n_wires, n_pub_out, n_pub_in, n_prv_in, n_labels, m = struct.unpack_from("<IIIIQI", h, 4 + fs)
+    rows, c, pos = [], secs[2], 0
+
+    def lc():
+        nonlocal pos
+        k = struct.unpack_from("<I", c, pos)[0]
+        pos += 4
+        D = {}
+        for _ in range(k):
+            w = struct.unpack_from("<I", c, pos)[0]
+            D[w] = int.from_bytes(c[pos + 4: pos + 4 + fs], "little")
+            pos += 4 + fs
+        return D
+    for _ in range(m):
+        rows.append((lc(), lc(), lc()))
+    assert pos == len(c)
+    return dict(prime=prime, n_wires=n_wires, n_pub_out=n_pub_out, n_pub_in=n_pub_in, n_prv_in=n_prv_in, n_labels=n_labels,
+                rows=rows, wire2label=np.frombuffer(secs[3], "<u8"))
+
+
+def write_sym(path, names, wire_of_signal):
+    with open(path, "w") as f:
+        for i in range(1, len(names)):
+            f.write("%d,%d,-1,%s\n" % (i, wire_of_signal[i], names[i]))
+
+
+def export(variant, out_dir, trials=3, verbose=True):
+    from oracle.ref_wasm import RefWasm
+    ref = RefWasm(variant)
+    w2s = np.frombuffer(ref.memory(gt.W2S_OFFSET[variant], 4 * ref.witness_size), np.uint32)
+    rng = random.Random(2024)
+    rows0 = None
+    for trial in range(trials):
+        inputs = gt.random_inputs(variant, rng, edge=0 if variant != "compression" else trial)
+        mdl = gt.model_for(variant, inputs, ref.prime)
+        rows, wire_of_signal = derive(mdl, w2s)
+        key = [(sorted(A.items()), sorted(B.items()), sorted(C.items())) for A, B, C in rows]
+        assert rows0 is None or key == rows0, "constraint structure depends on the input"
+        rows0 = key
+        d, pos = {}, 0
+        for nm, sz in ref.plan:
+            d[nm] = inputs[pos:pos + sz]
+            pos += sz
+        rc, wit = ref.calculate(d)
+        assert rc == 0
+        wi = [int.from_bytes(wit[32 * i:32 * i + 32].tobytes(), "little") for i in range(ref.witness_size)]
+        bad = check_rows(rows, wi, ref.prime)
+        assert bad is None, "the reference's own witness violates %r" % (bad,)
+    io = IO_COUNTS["compression" if variant == "compression" else "nova"]
+    os.makedirs(out_dir, exist_ok=True)
+    stem = {"compression": "blake3_compression", "nova_bn_o2": "blake3_nova", "nova_pasta_o2": "blake3_nova_pasta",
+            "nova_bn_o1": "blake3_nova_o1"}[variant]
+    r1 = os.path.join(out_dir, stem + ".r1cs")
+    write_r1cs(r1, rows, ref.prime, ref.witness_size, io[0], io[1], io[2], [int(s) for s in w2s])
+    write_sym(os.path.join(out_dir, stem + ".sym"), mdl.b.names, wire_of_signal)
+    nq = sum(1 for A, B, C in rows if A)
+    if verbose:
+        print("%-14s %s: %d wires, %d labels, %d constraints (%d quadratic + %d linear); the reference's witnesses satisfy all rows"
+              % (variant, r1, ref.witness_size, len(mdl.b.names), len(rows), nq, len(rows) - nq))
+    return r1, rows
+
+
+if __name__ == "__main__":
+    which = VARIANTS if sys.argv[1] == "all" else (sys.argv[1],)
+    for v in which:
+        export(v, sys.argv[2])

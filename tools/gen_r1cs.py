@@ -199,17 +199,66 @@ def is_trace_identity(row):
     return all(v == 0 for v in acc.values())
 
 
+def zero_mask_form(row):
+    """A linear row over BIT / W32 / W64 values, rewritten on the bits of the trace words it mentions (W32(t) = sum 2^i
+    BIT(t, i), W64(t) = W32(t) + 2^32 W32(t+1): identities of the expansion).  If what is left is a sum of bits with
+    coefficients of ONE sign and no constant, the row holds exactly when every one of those bits is 0 (the sum is far
+    below p, nothing wraps): returns {trace word: mask of bits that must be 0}.  None if the row has another form.
+    Example: Bits34's  add1.inp = sum 2^i out_bits[i] + 2^32 u + 2^33 v  with inp = W64(s, hi), out_bits = bits of s,
+    u / v = bits 0 / 1 of hi  <=>  hi & ~3 == 0."""
+    a, b, c = row
+    if a or b:
+        return None
+    acc = {}
+    for d, co in c:
+        if d == ONE:
+            acc[("one",)] = acc.get(("one",), 0) + co
+            continue
+        k = _kind(d)
+        if k == 0:
+            acc[(_word(d), _bit(d))] = acc.get((_word(d), _bit(d)), 0) + co
+        elif k in (1, 2):
+            for i in range(32 * k):
+                key = (_word(d) + (i >> 5), i & 31)
+                acc[key] = acc.get(key, 0) + (co << i)
+        else:
+            return None
+    acc = {k: v for k, v in acc.items() if v}
+    if not acc or ("one",) in acc:
+        return None
+    if not (all(v > 0 for v in acc.values()) or all(v < 0 for v in acc.values())):
+        return None
+    if sum(abs(v) for v in acc.values()) >= 1 << 200:
+        return None
+    masks = {}
+    for (w, i) in acc:
+        masks[w] = masks.get(w, 0) | (1 << i)
+    return masks
+
+
 def fuse_rows(rows):
     """Trace-space row set for the fused check: identities dropped, and every complete group of 32 XOR rows
     2*x_i*y_i = x_i + y_i - o_i over the bits of three words folded into ONE word-level row
     X ^ rotr(Y, dy) == rotr(O, do)  (flag XORW; the rotation rides in the descriptor's bit field)."""
     kept, xor_groups = [], {}
     n_ident = 0
+    zmask = {}
     for row in rows:
         if is_trace_identity(row):
             n_ident += 1
             continue
+        zm = zero_mask_form(row)
+        if zm is not None:
+            zmask[row] = zm
+            continue
         a, b, c = row
+        # IsZero:  in * inv = 1 - out  with in = S64(t) and inv = INV(t) of the SAME trace word: the product is 1 for
+        # in != 0 and 0 for in = 0 by the definition of the INV slot, so in trace space the row says  C.z == (in != 0)
+        # and needs no field arithmetic (flag ISZ; kept with A = in, no B).
+        if (len(a) == 1 and len(b) == 1 and a[0][1] == 1 and b[0][1] == 1 and _kind(a[0][0]) == 3 and _kind(b[0][0]) == KIND_INV
+                and _word(a[0][0]) == _word(b[0][0])):
+            kept.append((a, (), c))
+            continue
         if (len(a) == 1 and len(b) == 1 and len(c) == 3 and a[0][1] == 2 and b[0][1] == 1
                 and all(_kind(d) == 0 and d != ONE for d, _ in a + b + c)):
             cd = dict(c)
@@ -227,7 +276,7 @@ def fuse_rows(rows):
             xorw.append(((1 << 24) | tx, (1 << 24) | (dy.pop() << 16) | ty, (1 << 24) | (do.pop() << 16) | to))
         else:
             kept.extend(m[0] for m in members)
-    return kept, xorw, n_ident
+    return kept, xorw, n_ident, zmask
 
 
 def check_xorw(model, xorw):
@@ -238,8 +287,15 @@ def check_xorw(model, xorw):
         assert X ^ rot(Y, _bit(y)) == rot(O, _bit(o)), (x, y, o)
 
 
+def check_zmask(model, zmask):
+    b = model.b
+    for row, masks in zmask.items():
+        for w, m in masks.items():
+            assert b.trace.get(w, 0) & m == 0, (row, w, m)
+
+
 MERGE_BELOW = 16        # shape classes with fewer rows than this are merged into per-row-coefficient classes
-FLAG_FIELD, FLAG_WIDE, FLAG_XORW, FLAG_ROWCOEF = 1, 2, 4, 8
+FLAG_FIELD, FLAG_WIDE, FLAG_XORW, FLAG_ROWCOEF, FLAG_ZMASK, FLAG_ISZ = 1, 2, 4, 8, 16, 32
 _BOUND = {0: 1, 1: (1 << 32) - 1, 2: (1 << 64) - 1, 3: 1 << 63, 4: 1 << 255}
 
 
@@ -250,7 +306,7 @@ def _is_wide(nA, nB, nC, coefs, ones, kinds):
     return la >= 1 << 62 or lb >= 1 << 62 or lc >= 1 << 62 or la * lb >= 1 << 62
 
 
-def classify(rows, xorw=(), one=ONE):
+def classify(rows, xorw=(), one=ONE, zmask=None):
     """-> list of classes: dict(nA, nB, nC, flags, coefs, cols) with cols[t] = list of descs (one per row).
     Rows of identical shape AND coefficients share one coefficient vector; the many small groups that remain (rows whose
     coefficients are all different: IV[i] * is_parent, 2^k recompositions split by circom, ...) are merged by (nA, nB,
@@ -264,6 +320,8 @@ def classify(rows, xorw=(), one=ONE):
             return (d != one, co, d >> 24, d)
         a2, b2, c2 = sorted(a, key=key), sorted(bb, key=key), sorted(c, key=key)
         field = any((d >> 24) == KIND_INV for d, _ in a2 + b2 + c2)
+        if len(a2) == 1 and not b2:
+            field = "isz"                # folded IsZero row (see fuse_rows)
         shape = (len(a2), len(b2), len(c2), tuple(co for _, co in a2 + b2 + c2), tuple(d == one for d, _ in a2 + b2 + c2), field,
                  tuple(d >> 24 for d, _ in a2 + b2 + c2))
         groups.setdefault(shape, []).append([d for d, _ in a2 + b2 + c2])
@@ -271,10 +329,13 @@ def classify(rows, xorw=(), one=ONE):
     merged = {}
     for shape, members in sorted(groups.items(), key=lambda kv: (-len(kv[1]), kv[0])):
         nA, nB, nC, coefs, ones, field, kinds = shape
-        if field:
+        if field == "isz":
+            assert nA == 1 and nB == 0 and coefs[0] == 1, shape
+        elif field:
             assert nA == 1 and nB == 1 and coefs[0] == 1 and coefs[1] == 1, shape
         assert all(abs(x) < (1 << 100) for x in coefs)
         wide = not field and _is_wide(nA, nB, nC, coefs, ones, kinds)
+        fflag = FLAG_ISZ if field == "isz" else (FLAG_FIELD if field else 0)
         if len(members) < MERGE_BELOW:
             g = merged.setdefault((nA, nB, nC, field), dict(rows=[], wide=False))
             g["rows"].extend((m, coefs) for m in members)
@@ -282,15 +343,20 @@ def classify(rows, xorw=(), one=ONE):
             continue
         members.sort(key=lambda m: [((d >> 24), d & 0xFFFF, (d >> 16) & 31) for d in m])   # (kind, word, bit): long runs
         cols = [[m[t] for m in members] for t in range(nA + nB + nC)]
-        classes.append(dict(nA=nA, nB=nB, nC=nC, flags=(FLAG_FIELD if field else 0) | (FLAG_WIDE if wide else 0), coefs=coefs,
+        classes.append(dict(nA=nA, nB=nB, nC=nC, flags=fflag | (FLAG_WIDE if wide else 0), coefs=coefs,
                             cols=cols, count=len(members)))
     for (nA, nB, nC, field), g in sorted(merged.items()):
         rws = sorted(g["rows"], key=lambda mc: [((d >> 24), d & 0xFFFF, (d >> 16) & 31) for d in mc[0]])
         nt = nA + nB + nC
         cols = [[m[t] for m, _ in rws] for t in range(nt)]
         coefs = tuple(co[t] for t in range(nt) for _, co in rws)          # term-major, one per row
-        classes.append(dict(nA=nA, nB=nB, nC=nC, flags=FLAG_ROWCOEF | (FLAG_FIELD if field else 0) | (FLAG_WIDE if g["wide"] else 0),
+        classes.append(dict(nA=nA, nB=nB, nC=nC, flags=FLAG_ROWCOEF | (FLAG_ISZ if field == "isz" else (FLAG_FIELD if field else 0)) | (FLAG_WIDE if g["wide"] else 0),
                             coefs=coefs, cols=cols, count=len(rws)))
+    if zmask:
+        # one class row per (trace word, mask): column 0 = the word (as a W32 descriptor), column 1 = the mask itself
+        members = sorted({(w, m) for masks in zmask.values() for w, m in masks.items()})
+        classes.insert(0, dict(nA=0, nB=0, nC=2, flags=FLAG_ZMASK, coefs=(1, 1), cols=[[(1 << 24) | w for w, _ in members], [m for _, m in members]],
+                               count=len(members)))
     if xorw:
         members = sorted(xorw, key=lambda m: [(d & 0xFFFF) for d in m])
         classes.insert(0, dict(nA=1, nB=1, nC=1, flags=FLAG_XORW, coefs=(1, 1, 1), cols=[[m[t] for m in members] for t in range(3)],
@@ -366,17 +432,20 @@ def build(check_only=False, verbose=True):
             print("%-18s %6d non-trivial rows (%d unique; %d quadratic), %d classes, %d terms"
                   % (name, n_nontrivial, len(rows), sum(1 for r in rows if r[0]), len(classes), nnz))
         sets.append((name, classes, len(rows), nnz))
-        kept, xorw, n_ident = fuse_rows(rows)
+        kept, xorw, n_ident, zmask = fuse_rows(rows)
         for m in models:
             check_xorw(m, xorw)
-        fclasses = classify(kept, xorw)
-        fnnz = sum(len(a) + len(b) + len(c) for a, b, c in kept) + 3 * len(xorw)
-        assert n_ident + 32 * len(xorw) + len(kept) == len(rows)
+            check_zmask(m, zmask)
+        fclasses = classify(kept, xorw, zmask=zmask)
+        n_zm = fclasses[1]["count"] if zmask else 0
+        fnnz = sum(len(a) + len(b) + len(c) for a, b, c in kept) + 3 * len(xorw) + 2 * n_zm
+        assert n_ident + 32 * len(xorw) + len(kept) + len(zmask) == len(rows)
         if verbose:
             print("%-18s %6d rows evaluated in trace space: %d identities dropped, %d XOR rows folded into %d word rows, "
-                  "%d others; %d classes, %d terms" % (name + "_FUSED", len(kept) + len(xorw), n_ident, 32 * len(xorw),
-                                                        len(xorw), len(kept), len(fclasses), fnnz))
-        sets.append((name + "_FUSED", fclasses, len(kept) + len(xorw), fnnz))
+                  "%d bit-recomposition rows folded into %d zero-mask rows, %d others; %d classes, %d terms"
+                  % (name + "_FUSED", len(kept) + len(xorw) + n_zm, n_ident, 32 * len(xorw), len(xorw), len(zmask), n_zm,
+                     len(kept), len(fclasses), fnnz))
+        sets.append((name + "_FUSED", fclasses, len(kept) + len(xorw) + n_zm, fnnz))
     # slot-space sets for the stand-alone check of witnesses in HBM (O1 builds only)
     from oracle.ref_wasm import RefWasm
     for variant, setname in (("compression", "COMPRESSION_SLOTS"), ("nova_bn_o1", "NOVA_BN_O1_SLOTS")):

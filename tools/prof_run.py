@@ -1,5 +1,5 @@
 """prof_run.py -- minimal driver for ncu captures of the witness kernel (no timing claims).
-usage: python tools/prof_run.py [log2_n] [launches]"""
+usage: python tools/prof_run.py [log2_n] [launches] [circuit] [checked]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -11,6 +11,7 @@ from hot_proofs_blake3_circom_b200.inputs import lcg_compression_inputs
 logn = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 launches = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 circuit = sys.argv[3] if len(sys.argv) > 3 else "blake3_compression"
+checked = len(sys.argv) > 4 and sys.argv[4] == "checked"
 n = 1 << logn
 wc = pkg.builder(circuit, device=0)
 if circuit == "blake3_compression":
@@ -24,6 +25,9 @@ d_st = torch.empty(n, dtype=torch.uint8, device="cuda")
 d_pub = torch.empty(n * wc.nPublic, dtype=torch.int32, device="cuda")
 s = torch.cuda.current_stream().cuda_stream
 for _ in range(launches):
-    wc.witness_batch_device(d_in.data_ptr(), n, d_out.data_ptr(), d_st.data_ptr(), d_pub.data_ptr(), s)
+    if checked:
+        wc.witness_batch_device_checked(d_in.data_ptr(), n, d_out.data_ptr(), d_st.data_ptr(), d_pub.data_ptr(), 0, s)
+    else:
+        wc.witness_batch_device(d_in.data_ptr(), n, d_out.data_ptr(), d_st.data_ptr(), d_pub.data_ptr(), s)
 torch.cuda.synchronize()
 print("prof_run done", n, launches)

@@ -3,6 +3,9 @@ import os, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np, torch
+from hot_proofs_blake3_circom_b200 import _lib
+if os.environ.get("B3W_EXP_LIB"):          # experiment builds of the library
+    _lib.lib_path = lambda: os.environ["B3W_EXP_LIB"]
 import hot_proofs_blake3_circom_b200 as pkg
 from hot_proofs_blake3_circom_b200.inputs import lcg_compression_inputs, splitmix_nova_inputs
 

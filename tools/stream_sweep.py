@@ -45,7 +45,7 @@ if os.environ.get("B3W_EXP_LIB"):
 else:
     configs = [(c, p) for c in (4, 2, 1) for p in (8, 16, 24, 32, 40, 48, 64, 96)]
 if checked:
-    configs = [(c, p) for c in (4, 3, 2, 1) for p in (4, 8, 16, 24, 32)]
+    configs = [(c, p) for c in (2, 3, 1) for p in (16, 24, 32)]
 for rnd in range(2):
     for ctas, parts in configs:
         wc.set_launch(ctas, parts)
