@@ -177,7 +177,11 @@ def derive(model, w2s):
         add({}, {}, lc)
     for w0, w1 in extra_eq:
         add({}, {}, {w0: Fraction(1), w1: Fraction(-1)})
-    wire_of_signal = [wire_of.get(find(i), -1) if find(i) in wire_of else -1 for i in range(n)]
+    # circom's .sym names a wire only for the signal that carries it (the lowest-numbered member of an alias class);
+    # merged and eliminated signals get -1
+    wire_of_signal = [-1] * n
+    for wire, sig in enumerate(w2s):
+        wire_of_signal[int(sig)] = wire
     return rows, wire_of_signal
 
 
@@ -191,16 +195,16 @@ def check_rows(rows, witness_ints, p):
     return None
 
 
-def write_r1cs(path, rows, prime, n_wires, n_pub_out, n_pub_in, n_prv_in, labels):
+def write_r1cs(path, rows, prime, n_wires, n_pub_out, n_pub_in, n_prv_in, labels, n_labels):
     def lc_bytes(D):
         out = [struct.pack("<I", len(D))]
         for w in sorted(D):
             out.append(struct.pack("<I", w) + (D[w] % prime).to_bytes(32, "little"))
         return b"".join(out)
     header = struct.pack("<I", 32) + prime.to_bytes(32, "little") + struct.pack("<IIIIQI", n_wires, n_pub_out, n_pub_in, n_prv_in,
-                                                                               len(labels), len(rows))
+                                                                               n_labels, len(rows))
     cons = b"".join(lc_bytes(A) + lc_bytes(B) + lc_bytes(C) for A, B, C in rows)
-    w2l = b"".join(struct.pack("<Q", int(x)) for x in labels[:0]) if False else np.asarray(labels, "<u8").tobytes()
+    w2l = np.asarray(labels, "<u8").tobytes()
     with open(path, "wb") as f:
         f.write(b"r1cs" + struct.pack("<II", 1, 3))
         for sec_type, body in ((1, header), (2, cons), (3, w2l)):
@@ -274,7 +278,7 @@ def export(variant, out_dir, trials=3, verbose=True):
     stem = {"compression": "blake3_compression", "nova_bn_o2": "blake3_nova", "nova_pasta_o2": "blake3_nova_pasta",
             "nova_bn_o1": "blake3_nova_o1"}[variant]
     r1 = os.path.join(out_dir, stem + ".r1cs")
-    write_r1cs(r1, rows, ref.prime, ref.witness_size, io[0], io[1], io[2], [int(s) for s in w2s])
+    write_r1cs(r1, rows, ref.prime, ref.witness_size, io[0], io[1], io[2], [int(s) for s in w2s], len(mdl.b.names))
     write_sym(os.path.join(out_dir, stem + ".sym"), mdl.b.names, wire_of_signal)
     nq = sum(1 for A, B, C in rows if A)
     if verbose:
