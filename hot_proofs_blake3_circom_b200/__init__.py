@@ -7,7 +7,7 @@ Only the hot path of banyancomputer/hot-proofs-blake3-circom lives here:
   generate_witness.py    mirror of the reference's generate_witness.js CLI
 There is NO CPU fallback: every compute call fails loudly if the CUDA library or a GPU is missing.
 """
-from .witness_calculator import builder, WitnessCalculator, CIRCUITS, circuit_from_wasm  # noqa: F401
+from .witness_calculator import builder, WitnessCalculator, MultiGpuCalculator, CIRCUITS, circuit_from_wasm  # noqa: F401
 from ._lib import lib, lib_path, B3WError  # noqa: F401
 
-__all__ = ["builder", "WitnessCalculator", "CIRCUITS", "circuit_from_wasm", "lib", "lib_path", "B3WError"]
+__all__ = ["builder", "WitnessCalculator", "MultiGpuCalculator", "CIRCUITS", "circuit_from_wasm", "lib", "lib_path", "B3WError"]

@@ -17,7 +17,9 @@
 #include <stdlib.h>
 #include <new>
 #include <vector>
+#include <string>
 #include <algorithm>
+#include <thread>
 
 #include "../../include/blake3wit.h"
 #include "trace_layout.h"
@@ -1367,6 +1369,82 @@ extern "C" int b3w_nova_chain(b3w_ctx *c, const uint8_t *data, uint64_t len, uin
   }
   cudaFree(d_data); cudaFree(d_cv); cudaFree(d_nodes); cudaFree(d_path); cudaFree(d_depth); cudaFree(d_off); cudaFree(d_rows);
   return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU: one context + one host thread per device, contiguous index ranges, no collective
+// ------------------------------------------------------------------------------------------------
+struct b3w_multi {
+  std::vector<b3w_ctx *> ctx;
+};
+
+extern "C" int b3w_multi_create(const b3w_config *cfg, const int32_t *devices, uint32_t n_devices, b3w_multi **out) {
+  if (!cfg || !out || (n_devices && !devices)) return fail(B3W_ERR_INVALID, "b3w_multi_create: null argument");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(B3W_ERR_CUDA, "no CUDA device: %s (libblake3wit has no CPU path)", cudaGetErrorString(e));
+  b3w_multi *m = new (std::nothrow) b3w_multi();
+  if (!m) return fail(B3W_ERR_NOMEM, "out of host memory");
+  const uint32_t n = n_devices ? n_devices : (uint32_t)ndev;          // 0 devices listed = every visible device
+  for (uint32_t i = 0; i < n; i++) {
+    b3w_config c = *cfg;
+    c.device = n_devices ? devices[i] : (int32_t)i;
+    b3w_ctx *x = nullptr;
+    int rc = b3w_create(&c, &x);
+    if (rc) {
+      for (b3w_ctx *y : m->ctx) b3w_destroy(y);
+      delete m;
+      return rc;
+    }
+    m->ctx.push_back(x);
+  }
+  *out = m;
+  return B3W_OK;
+}
+
+extern "C" void b3w_multi_destroy(b3w_multi *m) {
+  if (!m) return;
+  for (b3w_ctx *x : m->ctx) b3w_destroy(x);
+  delete m;
+}
+
+extern "C" uint32_t b3w_multi_size(const b3w_multi *m) { return m ? (uint32_t)m->ctx.size() : 0u; }
+
+// shard g of G over [0, n): contiguous, balanced (the first n % G shards get one extra instance)
+static void shard_of(uint64_t n, uint32_t g, uint32_t G, uint64_t *first, uint64_t *count) {
+  const uint64_t base = n / G, extra = n % G;
+  *first = g * base + (g < extra ? g : extra);
+  *count = base + (g < extra ? 1 : 0);
+}
+
+extern "C" int b3w_shard_range(uint64_t n, uint32_t g, uint32_t n_shards, uint64_t *first, uint64_t *count) {
+  if (!first || !count || n_shards == 0 || g >= n_shards) return fail(B3W_ERR_INVALID, "b3w_shard_range: bad argument");
+  shard_of(n, g, n_shards, first, count);
+  return B3W_OK;
+}
+
+extern "C" int b3w_multi_witness_batch(b3w_multi *m, const uint32_t *in, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub) {
+  if (!m || m->ctx.empty() || (!in && n)) return fail(B3W_ERR_INVALID, "b3w_multi_witness_batch: null argument");
+  const uint32_t G = (uint32_t)m->ctx.size();
+  const circuit_def *d = m->ctx[0]->def;
+  std::vector<int> rc(G, B3W_OK);
+  std::vector<std::string> err(G);
+  std::vector<std::thread> th;
+  for (uint32_t g = 0; g < G; g++) {
+    th.emplace_back([&, g]() {
+      uint64_t first, count;
+      shard_of(n, g, G, &first, &count);
+      if (count == 0) return;
+      rc[g] = b3w_witness_batch(m->ctx[g], in + first * d->n_inputs, count, out ? out + first * (size_t)d->ws * 32 : nullptr,
+                                status ? status + first : nullptr, pub ? pub + first * d->n_public : nullptr);
+      if (rc[g]) err[g] = g_err;                       // g_err is thread-local: carry the text over to the caller
+    });
+  }
+  for (auto &t : th) t.join();
+  for (uint32_t g = 0; g < G; g++)
+    if (rc[g]) return fail(rc[g], "device %d (shard %u of %u): %s", m->ctx[g]->device, g, G, err[g].c_str());
+  return B3W_OK;
 }
 
 extern "C" void *b3w_host_alloc(size_t bytes) {

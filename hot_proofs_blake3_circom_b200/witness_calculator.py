@@ -272,3 +272,56 @@ class WitnessCalculator:
 
     def calib_fill(self, d_buf, nbytes, stream=0):
         _lib.check(self._L.b3w_calib_fill(self._h, d_buf, nbytes, stream or None))
+
+
+class MultiGpuCalculator:
+    """NEW: the batched entry point over several GPUs of one node (b3w_multi_*, include/blake3wit.h): contiguous index
+    ranges, one context and host thread per device, no collective.  devices=None takes every visible device."""
+
+    def __init__(self, circuit, devices=None, chunk=0, fused_check=False):
+        L = _lib.lib()
+        self._L = L
+        cid = circuit if isinstance(circuit, int) else (CIRCUIT_IDS[circuit] if isinstance(circuit, str) else circuit_from_wasm(circuit))
+        info = _lib.Info()
+        _lib.check(L.b3w_circuit_info(cid, C.byref(info)))
+        self.circuit, self.witnessSize, self.nInputs, self.nPublic = cid, info.witness_size, info.n_inputs, info.n_public
+        cfg = _lib.Config(cid, -1, chunk, _lib.B3W_FLAG_FUSED_CHECK if fused_check else 0)
+        devs = (C.c_int32 * len(devices))(*devices) if devices else None
+        h = C.c_void_p()
+        _lib.check(L.b3w_multi_create(C.byref(cfg), devs, len(devices) if devices else 0, C.byref(h)))
+        self._m = h
+        self.nDevices = L.b3w_multi_size(h)
+
+    def close(self):
+        if getattr(self, "_m", None):
+            self._L.b3w_multi_destroy(self._m)
+            self._m = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def shard(self, n, g):
+        """(first, count) of device slot g for a batch of n"""
+        first, count = C.c_uint64(), C.c_uint64()
+        _lib.check(self._L.b3w_shard_range(n, g, self.nDevices, C.byref(first), C.byref(count)))
+        return first.value, count.value
+
+    def calculateWitnessBatch(self, rows, want_witness=True, out=None):
+        rows = np.ascontiguousarray(rows, np.uint32)
+        if rows.ndim != 2 or rows.shape[1] != self.nInputs:
+            raise ValueError("expected an (n, %d) uint32 array" % self.nInputs)
+        n = rows.shape[0]
+        if want_witness and out is None:
+            out = np.empty((n, self.witnessSize * 32), np.uint8)
+        status = np.zeros(n, np.uint8)
+        pub = np.zeros((n, self.nPublic), np.uint32)
+        _lib.check(self._L.b3w_multi_witness_batch(self._m, rows.ctypes.data, n, out.ctypes.data if want_witness else None,
+                                                   status.ctypes.data, pub.ctypes.data))
+        return {"witness": out if want_witness else None, "status": status, "pub": pub}
+
+    def witness_batch_host(self, h_in, n, h_out=None, h_status=None, h_pub=None):
+        """raw host pointers (e.g. from b3w_host_alloc); used by the benches"""
+        _lib.check(self._L.b3w_multi_witness_batch(self._m, h_in, n, h_out, h_status, h_pub))

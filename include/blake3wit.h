@@ -156,6 +156,18 @@ int b3w_nova_chain_size(uint64_t len, uint64_t *n_chunks, uint64_t *total_steps)
 int b3w_nova_chain(b3w_ctx *ctx, const uint8_t *data, uint64_t len, uint8_t *out, uint8_t *status, uint32_t *pub,
                    uint32_t *rows, uint64_t *step_off, uint8_t root[32]);
 
+/* Multi-GPU form of b3w_witness_batch (BASELINE config 5; north_star: "each GPU fills its own slice of the host-pinned
+ * output").  Witnesses are independent, so the batch [0, n) is cut into contiguous index ranges, one per device, each
+ * driven by its own host thread and context; there is NO collective and no peer traffic.  b3w_shard_range() tells which
+ * range shard g of n_shards gets (the first n % n_shards shards hold one extra instance; host-only, needs no GPU).  devices == NULL / n_devices == 0 = every
+ * visible device; cfg->device is ignored.  A device may be listed more than once (each entry gets its own context). */
+typedef struct b3w_multi b3w_multi;
+int b3w_multi_create(const b3w_config *cfg, const int32_t *devices, uint32_t n_devices, b3w_multi **out);
+void b3w_multi_destroy(b3w_multi *m);
+uint32_t b3w_multi_size(const b3w_multi *m);
+int b3w_shard_range(uint64_t n, uint32_t g, uint32_t n_shards, uint64_t *first, uint64_t *count);
+int b3w_multi_witness_batch(b3w_multi *m, const uint32_t *in, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub);
+
 /* pinned host memory for batch buffers */
 void *b3w_host_alloc(size_t bytes);
 void b3w_host_free(void *p);

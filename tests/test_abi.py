@@ -76,6 +76,26 @@ def test_compute_fails_loudly_without_gpu(built):
         wc.calculateWitness({"h": [0] * 8, "m": [0] * 16, "t": [0, 0], "b": 0, "d": 0})
 
 
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_multi_gpu_entry_fails_loudly_without_gpu(built):
+    with pytest.raises(pkg.B3WError) as e:
+        pkg.MultiGpuCalculator("blake3_compression")
+    assert e.value.code == _lib.B3W_ERR_CUDA and "no CPU path" in str(e.value)
+
+
+def test_shard_range_equals_the_python_plan(built):
+    # the C ABI's index-range split (b3w_multi_witness_batch) and shard.py (bench.py / torch.distributed ranks) agree
+    from hot_proofs_blake3_circom_b200.shard import shard_range
+    L = pkg.lib()
+    first, count = C.c_uint64(), C.c_uint64()
+    for n in (0, 1, 7, 37, 65536, 2 ** 24 + 3):
+        for world in (1, 2, 3, 4, 8):
+            for r in range(world):
+                assert L.b3w_shard_range(n, r, world, C.byref(first), C.byref(count)) == 0
+                assert (first.value, count.value) == shard_range(n, r, world)
+    assert L.b3w_shard_range(5, 2, 2, C.byref(first), C.byref(count)) == _lib.B3W_ERR_INVALID
+
+
 def test_product_does_not_import_oracle():
     # the product path must never route through oracle/
     for dirpath, _, files in os.walk(os.path.join(ROOT, "hot_proofs_blake3_circom_b200")):

@@ -159,3 +159,31 @@ def test_full_2p16_checksums_and_properties(wc):
     got = w[sel].cpu().numpy().reshape(len(sel), WS * 32)
     assert np.array_equal(got, port.witness_batch("compression", rows[sel], nthreads=4))
     assert (checksum_np(got, WS) == sums[sel]).all()
+
+
+def test_multi_gpu_entry_point_matches_single(built):
+    """b3w_multi_witness_batch: contiguous shards, one host thread + context per device slot.  With one GPU in the box
+    the same device is listed three times, which exercises the sharding, the threads and the slice arithmetic; on a
+    multi-GPU box every visible device is used as well."""
+    import torch
+    rows = gen.splitmix_compression_inputs(301)
+    want = port.witness_batch("compression", rows, nthreads=4)
+    configs = [[0, 0, 0]]
+    if torch.cuda.device_count() > 1:
+        configs.append(None)
+    for devices in configs:
+        m = pkg.MultiGpuCalculator("blake3_compression", devices=devices, chunk=64)
+        assert m.nDevices == (len(devices) if devices else torch.cuda.device_count())
+        pos = 0
+        for g in range(m.nDevices):
+            first, count = m.shard(301, g)
+            assert first == pos
+            pos += count
+        assert pos == 301
+        res = m.calculateWitnessBatch(rows)
+        assert not res["status"].any()
+        assert np.array_equal(res["witness"], want)
+        assert np.array_equal(res["pub"], want.view(np.uint32).reshape(301, WS, 8)[:, 1:17, 0])
+        small = m.calculateWitnessBatch(rows[:2])            # fewer instances than device slots: empty shards
+        assert np.array_equal(small["witness"], want[:2])
+        m.close()

@@ -72,27 +72,31 @@ def config4():
 
 
 def config5():
+    """BASELINE configs[4]: 2^24 compression instances sharded by contiguous index range over every visible GPU through
+    the C ABI's multi-GPU entry point (one host thread + context per device, no collective), without / with the fused check."""
     n = 1 << 24
     for fused in (False, True):
-        wc = pkg.builder("blake3_compression", device=0, chunk=32768, fused_check=fused)
+        m = pkg.MultiGpuCalculator("blake3_compression", devices=None, chunk=32768, fused_check=fused)
         rows = gen.splitmix_compression_inputs(n)
         h_in = pinned(rows)
         del rows
         h_st = L.b3w_host_alloc(n)
         h_pub = L.b3w_host_alloc(n * 64)
-        f = lambda: _lib.check(L.b3w_witness_batch(wc._h, h_in, n, None, h_st, h_pub))
+        f = lambda: m.witness_batch_host(h_in, n, None, h_st, h_pub)
         dt = timed(f, reps=2)
         st = np.ctypeslib.as_array(C.cast(h_st, C.POINTER(C.c_uint8)), shape=(n,))
         assert not st.any()
-        print(json.dumps({"config": "configs[4]: blake3_compression 2^24 instances, %s, ONE B200 (shards are independent)"
-                          % ("fused on-device R1CS check" if fused else "no check"),
-                          "instances": n, "seconds": dt, "witnesses_per_s": n / dt, "TB_generated": n * 770976 / 1e12,
-                          "hbm_write_GBps": n * 770976 / dt / 1e9,
-                          "note": "b3w_witness_batch(out=NULL) with splitmix inputs (random h,t,d, ragged b): 12.9 TB streamed through "
-                                  "the HBM ring, status + out[16] D2H"}), flush=True)
+        pub = np.ctypeslib.as_array(C.cast(h_pub, C.POINTER(C.c_uint32)), shape=(n, 16))
+        print(json.dumps({"config": "configs[4]: blake3_compression 2^24 instances, %s, %d B200 (contiguous shards, no collective)"
+                          % ("fused on-device R1CS check" if fused else "no check", m.nDevices),
+                          "n_gpus": m.nDevices, "instances": n, "seconds": dt, "witnesses_per_s": n / dt,
+                          "TB_generated": n * 770976 / 1e12, "hbm_write_GBps_per_gpu": n * 770976 / dt / 1e9 / m.nDevices,
+                          "xor_of_out0": int(np.bitwise_xor.reduce(pub[:, 0])),
+                          "note": "b3w_multi_witness_batch(out=NULL) with splitmix inputs (random h,t,d, ragged b): 12.9 TB streamed "
+                                  "through the HBM rings, status + out[16] D2H into the shared pinned arrays"}), flush=True)
         for p in (h_in, h_st, h_pub):
             L.b3w_host_free(p)
-        wc.close()
+        m.close()
 
 
 if __name__ == "__main__":

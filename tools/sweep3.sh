@@ -1,4 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_r1cs.py tests/test_gpu_nova.py -x -q -m gpu 2>&1 | tail -5 | tee gpurun_out/pytest_gpu.log
-python tools/r1cs_quickbench.py 2>&1 | tee gpurun_out/r1cs_quickbench4.log
+python -m pytest tests -x -q -m gpu 2>&1 | tail -25 | tee gpurun_out/pytest_gpu.log
