@@ -17,6 +17,7 @@ Keys of the JSON line (rank 0):
   e2e        the same metric through the C ABI b3w_witness_batch() with HOST (pinned) buffers: H2D of the
              inputs and D2H of every witness byte + status + public outputs inside the timed region
   e2e_compact  ditto with out=NULL: witnesses only stream through the HBM ring, compact results come back
+  e2e_packed   ditto with every witness returned in compact form (its 3 776-byte trace)
   cpu_baseline the reference's own wasm witness program (oracle/_ref, translated to C) on all host cores,
              bounded sample (rank 0, N=1 only)
 --impl reference times that CPU path as its own arm.
@@ -63,7 +64,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -260,7 +261,30 @@ def run_own(args, rank, world, local_rank):
     got0 = np.ctypeslib.as_array(C.cast(h_out, C.POINTER(C.c_uint32)), shape=(WS * 8,))
     assert got0[8] == pub0[0] and got0[0] == 1                  # slot 0 == 1, slot 1 == out[0]
     t_compact = e2e_run(None, e2e_steps)
-    for p in (h_out, h_in, h_st, h_pub):
+    L.b3w_host_free(h_out)
+    # ... and with the witnesses returned in COMPACT form (the per-instance trace, 3 776 B: every slot is a pure function
+    # of it; b3w_unpack_device expands on demand)
+    pk_words = wc.packedWords
+    h_pk = L.b3w_host_alloc(n_e2e * pk_words * 4)
+    if not h_pk:
+        raise SystemExit("bench.py: pinned host allocation failed: " + L.b3w_last_error().decode())
+
+    def packed_run(steps):
+        from hot_proofs_blake3_circom_b200 import _lib
+        _lib.check(L.b3w_witness_batch_packed(wc._h, h_in, n_e2e, h_pk, h_st, h_pub))
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            _lib.check(L.b3w_witness_batch_packed(wc._h, h_in, n_e2e, h_pk, h_st, h_pub))
+        dt = time.perf_counter() - t0
+        barrier()
+        return max_over_ranks(dt) / steps
+
+    t_packed = packed_run(e2e_steps)
+    pk0 = np.ctypeslib.as_array(C.cast(h_pk, C.POINTER(C.c_uint32)), shape=(pk_words,))
+    assert pk0[1] == 1 and pk0[30] == pub0[0]                   # trace word 1 = the constant 1, word 30 = out[0]
+    for p in (h_pk, h_in, h_st, h_pub):
         L.b3w_host_free(p)
 
     # --- cpu baseline (rank 0, N=1 only): bounded sample on all host cores -------------------------
@@ -304,6 +328,10 @@ def run_own(args, rank, world, local_rank):
         "e2e_compact": {"value": world * n_e2e / t_compact, "unit": "witnesses/s", "h2d_bytes_per_step": n_e2e * IN_BYTES,
                         "d2h_bytes_per_step": n_e2e * (1 + 64), "ms_per_step": 1e3 * t_compact,
                         "api": "b3w_witness_batch(out=NULL): witnesses stream through the HBM ring, status + out[16] return"},
+        "e2e_packed": {"value": world * n_e2e / t_packed, "unit": "witnesses/s", "h2d_bytes_per_step": n_e2e * IN_BYTES,
+                       "d2h_bytes_per_step": n_e2e * (pk_words * 4 + 1 + 64), "ms_per_step": 1e3 * t_packed,
+                       "api": "b3w_witness_batch_packed(host pinned in/out): every witness returned in compact form "
+                              "(%d B trace per instance; expandable to the .wtns body with b3w_unpack_device)" % (pk_words * 4)},
         "gpu_launches": gpu_launches, "clocks": clocks}
     if cpu:
         line["cpu_baseline"] = cpu

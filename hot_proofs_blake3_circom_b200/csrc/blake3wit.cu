@@ -527,6 +527,66 @@ k_blake3_nova_witness(const uint32_t *__restrict__ in, uint64_t n, const uint32_
   }
 }
 
+// ---- compact ("packed") witnesses: SURVEY.md 8(f) rank 3 --------------------------------------------------------
+// Every slot of a witness is a pure function of the instance's trace (<= 1 324 u32) and the static slot table, so the
+// trace IS the witness in compact form: 3 776 B (compression) / 5 296 B (nova) instead of 770 976 / 745 312 B, ~200x less
+// to keep in HBM, move over PCIe or hand to a prover on the same GPU.  k_witness_packed writes traces, k_unpack expands
+// traces that are resident in device memory into the .wtns body layout (the expansion phase of the main kernels).
+template <bool NOVA>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+k_witness_packed(const uint32_t *__restrict__ in, uint64_t n, uint32_t stride_words, uint32_t *__restrict__ packed,
+                 uint8_t *__restrict__ status, uint32_t *__restrict__ pub) {
+  extern __shared__ __align__(16) uint32_t s_dyn[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  uint32_t *trace = s_dyn + wib * (NOVA ? NOVA_TRACE_STRIDE : TRACE_STRIDE);
+  const lane_sched ls = load_lane_sched(lane);
+  const uint64_t warp = (uint64_t)blockIdx.x * WARPS_PER_CTA + wib, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
+  constexpr int N_IN = NOVA ? 32 : 28, N_PUB = NOVA ? 15 : 16;
+  for (uint64_t i = warp; i < n; i += nwarps) {
+    __syncwarp();
+    for (uint32_t w = lane; w < stride_words; w += 32) trace[w] = 0u;     // words no template writes stay 0
+    __syncwarp();
+    if (lane == 0) trace[TR_ONE] = 1u;
+    if (lane < N_IN) trace[(NOVA ? NV_IN : TR_IN) + lane] = __ldg(in + i * N_IN + lane);
+    __syncwarp();
+    bool ok = true;
+    if (NOVA) ok = nova_trace(trace, lane);
+    __syncwarp();
+    if (ok) compression_trace(trace, lane, ls);
+    __syncwarp();
+    if (!ok && lane == 0) trace[TR_ONE] = 0u;                             // marks "no witness exists" (Assert Failed.)
+    if (status && lane == 0) status[i] = ok ? 0 : B3W_CIRCOM_ASSERT;
+    if (pub && lane < N_PUB) pub[i * N_PUB + lane] = !ok ? 0u : NOVA ? nova_public_output(trace, lane) : trace[TR_OUT + lane];
+    __syncwarp();
+    uint4 *dst = reinterpret_cast<uint4 *>(packed + i * stride_words);
+    const uint4 *src = reinterpret_cast<const uint4 *>(trace);
+    for (uint32_t q = lane; q < stride_words / 4; q += 32) dst[q] = src[q];
+  }
+}
+
+template <bool HAS_FIELD>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+k_unpack(const uint32_t *__restrict__ packed, uint64_t n, uint32_t stride_words, const uint32_t *__restrict__ desc, uint32_t ws,
+         const field_consts *__restrict__ F, const uint2 *__restrict__ fslots, uint32_t n_fslots, uint8_t *__restrict__ out,
+         uint32_t parts, uint32_t part_len) {
+  extern __shared__ __align__(16) uint32_t s_dyn[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  uint32_t *trace = s_dyn + wib * (HAS_FIELD ? NOVA_TRACE_STRIDE : TRACE_STRIDE);
+  const uint64_t warp = (uint64_t)blockIdx.x * WARPS_PER_CTA + wib, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
+  const uint64_t total = n * parts;
+  for (uint64_t item = warp; item < total; item += nwarps) {
+    const uint64_t i = item / parts;
+    const uint32_t part = (uint32_t)(item % parts);
+    const uint32_t a = part * part_len, b = a + part_len < ws ? a + part_len : ws;
+    __syncwarp();
+    const uint4 *src = reinterpret_cast<const uint4 *>(packed + i * stride_words);
+    uint4 *dst = reinterpret_cast<uint4 *>(trace);
+    for (uint32_t q = lane; q < stride_words / 4; q += 32) dst[q] = __ldg(src + q);
+    __syncwarp();
+    expand_slots<HAS_FIELD>(trace, desc, a, b, out + i * (uint64_t)ws * 32, lane, F, fslots, n_fslots);
+  }
+}
+
 // k_r1cs_check_witness: stand-alone check of witnesses resident in HBM (one warp per instance).
 __global__ void __launch_bounds__(256)
 k_r1cs_check_witness(const uint8_t *__restrict__ wit, uint64_t n, uint32_t ws, const r1cs_tables_dev T,
@@ -778,6 +838,11 @@ struct b3w_ctx {
   uint8_t *d_status[2];
   uint32_t *d_pub[2];
   bool ring_ready;
+  // staging for host-buffer batches of PACKED witnesses: 2 slots
+  cudaStream_t pk_st[2];
+  uint32_t *pk_in[2], *pk_buf[2], *pk_pub[2];
+  uint8_t *pk_status[2];
+  bool pk_ready;
 };
 
 extern "C" int b3w_version(void) { return B3W_VERSION; }
@@ -856,6 +921,7 @@ extern "C" int b3w_create(const b3w_config *cfg, b3w_ctx **out) {
   return B3W_OK;
 }
 
+static void free_packed_ring(b3w_ctx *c);
 static void free_ring(b3w_ctx *c) {
   for (int k = 0; k < 2; k++) {
     if (c->d_ring[k]) cudaFree(c->d_ring[k]);
@@ -874,6 +940,7 @@ extern "C" void b3w_destroy(b3w_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   free_ring(c);
+  free_packed_ring(c);
   if (c->d_desc) cudaFree(c->d_desc);
   if (c->d_field) cudaFree(c->d_field);
   if (c->d_fslots) cudaFree(c->d_fslots);
@@ -1369,6 +1436,112 @@ extern "C" int b3w_nova_chain(b3w_ctx *c, const uint8_t *data, uint64_t len, uin
   }
   cudaFree(d_data); cudaFree(d_cv); cudaFree(d_nodes); cudaFree(d_path); cudaFree(d_depth); cudaFree(d_off); cudaFree(d_rows);
   return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// compact witnesses, host side
+// ------------------------------------------------------------------------------------------------
+static uint32_t packed_words_of(const circuit_def *d) { return (d->trace_words + 3u) & ~3u; }
+static size_t trace_smem_of(const circuit_def *d) { return (size_t)WARPS_PER_CTA * (d->nova ? NOVA_TRACE_STRIDE : TRACE_STRIDE) * 4; }
+
+extern "C" int b3w_packed_words(uint32_t circuit, uint32_t *words) {
+  const circuit_def *d = find_def(circuit);
+  if (!d) return B3W_ERR_UNSUPPORTED;
+  if (!words) return fail(B3W_ERR_INVALID, "b3w_packed_words: null argument");
+  *words = packed_words_of(d);
+  return B3W_OK;
+}
+
+extern "C" int b3w_witness_batch_packed_device(b3w_ctx *c, const uint32_t *d_in, uint64_t n, uint32_t *d_packed, uint8_t *d_status,
+                                               uint32_t *d_pub, void *stream) {
+  if (!c || !d_in || !d_packed) return fail(B3W_ERR_INVALID, "b3w_witness_batch_packed_device: null argument");
+  if (((uintptr_t)d_packed & 15) != 0) return fail(B3W_ERR_INVALID, "d_packed must be 16-byte aligned");
+  CK(cudaSetDevice(c->device));
+  if (n == 0) return B3W_OK;
+  const uint64_t ctas = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA, cap = (uint64_t)c->sm_count * 6;
+  const unsigned grid = (unsigned)(ctas < cap ? ctas : cap);
+  const uint32_t sw = packed_words_of(c->def);
+  if (c->def->nova) {
+    k_witness_packed<true><<<grid, WARPS_PER_CTA * 32, trace_smem_of(c->def), (cudaStream_t)stream>>>(d_in, n, sw, d_packed, d_status, d_pub);
+  } else {
+    k_witness_packed<false><<<grid, WARPS_PER_CTA * 32, trace_smem_of(c->def), (cudaStream_t)stream>>>(d_in, n, sw, d_packed, d_status, d_pub);
+  }
+  CK(cudaGetLastError());
+  return B3W_OK;
+}
+
+extern "C" int b3w_unpack_device(b3w_ctx *c, const uint32_t *d_packed, uint64_t n, uint8_t *d_out, void *stream) {
+  if (!c || !d_packed || !d_out) return fail(B3W_ERR_INVALID, "b3w_unpack_device: null argument");
+  if (((uintptr_t)d_packed & 15) != 0 || ((uintptr_t)d_out & 31) != 0) return fail(B3W_ERR_INVALID, "d_packed must be 16-byte, d_out 32-byte aligned");
+  CK(cudaSetDevice(c->device));
+  if (n == 0) return B3W_OK;
+  const uint32_t parts = 8, part_len = ((c->def->ws + parts - 1) / parts + 31) / 32 * 32;
+  const uint64_t ctas = (n * parts + WARPS_PER_CTA - 1) / WARPS_PER_CTA, cap = (uint64_t)c->sm_count * 2;
+  const unsigned grid = (unsigned)(ctas < cap ? ctas : cap);
+  const uint32_t sw = packed_words_of(c->def);
+  if (c->def->nova) {
+    k_unpack<true><<<grid, WARPS_PER_CTA * 32, trace_smem_of(c->def), (cudaStream_t)stream>>>(d_packed, n, sw, c->d_desc, c->def->ws, c->d_field, c->d_fslots, c->n_fslots, d_out, parts, part_len);
+  } else {
+    k_unpack<false><<<grid, WARPS_PER_CTA * 32, trace_smem_of(c->def), (cudaStream_t)stream>>>(d_packed, n, sw, c->d_desc, c->def->ws, nullptr, nullptr, 0, d_out, parts, part_len);
+  }
+  CK(cudaGetLastError());
+  return B3W_OK;
+}
+
+// host buffers: chunks of PACKED_CHUNK instances through two device slots (allocated on first use, kept in the context), so
+// that the D2H of chunk j overlaps the kernel and H2D of chunk j+1
+#define PACKED_CHUNK (1u << 17)
+static int ensure_packed_ring(b3w_ctx *c) {
+  if (c->pk_ready) return B3W_OK;
+  const circuit_def *d = c->def;
+  for (int k = 0; k < 2; k++) {
+    CK(cudaStreamCreateWithFlags(&c->pk_st[k], cudaStreamNonBlocking));
+    CK(cudaMalloc(&c->pk_in[k], (size_t)PACKED_CHUNK * d->n_inputs * 4));
+    CK(cudaMalloc(&c->pk_buf[k], (size_t)PACKED_CHUNK * packed_words_of(d) * 4));
+    CK(cudaMalloc(&c->pk_status[k], (size_t)PACKED_CHUNK));
+    CK(cudaMalloc(&c->pk_pub[k], (size_t)PACKED_CHUNK * d->n_public * 4));
+  }
+  c->pk_ready = true;
+  return B3W_OK;
+}
+static void free_packed_ring(b3w_ctx *c) {
+  for (int k = 0; k < 2; k++) {
+    if (c->pk_in[k]) cudaFree(c->pk_in[k]);
+    if (c->pk_buf[k]) cudaFree(c->pk_buf[k]);
+    if (c->pk_status[k]) cudaFree(c->pk_status[k]);
+    if (c->pk_pub[k]) cudaFree(c->pk_pub[k]);
+    if (c->pk_st[k]) cudaStreamDestroy(c->pk_st[k]);
+    c->pk_in[k] = nullptr; c->pk_buf[k] = nullptr; c->pk_status[k] = nullptr; c->pk_pub[k] = nullptr; c->pk_st[k] = nullptr;
+  }
+  c->pk_ready = false;
+}
+
+extern "C" int b3w_witness_batch_packed(b3w_ctx *c, const uint32_t *in, uint64_t n, uint32_t *packed, uint8_t *status, uint32_t *pub) {
+  if (!c || (!in && n) || (!packed && n)) return fail(B3W_ERR_INVALID, "b3w_witness_batch_packed: null argument");
+  CK(cudaSetDevice(c->device));
+  if (n == 0) return B3W_OK;
+  int rc = ensure_packed_ring(c);
+  if (rc) { free_packed_ring(c); return rc; }
+  const circuit_def *d = c->def;
+  const uint32_t sw = packed_words_of(d);
+  uint64_t done = 0;
+  int k = 0;
+  while (done < n) {
+    const uint64_t m = n - done < PACKED_CHUNK ? n - done : PACKED_CHUNK;
+    cudaStream_t s = c->pk_st[k];
+    CK(cudaStreamSynchronize(s));                          // slot k's previous chunk has left the device
+    CK(cudaMemcpyAsync(c->pk_in[k], in + done * d->n_inputs, m * d->n_inputs * 4, cudaMemcpyHostToDevice, s));
+    rc = b3w_witness_batch_packed_device(c, c->pk_in[k], m, c->pk_buf[k], c->pk_status[k], c->pk_pub[k], s);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(packed + done * sw, c->pk_buf[k], m * sw * 4, cudaMemcpyDeviceToHost, s));
+    if (status) CK(cudaMemcpyAsync(status + done, c->pk_status[k], m, cudaMemcpyDeviceToHost, s));
+    if (pub) CK(cudaMemcpyAsync(pub + done * d->n_public, c->pk_pub[k], m * d->n_public * 4, cudaMemcpyDeviceToHost, s));
+    done += m;
+    k ^= 1;
+  }
+  CK(cudaStreamSynchronize(c->pk_st[0]));
+  CK(cudaStreamSynchronize(c->pk_st[1]));
+  return B3W_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -220,6 +220,48 @@ class WitnessCalculator:
                                              status.ctypes.data, pub.ctypes.data))
         return {"witness": out if want_witness else None, "status": status, "pub": pub}
 
+    # ---- NEW: compact witnesses (the per-instance trace; ~200x smaller than the .wtns body) ----
+    @property
+    def packedWords(self):
+        w = C.c_uint32()
+        _lib.check(self._L.b3w_packed_words(self.circuit, C.byref(w)))
+        return w.value
+
+    def calculateWitnessBatchPacked(self, inputs):
+        """As calculateWitnessBatch, but returns dict(packed=(n, packedWords) u32, status, pub): the witnesses in compact
+        form.  unpackWitnesses() (GPU) turns any subset of them into .wtns bodies."""
+        rows = np.ascontiguousarray(inputs, np.uint32) if isinstance(inputs, np.ndarray) else \
+            (np.stack([self._row(i) for i in inputs]) if len(inputs) else np.zeros((0, self.nInputs), np.uint32))
+        if rows.ndim != 2 or rows.shape[1] != self.nInputs:
+            raise ValueError("expected an (n, %d) uint32 array" % self.nInputs)
+        n = rows.shape[0]
+        packed = np.zeros((n, self.packedWords), np.uint32)
+        status = np.zeros(n, np.uint8)
+        pub = np.zeros((n, self.nPublic), np.uint32)
+        _lib.check(self._L.b3w_witness_batch_packed(self._h, rows.ctypes.data, n, packed.ctypes.data, status.ctypes.data,
+                                                    pub.ctypes.data))
+        return {"packed": packed, "status": status, "pub": pub}
+
+    def unpackWitnesses(self, packed):
+        """(n, packedWords) u32 -> (n, witnessSize*32) u8: the lazy .wtns-body export, expanded on the GPU."""
+        import torch
+        packed = np.ascontiguousarray(packed, np.uint32)
+        n = packed.shape[0]
+        with torch.cuda.device(self._cfg.device if self._cfg.device >= 0 else torch.cuda.current_device()):
+            self._h
+            d_p = torch.from_numpy(packed.view(np.int32)).cuda()
+            d_o = torch.empty((n, self.witnessSize * 32), dtype=torch.uint8, device="cuda")
+            self.unpack_device(d_p.data_ptr(), n, d_o.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            return d_o.cpu().numpy()
+
+    def witness_batch_packed_device(self, d_in, n, d_packed, d_status=0, d_pub=0, stream=0):
+        _lib.check(self._L.b3w_witness_batch_packed_device(self._h, d_in, n, d_packed, d_status or None, d_pub or None,
+                                                           stream or None))
+
+    def unpack_device(self, d_packed, n, d_out, stream=0):
+        _lib.check(self._L.b3w_unpack_device(self._h, d_packed, n, d_out, stream or None))
+
     # ---- NEW: all Nova step witnesses of a file (the batched form of rust_fold's prove_step loop) ----
     def novaChain(self, data, want_witness=False):
         """data: bytes.  Returns dict(n_chunks, total_steps, step_off=u64[n_chunks+1], rows=(steps,32) u32 step inputs,

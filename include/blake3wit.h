@@ -156,6 +156,20 @@ int b3w_nova_chain_size(uint64_t len, uint64_t *n_chunks, uint64_t *total_steps)
 int b3w_nova_chain(b3w_ctx *ctx, const uint8_t *data, uint64_t len, uint8_t *out, uint8_t *status, uint32_t *pub,
                    uint32_t *rows, uint64_t *step_off, uint8_t root[32]);
 
+/* COMPACT ("packed") witnesses.  Every slot of a witness is a pure function of the instance's trace (the few hundred u32
+ * values the circuit really computes: sums with carries, rotated words, step flags) and of the static slot table, so the
+ * trace is the witness in compact form: b3w_packed_words() u32 per instance = 3 776 B (blake3_compression) / 5 296 B
+ * (nova) instead of 770 976 / 745 312 B.  What the .wtns writer of witness_calculator.js:208-272 would store per
+ * instance becomes a lazy export: b3w_unpack_device() expands packed witnesses that are resident in device memory
+ * into the .wtns body layout, bit-identical to b3w_witness_batch_device().  An instance whose inputs assert is marked
+ * in status[] (and has word 1 of its packed record = 0 instead of 1); unpacking it yields no valid witness.
+ * d_packed / packed: n * b3w_packed_words() u32, 16-byte aligned. */
+int b3w_packed_words(uint32_t circuit, uint32_t *words);
+int b3w_witness_batch_packed_device(b3w_ctx *ctx, const uint32_t *d_in, uint64_t n, uint32_t *d_packed, uint8_t *d_status,
+                                    uint32_t *d_pub, void *stream);
+int b3w_witness_batch_packed(b3w_ctx *ctx, const uint32_t *in, uint64_t n, uint32_t *packed, uint8_t *status, uint32_t *pub);
+int b3w_unpack_device(b3w_ctx *ctx, const uint32_t *d_packed, uint64_t n, uint8_t *d_out, void *stream);
+
 /* Multi-GPU form of b3w_witness_batch (BASELINE config 5; north_star: "each GPU fills its own slice of the host-pinned
  * output").  Witnesses are independent, so the batch [0, n) is cut into contiguous index ranges, one per device, each
  * driven by its own host thread and context; there is NO collective and no peer traffic.  b3w_shard_range() tells which

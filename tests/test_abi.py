@@ -54,6 +54,14 @@ def test_wtns_header_equals_reference_golden(golden, built):
     assert hdr.tobytes() == golden["wtns"].tobytes()[:76]
 
 
+def test_packed_sizes(built):
+    L = pkg.lib()
+    w = C.c_uint32()
+    for cid, words in ((0, 944), (1, 1324), (2, 1324), (3, 1324)):
+        assert L.b3w_packed_words(cid, C.byref(w)) == 0 and w.value == words
+    assert L.b3w_packed_words(9, C.byref(w)) == _lib.B3W_ERR_UNSUPPORTED
+
+
 def test_input_signal_table(built):
     L = pkg.lib()
     off, size = C.c_uint32(), C.c_uint32()
