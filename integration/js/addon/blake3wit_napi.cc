@@ -5,6 +5,7 @@
 // Every compute call runs in napi_async_work so that `await` keeps the event loop free, as the async methods of the
 // reference's WitnessCalculator promise (witness_calculator.js:171,190,208).
 #include <node_api.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include "blake3wit.h"
@@ -97,14 +98,21 @@ static napi_value WtnsHeader(napi_env env, napi_callback_info info) {
 // witnessOne(ctx, row) -> Promise<Uint8Array>
 struct job {
   napi_async_work work; napi_deferred deferred;
-  b3w_ctx *ctx; uint32_t *rows; uint64_t n; b3w_info bi;
+  b3w_ctx *ctx; uint32_t circuit; uint32_t *rows; uint64_t n; b3w_info bi;
   uint8_t *out, *status; uint32_t *pub; bool one; int rc; char err[512];
 };
 static void job_run(napi_env, void *data) {
   job *j = (job *)data;
   j->rc = b3w_witness_batch(j->ctx, j->rows, j->n, j->out, j->status, j->pub);
   if (j->rc == B3W_OK && j->one && j->status[0]) j->rc = j->status[0];
-  if (j->rc) strncpy(j->err, j->rc == B3W_CIRCOM_ASSERT ? "Error: Assert Failed.\n" : b3w_last_error(), sizeof j->err - 1);
+  if (j->rc == B3W_CIRCOM_ASSERT) {
+    // witness_calculator.js:21-43,159-162: Error("Assert Failed.\n" + the printErrorMessage lines), re-wrapped
+    char trace[400];
+    b3w_assert_trace(j->circuit, j->rows, trace, sizeof trace);
+    snprintf(j->err, sizeof j->err, "Error: Assert Failed.\n%s", trace);
+  } else if (j->rc) {
+    strncpy(j->err, b3w_last_error(), sizeof j->err - 1);
+  }
 }
 static void job_free_buf(napi_env, void *data, void *) { free(data); }
 static void job_done(napi_env env, napi_status, void *data) {
@@ -148,6 +156,7 @@ static napi_value start_job(napi_env env, napi_callback_info info, bool one) {
   handle *h = NULL;
   NAPI_OK(napi_get_value_external(env, argv[0], (void **)&h));
   j->ctx = h->ctx;
+  j->circuit = h->circuit;
   b3w_circuit_info(h->circuit, &j->bi);
   napi_typedarray_type tt; size_t len; void *data; napi_value ab; size_t off;
   NAPI_OK(napi_get_typedarray_info(env, argv[1], &tt, &len, &data, &ab, &off));
