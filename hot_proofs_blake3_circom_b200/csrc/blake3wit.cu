@@ -762,6 +762,22 @@ __global__ void __launch_bounds__(256) k_fill(uint8_t *buf, uint64_t nslots) {
     st_slot(buf + s * 32, (uint32_t)s & 1u, 0u, 0u, 0u, 0u, 0u, 0u, 0u);
 }
 
+// The same store stream as the witness kernels without any of their work: warps take 32 KiB items from the dynamic
+// counters and write them with 1 KiB warp stores.  What this reaches is the ceiling of the store path for this access
+// pattern; the witness kernel is judged against it (and against the driver's copy benchmark).
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_fill_items(uint8_t *buf, uint64_t n_items, uint32_t item_slots, const sched_args sc) {
+  const int lane = threadIdx.x & 31;
+  uint32_t sub = (uint32_t)((blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5)) % SCHED_LANES), tries = 0;
+  while (tries < SCHED_LANES) {
+    unsigned long long id = lane == 0 ? atomicAdd(sc.counter + sub * SCHED_STRIDE, 1ull) * SCHED_LANES + sub : 0ull;
+    id = __shfl_sync(0xffffffffu, id, 0);
+    if (id >= n_items) { tries++; sub = (sub + 1) % SCHED_LANES; continue; }
+    uint8_t *dst = buf + id * (uint64_t)item_slots * 32;
+#pragma unroll 4
+    for (uint32_t sl = lane; sl < item_slots; sl += 32) st_slot(dst + (size_t)sl * 32, sl & 1u, 0u, 0u, 0u, 0u, 0u, 0u, 0u);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -1191,7 +1207,7 @@ extern "C" int b3w_debug_inject_fault(b3w_ctx *c, uint32_t trace_word, uint32_t 
 }
 
 extern "C" int b3w_debug_set_launch(b3w_ctx *c, int ctas_per_sm, uint32_t parts) {
-  if (!c || ctas_per_sm < 0 || parts > 1024) return fail(B3W_ERR_INVALID, "b3w_debug_set_launch: bad argument");
+  if (!c || ctas_per_sm < 0 || parts > 65536) return fail(B3W_ERR_INVALID, "b3w_debug_set_launch: bad argument");
   c->ctas_limit = ctas_per_sm;
   c->sched_parts = parts;
   return B3W_OK;
@@ -1257,6 +1273,27 @@ extern "C" int b3w_checksum_device(b3w_ctx *c, const uint8_t *d_wit, uint64_t n,
   if (n == 0) return B3W_OK;
   uint64_t ctas = (n + 7) / 8, cap = (uint64_t)c->sm_count * 8;
   k_checksum<<<(unsigned)(ctas < cap ? ctas : cap), 256, 0, (cudaStream_t)stream>>>((const uint64_t *)d_wit, n, c->def->ws, d_sums);
+  CK(cudaGetLastError());
+  return B3W_OK;
+}
+
+extern "C" int b3w_calib_fill_items(b3w_ctx *c, uint8_t *d_buf, uint64_t bytes, void *stream) {
+  if (!c || !d_buf) return fail(B3W_ERR_INVALID, "b3w_calib_fill_items: null argument");
+  if (((uintptr_t)d_buf & 31) != 0) return fail(B3W_ERR_INVALID, "d_buf must be 32-byte aligned");
+  CK(cudaSetDevice(c->device));
+  const uint32_t item_slots = c->sched_parts >= 32 ? c->sched_parts / 32 * 32 : 1024;   // default 32 KiB = the witness kernels' work item (tuning hook: set_launch parts >= 32 = slots per item)
+  const uint64_t n_items = bytes / (item_slots * 32ull);
+  if (n_items == 0) return B3W_OK;
+  sched_args sc;
+  if (!c->d_counters) CK(cudaMalloc(&c->d_counters, (size_t)N_SCHED_COUNTERS * SCHED_SET_U64 * sizeof(unsigned long long)));
+  const uint32_t set0 = c->next_counter % N_SCHED_COUNTERS;
+  c->next_counter += 2;
+  sc.counter = c->d_counters + (size_t)set0 * SCHED_SET_U64;
+  sc.parts = 1;
+  sc.part_len = item_slots;
+  CK(cudaMemsetAsync(sc.counter, 0, SCHED_SET_U64 * sizeof(unsigned long long), (cudaStream_t)stream));
+  const int per_sm = c->ctas_limit > 0 ? c->ctas_limit : 2;
+  k_fill_items<<<c->sm_count * per_sm, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(d_buf, n_items, item_slots, sc);
   CK(cudaGetLastError());
   return B3W_OK;
 }

@@ -312,8 +312,10 @@ class WitnessCalculator:
     def checksum_device(self, d_wit, n, d_sums, stream=0):
         _lib.check(self._L.b3w_checksum_device(self._h, d_wit, n, d_sums, stream or None))
 
-    def calib_fill(self, d_buf, nbytes, stream=0):
-        _lib.check(self._L.b3w_calib_fill(self._h, d_buf, nbytes, stream or None))
+    def calib_fill(self, d_buf, nbytes, stream=0, items=False):
+        """pure-store calibration; items=True uses the witness kernels' own store stream (32 KiB dynamic work items)"""
+        f = self._L.b3w_calib_fill_items if items else self._L.b3w_calib_fill
+        _lib.check(f(self._h, d_buf, nbytes, stream or None))
 
 
 class MultiGpuCalculator:

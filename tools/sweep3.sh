@@ -1,4 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_packed.py -x -q -m gpu 2>&1 | tail -25 | tee gpurun_out/pytest_gpu.log
-python tools/packed_quickbench.py 2>&1 | tee gpurun_out/packed_quickbench.log
+python bench.py --steps 20 --warmup 3 > gpurun_out/bench_own2.json 2> gpurun_out/bench_own2.err; tail -3 gpurun_out/bench_own2.err; cat gpurun_out/bench_own2.json
