@@ -1258,6 +1258,52 @@ extern "C" int b3w_witness_batch(b3w_ctx *c, const uint32_t *in, uint64_t n, uin
   return B3W_OK;
 }
 
+// Inputs as field elements (canonical or not): what `normalize` (witness_calculator.js:319-323) leaves is value mod p;
+// the kernels cover the circuits' honest domain [0, 2^32), anything else is refused with B3W_ERR_DOMAIN.
+static bool ge256(const uint32_t a[8], const uint32_t b[8]) {
+  for (int i = 7; i >= 0; i--)
+    if (a[i] != b[i]) return a[i] > b[i];
+  return true;
+}
+extern "C" int b3w_inputs_from_fr(uint32_t circuit, const uint8_t *in_fr, uint64_t n, uint32_t *rows) {
+  const circuit_def *d = find_def(circuit);
+  if (!d) return B3W_ERR_UNSUPPORTED;
+  if ((!in_fr || !rows) && n) return fail(B3W_ERR_INVALID, "b3w_inputs_from_fr: null argument");
+  uint32_t p[8];
+  memcpy(p, d->prime, 32);
+  for (uint64_t i = 0; i < n; i++)
+    for (uint32_t k = 0; k < d->n_inputs; k++) {
+      uint32_t v[8];
+      memcpy(v, in_fr + (i * d->n_inputs + k) * 32, 32);
+      while (ge256(v, p)) {                                  // value mod p (p > 2^253: at most a few rounds)
+        uint64_t br = 0;
+        for (int j = 0; j < 8; j++) {
+          uint64_t t = (uint64_t)v[j] - p[j] - br;
+          v[j] = (uint32_t)t;
+          br = (t >> 32) & 1;
+        }
+      }
+      if (v[1] | v[2] | v[3] | v[4] | v[5] | v[6] | v[7]) {
+        const char *nm = "?";
+        uint32_t idx = k;
+        for (int sg = 0; sg < d->n_sig; sg++)
+          if (k >= d->sig[sg].off && k < d->sig[sg].off + d->sig[sg].size) { nm = d->sig[sg].name; idx = k - d->sig[sg].off; }
+        return fail(B3W_ERR_DOMAIN, "instance %llu: input %s[%u] is outside the supported u32 domain", (unsigned long long)i, nm, idx);
+      }
+      rows[i * d->n_inputs + k] = v[0];
+    }
+  return B3W_OK;
+}
+
+extern "C" int b3w_witness_batch_fr(b3w_ctx *c, const uint8_t *in_fr, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub) {
+  if (!c || (!in_fr && n)) return fail(B3W_ERR_INVALID, "b3w_witness_batch_fr: null argument");
+  std::vector<uint32_t> rows;
+  try { rows.resize((size_t)n * c->def->n_inputs); } catch (...) { return fail(B3W_ERR_NOMEM, "out of host memory"); }
+  int rc = b3w_inputs_from_fr((uint32_t)(c->def - CIRCUITS), in_fr, n, rows.data());
+  if (rc) return rc;
+  return b3w_witness_batch(c, rows.data(), n, out, status, pub);
+}
+
 extern "C" int b3w_witness_one(b3w_ctx *c, const uint32_t *in, uint8_t *out) {
   if (!c || !in || !out) return fail(B3W_ERR_INVALID, "b3w_witness_one: null argument");
   uint8_t status = 0;

@@ -99,6 +99,14 @@ int b3w_witness_one(b3w_ctx *ctx, const uint32_t *in, uint8_t *out);
  * Host buffers from b3w_host_alloc() are pinned and copy at full PCIe rate. */
 int b3w_witness_batch(b3w_ctx *ctx, const uint32_t *in, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub);
 
+/* Field-element inputs: n rows of n_inputs Fr256 (32 bytes little-endian each, any 256-bit value: reduced mod p like
+ * `normalize`, witness_calculator.js:319-323) -- the form in which rust_fold holds them (`Vec<(String, Vec<F>)>`,
+ * rust_fold/src/blake3_circuit.rs:197-289).  b3w_inputs_from_fr converts to the u32 rows of the other entry points
+ * (host-only, needs no GPU); a value outside [0, 2^32) after reduction is refused with B3W_ERR_DOMAIN, naming the
+ * instance and signal.  b3w_witness_batch_fr = convert + b3w_witness_batch. */
+int b3w_inputs_from_fr(uint32_t circuit, const uint8_t *in_fr, uint64_t n, uint32_t *rows);
+int b3w_witness_batch_fr(b3w_ctx *ctx, const uint8_t *in_fr, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub);
+
 /* NEW batched entry point, DEVICE buffers (same layouts), asynchronous on `stream` (a cudaStream_t, may
  * be NULL for the default stream).  d_out must hold n*witness_size*32 bytes, 32-byte aligned. */
 int b3w_witness_batch_device(b3w_ctx *ctx, const uint32_t *d_in, uint64_t n, uint8_t *d_out, uint8_t *d_status,

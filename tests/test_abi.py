@@ -54,6 +54,23 @@ def test_wtns_header_equals_reference_golden(golden, built):
     assert hdr.tobytes() == golden["wtns"].tobytes()[:76]
 
 
+def test_inputs_from_fr_reduces_and_refuses(built):
+    L = pkg.lib()
+    P = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+    vals = [5, P + 7, 2 * P + 0xFFFFFFFF, 0] + list(range(24))
+    fr = np.frombuffer(b"".join(int(v).to_bytes(32, "little") for v in vals), np.uint8).copy()
+    rows = np.zeros(28, np.uint32)
+    assert L.b3w_inputs_from_fr(0, fr.ctypes.data, 1, rows.ctypes.data) == 0
+    assert list(rows) == [5, 7, 0xFFFFFFFF, 0] + list(range(24))
+    vals[9] = 2 ** 32                                            # m[1]
+    fr = np.frombuffer(b"".join(int(v).to_bytes(32, "little") for v in vals), np.uint8).copy()
+    assert L.b3w_inputs_from_fr(0, fr.ctypes.data, 1, rows.ctypes.data) == _lib.B3W_ERR_DOMAIN
+    assert b"input m[1]" in L.b3w_last_error()
+    vals[9] = P - 1                                              # "-1": legal for the wasm, outside the u32 domain here
+    fr = np.frombuffer(b"".join(int(v).to_bytes(32, "little") for v in vals), np.uint8).copy()
+    assert L.b3w_inputs_from_fr(0, fr.ctypes.data, 1, rows.ctypes.data) == _lib.B3W_ERR_DOMAIN
+
+
 def test_packed_sizes(built):
     L = pkg.lib()
     w = C.c_uint32()

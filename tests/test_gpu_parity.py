@@ -187,3 +187,19 @@ def test_multi_gpu_entry_point_matches_single(built):
         small = m.calculateWitnessBatch(rows[:2])            # fewer instances than device slots: empty shards
         assert np.array_equal(small["witness"], want[:2])
         m.close()
+
+
+def test_field_element_inputs_entry_point(wc):
+    """b3w_witness_batch_fr: Fr256 inputs (as rust_fold holds them), reduced mod p like normalize()."""
+    rows = gen.splitmix_compression_inputs(9)
+    P = wc.prime
+    fr = np.zeros((9, 28, 32), np.uint8)
+    for i in range(9):
+        for k in range(28):
+            v = int(rows[i, k]) + (P if (i + k) % 3 == 0 else 0)          # some values non-canonical (x + p)
+            fr[i, k] = np.frombuffer(v.to_bytes(32, "little"), np.uint8)
+    out = np.zeros((9, WS * 32), np.uint8)
+    st = np.ones(9, np.uint8)
+    _lib.check(pkg.lib().b3w_witness_batch_fr(wc._h, fr.ctypes.data, 9, out.ctypes.data, st.ctypes.data, None))
+    assert not st.any()
+    assert np.array_equal(out, port.witness_batch("compression", rows, nthreads=2))
