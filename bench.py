@@ -41,6 +41,7 @@ WIT_BYTES = WS * 32                 # 770 976 B written per witness (SURVEY.md 8
 IN_BYTES = 28 * 4                   # 112 B read per witness
 LOG2_BATCH = 16
 METRIC = "blake3_compression witnesses/sec"
+print_json = print
 WORKLOAD = "blake3_compression batch 2^16 random 64-byte blocks, BN254 Fr (BASELINE configs[1]), per GPU"
 
 
@@ -132,7 +133,7 @@ def run_reference(args, rank, world):
         t_total += secs
     value = per_step * args.steps / t_total
     sample = "%d witnesses per step (4 per host thread) of the LCG(6429) sequence, %d steps" % (per_step, args.steps)
-    print(json.dumps({
+    print_json(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "witnesses/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 + Fr256 (BN254)",
@@ -345,7 +346,7 @@ def run_own(args, rank, world, local_rank):
         "gpu_launches": gpu_launches, "clocks": clocks}
     if cpu:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line))
+    print_json(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -366,6 +367,13 @@ def main():
         os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
                                    "--nproc-per-node", str(args.gpus), "--master-addr", "127.0.0.1",
                                    "--master-port", "29517"] + sys.argv)
+    # stdout carries exactly ONE line, the JSON: anything a library prints there (e.g. NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    json_out = os.fdopen(real_stdout, "w")
+    global print_json
+    print_json = lambda line: (json_out.write(line + "\n"), json_out.flush())
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:
