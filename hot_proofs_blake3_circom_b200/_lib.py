@@ -17,7 +17,7 @@ EXPORTS = ("b3w_version", "b3w_last_error", "b3w_create", "b3w_destroy", "b3w_ci
            "b3w_witness_batch_device_checked", "b3w_r1cs_check_device", "b3w_r1cs_info", "b3w_debug_inject_fault",
            "b3w_nova_chain_size", "b3w_nova_chain", "b3w_debug_set_launch", "b3w_assert_trace",
            "b3w_inputs_from_fr", "b3w_witness_batch_fr", "b3w_packed_words", "b3w_witness_batch_packed_device", "b3w_witness_batch_packed", "b3w_unpack_device",
-           "b3w_multi_create", "b3w_multi_destroy", "b3w_multi_size", "b3w_shard_range", "b3w_multi_witness_batch")
+           "b3w_multi_create", "b3w_multi_destroy", "b3w_multi_size", "b3w_shard_range", "b3w_multi_witness_batch", "b3w_multi_nova_chain")
 
 
 class B3WError(RuntimeError):
@@ -85,6 +85,7 @@ def lib():
     L.b3w_multi_size.restype = C.c_uint32
     L.b3w_shard_range.argtypes = [u64, C.c_uint32, C.c_uint32, C.POINTER(u64), C.POINTER(u64)]
     L.b3w_multi_witness_batch.argtypes = [vp, vp, u64, vp, vp, vp]
+    L.b3w_multi_nova_chain.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp, vp]
     L.b3w_host_alloc.argtypes = [C.c_size_t]
     L.b3w_host_alloc.restype = vp
     L.b3w_host_free.argtypes = [vp]

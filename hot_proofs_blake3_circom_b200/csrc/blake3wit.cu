@@ -701,12 +701,13 @@ __global__ void k_parent_cvs(const uint32_t *__restrict__ nodes /* [first..first
 }
 // Step rows of every chunk (one thread per chunk): blake3_circuit.rs format_input() (:197-289) applied along
 // update_for_step() (:185-195), with z0 from main.rs:130-142 and z_{i+1} = the circuit's outputs.
-__global__ void k_chain_rows(const uint8_t *__restrict__ data, uint64_t len, uint64_t n_chunks,
+__global__ void k_chain_rows(const uint8_t *__restrict__ data, uint64_t len, uint64_t chunk_lo, uint64_t chunk_hi,
                              const uint32_t *__restrict__ cv, const uint32_t *__restrict__ path /* [chunk][max_depth] sibling refs */,
                              const uint32_t *__restrict__ depth_of /* parents above chunk c */, uint32_t max_depth,
-                             const uint64_t *__restrict__ step_off, uint32_t *__restrict__ rows) {
-  const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_chunks) return;
+                             const uint64_t *__restrict__ step_off, uint32_t *__restrict__ rows /* of chunks [lo, hi) */,
+                             uint32_t *__restrict__ root /* h_out of chunk 0's last step */) {
+  const uint64_t c = chunk_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= chunk_hi) return;
   const uint32_t n_par = depth_of[c];                 // parent_path.len()
   const uint32_t total_depth = n_par + 1;             // = leaf_depth (blake3_circuit.rs:169, main.rs:71)
   const uint32_t nb = chunk_blocks(len, c);
@@ -714,7 +715,7 @@ __global__ void k_chain_rows(const uint8_t *__restrict__ data, uint64_t len, uin
 #pragma unroll
   for (int i = 0; i < 8; i++) h[i] = B3_IV[i];
   uint32_t block_count = 0, depth = total_depth - 1;
-  uint32_t *row = rows + step_off[c] * 32;
+  uint32_t *row = rows + (step_off[c] - step_off[chunk_lo]) * 32;
   const uint32_t steps = nb + total_depth - 1;        // main.rs:94
   for (uint32_t st = 0; st < steps; st++, row += 32) {
     const bool leaf = st < nb;
@@ -752,6 +753,10 @@ __global__ void k_chain_rows(const uint8_t *__restrict__ data, uint64_t len, uin
       block_count += 1;
     }
     if ((is_parent || last) && !is_root) depth -= 1;
+  }
+  if (c == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) root[i] = h[i];
   }
 }
 
@@ -854,6 +859,8 @@ struct b3w_ctx {
   uint8_t *d_status[2];
   uint32_t *d_pub[2];
   bool ring_ready;
+  void *cs_ptr[8];           // chain driver scratch (grow-only)
+  size_t cs_cap[8];
   // staging for host-buffer batches of PACKED witnesses: 2 slots
   cudaStream_t pk_st[2];
   uint32_t *pk_in[2], *pk_buf[2], *pk_pub[2];
@@ -957,6 +964,8 @@ extern "C" void b3w_destroy(b3w_ctx *c) {
   cudaSetDevice(c->device);
   free_ring(c);
   free_packed_ring(c);
+  for (int i = 0; i < 8; i++)
+    if (c->cs_ptr[i]) cudaFree(c->cs_ptr[i]);
   if (c->d_desc) cudaFree(c->d_desc);
   if (c->d_field) cudaFree(c->d_field);
   if (c->d_fslots) cudaFree(c->d_fslots);
@@ -1395,31 +1404,20 @@ static void fill_paths(tree_plan &t, uint32_t ref, uint64_t n_chunks, std::vecto
   stack.push_back(l); fill_paths(t, r, n_chunks, stack); stack.pop_back();
 }
 
-extern "C" int b3w_nova_chain_size(uint64_t len, uint64_t *n_chunks, uint64_t *total_steps) {
+// Everything the host decides about a file before the device starts: the BLAKE3 tree (parents ordered by height so that
+// one launch hashes one level), every chunk's sibling path and its first step.
+struct chain_plan {
+  uint64_t nc = 0, total = 0;
+  size_t n_par = 0;
+  uint32_t max_depth = 1;
+  std::vector<uint32_t> nodes;                 // level-ordered parents: {left ref, right ref}
+  std::vector<std::pair<uint32_t, uint32_t>> levels;   // {first parent, count} per tree level, bottom up
+  std::vector<uint32_t> path, depth_of;
+  std::vector<uint64_t> step_off;              // nc + 1
+};
+static int make_chain_plan(uint64_t len, chain_plan &p) {
   const uint64_t nc = chunk_count_of(len);
   if (nc > 0x7FFFFFFFull) return fail(B3W_ERR_INVALID, "input too large for the chain driver (%llu chunks)", (unsigned long long)nc);
-  tree_plan t;
-  uint32_t h;
-  t.root = build_tree(t, 0, nc, nc, h);
-  t.max_depth = h ? h : 1;
-  t.depth_of.assign(nc, 0);
-  t.path.assign((size_t)nc * t.max_depth, 0);
-  std::vector<uint32_t> st;
-  fill_paths(t, t.root, nc, st);
-  uint64_t steps = 0;
-  for (uint64_t c = 0; c < nc; c++) steps += blocks_of_chunk(len, c) + t.depth_of[c];
-  if (n_chunks) *n_chunks = nc;
-  if (total_steps) *total_steps = steps;
-  return B3W_OK;
-}
-
-extern "C" int b3w_nova_chain(b3w_ctx *c, const uint8_t *data, uint64_t len, uint8_t *out, uint8_t *status, uint32_t *pub,
-                              uint32_t *rows_out, uint64_t *step_off_out, uint8_t root_out[32]) {
-  if (!c || (!data && len)) return fail(B3W_ERR_INVALID, "b3w_nova_chain: null argument");
-  if (!c->def->nova) return fail(B3W_ERR_INVALID, "b3w_nova_chain needs a nova circuit context");
-  CK(cudaSetDevice(c->device));
-  const uint64_t nc = chunk_count_of(len);
-  if (nc > 0x7FFFFFFFull) return fail(B3W_ERR_INVALID, "input too large for the chain driver");
   tree_plan t;
   uint32_t hgt;
   t.root = build_tree(t, 0, nc, nc, hgt);
@@ -1427,99 +1425,127 @@ extern "C" int b3w_nova_chain(b3w_ctx *c, const uint8_t *data, uint64_t len, uin
   t.depth_of.assign(nc, 0);
   t.path.assign((size_t)nc * t.max_depth, 0);
   { std::vector<uint32_t> st; fill_paths(t, t.root, nc, st); }
-  std::vector<uint64_t> step_off(nc + 1, 0);
-  for (uint64_t k = 0; k < nc; k++) step_off[k + 1] = step_off[k] + blocks_of_chunk(len, k) + t.depth_of[k];
-  const uint64_t total = step_off[nc];
-  const size_t n_par = t.height.size();
-  // parents ordered by height so that one launch handles one level
-  std::vector<uint32_t> order(n_par), remap(n_par);
-  for (size_t i = 0; i < n_par; i++) order[i] = (uint32_t)i;
+  p.nc = nc;
+  p.max_depth = t.max_depth;
+  p.n_par = t.height.size();
+  p.step_off.assign(nc + 1, 0);
+  for (uint64_t k = 0; k < nc; k++) p.step_off[k + 1] = p.step_off[k] + blocks_of_chunk(len, k) + t.depth_of[k];
+  p.total = p.step_off[nc];
+  std::vector<uint32_t> order(p.n_par), remap(p.n_par);
+  for (size_t i = 0; i < p.n_par; i++) order[i] = (uint32_t)i;
   std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return t.height[a] < t.height[b]; });
-  for (size_t i = 0; i < n_par; i++) remap[order[i]] = (uint32_t)i;
+  for (size_t i = 0; i < p.n_par; i++) remap[order[i]] = (uint32_t)i;
   auto fix = [&](uint32_t ref) { return ref < nc ? ref : (uint32_t)(nc + remap[ref - nc]); };
-  std::vector<uint32_t> nodes(2 * n_par + 2);
-  for (size_t i = 0; i < n_par; i++) { nodes[2 * i] = fix(t.nodes[2 * order[i]]); nodes[2 * i + 1] = fix(t.nodes[2 * order[i] + 1]); }
+  p.nodes.assign(2 * p.n_par + 2, 0);
+  for (size_t i = 0; i < p.n_par; i++) { p.nodes[2 * i] = fix(t.nodes[2 * order[i]]); p.nodes[2 * i + 1] = fix(t.nodes[2 * order[i] + 1]); }
   for (auto &r : t.path) r = fix(r);
-  const uint32_t root_ref = fix(t.root);
-
-  uint8_t *d_data = nullptr; uint32_t *d_cv = nullptr, *d_nodes = nullptr, *d_path = nullptr, *d_depth = nullptr, *d_rows = nullptr;
-  uint64_t *d_off = nullptr;
-  const size_t padded = (size_t)nc * 1024;
-  int rc = B3W_OK;
-  cudaError_t e = cudaMalloc(&d_data, padded);
-  if (e == cudaSuccess) e = cudaMemset(d_data, 0, padded);
-  if (e == cudaSuccess && len) e = cudaMemcpy(d_data, data, len, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMalloc(&d_cv, (nc + n_par) * 32);
-  if (e == cudaSuccess) e = cudaMalloc(&d_nodes, nodes.size() * 4);
-  if (e == cudaSuccess) e = cudaMemcpy(d_nodes, nodes.data(), nodes.size() * 4, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMalloc(&d_path, t.path.size() * 4);
-  if (e == cudaSuccess) e = cudaMemcpy(d_path, t.path.data(), t.path.size() * 4, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMalloc(&d_depth, nc * 4);
-  if (e == cudaSuccess) e = cudaMemcpy(d_depth, t.depth_of.data(), nc * 4, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMalloc(&d_off, (nc + 1) * 8);
-  if (e == cudaSuccess) e = cudaMemcpy(d_off, step_off.data(), (nc + 1) * 8, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMalloc(&d_rows, total * 128);
-  if (e == cudaSuccess) {
-    k_chunk_cvs<<<(unsigned)((nc + 127) / 128), 128>>>(d_data, len, nc, d_cv);
-    size_t i = 0;
-    while (i < n_par) {                                   // one launch per tree level
-      size_t j = i;
-      while (j < n_par && t.height[order[j]] == t.height[order[i]]) j++;
-      k_parent_cvs<<<(unsigned)((j - i + 127) / 128), 128>>>(d_nodes, (uint32_t)i, (uint32_t)(j - i), nc, d_cv);
-      i = j;
-    }
-    k_chain_rows<<<(unsigned)((nc + 63) / 64), 64>>>(d_data, len, nc, d_cv, d_path, d_depth, t.max_depth, d_off, d_rows);
-    e = cudaGetLastError();
+  for (size_t i = 0; i < p.n_par;) {
+    size_t j = i;
+    while (j < p.n_par && t.height[order[j]] == t.height[order[i]]) j++;
+    p.levels.push_back({(uint32_t)i, (uint32_t)(j - i)});
+    i = j;
   }
-  if (e == cudaSuccess && rows_out) e = cudaMemcpy(rows_out, d_rows, total * 128, cudaMemcpyDeviceToHost);
-  if (e == cudaSuccess && step_off_out) memcpy(step_off_out, step_off.data(), (nc + 1) * 8);
-  if (e != cudaSuccess) rc = fail(B3W_ERR_CUDA, "b3w_nova_chain: %s", cudaGetErrorString(e));
-  // all step witnesses, chunk by chunk through the ring (or straight to `out`)
-  if (rc == B3W_OK) {
-    rc = ensure_ring(c);
-    const size_t wbytes = (size_t)c->def->ws * 32;
-    uint64_t done = 0;
-    int k = 0;
-    while (rc == B3W_OK && done < total) {
-      uint64_t m = total - done < c->chunk ? total - done : c->chunk;
-      cudaStream_t s = c->st[k];
-      rc = launch_witness(c, d_rows + done * 32, m, c->d_ring[k], c->d_status[k], c->d_pub[k], s, (c->flags & B3W_FLAG_FUSED_CHECK) != 0);
-      if (rc) break;
-      cudaError_t e2 = cudaSuccess;
-      if (out) e2 = cudaMemcpyAsync(out + done * wbytes, c->d_ring[k], (size_t)m * wbytes, cudaMemcpyDeviceToHost, s);
-      if (e2 == cudaSuccess && status) e2 = cudaMemcpyAsync(status + done, c->d_status[k], (size_t)m, cudaMemcpyDeviceToHost, s);
-      if (e2 == cudaSuccess && pub) e2 = cudaMemcpyAsync(pub + done * 15, c->d_pub[k], (size_t)m * 60, cudaMemcpyDeviceToHost, s);
-      done += m;
-      k ^= 1;
-      if (e2 == cudaSuccess && done < total) e2 = cudaStreamSynchronize(c->st[k]);
-      if (e2 != cudaSuccess) rc = fail(B3W_ERR_CUDA, "b3w_nova_chain: %s", cudaGetErrorString(e2));
-    }
-    if (rc == B3W_OK) {
-      cudaError_t e2 = cudaStreamSynchronize(c->st[0]);
-      if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(c->st[1]);
-      if (e2 != cudaSuccess) rc = fail(B3W_ERR_CUDA, "b3w_nova_chain: %s", cudaGetErrorString(e2));
-    }
-  }
-  // the BLAKE3 root: root parent (or the lone chunk) re-compressed with the ROOT flag = the last step's h_out of any chunk
-  if (rc == B3W_OK && root_out) {
-    (void)root_ref;
-    std::vector<uint32_t> last(15);
-    // the last step of chunk 0 outputs the root chaining value (z_{i+1}[2..10]); it is in `pub` when given, else recompute
-    uint32_t *d_p1 = nullptr; uint8_t *d_o1 = nullptr, *d_s1 = nullptr;
-    cudaError_t e3 = cudaMalloc(&d_p1, 64);
-    if (e3 == cudaSuccess) e3 = cudaMalloc(&d_o1, (size_t)c->def->ws * 32);
-    if (e3 == cudaSuccess) e3 = cudaMalloc(&d_s1, 1);
-    if (e3 == cudaSuccess) {
-      rc = launch_witness(c, d_rows + (step_off[1] - 1) * 32, 1, d_o1, d_s1, d_p1, 0);
-      if (rc == B3W_OK) e3 = cudaMemcpy(last.data(), d_p1, 60, cudaMemcpyDeviceToHost);
-    }
-    if (e3 != cudaSuccess) rc = fail(B3W_ERR_CUDA, "b3w_nova_chain: %s", cudaGetErrorString(e3));
-    if (rc == B3W_OK) memcpy(root_out, &last[2], 32);
-    cudaFree(d_p1); cudaFree(d_o1); cudaFree(d_s1);
-  }
-  cudaFree(d_data); cudaFree(d_cv); cudaFree(d_nodes); cudaFree(d_path); cudaFree(d_depth); cudaFree(d_off); cudaFree(d_rows);
-  return rc;
+  p.path.swap(t.path);
+  p.depth_of.swap(t.depth_of);
+  return B3W_OK;
 }
+
+extern "C" int b3w_nova_chain_size(uint64_t len, uint64_t *n_chunks, uint64_t *total_steps) {
+  chain_plan p;
+  int rc = make_chain_plan(len, p);
+  if (rc) return rc;
+  if (n_chunks) *n_chunks = p.nc;
+  if (total_steps) *total_steps = p.total;
+  return B3W_OK;
+}
+
+// grow-only device scratch of the chain driver, kept in the context (cudaMalloc / cudaFree per call cost more than the
+// whole 1 MiB job)
+enum { CS_DATA, CS_CV, CS_NODES, CS_PATH, CS_DEPTH, CS_OFF, CS_ROWS, CS_ROOT, CS_SLOTS };
+static int chain_scratch(b3w_ctx *c, int slot, size_t need, void **out) {
+  if (c->cs_cap[slot] < need) {
+    if (c->cs_ptr[slot]) cudaFree(c->cs_ptr[slot]);
+    c->cs_ptr[slot] = nullptr;
+    c->cs_cap[slot] = 0;
+    size_t cap = need + need / 4 + 256;
+    CK(cudaMalloc(&c->cs_ptr[slot], cap));
+    c->cs_cap[slot] = cap;
+  }
+  *out = c->cs_ptr[slot];
+  return B3W_OK;
+}
+
+// Steps of chunks [lo, hi) of the file: this device hashes the whole tree (cheap), builds the rows of its chunks and
+// generates their step witnesses; host outputs are the caller's FULL arrays, written at this range's offsets.
+static int nova_chain_range(b3w_ctx *c, const chain_plan &p, const uint8_t *data, uint64_t len, uint64_t lo, uint64_t hi, uint8_t *out,
+                            uint8_t *status, uint32_t *pub, uint32_t *rows_out, uint8_t root_out[32]) {
+  CK(cudaSetDevice(c->device));
+  int rc = ensure_ring(c);
+  if (rc) return rc;
+  const uint64_t nc = p.nc, first = p.step_off[lo], total = p.step_off[hi] - first;
+  uint8_t *d_data; uint32_t *d_cv, *d_nodes, *d_path, *d_depth, *d_rows, *d_root; uint64_t *d_off;
+  const size_t padded = (size_t)nc * 1024;
+  if ((rc = chain_scratch(c, CS_DATA, padded, (void **)&d_data))) return rc;
+  if ((rc = chain_scratch(c, CS_CV, (nc + p.n_par) * 32, (void **)&d_cv))) return rc;
+  if ((rc = chain_scratch(c, CS_NODES, p.nodes.size() * 4, (void **)&d_nodes))) return rc;
+  if ((rc = chain_scratch(c, CS_PATH, p.path.size() * 4, (void **)&d_path))) return rc;
+  if ((rc = chain_scratch(c, CS_DEPTH, nc * 4, (void **)&d_depth))) return rc;
+  if ((rc = chain_scratch(c, CS_OFF, (nc + 1) * 8, (void **)&d_off))) return rc;
+  if ((rc = chain_scratch(c, CS_ROWS, (size_t)total * 128, (void **)&d_rows))) return rc;
+  if ((rc = chain_scratch(c, CS_ROOT, 32, (void **)&d_root))) return rc;
+  cudaStream_t s0 = c->st[0];
+  // the tail of the last chunk is zero padding (load_block reads whole 64-byte blocks)
+  const size_t tail = len & ~(size_t)1023;
+  CK(cudaMemsetAsync(d_data + tail, 0, padded - tail, s0));
+  if (len) CK(cudaMemcpyAsync(d_data, data, len, cudaMemcpyHostToDevice, s0));
+  CK(cudaMemcpyAsync(d_nodes, p.nodes.data(), p.nodes.size() * 4, cudaMemcpyHostToDevice, s0));
+  CK(cudaMemcpyAsync(d_path, p.path.data(), p.path.size() * 4, cudaMemcpyHostToDevice, s0));
+  CK(cudaMemcpyAsync(d_depth, p.depth_of.data(), nc * 4, cudaMemcpyHostToDevice, s0));
+  CK(cudaMemcpyAsync(d_off, p.step_off.data(), (nc + 1) * 8, cudaMemcpyHostToDevice, s0));
+  k_chunk_cvs<<<(unsigned)((nc + 127) / 128), 128, 0, s0>>>(d_data, len, nc, d_cv);
+  for (const auto &lv : p.levels)                                   // one launch per tree level
+    k_parent_cvs<<<(lv.second + 127) / 128, 128, 0, s0>>>(d_nodes, lv.first, lv.second, nc, d_cv);
+  k_chain_rows<<<(unsigned)((hi - lo + 63) / 64), 64, 0, s0>>>(d_data, len, lo, hi, d_cv, d_path, d_depth, p.max_depth, d_off, d_rows, d_root);
+  CK(cudaGetLastError());
+  if (rows_out) CK(cudaMemcpyAsync(rows_out + first * 32, d_rows, (size_t)total * 128, cudaMemcpyDeviceToHost, s0));
+  if (root_out && lo == 0) CK(cudaMemcpyAsync(root_out, d_root, 32, cudaMemcpyDeviceToHost, s0));
+  CK(cudaEventRecord(c->ev[0], s0));
+  CK(cudaStreamWaitEvent(c->st[1], c->ev[0], 0));                   // the rows exist before slot 1's first launch
+  // all step witnesses of the range, ring chunk by ring chunk (or straight to `out`)
+  const size_t wbytes = (size_t)c->def->ws * 32;
+  uint64_t done = 0;
+  int k = 0;
+  while (done < total) {
+    const uint64_t m = total - done < c->chunk ? total - done : c->chunk;
+    cudaStream_t s = c->st[k];
+    rc = launch_witness(c, d_rows + done * 32, m, c->d_ring[k], c->d_status[k], c->d_pub[k], s, (c->flags & B3W_FLAG_FUSED_CHECK) != 0);
+    if (rc) return rc;
+    const uint64_t g = first + done;
+    if (out) CK(cudaMemcpyAsync(out + g * wbytes, c->d_ring[k], (size_t)m * wbytes, cudaMemcpyDeviceToHost, s));
+    if (status) CK(cudaMemcpyAsync(status + g, c->d_status[k], (size_t)m, cudaMemcpyDeviceToHost, s));
+    if (pub) CK(cudaMemcpyAsync(pub + g * 15, c->d_pub[k], (size_t)m * 60, cudaMemcpyDeviceToHost, s));
+    done += m;
+    k ^= 1;
+    if (done < total) CK(cudaStreamSynchronize(c->st[k]));          // before reusing slot k its stream must have drained
+  }
+  CK(cudaStreamSynchronize(c->st[0]));
+  CK(cudaStreamSynchronize(c->st[1]));
+  return B3W_OK;
+}
+
+extern "C" int b3w_nova_chain(b3w_ctx *c, const uint8_t *data, uint64_t len, uint8_t *out, uint8_t *status, uint32_t *pub,
+                              uint32_t *rows_out, uint64_t *step_off_out, uint8_t root_out[32]) {
+  if (!c || (!data && len)) return fail(B3W_ERR_INVALID, "b3w_nova_chain: null argument");
+  if (!c->def->nova) return fail(B3W_ERR_INVALID, "b3w_nova_chain needs a nova circuit context");
+  chain_plan p;
+  int rc = make_chain_plan(len, p);
+  if (rc) return rc;
+  if (step_off_out) memcpy(step_off_out, p.step_off.data(), (p.nc + 1) * 8);
+  return nova_chain_range(c, p, data, len, 0, p.nc, out, status, pub, rows_out, root_out);
+}
+
+// (the multi-GPU form, b3w_multi_nova_chain, is with the other b3w_multi_* entry points below: the unit of sharding is a
+// chunk -- its steps chain into each other, chunks do not -- and every device hashes the whole tree.)
 
 // ------------------------------------------------------------------------------------------------
 // compact witnesses, host side
@@ -1700,6 +1726,41 @@ extern "C" int b3w_multi_witness_batch(b3w_multi *m, const uint32_t *in, uint64_
   for (auto &t : th) t.join();
   for (uint32_t g = 0; g < G; g++)
     if (rc[g]) return fail(rc[g], "device %d (shard %u of %u): %s", m->ctx[g]->device, g, G, err[g].c_str());
+  return B3W_OK;
+}
+
+extern "C" int b3w_multi_nova_chain(b3w_multi *m, const uint8_t *data, uint64_t len, uint8_t *out, uint8_t *status, uint32_t *pub,
+                                    uint32_t *rows_out, uint64_t *step_off_out, uint8_t root_out[32]) {
+  if (!m || m->ctx.empty() || (!data && len)) return fail(B3W_ERR_INVALID, "b3w_multi_nova_chain: null argument");
+  if (!m->ctx[0]->def->nova) return fail(B3W_ERR_INVALID, "b3w_multi_nova_chain needs a nova circuit context");
+  chain_plan p;
+  int rc0 = make_chain_plan(len, p);
+  if (rc0) return rc0;
+  if (step_off_out) memcpy(step_off_out, p.step_off.data(), (p.nc + 1) * 8);
+  const uint32_t G = (uint32_t)m->ctx.size();
+  // chunk boundaries that split the STEPS evenly: device g takes chunks [cut[g], cut[g+1])
+  std::vector<uint64_t> cut(G + 1, p.nc);
+  cut[0] = 0;
+  for (uint32_t g = 1; g < G; g++) {
+    const uint64_t target = p.total / G * g;
+    cut[g] = (uint64_t)(std::lower_bound(p.step_off.begin(), p.step_off.end(), target) - p.step_off.begin());
+    if (cut[g] > p.nc) cut[g] = p.nc;
+    if (cut[g] < cut[g - 1]) cut[g] = cut[g - 1];
+  }
+  std::vector<int> rc(G, B3W_OK);
+  std::vector<std::string> err(G);
+  std::vector<std::thread> th;
+  for (uint32_t g = 0; g < G; g++) {
+    if (cut[g] == cut[g + 1]) continue;
+    th.emplace_back([&, g]() {
+      rc[g] = nova_chain_range(m->ctx[g], p, data, len, cut[g], cut[g + 1], out, status, pub, rows_out, root_out);
+      if (rc[g]) err[g] = g_err;
+    });
+  }
+  for (auto &t : th) t.join();
+  for (uint32_t g = 0; g < G; g++)
+    if (rc[g]) return fail(rc[g], "device %d (chunks %llu..%llu): %s", m->ctx[g]->device, (unsigned long long)cut[g],
+                           (unsigned long long)cut[g + 1], err[g].c_str());
   return B3W_OK;
 }
 

@@ -86,6 +86,40 @@ def _to_bigint(n):
     raise TypeError("Cannot convert %r to a BigInt" % (n,))
 
 
+def pinned_array(shape, dtype):
+    """numpy array in pinned host memory (b3w_host_alloc): copies to / from the GPU run at full PCIe rate and overlap
+    with kernels.  Freed when the array is garbage collected."""
+    import weakref
+    L = _lib.lib()
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) * dt.itemsize
+    p = L.b3w_host_alloc(max(n, 1))
+    if not p:
+        raise B3WError(_lib.B3W_ERR_NOMEM, L.b3w_last_error().decode(errors="replace"))
+    buf = (C.c_uint8 * max(n, 1)).from_address(p)
+    arr = np.frombuffer(buf, dt, count=int(np.prod(shape))).reshape(shape)
+    weakref.finalize(buf, L.b3w_host_free, p)
+    return arr
+
+
+def _nova_chain(L, call, handle, witness_size, data, want_witness):
+    data = bytes(data)
+    nc, ns = C.c_uint64(), C.c_uint64()
+    _lib.check(L.b3w_nova_chain_size(len(data), C.byref(nc), C.byref(ns)))
+    nc, ns = nc.value, ns.value
+    buf = np.frombuffer(data, np.uint8) if data else np.zeros(1, np.uint8)
+    rows = pinned_array((ns, 32), np.uint32)
+    step_off = np.zeros(nc + 1, np.uint64)
+    status = pinned_array((ns,), np.uint8)
+    pub = pinned_array((ns, 15), np.uint32)
+    out = pinned_array((ns, witness_size * 32), np.uint8) if want_witness else None
+    root = np.zeros(32, np.uint8)
+    _lib.check(call(handle, buf.ctypes.data, len(data), out.ctypes.data if want_witness else None, status.ctypes.data,
+                    pub.ctypes.data, rows.ctypes.data, step_off.ctypes.data, root.ctypes.data))
+    return {"n_chunks": nc, "total_steps": ns, "step_off": step_off, "rows": rows, "status": status, "pub": pub,
+            "witness": out, "root": root.tobytes()}
+
+
 class WitnessCalculator:
     def __init__(self, circuit, sanity_check, device=-1, chunk=0, lazy=False, fused_check=False):
         L = _lib.lib()
@@ -266,22 +300,7 @@ class WitnessCalculator:
     def novaChain(self, data, want_witness=False):
         """data: bytes.  Returns dict(n_chunks, total_steps, step_off=u64[n_chunks+1], rows=(steps,32) u32 step inputs,
         status=u8[steps], pub=(steps,15) u32 = z_{i+1}, witness=(steps, witnessSize*32) u8 | None, root=32 bytes)."""
-        data = bytes(data)
-        nc, ns = C.c_uint64(), C.c_uint64()
-        _lib.check(self._L.b3w_nova_chain_size(len(data), C.byref(nc), C.byref(ns)))
-        nc, ns = nc.value, ns.value
-        buf = np.frombuffer(data, np.uint8) if data else np.zeros(1, np.uint8)
-        rows = np.zeros((ns, 32), np.uint32)
-        step_off = np.zeros(nc + 1, np.uint64)
-        status = np.zeros(ns, np.uint8)
-        pub = np.zeros((ns, 15), np.uint32)
-        out = np.empty((ns, self.witnessSize * 32), np.uint8) if want_witness else None
-        root = np.zeros(32, np.uint8)
-        _lib.check(self._L.b3w_nova_chain(self._h, buf.ctypes.data, len(data), out.ctypes.data if want_witness else None,
-                                          status.ctypes.data, pub.ctypes.data, rows.ctypes.data, step_off.ctypes.data,
-                                          root.ctypes.data))
-        return {"n_chunks": nc, "total_steps": ns, "step_off": step_off, "rows": rows, "status": status, "pub": pub,
-                "witness": out, "root": root.tobytes()}
+        return _nova_chain(self._L, self._L.b3w_nova_chain, self._h, self.witnessSize, data, want_witness)
 
     # ---- device-pointer plumbing used by bench.py / tests (torch supplies memory and streams) ----
     def witness_batch_device(self, d_in, n, d_out, d_status=0, d_pub=0, stream=0):
@@ -365,6 +384,10 @@ class MultiGpuCalculator:
         _lib.check(self._L.b3w_multi_witness_batch(self._m, rows.ctypes.data, n, out.ctypes.data if want_witness else None,
                                                    status.ctypes.data, pub.ctypes.data))
         return {"witness": out if want_witness else None, "status": status, "pub": pub}
+
+    def novaChain(self, data, want_witness=False):
+        """WitnessCalculator.novaChain over all devices: chunks are sharded (balanced by step count), no collective."""
+        return _nova_chain(self._L, self._L.b3w_multi_nova_chain, self._m, self.witnessSize, data, want_witness)
 
     def witness_batch_host(self, h_in, n, h_out=None, h_status=None, h_pub=None):
         """raw host pointers (e.g. from b3w_host_alloc); used by the benches"""

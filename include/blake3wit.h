@@ -192,6 +192,11 @@ void b3w_multi_destroy(b3w_multi *m);
 uint32_t b3w_multi_size(const b3w_multi *m);
 int b3w_shard_range(uint64_t n, uint32_t g, uint32_t n_shards, uint64_t *first, uint64_t *count);
 int b3w_multi_witness_batch(b3w_multi *m, const uint32_t *in, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub);
+/* b3w_nova_chain over several GPUs: the unit of sharding is a chunk (its steps chain into each other, chunks do not);
+ * every device hashes the whole BLAKE3 tree (cheap) and generates the step witnesses of a contiguous range of chunks,
+ * ranges balanced by step count, each writing its slice of the caller's arrays.  Same arguments as b3w_nova_chain. */
+int b3w_multi_nova_chain(b3w_multi *m, const uint8_t *data, uint64_t len, uint8_t *out, uint8_t *status, uint32_t *pub,
+                         uint32_t *rows, uint64_t *step_off, uint8_t root[32]);
 
 /* pinned host memory for batch buffers */
 void *b3w_host_alloc(size_t bytes);

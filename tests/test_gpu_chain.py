@@ -87,3 +87,31 @@ def test_config3_one_mebibyte(wc):
         ref = ref_wasm.RefWasm("nova_bn_o2")
         want, st, _ = ref.batch_u32(rows[sel[:26]], nthreads=min(NCPU, 26))
         assert (st == 0).all() and np.array_equal(got[:26], want)
+
+
+@pytest.mark.parametrize("n", [0, 1000, 5123, 64 * 1024 + 77])
+def test_multi_gpu_chain_equals_single(wc, n):
+    """b3w_multi_nova_chain: chunks sharded over device slots (balanced by steps), every slot hashes the whole tree.
+    With one GPU the same device is listed three times; on a multi-GPU box all visible devices are used too."""
+    import torch
+    data = synth(n)
+    one = wc.novaChain(data, want_witness=n <= 5123)
+    configs = [[0, 0, 0]] + ([None] if torch.cuda.device_count() > 1 else [])
+    for devices in configs:
+        m = pkg.MultiGpuCalculator("blake3_nova", devices=devices, chunk=64)
+        res = m.novaChain(data, want_witness=n <= 5123)
+        for k in ("rows", "status", "pub", "step_off"):
+            assert np.array_equal(res[k], one[k]), k
+        assert res["root"] == one["root"] and res["total_steps"] == one["total_steps"]
+        if n <= 5123:
+            assert np.array_equal(res["witness"], one["witness"])
+        m.close()
+
+
+def test_chain_called_twice_with_shrinking_input(wc):
+    # the grow-only device scratch is reused: stale bytes of a longer earlier input must not leak into a shorter one
+    big, small = synth(9000), synth(1500, seed=7)
+    wc.novaChain(big)
+    res = wc.novaChain(small)
+    rows, off, finals = nova_chain_ref.chain_rows(small)
+    assert np.array_equal(res["rows"], np.array(rows, np.uint32)) and res["root"] == finals[0]
