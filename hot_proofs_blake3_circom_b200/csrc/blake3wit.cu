@@ -1,4 +1,6 @@
-// blake3wit.cu -- sm_100a kernels + C ABI of libblake3wit.so (see include/blake3wit.h).
+// blake3wit.cu -- C ABI of libblake3wit.so (see include/blake3wit.h) and the host side around the sm_100a kernels, which
+// live in kernels_witness.cuh (trace + expansion + fused check), kernels_chain.cuh (BLAKE3 tree, step rows) and
+// kernels_aux.cuh (compact witnesses, HBM check, checksum, calibration).
 //
 // Replaces the reference's wasm witness programs (build/**/**.wasm driven by
 // blake3_nova_js/witness_calculator.js:131-272).  Per instance:
@@ -46,742 +48,9 @@ static int fail(int code, const char *fmt, ...) {
     if (e_ != cudaSuccess) return fail(B3W_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
 
-// ------------------------------------------------------------------------------------------------
-// device helpers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t rotr32(uint32_t x, int r) { return __funnelshift_r(x, x, r); }
-
-// Cache policy of the witness stores: written once and never re-read by this kernel, so they bypass L1 and are marked
-// evict-first in L2 (keeps the descriptor / field tables resident there; +5 % on the nova kernel, +0.3 % on compression).
-// B3W_ST_HINT is an experiment switch; 1 is what ships.
-#ifndef B3W_ST_HINT
-#define B3W_ST_HINT 1
-#endif
-#if B3W_ST_HINT == 0
-#define B3W_ST_QUAL ".L1::no_allocate"
-#elif B3W_ST_HINT == 1
-#define B3W_ST_QUAL ".L1::no_allocate.L2::evict_first"
-#else
-#define B3W_ST_QUAL ".cs"
-#endif
-// 256-bit streaming store of one witness slot {w0..w7}: written once, never re-read by this kernel.
-__device__ __forceinline__ void st_slot(void *p, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4,
-                                        uint32_t w5, uint32_t w6, uint32_t w7) {
-  asm volatile("st.global" B3W_ST_QUAL ".v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w0), "r"(w1), "r"(w2),
-               "r"(w3), "r"(w4), "r"(w5), "r"(w6), "r"(w7)
-               : "memory");
-}
-
-// A full 8-limb field element goes out as two 128-bit stores.  (ptxas 12.9 mis-handles the live ranges of a
-// v8.b32 store whose eight operands are all computed values inside a non-inlined function and keeps only the first
-// limb -- seen in SASS as a 32-bit STG; the {lo, hi, 0...} form above is not affected.  tests/test_gpu_nova.py pins it.)
-__device__ __forceinline__ void st_slot_fr(void *p, const uint32_t *l) {
-  asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
-  asm volatile("st.global.L1::no_allocate.v4.b32 [%0+16], {%1,%2,%3,%4};" ::"l"(p), "r"(l[4]), "r"(l[5]), "r"(l[6]), "r"(l[7]) : "memory");
-}
-
-// BLAKE3 message schedule: MSG_SCHED[r][j] = index into the original m[] of the word that round r
-// sees at position j, i.e. sigma applied r times (circuits/blake3_common.circom:20-24,
-// circuits/blake3_compression.circom:198-209).
-__constant__ uint8_t MSG_SCHED[7][16] = {
-    {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15},
-    {2, 6, 3, 10, 7, 0, 4, 13, 1, 11, 12, 5, 9, 14, 15, 8},
-    {3, 4, 10, 12, 13, 2, 7, 14, 6, 5, 9, 0, 11, 15, 8, 1},
-    {10, 7, 12, 9, 14, 3, 13, 15, 4, 0, 11, 2, 5, 8, 1, 6},
-    {12, 13, 9, 11, 15, 10, 14, 8, 7, 2, 5, 3, 0, 1, 6, 4},
-    {9, 14, 11, 5, 8, 12, 15, 1, 13, 3, 0, 10, 2, 6, 4, 7},
-    {11, 15, 5, 0, 1, 9, 8, 6, 14, 10, 2, 12, 3, 4, 7, 13}};
-
-// One HalfFunG (circuits/blake3_compression.circom:72-100) on this lane's (a,b,c,d); lanes 0..3 record it.
-template <int R1, int R2>
-__device__ __forceinline__ void half_g(uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &d, uint32_t xy, uint32_t *rec,
-                                       bool writer) {
-  uint32_t s = a + b;
-  uint32_t hi1 = (s < a);
-  uint32_t s2 = s + xy;
-  hi1 += (s2 < s);                       // add1 = Bits34(v[a]+v[b]+xy): carries u = bit0, v = bit1   (:83,:88)
-  uint32_t d_old = d;
-  d = rotr32(d ^ s2, R1);                // rxor2 = RotXorWordBits(R1)(v[d], add1.out_bits)            (:89-90)
-  uint32_t t = c + d;
-  uint32_t hi3 = (t < c);                // add3 = Bits33(v[c] + rxor2.out_word)                        (:91)
-  uint32_t b_old = b;
-  b = rotr32(b ^ t, R2);                 // rxor4 = RotXorWordBits(R2)(v[b], add3.out_bits)            (:92-93)
-  a = s2;
-  c = t;
-  if (writer) {
-    *reinterpret_cast<uint4 *>(rec) = make_uint4(a, hi1, d_old, d);
-    *reinterpret_cast<uint4 *>(rec + 4) = make_uint4(c, hi3, b_old, b);
-  }
-}
-
-// This lane's slice of the message schedule, packed for registers: word r holds the four m[] indices that lane
-// q = lane & 3 needs in round r (columns: msg[2q], msg[2q+1]; diagonals: msg[8+2q], msg[9+2q]), one byte each.
-struct lane_sched { uint32_t w[7]; };
-__device__ __forceinline__ lane_sched load_lane_sched(int lane) {
-  const int q = lane & 3;
-  lane_sched ls;
-#pragma unroll
-  for (int r = 0; r < 7; r++)
-    ls.w[r] = (uint32_t)MSG_SCHED[r][2 * q] | ((uint32_t)MSG_SCHED[r][2 * q + 1] << 8) | ((uint32_t)MSG_SCHED[r][8 + 2 * q] << 16) |
-              ((uint32_t)MSG_SCHED[r][9 + 2 * q] << 24);
-  return ls;
-}
-
-// Phase 1 for the compression circuit.  trace[TR_IN..TR_IN+28) must already hold h,m,t,b,d.
-// All 32 lanes execute (8 redundant groups of 4); lanes 0..3 write.
-__device__ __forceinline__ void compression_trace(uint32_t *trace, int lane, const lane_sched &ls) {
-  const int q = lane & 3;
-  const bool writer = lane < 4;
-  const uint32_t IVq[4] = {0x6A09E667u, 0xBB67AE85u, 0x3C6EF372u, 0xA54FF53Au};
-  uint32_t a = trace[TR_IN + q];                 // v[q]     = h[q]
-  uint32_t b = trace[TR_IN + 4 + q];             // v[4+q]   = h[4+q]
-  uint32_t c = q == 0 ? IVq[0] : q == 1 ? IVq[1] : q == 2 ? IVq[2] : IVq[3];   // v[8+q] = IV[q]
-  uint32_t d = trace[TR_IN + 24 + q];            // v[12+q]  = t0,t1,b,d               (:184-187)
-  const uint32_t h_lo = a, h_hi = b;
-  const uint32_t *m = trace + TR_IN + 8;
-#pragma unroll
-  for (int r = 0; r < 7; r++) {
-    uint32_t *rec = trace + TR_HG + 128 * r + 16 * q;
-    const uint32_t sw = ls.w[r];
-    const uint32_t m0 = m[sw & 15u], m1 = m[(sw >> 8) & 15u], m2 = m[(sw >> 16) & 15u], m3 = m[sw >> 24];
-    // columns: G(q, 4+q, 8+q, 12+q) with msg[2q], msg[2q+1]                              (:145-148)
-    half_g<16, 12>(a, b, c, d, m0, rec, writer);
-    half_g<8, 7>(a, b, c, d, m1, rec + 8, writer);
-    // diagonals: lane q takes b from column q+1, c from q+2, d from q+3                  (:150-153)
-    b = __shfl_sync(0xffffffffu, b, (q + 1) & 3, 4);
-    c = __shfl_sync(0xffffffffu, c, (q + 2) & 3, 4);
-    d = __shfl_sync(0xffffffffu, d, (q + 3) & 3, 4);
-    half_g<16, 12>(a, b, c, d, m2, rec + 64, writer);
-    half_g<8, 7>(a, b, c, d, m3, rec + 72, writer);
-    b = __shfl_sync(0xffffffffu, b, (q + 3) & 3, 4);
-    c = __shfl_sync(0xffffffffu, c, (q + 2) & 3, 4);
-    d = __shfl_sync(0xffffffffu, d, (q + 1) & 3, 4);
-  }
-  if (writer) {                                  // out[i] = v[i]^v[i+8], out[i+8] = v[i+8]^h[i]  (:213-227)
-    trace[TR_OUT + q] = a ^ c;
-    trace[TR_OUT + 4 + q] = b ^ d;
-    trace[TR_OUT + 8 + q] = c ^ h_lo;
-    trace[TR_OUT + 12 + q] = d ^ h_hi;
-  }
-}
-
-// Phase 1 for the nova step circuit Blake3Nova(0) (circuits/blake3_nova.circom:169-267, as built: without
-// the Num2Bits(8) range checks of :25-30).  trace[NV_IN..NV_IN+32) holds the 32 inputs.  Computes every
-// nova-level value (trace indices: nova_trace.h, generated from tools/circuit_model.py) and the inputs of
-// the embedded compression (TR_IN..).  Returns false when a constraint fails ("Assert Failed.").
-__device__ __forceinline__ bool nova_trace(uint32_t *trace, int lane) {
-  const uint32_t *in = trace + NV_IN;
-  const uint32_t n_blocks = in[0], block_count = in[1], low = in[10], high = in[11];
-  const uint32_t leaf_depth = in[12], total_depth = in[13], depth = in[14], bb = in[31];
-  // Blake3NovaTreePath_CheckDepth (:13-45)
-  const int64_t v1 = (int64_t)depth + 256 - ((int64_t)leaf_depth - 1);      // check_parent = LessThan(8)(depth, leaf_depth-1)
-  const int64_t v2 = (int64_t)leaf_depth + 256 - ((int64_t)depth + 1);      // exceed_depth = GreaterEqThan(8)(depth, leaf_depth)
-  // Num2Bits(9) recomposition must hold for both, and exceed_depth.out === 0 (:44)
-  if (v1 < 0 || v1 >= 512 || v2 < 0 || v2 >= 512 || ((v2 >> 8) & 1) == 0) return false;
-  const uint32_t is_parent = 1u - (uint32_t)((v1 >> 8) & 1);
-  const uint32_t is_root = depth == 0;
-  // Blake3GetFlag (:122-167)
-  const uint32_t not_root = 1u - is_root, not_parent = 1u - is_parent;
-  const uint32_t first = block_count == 0;
-  const uint32_t last = (int64_t)block_count == (int64_t)n_blocks - 1;
-  const uint32_t is_last = last & not_parent, first_set = first & not_parent;
-  const uint32_t urf_tmp = is_parent | last, urf = urf_tmp & is_root;
-  const uint32_t dflags = first_set + 2u * is_last + 8u * urf + 4u * is_parent;
-  // Blake3GetDownLeftPath (:47-84): eqs[i] = IsEqual(depth, total_depth - i - 2), i = lane and lane + 32
-  const int64_t in1a = (int64_t)total_depth - lane - 2, in1b = in1a - 32;
-  const int64_t da = in1a - depth, db = in1b - depth;
-  uint2 *eq_in1 = reinterpret_cast<uint2 *>(trace + NV_EQ_IN1), *eq_d = reinterpret_cast<uint2 *>(trace + NV_EQ_D);
-  eq_in1[lane] = make_uint2((uint32_t)in1a, (uint32_t)((uint64_t)in1a >> 32));
-  eq_in1[lane + 32] = make_uint2((uint32_t)in1b, (uint32_t)((uint64_t)in1b >> 32));
-  eq_d[lane] = make_uint2((uint32_t)da, (uint32_t)((uint64_t)da >> 32));
-  eq_d[lane + 32] = make_uint2((uint32_t)db, (uint32_t)((uint64_t)db >> 32));
-  const uint32_t eq_lo = __ballot_sync(0xffffffffu, da == 0), eq_hi = __ballot_sync(0xffffffffu, db == 0);
-  // bit_at_depth[i] = sum_{j<=i} (1 - n2b.out[j]) * eqs[j].out: at most one term is non-zero  (:65,:70)
-  const uint64_t mask = (((uint64_t)eq_hi << 32) | eq_lo) & ~(((uint64_t)high << 32) | low);
-  const uint64_t bad = mask ? ~((mask & (0 - mask)) - 1) : 0;
-  const uint32_t dlp = not_parent + is_parent * (uint32_t)(bad >> 63);      // out (:79); boolean by construction (:81)
-  // Blake3GetFinal_m (:86-120)
-  if (lane < 16) {
-    const uint32_t hw = in[2 + (lane & 7)], mw = in[15 + lane], mo = in[15 + (lane & 7)];
-    const uint32_t td = lane < 8 ? hw * dlp : hw * (1u - dlp);
-    const uint32_t mp = (lane < 8 ? mw * (1u - dlp) : mo * dlp) + td;
-    const uint32_t tp = mp * is_parent;
-    trace[NV_TMP_DOWN + lane] = td;
-    trace[NV_M_IS_PAR + lane] = mp;
-    trace[NV_TMP_IS_PAR + lane] = tp;
-    trace[TR_IN + 8 + lane] = mw * not_parent + tp;                          // out_m -> compression m
-  }
-  if (lane < 8) {                                                           // :229-233
-    const uint32_t IVc[8] = {0x6A09E667u, 0xBB67AE85u, 0x3C6EF372u, 0xA54FF53Au, 0x510E527Fu, 0x9B05688Cu, 0x1F83D9ABu, 0x5BE0CD19u};
-    uint32_t ivw = IVc[0];
-#pragma unroll
-    for (int j = 1; j < 8; j++) ivw = lane == j ? IVc[j] : ivw;
-    const uint32_t tiv = ivw * is_parent;
-    trace[NV_TMPIV + lane] = tiv;
-    trace[TR_IN + lane] = in[2 + lane] * not_parent + tiv;                   // h_compression
-  }
-  if (lane == 0) {
-    const uint32_t cdd = is_last | is_parent, decr = cdd & not_root;        // :254-258
-    const int64_t neg_depth = -(int64_t)depth, neg_bc = -(int64_t)block_count;
-    const int64_t nbm1 = (int64_t)n_blocks - 1, bc_diff = nbm1 - block_count;
-    const uint64_t bc_out = (uint64_t)block_count + not_parent;             // :251
-    trace[NV_V1] = (uint32_t)v1; trace[NV_V2] = (uint32_t)v2;
-    trace[NV_LDM1] = leaf_depth - 1u; trace[NV_DP1] = depth + 1u;
-    trace[NV_IS_PARENT] = is_parent; trace[NV_EXCEED] = 0u; trace[NV_IS_ROOT] = is_root;
-    trace[NV_NOT_ROOT] = not_root; trace[NV_NOT_PARENT] = not_parent;
-    trace[NV_BC_FIRST] = first; trace[NV_BC_LAST] = last; trace[NV_IS_LAST] = is_last; trace[NV_FIRST_SET] = first_set;
-    trace[NV_URF_TMP] = urf_tmp; trace[NV_URF] = urf; trace[NV_DLP] = dlp;
-    trace[NV_CDD] = cdd; trace[NV_DECR] = decr; trace[NV_DEPTH_OUT] = depth - decr;   // :262
-    trace[NV_NEG_DEPTH] = (uint32_t)neg_depth; trace[NV_NEG_DEPTH + 1] = (uint32_t)((uint64_t)neg_depth >> 32);
-    trace[NV_NEG_BC] = (uint32_t)neg_bc; trace[NV_NEG_BC + 1] = (uint32_t)((uint64_t)neg_bc >> 32);
-    trace[NV_NBM1] = (uint32_t)nbm1; trace[NV_NBM1 + 1] = (uint32_t)((uint64_t)nbm1 >> 32);
-    trace[NV_BC_DIFF] = (uint32_t)bc_diff; trace[NV_BC_DIFF + 1] = (uint32_t)((uint64_t)bc_diff >> 32);
-    trace[NV_BC_OUT] = (uint32_t)bc_out; trace[NV_BC_OUT + 1] = (uint32_t)(bc_out >> 32);
-    trace[NV_EQ_OUT] = eq_lo; trace[NV_EQ_OUT + 1] = eq_hi;
-    trace[NV_BAD] = (uint32_t)bad; trace[NV_BAD + 1] = (uint32_t)(bad >> 32);
-    trace[TR_IN + 24] = low * not_parent;                                   // t[0] (:245)
-    trace[TR_IN + 25] = high * not_parent;                                  // t[1] (:244)
-    trace[TR_IN + 26] = bb;
-    trace[TR_IN + 27] = dflags;                                             // comp_d.out (:161-165)
-  }
-  return true;
-}
-
-// Slow path of phase 2 (nova only): a slot that holds a true field element.  Kept out of line so that the hot
-// loop keeps its small register footprint.
-__device__ __forceinline__ void store_field_slot(uint8_t *p, uint32_t kind, uint32_t lo, uint32_t hi,
-                                              const field_consts *__restrict__ F) {
-  const int64_t x = (int64_t)(((uint64_t)hi << 32) | lo);
-  fr_t v;
-  if (kind == DK_S64) v = fr_from_s64(x, F->p);
-  else v = fr_inv_s64(x, *F);
-  st_slot_fr(p, v.l);
-}
-
-// Phase 2: expand the trace into witness slots [s0, s1) at `dst` (32 B per slot).
-// kinds BIT / W32 / W64 are the hot path (single 256-bit store, upper 6 words from RZ).  Nova's true field elements
-// (kinds S64 / INV; 67 .. 260 slots per witness) are skipped here and written by a second pass over the list of field
-// slots (`fslots`: {slot, descriptor} pairs), in which all 32 lanes do field arithmetic together instead of one lane
-// diverging inside the hot loop.
-template <bool HAS_FIELD>
-__device__ __forceinline__ void expand_slots(const uint32_t *trace, const uint32_t *__restrict__ desc, uint32_t s0, uint32_t s1,
-                                             uint8_t *dst, int lane, const field_consts *__restrict__ F,
-                                             const uint2 *__restrict__ fslots, uint32_t n_fslots) {
-#pragma unroll 4
-  for (uint32_t s = s0 + lane; s < s1; s += 32) {
-    const uint32_t dsc = __ldg(desc + s);
-    const uint32_t t = dsc & 0xFFFFu, k = (dsc >> 16) & 31u, kind = dsc >> 24;
-    const uint32_t w = trace[t];
-    uint32_t lo = kind == DK_BIT ? ((w >> k) & 1u) : w;
-    uint32_t hi = kind == DK_W64 ? trace[t + 1] : 0u;
-    if (!HAS_FIELD || kind < DK_S64) st_slot(dst + (size_t)s * 32, lo, hi, 0u, 0u, 0u, 0u, 0u, 0u);
-  }
-  if (HAS_FIELD) {
-    for (uint32_t j = lane; j < n_fslots; j += 32) {
-      const uint2 fs = __ldg(fslots + j);
-      const uint32_t t = fs.y & 0xFFFFu;
-      if (fs.x >= s0 && fs.x < s1) store_field_slot(dst + (size_t)fs.x * 32, fs.y >> 24, trace[t], trace[t + 1], F);
-    }
-  }
-}
-
-#define WARPS_PER_CTA 8
-#define TRACE_STRIDE 960          // u32 words per warp, compression (>= 944, 16-byte multiple)
-#define NOVA_TRACE_STRIDE 1344    // u32 words per warp, nova (>= NOVA_TRACE_WORDS)
-static_assert(NOVA_TRACE_WORDS <= NOVA_TRACE_STRIDE, "nova trace does not fit its stride");
-#define NOVA_SMEM(warps) ((warps) * NOVA_TRACE_STRIDE * 4)
-
-// Optional extras of the checked kernel variants: the fused R1CS check (rows evaluated on the shared-memory trace,
-// nothing re-read from HBM) and a fault-injection hook for its negative tests.
-struct check_args {
-  r1cs_tables_dev T;
-  const field_consts *F;
-  uint32_t *first_bad;       // per instance: smallest violated row id or B3W_NO_ROW (may be NULL)
-  uint32_t fault_word;       // trace word to corrupt (B3W_NO_ROW = none) ...
-  uint32_t fault_mask;       // ... by xor with this mask, after the trace phase
-};
-
-// Work distribution.  A work item is one PART of one instance: slots [part * part_len, (part + 1) * part_len) of its
-// witness.  Warps of the persistent grid take items from a global counter (dynamic scheduling): SMs do not all see the
-// same HBM bandwidth, and with a static split the launch ends with a long tail of slow warps; measured on B200
-// (2^16 compression instances) 5.9 TB/s static vs 7.2 TB/s dynamic.  A warp computes the (cheap) trace of the
-// item's instance and expands only the item's slots; part 0 also writes status / public outputs / the check result.
-#define SCHED_LANES 8             // sub-counters per launch: same-address atomics serialise in one L2 slice (~2.4 ns each)
-#define SCHED_STRIDE 16           // u64 between sub-counters (128 B: one L2 line each)
-struct sched_args {
-  unsigned long long *counter;     // SCHED_LANES sub-counters, zeroed before the launch; sub-counter c hands out the
-                                   // items {v * SCHED_LANES + c}
-  unsigned int parts;              // items per instance
-  unsigned int part_len;           // slots per item, a multiple of 32
-};
-
-// Software pipeline over work items: while item k is traced and expanded, the input row of item k+1 is already on its
-// way from HBM and the counter grab for item k+2 is in flight, so neither latency sits between two expansions.
-template <int N_IN>
-struct item_pipe {
-  const sched_args &sc;
-  const uint32_t *__restrict__ in;
-  uint64_t n, total;
-  int lane;
-  uint32_t sub, tries;                    // current sub-counter, exhausted sub-counters seen so far
-  unsigned long long cur, nxt, grabbed;   // item ids: being processed / input row loading / grab in flight (lane 0)
-  uint32_t cur_in, nxt_in;                // this lane's word of the input rows
-
-  __device__ __forceinline__ unsigned long long grab() {
-    return lane == 0 ? atomicAdd(sc.counter + sub * SCHED_STRIDE, 1ull) * SCHED_LANES + sub : 0ull;
-  }
-  // the grabbed id, or -- when its sub-counter has run dry -- an id from the next sub-counter that still has work
-  // (a dry result that was grabbed before the last switch says nothing about the current sub-counter)
-  __device__ __forceinline__ unsigned long long resolve(unsigned long long g) {
-    unsigned long long id = __shfl_sync(0xffffffffu, g, 0);
-    while (id >= total && tries < SCHED_LANES) {
-      if (id % SCHED_LANES == sub) {
-        tries++;
-        sub = (sub + 1) % SCHED_LANES;
-      }
-      id = __shfl_sync(0xffffffffu, grab(), 0);
-    }
-    return id;
-  }
-  __device__ __forceinline__ uint32_t load_row(unsigned long long item) {
-    return (item < total && lane < N_IN) ? __ldg(in + (item / sc.parts) * N_IN + lane) : 0u;
-  }
-  __device__ __forceinline__ item_pipe(const sched_args &sc_, const uint32_t *in_, uint64_t n_, int lane_, uint64_t gwarp)
-      : sc(sc_), in(in_), n(n_), total(n_ * sc_.parts), lane(lane_), sub((uint32_t)(gwarp % SCHED_LANES)), tries(0) {
-    cur = resolve(grab());
-    nxt = resolve(grab());
-    cur_in = load_row(cur);
-    nxt_in = load_row(nxt);
-    grabbed = grab();
-  }
-  __device__ __forceinline__ bool valid() const { return cur < total; }
-  __device__ __forceinline__ uint64_t inst() const { return cur / sc.parts; }
-  __device__ __forceinline__ uint32_t part() const { return (uint32_t)(cur % sc.parts); }
-  // call once the current item's input word has been consumed: shifts the pipeline and refills its far end
-  __device__ __forceinline__ void advance() {
-    cur = nxt;
-    cur_in = nxt_in;
-    nxt = resolve(grabbed);
-    nxt_in = load_row(nxt);
-    grabbed = grab();
-  }
-};
-
-// The *_checked variants add CHECK_WARPS "checker" warps to every CTA.  The 8 expansion warps run exactly the loop of the
-// plain kernel (so the store stream keeps the shape that reaches the write roofline); the checker warps take whole
-// instances from a second set of counters, recompute the trace and evaluate the R1CS rows on it, filling issue slots the
-// store-bound expansion leaves idle.  A warp whose own queue has run dry helps with the other queue (phase 1), so the
-// launch has no tail of one kind of work.  With the check inside the expansion warps (4 items per witness, every
-// resident CTA) the fused kernels ran at 6.3 (compression) / 4.95 TB/s (nova); see profiles/.
-#ifdef B3W_EXP_NOCHECK              /* experiment builds only: checker warps trace but do not evaluate rows */
-#define B3W_EXP_CHECK(x) B3W_NO_ROW
-#else
-#define B3W_EXP_CHECK(x) (x)
-#endif
-#ifndef CHECK_WARPS
-#define CHECK_WARPS 4
-#endif
-
-// k_blake3_comp_witness: compression circuit, one warp per work item (see above).
-template <bool CHECK>
-__global__ void __launch_bounds__((WARPS_PER_CTA + (CHECK ? CHECK_WARPS : 0)) * 32, CHECK ? 2 : 4)
-k_blake3_comp_witness(const uint32_t *__restrict__ in, uint64_t n, const uint32_t *__restrict__ desc, uint32_t ws,
-                      uint8_t *__restrict__ out, uint8_t *__restrict__ status, uint32_t *__restrict__ pub,
-                      const check_args ck, const sched_args sc, const sched_args sck) {
-  constexpr int WARPS = WARPS_PER_CTA + (CHECK ? CHECK_WARPS : 0);
-  __shared__ __align__(16) uint32_t s_trace[WARPS][TRACE_STRIDE];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  uint32_t *trace = s_trace[wib];
-  if (lane == 0) { trace[TR_ZERO] = 0u; trace[TR_ONE] = 1u; }
-  const lane_sched ls = load_lane_sched(lane);
-  const bool checker = CHECK && wib >= WARPS_PER_CTA;
-  const bool fault = CHECK && ck.fault_word != B3W_NO_ROW;
-#pragma unroll 1
-  for (int phase = 0; phase < (CHECK ? 2 : 1); phase++) {
-    if (CHECK && checker == (phase == 0)) {
-      // ---- check items: one instance each ----
-      for (item_pipe<28> pipe(sck, in, n, lane, (uint64_t)blockIdx.x * WARPS + wib); pipe.valid();) {
-        const uint64_t i = pipe.inst();
-        __syncwarp();
-        if (lane < 28) trace[TR_IN + lane] = pipe.cur_in;
-        pipe.advance();
-        __syncwarp();
-        compression_trace(trace, lane, ls);
-        __syncwarp();
-        if (fault && lane == 0) trace[ck.fault_word] ^= ck.fault_mask;
-        __syncwarp();
-        const uint32_t bad = B3W_EXP_CHECK(r1cs_check_instance(TraceSrc{trace, ck.F}, ck.T, lane));
-        if (ck.first_bad && lane == 0) ck.first_bad[i] = bad;
-        if (status && lane == 0) status[i] = bad != B3W_NO_ROW ? B3W_R1CS_VIOLATION : 0;
-      }
-    } else {
-      // ---- expansion items: 1/parts of one witness each ----
-      for (item_pipe<28> pipe(sc, in, n, lane, (uint64_t)blockIdx.x * WARPS + wib); pipe.valid();) {
-        const uint64_t i = pipe.inst();
-        const uint32_t part = pipe.part();
-        const uint32_t a = part * sc.part_len, b = a + sc.part_len < ws ? a + sc.part_len : ws;
-        __syncwarp();                               // the previous expansion has finished reading the trace
-        if (lane < 28) trace[TR_IN + lane] = pipe.cur_in;
-        pipe.advance();
-        __syncwarp();
-        compression_trace(trace, lane, ls);
-        __syncwarp();
-        if (part == 0) {                            // this warp owns the instance's head
-          if (pub && lane < 16) pub[i * 16 + lane] = trace[TR_OUT + lane];
-          // u32 inputs can never violate a constraint of this circuit (which the fused check confirms row by row)
-          if (!CHECK && status && lane == 0) status[i] = 0;
-        }
-        if (fault) {                                // keep the injected fault visible in the witness
-          if (lane == 0) trace[ck.fault_word] ^= ck.fault_mask;
-          __syncwarp();
-        }
-        expand_slots<false>(trace, desc, a, b, out + i * (uint64_t)ws * 32, lane, nullptr, nullptr, 0);
-      }
-    }
-  }
-}
-
-// The 15 outputs z_{i+1} of a nova step, one per lane < 15: n_blocks_out, block_count_out, h_out[8], total_depth_out,
-// depth_out, chunk_idx_low/high_out, leaf_depth_out (circuits/blake3_nova.circom:195-202).
-__device__ __forceinline__ uint32_t nova_public_output(const uint32_t *trace, int lane) {
-  if (lane == 0) return trace[NV_IN + 0];
-  if (lane == 1) return trace[NV_BC_OUT];
-  if (lane < 10) return trace[TR_OUT + lane - 2];
-  if (lane == 10) return trace[NV_IN + 13];
-  if (lane == 11) return trace[NV_DEPTH_OUT];
-  if (lane == 12) return trace[NV_IN + 10];
-  if (lane == 13) return trace[NV_IN + 11];
-  return trace[NV_IN + 12];
-}
-
-// k_blake3_nova_witness: the nova step circuit (all three committed builds share it; they differ in the
-// slot table and the prime).  pub = z_{i+1} = the 15 outputs (low 32 bits each).
-template <bool CHECK>
-__global__ void __launch_bounds__((WARPS_PER_CTA + (CHECK ? CHECK_WARPS : 0)) * 32, CHECK ? 2 : 3)
-k_blake3_nova_witness(const uint32_t *__restrict__ in, uint64_t n, const uint32_t *__restrict__ desc, uint32_t ws,
-                      const field_consts *__restrict__ F, const uint2 *__restrict__ fslots, uint32_t n_fslots,
-                      uint8_t *__restrict__ out, uint8_t *__restrict__ status, uint32_t *__restrict__ pub,
-                      const check_args ck, const sched_args sc, const sched_args sck) {
-  constexpr int WARPS = WARPS_PER_CTA + (CHECK ? CHECK_WARPS : 0);
-  extern __shared__ __align__(16) uint32_t s_dyn[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  uint32_t *trace = s_dyn + wib * NOVA_TRACE_STRIDE;
-  if (lane == 0) { trace[TR_ZERO] = 0u; trace[TR_ONE] = 1u; }
-  const lane_sched ls = load_lane_sched(lane);
-  const bool checker = CHECK && wib >= WARPS_PER_CTA;
-  const bool fault = CHECK && ck.fault_word != B3W_NO_ROW;
-#pragma unroll 1
-  for (int phase = 0; phase < (CHECK ? 2 : 1); phase++) {
-    if (CHECK && checker == (phase == 0)) {
-      for (item_pipe<32> pipe(sck, in, n, lane, (uint64_t)blockIdx.x * WARPS + wib); pipe.valid();) {
-        const uint64_t i = pipe.inst();
-        __syncwarp();
-        trace[NV_IN + lane] = pipe.cur_in;
-        pipe.advance();
-        __syncwarp();
-        if (!nova_trace(trace, lane)) {           // the reference throws "Assert Failed.": no witness exists
-          if (status && lane == 0) status[i] = B3W_CIRCOM_ASSERT;
-          if (ck.first_bad && lane == 0) ck.first_bad[i] = B3W_NO_ROW;
-          continue;
-        }
-        __syncwarp();
-        compression_trace(trace, lane, ls);
-        __syncwarp();
-        if (fault && lane == 0) trace[ck.fault_word] ^= ck.fault_mask;
-        __syncwarp();
-        const uint32_t bad = B3W_EXP_CHECK(r1cs_check_instance(TraceSrc{trace, ck.F}, ck.T, lane));
-        if (ck.first_bad && lane == 0) ck.first_bad[i] = bad;
-        if (status && lane == 0) status[i] = bad != B3W_NO_ROW ? B3W_R1CS_VIOLATION : 0;
-      }
-    } else {
-      for (item_pipe<32> pipe(sc, in, n, lane, (uint64_t)blockIdx.x * WARPS + wib); pipe.valid();) {
-        const uint64_t i = pipe.inst();
-        const uint32_t part = pipe.part();
-        const uint32_t a = part * sc.part_len, b = a + sc.part_len < ws ? a + sc.part_len : ws;
-        const bool head = part == 0;
-        __syncwarp();
-        trace[NV_IN + lane] = pipe.cur_in;
-        pipe.advance();
-        __syncwarp();
-        if (!nova_trace(trace, lane)) {
-          if (head) {
-            if (!CHECK && status && lane == 0) status[i] = B3W_CIRCOM_ASSERT;
-            if (pub && lane < 15) pub[i * 15 + lane] = 0u;
-          }
-          continue;
-        }
-        __syncwarp();
-        compression_trace(trace, lane, ls);
-        __syncwarp();
-        if (head) {
-          if (!CHECK && status && lane == 0) status[i] = 0;
-          if (pub && lane < 15) pub[i * 15 + lane] = nova_public_output(trace, lane);
-        }
-        if (fault) {
-          if (lane == 0) trace[ck.fault_word] ^= ck.fault_mask;
-          __syncwarp();
-        }
-        expand_slots<true>(trace, desc, a, b, out + i * (uint64_t)ws * 32, lane, F, fslots, n_fslots);
-      }
-    }
-  }
-}
-
-// ---- compact ("packed") witnesses: SURVEY.md 8(f) rank 3 --------------------------------------------------------
-// Every slot of a witness is a pure function of the instance's trace (<= 1 324 u32) and the static slot table, so the
-// trace IS the witness in compact form: 3 776 B (compression) / 5 296 B (nova) instead of 770 976 / 745 312 B, ~200x less
-// to keep in HBM, move over PCIe or hand to a prover on the same GPU.  k_witness_packed writes traces, k_unpack expands
-// traces that are resident in device memory into the .wtns body layout (the expansion phase of the main kernels).
-template <bool NOVA>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-k_witness_packed(const uint32_t *__restrict__ in, uint64_t n, uint32_t stride_words, uint32_t *__restrict__ packed,
-                 uint8_t *__restrict__ status, uint32_t *__restrict__ pub) {
-  extern __shared__ __align__(16) uint32_t s_dyn[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  uint32_t *trace = s_dyn + wib * (NOVA ? NOVA_TRACE_STRIDE : TRACE_STRIDE);
-  const lane_sched ls = load_lane_sched(lane);
-  const uint64_t warp = (uint64_t)blockIdx.x * WARPS_PER_CTA + wib, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
-  constexpr int N_IN = NOVA ? 32 : 28, N_PUB = NOVA ? 15 : 16;
-  for (uint64_t i = warp; i < n; i += nwarps) {
-    __syncwarp();
-    for (uint32_t w = lane; w < stride_words; w += 32) trace[w] = 0u;     // words no template writes stay 0
-    __syncwarp();
-    if (lane == 0) trace[TR_ONE] = 1u;
-    if (lane < N_IN) trace[(NOVA ? NV_IN : TR_IN) + lane] = __ldg(in + i * N_IN + lane);
-    __syncwarp();
-    bool ok = true;
-    if (NOVA) ok = nova_trace(trace, lane);
-    __syncwarp();
-    if (ok) compression_trace(trace, lane, ls);
-    __syncwarp();
-    if (!ok && lane == 0) trace[TR_ONE] = 0u;                             // marks "no witness exists" (Assert Failed.)
-    if (status && lane == 0) status[i] = ok ? 0 : B3W_CIRCOM_ASSERT;
-    if (pub && lane < N_PUB) pub[i * N_PUB + lane] = !ok ? 0u : NOVA ? nova_public_output(trace, lane) : trace[TR_OUT + lane];
-    __syncwarp();
-    uint4 *dst = reinterpret_cast<uint4 *>(packed + i * stride_words);
-    const uint4 *src = reinterpret_cast<const uint4 *>(trace);
-    for (uint32_t q = lane; q < stride_words / 4; q += 32) dst[q] = src[q];
-  }
-}
-
-template <bool HAS_FIELD>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-k_unpack(const uint32_t *__restrict__ packed, uint64_t n, uint32_t stride_words, const uint32_t *__restrict__ desc, uint32_t ws,
-         const field_consts *__restrict__ F, const uint2 *__restrict__ fslots, uint32_t n_fslots, uint8_t *__restrict__ out,
-         uint32_t parts, uint32_t part_len) {
-  extern __shared__ __align__(16) uint32_t s_dyn[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  uint32_t *trace = s_dyn + wib * (HAS_FIELD ? NOVA_TRACE_STRIDE : TRACE_STRIDE);
-  const uint64_t warp = (uint64_t)blockIdx.x * WARPS_PER_CTA + wib, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
-  const uint64_t total = n * parts;
-  for (uint64_t item = warp; item < total; item += nwarps) {
-    const uint64_t i = item / parts;
-    const uint32_t part = (uint32_t)(item % parts);
-    const uint32_t a = part * part_len, b = a + part_len < ws ? a + part_len : ws;
-    __syncwarp();
-    const uint4 *src = reinterpret_cast<const uint4 *>(packed + i * stride_words);
-    uint4 *dst = reinterpret_cast<uint4 *>(trace);
-    for (uint32_t q = lane; q < stride_words / 4; q += 32) dst[q] = __ldg(src + q);
-    __syncwarp();
-    expand_slots<HAS_FIELD>(trace, desc, a, b, out + i * (uint64_t)ws * 32, lane, F, fslots, n_fslots);
-  }
-}
-
-// k_r1cs_check_witness: stand-alone check of witnesses resident in HBM (one warp per instance).
-__global__ void __launch_bounds__(256)
-k_r1cs_check_witness(const uint8_t *__restrict__ wit, uint64_t n, uint32_t ws, const r1cs_tables_dev T,
-                     const field_consts *__restrict__ F, uint8_t *__restrict__ status, uint32_t *__restrict__ first_bad) {
-  const int lane = threadIdx.x & 31;
-  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-  for (uint64_t i = warp; i < n; i += nwarps) {
-    SlotSrc src{reinterpret_cast<const uint32_t *>(wit + i * (uint64_t)ws * 32), F};
-    const uint32_t bad = r1cs_check_instance(src, T, lane);
-    if (lane == 0) {
-      if (status) status[i] = bad == B3W_NO_ROW ? 0 : B3W_R1CS_VIOLATION;
-      if (first_bad) first_bad[i] = bad;
-    }
-  }
-}
-
-// ---- checksum of resident witnesses (verification helper; reads HBM) ----
-__device__ __forceinline__ uint64_t mix64(uint64_t x) { return (x + 1) * 0x9E3779B97F4A7C15ull; }
-__global__ void __launch_bounds__(256) k_checksum(const uint64_t *__restrict__ wit, uint64_t n, uint32_t ws,
-                                                  uint64_t *__restrict__ sums) {
-  const int lane = threadIdx.x & 31;
-  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-  for (uint64_t i = warp; i < n; i += nwarps) {
-    const uint64_t *w = wit + i * (uint64_t)ws * 4;
-    uint64_t acc = 0;
-    for (uint32_t e = lane; e < ws * 4; e += 32) acc += (w[e] + 1) * mix64(e);
-#pragma unroll
-    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) sums[i] = acc;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Chained-chunk driver (BASELINE config 3): the step schedule of the reference's Nova driver
-// (rust_fold/src/main.rs:71-94,130-142,166-171 and rust_fold/src/blake3_circuit.rs:160-290), batched.
-// Step i+1 consumes step i's outputs (h, block_count, depth), but those are plain BLAKE3 chaining values, so the
-// whole chain of every chunk is pre-computed with native u32 compressions and all step witnesses are then
-// generated independently by k_blake3_nova_witness.  The sibling chaining values that the reference gets from
-// bao slice extraction (rust_fold/src/blake3_hash.rs:17-93) come from a BLAKE3 tree hashed on the device.
-// ------------------------------------------------------------------------------------------------
-#define B3_CHUNK_START 1u
-#define B3_CHUNK_END 2u
-#define B3_PARENT 4u
-#define B3_ROOT 8u
-
-__device__ __forceinline__ void b3_g(uint32_t *v, int a, int b, int c, int d, uint32_t x, uint32_t y) {
-  v[a] = v[a] + v[b] + x; v[d] = rotr32(v[d] ^ v[a], 16);
-  v[c] = v[c] + v[d];     v[b] = rotr32(v[b] ^ v[c], 12);
-  v[a] = v[a] + v[b] + y; v[d] = rotr32(v[d] ^ v[a], 8);
-  v[c] = v[c] + v[d];     v[b] = rotr32(v[b] ^ v[c], 7);
-}
-// plain BLAKE3 compression, first 8 output words (the chaining value)
-__device__ void b3_compress_cv(const uint32_t h[8], const uint32_t m[16], uint32_t t0, uint32_t t1, uint32_t blen,
-                               uint32_t flags, uint32_t out[8]) {
-  uint32_t v[16] = {h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7],
-                    0x6A09E667u, 0xBB67AE85u, 0x3C6EF372u, 0xA54FF53Au, t0, t1, blen, flags};
-#pragma unroll 1
-  for (int r = 0; r < 7; r++) {
-    const uint8_t *s = MSG_SCHED[r];
-    b3_g(v, 0, 4, 8, 12, m[s[0]], m[s[1]]);   b3_g(v, 1, 5, 9, 13, m[s[2]], m[s[3]]);
-    b3_g(v, 2, 6, 10, 14, m[s[4]], m[s[5]]);  b3_g(v, 3, 7, 11, 15, m[s[6]], m[s[7]]);
-    b3_g(v, 0, 5, 10, 15, m[s[8]], m[s[9]]);  b3_g(v, 1, 6, 11, 12, m[s[10]], m[s[11]]);
-    b3_g(v, 2, 7, 8, 13, m[s[12]], m[s[13]]); b3_g(v, 3, 4, 9, 14, m[s[14]], m[s[15]]);
-  }
-#pragma unroll
-  for (int i = 0; i < 8; i++) out[i] = v[i] ^ v[i + 8];
-}
-__constant__ uint32_t B3_IV[8] = {0x6A09E667u, 0xBB67AE85u, 0x3C6EF372u, 0xA54FF53Au, 0x510E527Fu, 0x9B05688Cu, 0x1F83D9ABu, 0x5BE0CD19u};
-
-// bytes [off, off+64) of the (zero padded) input as 16 little-endian words + the count of real bytes
-__device__ __forceinline__ uint32_t load_block(const uint8_t *data, uint64_t len, uint64_t off, uint32_t m[16]) {
-  const uint32_t *w = reinterpret_cast<const uint32_t *>(data + off);     // the device copy is padded to 64 B
-#pragma unroll
-  for (int i = 0; i < 16; i++) m[i] = w[i];
-  return off >= len ? 0u : (uint32_t)(len - off < 64 ? len - off : 64);
-}
-__device__ __forceinline__ uint32_t chunk_blocks(uint64_t len, uint64_t c) {
-  const uint64_t cb = len - c * 1024 < 1024 ? len - c * 1024 : 1024;   // bytes in chunk c
-  const uint32_t nb = (uint32_t)((cb + 63) / 64);                          // utils.rs:112-114
-  return nb ? nb : 1;                                                      // the empty input is one empty block
-}
-
-// chunk chaining values: cv[c] for c < n_chunks (one thread per chunk)
-__global__ void k_chunk_cvs(const uint8_t *__restrict__ data, uint64_t len, uint64_t n_chunks, uint32_t *__restrict__ cv) {
-  const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_chunks) return;
-  uint32_t h[8], m[16];
-#pragma unroll
-  for (int i = 0; i < 8; i++) h[i] = B3_IV[i];
-  const uint32_t nb = chunk_blocks(len, c);
-  for (uint32_t k = 0; k < nb; k++) {
-    const uint32_t bl = load_block(data, len, c * 1024 + 64ull * k, m);
-    b3_compress_cv(h, m, (uint32_t)c, (uint32_t)(c >> 32), bl, (k == 0 ? B3_CHUNK_START : 0u) | (k == nb - 1 ? B3_CHUNK_END : 0u), h);
-  }
-#pragma unroll
-  for (int i = 0; i < 8; i++) cv[c * 8 + i] = h[i];
-}
-// one tree level: parent j = compress(IV, cv[left] || cv[right], PARENT)
-__global__ void k_parent_cvs(const uint32_t *__restrict__ nodes /* [first..first+count) x {left, right} */, uint32_t first,
-                             uint32_t count, uint64_t n_chunks, uint32_t *__restrict__ cv) {
-  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= count) return;
-  const uint32_t l = nodes[2 * (first + j)], r = nodes[2 * (first + j) + 1];
-  uint32_t m[16], h[8], o[8];
-#pragma unroll
-  for (int i = 0; i < 8; i++) { m[i] = cv[(uint64_t)l * 8 + i]; m[8 + i] = cv[(uint64_t)r * 8 + i]; h[i] = B3_IV[i]; }
-  b3_compress_cv(h, m, 0, 0, 64, B3_PARENT, o);
-#pragma unroll
-  for (int i = 0; i < 8; i++) cv[(n_chunks + first + j) * 8 + i] = o[i];
-}
-// Step rows of every chunk (one thread per chunk): blake3_circuit.rs format_input() (:197-289) applied along
-// update_for_step() (:185-195), with z0 from main.rs:130-142 and z_{i+1} = the circuit's outputs.
-__global__ void k_chain_rows(const uint8_t *__restrict__ data, uint64_t len, uint64_t chunk_lo, uint64_t chunk_hi,
-                             const uint32_t *__restrict__ cv, const uint32_t *__restrict__ path /* [chunk][max_depth] sibling refs */,
-                             const uint32_t *__restrict__ depth_of /* parents above chunk c */, uint32_t max_depth,
-                             const uint64_t *__restrict__ step_off, uint32_t *__restrict__ rows /* of chunks [lo, hi) */,
-                             uint32_t *__restrict__ root /* h_out of chunk 0's last step */) {
-  const uint64_t c = chunk_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= chunk_hi) return;
-  const uint32_t n_par = depth_of[c];                 // parent_path.len()
-  const uint32_t total_depth = n_par + 1;             // = leaf_depth (blake3_circuit.rs:169, main.rs:71)
-  const uint32_t nb = chunk_blocks(len, c);
-  uint32_t h[8], m[16];
-#pragma unroll
-  for (int i = 0; i < 8; i++) h[i] = B3_IV[i];
-  uint32_t block_count = 0, depth = total_depth - 1;
-  uint32_t *row = rows + (step_off[c] - step_off[chunk_lo]) * 32;
-  const uint32_t steps = nb + total_depth - 1;        // main.rs:94
-  for (uint32_t st = 0; st < steps; st++, row += 32) {
-    const bool leaf = st < nb;
-    uint32_t bl;
-    if (leaf) {
-      bl = load_block(data, len, c * 1024 + 64ull * st, m);                 // :207-224
-    } else {
-      const uint32_t sib = path[c * max_depth + depth];                    // parent_path[current_depth] (:234)
-#pragma unroll
-      for (int i = 0; i < 8; i++) { m[i] = cv[(uint64_t)sib * 8 + i]; m[8 + i] = 0; }
-      bl = 64;                                                             // :229
-    }
-    row[0] = nb; row[1] = block_count;
-#pragma unroll
-    for (int i = 0; i < 8; i++) row[2 + i] = h[i];
-    row[10] = (uint32_t)c; row[11] = (uint32_t)(c >> 32);
-    row[12] = total_depth; row[13] = total_depth; row[14] = depth;
-#pragma unroll
-    for (int i = 0; i < 16; i++) row[15 + i] = m[i];
-    row[31] = bl;
-    // what the circuit will output (circuits/blake3_nova.circom:122-167, 229-266), natively
-    const bool is_parent = depth + 1 < total_depth, is_root = depth == 0;
-    const bool last = block_count + 1 == nb;
-    uint32_t mm[16], hh[8];
-    uint32_t flags;
-    if (is_parent) {
-      const bool left = ((c >> (total_depth - 2 - depth)) & 1) == 0;       // Blake3GetDownLeftPath (:47-84)
-#pragma unroll
-      for (int i = 0; i < 8; i++) { mm[i] = left ? h[i] : m[i]; mm[8 + i] = left ? m[i] : h[i]; hh[i] = B3_IV[i]; }
-      flags = B3_PARENT | (is_root ? B3_ROOT : 0u);
-      b3_compress_cv(hh, mm, 0, 0, bl, flags, h);
-    } else {
-      flags = (block_count == 0 ? B3_CHUNK_START : 0u) | (last ? B3_CHUNK_END : 0u) | (last && is_root ? B3_ROOT : 0u);
-      b3_compress_cv(h, m, (uint32_t)c, (uint32_t)(c >> 32), bl, flags, h);
-      block_count += 1;
-    }
-    if ((is_parent || last) && !is_root) depth -= 1;
-  }
-  if (c == 0) {
-#pragma unroll
-    for (int i = 0; i < 8; i++) root[i] = h[i];
-  }
-}
-
-// ---- pure-store calibration ----
-__global__ void __launch_bounds__(256) k_fill(uint8_t *buf, uint64_t nslots) {
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nslots; s += stride)
-    st_slot(buf + s * 32, (uint32_t)s & 1u, 0u, 0u, 0u, 0u, 0u, 0u, 0u);
-}
-
-// The same store stream as the witness kernels without any of their work: warps take 32 KiB items from the dynamic
-// counters and write them with 1 KiB warp stores.  What this reaches is the ceiling of the store path for this access
-// pattern; the witness kernel is judged against it (and against the driver's copy benchmark).
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_fill_items(uint8_t *buf, uint64_t n_items, uint32_t item_slots, const sched_args sc) {
-  const int lane = threadIdx.x & 31;
-  uint32_t sub = (uint32_t)((blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5)) % SCHED_LANES), tries = 0;
-  while (tries < SCHED_LANES) {
-    unsigned long long id = lane == 0 ? atomicAdd(sc.counter + sub * SCHED_STRIDE, 1ull) * SCHED_LANES + sub : 0ull;
-    id = __shfl_sync(0xffffffffu, id, 0);
-    if (id >= n_items) { tries++; sub = (sub + 1) % SCHED_LANES; continue; }
-    uint8_t *dst = buf + id * (uint64_t)item_slots * 32;
-#pragma unroll 4
-    for (uint32_t sl = lane; sl < item_slots; sl += 32) st_slot(dst + (size_t)sl * 32, sl & 1u, 0u, 0u, 0u, 0u, 0u, 0u, 0u);
-  }
-}
+#include "kernels_witness.cuh"
+#include "kernels_chain.cuh"
+#include "kernels_aux.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // host side
