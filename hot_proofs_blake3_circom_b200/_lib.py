@@ -13,7 +13,7 @@ B3W_FLAG_FUSED_CHECK = 1
 
 EXPORTS = ("b3w_version", "b3w_last_error", "b3w_create", "b3w_destroy", "b3w_circuit_info", "b3w_wtns_header",
            "b3w_input_signal", "b3w_witness_one", "b3w_witness_batch", "b3w_witness_batch_device",
-           "b3w_checksum_device", "b3w_calib_fill", "b3w_calib_fill_items", "b3w_host_alloc", "b3w_host_free",
+           "b3w_checksum_device", "b3w_calib_fill", "b3w_calib_fill_items", "b3w_calib_fill_bulk", "b3w_host_alloc", "b3w_host_free",
            "b3w_witness_batch_device_checked", "b3w_r1cs_check_device", "b3w_r1cs_info", "b3w_debug_inject_fault",
            "b3w_nova_chain_size", "b3w_nova_chain", "b3w_debug_set_launch", "b3w_assert_trace",
            "b3w_inputs_from_fr", "b3w_witness_batch_fr", "b3w_packed_words", "b3w_witness_batch_packed_device", "b3w_witness_batch_packed", "b3w_unpack_device",
@@ -72,6 +72,7 @@ def lib():
     L.b3w_nova_chain.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp, vp]
     L.b3w_calib_fill.argtypes = [vp, vp, u64, vp]
     L.b3w_calib_fill_items.argtypes = [vp, vp, u64, vp]
+    L.b3w_calib_fill_bulk.argtypes = [vp, vp, u64, vp]
     L.b3w_inputs_from_fr.argtypes = [C.c_uint32, vp, u64, vp]
     L.b3w_witness_batch_fr.argtypes = [vp, vp, u64, vp, vp, vp]
     L.b3w_packed_words.argtypes = [C.c_uint32, u32p]

@@ -622,6 +622,28 @@ extern "C" int b3w_calib_fill_items(b3w_ctx *c, uint8_t *d_buf, uint64_t bytes, 
   return B3W_OK;
 }
 
+extern "C" int b3w_calib_fill_bulk(b3w_ctx *c, uint8_t *d_buf, uint64_t bytes, void *stream) {
+  if (!c || !d_buf) return fail(B3W_ERR_INVALID, "b3w_calib_fill_bulk: null argument");
+  if (((uintptr_t)d_buf & 127) != 0) return fail(B3W_ERR_INVALID, "d_buf must be 128-byte aligned");
+  CK(cudaSetDevice(c->device));
+  const uint32_t item_bytes = (c->sched_parts >= 32 ? c->sched_parts / 32 * 32 : 1024) * 32;     // tuning hook as in b3w_calib_fill_items
+  const uint64_t n_items = bytes / item_bytes;
+  if (n_items == 0) return B3W_OK;
+  sched_args sc;
+  if (!c->d_counters) CK(cudaMalloc(&c->d_counters, (size_t)N_SCHED_COUNTERS * SCHED_SET_U64 * sizeof(unsigned long long)));
+  const uint32_t set0 = c->next_counter % N_SCHED_COUNTERS;
+  c->next_counter += 2;
+  sc.counter = c->d_counters + (size_t)set0 * SCHED_SET_U64;
+  sc.parts = 1;
+  sc.part_len = item_bytes / 32;
+  CK(cudaMemsetAsync(sc.counter, 0, SCHED_SET_U64 * sizeof(unsigned long long), (cudaStream_t)stream));
+  CK(cudaFuncSetAttribute(k_fill_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)item_bytes));
+  const int per_sm = c->ctas_limit > 0 ? c->ctas_limit : 2;
+  k_fill_bulk<<<c->sm_count * per_sm, 128, item_bytes, (cudaStream_t)stream>>>(d_buf, n_items, item_bytes, sc);
+  CK(cudaGetLastError());
+  return B3W_OK;
+}
+
 extern "C" int b3w_calib_fill(b3w_ctx *c, uint8_t *d_buf, uint64_t bytes, void *stream) {
   if (!c || !d_buf) return fail(B3W_ERR_INVALID, "b3w_calib_fill: null argument");
   CK(cudaSetDevice(c->device));

@@ -118,3 +118,26 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_fill_items(uint8_t *buf,
   }
 }
 
+
+// The same item stream written by the TMA engine instead of the LSU: one elected thread per CTA issues bulk copies
+// (cp.async.bulk.global.shared::cta, SASS UBLKCP) of a constant shared-memory tile.  Measures what staging expanded
+// witness tiles in shared memory + bulk stores could reach at best ("considered and not built").
+__global__ void __launch_bounds__(128) k_fill_bulk(uint8_t *buf, uint64_t n_items, uint32_t item_bytes, const sched_args sc) {
+  extern __shared__ __align__(128) uint8_t s_tile[];
+  for (uint32_t i = threadIdx.x * 16; i < item_bytes; i += blockDim.x * 16)
+    *reinterpret_cast<uint4 *>(s_tile + i) = make_uint4((i >> 5) & 1u, 0u, 0u, 0u);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  const uint32_t src = (uint32_t)__cvta_generic_to_shared(s_tile);
+  uint32_t sub = blockIdx.x % SCHED_LANES, tries = 0;
+  while (tries < SCHED_LANES) {
+    const unsigned long long id = atomicAdd(sc.counter + sub * SCHED_STRIDE, 1ull) * SCHED_LANES + sub;
+    if (id >= n_items) { tries++; sub = (sub + 1) % SCHED_LANES; continue; }
+    uint8_t *dst = buf + id * (uint64_t)item_bytes;
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(item_bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 8;" ::: "memory");      // the tile is constant: only bound the queue depth
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}

@@ -333,7 +333,7 @@ class WitnessCalculator:
 
     def calib_fill(self, d_buf, nbytes, stream=0, items=False):
         """pure-store calibration; items=True uses the witness kernels' own store stream (32 KiB dynamic work items)"""
-        f = self._L.b3w_calib_fill_items if items else self._L.b3w_calib_fill
+        f = self._L.b3w_calib_fill_bulk if items == "bulk" else self._L.b3w_calib_fill_items if items else self._L.b3w_calib_fill
         _lib.check(f(self._h, d_buf, nbytes, stream or None))
 
 

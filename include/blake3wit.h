@@ -150,6 +150,9 @@ int b3w_calib_fill(b3w_ctx *ctx, uint8_t *d_buf, uint64_t bytes, void *stream);
 /* ditto with the store stream of the witness kernels (32 KiB work items from the dynamic counters, 1 KiB per warp store,
  * same grid): the ceiling of the store path for that access pattern, with none of the kernels' work in the way. */
 int b3w_calib_fill_items(b3w_ctx *ctx, uint8_t *d_buf, uint64_t bytes, void *stream);
+/* ditto through the TMA engine: bulk copies (cp.async.bulk shared -> global) of a constant shared-memory tile, one per
+ * item; what "stage tiles in shared memory + bulk stores" could reach at best. */
+int b3w_calib_fill_bulk(b3w_ctx *ctx, uint8_t *d_buf, uint64_t bytes, void *stream);
 
 /* Chained-chunk driver (BASELINE config 3): all Nova step witnesses of a file, the batched form of the reference's
  * rust_fold loop (main.rs:71-94,166-171 around blake3_circuit.rs:160-290: update_for_step / format_input / synthesize).
