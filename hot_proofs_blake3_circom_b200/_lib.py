@@ -16,7 +16,7 @@ EXPORTS = ("b3w_version", "b3w_last_error", "b3w_create", "b3w_destroy", "b3w_ci
            "b3w_checksum_device", "b3w_calib_fill", "b3w_calib_fill_items", "b3w_calib_fill_bulk", "b3w_host_alloc", "b3w_host_free",
            "b3w_witness_batch_device_checked", "b3w_r1cs_check_device", "b3w_r1cs_info", "b3w_debug_inject_fault",
            "b3w_nova_chain_size", "b3w_nova_chain", "b3w_debug_set_launch", "b3w_assert_trace",
-           "b3w_inputs_from_fr", "b3w_witness_batch_fr", "b3w_packed_words", "b3w_witness_batch_packed_device", "b3w_witness_batch_packed", "b3w_unpack_device",
+           "b3w_r1cs_load", "b3w_r1cs_load_file", "b3w_inputs_from_fr", "b3w_witness_batch_fr", "b3w_packed_words", "b3w_witness_batch_packed_device", "b3w_witness_batch_packed", "b3w_unpack_device",
            "b3w_multi_create", "b3w_multi_destroy", "b3w_multi_size", "b3w_shard_range", "b3w_multi_witness_batch", "b3w_multi_nova_chain")
 
 
@@ -73,6 +73,8 @@ def lib():
     L.b3w_calib_fill.argtypes = [vp, vp, u64, vp]
     L.b3w_calib_fill_items.argtypes = [vp, vp, u64, vp]
     L.b3w_calib_fill_bulk.argtypes = [vp, vp, u64, vp]
+    L.b3w_r1cs_load.argtypes = [vp, vp, C.c_size_t, u32p]
+    L.b3w_r1cs_load_file.argtypes = [vp, C.c_char_p, u32p]
     L.b3w_inputs_from_fr.argtypes = [C.c_uint32, vp, u64, vp]
     L.b3w_witness_batch_fr.argtypes = [vp, vp, u64, vp, vp, vp]
     L.b3w_packed_words.argtypes = [C.c_uint32, u32p]

@@ -51,6 +51,8 @@ static int fail(int code, const char *fmt, ...) {
 #include "kernels_witness.cuh"
 #include "kernels_chain.cuh"
 #include "kernels_aux.cuh"
+#include "kernels_r1cs_staged.cuh"
+#include "r1cs_load.h"
 
 // ------------------------------------------------------------------------------------------------
 // host side
@@ -114,7 +116,8 @@ struct b3w_ctx {
   uint32_t flags;
   // R1CS tables (built on first use)
   bool r1cs_ready;
-  struct r1cs_dev { r1cs_class_dev *cls; int64_t *lo, *hi; uint32_t *terms; uint32_t ncls; } r_fused, r_slots;
+  struct r1cs_dev { r1cs_class_dev *cls; int64_t *lo, *hi; uint32_t *terms; uint32_t ncls; fr_t *coef_fr; uint32_t *row_ids, *nblk; uint32_t rows; } r_fused, r_slots;
+  bool r1cs_loaded;          // r_slots comes from b3w_r1cs_load, not from the built-in tables
   uint32_t fault_word, fault_mask;
   int ctas_limit;           // tuning hook: cap on resident CTAs per SM (0 = occupancy limit)
   uint32_t sched_parts;     // work items per instance (0 = default)
@@ -214,6 +217,16 @@ extern "C" int b3w_create(const b3w_config *cfg, b3w_ctx **out) {
 }
 
 static void free_packed_ring(b3w_ctx *c);
+static void free_r1cs_dev(b3w_ctx::r1cs_dev *r) {
+  if (r->cls) cudaFree(r->cls);
+  if (r->lo) cudaFree(r->lo);
+  if (r->hi) cudaFree(r->hi);
+  if (r->terms) cudaFree(r->terms);
+  if (r->coef_fr) cudaFree(r->coef_fr);
+  if (r->row_ids) cudaFree(r->row_ids);
+  if (r->nblk) cudaFree(r->nblk);
+  memset(r, 0, sizeof *r);
+}
 static void free_ring(b3w_ctx *c) {
   for (int k = 0; k < 2; k++) {
     if (c->d_ring[k]) cudaFree(c->d_ring[k]);
@@ -239,12 +252,7 @@ extern "C" void b3w_destroy(b3w_ctx *c) {
   if (c->d_field) cudaFree(c->d_field);
   if (c->d_fslots) cudaFree(c->d_fslots);
   if (c->d_counters) cudaFree(c->d_counters);
-  for (b3w_ctx::r1cs_dev *r : {&c->r_slots, &c->r_fused}) {
-    if (r->cls) cudaFree(r->cls);
-    if (r->lo) cudaFree(r->lo);
-    if (r->hi) cudaFree(r->hi);
-    if (r->terms) cudaFree(r->terms);
-  }
+  for (b3w_ctx::r1cs_dev *r : {&c->r_slots, &c->r_fused}) free_r1cs_dev(r);
   free(c->h_desc);
   delete c;
 }
@@ -332,7 +340,7 @@ extern "C" int b3w_assert_trace(uint32_t circuit, const uint32_t *in, char *buf,
 }
 
 // Expand the class / coefficient / column tables of one R1CS row set (r1cs_tables.h) and upload them.
-static int upload_r1cs_set(b3w_ctx *c, const circuit_def::r1cs_set &set, b3w_ctx::r1cs_dev *out) {
+static int upload_r1cs_set(b3w_ctx *c, const circuit_def::r1cs_set &set, b3w_ctx::r1cs_dev *out, bool as_blocks = false) {
   const size_t ncls = set.ncls;
   if (ncls == 0) return B3W_OK;
   r1cs_class_dev *cls = (r1cs_class_dev *)calloc(ncls, sizeof *cls);
@@ -362,14 +370,26 @@ static int upload_r1cs_set(b3w_ctx *c, const circuit_def::r1cs_set &set, b3w_ctx
     row_off += s.count;
   }
   if (corrupt || term_off != set.terms || row_off != set.rows) return done(fail(B3W_ERR_INVALID, "R1CS tables of %s are corrupt", c->def->name));
+  // slot-space sets are evaluated block-wise by the staged checker: replace the term matrices by row blocks
+  std::vector<uint32_t> tvec(td, td + set.terms), nblk;
+  if (as_blocks) {
+    std::vector<r1cs_class_dev> cv(cls, cls + ncls);
+    std::vector<uint32_t> blocks;
+    stg_blockify(cv, std::vector<uint32_t>(td, td + set.terms), blocks, nblk, std::vector<int64_t>(lo, lo + set.ncoef),
+                 std::vector<int64_t>(hi, hi + set.ncoef));
+    memcpy(cls, cv.data(), ncls * sizeof *cls);
+    tvec.swap(blocks);
+  }
   cudaError_t e = cudaMalloc(&out->cls, ncls * sizeof *cls);
   if (e == cudaSuccess) e = cudaMalloc(&out->lo, set.ncoef * 8);
   if (e == cudaSuccess) e = cudaMalloc(&out->hi, set.ncoef * 8);
-  if (e == cudaSuccess) e = cudaMalloc(&out->terms, (size_t)set.terms * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&out->terms, tvec.size() * 4 + 16);
+  if (e == cudaSuccess && as_blocks) e = cudaMalloc(&out->nblk, nblk.size() * 4);
   if (e == cudaSuccess) e = cudaMemcpy(out->cls, cls, ncls * sizeof *cls, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(out->lo, lo, set.ncoef * 8, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(out->hi, hi, set.ncoef * 8, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(out->terms, td, (size_t)set.terms * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(out->terms, tvec.data(), tvec.size() * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && as_blocks) e = cudaMemcpy(out->nblk, nblk.data(), nblk.size() * 4, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) rc = fail(B3W_ERR_CUDA, "R1CS table upload: %s", cudaGetErrorString(e));
   out->ncls = (uint32_t)ncls;
   return done(rc);
@@ -378,7 +398,7 @@ static int upload_r1cs_set(b3w_ctx *c, const circuit_def::r1cs_set &set, b3w_ctx
 static int ensure_r1cs(b3w_ctx *c) {
   if (c->r1cs_ready) return B3W_OK;
   int rc = upload_r1cs_set(c, c->def->r_fused, &c->r_fused);
-  if (rc == B3W_OK) rc = upload_r1cs_set(c, c->def->r_slots, &c->r_slots);
+  if (rc == B3W_OK && !c->r1cs_loaded) rc = upload_r1cs_set(c, c->def->r_slots, &c->r_slots);
   if (rc == B3W_OK) c->r1cs_ready = true;
   return rc;
 }
@@ -464,15 +484,81 @@ extern "C" int b3w_r1cs_check_device(b3w_ctx *c, const uint8_t *d_wit, uint64_t 
   int rc = ensure_r1cs(c);
   if (rc) return rc;
   if (c->r_slots.ncls == 0)
-    return fail(B3W_ERR_UNSUPPORTED, "%s: circom's O2 pass removed signals that the template-level rows refer to; use the "
-                "fused check (b3w_witness_batch_device_checked) for this build", c->def->name);
+    return fail(B3W_ERR_UNSUPPORTED, "%s: circom's O2 pass removed signals that the built-in template-level rows refer to; load the "
+                "O2-form system with b3w_r1cs_load (tools/export_r1cs.py writes it) or use the fused check", c->def->name);
   if (n == 0) return B3W_OK;
-  r1cs_tables_dev T{c->r_slots.cls, c->r_slots.lo, c->r_slots.hi, c->r_slots.terms, c->r_slots.ncls};
-  uint64_t ctas = (n + 7) / 8, cap = (uint64_t)c->sm_count * 8;
-  k_r1cs_check_witness<<<(unsigned)(ctas < cap ? ctas : cap), 256, 0, (cudaStream_t)stream>>>(d_wit, n, c->def->ws, T, c->d_field,
-                                                                                            d_status, d_first_bad);
+  r1cs_tables_dev T{c->r_slots.cls, c->r_slots.lo, c->r_slots.hi, c->r_slots.terms, c->r_slots.ncls, c->r_slots.coef_fr, c->r_slots.row_ids, c->r_slots.nblk};
+  if (!c->r1cs_loaded) {
+    // built-in rows (value kinds known offline: exact 64/128-bit integer classes + IsZero rows in Fr): one warp per instance
+    uint64_t ctas = (n + 7) / 8, cap8 = (uint64_t)c->sm_count * 8;
+    k_r1cs_check_witness<<<(unsigned)(ctas < cap8 ? ctas : cap8), 256, 0, (cudaStream_t)stream>>>(d_wit, n, c->def->ws, T, c->d_field,
+                                                                                                d_status, d_first_bad);
+    CK(cudaGetLastError());
+    return B3W_OK;
+  }
+  // a loaded system: the general evaluator (one CTA per instance, witness staged in shared memory, Fr fallback)
+  const size_t smem = (size_t)((c->def->ws + 1) & ~1u) * 8 + (size_t)STG_MAX_BIG * 32;
+  CK(cudaFuncSetAttribute(k_r1cs_check_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const uint64_t cap = (uint64_t)c->sm_count;
+  k_r1cs_check_staged<<<(unsigned)(n < cap ? n : cap), STG_THREADS, smem, (cudaStream_t)stream>>>(d_wit, n, c->def->ws, T, c->d_field,
+                                                                                                 d_status, d_first_bad);
   CK(cudaGetLastError());
   return B3W_OK;
+}
+
+// Replace the built-in slot-space row set of this context by the constraint system of an iden3 `.r1cs` file: the
+// reference's own build/*.r1cs where the user has them, or the equivalents written by tools/export_r1cs.py.
+extern "C" int b3w_r1cs_load(b3w_ctx *c, const uint8_t *data, size_t len, uint32_t *n_rows) {
+  if (!c || !data) return fail(B3W_ERR_INVALID, "b3w_r1cs_load: null argument");
+  CK(cudaSetDevice(c->device));
+  r1cs_host_set h;
+  std::string err;
+  int rc = r1cs_parse(data, len, c->def->prime, c->def->ws, h, err);
+  if (rc) return fail(rc, "b3w_r1cs_load: %s", err.c_str());
+  if (h.cls.size() > STG_MAX_CLASSES)
+    return fail(B3W_ERR_UNSUPPORTED, "b3w_r1cs_load: %zu shape classes (the checker holds %d)", h.cls.size(), STG_MAX_CLASSES);
+  std::vector<uint32_t> blocks, nblk;
+  stg_blockify(h.cls, h.terms, blocks, nblk, h.lo, h.hi);
+  h.terms.swap(blocks);
+  b3w_ctx::r1cs_dev d;
+  memset(&d, 0, sizeof d);
+  cudaError_t e = cudaMalloc(&d.cls, h.cls.size() * sizeof(r1cs_class_dev) + 16);
+  if (e == cudaSuccess) e = cudaMalloc(&d.nblk, nblk.size() * 4 + 16);
+  if (e == cudaSuccess && !nblk.empty()) e = cudaMemcpy(d.nblk, nblk.data(), nblk.size() * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&d.lo, h.lo.size() * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&d.hi, h.hi.size() * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&d.terms, h.terms.size() * 4 + 16);
+  if (e == cudaSuccess) e = cudaMalloc(&d.coef_fr, h.coef_fr.size() * sizeof(fr_t));
+  if (e == cudaSuccess) e = cudaMalloc(&d.row_ids, h.row_ids.size() * 4 + 16);
+  if (e == cudaSuccess && !h.cls.empty()) e = cudaMemcpy(d.cls, h.cls.data(), h.cls.size() * sizeof(r1cs_class_dev), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d.lo, h.lo.data(), h.lo.size() * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d.hi, h.hi.data(), h.hi.size() * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && !h.terms.empty()) e = cudaMemcpy(d.terms, h.terms.data(), h.terms.size() * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d.coef_fr, h.coef_fr.data(), h.coef_fr.size() * sizeof(fr_t), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && !h.row_ids.empty()) e = cudaMemcpy(d.row_ids, h.row_ids.data(), h.row_ids.size() * 4, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    free_r1cs_dev(&d);
+    return fail(B3W_ERR_CUDA, "b3w_r1cs_load: %s", cudaGetErrorString(e));
+  }
+  d.ncls = (uint32_t)h.cls.size();
+  d.rows = h.rows;
+  free_r1cs_dev(&c->r_slots);
+  c->r_slots = d;
+  c->r1cs_loaded = true;
+  if (n_rows) *n_rows = h.rows;
+  return B3W_OK;
+}
+
+extern "C" int b3w_r1cs_load_file(b3w_ctx *c, const char *path, uint32_t *n_rows) {
+  if (!c || !path) return fail(B3W_ERR_INVALID, "b3w_r1cs_load_file: null argument");
+  FILE *f = fopen(path, "rb");
+  if (!f) return fail(B3W_ERR_INVALID, "b3w_r1cs_load_file: cannot open %s", path);
+  std::vector<uint8_t> buf;
+  uint8_t tmp[1 << 16];
+  size_t k;
+  while ((k = fread(tmp, 1, sizeof tmp, f)) > 0) buf.insert(buf.end(), tmp, tmp + k);
+  fclose(f);
+  return b3w_r1cs_load(c, buf.data(), buf.size(), n_rows);
 }
 
 extern "C" int b3w_debug_inject_fault(b3w_ctx *c, uint32_t trace_word, uint32_t xor_mask) {

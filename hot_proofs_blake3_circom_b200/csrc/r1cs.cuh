@@ -6,7 +6,8 @@
 // by tools/gen_r1cs.py (r1cs_tables.h), grouped into shape classes: the 32 lanes of a warp evaluate 32 rows of
 // identical shape, term columns are term-major so that lane loads coalesce.
 //
-// Two value sources share the evaluator:
+// This file holds the FUSED check (value source TraceSrc); the stand-alone check of witnesses resident in HBM shares the
+// class tables and lives in kernels_r1cs_staged.cuh (value source StagedSrc: a compact shared-memory copy of the witness).
 //   TraceSrc  -- the fused check: a term is a slot DESCRIPTOR and its value is taken from the shared-memory trace
 //                that the expansion is about to read (nothing is re-read from HBM).  In trace space the rows that are
 //                identities for ANY trace content (booleanity of a bit extracted by shift-and-mask; w == sum 2^i
@@ -14,8 +15,6 @@
 //                triple are evaluated bit-sliced as ONE word comparison (class flag XORW), and a recomposition row
 //                whose only content in trace space is "these bits of that word are 0" (e.g. Bits34: the carry word
 //                of a 34-bit sum is < 4) is evaluated as ONE mask test (class flag ZMASK): the *_FUSED row sets;
-//   SlotSrc   -- the stand-alone check of witnesses resident in HBM: a term is a witness SLOT index and its value
-//                is the 32-byte field element found there.
 // Arithmetic: every row of these circuits except IsZero's `in*inv = 1 - out` is an identity between integers far
 // below p (bits, u32 words, <= 66-bit sums, small negatives), so it is evaluated exactly in signed 64-bit (NARROW
 // classes) or signed 128-bit (WIDE) integers; the 67 IsZero rows per nova witness go through Montgomery
@@ -43,8 +42,11 @@ struct r1cs_tables_dev {
   const r1cs_class_dev *cls;
   const int64_t *coef_lo;      // low 64 bits of each coefficient (two's complement)
   const int64_t *coef_hi;      // high 64 bits
-  const uint32_t *terms;       // descriptors (TraceSrc) or slot indices (SlotSrc), [class][term][row]
+  const uint32_t *terms;       // descriptors (TraceSrc) or slot indices (StagedSrc), [class][term][row]
   uint32_t n_classes;
+  const fr_t *coef_fr;         // loaded sets only: full field-element coefficients of the BIGCOEF classes (else NULL)
+  const uint32_t *row_ids;     // loaded sets only: constraint index in the .r1cs file of each class row (else NULL)
+  const uint32_t *cls_blocks;  // slot-space sets: `terms` holds row BLOCKS (kernels_r1cs_staged.cuh), this many per class
 };
 
 typedef __int128 i128;
@@ -85,6 +87,8 @@ __device__ __forceinline__ bool r1cs_xorw_row(const uint32_t *trace, const r1cs_
   return (X ^ __funnelshift_r(Y, Y, (dy >> 16) & 31u)) == __funnelshift_r(O, O, (dz >> 16) & 31u);
 }
 
+// SlotSrc -- the stand-alone check of witnesses resident in HBM against the BUILT-IN slot-space rows: a term is a
+// witness slot index and its value is the 32-byte field element found there (kernels_aux.cuh, k_r1cs_check_witness).
 struct SlotSrc {
   const uint32_t *wit;          // this instance's witness, 8 u32 per slot
   const field_consts *F;
@@ -111,6 +115,7 @@ struct SlotSrc {
   __device__ __forceinline__ bool xorw(const r1cs_class_dev &, const r1cs_tables_dev &, uint32_t) const { return false; }
   __device__ __forceinline__ bool zmask(const r1cs_class_dev &, const r1cs_tables_dev &, uint32_t) const { return false; }
 };
+
 __device__ __forceinline__ bool TraceSrc::xorw(const r1cs_class_dev &c, const r1cs_tables_dev &T, uint32_t r) const {
   return r1cs_xorw_row(trace, c, T, r);
 }

@@ -316,6 +316,16 @@ class WitnessCalculator:
         """stand-alone R1CS check of witnesses resident in device memory (O1 builds)"""
         _lib.check(self._L.b3w_r1cs_check_device(self._h, d_wit, n, d_status or None, d_first_bad or None, stream or None))
 
+    def r1cs_load(self, r1cs):
+        """use the constraint system of an iden3 .r1cs file (bytes or a path) for r1cs_check_device; returns its row count"""
+        n = C.c_uint32()
+        if isinstance(r1cs, (bytes, bytearray, memoryview, np.ndarray)):
+            buf = np.frombuffer(bytes(r1cs), np.uint8)
+            _lib.check(self._L.b3w_r1cs_load(self._h, buf.ctypes.data, buf.size, C.byref(n)))
+        else:
+            _lib.check(self._L.b3w_r1cs_load_file(self._h, str(r1cs).encode(), C.byref(n)))
+        return n.value
+
     def r1cs_info(self):
         rows, terms = C.c_uint32(), C.c_uint32()
         _lib.check(self._L.b3w_r1cs_info(self.circuit, C.byref(rows), C.byref(terms)))

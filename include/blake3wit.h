@@ -121,11 +121,24 @@ int b3w_witness_batch_device(b3w_ctx *ctx, const uint32_t *d_in, uint64_t n, uin
 int b3w_witness_batch_device_checked(b3w_ctx *ctx, const uint32_t *d_in, uint64_t n, uint8_t *d_out, uint8_t *d_status,
                                      uint32_t *d_pub, uint32_t *d_first_bad, void *stream);
 
-/* Stand-alone R1CS check of witnesses that are RESIDENT IN DEVICE MEMORY (re-reads them): sparse A.z * B.z - C.z over
- * Fr, one warp per instance.  Available for the O1 builds (blake3_compression, NOVA_BN_O1), whose witness still holds
- * every value the template-level rows mention; B3W_ERR_UNSUPPORTED for the O2 builds. */
+/* Stand-alone R1CS check of witnesses that are RESIDENT IN DEVICE MEMORY: sparse A.z * B.z - C.z over Fr, one CTA per
+ * instance (the witness is streamed from HBM once into a compact shared-memory copy, rows are evaluated from there).
+ * Built-in rows exist for the O1 builds (blake3_compression, NOVA_BN_O1), whose witness still holds every value the
+ * template-level rows mention; for the O2 builds load a system first (b3w_r1cs_load), else B3W_ERR_UNSUPPORTED.
+ * d_first_bad[i] = smallest violated row, B3W_NO_ROW, or 0xFFFFFFFE when a slot is not a canonical field element. */
 int b3w_r1cs_check_device(b3w_ctx *ctx, const uint8_t *d_wit, uint64_t n, uint8_t *d_status, uint32_t *d_first_bad,
                           void *stream);
+
+/* Load the constraint system that b3w_r1cs_check_device evaluates from an iden3 `.r1cs` file (binary format v1) instead
+ * of the built-in template-derived rows: the reference's own build/ *.r1cs where they exist (they are missing from the
+ * reference tree, .MISSING_LARGE_BLOBS; rust_fold loads them at blake3_circuit.rs:71-81), or the equivalent systems
+ * written by tools/export_r1cs.py -- which is how the two O2 builds get a stand-alone check.  The file's prime and wire
+ * count must match the context's circuit.  Rows with coefficients that are not small integers are evaluated in Fr
+ * (Montgomery), everything else in exact 128-bit integers with an Fr fallback, so ANY satisfied system is accepted and
+ * any violated row reported; d_first_bad then holds the constraint's index in the file.  n_rows (may be NULL)
+ * receives the number of constraints. */
+int b3w_r1cs_load(b3w_ctx *ctx, const uint8_t *r1cs, size_t len, uint32_t *n_rows);
+int b3w_r1cs_load_file(b3w_ctx *ctx, const char *path, uint32_t *n_rows);
 
 /* rows / non-zero terms of the circuit's template-level constraint system in O1 form
  * (blake3_compression: 24 544 rows = 23 376 quadratic + 1 168 linear; nova: 25 064) */

@@ -2,6 +2,9 @@
 The reference's own tests check constraints through circom_tester's expectPass (test/blake3_hash.test.ts:36,57);
 its .r1cs files are absent, so the rows are re-derived from the templates (tools/gen_r1cs.py): R1CS parity with the
 reference's files is NOT pinned, satisfaction is."""
+import os
+import sys
+
 import numpy as np
 import pytest
 import torch
@@ -11,6 +14,7 @@ from hot_proofs_blake3_circom_b200 import _lib
 from hot_proofs_blake3_circom_b200 import inputs as gen
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def run(wc, rows, checked=False):
@@ -118,4 +122,92 @@ def test_fused_check_flag_on_host_batches(built):
     wc.inject_fault(48 + 3, 1)
     res = wc.calculateWitnessBatch(rows, want_witness=False)
     assert (res["status"] == _lib.B3W_R1CS_VIOLATION).all()
+    wc.close()
+
+
+# ---- b3w_r1cs_load: constraint systems from iden3 .r1cs files ------------------------------------------------------
+@pytest.fixture(scope="module")
+def exported(tmp_path_factory):
+    """the .r1cs files tools/export_r1cs.py regenerates (the reference's own are missing from its tree)"""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import export_r1cs as ex
+    d = tmp_path_factory.mktemp("r1cs")
+    return {v: ex.export(v, str(d), trials=1, verbose=False)[0] for v in ("compression", "nova_pasta_o2", "nova_bn_o1")}
+
+
+@pytest.mark.parametrize("name,variant,rows_fn,n_rows", [("blake3_compression", "compression", gen.splitmix_compression_inputs, 24544),
+                                                        ("blake3_nova_pasta", "nova_pasta_o2", gen.splitmix_nova_inputs, 23743),
+                                                        ("blake3_nova_o1", "nova_bn_o1", gen.splitmix_nova_inputs, 25067)])
+def test_loaded_r1cs_accepts_valid_and_rejects_corruption(built, exported, name, variant, rows_fn, n_rows):
+    wc = pkg.builder(name, device=0)
+    assert wc.r1cs_load(exported[variant]) == n_rows               # from a path ...
+    assert wc.r1cs_load(open(exported[variant], "rb").read()) == n_rows   # ... and from bytes
+    n, ws = 256, wc.witnessSize
+    rows = rows_fn(n, first=11)
+    d_out, st, _ = run(wc, rows)
+    assert int(st.max()) == 0
+    status, bad = hbm_check(wc, d_out, n)
+    assert (status == 0).all() and (bad == _lib.B3W_NO_ROW).all()
+    w = d_out.view(n, ws, 32)
+    rng = np.random.default_rng(3)
+    slots = rng.integers(0, ws, n)
+    slots[:4] = [0, 1, ws - 1, 17]
+    idx = torch.arange(n, device="cuda")
+    sl = torch.from_numpy(slots).cuda()
+    w[idx, sl, 0] += 1
+    status, bad = hbm_check(wc, d_out, n)
+    assert (status == _lib.B3W_R1CS_VIOLATION).all(), "undetected corruption in slots %s" % slots[status == 0][:10]
+    assert (bad < n_rows).all()                                    # a constraint index of the file
+    # the reported row really is violated by that witness (host re-evaluation of the file's row)
+    import export_r1cs as ex
+    r = ex.read_r1cs(exported[variant])
+    for i in (0, 1, 2, 3, 100):
+        body = d_out.view(n, ws * 32)[i].cpu().numpy().tobytes()
+        wi = [int.from_bytes(body[32 * k:32 * k + 32], "little") for k in range(ws)]
+        assert ex.check_rows([r["rows"][int(bad[i])]], wi, r["prime"]) is not None
+    # a non-canonical slot (>= p) is reported as such
+    w[idx, sl, 0] -= 1
+    w[7, 5, :] = 0xFF
+    status, bad = hbm_check(wc, d_out, n)
+    assert status[7] == _lib.B3W_R1CS_VIOLATION and bad[7] == 0xFFFFFFFE and (np.delete(status, 7) == 0).all()
+    wc.close()
+
+
+def test_r1cs_load_rejects_foreign_files(built, exported):
+    wc = pkg.builder("blake3_nova", device=0)                         # BN254, 23 291 wires
+    for variant in ("compression", "nova_pasta_o2"):                  # wrong wire count / wrong prime
+        with pytest.raises(pkg.B3WError) as e:
+            wc.r1cs_load(exported[variant])
+        assert e.value.code == _lib.B3W_ERR_INVALID
+    with pytest.raises(pkg.B3WError):
+        wc.r1cs_load(b"r1cs\x01\x00\x00\x00")
+    wc.close()
+
+
+def test_loaded_r1cs_with_field_coefficients(built, exported):
+    """Rows scaled by a large field element (as circom's own O2 output contains, e.g. 2^-31 mod p) take the BIGCOEF
+    path: every coefficient of every 7th row is multiplied by a random field element, which keeps the solution set."""
+    import export_r1cs as ex
+    r = ex.read_r1cs(exported["compression"])
+    p = r["prime"]
+    rng = np.random.default_rng(5)
+    rows = []
+    for i, (A, B, C) in enumerate(r["rows"]):
+        if i % 7 == 0:
+            k = int.from_bytes(rng.bytes(31), "little") + 2 ** 200
+            scale = lambda D, m: {w: (c * m) % p for w, c in D.items()}
+            rows.append((scale(A, k), B, scale(C, k)) if A else (A, B, scale(C, k)))
+        else:
+            rows.append((A, B, C))
+    path = os.path.join(os.path.dirname(exported["compression"]), "scaled.r1cs")
+    ex.write_r1cs(path, rows, p, r["n_wires"], 16, 0, 28, [int(x) for x in r["wire2label"]], r["n_labels"])
+    wc = pkg.builder("blake3_compression", device=0)
+    assert wc.r1cs_load(path) == 24544
+    n = 64
+    d_out, st, _ = run(wc, gen.lcg_compression_inputs(n))
+    status, bad = hbm_check(wc, d_out, n)
+    assert (status == 0).all()
+    d_out.view(n, wc.witnessSize, 32)[:, 1700, 0] ^= 1
+    status, bad = hbm_check(wc, d_out, n)
+    assert (status == _lib.B3W_R1CS_VIOLATION).all()
     wc.close()

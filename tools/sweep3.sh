@@ -1,6 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for tool in memcheck racecheck synccheck; do
-  timeout 900 compute-sanitizer --tool $tool --print-limit 5 python tools/sanitize_run.py > gpurun_out/sanitizer_$tool.log 2>&1
-  echo "== $tool: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/sanitizer_$tool.log | tail -1) $(grep -c 'sanitize_run done' gpurun_out/sanitizer_$tool.log)"
-done
+python -m pytest tests/test_gpu_r1cs.py -x -q -m gpu 2>&1 | tail -25 | tee gpurun_out/pytest_gpu.log
+python tools/r1cs_quickbench.py 2>&1 | tee gpurun_out/r1cs_quickbench5.log
