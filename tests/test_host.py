@@ -108,3 +108,57 @@ def test_assert_trace_empty_for_compression(built):
     buf = C.create_string_buffer(64)
     row = np.full(28, 0xFFFFFFFF, np.uint32)
     assert pkg.lib().b3w_assert_trace(0, row.ctypes.data, buf, len(buf)) == 0 and buf.value == b""
+
+
+# ---- property tests (hypothesis) of the input normalisation: witness_calculator.js:319-323 `BigInt(n) % prime`, made
+# non-negative, in every value form a JS caller can pass; and of the C-side Fr256 conversion -------------------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+_u32 = st.integers(min_value=0, max_value=2 ** 32 - 1)
+_forms = st.sampled_from(["int", "str", "hex", "plus_p", "minus_p", "neg_wrap", "np"])
+
+
+def _encode(v, form):
+    if form == "int":
+        return v
+    if form == "str":
+        return str(v)
+    if form == "hex":
+        return hex(v)
+    if form == "plus_p":
+        return v + 3 * P
+    if form == "minus_p":
+        return str(v - 2 * P)            # negative: JS `%` keeps the sign, normalize() adds the prime back
+    if form == "neg_wrap":
+        return -(P - v) if v else 0
+    return np.uint32(v)
+
+
+@settings(max_examples=60, deadline=None)
+@given(vals=st.lists(_u32, min_size=28, max_size=28), forms=st.lists(_forms, min_size=28, max_size=28))
+def test_row_normalisation_property(wc, vals, forms):
+    enc = [_encode(v, f) for v, f in zip(vals, forms)]
+    inp = {"t": enc[24:26], "h": enc[0:8], "d": enc[27], "m": [enc[8:16], enc[16:24]], "b": enc[26]}   # any key order, nesting
+    assert list(wc._row(inp)) == vals
+
+
+@settings(max_examples=40, deadline=None)
+@given(vals=st.lists(_u32, min_size=32, max_size=32), ks=st.lists(st.integers(min_value=0, max_value=3), min_size=32, max_size=32))
+def test_inputs_from_fr_property(built, vals, ks):
+    # nova rows under the Pallas scalar field: value + k*p for the k that still fit 256 bits
+    PALLAS = 0x40000000000000000000000000000000224698fc0994a8dd8c46eb2100000001
+    fr = np.frombuffer(b"".join((v + k * PALLAS).to_bytes(32, "little") for v, k in zip(vals, ks)), np.uint8).copy()
+    rows = np.zeros(32, np.uint32)
+    assert pkg.lib().b3w_inputs_from_fr(2, fr.ctypes.data, 1, rows.ctypes.data) == 0
+    assert list(rows) == vals
+
+
+@settings(max_examples=30, deadline=None)
+@given(v=st.integers(min_value=2 ** 32, max_value=P - 1), pos=st.integers(min_value=0, max_value=27))
+def test_out_of_domain_values_are_always_refused(wc, v, pos):
+    row = [1] * 28
+    row[pos] = v
+    inp = {"h": row[0:8], "m": row[8:24], "t": row[24:26], "b": row[26], "d": row[27]}
+    with pytest.raises(pkg.B3WError) as e:
+        wc._row(inp)
+    assert e.value.code == _lib.B3W_ERR_DOMAIN
