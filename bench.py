@@ -244,10 +244,10 @@ def run_own(args, rank, world, local_rank):
     n_e2e = n
     while n_e2e * WIT_BYTES > budget and n_e2e > 1024:
         n_e2e //= 2
-    h_out = L.b3w_host_alloc(n_e2e * WIT_BYTES)
-    h_in = L.b3w_host_alloc(n_e2e * IN_BYTES)
-    h_st = L.b3w_host_alloc(n_e2e)
-    h_pub = L.b3w_host_alloc(n_e2e * 64)
+    h_out = L.b3w_host_alloc_near(n_e2e * WIT_BYTES, local_rank)       # pinned, on the GPU's own NUMA node
+    h_in = L.b3w_host_alloc_near(n_e2e * IN_BYTES, local_rank)
+    h_st = L.b3w_host_alloc_near(n_e2e, local_rank)
+    h_pub = L.b3w_host_alloc_near(n_e2e * 64, local_rank)
     if not (h_out and h_in and h_st and h_pub):
         raise SystemExit("bench.py: pinned host allocation failed: " + L.b3w_last_error().decode())
     import ctypes as C
@@ -275,7 +275,7 @@ def run_own(args, rank, world, local_rank):
     # ... and with the witnesses returned in COMPACT form (the per-instance trace, 3 776 B: every slot is a pure function
     # of it; b3w_unpack_device expands on demand)
     pk_words = wc.packedWords
-    h_pk = L.b3w_host_alloc(n_e2e * pk_words * 4)
+    h_pk = L.b3w_host_alloc_near(n_e2e * pk_words * 4, local_rank)
     if not h_pk:
         raise SystemExit("bench.py: pinned host allocation failed: " + L.b3w_last_error().decode())
 

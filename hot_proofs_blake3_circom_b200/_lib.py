@@ -13,7 +13,7 @@ B3W_FLAG_FUSED_CHECK = 1
 
 EXPORTS = ("b3w_version", "b3w_last_error", "b3w_create", "b3w_destroy", "b3w_circuit_info", "b3w_wtns_header",
            "b3w_input_signal", "b3w_witness_one", "b3w_witness_batch", "b3w_witness_batch_device",
-           "b3w_checksum_device", "b3w_calib_fill", "b3w_calib_fill_items", "b3w_calib_fill_bulk", "b3w_host_alloc", "b3w_host_free",
+           "b3w_checksum_device", "b3w_calib_fill", "b3w_calib_fill_items", "b3w_calib_fill_bulk", "b3w_host_alloc", "b3w_host_alloc_near", "b3w_host_free",
            "b3w_witness_batch_device_checked", "b3w_r1cs_check_device", "b3w_r1cs_info", "b3w_debug_inject_fault",
            "b3w_nova_chain_size", "b3w_nova_chain", "b3w_debug_set_launch", "b3w_assert_trace",
            "b3w_r1cs_load", "b3w_r1cs_load_file", "b3w_inputs_from_fr", "b3w_witness_batch_fr", "b3w_packed_words", "b3w_witness_batch_packed_device", "b3w_witness_batch_packed", "b3w_unpack_device",
@@ -91,6 +91,8 @@ def lib():
     L.b3w_multi_nova_chain.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp, vp]
     L.b3w_host_alloc.argtypes = [C.c_size_t]
     L.b3w_host_alloc.restype = vp
+    L.b3w_host_alloc_near.argtypes = [C.c_size_t, C.c_int]
+    L.b3w_host_alloc_near.restype = vp
     L.b3w_host_free.argtypes = [vp]
     L.b3w_host_free.restype = None
     _LIB = L

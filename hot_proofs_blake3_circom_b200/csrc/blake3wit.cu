@@ -22,6 +22,11 @@
 #include <string>
 #include <algorithm>
 #include <thread>
+#include <ctype.h>
+#ifdef __linux__
+#include <unistd.h>
+#include <sys/syscall.h>
+#endif
 
 #include "../../include/blake3wit.h"
 #include "trace_layout.h"
@@ -1139,6 +1144,47 @@ extern "C" int b3w_multi_nova_chain(b3w_multi *m, const uint8_t *data, uint64_t 
     if (rc[g]) return fail(rc[g], "device %d (chunks %llu..%llu): %s", m->ctx[g]->device, (unsigned long long)cut[g],
                            (unsigned long long)cut[g + 1], err[g].c_str());
   return B3W_OK;
+}
+
+// NUMA node of a CUDA device (from sysfs; -1 when unknown)
+static int device_numa_node(int device) {
+  char pci[32] = {0}, path[128];
+  if (cudaDeviceGetPCIBusId(pci, sizeof pci, device) != cudaSuccess) return -1;
+  for (char *p = pci; *p; p++) *p = (char)tolower(*p);
+  snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", pci);
+  FILE *f = fopen(path, "r");
+  if (!f) return -1;
+  int node = -1;
+  if (fscanf(f, "%d", &node) != 1) node = -1;
+  fclose(f);
+  return node;
+}
+
+// Pinned host memory on the NUMA node the device hangs off: with 8 GPUs on two sockets, D2H streams that cross the
+// socket interconnect cap the whole box (measured: 92 GB/s total at N = 8 against 174 GB/s at N = 4 with default placement).
+// The pages are faulted in inside cudaHostAlloc, so a preferred-node policy around the call is enough.
+extern "C" void *b3w_host_alloc_near(size_t bytes, int device) {
+  int dev = device;
+  if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) dev = -1;
+  const int node = dev >= 0 ? device_numa_node(dev) : -1;
+  bool policy_set = false;
+#ifdef __linux__
+  if (node >= 0 && node < 1024) {
+    unsigned long mask[16] = {0};
+    mask[node / (8 * sizeof(unsigned long))] = 1ul << (node % (8 * sizeof(unsigned long)));
+    policy_set = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, (unsigned long)(8 * sizeof mask)) == 0;
+  }
+#endif
+  void *p = nullptr;
+  cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
+#ifdef __linux__
+  if (policy_set) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0ul);
+#endif
+  if (e != cudaSuccess) {
+    fail(B3W_ERR_NOMEM, "cudaHostAlloc(%zu) failed", bytes);
+    return nullptr;
+  }
+  return p;
 }
 
 extern "C" void *b3w_host_alloc(size_t bytes) {

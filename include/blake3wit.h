@@ -216,6 +216,9 @@ int b3w_multi_nova_chain(b3w_multi *m, const uint8_t *data, uint64_t len, uint8_
 
 /* pinned host memory for batch buffers */
 void *b3w_host_alloc(size_t bytes);
+/* ditto, placed on the NUMA node the given CUDA device is attached to (-1 = current device): keeps the D2H stream of
+ * each GPU of a multi-socket box off the socket interconnect. */
+void *b3w_host_alloc_near(size_t bytes, int device);
 void b3w_host_free(void *p);
 
 #ifdef __cplusplus
