@@ -203,14 +203,14 @@ extern "C" int b3w_create(const b3w_config *cfg, b3w_ctx **out) {
     delete F;
     if (e1 != cudaSuccess) { b3w_destroy(c); return fail(B3W_ERR_CUDA, "field table upload: %s", cudaGetErrorString(e1)); }
   }
-  const int bs_plain = WARPS_PER_CTA * 32, bs_checked = (WARPS_PER_CTA + CHECK_WARPS) * 32;
+  const int bs_plain = WARPS_PER_CTA * 32, bs_checked = (WARPS_PER_CTA + (d->nova ? NOVA_CHECK_WARPS : CHECK_WARPS)) * 32;
   if (d->nova) {
-    e1 = cudaFuncSetAttribute(k_blake3_nova_witness<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NOVA_SMEM(WARPS_PER_CTA + CHECK_WARPS));
+    e1 = cudaFuncSetAttribute(k_blake3_nova_witness<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NOVA_SMEM(WARPS_PER_CTA + NOVA_CHECK_WARPS));
     if (e1 == cudaSuccess)
       e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, k_blake3_nova_witness<false>, bs_plain, NOVA_SMEM(WARPS_PER_CTA));
     if (e1 == cudaSuccess)
       e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm_checked, k_blake3_nova_witness<true>, bs_checked,
-                                                         NOVA_SMEM(WARPS_PER_CTA + CHECK_WARPS));
+                                                         NOVA_SMEM(WARPS_PER_CTA + NOVA_CHECK_WARPS));
   } else {
     e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, k_blake3_comp_witness<false>, bs_plain, 0);
     if (e1 == cudaSuccess)
@@ -433,7 +433,7 @@ static int launch_witness(b3w_ctx *c, const uint32_t *d_in, uint64_t n, uint8_t 
     ck.fault_word = c->fault_word;
     ck.fault_mask = c->fault_mask;
   }
-  const unsigned bs = (WARPS_PER_CTA + (check ? CHECK_WARPS : 0)) * 32;
+  const unsigned bs = (WARPS_PER_CTA + (check ? (c->def->nova ? NOVA_CHECK_WARPS : CHECK_WARPS) : 0)) * 32;
   // work distribution (see sched_args): expansion items, and -- checked kernels -- one check item per instance
   sched_args sc, sck;
   if (!c->d_counters) CK(cudaMalloc(&c->d_counters, (size_t)N_SCHED_COUNTERS * SCHED_SET_U64 * sizeof(unsigned long long)));
@@ -447,7 +447,7 @@ static int launch_witness(b3w_ctx *c, const uint32_t *d_in, uint64_t n, uint8_t 
   sck.part_len = 0;
   CK(cudaMemsetAsync(sc.counter, 0, 2 * SCHED_SET_U64 * sizeof(unsigned long long), s));
   if (c->def->nova) {
-    if (check) k_blake3_nova_witness<true><<<grid, bs, NOVA_SMEM(WARPS_PER_CTA + CHECK_WARPS), s>>>(d_in, n, c->d_desc, c->def->ws, c->d_field, c->d_fslots, c->n_fslots, d_out, d_status, d_pub, ck, sc, sck);
+    if (check) k_blake3_nova_witness<true><<<grid, bs, NOVA_SMEM(WARPS_PER_CTA + NOVA_CHECK_WARPS), s>>>(d_in, n, c->d_desc, c->def->ws, c->d_field, c->d_fslots, c->n_fslots, d_out, d_status, d_pub, ck, sc, sck);
     else k_blake3_nova_witness<false><<<grid, bs, NOVA_SMEM(WARPS_PER_CTA), s>>>(d_in, n, c->d_desc, c->def->ws, c->d_field, c->d_fslots, c->n_fslots, d_out, d_status, d_pub, ck, sc, sck);
   } else {
     if (check) k_blake3_comp_witness<true><<<grid, bs, 0, s>>>(d_in, n, c->d_desc, c->def->ws, d_out, d_status, d_pub, ck, sc, sck);

@@ -335,7 +335,10 @@ struct item_pipe {
 #define B3W_EXP_CHECK(x) (x)
 #endif
 #ifndef CHECK_WARPS
-#define CHECK_WARPS 4
+#define CHECK_WARPS 4          /* compression */
+#endif
+#ifndef NOVA_CHECK_WARPS
+#define NOVA_CHECK_WARPS 4     /* nova: more rows per instance (1 124 vs 688) */
 #endif
 
 // k_blake3_comp_witness: compression circuit, one warp per work item (see above).
@@ -413,12 +416,12 @@ __device__ __forceinline__ uint32_t nova_public_output(const uint32_t *trace, in
 // k_blake3_nova_witness: the nova step circuit (all three committed builds share it; they differ in the
 // slot table and the prime).  pub = z_{i+1} = the 15 outputs (low 32 bits each).
 template <bool CHECK>
-__global__ void __launch_bounds__((WARPS_PER_CTA + (CHECK ? CHECK_WARPS : 0)) * 32, CHECK ? 2 : 3)
+__global__ void __launch_bounds__((WARPS_PER_CTA + (CHECK ? NOVA_CHECK_WARPS : 0)) * 32, CHECK ? 2 : 3)
 k_blake3_nova_witness(const uint32_t *__restrict__ in, uint64_t n, const uint32_t *__restrict__ desc, uint32_t ws,
                       const field_consts *__restrict__ F, const uint2 *__restrict__ fslots, uint32_t n_fslots,
                       uint8_t *__restrict__ out, uint8_t *__restrict__ status, uint32_t *__restrict__ pub,
                       const check_args ck, const sched_args sc, const sched_args sck) {
-  constexpr int WARPS = WARPS_PER_CTA + (CHECK ? CHECK_WARPS : 0);
+  constexpr int WARPS = WARPS_PER_CTA + (CHECK ? NOVA_CHECK_WARPS : 0);
   extern __shared__ __align__(16) uint32_t s_dyn[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   uint32_t *trace = s_dyn + wib * NOVA_TRACE_STRIDE;
