@@ -58,6 +58,7 @@ static int fail(int code, const char *fmt, ...) {
 #include "kernels_aux.cuh"
 #include "kernels_r1cs_staged.cuh"
 #include "r1cs_load.h"
+#include "wide_domain.h"
 
 // ------------------------------------------------------------------------------------------------
 // host side
@@ -135,7 +136,9 @@ struct b3w_ctx {
   uint32_t *d_in[2];
   uint8_t *d_status[2];
   uint32_t *d_pub[2];
+  int8_t *d_ext[2];          // compression only: m_ext of the chunk (wide batches)
   bool ring_ready;
+  uint32_t m_slot0;          // compression only: witness slot of m[0] (the 16 m slots are consecutive)
   void *cs_ptr[8];           // chain driver scratch (grow-only)
   size_t cs_cap[8];
   // staging for host-buffer batches of PACKED witnesses: 2 slots
@@ -168,7 +171,8 @@ extern "C" int b3w_create(const b3w_config *cfg, b3w_ctx **out) {
   c->chunk = cfg->chunk ? cfg->chunk : 1024;
   c->flags = cfg->flags;
   c->fault_word = B3W_NO_ROW;
-  CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, dev));
+  cudaError_t e1 = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, dev);
+  if (e1 != cudaSuccess) { delete c; return fail(B3W_ERR_CUDA, "device attribute query: %s", cudaGetErrorString(e1)); }
   // expand the run-length table to one descriptor per slot and upload it
   const circuit_def *d = c->def;
   uint32_t *h = (uint32_t *)malloc((size_t)d->ws * 4);
@@ -177,10 +181,24 @@ extern "C" int b3w_create(const b3w_config *cfg, b3w_ctx **out) {
   for (size_t i = 0; i < d->n_segs; i++)
     for (uint32_t j = 0; j < d->segs[i].count; j++) h[pos++] = d->segs[i].desc0 + j * d->segs[i].delta;
   if (pos != d->ws) { free(h); delete c; return fail(B3W_ERR_INVALID, "slot table of %s is corrupt", d->name); }
-  cudaError_t e1 = cudaMalloc(&c->d_desc, (size_t)d->ws * 4);
+  e1 = cudaMalloc(&c->d_desc, (size_t)d->ws * 4);
   if (e1 == cudaSuccess) e1 = cudaMemcpy(c->d_desc, h, (size_t)d->ws * 4, cudaMemcpyHostToDevice);
   c->h_desc = h;
   if (e1 != cudaSuccess) { b3w_destroy(c); return fail(B3W_ERR_CUDA, "descriptor upload: %s", cudaGetErrorString(e1)); }
+  if (!d->nova) {
+    // the wide-domain kernels rewrite the witness slots of m[0..15]: exactly 16 consecutive W32 slots read TR_IN + 8 + j
+    uint32_t first = 0, found = 0;
+    for (uint32_t sl = 0; sl < d->ws; sl++) {
+      const uint32_t t = h[sl] & 0xFFFFu;
+      if ((h[sl] >> 24) == DK_W32 && t >= TR_IN + 8 && t < TR_IN + 24) {
+        if (found == 0) first = sl;
+        if (sl != first + found || t != TR_IN + 8 + found) { found = 99; break; }
+        found++;
+      }
+    }
+    if (found != 16) { b3w_destroy(c); return fail(B3W_ERR_INVALID, "slot table of %s: the m slots are not where the wide path expects them", d->name); }
+    c->m_slot0 = first;
+  }
   {
     std::vector<uint2> fs;
     for (uint32_t sl = 0; sl < d->ws; sl++)
@@ -212,9 +230,9 @@ extern "C" int b3w_create(const b3w_config *cfg, b3w_ctx **out) {
       e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm_checked, k_blake3_nova_witness<true>, bs_checked,
                                                          NOVA_SMEM(WARPS_PER_CTA + NOVA_CHECK_WARPS));
   } else {
-    e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, k_blake3_comp_witness<false>, bs_plain, 0);
+    e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, k_blake3_comp_witness<false, false>, bs_plain, 0);
     if (e1 == cudaSuccess)
-      e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm_checked, k_blake3_comp_witness<true>, bs_checked, 0);
+      e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm_checked, k_blake3_comp_witness<true, false>, bs_checked, 0);
   }
   if (e1 != cudaSuccess || c->ctas_per_sm < 1 || c->ctas_per_sm_checked < 1) { b3w_destroy(c); return fail(B3W_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e1)); }
   *out = c;
@@ -238,9 +256,10 @@ static void free_ring(b3w_ctx *c) {
     if (c->d_in[k]) cudaFree(c->d_in[k]);
     if (c->d_status[k]) cudaFree(c->d_status[k]);
     if (c->d_pub[k]) cudaFree(c->d_pub[k]);
+    if (c->d_ext[k]) cudaFree(c->d_ext[k]);
     if (c->st[k]) cudaStreamDestroy(c->st[k]);
     if (c->ev[k]) cudaEventDestroy(c->ev[k]);
-    c->d_ring[k] = nullptr; c->d_in[k] = nullptr; c->d_status[k] = nullptr; c->d_pub[k] = nullptr;
+    c->d_ring[k] = nullptr; c->d_in[k] = nullptr; c->d_status[k] = nullptr; c->d_pub[k] = nullptr; c->d_ext[k] = nullptr;
     c->st[k] = nullptr; c->ev[k] = nullptr;
   }
   c->ring_ready = false;
@@ -409,8 +428,10 @@ static int ensure_r1cs(b3w_ctx *c) {
 }
 
 static int launch_witness(b3w_ctx *c, const uint32_t *d_in, uint64_t n, uint8_t *d_out, uint8_t *d_status,
-                          uint32_t *d_pub, cudaStream_t s, bool check = false, uint32_t *d_first_bad = nullptr) {
+                          uint32_t *d_pub, cudaStream_t s, bool check = false, uint32_t *d_first_bad = nullptr,
+                          const int8_t *d_m_ext = nullptr) {
   if (n == 0) return B3W_OK;
+  if (d_m_ext && c->def->nova) return fail(B3W_ERR_UNSUPPORTED, "%s: only blake3_compression has a wide-domain kernel", c->def->name);
   // Persistent grid, work items handed out dynamically (see sched_args).  Defaults from sweeps on B200 (profiles/):
   // fastest with only 2 CTAs per SM (16 expansion warps) and 24 items per witness (32 KiB each: the GPU-wide write front
   // stays compact).  The checked kernels have the same expansion shape plus CHECK_WARPS checker warps per CTA.
@@ -450,8 +471,14 @@ static int launch_witness(b3w_ctx *c, const uint32_t *d_in, uint64_t n, uint8_t 
     if (check) k_blake3_nova_witness<true><<<grid, bs, NOVA_SMEM(WARPS_PER_CTA + NOVA_CHECK_WARPS), s>>>(d_in, n, c->d_desc, c->def->ws, c->d_field, c->d_fslots, c->n_fslots, d_out, d_status, d_pub, ck, sc, sck);
     else k_blake3_nova_witness<false><<<grid, bs, NOVA_SMEM(WARPS_PER_CTA), s>>>(d_in, n, c->d_desc, c->def->ws, c->d_field, c->d_fslots, c->n_fslots, d_out, d_status, d_pub, ck, sc, sck);
   } else {
-    if (check) k_blake3_comp_witness<true><<<grid, bs, 0, s>>>(d_in, n, c->d_desc, c->def->ws, d_out, d_status, d_pub, ck, sc, sck);
-    else k_blake3_comp_witness<false><<<grid, bs, 0, s>>>(d_in, n, c->d_desc, c->def->ws, d_out, d_status, d_pub, ck, sc, sck);
+    const wide_args wd{d_m_ext, c->d_field, c->m_slot0};
+    if (d_m_ext) {
+      if (check) k_blake3_comp_witness<true, true><<<grid, bs, 0, s>>>(d_in, n, c->d_desc, c->def->ws, d_out, d_status, d_pub, ck, sc, sck, wd);
+      else k_blake3_comp_witness<false, true><<<grid, bs, 0, s>>>(d_in, n, c->d_desc, c->def->ws, d_out, d_status, d_pub, ck, sc, sck, wd);
+    } else {
+      if (check) k_blake3_comp_witness<true, false><<<grid, bs, 0, s>>>(d_in, n, c->d_desc, c->def->ws, d_out, d_status, d_pub, ck, sc, sck, wd);
+      else k_blake3_comp_witness<false, false><<<grid, bs, 0, s>>>(d_in, n, c->d_desc, c->def->ws, d_out, d_status, d_pub, ck, sc, sck, wd);
+    }
   }
   CK(cudaGetLastError());
   return B3W_OK;
@@ -582,8 +609,7 @@ extern "C" int b3w_debug_set_launch(b3w_ctx *c, int ctas_per_sm, uint32_t parts)
   return B3W_OK;
 }
 
-static int ensure_ring(b3w_ctx *c) {
-  if (c->ring_ready) return B3W_OK;
+static int alloc_ring(b3w_ctx *c) {
   const circuit_def *d = c->def;
   for (int k = 0; k < 2; k++) {
     CK(cudaStreamCreateWithFlags(&c->st[k], cudaStreamNonBlocking));
@@ -592,27 +618,33 @@ static int ensure_ring(b3w_ctx *c) {
     CK(cudaMalloc(&c->d_in[k], (size_t)c->chunk * d->n_inputs * 4));
     CK(cudaMalloc(&c->d_status[k], (size_t)c->chunk));
     CK(cudaMalloc(&c->d_pub[k], (size_t)c->chunk * d->n_public * 4));
+    if (!d->nova) CK(cudaMalloc(&c->d_ext[k], (size_t)c->chunk * 16));
   }
+  return B3W_OK;
+}
+// the two ring slots exist completely or not at all (a half-built ring is released before the error is returned)
+static int ensure_ring(b3w_ctx *c) {
+  if (c->ring_ready) return B3W_OK;
+  const int rc = alloc_ring(c);
+  if (rc) { free_ring(c); return rc; }
   c->ring_ready = true;
   return B3W_OK;
 }
 
-extern "C" int b3w_witness_batch(b3w_ctx *c, const uint32_t *in, uint64_t n, uint8_t *out, uint8_t *status,
-                                 uint32_t *pub) {
-  if (!c || (!in && n)) return fail(B3W_ERR_INVALID, "b3w_witness_batch: null argument");
-  CK(cudaSetDevice(c->device));
-  int rc = ensure_ring(c);
-  if (rc) { free_ring(c); return rc; }
+// Host-buffer batches: chunks of c->chunk instances through the two ring slots; chunk j runs on stream j & 1 and its D2H
+// overlaps the next chunk's kernel.  m_ext != NULL selects the wide-domain kernel (compression only).
+static int batch_chunks(b3w_ctx *c, const uint32_t *in, const int8_t *m_ext, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub) {
   const circuit_def *d = c->def;
   const size_t wbytes = (size_t)d->ws * 32;
-  // two ring slots: chunk j runs on stream j&1; its D2H overlaps the next chunk's kernel
   uint64_t done = 0;
   int k = 0;
   while (done < n) {
     uint64_t m = n - done < c->chunk ? n - done : c->chunk;
     cudaStream_t s = c->st[k];
     CK(cudaMemcpyAsync(c->d_in[k], in + done * d->n_inputs, (size_t)m * d->n_inputs * 4, cudaMemcpyHostToDevice, s));
-    rc = launch_witness(c, c->d_in[k], m, c->d_ring[k], c->d_status[k], c->d_pub[k], s, (c->flags & B3W_FLAG_FUSED_CHECK) != 0);
+    if (m_ext) CK(cudaMemcpyAsync(c->d_ext[k], m_ext + done * 16, (size_t)m * 16, cudaMemcpyHostToDevice, s));
+    int rc = launch_witness(c, c->d_in[k], m, c->d_ring[k], c->d_status[k], c->d_pub[k], s, (c->flags & B3W_FLAG_FUSED_CHECK) != 0,
+                            nullptr, m_ext ? c->d_ext[k] : nullptr);
     if (rc) return rc;
     if (out) CK(cudaMemcpyAsync(out + done * wbytes, c->d_ring[k], (size_t)m * wbytes, cudaMemcpyDeviceToHost, s));
     if (status) CK(cudaMemcpyAsync(status + done, c->d_status[k], (size_t)m, cudaMemcpyDeviceToHost, s));
@@ -622,9 +654,25 @@ extern "C" int b3w_witness_batch(b3w_ctx *c, const uint32_t *in, uint64_t n, uin
     // before reusing slot k (two chunks ago) its stream must have drained
     if (done < n) CK(cudaStreamSynchronize(c->st[k]));
   }
-  CK(cudaStreamSynchronize(c->st[0]));
-  CK(cudaStreamSynchronize(c->st[1]));
   return B3W_OK;
+}
+static int batch_host(b3w_ctx *c, const uint32_t *in, const int8_t *m_ext, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub) {
+  CK(cudaSetDevice(c->device));
+  int rc = ensure_ring(c);
+  if (rc) return rc;
+  rc = batch_chunks(c, in, m_ext, n, out, status, pub);
+  // drain both slots on every path: after an error no copy into the caller's buffers may still be in flight
+  const cudaError_t e0 = cudaStreamSynchronize(c->st[0]), e1 = cudaStreamSynchronize(c->st[1]);
+  if (rc) return rc;
+  if (e0 != cudaSuccess || e1 != cudaSuccess)
+    return fail(B3W_ERR_CUDA, "b3w_witness_batch: %s", cudaGetErrorString(e0 != cudaSuccess ? e0 : e1));
+  return B3W_OK;
+}
+
+extern "C" int b3w_witness_batch(b3w_ctx *c, const uint32_t *in, uint64_t n, uint8_t *out, uint8_t *status,
+                                 uint32_t *pub) {
+  if (!c || (!in && n)) return fail(B3W_ERR_INVALID, "b3w_witness_batch: null argument");
+  return batch_host(c, in, nullptr, n, out, status, pub);
 }
 
 // Inputs as field elements (canonical or not): what `normalize` (witness_calculator.js:319-323) leaves is value mod p;
@@ -664,13 +712,87 @@ extern "C" int b3w_inputs_from_fr(uint32_t circuit, const uint8_t *in_fr, uint64
   return B3W_OK;
 }
 
+static fr_t prime_of(const circuit_def *d) {
+  fr_t p;
+  memcpy(p.l, d->prime, 32);
+  return p;
+}
+
+// The full input domain of blake3_compression (wide_domain.h): Fr256 inputs -> u32 rows + the signed high parts of the
+// message words.  Nothing is refused: an instance that cannot satisfy the circuit is marked (m_ext[i][0] = 127) and comes
+// back from the kernels with status 4, like the reference's "Assert Failed.".
+extern "C" int b3w_inputs_from_fr_wide(uint32_t circuit, const uint8_t *in_fr, uint64_t n, uint32_t *rows, int8_t *m_ext,
+                                       uint64_t *n_wide) {
+  const circuit_def *d = find_def(circuit);
+  if (!d) return B3W_ERR_UNSUPPORTED;
+  if (d->nova) return fail(B3W_ERR_UNSUPPORTED, "%s: only blake3_compression has the full-domain path (nova inputs must be u32)", d->name);
+  if ((!in_fr || !rows || !m_ext) && n) return fail(B3W_ERR_INVALID, "b3w_inputs_from_fr_wide: null argument");
+  const fr_t p = prime_of(d);
+  uint64_t wide = 0;
+  for (uint64_t i = 0; i < n; i++) {
+    fr_t v[28];
+    for (int k = 0; k < 28; k++) v[k] = wd_load_reduced(in_fr + (i * 28 + k) * 32, p);
+    if (wd_convert_compression(v, p, rows + i * 28, m_ext + i * 16)) wide++;
+  }
+  if (n_wide) *n_wide = wide;
+  return B3W_OK;
+}
+
+extern "C" int b3w_witness_batch_wide(b3w_ctx *c, const uint32_t *in, const int8_t *m_ext, uint64_t n, uint8_t *out, uint8_t *status,
+                                      uint32_t *pub) {
+  if (!c || ((!in || !m_ext) && n)) return fail(B3W_ERR_INVALID, "b3w_witness_batch_wide: null argument");
+  if (c->def->nova) return fail(B3W_ERR_UNSUPPORTED, "%s: only blake3_compression has a wide-domain kernel", c->def->name);
+  return batch_host(c, in, m_ext, n, out, status, pub);
+}
+
+extern "C" int b3w_witness_batch_device_wide(b3w_ctx *c, const uint32_t *d_in, const int8_t *d_m_ext, uint64_t n, uint8_t *d_out,
+                                             uint8_t *d_status, uint32_t *d_pub, uint32_t *d_first_bad, void *stream) {
+  if (!c || !d_in || !d_m_ext || !d_out) return fail(B3W_ERR_INVALID, "b3w_witness_batch_device_wide: null argument");
+  if (((uintptr_t)d_out & 31) != 0) return fail(B3W_ERR_INVALID, "d_out must be 32-byte aligned");
+  CK(cudaSetDevice(c->device));
+  return launch_witness(c, d_in, n, d_out, d_status, d_pub, (cudaStream_t)stream, (c->flags & B3W_FLAG_FUSED_CHECK) != 0 || d_first_bad != nullptr,
+                        d_first_bad, d_m_ext);
+}
+
 extern "C" int b3w_witness_batch_fr(b3w_ctx *c, const uint8_t *in_fr, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub) {
   if (!c || (!in_fr && n)) return fail(B3W_ERR_INVALID, "b3w_witness_batch_fr: null argument");
+  const uint32_t circuit = (uint32_t)(c->def - CIRCUITS);
   std::vector<uint32_t> rows;
-  try { rows.resize((size_t)n * c->def->n_inputs); } catch (...) { return fail(B3W_ERR_NOMEM, "out of host memory"); }
-  int rc = b3w_inputs_from_fr((uint32_t)(c->def - CIRCUITS), in_fr, n, rows.data());
+  std::vector<int8_t> ext;
+  try {
+    rows.resize((size_t)n * c->def->n_inputs);
+    if (!c->def->nova) ext.resize((size_t)n * 16);
+  } catch (...) { return fail(B3W_ERR_NOMEM, "out of host memory"); }
+  if (c->def->nova) {                                       // nova: the u32 domain only
+    int rc = b3w_inputs_from_fr(circuit, in_fr, n, rows.data());
+    if (rc) return rc;
+    return b3w_witness_batch(c, rows.data(), n, out, status, pub);
+  }
+  uint64_t n_wide = 0;
+  int rc = b3w_inputs_from_fr_wide(circuit, in_fr, n, rows.data(), ext.data(), &n_wide);
   if (rc) return rc;
-  return b3w_witness_batch(c, rows.data(), n, out, status, pub);
+  return batch_host(c, rows.data(), n_wide ? ext.data() : nullptr, n, out, status, pub);
+}
+
+// b3w_assert_trace for field-element inputs.  blake3_compression: any input (the range constraints are replayed in the
+// wasm's execution order, wide_domain.h); nova: inputs in the u32 domain.
+extern "C" int b3w_assert_trace_fr(uint32_t circuit, const uint8_t *in_fr, char *buf, size_t cap) {
+  const circuit_def *d = find_def(circuit);
+  if (!d) return B3W_ERR_UNSUPPORTED;
+  if (!in_fr || (!buf && cap)) return fail(B3W_ERR_INVALID, "b3w_assert_trace_fr: null argument");
+  if (cap) buf[0] = 0;
+  if (d->nova) {
+    uint32_t row[32];
+    int rc = b3w_inputs_from_fr(circuit, in_fr, 1, row);
+    return rc ? rc : b3w_assert_trace(circuit, row, buf, cap);
+  }
+  const fr_t p = prime_of(d);
+  fr_t v[28];
+  for (int k = 0; k < 28; k++) v[k] = wd_load_reduced(in_fr + k * 32, p);
+  const wd_fail f = wd_first_assert_compression(v, p);
+  if (f.kind == 0) return B3W_OK;
+  wd_assert_text_compression(f, buf, cap);
+  return B3W_CIRCOM_ASSERT;
 }
 
 extern "C" int b3w_witness_one(b3w_ctx *c, const uint32_t *in, uint8_t *out) {

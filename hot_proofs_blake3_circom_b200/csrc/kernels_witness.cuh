@@ -341,12 +341,62 @@ struct item_pipe {
 #define NOVA_CHECK_WARPS 4     /* nova: more rows per instance (1 124 vs 688) */
 #endif
 
+// ---- the FULL input domain of blake3_compression (WIDE kernel variants) -------------------------------------------
+// The circuit range-checks every input except the message words (circuits/blake3_compression.circom:169-170 TODO): m[j]
+// only ever enters a sum add1 = Bits34(v[a] + v[b] + m[j]), whose recomposition constraint holds whenever that sum, as a
+// canonical field element, is below 2^34 (circuits/blake3_common.circom:182-203) -- e.g. m[0] = 2^32 or m[0] = p - 1 give
+// valid witnesses in the reference.  A message word of a satisfying input is therefore a signed
+// integer m = ext * 2^32 + lo with ext in [-2, 3], and such an instance differs from the u32 instance with the same lo
+// words in exactly two places: the carry word of every half-G record that adds m[j] grows by ext[j] (and must stay in
+// [0, 3], else "Assert Failed."), and the witness slots of m itself hold m mod p.  So the wide variants run the ordinary
+// u32 trace and then apply that correction; the hot (u32-only) instantiations do not contain any of it.
+#define TR_EXT 944u               /* 16 sign-extended ext words; free in the compression kernels' 960-word trace stride */
+/* B3W_EXT_ASSERT (include/blake3wit.h) in m_ext[i][0]: the host already knows that instance i asserts; no carry survives + 127 */
+static_assert(TR_EXT >= B3W_TRACE_WORDS_COMPRESSION && TR_EXT + 16 <= TRACE_STRIDE, "ext words do not fit the compression trace stride");
+struct wide_args {
+  const int8_t *m_ext;            // n x 16, or NULL (then the kernel must be a non-WIDE instantiation)
+  const field_consts *F;
+  uint32_t m_slot0;               // witness slot of m[0]; m[j] is slot m_slot0 + j
+};
+
+// Adds ext to the carry words of the 112 half-G records (APPLY) or only looks at them; true = some sum left [0, 2^34).
+template <bool APPLY>
+__device__ __forceinline__ bool wide_carries(uint32_t *trace, int lane) {
+  bool bad = false;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int rec = lane + 32 * k;                 // record ((round * 8 + g) * 2 + half) adds msg[2g + half] of that round
+    if (rec < 112) {
+      const int e = (int)trace[TR_EXT + MSG_SCHED[rec >> 4][rec & 15]];
+      const int c = (int)trace[TR_HG + 8 * rec + 1] + e;
+      bad = bad || c < 0 || c > 3;
+      if (APPLY) trace[TR_HG + 8 * rec + 1] = (uint32_t)c;
+    }
+  }
+  return __any_sync(0xffffffffu, bad);
+}
+
+// The m slots of a wide instance inside [a, b): m mod p.  Each is rewritten by the lane that expand_slots used for it
+// (a is a multiple of 32), so the two stores to one address are ordered by program order.
+__device__ __forceinline__ void wide_patch_m(const uint32_t *trace, const wide_args &wd, uint32_t a, uint32_t b, uint8_t *dst, int lane) {
+  const uint32_t j = ((uint32_t)lane - wd.m_slot0) & 31u, s = wd.m_slot0 + j;
+  if (j < 16u && s >= a && s < b) {
+    const int e = (int)trace[TR_EXT + j];
+    const uint32_t lo = trace[TR_IN + 8 + j];
+    if (e > 0) st_slot(dst + (size_t)s * 32, lo, (uint32_t)e, 0u, 0u, 0u, 0u, 0u, 0u);
+    else if (e < 0) {
+      const fr_t v = fr_from_s64((int64_t)(((uint64_t)(uint32_t)e << 32) | lo), wd.F->p);
+      st_slot_fr(dst + (size_t)s * 32, v.l);
+    }
+  }
+}
+
 // k_blake3_comp_witness: compression circuit, one warp per work item (see above).
-template <bool CHECK>
+template <bool CHECK, bool WIDE>
 __global__ void __launch_bounds__((WARPS_PER_CTA + (CHECK ? CHECK_WARPS : 0)) * 32, CHECK ? 2 : 4)
 k_blake3_comp_witness(const uint32_t *__restrict__ in, uint64_t n, const uint32_t *__restrict__ desc, uint32_t ws,
                       uint8_t *__restrict__ out, uint8_t *__restrict__ status, uint32_t *__restrict__ pub,
-                      const check_args ck, const sched_args sc, const sched_args sck) {
+                      const check_args ck, const sched_args sc, const sched_args sck, const wide_args wd) {
   constexpr int WARPS = WARPS_PER_CTA + (CHECK ? CHECK_WARPS : 0);
   __shared__ __align__(16) uint32_t s_trace[WARPS][TRACE_STRIDE];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -363,15 +413,19 @@ k_blake3_comp_witness(const uint32_t *__restrict__ in, uint64_t n, const uint32_
         const uint64_t i = pipe.inst();
         __syncwarp();
         if (lane < 28) trace[TR_IN + lane] = pipe.cur_in;
+        if (WIDE && lane < 16) trace[TR_EXT + lane] = (uint32_t)(int)wd.m_ext[i * 16 + lane];
         pipe.advance();
         __syncwarp();
         compression_trace(trace, lane, ls);
         __syncwarp();
         if (fault && lane == 0) trace[ck.fault_word] ^= ck.fault_mask;
         __syncwarp();
+        // WIDE: the rows are evaluated on the u32 instance with the same low words (they hold for one iff for the other:
+        // the ext terms cancel), the carry range decides "Assert Failed."
         const uint32_t bad = B3W_EXP_CHECK(r1cs_check_instance(TraceSrc{trace, ck.F}, ck.T, lane));
-        if (ck.first_bad && lane == 0) ck.first_bad[i] = bad;
-        if (status && lane == 0) status[i] = bad != B3W_NO_ROW ? B3W_R1CS_VIOLATION : 0;
+        const bool asserted = WIDE && wide_carries<false>(trace, lane);
+        if (ck.first_bad && lane == 0) ck.first_bad[i] = asserted ? B3W_NO_ROW : bad;
+        if (status && lane == 0) status[i] = asserted ? B3W_CIRCOM_ASSERT : bad != B3W_NO_ROW ? B3W_R1CS_VIOLATION : 0;
       }
     } else {
       // ---- expansion items: 1/parts of one witness each ----
@@ -381,10 +435,22 @@ k_blake3_comp_witness(const uint32_t *__restrict__ in, uint64_t n, const uint32_
         const uint32_t a = part * sc.part_len, b = a + sc.part_len < ws ? a + sc.part_len : ws;
         __syncwarp();                               // the previous expansion has finished reading the trace
         if (lane < 28) trace[TR_IN + lane] = pipe.cur_in;
+        if (WIDE && lane < 16) trace[TR_EXT + lane] = (uint32_t)(int)wd.m_ext[i * 16 + lane];
         pipe.advance();
         __syncwarp();
         compression_trace(trace, lane, ls);
         __syncwarp();
+        if (WIDE) {
+          const bool asserted = wide_carries<true>(trace, lane);
+          __syncwarp();
+          if (asserted) {                           // the reference throws "Assert Failed.": no witness exists
+            if (part == 0) {
+              if (!CHECK && status && lane == 0) status[i] = B3W_CIRCOM_ASSERT;
+              if (pub && lane < 16) pub[i * 16 + lane] = 0u;
+            }
+            continue;
+          }
+        }
         if (part == 0) {                            // this warp owns the instance's head
           if (pub && lane < 16) pub[i * 16 + lane] = trace[TR_OUT + lane];
           // u32 inputs can never violate a constraint of this circuit (which the fused check confirms row by row)
@@ -395,6 +461,7 @@ k_blake3_comp_witness(const uint32_t *__restrict__ in, uint64_t n, const uint32_
           __syncwarp();
         }
         expand_slots<false>(trace, desc, a, b, out + i * (uint64_t)ws * 32, lane, nullptr, nullptr, 0);
+        if (WIDE) wide_patch_m(trace, wd, a, b, out + i * (uint64_t)ws * 32, lane);
       }
     }
   }

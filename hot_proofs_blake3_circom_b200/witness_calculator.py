@@ -14,8 +14,9 @@ parity tests are written against it the way the reference's tests use witness_ca
 Differences that are deliberate and loud:
   * `code` (the .wasm bytes) only selects the circuit (by sha256); an unknown wasm raises -- there is no
     WebAssembly engine here to fall back to.
-  * input values must lie in the circuits' honest domain [0, 2^32) after reduction mod p; anything else
-    raises B3WError(B3W_ERR_DOMAIN) instead of being computed in the field.
+  * blake3_compression takes every input the reference takes (any field element: the circuit's own constraints
+    decide between a witness and "Assert Failed.", as in the wasm); the nova circuits cover their honest domain
+    [0, 2^32) after reduction mod p, anything else raises B3WError(B3W_ERR_DOMAIN) instead of being computed.
   * methods are plain (synchronous) functions.
 """
 import ctypes as C
@@ -170,8 +171,10 @@ class WitnessCalculator:
             return 0, 0          # the wasm's getInputSignalSize returns 0 for an unknown name
         return off.value, size.value
 
-    def _row(self, inp):
-        row = np.zeros(self.nInputs, np.uint32)
+    def _values(self, inp):
+        """The checks of _doCalculateWitness (:138-168) -> the nInputs values in declaration order, each BigInt(n) % prime
+        made non-negative (normalize, :319-323)."""
+        vals = [0] * self.nInputs
         input_counter = 0
         for k in inp.keys():
             f_arr = _flat_array(inp[k])
@@ -183,27 +186,56 @@ class WitnessCalculator:
             if len(f_arr) > signal_size:
                 raise RuntimeError("Too many values for input signal %s\n" % k)
             for i, v in enumerate(f_arr):
-                x = _to_bigint(v) % self.prime        # normalize(): BigInt(n) % prime, made non-negative
-                if x >> 32:
-                    raise B3WError(_lib.B3W_ERR_DOMAIN,
-                                   "input %s[%d] = %d is outside the supported u32 domain" % (k, i, x))
-                row[off + i] = x
+                vals[off + i] = _to_bigint(v) % self.prime
                 input_counter += 1
         if input_counter < self.nInputs:
             raise RuntimeError("Not all inputs have been set. Only %d out of %d" % (input_counter, self.nInputs))
-        return row
+        return vals
+
+    def _row(self, inp):
+        """-> the u32 input row; values outside [0, 2^32) raise B3WError(B3W_ERR_DOMAIN)."""
+        vals = self._values(inp)
+        for idx, x in enumerate(vals):
+            if x >> 32:
+                raise B3WError(_lib.B3W_ERR_DOMAIN, "input %s = %d is outside the u32 domain" % (self._signal_at(idx), x))
+        return np.array(vals, np.uint32)
+
+    def _signal_at(self, idx):
+        for name in ("h", "m", "t", "b", "d", "n_blocks", "block_count", "chunk_idx_low", "chunk_idx_high", "leaf_depth",
+                     "total_depth", "depth"):
+            off, size = self._input_signal_size(name)
+            if size and off <= idx < off + size:
+                return "%s[%d]" % (name, idx - off)
+        return "#%d" % idx
+
+    @staticmethod
+    def _fr_bytes(vals):
+        return np.frombuffer(b"".join(int(v).to_bytes(32, "little") for v in vals), np.uint8).copy()
 
     def _do_calculate(self, inp):
-        row = self._row(inp)
+        vals = self._values(inp)
+        u32 = all(x >> 32 == 0 for x in vals)
+        if not u32 and self.circuit != 0:
+            self._row(inp)                            # raises B3W_ERR_DOMAIN naming the input (nova: u32 domain only)
         if self.circuit != 0:
             # the nova circuits execute log("D_FLAGS: ", D_FLAGS) once per witness (circuits/blake3_nova.circom:166);
             # witness_calculator.js:44-61 prints it with console.log.  The batched entry point stays silent.
             print("D_FLAGS:  0")
         out = np.empty(self.witnessSize * 32, np.uint8)
-        rc = self._L.b3w_witness_one(self._h, row.ctypes.data, out.ctypes.data)
+        if u32:
+            row = np.array(vals, np.uint32)
+            rc = self._L.b3w_witness_one(self._h, row.ctypes.data, out.ctypes.data)
+            trace = lambda: self.assertTrace(row)
+        else:
+            # blake3_compression takes any field element (only the circuit's own constraints decide, as in the reference)
+            fr = self._fr_bytes(vals)
+            status = np.zeros(1, np.uint8)
+            _lib.check(self._L.b3w_witness_batch_fr(self._h, fr.ctypes.data, 1, out.ctypes.data, status.ctypes.data, None))
+            rc = int(status[0])
+            trace = lambda: self.assertTraceFr(vals)
         if rc == _lib.B3W_CIRCOM_ASSERT:
             # witness_calculator.js:21-39,159-162: Error("Assert Failed.\n" + the printErrorMessage lines), re-wrapped
-            raise RuntimeError("Error: Assert Failed.\n" + self.assertTrace(row))
+            raise RuntimeError("Error: Assert Failed.\n" + trace())
         _lib.check(rc)
         return out
 
@@ -212,6 +244,15 @@ class WitnessCalculator:
         row = np.ascontiguousarray(row, np.uint32)
         buf = C.create_string_buffer(1024)
         rc = self._L.b3w_assert_trace(self.circuit, row.ctypes.data, buf, len(buf))
+        if rc not in (0, _lib.B3W_CIRCOM_ASSERT):
+            _lib.check(rc)
+        return buf.value.decode()
+
+    def assertTraceFr(self, vals):
+        """ditto for nInputs field elements (ints, already reduced or not)."""
+        fr = self._fr_bytes([int(v) % self.prime for v in vals])
+        buf = C.create_string_buffer(1024)
+        rc = self._L.b3w_assert_trace_fr(self.circuit, fr.ctypes.data, buf, len(buf))
         if rc not in (0, _lib.B3W_CIRCOM_ASSERT):
             _lib.check(rc)
         return buf.value.decode()
@@ -238,21 +279,47 @@ class WitnessCalculator:
         """inputs: list of input objects (as for calculateWitness) or an (n, nInputs) uint32 array in
         circuit declaration order.  Returns dict(witness=(n, witnessSize*32) u8 | None, status=u8[n],
         pub=(n, nPublic) u32)."""
+        fr = None
         if isinstance(inputs, np.ndarray):
             rows = np.ascontiguousarray(inputs, np.uint32)
             if rows.ndim != 2 or rows.shape[1] != self.nInputs:
                 raise ValueError("expected an (n, %d) uint32 array" % self.nInputs)
         else:
-            rows = np.stack([self._row(i) for i in inputs]) if len(inputs) else np.zeros((0, self.nInputs), np.uint32)
+            vals = [self._values(i) for i in inputs]
+            if self.circuit == 0 and any(x >> 32 for v in vals for x in v):
+                fr = self._fr_bytes([x for v in vals for x in v])          # field-element inputs: b3w_witness_batch_fr
+                rows = np.zeros((len(vals), self.nInputs), np.uint32)
+            else:
+                rows = np.stack([self._row(i) for i in inputs]) if len(inputs) else np.zeros((0, self.nInputs), np.uint32)
         n = rows.shape[0]
         if want_witness and out is None:
             out = np.empty((n, self.witnessSize * 32), np.uint8)
         status = np.zeros(n, np.uint8)
         pub = np.zeros((n, self.nPublic), np.uint32)
-        _lib.check(self._L.b3w_witness_batch(self._h, rows.ctypes.data, n,
-                                             out.ctypes.data if want_witness else None,
-                                             status.ctypes.data, pub.ctypes.data))
+        if fr is not None:
+            _lib.check(self._L.b3w_witness_batch_fr(self._h, fr.ctypes.data, n, out.ctypes.data if want_witness else None,
+                                                    status.ctypes.data, pub.ctypes.data))
+        else:
+            _lib.check(self._L.b3w_witness_batch(self._h, rows.ctypes.data, n,
+                                                 out.ctypes.data if want_witness else None,
+                                                 status.ctypes.data, pub.ctypes.data))
         return {"witness": out if want_witness else None, "status": status, "pub": pub}
+
+    def calculateWitnessBatchFr(self, values, want_witness=True):
+        """values: (n, nInputs) Python ints / an (n, nInputs, 32) uint8 array of little-endian field elements.
+        blake3_compression: every input the reference accepts; nova: u32 values only (B3W_ERR_DOMAIN otherwise)."""
+        if isinstance(values, np.ndarray) and values.dtype == np.uint8:
+            fr = np.ascontiguousarray(values).reshape(-1)
+            n = values.shape[0]
+        else:
+            n = len(values)
+            fr = self._fr_bytes([int(x) % self.prime for v in values for x in v]) if n else np.zeros(0, np.uint8)
+        out = np.empty((n, self.witnessSize * 32), np.uint8) if want_witness else None
+        status = np.zeros(n, np.uint8)
+        pub = np.zeros((n, self.nPublic), np.uint32)
+        _lib.check(self._L.b3w_witness_batch_fr(self._h, fr.ctypes.data, n, out.ctypes.data if want_witness else None,
+                                                status.ctypes.data, pub.ctypes.data))
+        return {"witness": out, "status": status, "pub": pub}
 
     # ---- NEW: compact witnesses (the per-instance trace; ~200x smaller than the .wtns body) ----
     @property
@@ -311,6 +378,11 @@ class WitnessCalculator:
         """generation + fused R1CS check (rows evaluated on the shared-memory trace)"""
         _lib.check(self._L.b3w_witness_batch_device_checked(self._h, d_in, n, d_out, d_status or None, d_pub or None,
                                                             d_first_bad or None, stream or None))
+
+    def witness_batch_device_wide(self, d_in, d_m_ext, n, d_out, d_status=0, d_pub=0, d_first_bad=0, stream=0):
+        """blake3_compression with wide message words (m = m_ext * 2^32 + row word); d_first_bad != 0 adds the fused check"""
+        _lib.check(self._L.b3w_witness_batch_device_wide(self._h, d_in, d_m_ext, n, d_out, d_status or None, d_pub or None,
+                                                         d_first_bad or None, stream or None))
 
     def r1cs_check_device(self, d_wit, n, d_status=0, d_first_bad=0, stream=0):
         """stand-alone R1CS check of witnesses resident in device memory (O1 builds)"""

@@ -26,7 +26,7 @@ extern "C" {
 #define B3W_ERR_INVALID (-1)     /* bad argument */
 #define B3W_ERR_CUDA (-2)        /* CUDA runtime error or no device; text in b3w_last_error() */
 #define B3W_ERR_NOMEM (-3)
-#define B3W_ERR_DOMAIN (-4)      /* an input is outside the supported (u32) domain */
+#define B3W_ERR_DOMAIN (-4)      /* an input is outside the supported domain (nova circuits: u32) */
 #define B3W_ERR_UNSUPPORTED (-5)
 #define B3W_CIRCOM_ASSERT 4      /* "Assert Failed." (witness_calculator.js:29-30) */
 #define B3W_R1CS_VIOLATION 7     /* per-instance status of the on-device R1CS check: some row has A.z * B.z != C.z */
@@ -103,9 +103,33 @@ int b3w_witness_batch(b3w_ctx *ctx, const uint32_t *in, uint64_t n, uint8_t *out
  * `normalize`, witness_calculator.js:319-323) -- the form in which rust_fold holds them (`Vec<(String, Vec<F>)>`,
  * rust_fold/src/blake3_circuit.rs:197-289).  b3w_inputs_from_fr converts to the u32 rows of the other entry points
  * (host-only, needs no GPU); a value outside [0, 2^32) after reduction is refused with B3W_ERR_DOMAIN, naming the
- * instance and signal.  b3w_witness_batch_fr = convert + b3w_witness_batch. */
+ * instance and signal.  b3w_witness_batch_fr = convert + b3w_witness_batch (nova circuits; blake3_compression: see below). */
 int b3w_inputs_from_fr(uint32_t circuit, const uint8_t *in_fr, uint64_t n, uint32_t *rows);
 int b3w_witness_batch_fr(b3w_ctx *ctx, const uint8_t *in_fr, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub);
+
+/* The FULL input domain of blake3_compression.  The reference takes any field element for every input
+ * (witness_calculator.js:319-323) and lets the circuit decide: h, t, b, d pass through ToBits(32), so a value >= 2^32
+ * ends in "Assert Failed."; the message words are not range-checked (circuits/blake3_compression.circom:169-170) and only
+ * enter 34-bit sums, so e.g. m[0] = 2^32 or m[0] = p - 1 give VALID witnesses.  A satisfying input
+ * therefore has message words m = ext * 2^32 + lo with ext in [-2, 3]:
+ *   b3w_inputs_from_fr_wide   Fr256 rows -> u32 rows (lo words) + m_ext (n x 16 int8).  Refuses nothing: an instance that
+ *                             cannot satisfy the circuit gets m_ext[i][0] = B3W_EXT_ASSERT and comes back with status 4.
+ *                             *n_wide (may be NULL) = instances that are not plain u32 rows.  Host-only, needs no GPU.
+ *   b3w_witness_batch_wide / _device_wide   as b3w_witness_batch / b3w_witness_batch_device(_checked) with m_ext; the sums
+ *                             that leave [0, 2^34) are detected on the device (status 4, no witness, pub = 0).  With
+ *                             d_first_bad != NULL or B3W_FLAG_FUSED_CHECK the fused R1CS check runs as well.
+ *   b3w_witness_batch_fr      (above) takes this path for blake3_compression, so it accepts every input the reference
+ *                             accepts; for the nova circuits it still covers the u32 domain only (B3W_ERR_DOMAIN otherwise).
+ *   b3w_assert_trace_fr       b3w_assert_trace for ONE Fr256 input row: the reference's per-template trace of the first
+ *                             failing constraint in the wasm's execution order, e.g. for b = 2^33 "Error in template ToBits_3
+ *                             line: 153\nError in template RotXorWordBits_5 line: 62\nError in template HalfFunG_18 line: 91\n...". */
+#define B3W_EXT_ASSERT 127
+int b3w_inputs_from_fr_wide(uint32_t circuit, const uint8_t *in_fr, uint64_t n, uint32_t *rows, int8_t *m_ext, uint64_t *n_wide);
+int b3w_witness_batch_wide(b3w_ctx *ctx, const uint32_t *in, const int8_t *m_ext, uint64_t n, uint8_t *out, uint8_t *status,
+                           uint32_t *pub);
+int b3w_witness_batch_device_wide(b3w_ctx *ctx, const uint32_t *d_in, const int8_t *d_m_ext, uint64_t n, uint8_t *d_out,
+                                  uint8_t *d_status, uint32_t *d_pub, uint32_t *d_first_bad, void *stream);
+int b3w_assert_trace_fr(uint32_t circuit, const uint8_t *in_fr, char *buf, size_t cap);
 
 /* NEW batched entry point, DEVICE buffers (same layouts), asynchronous on `stream` (a cudaStream_t, may
  * be NULL for the default stream).  d_out must hold n*witness_size*32 bytes, 32-byte aligned. */
