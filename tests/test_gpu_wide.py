@@ -72,7 +72,7 @@ def test_reference_fixture(wc, wide_cases):
     assert np.array_equal(res["witness"][valid], want)
     assert (res["pub"][status == 4] == 0).all()
     # out[16] = witness slots 1..16
-    assert np.array_equal(res["pub"][valid], want.reshape(len(valid), WS, 8).view(np.uint32)[:, 1:17, 0])
+    assert np.array_equal(res["pub"][valid], want.view(np.uint32).reshape(len(valid), WS, 8)[:, 1:17, 0])
 
 
 def test_surveyed_cases_through_the_single_witness_api(wc, golden, wide_cases):
