@@ -96,19 +96,23 @@ static napi_value WtnsHeader(napi_env env, napi_callback_info info) {
 
 // witnessBatch(ctx, rows: Uint32Array, n, wantWitness) -> Promise<{witness: Uint8Array|null, status: Uint8Array, pub: Uint32Array}>
 // witnessOne(ctx, row) -> Promise<Uint8Array>
+// witnessBatchFr(ctx, fr: Uint8Array(n * nInputs * 32), n, wantWitness) / witnessOneFr(ctx, fr): the same with inputs as
+// little-endian field elements (b3w_witness_batch_fr: blake3_compression takes every value the reference takes)
 struct job {
   napi_async_work work; napi_deferred deferred;
-  b3w_ctx *ctx; uint32_t circuit; uint32_t *rows; uint64_t n; b3w_info bi;
+  b3w_ctx *ctx; uint32_t circuit; uint32_t *rows; uint8_t *fr; uint64_t n; b3w_info bi;
   uint8_t *out, *status; uint32_t *pub; bool one; int rc; char err[512];
 };
 static void job_run(napi_env, void *data) {
   job *j = (job *)data;
-  j->rc = b3w_witness_batch(j->ctx, j->rows, j->n, j->out, j->status, j->pub);
+  j->rc = j->fr ? b3w_witness_batch_fr(j->ctx, j->fr, j->n, j->out, j->status, j->pub)
+                : b3w_witness_batch(j->ctx, j->rows, j->n, j->out, j->status, j->pub);
   if (j->rc == B3W_OK && j->one && j->status[0]) j->rc = j->status[0];
   if (j->rc == B3W_CIRCOM_ASSERT) {
     // witness_calculator.js:21-43,159-162: Error("Assert Failed.\n" + the printErrorMessage lines), re-wrapped
     char trace[400];
-    b3w_assert_trace(j->circuit, j->rows, trace, sizeof trace);
+    if (j->fr) b3w_assert_trace_fr(j->circuit, j->fr, trace, sizeof trace);
+    else b3w_assert_trace(j->circuit, j->rows, trace, sizeof trace);
     snprintf(j->err, sizeof j->err, "Error: Assert Failed.\n%s", trace);
   } else if (j->rc) {
     strncpy(j->err, b3w_last_error(), sizeof j->err - 1);
@@ -147,9 +151,10 @@ static void job_done(napi_env env, napi_status, void *data) {
   }
   napi_delete_async_work(env, j->work);
   free(j->rows);
+  free(j->fr);
   free(j);
 }
-static napi_value start_job(napi_env env, napi_callback_info info, bool one) {
+static napi_value start_job(napi_env env, napi_callback_info info, bool one, bool fr = false) {
   size_t argc = 4; napi_value argv[4];
   NAPI_OK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
   job *j = (job *)calloc(1, sizeof(job));
@@ -166,10 +171,19 @@ static napi_value start_job(napi_env env, napi_callback_info info, bool one) {
     uint32_t n32; NAPI_OK(napi_get_value_uint32(env, argv[2], &n32)); j->n = n32;
     NAPI_OK(napi_get_value_bool(env, argv[3], &want));
   }
-  if (len != (size_t)j->n * j->bi.n_inputs) { free(j); napi_throw_error(env, NULL, "rows must hold n * nInputs values"); return NULL; }
+  if (len != (size_t)j->n * j->bi.n_inputs * (fr ? 32 : 1) || tt != (fr ? napi_uint8_array : napi_uint32_array)) {
+    free(j);
+    napi_throw_error(env, NULL, fr ? "fr must be a Uint8Array of n * nInputs * 32 bytes" : "rows must be a Uint32Array of n * nInputs values");
+    return NULL;
+  }
   j->one = one;
-  j->rows = (uint32_t *)malloc(len * 4);
-  memcpy(j->rows, data, len * 4);
+  if (fr) {
+    j->fr = (uint8_t *)malloc(len ? len : 1);
+    memcpy(j->fr, data, len);
+  } else {
+    j->rows = (uint32_t *)malloc(len ? len * 4 : 4);
+    memcpy(j->rows, data, len * 4);
+  }
   j->status = (uint8_t *)calloc(j->n ? j->n : 1, 1);
   j->pub = (uint32_t *)calloc((j->n ? j->n : 1) * 16, 4);
   j->out = want ? (uint8_t *)malloc((size_t)(j->n ? j->n : 1) * j->bi.witness_size * 32) : NULL;
@@ -182,12 +196,15 @@ static napi_value start_job(napi_env env, napi_callback_info info, bool one) {
 }
 static napi_value WitnessBatch(napi_env env, napi_callback_info info) { return start_job(env, info, false); }
 static napi_value WitnessOne(napi_env env, napi_callback_info info) { return start_job(env, info, true); }
+static napi_value WitnessBatchFr(napi_env env, napi_callback_info info) { return start_job(env, info, false, true); }
+static napi_value WitnessOneFr(napi_env env, napi_callback_info info) { return start_job(env, info, true, true); }
 
 static napi_value Init(napi_env env, napi_value exports) {
   napi_property_descriptor d[] = {
       {"create", 0, Create, 0, 0, 0, napi_default, 0},           {"circuitInfo", 0, CircuitInfo, 0, 0, 0, napi_default, 0},
       {"inputSignal", 0, InputSignal, 0, 0, 0, napi_default, 0}, {"wtnsHeader", 0, WtnsHeader, 0, 0, 0, napi_default, 0},
-      {"witnessBatch", 0, WitnessBatch, 0, 0, 0, napi_default, 0}, {"witnessOne", 0, WitnessOne, 0, 0, 0, napi_default, 0}};
+      {"witnessBatch", 0, WitnessBatch, 0, 0, 0, napi_default, 0}, {"witnessOne", 0, WitnessOne, 0, 0, 0, napi_default, 0},
+      {"witnessBatchFr", 0, WitnessBatchFr, 0, 0, 0, napi_default, 0}, {"witnessOneFr", 0, WitnessOneFr, 0, 0, 0, napi_default, 0}};
   napi_define_properties(env, exports, sizeof d / sizeof d[0], d);
   return exports;
 }

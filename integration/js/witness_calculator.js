@@ -5,6 +5,10 @@
 // programs).  A wasm it does not know falls through to the ORIGINAL WebAssembly implementation, which the caller
 // keeps as ./witness_calculator.wasm.js (the unmodified reference file); so does options.forceWasm.
 //
+// Input domain: blake3_compression takes every value the reference takes (field elements go to the library as Fr256,
+// b3w_witness_batch_fr).  The nova kernels cover the circuits' honest u32 domain; an input outside it is handed to the
+// reference's own wasm program (built lazily from the same `code`), so the drop-in never answers differently.
+//
 // NOTE: Node is not available in the build image of this repository, so this file is reviewed, not executed,
 // there; hot_proofs_blake3_circom_b200/witness_calculator.py mirrors it line by line and IS exercised by the tests.
 const crypto = require("crypto");
@@ -23,12 +27,14 @@ module.exports = async function builder(code, options) {
         return require("./witness_calculator.wasm.js")(code, options);      // the reference path, untouched
     }
     const addon = require("./build/Release/blake3wit_napi.node");
-    return new WitnessCalculator(addon, addon.create(circuit, options.device === undefined ? -1 : options.device), circuit, options);
+    return new WitnessCalculator(addon, addon.create(circuit, options.device === undefined ? -1 : options.device), circuit, options, code);
 };
 
 class WitnessCalculator {
-    constructor(addon, ctx, circuit, sanityCheck) {
+    constructor(addon, ctx, circuit, sanityCheck, code) {
         this.addon = addon;
+        this.code = code;                          // kept for inputs outside the nova kernels' domain
+        this.wasmCalculator = null;
         this.instance = ctx;                       // the reference keeps the wasm instance here
         this.circuit = circuit;
         const info = addon.circuitInfo(circuit);   // b3w_circuit_info
@@ -44,34 +50,52 @@ class WitnessCalculator {
         return this.version;
     }
 
-    // witness_calculator.js:131-169 -- same checks, same messages; values end up in one u32 row
-    _row(input) {
-        const row = new Uint32Array(this.nInputs);
+    // witness_calculator.js:131-169 -- same checks, same messages; -> the nInputs values in declaration order (BigInt)
+    _values(input) {
+        const vals = new Array(this.nInputs).fill(0n);
         let input_counter = 0;
         Object.keys(input).forEach((k) => {
             const fArr = flatArray(input[k]);
-            const sig = this.addon.inputSignal(this.circuit, k);          // {offset, size}; size 0 for unknown names
-            const signalSize = sig ? sig.size : 0;
+            const sig = this.addon.inputSignal(this.circuit, k);          // {offset, size}; null for unknown names
+            const signalSize = sig ? sig.size : 0;                        // the wasm's getInputSignalSize returns 0 then
             if (signalSize < 0) throw new Error(`Signal ${k} not found\n`);
             if (fArr.length < signalSize) throw new Error(`Not enough values for input signal ${k}\n`);
             if (fArr.length > signalSize) throw new Error(`Too many values for input signal ${k}\n`);
             for (let i = 0; i < fArr.length; i++) {
-                const v = normalize(fArr[i], this.prime);
-                if (v >> 32n) throw new Error(`input ${k}[${i}] = ${v} is outside the supported u32 domain`);
-                row[sig.offset + i] = Number(v);
+                vals[sig.offset + i] = normalize(fArr[i], this.prime);
                 input_counter++;
             }
         });
         if (input_counter < this.nInputs) {
             throw new Error(`Not all inputs have been set. Only ${input_counter} out of ${this.nInputs}`);
         }
+        return vals;
+    }
+
+    _row(vals) {
+        const row = new Uint32Array(this.nInputs);
+        vals.forEach((v, i) => { row[i] = Number(v); });
         return row;
     }
 
+    _fr(vals) {                                    // nInputs x 32 bytes, little-endian
+        const fr = new Uint8Array(vals.length * 32);
+        vals.forEach((v, i) => { for (let j = 0; j < 32; j++) { fr[32 * i + j] = Number(v & 0xffn); v >>= 8n; } });
+        return fr;
+    }
+
+    async _wasm() {                                // the reference's own program, for inputs the nova kernels do not cover
+        if (!this.wasmCalculator) this.wasmCalculator = await require("./witness_calculator.wasm.js")(this.code, this.sanityCheck);
+        return this.wasmCalculator;
+    }
+
     async _bin(input) {
-        const row = this._row(input);
+        const vals = this._values(input);
+        const u32 = vals.every((v) => v >> 32n === 0n);
+        if (!u32 && this.circuit !== 0) return (await this._wasm()).calculateBinWitness(input, this.sanityCheck);
         if (this.circuit !== 0) console.log("D_FLAGS:  0");                 // circuits/blake3_nova.circom:166
-        return await this.addon.witnessOne(this.instance, row);            // napi_async_work around b3w_witness_one
+        if (!u32) return await this.addon.witnessOneFr(this.instance, this._fr(vals));   // b3w_witness_batch_fr
+        return await this.addon.witnessOne(this.instance, this._row(vals)); // napi_async_work around b3w_witness_batch
     }
 
     async calculateWitness(input, sanityCheck) {
@@ -103,16 +127,17 @@ class WitnessCalculator {
     // opts.witness === false keeps the witnesses on the GPU and returns only status + public outputs.
     async calculateWitnessBatch(inputs, opts) {
         opts = opts || {};
-        let rows, n;
-        if (Array.isArray(inputs)) {
-            n = inputs.length;
-            rows = new Uint32Array(n * this.nInputs);
-            inputs.forEach((inp, i) => rows.set(this._row(inp), i * this.nInputs));
-        } else {
-            rows = inputs.rows;
-            n = inputs.n;
+        if (!Array.isArray(inputs)) {
+            return await this.addon.witnessBatch(this.instance, inputs.rows, inputs.n, opts.witness !== false);   // {witness, status, pub}
         }
-        return await this.addon.witnessBatch(this.instance, rows, n, opts.witness !== false);   // {witness, status, pub}
+        const n = inputs.length;
+        const vals = inputs.map((inp) => this._values(inp));
+        const u32 = vals.every((v) => v.every((x) => x >> 32n === 0n));
+        if (!u32 && this.circuit !== 0) throw new Error("calculateWitnessBatch: the nova circuits take u32 inputs (use calculateWitness for field-valued inputs)");
+        if (!u32) return await this.addon.witnessBatchFr(this.instance, this._fr(vals.flat()), n, opts.witness !== false);
+        const rows = new Uint32Array(n * this.nInputs);
+        vals.forEach((v, i) => rows.set(this._row(v), i * this.nInputs));
+        return await this.addon.witnessBatch(this.instance, rows, n, opts.witness !== false);
     }
 }
 

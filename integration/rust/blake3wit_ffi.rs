@@ -26,6 +26,9 @@ extern "C" {
     pub fn b3w_circuit_info(circuit: u32, info: *mut B3wInfo) -> c_int;
     pub fn b3w_witness_one(ctx: *mut B3wCtx, input: *const u32, out: *mut u8) -> c_int;
     pub fn b3w_witness_batch(ctx: *mut B3wCtx, input: *const u32, n: u64, out: *mut u8, status: *mut u8, publ: *mut u32) -> c_int;
+    /// inputs as canonical little-endian field elements (`F::to_repr()`), n rows of n_inputs x 32 bytes
+    pub fn b3w_witness_batch_fr(ctx: *mut B3wCtx, input_fr: *const u8, n: u64, out: *mut u8, status: *mut u8, publ: *mut u32) -> c_int;
+    pub fn b3w_assert_trace_fr(circuit: u32, input_fr: *const u8, buf: *mut c_char, cap: usize) -> c_int;
     pub fn b3w_nova_chain_size(len: u64, n_chunks: *mut u64, total_steps: *mut u64) -> c_int;
     pub fn b3w_nova_chain(ctx: *mut B3wCtx, data: *const u8, len: u64, out: *mut u8, status: *mut u8, publ: *mut u32,
                           rows: *mut u32, step_off: *mut u64, root: *mut u8) -> c_int;
