@@ -18,6 +18,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include <new>
+#include <exception>
 #include <vector>
 #include <string>
 #include <algorithm>
@@ -52,6 +53,21 @@ static int fail(int code, const char *fmt, ...) {
     cudaError_t e_ = (call);                                                                         \
     if (e_ != cudaSuccess) return fail(B3W_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
+
+// The C ABI never lets a C++ exception cross it ("never abort"): entry points that allocate through the standard library
+// or start threads run their bodies under this guard.
+template <class F>
+static int guarded(const char *what, F &&body) {
+  try {
+    return body();
+  } catch (const std::bad_alloc &) {
+    return fail(B3W_ERR_NOMEM, "%s: out of host memory", what);
+  } catch (const std::exception &e) {
+    return fail(B3W_ERR_INVALID, "%s: %s", what, e.what());
+  } catch (...) {
+    return fail(B3W_ERR_INVALID, "%s: unexpected exception", what);
+  }
+}
 
 #include "kernels_witness.cuh"
 #include "kernels_chain.cuh"
@@ -151,7 +167,7 @@ struct b3w_ctx {
 extern "C" int b3w_version(void) { return B3W_VERSION; }
 extern "C" const char *b3w_last_error(void) { return g_err; }
 
-extern "C" int b3w_create(const b3w_config *cfg, b3w_ctx **out) {
+static int b3w_create_impl(const b3w_config *cfg, b3w_ctx **out) {
   if (!cfg || !out) return fail(B3W_ERR_INVALID, "b3w_create: null argument");
   if (cfg->circuit >= (uint32_t)N_CIRCUITS) return fail(B3W_ERR_UNSUPPORTED, "b3w_create: circuit %u not built", cfg->circuit);
   if (cfg->flags & ~(uint32_t)B3W_FLAG_FUSED_CHECK) return fail(B3W_ERR_INVALID, "b3w_create: unknown flags 0x%x", cfg->flags);
@@ -237,6 +253,9 @@ extern "C" int b3w_create(const b3w_config *cfg, b3w_ctx **out) {
   if (e1 != cudaSuccess || c->ctas_per_sm < 1 || c->ctas_per_sm_checked < 1) { b3w_destroy(c); return fail(B3W_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e1)); }
   *out = c;
   return B3W_OK;
+}
+extern "C" int b3w_create(const b3w_config *cfg, b3w_ctx **out) {
+  return guarded("b3w_create", [&]() { return b3w_create_impl(cfg, out); });
 }
 
 static void free_packed_ring(b3w_ctx *c);
@@ -540,7 +559,7 @@ extern "C" int b3w_r1cs_check_device(b3w_ctx *c, const uint8_t *d_wit, uint64_t 
 
 // Replace the built-in slot-space row set of this context by the constraint system of an iden3 `.r1cs` file: the
 // reference's own build/*.r1cs where the user has them, or the equivalents written by tools/export_r1cs.py.
-extern "C" int b3w_r1cs_load(b3w_ctx *c, const uint8_t *data, size_t len, uint32_t *n_rows) {
+static int b3w_r1cs_load_impl(b3w_ctx *c, const uint8_t *data, size_t len, uint32_t *n_rows) {
   if (!c || !data) return fail(B3W_ERR_INVALID, "b3w_r1cs_load: null argument");
   CK(cudaSetDevice(c->device));
   r1cs_host_set h;
@@ -580,8 +599,11 @@ extern "C" int b3w_r1cs_load(b3w_ctx *c, const uint8_t *data, size_t len, uint32
   if (n_rows) *n_rows = h.rows;
   return B3W_OK;
 }
+extern "C" int b3w_r1cs_load(b3w_ctx *c, const uint8_t *data, size_t len, uint32_t *n_rows) {
+  return guarded("b3w_r1cs_load", [&]() { return b3w_r1cs_load_impl(c, data, len, n_rows); });
+}
 
-extern "C" int b3w_r1cs_load_file(b3w_ctx *c, const char *path, uint32_t *n_rows) {
+static int b3w_r1cs_load_file_impl(b3w_ctx *c, const char *path, uint32_t *n_rows) {
   if (!c || !path) return fail(B3W_ERR_INVALID, "b3w_r1cs_load_file: null argument");
   FILE *f = fopen(path, "rb");
   if (!f) return fail(B3W_ERR_INVALID, "b3w_r1cs_load_file: cannot open %s", path);
@@ -591,6 +613,9 @@ extern "C" int b3w_r1cs_load_file(b3w_ctx *c, const char *path, uint32_t *n_rows
   while ((k = fread(tmp, 1, sizeof tmp, f)) > 0) buf.insert(buf.end(), tmp, tmp + k);
   fclose(f);
   return b3w_r1cs_load(c, buf.data(), buf.size(), n_rows);
+}
+extern "C" int b3w_r1cs_load_file(b3w_ctx *c, const char *path, uint32_t *n_rows) {
+  return guarded("b3w_r1cs_load_file", [&]() { return b3w_r1cs_load_file_impl(c, path, n_rows); });
 }
 
 extern "C" int b3w_debug_inject_fault(b3w_ctx *c, uint32_t trace_word, uint32_t xor_mask) {
@@ -754,7 +779,7 @@ extern "C" int b3w_witness_batch_device_wide(b3w_ctx *c, const uint32_t *d_in, c
                         d_first_bad, d_m_ext);
 }
 
-extern "C" int b3w_witness_batch_fr(b3w_ctx *c, const uint8_t *in_fr, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub) {
+static int b3w_witness_batch_fr_impl(b3w_ctx *c, const uint8_t *in_fr, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub) {
   if (!c || (!in_fr && n)) return fail(B3W_ERR_INVALID, "b3w_witness_batch_fr: null argument");
   const uint32_t circuit = (uint32_t)(c->def - CIRCUITS);
   std::vector<uint32_t> rows;
@@ -772,6 +797,9 @@ extern "C" int b3w_witness_batch_fr(b3w_ctx *c, const uint8_t *in_fr, uint64_t n
   int rc = b3w_inputs_from_fr_wide(circuit, in_fr, n, rows.data(), ext.data(), &n_wide);
   if (rc) return rc;
   return batch_host(c, rows.data(), n_wide ? ext.data() : nullptr, n, out, status, pub);
+}
+extern "C" int b3w_witness_batch_fr(b3w_ctx *c, const uint8_t *in_fr, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub) {
+  return guarded("b3w_witness_batch_fr", [&]() { return b3w_witness_batch_fr_impl(c, in_fr, n, out, status, pub); });
 }
 
 // b3w_assert_trace for field-element inputs.  blake3_compression: any input (the range constraints are replayed in the
@@ -954,13 +982,16 @@ static int make_chain_plan(uint64_t len, chain_plan &p) {
   return B3W_OK;
 }
 
-extern "C" int b3w_nova_chain_size(uint64_t len, uint64_t *n_chunks, uint64_t *total_steps) {
+static int b3w_nova_chain_size_impl(uint64_t len, uint64_t *n_chunks, uint64_t *total_steps) {
   chain_plan p;
   int rc = make_chain_plan(len, p);
   if (rc) return rc;
   if (n_chunks) *n_chunks = p.nc;
   if (total_steps) *total_steps = p.total;
   return B3W_OK;
+}
+extern "C" int b3w_nova_chain_size(uint64_t len, uint64_t *n_chunks, uint64_t *total_steps) {
+  return guarded("b3w_nova_chain_size", [&]() { return b3w_nova_chain_size_impl(len, n_chunks, total_steps); });
 }
 
 // grow-only device scratch of the chain driver, kept in the context (cudaMalloc / cudaFree per call cost more than the
@@ -1037,7 +1068,7 @@ static int nova_chain_range(b3w_ctx *c, const chain_plan &p, const uint8_t *data
   return B3W_OK;
 }
 
-extern "C" int b3w_nova_chain(b3w_ctx *c, const uint8_t *data, uint64_t len, uint8_t *out, uint8_t *status, uint32_t *pub,
+static int b3w_nova_chain_impl(b3w_ctx *c, const uint8_t *data, uint64_t len, uint8_t *out, uint8_t *status, uint32_t *pub,
                               uint32_t *rows_out, uint64_t *step_off_out, uint8_t root_out[32]) {
   if (!c || (!data && len)) return fail(B3W_ERR_INVALID, "b3w_nova_chain: null argument");
   if (!c->def->nova) return fail(B3W_ERR_INVALID, "b3w_nova_chain needs a nova circuit context");
@@ -1046,6 +1077,10 @@ extern "C" int b3w_nova_chain(b3w_ctx *c, const uint8_t *data, uint64_t len, uin
   if (rc) return rc;
   if (step_off_out) memcpy(step_off_out, p.step_off.data(), (p.nc + 1) * 8);
   return nova_chain_range(c, p, data, len, 0, p.nc, out, status, pub, rows_out, root_out);
+}
+extern "C" int b3w_nova_chain(b3w_ctx *c, const uint8_t *data, uint64_t len, uint8_t *out, uint8_t *status, uint32_t *pub,
+                              uint32_t *rows_out, uint64_t *step_off_out, uint8_t root_out[32]) {
+  return guarded("b3w_nova_chain", [&]() { return b3w_nova_chain_impl(c, data, len, out, status, pub, rows_out, step_off_out, root_out); });
 }
 
 // (the multi-GPU form, b3w_multi_nova_chain, is with the other b3w_multi_* entry points below: the unit of sharding is a
@@ -1163,8 +1198,14 @@ extern "C" int b3w_witness_batch_packed(b3w_ctx *c, const uint32_t *in, uint64_t
 struct b3w_multi {
   std::vector<b3w_ctx *> ctx;
 };
+// joins on every path out of the scope: a std::thread that is destroyed while joinable terminates the process
+struct thread_group {
+  std::vector<std::thread> th;
+  void join() { for (auto &t : th) if (t.joinable()) t.join(); }
+  ~thread_group() { join(); }
+};
 
-extern "C" int b3w_multi_create(const b3w_config *cfg, const int32_t *devices, uint32_t n_devices, b3w_multi **out) {
+static int b3w_multi_create_impl(const b3w_config *cfg, const int32_t *devices, uint32_t n_devices, b3w_multi **out) {
   if (!cfg || !out || (n_devices && !devices)) return fail(B3W_ERR_INVALID, "b3w_multi_create: null argument");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -1188,6 +1229,9 @@ extern "C" int b3w_multi_create(const b3w_config *cfg, const int32_t *devices, u
   *out = m;
   return B3W_OK;
 }
+extern "C" int b3w_multi_create(const b3w_config *cfg, const int32_t *devices, uint32_t n_devices, b3w_multi **out) {
+  return guarded("b3w_multi_create", [&]() { return b3w_multi_create_impl(cfg, devices, n_devices, out); });
+}
 
 extern "C" void b3w_multi_destroy(b3w_multi *m) {
   if (!m) return;
@@ -1210,15 +1254,15 @@ extern "C" int b3w_shard_range(uint64_t n, uint32_t g, uint32_t n_shards, uint64
   return B3W_OK;
 }
 
-extern "C" int b3w_multi_witness_batch(b3w_multi *m, const uint32_t *in, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub) {
+static int b3w_multi_witness_batch_impl(b3w_multi *m, const uint32_t *in, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub) {
   if (!m || m->ctx.empty() || (!in && n)) return fail(B3W_ERR_INVALID, "b3w_multi_witness_batch: null argument");
   const uint32_t G = (uint32_t)m->ctx.size();
   const circuit_def *d = m->ctx[0]->def;
   std::vector<int> rc(G, B3W_OK);
   std::vector<std::string> err(G);
-  std::vector<std::thread> th;
+  thread_group tg;
   for (uint32_t g = 0; g < G; g++) {
-    th.emplace_back([&, g]() {
+    tg.th.emplace_back([&, g]() {
       uint64_t first, count;
       shard_of(n, g, G, &first, &count);
       if (count == 0) return;
@@ -1227,13 +1271,16 @@ extern "C" int b3w_multi_witness_batch(b3w_multi *m, const uint32_t *in, uint64_
       if (rc[g]) err[g] = g_err;                       // g_err is thread-local: carry the text over to the caller
     });
   }
-  for (auto &t : th) t.join();
+  tg.join();
   for (uint32_t g = 0; g < G; g++)
     if (rc[g]) return fail(rc[g], "device %d (shard %u of %u): %s", m->ctx[g]->device, g, G, err[g].c_str());
   return B3W_OK;
 }
+extern "C" int b3w_multi_witness_batch(b3w_multi *m, const uint32_t *in, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub) {
+  return guarded("b3w_multi_witness_batch", [&]() { return b3w_multi_witness_batch_impl(m, in, n, out, status, pub); });
+}
 
-extern "C" int b3w_multi_nova_chain(b3w_multi *m, const uint8_t *data, uint64_t len, uint8_t *out, uint8_t *status, uint32_t *pub,
+static int b3w_multi_nova_chain_impl(b3w_multi *m, const uint8_t *data, uint64_t len, uint8_t *out, uint8_t *status, uint32_t *pub,
                                     uint32_t *rows_out, uint64_t *step_off_out, uint8_t root_out[32]) {
   if (!m || m->ctx.empty() || (!data && len)) return fail(B3W_ERR_INVALID, "b3w_multi_nova_chain: null argument");
   if (!m->ctx[0]->def->nova) return fail(B3W_ERR_INVALID, "b3w_multi_nova_chain needs a nova circuit context");
@@ -1253,19 +1300,23 @@ extern "C" int b3w_multi_nova_chain(b3w_multi *m, const uint8_t *data, uint64_t 
   }
   std::vector<int> rc(G, B3W_OK);
   std::vector<std::string> err(G);
-  std::vector<std::thread> th;
+  thread_group tg;
   for (uint32_t g = 0; g < G; g++) {
     if (cut[g] == cut[g + 1]) continue;
-    th.emplace_back([&, g]() {
+    tg.th.emplace_back([&, g]() {
       rc[g] = nova_chain_range(m->ctx[g], p, data, len, cut[g], cut[g + 1], out, status, pub, rows_out, root_out);
       if (rc[g]) err[g] = g_err;
     });
   }
-  for (auto &t : th) t.join();
+  tg.join();
   for (uint32_t g = 0; g < G; g++)
     if (rc[g]) return fail(rc[g], "device %d (chunks %llu..%llu): %s", m->ctx[g]->device, (unsigned long long)cut[g],
                            (unsigned long long)cut[g + 1], err[g].c_str());
   return B3W_OK;
+}
+extern "C" int b3w_multi_nova_chain(b3w_multi *m, const uint8_t *data, uint64_t len, uint8_t *out, uint8_t *status, uint32_t *pub,
+                                    uint32_t *rows_out, uint64_t *step_off_out, uint8_t root_out[32]) {
+  return guarded("b3w_multi_nova_chain", [&]() { return b3w_multi_nova_chain_impl(m, data, len, out, status, pub, rows_out, step_off_out, root_out); });
 }
 
 // NUMA node of a CUDA device (from sysfs; -1 when unknown)

@@ -69,6 +69,7 @@ static int r1cs_parse(const uint8_t *data, size_t len, const uint8_t prime[32], 
   // constraints
   pos = sec_off[2];
   const size_t cend = sec_off[2] + sec_len[2];
+  if ((uint64_t)m * 12 > (uint64_t)(cend - pos)) { err = "the header announces more constraints than the file holds"; return B3W_ERR_INVALID; }
   std::vector<row> rows(m);
   for (uint32_t i = 0; i < m; i++) {
     row &R = rows[i];
@@ -77,6 +78,7 @@ static int r1cs_parse(const uint8_t *data, size_t len, const uint8_t prime[32], 
     for (int part = 0; part < 3; part++) {
       uint32_t k;
       if (!rd32(data, cend, pos, k) || (size_t)k * 36 > cend - pos) { err = "truncated constraint " + std::to_string(i); return B3W_ERR_INVALID; }
+      if (k > 65535) { err = "constraint " + std::to_string(i) + " has " + std::to_string(k) + " terms in one linear combination"; return B3W_ERR_UNSUPPORTED; }
       R.part[part].resize(k);
       for (uint32_t j = 0; j < k; j++) {
         term &T = R.part[part][j];

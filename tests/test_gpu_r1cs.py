@@ -211,3 +211,46 @@ def test_loaded_r1cs_with_field_coefficients(built, exported):
     status, bad = hbm_check(wc, d_out, n)
     assert (status == _lib.B3W_R1CS_VIOLATION).all()
     wc.close()
+
+
+def test_r1cs_load_survives_damaged_files(built, exported):
+    """Truncated files, lying counts and flipped header bytes come back as error codes: the library never aborts."""
+    import struct
+    good = open(exported["compression"], "rb").read()
+    wc = pkg.builder("blake3_compression", device=0)
+    L, h = pkg.lib(), wc._h
+
+    def load(b):
+        buf = np.frombuffer(bytes(b), np.uint8) if len(b) else np.zeros(1, np.uint8)
+        return L.b3w_r1cs_load(h, buf.ctypes.data, len(b), None)
+    assert load(good) == 0
+    for cut in (0, 3, 4, 11, 12, 23, 24, 60, 100, 1000, len(good) // 2, len(good) - 1):
+        assert load(good[:cut]) < 0, cut
+    # section table starts at byte 12: type u32, size u64; the header section holds field size, prime, counts
+    pos = 12
+    secs = {}
+    for _ in range(struct.unpack_from("<I", good, 8)[0]):
+        t, sz = struct.unpack_from("<IQ", good, pos)
+        secs[t] = (pos + 12, sz)
+        pos += 12 + sz
+    hdr = secs[1][0]
+    m_off = hdr + 4 + 32 + 16 + 8                      # nConstraints
+    for value in (0xFFFFFFFF, 0x7FFFFFFF, 24545, 10**7):
+        bad = bytearray(good)
+        struct.pack_into("<I", bad, m_off, value)
+        assert load(bad) < 0, value                    # more constraints announced than the file holds
+    bad = bytearray(good)
+    struct.pack_into("<I", bad, secs[2][0], 0x10000000)          # nA of constraint 0
+    assert load(bad) < 0
+    bad = bytearray(good)
+    struct.pack_into("<Q", bad, 12 + 4, 2**63)                    # size of the first section
+    assert load(bad) < 0
+    rng = np.random.default_rng(9)
+    for _ in range(40):                                          # random damage in the first 200 bytes / anywhere
+        bad = bytearray(good)
+        for k in rng.integers(0, 200 if _ % 2 else len(good), 3):
+            bad[int(k)] ^= int(rng.integers(1, 256))
+        rc = load(bad)
+        assert rc <= 0                                           # an error code or an (equally large) accepted system
+    assert load(good) == 0
+    wc.close()
