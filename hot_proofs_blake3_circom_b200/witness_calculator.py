@@ -103,6 +103,18 @@ def pinned_array(shape, dtype):
     return arr
 
 
+PINNED_FROM = 32 << 20     # witness buffers of at least this many bytes are allocated pinned (full PCIe rate, overlap)
+
+
+def _witness_buffer(n, row_bytes):
+    if n * row_bytes >= PINNED_FROM:
+        try:
+            return pinned_array((n, row_bytes), np.uint8)
+        except B3WError:
+            pass                                   # locked-memory limit: a pageable buffer still works, only slower
+    return np.empty((n, row_bytes), np.uint8)
+
+
 def _nova_chain(L, call, handle, witness_size, data, want_witness):
     data = bytes(data)
     nc, ns = C.c_uint64(), C.c_uint64()
@@ -293,7 +305,7 @@ class WitnessCalculator:
                 rows = np.stack([self._row(i) for i in inputs]) if len(inputs) else np.zeros((0, self.nInputs), np.uint32)
         n = rows.shape[0]
         if want_witness and out is None:
-            out = np.empty((n, self.witnessSize * 32), np.uint8)
+            out = _witness_buffer(n, self.witnessSize * 32)
         status = np.zeros(n, np.uint8)
         pub = np.zeros((n, self.nPublic), np.uint32)
         if fr is not None:
@@ -314,7 +326,7 @@ class WitnessCalculator:
         else:
             n = len(values)
             fr = self._fr_bytes([int(x) % self.prime for v in values for x in v]) if n else np.zeros(0, np.uint8)
-        out = np.empty((n, self.witnessSize * 32), np.uint8) if want_witness else None
+        out = _witness_buffer(n, self.witnessSize * 32) if want_witness else None
         status = np.zeros(n, np.uint8)
         pub = np.zeros((n, self.nPublic), np.uint32)
         _lib.check(self._L.b3w_witness_batch_fr(self._h, fr.ctypes.data, n, out.ctypes.data if want_witness else None,
@@ -460,7 +472,7 @@ class MultiGpuCalculator:
             raise ValueError("expected an (n, %d) uint32 array" % self.nInputs)
         n = rows.shape[0]
         if want_witness and out is None:
-            out = np.empty((n, self.witnessSize * 32), np.uint8)
+            out = _witness_buffer(n, self.witnessSize * 32)
         status = np.zeros(n, np.uint8)
         pub = np.zeros((n, self.nPublic), np.uint32)
         _lib.check(self._L.b3w_multi_witness_batch(self._m, rows.ctypes.data, n, out.ctypes.data if want_witness else None,

@@ -101,7 +101,7 @@ static napi_value WtnsHeader(napi_env env, napi_callback_info info) {
 struct job {
   napi_async_work work; napi_deferred deferred;
   b3w_ctx *ctx; uint32_t circuit; uint32_t *rows; uint8_t *fr; uint64_t n; b3w_info bi;
-  uint8_t *out, *status; uint32_t *pub; bool one; int rc; char err[512];
+  uint8_t *out, *status; uint32_t *pub; bool one, out_pinned; int rc; char err[512];
 };
 static void job_run(napi_env, void *data) {
   job *j = (job *)data;
@@ -119,6 +119,20 @@ static void job_run(napi_env, void *data) {
   }
 }
 static void job_free_buf(napi_env, void *data, void *) { free(data); }
+// Witness buffers of large batches are PINNED host memory (b3w_host_alloc): the device-to-host copy of a pageable buffer
+// runs at a fraction of the PCIe rate and cannot overlap the next chunk's kernel.  Small ones (a single witness is
+// 771 KB) stay on malloc, which is cheaper than pinning.
+#define PINNED_FROM ((size_t)32 << 20)
+static uint8_t *out_alloc(size_t bytes, bool *pinned) {
+  *pinned = bytes >= PINNED_FROM;
+  if (*pinned) {
+    uint8_t *p = (uint8_t *)b3w_host_alloc(bytes);
+    if (p) return p;
+    *pinned = false;                                   // pinning can fail (locked-memory limit): fall back to pageable
+  }
+  return (uint8_t *)malloc(bytes ? bytes : 1);
+}
+static void job_free_pinned(napi_env, void *data, void *) { b3w_host_free(data); }
 static void job_done(napi_env env, napi_status, void *data) {
   job *j = (job *)data;
   napi_value res, v, ab;
@@ -126,10 +140,11 @@ static void job_done(napi_env env, napi_status, void *data) {
     napi_value msg; napi_create_string_utf8(env, j->err, NAPI_AUTO_LENGTH, &msg);
     napi_create_error(env, NULL, msg, &res);
     napi_reject_deferred(env, j->deferred, res);
-    free(j->out); free(j->status); free(j->pub);
+    if (j->out_pinned) b3w_host_free(j->out); else free(j->out);
+    free(j->status); free(j->pub);
   } else if (j->one) {
     size_t wb = (size_t)j->bi.witness_size * 32;
-    napi_create_external_arraybuffer(env, j->out, wb, job_free_buf, NULL, &ab);
+    napi_create_external_arraybuffer(env, j->out, wb, j->out_pinned ? job_free_pinned : job_free_buf, NULL, &ab);
     napi_create_typedarray(env, napi_uint8_array, wb, ab, 0, &res);
     napi_resolve_deferred(env, j->deferred, res);
     free(j->status); free(j->pub);
@@ -137,7 +152,7 @@ static void job_done(napi_env env, napi_status, void *data) {
     napi_create_object(env, &res);
     if (j->out) {
       size_t wb = (size_t)j->n * j->bi.witness_size * 32;
-      napi_create_external_arraybuffer(env, j->out, wb, job_free_buf, NULL, &ab);
+      napi_create_external_arraybuffer(env, j->out, wb, j->out_pinned ? job_free_pinned : job_free_buf, NULL, &ab);
       napi_create_typedarray(env, napi_uint8_array, wb, ab, 0, &v);
     } else napi_get_null(env, &v);
     napi_set_named_property(env, res, "witness", v);
@@ -186,7 +201,12 @@ static napi_value start_job(napi_env env, napi_callback_info info, bool one, boo
   }
   j->status = (uint8_t *)calloc(j->n ? j->n : 1, 1);
   j->pub = (uint32_t *)calloc((j->n ? j->n : 1) * 16, 4);
-  j->out = want ? (uint8_t *)malloc((size_t)(j->n ? j->n : 1) * j->bi.witness_size * 32) : NULL;
+  j->out = want ? out_alloc((size_t)(j->n ? j->n : 1) * j->bi.witness_size * 32, &j->out_pinned) : NULL;
+  if (want && !j->out) {
+    free(j->rows); free(j->fr); free(j->status); free(j->pub); free(j);
+    napi_throw_error(env, NULL, "out of host memory for the witness buffer");
+    return NULL;
+  }
   napi_value promise, name;
   NAPI_OK(napi_create_promise(env, &j->deferred, &promise));
   NAPI_OK(napi_create_string_utf8(env, "b3w_witness_batch", NAPI_AUTO_LENGTH, &name));

@@ -19,4 +19,21 @@ for name, rows in (("blake3_compression", gen.splitmix_compression_inputs(70)), 
     if name != "blake3_compression":
         wc.novaChain(bytes(range(256)) * 13)
     wc.close()
+# the wide-domain kernels (blake3_compression with message words outside u32; plain and fused-check contexts)
+P = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+vals = []
+for i, r in enumerate(gen.splitmix_compression_inputs(48)):
+    v = [int(x) for x in r]
+    if i % 3 == 0:
+        v[8 + i % 16] = 2**32 + i
+    elif i % 3 == 1:
+        v[8 + i % 16] = P - 1 - i
+    if i % 11 == 0:
+        v[26] = 2**33                      # asserts
+    vals.append(v)
+for fused in (False, True):
+    wc = pkg.builder("blake3_compression", device=0, chunk=32, fused_check=fused)
+    res = wc.calculateWitnessBatchFr(vals)
+    assert set(np.unique(res["status"])) <= {0, 4}
+    wc.close()
 print("sanitize_run done")
