@@ -70,6 +70,7 @@ static int guarded(const char *what, F &&body) {
 }
 
 #include "kernels_witness.cuh"
+#include "kernels_nova_wide.cuh"
 #include "kernels_chain.cuh"
 #include "kernels_aux.cuh"
 #include "kernels_r1cs_staged.cuh"
@@ -155,6 +156,11 @@ struct b3w_ctx {
   int8_t *d_ext[2];          // compression only: m_ext of the chunk (wide batches)
   bool ring_ready;
   uint32_t m_slot0;          // compression only: witness slot of m[0] (the 16 m slots are consecutive)
+  // nova only, built on first use: the wide (field-element input) kernel's override list and input staging
+  uint2 *d_wslots;
+  uint32_t *d_lane_off;
+  uint8_t *d_fr;             // chunk x 32 x 32 bytes
+  bool nw_ready;
   void *cs_ptr[8];           // chain driver scratch (grow-only)
   size_t cs_cap[8];
   // staging for host-buffer batches of PACKED witnesses: 2 slots
@@ -295,6 +301,9 @@ extern "C" void b3w_destroy(b3w_ctx *c) {
   if (c->d_field) cudaFree(c->d_field);
   if (c->d_fslots) cudaFree(c->d_fslots);
   if (c->d_counters) cudaFree(c->d_counters);
+  if (c->d_wslots) cudaFree(c->d_wslots);
+  if (c->d_lane_off) cudaFree(c->d_lane_off);
+  if (c->d_fr) cudaFree(c->d_fr);
   for (b3w_ctx::r1cs_dev *r : {&c->r_slots, &c->r_fused}) free_r1cs_dev(r);
   free(c->h_desc);
   delete c;
@@ -737,6 +746,76 @@ extern "C" int b3w_inputs_from_fr(uint32_t circuit, const uint8_t *in_fr, uint64
   return B3W_OK;
 }
 
+// ---- nova step circuits on field-element inputs (kernels_nova_wide.cuh) ---------------------------------------------
+// trace words whose value is a function of a possibly field-valued input: the slots that read them through a W32 / W64 /
+// S64 / INV descriptor are rewritten by the wide kernel's override pass
+static bool nova_field_word(uint32_t t) {
+  return (t >= NV_IN && t < NV_IN + 32) || t == NV_LDM1 || t == NV_DP1 || t == NV_DEPTH_OUT || (t >= NV_NEG_DEPTH && t < NV_BC_OUT + 2) ||
+         (t >= NV_TMP_DOWN && t < NV_EQ_D + 128) || (t >= TR_IN + 8 && t < TR_IN + 24);
+}
+static int ensure_nova_wide(b3w_ctx *c) {
+  if (c->nw_ready) return B3W_OK;
+  const circuit_def *d = c->def;
+  std::vector<uint2> lanes[32];
+  for (uint32_t sl = 0; sl < d->ws; sl++) {
+    const uint32_t dsc = c->h_desc[sl], kind = dsc >> 24, t = dsc & 0xFFFFu;
+    if (kind >= DK_W32 && nova_field_word(t)) lanes[sl & 31].push_back(make_uint2(sl, dsc));
+    else if (kind >= DK_S64) return fail(B3W_ERR_INVALID, "slot table of %s: field slot %u is not covered by the wide kernel", d->name, sl);
+    // Num2Bits(65).out[64]: constant 0 for u32 inputs; present in the O1 build only, right after out[63]
+    if (dsc == ((DK_BIT << 24) | (31u << 16) | (NV_IN + 11)) && sl + 1 < d->ws && c->h_desc[sl + 1] == ((DK_W32 << 24) | TR_ZERO))
+      lanes[(sl + 1) & 31].push_back(make_uint2(sl + 1, DK_WIDE_BIT64 << 24));
+  }
+  std::vector<uint2> all;
+  uint32_t off[33];
+  for (int l = 0; l < 32; l++) {
+    off[l] = (uint32_t)all.size();
+    all.insert(all.end(), lanes[l].begin(), lanes[l].end());
+  }
+  off[32] = (uint32_t)all.size();
+  CK(cudaMalloc(&c->d_wslots, all.size() * sizeof(uint2) + 16));
+  CK(cudaMemcpy(c->d_wslots, all.data(), all.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&c->d_lane_off, sizeof off));
+  CK(cudaMemcpy(c->d_lane_off, off, sizeof off, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&c->d_fr, (size_t)c->chunk * 1024));
+  c->nw_ready = true;
+  return B3W_OK;
+}
+
+// fr: n x 32 canonical field elements (host).  One ring slot, chunk after chunk (this path is about coverage, not speed).
+static int nova_wide_chunks(b3w_ctx *c, const uint8_t *fr, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub) {
+  const circuit_def *d = c->def;
+  const size_t wbytes = (size_t)d->ws * 32;
+  cudaStream_t s = c->st[0];
+  const nova_wide_args wa{c->d_fr, c->d_wslots, c->d_lane_off, c->d_field};
+  for (uint64_t done = 0; done < n;) {
+    const uint64_t m = n - done < c->chunk ? n - done : c->chunk;
+    CK(cudaMemcpyAsync(c->d_fr, fr + done * 1024, (size_t)m * 1024, cudaMemcpyHostToDevice, s));
+    const uint64_t ctas = (m + NW_WARPS - 1) / NW_WARPS, cap = (uint64_t)c->sm_count * 8;
+    k_blake3_nova_witness_wide<<<(unsigned)(ctas < cap ? ctas : cap), NW_WARPS * 32, NW_WARPS * NW_STRIDE * 4, s>>>(
+        wa, m, c->d_desc, d->ws, c->d_ring[0], c->d_status[0], c->d_pub[0]);
+    CK(cudaGetLastError());
+    if (out) CK(cudaMemcpyAsync(out + done * wbytes, c->d_ring[0], (size_t)m * wbytes, cudaMemcpyDeviceToHost, s));
+    if (status) CK(cudaMemcpyAsync(status + done, c->d_status[0], (size_t)m, cudaMemcpyDeviceToHost, s));
+    if (pub) CK(cudaMemcpyAsync(pub + done * 15, c->d_pub[0], (size_t)m * 60, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    done += m;
+  }
+  return B3W_OK;
+}
+static int nova_wide_batch(b3w_ctx *c, const uint8_t *fr, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub) {
+  if (c->flags & B3W_FLAG_FUSED_CHECK)
+    return fail(B3W_ERR_UNSUPPORTED, "%s: the fused R1CS check covers u32 inputs; this batch holds field-valued ones", c->def->name);
+  CK(cudaSetDevice(c->device));
+  int rc = ensure_ring(c);
+  if (rc == B3W_OK) rc = ensure_nova_wide(c);
+  if (rc) return rc;
+  rc = nova_wide_chunks(c, fr, n, out, status, pub);
+  const cudaError_t e = cudaStreamSynchronize(c->st[0]);          // no copy into the caller's buffers outlives the call
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(B3W_ERR_CUDA, "b3w_witness_batch_fr: %s", cudaGetErrorString(e));
+  return B3W_OK;
+}
+
 static fr_t prime_of(const circuit_def *d) {
   fr_t p;
   memcpy(p.l, d->prime, 32);
@@ -788,10 +867,20 @@ static int b3w_witness_batch_fr_impl(b3w_ctx *c, const uint8_t *in_fr, uint64_t 
     rows.resize((size_t)n * c->def->n_inputs);
     if (!c->def->nova) ext.resize((size_t)n * 16);
   } catch (...) { return fail(B3W_ERR_NOMEM, "out of host memory"); }
-  if (c->def->nova) {                                       // nova: the u32 domain only
-    int rc = b3w_inputs_from_fr(circuit, in_fr, n, rows.data());
-    if (rc) return rc;
-    return b3w_witness_batch(c, rows.data(), n, out, status, pub);
+  if (c->def->nova) {
+    // u32 inputs (what every driver of the reference produces) take the hot kernels; a batch that holds anything else
+    // runs on the general kernel, which evaluates the nova-level logic on field elements
+    const fr_t p = prime_of(c->def);
+    std::vector<uint8_t> canon((size_t)n * 1024);
+    bool all_u32 = true;
+    for (uint64_t i = 0; i < n * 32; i++) {
+      const fr_t v = wd_load_reduced(in_fr + i * 32, p);
+      memcpy(canon.data() + i * 32, v.l, 32);
+      rows[i] = v.l[0];
+      all_u32 = all_u32 && wd_fits(v, 32);
+    }
+    if (all_u32) return b3w_witness_batch(c, rows.data(), n, out, status, pub);
+    return nova_wide_batch(c, canon.data(), n, out, status, pub);
   }
   uint64_t n_wide = 0;
   int rc = b3w_inputs_from_fr_wide(circuit, in_fr, n, rows.data(), ext.data(), &n_wide);
@@ -802,19 +891,19 @@ extern "C" int b3w_witness_batch_fr(b3w_ctx *c, const uint8_t *in_fr, uint64_t n
   return guarded("b3w_witness_batch_fr", [&]() { return b3w_witness_batch_fr_impl(c, in_fr, n, out, status, pub); });
 }
 
-// b3w_assert_trace for field-element inputs.  blake3_compression: any input (the range constraints are replayed in the
-// wasm's execution order, wide_domain.h); nova: inputs in the u32 domain.
+// b3w_assert_trace for field-element inputs, any values: the circuits' range constraints are replayed in the wasm's
+// execution order (wide_domain.h).
 extern "C" int b3w_assert_trace_fr(uint32_t circuit, const uint8_t *in_fr, char *buf, size_t cap) {
   const circuit_def *d = find_def(circuit);
   if (!d) return B3W_ERR_UNSUPPORTED;
   if (!in_fr || (!buf && cap)) return fail(B3W_ERR_INVALID, "b3w_assert_trace_fr: null argument");
   if (cap) buf[0] = 0;
-  if (d->nova) {
-    uint32_t row[32];
-    int rc = b3w_inputs_from_fr(circuit, in_fr, 1, row);
-    return rc ? rc : b3w_assert_trace(circuit, row, buf, cap);
-  }
   const fr_t p = prime_of(d);
+  if (d->nova) {
+    fr_t v[32];
+    for (int k = 0; k < 32; k++) v[k] = wd_load_reduced(in_fr + k * 32, p);
+    return wd_assert_text_nova(v, p, buf, cap) ? B3W_CIRCOM_ASSERT : B3W_OK;
+  }
   fr_t v[28];
   for (int k = 0; k < 28; k++) v[k] = wd_load_reduced(in_fr + k * 32, p);
   const wd_fail f = wd_first_assert_compression(v, p);

@@ -360,14 +360,15 @@ struct wide_args {
 };
 
 // Adds ext to the carry words of the 112 half-G records (APPLY) or only looks at them; true = some sum left [0, 2^34).
+// ext: 16 sign-extended words (the compression kernels keep them at trace + TR_EXT).
 template <bool APPLY>
-__device__ __forceinline__ bool wide_carries(uint32_t *trace, int lane) {
+__device__ __forceinline__ bool wide_carries_at(uint32_t *trace, const uint32_t *ext, int lane) {
   bool bad = false;
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     const int rec = lane + 32 * k;                 // record ((round * 8 + g) * 2 + half) adds msg[2g + half] of that round
     if (rec < 112) {
-      const int e = (int)trace[TR_EXT + MSG_SCHED[rec >> 4][rec & 15]];
+      const int e = (int)ext[MSG_SCHED[rec >> 4][rec & 15]];
       const int c = (int)trace[TR_HG + 8 * rec + 1] + e;
       bad = bad || c < 0 || c > 3;
       if (APPLY) trace[TR_HG + 8 * rec + 1] = (uint32_t)c;
@@ -375,6 +376,8 @@ __device__ __forceinline__ bool wide_carries(uint32_t *trace, int lane) {
   }
   return __any_sync(0xffffffffu, bad);
 }
+template <bool APPLY>
+__device__ __forceinline__ bool wide_carries(uint32_t *trace, int lane) { return wide_carries_at<APPLY>(trace, trace + TR_EXT, lane); }
 
 // The m slots of a wide instance inside [a, b): m mod p.  Each is rewritten by the lane that expand_slots used for it
 // (a is a multiple of 32), so the two stores to one address are ordered by program order.

@@ -18,6 +18,7 @@
 #include <stdio.h>
 #include <string.h>
 #include "fr.cuh"
+#include "nova_wide_logic.h"
 
 static inline fr_t wd_load_reduced(const uint8_t *le32, const fr_t &p) {
   fr_t v;
@@ -106,29 +107,76 @@ static inline wd_fail wd_first_assert_compression(const fr_t in[28], const fr_t 
   return wd_fail{0, 0, 0, 0};
 }
 
-// Template instance numbers and line numbers as compiled into build/blake3_compression/.../blake3_compression.wasm
-// (circom 2.1.6 numbers template instances in instantiation order; observed through the reference's own error path).
-static inline void wd_assert_text_compression(const wd_fail &f, char *buf, size_t cap) {
+// Template instance numbers and line numbers as compiled into the committed wasm files (circom 2.1.6 numbers template
+// instances in instantiation order; observed through the reference's own error path).  Stand-alone blake3_compression:
+// id_off = 0, line_off = 0, no suffix.  Inside the nova step circuits the same templates are instances 13 higher
+// (Bits34_14, ToBits_16, RotXorWordBits_18 / _20, HalfFunG_21.., SingleRound_49, XorWord2_52, Blake3Compression_53), the
+// Blake3Compression lines are one higher (the nova wasm files were compiled from a blake3_compression.circom with one more
+// line above the template body), and the stack ends in Blake3Nova_54 line 239 (`blake3Compression.t[0] <== ...`, the
+// component's last input); identical in all three nova builds.
+static inline void wd_assert_text_compression(const wd_fail &f, char *buf, size_t cap, int id_off = 0, int line_off = 0,
+                                              const char *suffix = "") {
   static const int HALF1[8] = {8, 15, 18, 21, 24, 27, 30, 33}, HALF2[8] = {13, 16, 19, 22, 25, 28, 31, 34},
                    MIX[8] = {14, 17, 20, 23, 26, 29, 32, 35};
   if (!cap) return;
   buf[0] = 0;
   if (f.kind == 0) return;
   if (f.kind == 4) {
-    snprintf(buf, cap, "Error in template ToBits_3 line: 153\nError in template XorWord2_39 line: 66\n"
-                       "Error in template Blake3Compression_40 line: 224\n");
+    snprintf(buf, cap, "Error in template ToBits_%d line: 153\nError in template XorWord2_%d line: 66\n"
+                       "Error in template Blake3Compression_%d line: %d\n%s", 3 + id_off, 39 + id_off, 40 + id_off, 224 + line_off, suffix);
     return;
   }
-  const int hid = f.half ? HALF2[f.g] : HALF1[f.g];
-  char head[160];
-  if (f.kind == 1) snprintf(head, sizeof head, "Error in template Bits34_1 line: 201\nError in template HalfFunG_%d line: 89\n", hid);
+  const int hid = (f.half ? HALF2[f.g] : HALF1[f.g]) + id_off;
+  char head[200];
+  if (f.kind == 1) snprintf(head, sizeof head, "Error in template Bits34_%d line: 201\nError in template HalfFunG_%d line: 89\n", 1 + id_off, hid);
   else if (f.kind == 2)
-    snprintf(head, sizeof head, "Error in template ToBits_3 line: 153\nError in template RotXorWordBits_5 line: 62\n"
-                                "Error in template HalfFunG_%d line: 91\n", hid);
+    snprintf(head, sizeof head, "Error in template ToBits_%d line: 153\nError in template RotXorWordBits_%d line: 62\n"
+                                "Error in template HalfFunG_%d line: 91\n", 3 + id_off, 5 + id_off, hid);
   else
-    snprintf(head, sizeof head, "Error in template ToBits_3 line: 153\nError in template RotXorWordBits_7 line: 62\n"
-                                "Error in template HalfFunG_%d line: 94\n", hid);
-  snprintf(buf, cap, "%sError in template MixFunG_%d line: %d\nError in template SingleRound_36 line: 156\n"
-                     "Error in template Blake3Compression_40 line: %d\n", head, MIX[f.g], f.half ? 121 : 116,
-           f.round == 0 ? 194 : 207);        // rounds[0].inp <== init (:194) / rounds[i].out ==> rounds[i + 1].inp (:207)
+    snprintf(head, sizeof head, "Error in template ToBits_%d line: 153\nError in template RotXorWordBits_%d line: 62\n"
+                                "Error in template HalfFunG_%d line: 94\n", 3 + id_off, 7 + id_off, hid);
+  // rounds[0].inp <== init (:194) / rounds[i].out ==> rounds[i + 1].inp (:207)
+  snprintf(buf, cap, "%sError in template MixFunG_%d line: %d\nError in template SingleRound_%d line: 156\n"
+                     "Error in template Blake3Compression_%d line: %d\n%s", head, MIX[f.g] + id_off, f.half ? 121 : 116, 36 + id_off,
+           40 + id_off, (f.round == 0 ? 194 : 207) + line_off, suffix);
+}
+
+// ---- nova step circuits: first failing constraint for ANY 32 field elements, and its text ---------------------------
+// Order (components run when their last input arrives): check_depth (:201 as built), final_m with down_left_path's
+// Num2Bits(65) (:221), then the embedded Blake3Compression (:239), which sees h_compression, final_m.out_m,
+// t = chunk_idx * (1 - is_parent), b and comp_d.out (circuits/blake3_nova.circom:222-245).
+static inline int wd_assert_text_nova(const fr_t in[32], const fr_t &p, char *buf, size_t cap) {
+  if (cap) buf[0] = 0;
+  const nova_wide_scalars s = nova_wide_scalar_logic(nw_in_array{in}, p);
+  const char *msg = nullptr;
+  if (s.fail == NW_FAIL_V1)
+    msg = "Error in template Num2Bits_2 line: 38\nError in template LessThan_3 line: 96\n"
+          "Error in template Blake3NovaTreePath_CheckDepth_5 line: 27\nError in template Blake3Nova_54 line: 201\n";
+  else if (s.fail == NW_FAIL_V2)
+    msg = "Error in template Num2Bits_2 line: 38\nError in template LessThan_3 line: 96\nError in template GreaterEqThan_4 line: 138\n"
+          "Error in template Blake3NovaTreePath_CheckDepth_5 line: 37\nError in template Blake3Nova_54 line: 201\n";
+  else if (s.fail == NW_FAIL_EXCEED)
+    msg = "Error in template Blake3NovaTreePath_CheckDepth_5 line: 38\nError in template Blake3Nova_54 line: 201\n";
+  else if (s.fail == NW_FAIL_N2B65)
+    msg = "Error in template Num2Bits_11 line: 38\nError in template Blake3GetDownLeftPath_12 line: 53\n"
+          "Error in template Blake3GetFinal_m_13 line: 96\nError in template Blake3Nova_54 line: 221\n";
+  if (msg) {
+    if (cap) snprintf(buf, cap, "%s", msg);
+    return 4;
+  }
+  static const uint32_t IV8[8] = {0x6A09E667u, 0xBB67AE85u, 0x3C6EF372u, 0xA54FF53Au, 0x510E527Fu, 0x9B05688Cu, 0x1F83D9ABu, 0x5BE0CD19u};
+  fr_t c[28];
+  for (int j = 0; j < 8; j++) c[j] = s.is_parent ? fr_from_u64(IV8[j]) : in[2 + j];                     // h_compression (:229-233)
+  for (uint32_t j = 0; j < 16; j++) {
+    const uint32_t om = nova_wide_select(j, s.is_parent, s.dlp).out_m;
+    c[8 + j] = om == NW_SEL_ZERO ? fr_zero() : in[om];
+  }
+  c[24] = s.not_parent ? in[10] : fr_zero();                                                            // t[0], t[1] (:244-245)
+  c[25] = s.not_parent ? in[11] : fr_zero();
+  c[26] = in[31];
+  c[27] = fr_from_u64(s.dflags);
+  const wd_fail f = wd_first_assert_compression(c, p);
+  if (f.kind == 0) return 0;
+  wd_assert_text_compression(f, buf, cap, 13, 1, "Error in template Blake3Nova_54 line: 239\n");
+  return 4;
 }

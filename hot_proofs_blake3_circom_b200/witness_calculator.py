@@ -14,9 +14,10 @@ parity tests are written against it the way the reference's tests use witness_ca
 Differences that are deliberate and loud:
   * `code` (the .wasm bytes) only selects the circuit (by sha256); an unknown wasm raises -- there is no
     WebAssembly engine here to fall back to.
-  * blake3_compression takes every input the reference takes (any field element: the circuit's own constraints
-    decide between a witness and "Assert Failed.", as in the wasm); the nova circuits cover their honest domain
-    [0, 2^32) after reduction mod p, anything else raises B3WError(B3W_ERR_DOMAIN) instead of being computed.
+  * every input the reference takes is taken (any field element: the circuit's own constraints decide between a
+    witness and "Assert Failed.", as in the wasm).  u32 inputs -- all that the reference's drivers produce -- run on
+    the hot kernels; field-valued ones go through b3w_witness_batch_fr (u32 row arrays stay u32: _row() raises
+    B3WError(B3W_ERR_DOMAIN) for anything else).
   * methods are plain (synchronous) functions.
 """
 import ctypes as C
@@ -227,8 +228,6 @@ class WitnessCalculator:
     def _do_calculate(self, inp):
         vals = self._values(inp)
         u32 = all(x >> 32 == 0 for x in vals)
-        if not u32 and self.circuit != 0:
-            self._row(inp)                            # raises B3W_ERR_DOMAIN naming the input (nova: u32 domain only)
         if self.circuit != 0:
             # the nova circuits execute log("D_FLAGS: ", D_FLAGS) once per witness (circuits/blake3_nova.circom:166);
             # witness_calculator.js:44-61 prints it with console.log.  The batched entry point stays silent.
@@ -239,7 +238,7 @@ class WitnessCalculator:
             rc = self._L.b3w_witness_one(self._h, row.ctypes.data, out.ctypes.data)
             trace = lambda: self.assertTrace(row)
         else:
-            # blake3_compression takes any field element (only the circuit's own constraints decide, as in the reference)
+            # any field element is an input (only the circuit's own constraints decide, as in the reference)
             fr = self._fr_bytes(vals)
             status = np.zeros(1, np.uint8)
             _lib.check(self._L.b3w_witness_batch_fr(self._h, fr.ctypes.data, 1, out.ctypes.data, status.ctypes.data, None))
@@ -298,7 +297,7 @@ class WitnessCalculator:
                 raise ValueError("expected an (n, %d) uint32 array" % self.nInputs)
         else:
             vals = [self._values(i) for i in inputs]
-            if self.circuit == 0 and any(x >> 32 for v in vals for x in v):
+            if any(x >> 32 for v in vals for x in v):
                 fr = self._fr_bytes([x for v in vals for x in v])          # field-element inputs: b3w_witness_batch_fr
                 rows = np.zeros((len(vals), self.nInputs), np.uint32)
             else:
@@ -319,7 +318,7 @@ class WitnessCalculator:
 
     def calculateWitnessBatchFr(self, values, want_witness=True):
         """values: (n, nInputs) Python ints / an (n, nInputs, 32) uint8 array of little-endian field elements.
-        blake3_compression: every input the reference accepts; nova: u32 values only (B3W_ERR_DOMAIN otherwise)."""
+        Every input the reference accepts; a nova batch that holds a value outside u32 runs on the general (slower) kernel."""
         if isinstance(values, np.ndarray) and values.dtype == np.uint8:
             fr = np.ascontiguousarray(values).reshape(-1)
             n = values.shape[0]

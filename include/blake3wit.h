@@ -26,7 +26,7 @@ extern "C" {
 #define B3W_ERR_INVALID (-1)     /* bad argument */
 #define B3W_ERR_CUDA (-2)        /* CUDA runtime error or no device; text in b3w_last_error() */
 #define B3W_ERR_NOMEM (-3)
-#define B3W_ERR_DOMAIN (-4)      /* an input is outside the supported domain (nova circuits: u32) */
+#define B3W_ERR_DOMAIN (-4)      /* b3w_inputs_from_fr: a value does not fit the u32 row format */
 #define B3W_ERR_UNSUPPORTED (-5)
 #define B3W_CIRCOM_ASSERT 4      /* "Assert Failed." (witness_calculator.js:29-30) */
 #define B3W_R1CS_VIOLATION 7     /* per-instance status of the on-device R1CS check: some row has A.z * B.z != C.z */
@@ -103,26 +103,31 @@ int b3w_witness_batch(b3w_ctx *ctx, const uint32_t *in, uint64_t n, uint8_t *out
  * `normalize`, witness_calculator.js:319-323) -- the form in which rust_fold holds them (`Vec<(String, Vec<F>)>`,
  * rust_fold/src/blake3_circuit.rs:197-289).  b3w_inputs_from_fr converts to the u32 rows of the other entry points
  * (host-only, needs no GPU); a value outside [0, 2^32) after reduction is refused with B3W_ERR_DOMAIN, naming the
- * instance and signal.  b3w_witness_batch_fr = convert + b3w_witness_batch (nova circuits; blake3_compression: see below). */
+ * instance and signal.  b3w_witness_batch_fr takes ANY field elements (see "The FULL input domain" below). */
 int b3w_inputs_from_fr(uint32_t circuit, const uint8_t *in_fr, uint64_t n, uint32_t *rows);
 int b3w_witness_batch_fr(b3w_ctx *ctx, const uint8_t *in_fr, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub);
 
-/* The FULL input domain of blake3_compression.  The reference takes any field element for every input
- * (witness_calculator.js:319-323) and lets the circuit decide: h, t, b, d pass through ToBits(32), so a value >= 2^32
- * ends in "Assert Failed."; the message words are not range-checked (circuits/blake3_compression.circom:169-170) and only
- * enter 34-bit sums, so e.g. m[0] = 2^32 or m[0] = p - 1 give VALID witnesses.  A satisfying input
- * therefore has message words m = ext * 2^32 + lo with ext in [-2, 3]:
+/* The FULL input domain.  The reference takes any field element for every input (witness_calculator.js:319-323) and lets
+ * the circuit decide.  b3w_witness_batch_fr (above) does the same for all four circuits: every input the reference accepts
+ * gives the reference's witness, every other one status 4 ("Assert Failed."), and b3w_assert_trace_fr the text the wasm
+ * prints for it.  u32 inputs -- everything the reference's drivers and tests produce -- stay on the hot kernels.
+ *
+ * blake3_compression: h, t, b, d pass through ToBits(32), so a value >= 2^32 asserts; the message
+ * words are not range-checked (circuits/blake3_compression.circom:169-170) and only enter 34-bit sums, so e.g.
+ * m[0] = 2^32 or m[0] = p - 1 give VALID witnesses.  A satisfying input has message words m = ext * 2^32 + lo, ext in [-2, 3]:
  *   b3w_inputs_from_fr_wide   Fr256 rows -> u32 rows (lo words) + m_ext (n x 16 int8).  Refuses nothing: an instance that
  *                             cannot satisfy the circuit gets m_ext[i][0] = B3W_EXT_ASSERT and comes back with status 4.
  *                             *n_wide (may be NULL) = instances that are not plain u32 rows.  Host-only, needs no GPU.
  *   b3w_witness_batch_wide / _device_wide   as b3w_witness_batch / b3w_witness_batch_device(_checked) with m_ext; the sums
  *                             that leave [0, 2^34) are detected on the device (status 4, no witness, pub = 0).  With
  *                             d_first_bad != NULL or B3W_FLAG_FUSED_CHECK the fused R1CS check runs as well.
- *   b3w_witness_batch_fr      (above) takes this path for blake3_compression, so it accepts every input the reference
- *                             accepts; for the nova circuits it still covers the u32 domain only (B3W_ERR_DOMAIN otherwise).
- *   b3w_assert_trace_fr       b3w_assert_trace for ONE Fr256 input row: the reference's per-template trace of the first
- *                             failing constraint in the wasm's execution order, e.g. for b = 2^33 "Error in template ToBits_3
- *                             line: 153\nError in template RotXorWordBits_5 line: 62\nError in template HalfFunG_18 line: 91\n...". */
+ * nova step circuits: as built they constrain little (leaf_depth - depth in [1, 256], chunk_idx_low + 2^32 chunk_idx_high
+ * < 2^65, and the embedded compression's ranges); n_blocks, block_count, total_depth, depth may be ANY field elements.  A
+ * batch that holds a value outside u32 runs on a general kernel that evaluates the nova-level logic on field elements
+ * (pub then holds the low 32 bits of the outputs; the fused-check flag is refused for such a batch).
+ *   b3w_assert_trace_fr       b3w_assert_trace for ONE Fr256 input row of any circuit: the reference's per-template trace of
+ *                             the first failing constraint in the wasm's execution order, e.g. for b = 2^33 "Error in template
+ *                             ToBits_3 line: 153\nError in template RotXorWordBits_5 line: 62\nError in template HalfFunG_18 line: 91\n...". */
 #define B3W_EXT_ASSERT 127
 int b3w_inputs_from_fr_wide(uint32_t circuit, const uint8_t *in_fr, uint64_t n, uint32_t *rows, int8_t *m_ext, uint64_t *n_wide);
 int b3w_witness_batch_wide(b3w_ctx *ctx, const uint32_t *in, const int8_t *m_ext, uint64_t n, uint8_t *out, uint8_t *status,

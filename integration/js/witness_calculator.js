@@ -5,9 +5,9 @@
 // programs).  A wasm it does not know falls through to the ORIGINAL WebAssembly implementation, which the caller
 // keeps as ./witness_calculator.wasm.js (the unmodified reference file); so does options.forceWasm.
 //
-// Input domain: blake3_compression takes every value the reference takes (field elements go to the library as Fr256,
-// b3w_witness_batch_fr).  The nova kernels cover the circuits' honest u32 domain; an input outside it is handed to the
-// reference's own wasm program (built lazily from the same `code`), so the drop-in never answers differently.
+// Input domain: every value the reference takes.  u32 inputs (all that the reference's drivers produce) go to the hot
+// kernels as one u32 row; anything else goes to the library as Fr256 (b3w_witness_batch_fr), which answers with the
+// reference's witness or the reference's "Assert Failed." text.
 //
 // NOTE: Node is not available in the build image of this repository, so this file is reviewed, not executed,
 // there; hot_proofs_blake3_circom_b200/witness_calculator.py mirrors it line by line and IS exercised by the tests.
@@ -27,14 +27,12 @@ module.exports = async function builder(code, options) {
         return require("./witness_calculator.wasm.js")(code, options);      // the reference path, untouched
     }
     const addon = require("./build/Release/blake3wit_napi.node");
-    return new WitnessCalculator(addon, addon.create(circuit, options.device === undefined ? -1 : options.device), circuit, options, code);
+    return new WitnessCalculator(addon, addon.create(circuit, options.device === undefined ? -1 : options.device), circuit, options);
 };
 
 class WitnessCalculator {
-    constructor(addon, ctx, circuit, sanityCheck, code) {
+    constructor(addon, ctx, circuit, sanityCheck) {
         this.addon = addon;
-        this.code = code;                          // kept for inputs outside the nova kernels' domain
-        this.wasmCalculator = null;
         this.instance = ctx;                       // the reference keeps the wasm instance here
         this.circuit = circuit;
         const info = addon.circuitInfo(circuit);   // b3w_circuit_info
@@ -84,15 +82,9 @@ class WitnessCalculator {
         return fr;
     }
 
-    async _wasm() {                                // the reference's own program, for inputs the nova kernels do not cover
-        if (!this.wasmCalculator) this.wasmCalculator = await require("./witness_calculator.wasm.js")(this.code, this.sanityCheck);
-        return this.wasmCalculator;
-    }
-
     async _bin(input) {
         const vals = this._values(input);
         const u32 = vals.every((v) => v >> 32n === 0n);
-        if (!u32 && this.circuit !== 0) return (await this._wasm()).calculateBinWitness(input, this.sanityCheck);
         if (this.circuit !== 0) console.log("D_FLAGS:  0");                 // circuits/blake3_nova.circom:166
         if (!u32) return await this.addon.witnessOneFr(this.instance, this._fr(vals));   // b3w_witness_batch_fr
         return await this.addon.witnessOne(this.instance, this._row(vals)); // napi_async_work around b3w_witness_batch
@@ -133,7 +125,6 @@ class WitnessCalculator {
         const n = inputs.length;
         const vals = inputs.map((inp) => this._values(inp));
         const u32 = vals.every((v) => v.every((x) => x >> 32n === 0n));
-        if (!u32 && this.circuit !== 0) throw new Error("calculateWitnessBatch: the nova circuits take u32 inputs (use calculateWitness for field-valued inputs)");
         if (!u32) return await this.addon.witnessBatchFr(this.instance, this._fr(vals.flat()), n, opts.witness !== false);
         const rows = new Uint32Array(n * this.nInputs);
         vals.forEach((v, i) => rows.set(this._row(v), i * this.nInputs));
