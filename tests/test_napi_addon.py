@@ -182,3 +182,25 @@ def test_field_element_inputs_and_assert_text_through_the_addon(napi, ctx):
     res = napi.await_(napi.call("witnessBatchFr", ctx, napi.typed(fr.reshape(-1)), napi.L.mk_u32(n), napi.L.mk_bool(1)))
     assert np.array_equal(napi.array_of(napi.get(res, "status")), status.astype(np.uint8))
     assert np.array_equal(napi.array_of(napi.get(res, "witness")).reshape(n, -1)[valid], want)
+
+
+@pytest.mark.gpu
+def test_nova_field_element_inputs_through_the_addon(napi):
+    """a nova context: field-valued n_blocks / depths give the reference's witness, a failing CheckDepth its text"""
+    wide = np.load(os.path.join(ROOT, "tests", "golden", "nova_wide_cases.npz"))
+    fr, status, valid, want, text = (wide["nova_pasta_o2" + k] for k in ("_fr", "_status", "_valid", "_witness", "_text"))
+    valid = list(valid)
+    h = napi.call("create", napi.L.mk_u32(2), napi.L.mk_i32(0))
+    seen = set()
+    for i in range(len(status)):
+        if status[i] in seen and i > 8:
+            continue
+        seen.add(int(status[i]))
+        call = napi.call("witnessOneFr", h, napi.typed(fr[i].reshape(-1)))
+        if status[i] == 0:
+            assert napi.array_of(napi.await_(call)).tobytes() == want[valid.index(i)].tobytes()
+        else:
+            with pytest.raises(RuntimeError) as e:
+                napi.await_(call)
+            assert str(e.value) == "Error: Assert Failed.\n" + bytes(text[i]).decode()
+    assert seen == {0, 4}

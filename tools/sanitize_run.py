@@ -36,4 +36,19 @@ for fused in (False, True):
     res = wc.calculateWitnessBatchFr(vals)
     assert set(np.unique(res["status"])) <= {0, 4}
     wc.close()
+# the general nova kernel (field-valued inputs), all three builds
+for name in ("blake3_nova", "blake3_nova_pasta", "blake3_nova_o1"):
+    wc = pkg.builder(name, device=0, chunk=16)
+    vals = [[int(x) for x in r] for r in gen.splitmix_nova_inputs(40)]
+    for i, v in enumerate(vals):
+        if i % 4 == 0:
+            v[0] = wc.prime - 3 - i                     # n_blocks: a field element
+        elif i % 4 == 1:
+            X = (0x123456789ABCDEF << 120) + i
+            v[14], v[12], v[13] = X, X + 1 + i % 200, X + 2 + i % 60
+        elif i % 4 == 2:
+            v[15 + i % 16] = 2**32 + i
+    res = wc.calculateWitnessBatchFr(vals)
+    assert set(np.unique(res["status"])) <= {0, 4}
+    wc.close()
 print("sanitize_run done")
