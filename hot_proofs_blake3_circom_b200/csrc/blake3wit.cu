@@ -141,6 +141,7 @@ struct b3w_ctx {
   bool r1cs_ready;
   struct r1cs_dev { r1cs_class_dev *cls; int64_t *lo, *hi; uint32_t *terms; uint32_t ncls; fr_t *coef_fr; uint32_t *row_ids, *nblk; uint32_t rows; } r_fused, r_slots;
   bool r1cs_loaded;          // r_slots comes from b3w_r1cs_load, not from the built-in tables
+  bool slots_staged;         // r_slots is in row-block form: evaluated by k_r1cs_check_staged (always true for loaded sets)
   uint32_t fault_word, fault_mask;
   int ctas_limit;           // tuning hook: cap on resident CTAs per SM (0 = occupancy limit)
   uint32_t sched_parts;     // work items per instance (0 = default)
@@ -450,7 +451,13 @@ static int upload_r1cs_set(b3w_ctx *c, const circuit_def::r1cs_set &set, b3w_ctx
 static int ensure_r1cs(b3w_ctx *c) {
   if (c->r1cs_ready) return B3W_OK;
   int rc = upload_r1cs_set(c, c->def->r_fused, &c->r_fused);
-  if (rc == B3W_OK && !c->r1cs_loaded) rc = upload_r1cs_set(c, c->def->r_slots, &c->r_slots);
+  if (rc == B3W_OK && !c->r1cs_loaded) {
+    // the built-in slot-space rows go through the staged evaluator too (witness streamed once into shared memory, 64-bit
+    // row arithmetic); B3W_STANDALONE_CHECK=warp keeps the older one-warp-per-instance evaluator for comparison
+    const char *e = getenv("B3W_STANDALONE_CHECK");
+    c->slots_staged = !(e && strcmp(e, "warp") == 0);
+    rc = upload_r1cs_set(c, c->def->r_slots, &c->r_slots, c->slots_staged);
+  }
   if (rc == B3W_OK) c->r1cs_ready = true;
   return rc;
 }
@@ -548,7 +555,7 @@ extern "C" int b3w_r1cs_check_device(b3w_ctx *c, const uint8_t *d_wit, uint64_t 
                 "O2-form system with b3w_r1cs_load (tools/export_r1cs.py writes it) or use the fused check", c->def->name);
   if (n == 0) return B3W_OK;
   r1cs_tables_dev T{c->r_slots.cls, c->r_slots.lo, c->r_slots.hi, c->r_slots.terms, c->r_slots.ncls, c->r_slots.coef_fr, c->r_slots.row_ids, c->r_slots.nblk};
-  if (!c->r1cs_loaded) {
+  if (!c->slots_staged) {
     // built-in rows (value kinds known offline: exact 64/128-bit integer classes + IsZero rows in Fr): one warp per instance
     uint64_t ctas = (n + 7) / 8, cap8 = (uint64_t)c->sm_count * 8;
     k_r1cs_check_witness<<<(unsigned)(ctas < cap8 ? ctas : cap8), 256, 0, (cudaStream_t)stream>>>(d_wit, n, c->def->ws, T, c->d_field,
@@ -605,6 +612,7 @@ static int b3w_r1cs_load_impl(b3w_ctx *c, const uint8_t *data, size_t len, uint3
   free_r1cs_dev(&c->r_slots);
   c->r_slots = d;
   c->r1cs_loaded = true;
+  c->slots_staged = true;
   if (n_rows) *n_rows = h.rows;
   return B3W_OK;
 }

@@ -29,6 +29,16 @@
 #define R1CS_FLAG_COEF64 128u /* slot-space sets: every coefficient of the class fits int64 (set by stg_blockify) */
 #define R1CS_FLAG_MATRIX 256u /* slot-space sets: `terms` holds the [term][row] matrix of this class, not row blocks */
 #define R1CS_FLAG_BIGCOEF 64u /* loaded sets only: coefficients are full field elements, stored per class in coef_fr */
+#define R1CS_FLAG_FAST64 1024u /* slot-space sets: eligible for the 64-bit evaluator below (set by stg_blockify) */
+#define R1CS_FLAG_BOOLROW 512u /* slot-space sets: every row of the class is  (a x) * (b x - b w0) = 0, i.e. "x is 0 or 1" (set by stg_blockify) */
+// The 64-bit fast path.  Almost every term of these systems is (small coefficient) x (word) or (power of two) x (bit).
+// With every staged value below 2^40 in magnitude (checked while staging: STG_FAST_VMAX), a term whose coefficient is at
+// most 2^16 in magnitude is below 2^56, and a term with a larger coefficient (< 2^56: classes flagged FAST64 by the host)
+// is below 2^56 too PROVIDED its value is 0 or 1 -- which is tested per term.  A linear combination has at most
+// 64 terms, so it stays below 2^62 and plain int64 arithmetic is exact; a row that fails the per-term test (or meets a
+// genuine field element) is re-evaluated exactly in Fr.  One 128-bit product per row decides A*B == C.
+#define STG_FAST_VMAX 40
+#define STG_FAST_COEF 16
 
 struct StagedSrc {
   const uint64_t *val;       // shared: tag | payload per slot
@@ -77,6 +87,23 @@ __device__ __forceinline__ i128 staged_term(const StagedSrc &src, const r1cs_cla
   const uint32_t ci = (c.flags & R1CS_FLAG_ROWCOEF) ? c.coef_off + t * c.count + r : c.coef_off + t;
   if (c.flags & R1CS_FLAG_COEF64) return (i128)T.coef_lo[ci] * (i128)v;
   return (((i128)T.coef_hi[ci] << 64) | (i128)(uint64_t)T.coef_lo[ci]) * (i128)v;
+}
+
+// 64-bit term (see STG_FAST_*): `slow` turns true when the row has to be re-evaluated exactly
+__device__ __forceinline__ int64_t staged_term64(const StagedSrc &src, const r1cs_class_dev &c, const r1cs_tables_dev &T, uint32_t t, uint32_t r,
+                                                uint32_t wire, bool &slow) {
+  const uint64_t x = src.val[wire];
+  const uint64_t mag = x & STG_PAYLOAD;
+  const int64_t v = (x & STG_TAG_NEG) ? -(int64_t)mag : (int64_t)mag;
+  const uint32_t ci = (c.flags & R1CS_FLAG_ROWCOEF) ? c.coef_off + t * c.count + r : c.coef_off + t;
+  const int64_t co = T.coef_lo[ci];
+  const uint64_t aco = co < 0 ? (uint64_t)0 - (uint64_t)co : (uint64_t)co;
+  slow = slow || (x & STG_TAG_BIG) != 0 || ((aco >> STG_FAST_COEF) != 0 && mag > 1);
+  return co * v;
+}
+__device__ __forceinline__ bool staged_verdict64(const r1cs_class_dev &c, int64_t L0, int64_t L1, int64_t L2) {
+  if (c.nA == 0 || c.nB == 0) return L2 == 0;
+  return (i128)L0 * (i128)L1 == (i128)L2;
 }
 
 // verdict of one row from its three exact linear combinations (integer path), with the Fr fallback left to the caller
@@ -145,16 +172,23 @@ __device__ __forceinline__ uint32_t stg_ld_stream(const uint32_t *p) {
 // one block: lane = row.  The header is fetched 32 words at a time by the whole warp (one coalesced L2 access per 16
 // terms, the next chunk already in flight) and handed round with shuffles.  Returns the violated row's id (class order,
 // or the file's constraint index) or B3W_NO_ROW.
+template <bool FAST>
 __device__ __forceinline__ uint32_t staged_block(const StagedSrc &src, const r1cs_class_dev &c, const r1cs_tables_dev &T, const uint32_t *hdr,
                                                 uint32_t lane) {
+  typedef typename std::conditional<FAST, int64_t, i128>::type acc_t;
   const uint32_t nt = (uint32_t)c.nA + c.nB + c.nC, hw = 2u + 2u * nt, nchunks = (hw + 31u) >> 5;
   uint32_t h = lane < hw ? stg_ld_stream(hdr + lane) : 0u;
   const uint32_t row0 = __shfl_sync(0xffffffffu, h, 0), len = __shfl_sync(0xffffffffu, h, 1);
   const bool active = lane < len;
   const uint32_t ln = active ? lane : 0u;                   // idle lanes shadow row 0 of the block: every load stays in range
   const uint32_t r = row0 + ln;
-  i128 L0 = 0, L1 = 0, acc = 0;
-  bool ok = !(c.flags & R1CS_FLAG_BIGCOEF);
+  if (FAST && (c.flags & R1CS_FLAG_BOOLROW)) {              // "x is 0 or 1": the wire of the A term is all that matters
+    const uint32_t base = __shfl_sync(0xffffffffu, h, 2), step = __shfl_sync(0xffffffffu, h, 3);
+    if (!active || src.val[base + ln * step] < 2ull) return B3W_NO_ROW;
+    return T.row_ids ? T.row_ids[c.row_off + r] : c.row_off + r;
+  }
+  acc_t L0 = 0, L1 = 0, acc = 0;
+  bool ok = !(c.flags & R1CS_FLAG_BIGCOEF), slow = false;
   const uint32_t nAB = (uint32_t)c.nA + c.nB;
   for (uint32_t k = 0; k < nchunks; k++) {
     const uint32_t nxt = 32u * (k + 1u) + lane;
@@ -165,14 +199,21 @@ __device__ __forceinline__ uint32_t staged_block(const StagedSrc &src, const r1c
       const uint32_t base = __shfl_sync(0xffffffffu, h, l), step = __shfl_sync(0xffffffffu, h, l + 1u);
       if (t == c.nA) { L0 = acc; acc = 0; }               // part boundaries are warp-uniform
       if (t == nAB) { L1 = acc; acc = 0; }
-      acc += staged_term(src, c, T, t, r, base + ln * step, ok);
+      if (FAST) acc += (acc_t)staged_term64(src, c, T, t, r, base + ln * step, slow);
+      else acc += (acc_t)staged_term(src, c, T, t, r, base + ln * step, ok);
     }
     h = hn;
   }
   if (nt == c.nA) { L0 = acc; acc = 0; }
   if (nt == nAB) { L1 = acc; acc = 0; }
-  bool need_fr = !ok;
-  bool holds = ok && staged_int_verdict(c, L0, L1, acc, need_fr);
+  bool need_fr, holds;
+  if (FAST) {
+    need_fr = slow;
+    holds = !slow && staged_verdict64(c, (int64_t)L0, (int64_t)L1, (int64_t)acc);
+  } else {
+    need_fr = !ok;
+    holds = ok && staged_int_verdict(c, (i128)L0, (i128)L1, (i128)acc, need_fr);
+  }
   if (need_fr && active) holds = staged_row_fr(src, c, T, hdr, ln, r);
   if (holds || !active) return B3W_NO_ROW;
   return T.row_ids ? T.row_ids[c.row_off + r] : c.row_off + r;
@@ -181,25 +222,38 @@ __device__ __forceinline__ uint32_t staged_block(const StagedSrc &src, const r1c
 // MATRIX classes: rows whose columns are not affine over consecutive rows (blocks would hold ~2 rows: the 33..35-term
 // bit recompositions, whose gadget instances are unevenly spaced in the witness) keep one table entry per term per row;
 // lane = row, 32 rows per warp step whatever their wires are.
+template <bool FAST>
 __device__ __forceinline__ uint32_t staged_matrix_row(const StagedSrc &src, const r1cs_class_dev &c, const r1cs_tables_dev &T, uint32_t r0) {
+  typedef typename std::conditional<FAST, int64_t, i128>::type acc_t;
   const bool active = r0 < c.count;
   const uint32_t r = active ? r0 : c.count - 1u;
   const uint32_t *m = T.terms + c.term_off + r;
   const uint32_t nt = (uint32_t)c.nA + c.nB + c.nC, nAB = (uint32_t)c.nA + c.nB;
-  i128 L0 = 0, L1 = 0, acc = 0;
-  bool ok = !(c.flags & R1CS_FLAG_BIGCOEF);
+  acc_t L0 = 0, L1 = 0, acc = 0;
+  bool ok = !(c.flags & R1CS_FLAG_BIGCOEF), slow = false;
   uint32_t w = stg_ld_stream(m);
+  if (FAST && (c.flags & R1CS_FLAG_BOOLROW)) {
+    if (!active || src.val[w] < 2ull) return B3W_NO_ROW;
+    return T.row_ids ? T.row_ids[c.row_off + r] : c.row_off + r;
+  }
   for (uint32_t t = 0; t < nt; t++) {
     const uint32_t wn = t + 1u < nt ? stg_ld_stream(m + (size_t)(t + 1u) * c.count) : 0u;      // next term's wire in flight
     if (t == c.nA) { L0 = acc; acc = 0; }
     if (t == nAB) { L1 = acc; acc = 0; }
-    acc += staged_term(src, c, T, t, r, w, ok);
+    if (FAST) acc += (acc_t)staged_term64(src, c, T, t, r, w, slow);
+    else acc += (acc_t)staged_term(src, c, T, t, r, w, ok);
     w = wn;
   }
   if (nt == c.nA) { L0 = acc; acc = 0; }
   if (nt == nAB) { L1 = acc; acc = 0; }
-  bool need_fr = !ok;
-  bool holds = ok && staged_int_verdict(c, L0, L1, acc, need_fr);
+  bool need_fr, holds;
+  if (FAST) {
+    need_fr = slow;
+    holds = !slow && staged_verdict64(c, (int64_t)L0, (int64_t)L1, (int64_t)acc);
+  } else {
+    need_fr = !ok;
+    holds = ok && staged_int_verdict(c, (i128)L0, (i128)L1, (i128)acc, need_fr);
+  }
   if (need_fr && active) holds = staged_row_fr(src, c, T, nullptr, 0, r);
   if (holds || !active) return B3W_NO_ROW;
   return T.row_ids ? T.row_ids[c.row_off + r] : c.row_off + r;
@@ -211,7 +265,7 @@ k_r1cs_check_staged(const uint8_t *__restrict__ wit, uint64_t n, uint32_t ws, co
   extern __shared__ __align__(16) uint8_t s_raw[];
   uint64_t *val = reinterpret_cast<uint64_t *>(s_raw);
   uint32_t *big = reinterpret_cast<uint32_t *>(s_raw + (size_t)((ws + 1) & ~1u) * 8);
-  __shared__ uint32_t s_nbig, s_bad, s_noncanon;
+  __shared__ uint32_t s_nbig, s_bad, s_noncanon, s_large;
   __shared__ r1cs_class_dev s_cls[STG_MAX_CLASSES];
   __shared__ uint32_t s_nblk[STG_MAX_CLASSES];
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -221,7 +275,7 @@ k_r1cs_check_staged(const uint8_t *__restrict__ wit, uint64_t n, uint32_t ws, co
   for (int j = 0; j < 8; j++) p.l[j] = F->p.l[j];
   for (uint64_t i = blockIdx.x; i < n; i += gridDim.x) {
     __syncthreads();                                        // the previous instance's rows are done with val / big
-    if (tid == 0) { s_nbig = 0; s_bad = B3W_NO_ROW; s_noncanon = 0; }
+    if (tid == 0) { s_nbig = 0; s_bad = B3W_NO_ROW; s_noncanon = 0; s_large = 0; }
     __syncthreads();
     // ---- phase 1: stream the witness once (4 slots per thread in flight), keep 8 bytes per slot ----
     const uint4 *w = reinterpret_cast<const uint4 *>(wit + i * (uint64_t)ws * 32);
@@ -240,6 +294,7 @@ k_r1cs_check_staged(const uint8_t *__restrict__ wit, uint64_t n, uint32_t ws, co
         uint64_t v;
         if ((a[u].z | a[u].w | b[u].x | b[u].y | b[u].z | b[u].w) == 0 && (a[u].y >> 30) == 0) {
           v = ((uint64_t)a[u].y << 32) | a[u].x;
+          if (a[u].y >> (STG_FAST_VMAX - 32)) atomicOr(&s_large, 1u);
         } else {
           fr_t x, d;
           x.l[0] = a[u].x; x.l[1] = a[u].y; x.l[2] = a[u].z; x.l[3] = a[u].w;
@@ -248,6 +303,7 @@ k_r1cs_check_staged(const uint8_t *__restrict__ wit, uint64_t n, uint32_t ws, co
           if (borrow || fr_is_zero(d)) atomicOr(&s_noncanon, 1u);      // x >= p: not a canonical field element
           if (!borrow && (d.l[2] | d.l[3] | d.l[4] | d.l[5] | d.l[6] | d.l[7]) == 0 && (d.l[1] >> 30) == 0) {
             v = STG_TAG_NEG | ((uint64_t)d.l[1] << 32) | d.l[0];
+            if (d.l[1] >> (STG_FAST_VMAX - 32)) atomicOr(&s_large, 1u);
           } else {
             const uint32_t k = atomicAdd(&s_nbig, 1u);
             v = STG_TAG_BIG | k;
@@ -267,14 +323,21 @@ k_r1cs_check_staged(const uint8_t *__restrict__ wit, uint64_t n, uint32_t ws, co
     } else if (!s_noncanon && !STG_EXP_SKIP_P2) {
       // ---- phase 2: every row from shared memory, one block of <= 32 rows per warp step ----
       const StagedSrc src{val, big, F};
+      // the 64-bit path needs every small value below 2^STG_FAST_VMAX and wire 0 to be the constant 1 (BOOLROW classes
+      // rely on it); classes with wide coefficients keep the 128-bit evaluator
+      const bool fast_ok = !s_large && val[0] == 1ull;
       for (uint32_t ci = 0; ci < T.n_classes; ci++) {
         const r1cs_class_dev c = s_cls[ci];
         const uint32_t nb = s_nblk[ci], hw = 2u + 2u * (c.nA + c.nB + c.nC);
+        const bool fast = fast_ok && (c.flags & R1CS_FLAG_FAST64);
         if (c.flags & R1CS_FLAG_MATRIX) {
-          for (uint32_t r = tid; r < ((c.count + 31u) & ~31u); r += STG_THREADS) bad = min(bad, staged_matrix_row(src, c, T, r));
+          for (uint32_t r = tid; r < ((c.count + 31u) & ~31u); r += STG_THREADS)
+            bad = min(bad, fast ? staged_matrix_row<true>(src, c, T, r) : staged_matrix_row<false>(src, c, T, r));
         } else {
-          for (uint32_t b = warp; b < nb; b += STG_THREADS / 32)
-            bad = min(bad, staged_block(src, c, T, T.terms + c.term_off + (size_t)b * hw, lane));
+          for (uint32_t b = warp; b < nb; b += STG_THREADS / 32) {
+            const uint32_t *hdr = T.terms + c.term_off + (size_t)b * hw;
+            bad = min(bad, fast ? staged_block<true>(src, c, T, hdr, lane) : staged_block<false>(src, c, T, hdr, lane));
+          }
         }
       }
     }

@@ -8,6 +8,7 @@
 #pragma once
 #include <map>
 #include <vector>
+#include <stdint.h>
 
 struct r1cs_host_set {
   std::vector<r1cs_class_dev> cls;
@@ -182,9 +183,27 @@ static void stg_blockify(std::vector<r1cs_class_dev> &cls, const std::vector<uin
     const uint32_t *m = terms.data() + c.term_off;
     if (!(c.flags & R1CS_FLAG_BIGCOEF)) {
       const size_t ncoef = (c.flags & R1CS_FLAG_ROWCOEF) ? (size_t)nt * c.count : nt;
-      bool fits = true;
-      for (size_t i = 0; i < ncoef && fits; i++) fits = hi[c.coef_off + i] == (lo[c.coef_off + i] < 0 ? -1 : 0);
+      bool fits = true, fits56 = true;
+      for (size_t i = 0; i < ncoef && fits; i++) {
+        const int64_t l = lo[c.coef_off + i];
+        fits = hi[c.coef_off + i] == (l < 0 ? -1 : 0);
+        fits56 = fits56 && fits && l > -(1ll << 56) && l < (1ll << 56);
+      }
       if (fits) c.flags |= R1CS_FLAG_COEF64;
+      // the 64-bit evaluator (kernels_r1cs_staged.cuh, STG_FAST_*): <= 64 terms of < 2^56 each stay below 2^62
+      if (fits && fits56 && c.nA <= 64 && c.nB <= 64 && c.nC <= 64) c.flags |= R1CS_FLAG_FAST64;
+      // booleanity rows  (a x) * (b x - b w0) = 0  with w0 = wire 0, the constant 1:  "x is 0 or 1"
+      if (fits && c.nA == 1 && c.nB == 2 && c.nC == 0 && c.count) {
+        bool boolrow = true;
+        for (uint32_t r = 0; r < c.count && boolrow; r++) {
+          auto co = [&](uint32_t t) { return lo[c.coef_off + ((c.flags & R1CS_FLAG_ROWCOEF) ? (size_t)t * c.count + r : t)]; };
+          const uint32_t x = m[r], w1 = m[(size_t)c.count + r], w2 = m[(size_t)2 * c.count + r];
+          const int64_t a = co(0), b1 = co(1), b2 = co(2);
+          const bool fwd = w1 == x && w2 == 0, rev = w2 == x && w1 == 0;        // which B term is x, which is the constant
+          boolrow = x != 0 && a != 0 && b1 != 0 && b1 == -b2 && b1 != INT64_MIN && (fwd || rev);
+        }
+        if (boolrow) c.flags |= R1CS_FLAG_BOOLROW;
+      }
     }
     if (blocks.size() & 1) blocks.push_back(0);
     std::vector<uint32_t> mine;
