@@ -392,70 +392,77 @@ extern "C" int b3w_assert_trace(uint32_t circuit, const uint32_t *in, char *buf,
   return B3W_CIRCOM_ASSERT;
 }
 
-// Expand the class / coefficient / column tables of one R1CS row set (r1cs_tables.h) and upload them.
-static int upload_r1cs_set(b3w_ctx *c, const circuit_def::r1cs_set &set, b3w_ctx::r1cs_dev *out, bool as_blocks = false) {
+// Expand the class / coefficient / column tables of one R1CS row set (r1cs_tables.h): host only.
+struct r1cs_expanded {
+  std::vector<r1cs_class_dev> cls;
+  std::vector<int64_t> lo, hi;
+  std::vector<uint32_t> terms, nblk;     // terms: [class][term][row] matrices, or row blocks after stg_blockify (then nblk is set)
+};
+static bool expand_r1cs_set(const circuit_def::r1cs_set &set, r1cs_expanded &x, bool as_blocks) {
   const size_t ncls = set.ncls;
-  if (ncls == 0) return B3W_OK;
-  r1cs_class_dev *cls = (r1cs_class_dev *)calloc(ncls, sizeof *cls);
-  int64_t *lo = (int64_t *)calloc(set.ncoef, 8), *hi = (int64_t *)calloc(set.ncoef, 8);
-  uint32_t *td = (uint32_t *)calloc(set.terms, 4);
-  int rc = B3W_OK;
-  auto done = [&](int code) { free(cls); free(lo); free(hi); free(td); return code; };
-  if (!cls || !lo || !hi || !td) return done(fail(B3W_ERR_NOMEM, "out of host memory"));
-  for (size_t i = 0; i < set.ncoef; i++) { lo[i] = (int64_t)set.coef[i][0]; hi[i] = (int64_t)set.coef[i][1]; }
+  x.cls.resize(ncls);
+  x.lo.resize(set.ncoef);
+  x.hi.resize(set.ncoef);
+  x.terms.assign(set.terms, 0);
+  for (size_t i = 0; i < set.ncoef; i++) { x.lo[i] = (int64_t)set.coef[i][0]; x.hi[i] = (int64_t)set.coef[i][1]; }
   uint32_t term_off = 0, row_off = 0;
-  bool corrupt = false;
-  for (size_t k = 0; k < ncls && !corrupt; k++) {
+  for (size_t k = 0; k < ncls; k++) {
     const b3w_r1cs_class &s = set.cls[k];
-    cls[k] = r1cs_class_dev{s.nA, s.nB, s.nC, s.flags, s.count, s.coef_off, term_off, row_off};
+    x.cls[k] = r1cs_class_dev{s.nA, s.nB, s.nC, s.flags, s.count, s.coef_off, term_off, row_off};
     size_t pos = s.col_off;
-    for (uint32_t t = 0; t < (uint32_t)(s.nA + s.nB + s.nC) && !corrupt; t++) {
-      if (pos >= set.ncols || set.cols[pos].desc0 != 0xFFFFFFFFu || term_off + s.count > set.terms) { corrupt = true; break; }
+    for (uint32_t t = 0; t < (uint32_t)(s.nA + s.nB + s.nC); t++) {
+      if (pos >= set.ncols || set.cols[pos].desc0 != 0xFFFFFFFFu || term_off + s.count > set.terms) return false;
       uint32_t nruns = set.cols[pos++].count, w = 0;
-      for (uint32_t r = 0; r < nruns && !corrupt; r++, pos++)
+      for (uint32_t r = 0; r < nruns; r++, pos++)
         for (uint32_t j = 0; j < set.cols[pos].count; j++) {
-          if (w >= s.count) { corrupt = true; break; }
-          td[term_off + w++] = set.cols[pos].desc0 + j * (uint32_t)set.cols[pos].delta;
+          if (w >= s.count) return false;
+          x.terms[term_off + w++] = set.cols[pos].desc0 + j * (uint32_t)set.cols[pos].delta;
         }
-      if (w != s.count) corrupt = true;
+      if (w != s.count) return false;
       term_off += s.count;
     }
     row_off += s.count;
   }
-  if (corrupt || term_off != set.terms || row_off != set.rows) return done(fail(B3W_ERR_INVALID, "R1CS tables of %s are corrupt", c->def->name));
+  if (term_off != set.terms || row_off != set.rows) return false;
   // slot-space sets are evaluated block-wise by the staged checker: replace the term matrices by row blocks
-  std::vector<uint32_t> tvec(td, td + set.terms), nblk;
   if (as_blocks) {
-    std::vector<r1cs_class_dev> cv(cls, cls + ncls);
     std::vector<uint32_t> blocks;
-    stg_blockify(cv, std::vector<uint32_t>(td, td + set.terms), blocks, nblk, std::vector<int64_t>(lo, lo + set.ncoef),
-                 std::vector<int64_t>(hi, hi + set.ncoef));
-    memcpy(cls, cv.data(), ncls * sizeof *cls);
-    tvec.swap(blocks);
+    stg_blockify(x.cls, x.terms, blocks, x.nblk, x.lo, x.hi);
+    x.terms.swap(blocks);
   }
-  cudaError_t e = cudaMalloc(&out->cls, ncls * sizeof *cls);
-  if (e == cudaSuccess) e = cudaMalloc(&out->lo, set.ncoef * 8);
-  if (e == cudaSuccess) e = cudaMalloc(&out->hi, set.ncoef * 8);
-  if (e == cudaSuccess) e = cudaMalloc(&out->terms, tvec.size() * 4 + 16);
-  if (e == cudaSuccess && as_blocks) e = cudaMalloc(&out->nblk, nblk.size() * 4);
-  if (e == cudaSuccess) e = cudaMemcpy(out->cls, cls, ncls * sizeof *cls, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(out->lo, lo, set.ncoef * 8, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(out->hi, hi, set.ncoef * 8, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(out->terms, tvec.data(), tvec.size() * 4, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess && as_blocks) e = cudaMemcpy(out->nblk, nblk.data(), nblk.size() * 4, cudaMemcpyHostToDevice);
-  if (e != cudaSuccess) rc = fail(B3W_ERR_CUDA, "R1CS table upload: %s", cudaGetErrorString(e));
+  return true;
+}
+
+static int upload_r1cs_set(b3w_ctx *c, const circuit_def::r1cs_set &set, b3w_ctx::r1cs_dev *out, bool as_blocks = false) {
+  if (set.ncls == 0) return B3W_OK;
+  r1cs_expanded x;
+  if (!expand_r1cs_set(set, x, as_blocks)) return fail(B3W_ERR_INVALID, "R1CS tables of %s are corrupt", c->def->name);
+  const size_t ncls = x.cls.size();
+  cudaError_t e = cudaMalloc(&out->cls, ncls * sizeof(r1cs_class_dev));
+  if (e == cudaSuccess) e = cudaMalloc(&out->lo, x.lo.size() * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&out->hi, x.hi.size() * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&out->terms, x.terms.size() * 4 + 16);
+  if (e == cudaSuccess && as_blocks) e = cudaMalloc(&out->nblk, x.nblk.size() * 4);
+  if (e == cudaSuccess) e = cudaMemcpy(out->cls, x.cls.data(), ncls * sizeof(r1cs_class_dev), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(out->lo, x.lo.data(), x.lo.size() * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(out->hi, x.hi.data(), x.hi.size() * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(out->terms, x.terms.data(), x.terms.size() * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && as_blocks) e = cudaMemcpy(out->nblk, x.nblk.data(), x.nblk.size() * 4, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return fail(B3W_ERR_CUDA, "R1CS table upload: %s", cudaGetErrorString(e));
   out->ncls = (uint32_t)ncls;
-  return done(rc);
+  return B3W_OK;
 }
 
 static int ensure_r1cs(b3w_ctx *c) {
   if (c->r1cs_ready) return B3W_OK;
   int rc = upload_r1cs_set(c, c->def->r_fused, &c->r_fused);
   if (rc == B3W_OK && !c->r1cs_loaded) {
-    // the built-in slot-space rows go through the staged evaluator too (witness streamed once into shared memory, 64-bit
-    // row arithmetic); B3W_STANDALONE_CHECK=warp keeps the older one-warp-per-instance evaluator for comparison
+    // the built-in slot-space rows keep the one-warp-per-instance evaluator (value kinds known offline, IsZero rows as two
+    // Montgomery products): measured on B200 1.24 (compression) / 1.18 M witnesses/s (nova O1) against 1.22 / 0.41 M/s for
+    // the staged evaluator, whose generic Fr fallback is slow on nova's field-valued slots.  B3W_STANDALONE_CHECK=staged
+    // routes them through the staged evaluator (experiments, profiles/r01i_r1cs_check.jsonl).
     const char *e = getenv("B3W_STANDALONE_CHECK");
-    c->slots_staged = !(e && strcmp(e, "warp") == 0);
+    c->slots_staged = e && strcmp(e, "staged") == 0;
     rc = upload_r1cs_set(c, c->def->r_slots, &c->r_slots, c->slots_staged);
   }
   if (rc == B3W_OK) c->r1cs_ready = true;

@@ -11,8 +11,11 @@
 // every term is small, Montgomery arithmetic in Fr otherwise (field-valued slots, coefficients that are not small
 // integers, products that could overflow) -- so ANY satisfied row is accepted and any violated row rejected, whatever
 // the values and coefficients are.  Measured on B200 (profiles/): phase 1 alone 6.9 M witnesses/s (5.4 TB/s of reads);
-// with phase 2, 0.9 M/s (compression, 24 544 rows) -- the row arithmetic (~100 warp instructions per term step) is the
-// bound, not memory.
+// with phase 2, 0.9 M/s with 128-bit row arithmetic throughout, 1.22 M/s (compression, 24 544 rows) since rows of small
+// coefficients run in 64-bit arithmetic and booleanity rows are a single comparison (STG_FAST_*, BOOLROW).  What is left
+// is latency: the witness copy takes 209 KB of shared memory, so one CTA per SM has to hide the L2 latency of the block
+// headers / term matrices (~1 200 warp steps per instance over 32 warps) by itself; rows that touch genuine field
+// elements (nova: ~200 slots) pay the generic Fr fallback (nova O1: 0.41 M/s).
 // Included by blake3wit.cu only, after r1cs.cuh.
 #pragma once
 
