@@ -145,3 +145,25 @@ def test_sass_streaming_stores_are_wide(built):
     assert len(na) > 10
     assert all(".256" in l or ".128" in l for l in na), [l for l in na if ".256" not in l and ".128" not in l][:3]
     assert sum(".256" in l for l in na) > 10
+
+
+def test_header_is_plain_c_and_links_from_c(built, tmp_path):
+    """the boundary is a C ABI: include/blake3wit.h compiles as strict C99 and a C program links against the library"""
+    import subprocess
+    src = tmp_path / "c_abi.c"
+    src.write_text('#include <stdio.h>\n#include <string.h>\n#include "blake3wit.h"\n'
+                   'int main(void) {\n'
+                   '  b3w_info i; unsigned char hdr[76]; uint32_t off, size;\n'
+                   '  if (b3w_version() != B3W_VERSION) return 1;\n'
+                   '  if (b3w_circuit_info(B3W_COMPRESSION, &i) != B3W_OK || i.witness_size != 24093u) return 2;\n'
+                   '  if (b3w_wtns_header(B3W_NOVA_PASTA_O2, hdr) != B3W_OK || memcmp(hdr, "wtns", 4) != 0) return 3;\n'
+                   '  if (b3w_input_signal(B3W_NOVA_BN_O2, "m", &off, &size) != B3W_OK || off != 15u || size != 16u) return 4;\n'
+                   '  if (b3w_input_signal(B3W_COMPRESSION, "nope", &off, &size) != B3W_ERR_INVALID) return 5;\n'
+                   '  printf("%s\\n", b3w_last_error());\n  return 0;\n}\n')
+    exe = tmp_path / "c_abi"
+    libdir = os.path.dirname(pkg.lib_path())
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                    "-L", libdir, "-lblake3wit", "-Wl,-rpath," + libdir, "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.returncode
+    assert "Signal nope not found" in r.stdout
