@@ -1,5 +1,5 @@
 """bench_configs.py -- measurements for the BASELINE configs that bench.py's single JSON line does not carry
-(configs[2..4]); one JSON line each, written for profiles/.  Not the driver's benchmark (that is bench.py)."""
+(configs[0], configs[2..4]); one JSON line each, written for profiles/.  Not the driver's benchmark (that is bench.py)."""
 import ctypes as C
 import json
 import os
@@ -32,6 +32,45 @@ def timed(f, reps=3, warm=1):
         f()
     torch.cuda.synchronize()
     return (time.perf_counter() - t) / reps
+
+
+def config1():
+    """BASELINE configs[0]: ONE witness from inputs/blake3_compression (the LCG(6429) golden input) -- what
+    `node generate_witness.js` does in the reference (0.25-0.35 s in its wasm).  Latency of the C ABI call and of the
+    calculateWTNSBin wrapper, plus the CPU reference (Oracle A) on the same input, one thread."""
+    wc = pkg.builder("blake3_compression", device=0)
+    row = gen.lcg_compression_inputs(1)[0]
+    inp = {"h": [int(x) for x in row[0:8]], "m": [int(x) for x in row[8:24]], "t": [0, 0], "b": 64, "d": 0}
+    golden = np.load(os.path.join(ROOT, "tests", "golden", "compression_golden.npz"))
+    assert wc.calculateWTNSBin(inp, 0).tobytes() == golden["wtns"].tobytes()
+    out = np.empty(wc.witnessSize * 32, np.uint8)
+    from hot_proofs_blake3_circom_b200.witness_calculator import pinned_array
+    out_p = pinned_array((wc.witnessSize * 32,), np.uint8)
+
+    def lat(f, reps=300):
+        for _ in range(20):
+            f()
+        ts = []
+        for _ in range(reps):
+            t = time.perf_counter()
+            f()
+            ts.append(time.perf_counter() - t)
+        return float(np.median(ts)), float(np.percentile(ts, 99))
+    abi = lat(lambda: _lib.check(L.b3w_witness_one(wc._h, row.ctypes.data, out.ctypes.data)))
+    abi_p = lat(lambda: _lib.check(L.b3w_witness_one(wc._h, row.ctypes.data, out_p.ctypes.data)))
+    api = lat(lambda: wc.calculateWTNSBin(inp, 0), reps=100)
+    line = {"config": "configs[0]: blake3_compression single witness (golden input), 1 B200", "witness_bytes": wc.witnessSize * 32,
+            "b3w_witness_one_median_us": abi[0] * 1e6, "b3w_witness_one_p99_us": abi[1] * 1e6,
+            "b3w_witness_one_pinned_out_median_us": abi_p[0] * 1e6,
+            "calculateWTNSBin_python_median_us": api[0] * 1e6,
+            "note": "host row in, 770 976-byte witness out (pageable / pinned buffer); byte-identical to the reference's witness.wtns"}
+    from oracle import ref_wasm
+    if ref_wasm.available("compression"):
+        ref = ref_wasm.RefWasm("compression")
+        _, st, secs = ref.batch_u32(gen.lcg_compression_inputs(4), nthreads=1, want_out=True)
+        line["reference_wasm_one_thread_ms"] = secs / 4 * 1e3
+    print(json.dumps(line), flush=True)
+    wc.close()
 
 
 def config3():
@@ -111,7 +150,9 @@ def config5():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["3", "4", "5"]
+    which = sys.argv[1:] or ["1", "3", "4", "5"]
+    if "1" in which:
+        config1()
     if "3" in which:
         config3()
     if "4" in which:
