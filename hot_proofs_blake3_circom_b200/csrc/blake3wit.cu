@@ -74,6 +74,7 @@ static int guarded(const char *what, F &&body) {
 #include "kernels_chain.cuh"
 #include "kernels_aux.cuh"
 #include "kernels_r1cs_staged.cuh"
+#include "kernels_r1cs_compact.cuh"
 #include "r1cs_load.h"
 #include "wide_domain.h"
 
@@ -141,7 +142,7 @@ struct b3w_ctx {
   bool r1cs_ready;
   struct r1cs_dev { r1cs_class_dev *cls; int64_t *lo, *hi; uint32_t *terms; uint32_t ncls; fr_t *coef_fr; uint32_t *row_ids, *nblk; uint32_t rows; } r_fused, r_slots;
   bool r1cs_loaded;          // r_slots comes from b3w_r1cs_load, not from the built-in tables
-  bool slots_staged;         // r_slots is in row-block form: evaluated by k_r1cs_check_staged (always true for loaded sets)
+  bool slots_staged;         // r_slots is in row-block form: evaluated by k_r1cs_check_compact / _staged (always true for loaded sets)
   uint32_t fault_word, fault_mask;
   int ctas_limit;           // tuning hook: cap on resident CTAs per SM (0 = occupancy limit)
   uint32_t sched_parts;     // work items per instance (0 = default)
@@ -462,7 +463,7 @@ static int ensure_r1cs(b3w_ctx *c) {
     // the staged evaluator, whose generic Fr fallback is slow on nova's field-valued slots.  B3W_STANDALONE_CHECK=staged
     // routes them through the staged evaluator (experiments, profiles/r01i_r1cs_check.jsonl).
     const char *e = getenv("B3W_STANDALONE_CHECK");
-    c->slots_staged = e && strcmp(e, "staged") == 0;
+    c->slots_staged = e && (strcmp(e, "staged") == 0 || strcmp(e, "compact") == 0);
     rc = upload_r1cs_set(c, c->def->r_slots, &c->r_slots, c->slots_staged);
   }
   if (rc == B3W_OK) c->r1cs_ready = true;
@@ -570,7 +571,20 @@ extern "C" int b3w_r1cs_check_device(b3w_ctx *c, const uint8_t *d_wit, uint64_t 
     CK(cudaGetLastError());
     return B3W_OK;
   }
-  // a loaded system: the general evaluator (one CTA per instance, witness staged in shared memory, Fr fallback)
+  // a loaded system: the general evaluators (one CTA per instance, Fr fallback)
+  const char *mode = getenv("B3W_STANDALONE_CHECK");
+  if (!(mode && strcmp(mode, "staged") == 0)) {
+    // compact shared-memory copy of the witness (2 bits per slot + a side table): several CTAs per SM
+    const uint32_t words = (c->def->ws + 31u) >> 5;
+    const size_t smem_c = (size_t)((3 * words + 2) & ~1u) * 4 + (size_t)CPT_SIDE_MAX * 8;
+    CK(cudaFuncSetAttribute(k_r1cs_check_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+    const uint64_t cap_c = (uint64_t)c->sm_count * CPT_CTAS_PER_SM;
+    k_r1cs_check_compact<<<(unsigned)(n < cap_c ? n : cap_c), CPT_THREADS, smem_c, (cudaStream_t)stream>>>(d_wit, n, c->def->ws, T, c->d_field,
+                                                                                                           d_status, d_first_bad);
+    CK(cudaGetLastError());
+    return B3W_OK;
+  }
+  // B3W_STANDALONE_CHECK=staged: witness staged with 8 bytes per slot, one CTA per SM (kept for comparison)
   const size_t smem = (size_t)((c->def->ws + 1) & ~1u) * 8 + (size_t)STG_MAX_BIG * 32;
   CK(cudaFuncSetAttribute(k_r1cs_check_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const uint64_t cap = (uint64_t)c->sm_count;

@@ -47,6 +47,7 @@ struct StagedSrc {
   const uint64_t *val;       // shared: tag | payload per slot
   const uint32_t *big;       // shared: 8 limbs per big value
   const field_consts *F;
+  __device__ __forceinline__ uint64_t get(uint32_t s) const { return val[s]; }      // tag | payload
   __device__ __forceinline__ bool small(uint32_t s, i128 &v) const {
     const uint64_t x = val[s];
     if (x & STG_TAG_BIG) return false;
@@ -82,9 +83,10 @@ __device__ __forceinline__ i128 staged_coef(const r1cs_class_dev &c, const r1cs_
 
 // coefficient * value of one term, exact in 128 bits.  COEF64 classes (every coefficient fits int64: all but the
 // 2^64 of Num2Bits(65)) need one 64x64->128 multiply; `ok` turns false when the slot holds a genuine field element.
-__device__ __forceinline__ i128 staged_term(const StagedSrc &src, const r1cs_class_dev &c, const r1cs_tables_dev &T, uint32_t t, uint32_t r,
+template <class Src>
+__device__ __forceinline__ i128 staged_term(const Src &src, const r1cs_class_dev &c, const r1cs_tables_dev &T, uint32_t t, uint32_t r,
                                            uint32_t wire, bool &ok) {
-  const uint64_t x = src.val[wire];
+  const uint64_t x = src.get(wire);
   ok = ok && !(x & STG_TAG_BIG);
   const int64_t v = (x & STG_TAG_NEG) ? -(int64_t)(x & STG_PAYLOAD) : (int64_t)(x & STG_PAYLOAD);
   const uint32_t ci = (c.flags & R1CS_FLAG_ROWCOEF) ? c.coef_off + t * c.count + r : c.coef_off + t;
@@ -93,9 +95,10 @@ __device__ __forceinline__ i128 staged_term(const StagedSrc &src, const r1cs_cla
 }
 
 // 64-bit term (see STG_FAST_*): `slow` turns true when the row has to be re-evaluated exactly
-__device__ __forceinline__ int64_t staged_term64(const StagedSrc &src, const r1cs_class_dev &c, const r1cs_tables_dev &T, uint32_t t, uint32_t r,
+template <class Src>
+__device__ __forceinline__ int64_t staged_term64(const Src &src, const r1cs_class_dev &c, const r1cs_tables_dev &T, uint32_t t, uint32_t r,
                                                 uint32_t wire, bool &slow) {
-  const uint64_t x = src.val[wire];
+  const uint64_t x = src.get(wire);
   const uint64_t mag = x & STG_PAYLOAD;
   const int64_t v = (x & STG_TAG_NEG) ? -(int64_t)mag : (int64_t)mag;
   const uint32_t ci = (c.flags & R1CS_FLAG_ROWCOEF) ? c.coef_off + t * c.count + r : c.coef_off + t;
@@ -139,7 +142,8 @@ __device__ __forceinline__ uint32_t stg_row_wire(const r1cs_class_dev &c, const 
 
 // exact evaluation of one row in Fr (slow path: a term is a genuine field element, the coefficients are, or the integer
 // product could overflow)
-__device__ __noinline__ bool staged_row_fr(const StagedSrc &src, const r1cs_class_dev &c, const r1cs_tables_dev &T, const uint32_t *hdr,
+template <class Src>
+__device__ __noinline__ bool staged_row_fr(const Src &src, const r1cs_class_dev &c, const r1cs_tables_dev &T, const uint32_t *hdr,
                                            uint32_t lane, uint32_t r) {
   const field_consts &F = *src.F;
   const uint32_t n[3] = {c.nA, c.nB, c.nC};
@@ -175,8 +179,8 @@ __device__ __forceinline__ uint32_t stg_ld_stream(const uint32_t *p) {
 // one block: lane = row.  The header is fetched 32 words at a time by the whole warp (one coalesced L2 access per 16
 // terms, the next chunk already in flight) and handed round with shuffles.  Returns the violated row's id (class order,
 // or the file's constraint index) or B3W_NO_ROW.
-template <bool FAST>
-__device__ __forceinline__ uint32_t staged_block(const StagedSrc &src, const r1cs_class_dev &c, const r1cs_tables_dev &T, const uint32_t *hdr,
+template <bool FAST, class Src>
+__device__ __forceinline__ uint32_t staged_block(const Src &src, const r1cs_class_dev &c, const r1cs_tables_dev &T, const uint32_t *hdr,
                                                 uint32_t lane) {
   typedef typename std::conditional<FAST, int64_t, i128>::type acc_t;
   const uint32_t nt = (uint32_t)c.nA + c.nB + c.nC, hw = 2u + 2u * nt, nchunks = (hw + 31u) >> 5;
@@ -187,7 +191,7 @@ __device__ __forceinline__ uint32_t staged_block(const StagedSrc &src, const r1c
   const uint32_t r = row0 + ln;
   if (FAST && (c.flags & R1CS_FLAG_BOOLROW)) {              // "x is 0 or 1": the wire of the A term is all that matters
     const uint32_t base = __shfl_sync(0xffffffffu, h, 2), step = __shfl_sync(0xffffffffu, h, 3);
-    if (!active || src.val[base + ln * step] < 2ull) return B3W_NO_ROW;
+    if (!active || src.get(base + ln * step) < 2ull) return B3W_NO_ROW;
     return T.row_ids ? T.row_ids[c.row_off + r] : c.row_off + r;
   }
   acc_t L0 = 0, L1 = 0, acc = 0;
@@ -225,8 +229,8 @@ __device__ __forceinline__ uint32_t staged_block(const StagedSrc &src, const r1c
 // MATRIX classes: rows whose columns are not affine over consecutive rows (blocks would hold ~2 rows: the 33..35-term
 // bit recompositions, whose gadget instances are unevenly spaced in the witness) keep one table entry per term per row;
 // lane = row, 32 rows per warp step whatever their wires are.
-template <bool FAST>
-__device__ __forceinline__ uint32_t staged_matrix_row(const StagedSrc &src, const r1cs_class_dev &c, const r1cs_tables_dev &T, uint32_t r0) {
+template <bool FAST, class Src>
+__device__ __forceinline__ uint32_t staged_matrix_row(const Src &src, const r1cs_class_dev &c, const r1cs_tables_dev &T, uint32_t r0) {
   typedef typename std::conditional<FAST, int64_t, i128>::type acc_t;
   const bool active = r0 < c.count;
   const uint32_t r = active ? r0 : c.count - 1u;
@@ -236,7 +240,7 @@ __device__ __forceinline__ uint32_t staged_matrix_row(const StagedSrc &src, cons
   bool ok = !(c.flags & R1CS_FLAG_BIGCOEF), slow = false;
   uint32_t w = stg_ld_stream(m);
   if (FAST && (c.flags & R1CS_FLAG_BOOLROW)) {
-    if (!active || src.val[w] < 2ull) return B3W_NO_ROW;
+    if (!active || src.get(w) < 2ull) return B3W_NO_ROW;
     return T.row_ids ? T.row_ids[c.row_off + r] : c.row_off + r;
   }
   for (uint32_t t = 0; t < nt; t++) {

@@ -38,11 +38,14 @@ for name, gen in (("blake3_compression", lcg_compression_inputs), ("blake3_nova_
         assert int(d_st.max()) == 0
         out.update(hbm_check_ms=round(t_hbm, 3), hbm_check_wit_per_s=round(n / t_hbm * 1e3),
                    hbm_check_read_gbs=round(n * wc.witnessSize * 32 / t_hbm / 1e6))
-        os.environ["B3W_STANDALONE_CHECK"] = "staged"
-        wc2 = pkg.builder(name, device=0)
-        t_stg = timeit(lambda: wc2.r1cs_check_device(d_out.data_ptr(), n, d_st.data_ptr(), d_bad.data_ptr(), s))
-        del os.environ["B3W_STANDALONE_CHECK"]
-        out.update(hbm_check_staged_ms=round(t_stg, 3), hbm_check_staged_wit_per_s=round(n / t_stg * 1e3))
-        wc2.close()
+        for mode in ("compact", "staged"):
+            os.environ["B3W_STANDALONE_CHECK"] = mode
+            wc2 = pkg.builder(name, device=0)
+            t_m = timeit(lambda: wc2.r1cs_check_device(d_out.data_ptr(), n, d_st.data_ptr(), d_bad.data_ptr(), s))
+            assert int(d_st.max()) == 0
+            del os.environ["B3W_STANDALONE_CHECK"]
+            out.update({"hbm_check_%s_ms" % mode: round(t_m, 3), "hbm_check_%s_wit_per_s" % mode: round(n / t_m * 1e3),
+                        "hbm_check_%s_read_gbs" % mode: round(n * wc.witnessSize * 32 / t_m / 1e6)})
+            wc2.close()
     print(json.dumps(out), flush=True)
     del d_out; wc.close()
