@@ -12,8 +12,16 @@
 // a genuine field element is re-read from the witness in HBM when the Fr path needs it; a witness with more non-bit
 // slots than the side table holds (not one of these circuits' witnesses, but the checker must still answer) is
 // evaluated with every non-bit value converted from HBM on the fly.
+// Measured on B200 (profiles/r01i_r1cs_check.jsonl, 2^15 witnesses): streaming + classification alone 6.3 TB/s; with the
+// rows 1.57 M witnesses/s (compression, 24 544 rows; staged 1.20) and 0.87 M/s (nova O1; staged 0.41).  The generic row
+// arithmetic (117 760 terms per witness) is now 75 % of the time and issue-bound; prefetching the block headers or keeping
+// them in L1 changes nothing.  What would: recognising the XOR rows (2xy = x + y - o over bits) the way BOOLROW
+// recognises booleanity rows.
 #pragma once
 
+#ifndef CPT_EXP
+#define CPT_EXP 0                 /* experiment builds only: 1 = no row evaluation, 2 = pass A only */
+#endif
 #define CPT_THREADS 256
 #define CPT_SIDE_MAX 1536u        /* non-bit slots per witness in the side table (compression 713, nova O1 ~1 250) */
 
@@ -36,6 +44,8 @@ __device__ __forceinline__ uint64_t cpt_classify(const uint4 a, const uint4 b, u
 }
 
 struct CompactSrc {
+  // several CTAs per SM walk the same tables: let them live in L1 (about 170 KB are left next to 4 compact copies)
+  static __device__ __forceinline__ uint32_t ld_table(const uint32_t *p) { return __ldg(p); }
   const uint32_t *isbit, *bitval, *rank;     // shared: one bit per slot (x2), non-bit slots before each 32-slot word
   const uint64_t *side;                      // shared: tagged values of the non-bit slots, in slot order
   const uint4 *wit;                          // this instance's witness in HBM (2 x uint4 per slot)
@@ -130,7 +140,7 @@ k_r1cs_check_compact(const uint8_t *__restrict__ wit, uint64_t n, uint32_t ws, c
     const uint32_t n_side = rank[words];
     const bool side_ok = n_side <= CPT_SIDE_MAX;
     // ---- pass B: the non-bit slots again (3 % of the witness, L2 hits): classify, fill the side table ----
-    {
+    if (CPT_EXP < 2) {
       bool noncanon = false, large = false;
       for (uint32_t wd = warp; wd < words; wd += CPT_THREADS / 32) {
         const uint32_t m = ~isbit[wd];
@@ -144,7 +154,7 @@ k_r1cs_check_compact(const uint8_t *__restrict__ wit, uint64_t n, uint32_t ws, c
     }
     __syncthreads();
     uint32_t bad = B3W_NO_ROW;
-    if (!(s_flags & 1u)) {
+    if (!(s_flags & 1u) && CPT_EXP == 0) {
       // ---- every row from the compact copy, one block of <= 32 rows per warp step ----
       const CompactSrc src{isbit, bitval, rank, side, w, F, side_ok};
       const bool fast_ok = !(s_flags & 2u) && src.get(0) == 1ull;
@@ -158,6 +168,9 @@ k_r1cs_check_compact(const uint8_t *__restrict__ wit, uint64_t n, uint32_t ws, c
         } else {
           for (uint32_t b = warp; b < nb; b += CPT_THREADS / 32) {
             const uint32_t *hdr = T.terms + c.term_off + (size_t)b * hw;
+            // this warp's next header on its way into L1 while the current block is evaluated
+            if (b + CPT_THREADS / 32 < nb && lane * 32u < hw)
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(hdr + (size_t)(CPT_THREADS / 32) * hw + lane * 32u));
             bad = min(bad, fast ? staged_block<true>(src, c, T, hdr, lane) : staged_block<false>(src, c, T, hdr, lane));
           }
         }

@@ -43,7 +43,15 @@
 #define STG_FAST_VMAX 40
 #define STG_FAST_COEF 16
 
+// header words are streamed (each is used once per instance): keep them out of L1, where the coefficients live
+__device__ __forceinline__ uint32_t stg_ld_stream(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
 struct StagedSrc {
+  static __device__ __forceinline__ uint32_t ld_table(const uint32_t *p) { return stg_ld_stream(p); }     // row-block headers / term matrices
   const uint64_t *val;       // shared: tag | payload per slot
   const uint32_t *big;       // shared: 8 limbs per big value
   const field_consts *F;
@@ -169,13 +177,6 @@ __device__ __noinline__ bool staged_row_fr(const Src &src, const r1cs_class_dev 
   return eq;
 }
 
-// header words are streamed (each is used once per instance): keep them out of L1, where the coefficients live
-__device__ __forceinline__ uint32_t stg_ld_stream(const uint32_t *p) {
-  uint32_t v;
-  asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(v) : "l"(p));
-  return v;
-}
-
 // one block: lane = row.  The header is fetched 32 words at a time by the whole warp (one coalesced L2 access per 16
 // terms, the next chunk already in flight) and handed round with shuffles.  Returns the violated row's id (class order,
 // or the file's constraint index) or B3W_NO_ROW.
@@ -184,7 +185,7 @@ __device__ __forceinline__ uint32_t staged_block(const Src &src, const r1cs_clas
                                                 uint32_t lane) {
   typedef typename std::conditional<FAST, int64_t, i128>::type acc_t;
   const uint32_t nt = (uint32_t)c.nA + c.nB + c.nC, hw = 2u + 2u * nt, nchunks = (hw + 31u) >> 5;
-  uint32_t h = lane < hw ? stg_ld_stream(hdr + lane) : 0u;
+  uint32_t h = lane < hw ? Src::ld_table(hdr + lane) : 0u;
   const uint32_t row0 = __shfl_sync(0xffffffffu, h, 0), len = __shfl_sync(0xffffffffu, h, 1);
   const bool active = lane < len;
   const uint32_t ln = active ? lane : 0u;                   // idle lanes shadow row 0 of the block: every load stays in range
@@ -199,7 +200,7 @@ __device__ __forceinline__ uint32_t staged_block(const Src &src, const r1cs_clas
   const uint32_t nAB = (uint32_t)c.nA + c.nB;
   for (uint32_t k = 0; k < nchunks; k++) {
     const uint32_t nxt = 32u * (k + 1u) + lane;
-    const uint32_t hn = (k + 1u < nchunks && nxt < hw) ? stg_ld_stream(hdr + nxt) : 0u;
+    const uint32_t hn = (k + 1u < nchunks && nxt < hw) ? Src::ld_table(hdr + nxt) : 0u;
     const uint32_t t_lo = k == 0 ? 0u : 16u * k - 1u, t_hi = min(nt, 16u * k + 15u);
     for (uint32_t t = t_lo; t < t_hi; t++) {
       const uint32_t l = (2u + 2u * t) & 31u;
@@ -238,13 +239,13 @@ __device__ __forceinline__ uint32_t staged_matrix_row(const Src &src, const r1cs
   const uint32_t nt = (uint32_t)c.nA + c.nB + c.nC, nAB = (uint32_t)c.nA + c.nB;
   acc_t L0 = 0, L1 = 0, acc = 0;
   bool ok = !(c.flags & R1CS_FLAG_BIGCOEF), slow = false;
-  uint32_t w = stg_ld_stream(m);
+  uint32_t w = Src::ld_table(m);
   if (FAST && (c.flags & R1CS_FLAG_BOOLROW)) {
     if (!active || src.get(w) < 2ull) return B3W_NO_ROW;
     return T.row_ids ? T.row_ids[c.row_off + r] : c.row_off + r;
   }
   for (uint32_t t = 0; t < nt; t++) {
-    const uint32_t wn = t + 1u < nt ? stg_ld_stream(m + (size_t)(t + 1u) * c.count) : 0u;      // next term's wire in flight
+    const uint32_t wn = t + 1u < nt ? Src::ld_table(m + (size_t)(t + 1u) * c.count) : 0u;      // next term's wire in flight
     if (t == c.nA) { L0 = acc; acc = 0; }
     if (t == nAB) { L1 = acc; acc = 0; }
     if (FAST) acc += (acc_t)staged_term64(src, c, T, t, r, w, slow);
