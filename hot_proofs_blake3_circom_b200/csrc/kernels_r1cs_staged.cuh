@@ -33,6 +33,7 @@
 #define R1CS_FLAG_MATRIX 256u /* slot-space sets: `terms` holds the [term][row] matrix of this class, not row blocks */
 #define R1CS_FLAG_BIGCOEF 64u /* loaded sets only: coefficients are full field elements, stored per class in coef_fr */
 #define R1CS_FLAG_FAST64 1024u /* slot-space sets: eligible for the 64-bit evaluator below (set by stg_blockify) */
+#define R1CS_FLAG_XORROW 2048u /* slot-space sets: every row is  (a x)(b y) = k x + k y - k o  with  a b = 2 k: for bits, o = x xor y (set by stg_blockify) */
 #define R1CS_FLAG_BOOLROW 512u /* slot-space sets: every row of the class is  (a x) * (b x - b w0) = 0, i.e. "x is 0 or 1" (set by stg_blockify) */
 // The 64-bit fast path.  Almost every term of these systems is (small coefficient) x (word) or (power of two) x (bit).
 // With every staged value below 2^40 in magnitude (checked while staging: STG_FAST_VMAX), a term whose coefficient is at
@@ -193,6 +194,15 @@ __device__ __forceinline__ uint32_t staged_block(const Src &src, const r1cs_clas
   if (FAST && (c.flags & R1CS_FLAG_BOOLROW)) {              // "x is 0 or 1": the wire of the A term is all that matters
     const uint32_t base = __shfl_sync(0xffffffffu, h, 2), step = __shfl_sync(0xffffffffu, h, 3);
     if (!active || src.get(base + ln * step) < 2ull) return B3W_NO_ROW;
+    return T.row_ids ? T.row_ids[c.row_off + r] : c.row_off + r;
+  }
+  if (FAST && (c.flags & R1CS_FLAG_XORROW)) {               // terms: x | y | the three of {x, y, o} in some order (hw = 12)
+    uint32_t wv[5];
+#pragma unroll
+    for (int t = 0; t < 5; t++) wv[t] = __shfl_sync(0xffffffffu, h, 2 + 2 * t) + ln * __shfl_sync(0xffffffffu, h, 3 + 2 * t);
+    const uint64_t vx = src.get(wv[0]), vy = src.get(wv[1]), vo = src.get(wv[2] ^ wv[3] ^ wv[4] ^ wv[0] ^ wv[1]);
+    bool holds = (vx | vy | vo) < 2ull ? vo == (vx ^ vy) : staged_row_fr(src, c, T, hdr, ln, r);      // not all bits: exact evaluation
+    if (holds || !active) return B3W_NO_ROW;
     return T.row_ids ? T.row_ids[c.row_off + r] : c.row_off + r;
   }
   acc_t L0 = 0, L1 = 0, acc = 0;

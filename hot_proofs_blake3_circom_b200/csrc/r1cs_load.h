@@ -204,6 +204,29 @@ static void stg_blockify(std::vector<r1cs_class_dev> &cls, const std::vector<uin
         }
         if (boolrow) c.flags |= R1CS_FLAG_BOOLROW;
       }
+      // XOR rows  (a x)(b y) = k x + k y - k o  with a b = 2 k  (circom's  2 x y = x + y - out  for bit operands, any scaling
+      // or term order): over bits it says o = x xor y.  The device finds o as the C wire that is neither x nor y.
+      if (fits && c.nA == 1 && c.nB == 1 && c.nC == 3 && c.count) {
+        bool xorrow = true;
+        for (uint32_t r = 0; r < c.count && xorrow; r++) {
+          auto co = [&](uint32_t t) { return lo[c.coef_off + ((c.flags & R1CS_FLAG_ROWCOEF) ? (size_t)t * c.count + r : t)]; };
+          const uint32_t x = m[r], y = m[(size_t)c.count + r];
+          const int64_t a = co(0), b = co(1);
+          int64_t kx = 0, ky = 0, ko = 0;
+          uint32_t seen = 0, o = 0;
+          for (uint32_t t = 2; t < 5; t++) {
+            const uint32_t wq = m[(size_t)t * c.count + r];
+            if (wq == x && !(seen & 1u)) { kx = co(t); seen |= 1u; }
+            else if (wq == y && !(seen & 2u)) { ky = co(t); seen |= 2u; }
+            else if (!(seen & 4u)) { ko = co(t); o = wq; seen |= 4u; }
+            else seen |= 8u;
+          }
+          const bool small = a > -(1ll << 30) && a < (1ll << 30) && b > -(1ll << 30) && b < (1ll << 30);
+          xorrow = seen == 7u && x != y && o != x && o != y && x != 0 && y != 0 && o != 0 && small && kx != 0 && kx == ky &&
+                   ko == -kx && a * b == 2 * kx;
+        }
+        if (xorrow) c.flags |= R1CS_FLAG_XORROW;
+      }
     }
     if (blocks.size() & 1) blocks.push_back(0);
     std::vector<uint32_t> mine;
