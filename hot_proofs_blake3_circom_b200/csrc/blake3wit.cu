@@ -454,16 +454,19 @@ static int upload_r1cs_set(b3w_ctx *c, const circuit_def::r1cs_set &set, b3w_ctx
   return B3W_OK;
 }
 
+#ifndef B3W_BUILTIN_COMPACT
+#define B3W_BUILTIN_COMPACT(def) (!(def)->nova)
+#endif
 static int ensure_r1cs(b3w_ctx *c) {
   if (c->r1cs_ready) return B3W_OK;
   int rc = upload_r1cs_set(c, c->def->r_fused, &c->r_fused);
   if (rc == B3W_OK && !c->r1cs_loaded) {
-    // the built-in slot-space rows keep the one-warp-per-instance evaluator (value kinds known offline, IsZero rows as two
-    // Montgomery products): measured on B200 1.24 (compression) / 1.18 M witnesses/s (nova O1) against 1.22 / 0.41 M/s for
-    // the staged evaluator, whose generic Fr fallback is slow on nova's field-valued slots.  B3W_STANDALONE_CHECK=staged
-    // routes them through the staged evaluator (experiments, profiles/r01i_r1cs_check.jsonl).
+    // Built-in slot-space rows: two evaluators.  "warp" = one warp per instance reading the witness in place (value kinds
+    // known offline, IsZero rows as two Montgomery products); "compact" = the general evaluator of loaded systems on a
+    // compact shared-memory copy (kernels_r1cs_compact.cuh).  Default = whichever measured faster on B200
+    // (profiles/r01i_r1cs_check.jsonl); B3W_STANDALONE_CHECK=warp|compact|staged overrides.
     const char *e = getenv("B3W_STANDALONE_CHECK");
-    c->slots_staged = e && (strcmp(e, "staged") == 0 || strcmp(e, "compact") == 0);
+    c->slots_staged = e ? (strcmp(e, "staged") == 0 || strcmp(e, "compact") == 0) : B3W_BUILTIN_COMPACT(c->def);
     rc = upload_r1cs_set(c, c->def->r_slots, &c->r_slots, c->slots_staged);
   }
   if (rc == B3W_OK) c->r1cs_ready = true;

@@ -26,9 +26,8 @@
 #define CPT_SIDE_MAX 1536u        /* non-bit slots per witness in the side table (compression 713, nova O1 ~1 250) */
 
 // 32-byte slot -> tagged 8-byte value (the staged checker's encoding); BIG = "genuine field element", payload = slot index
-__device__ __forceinline__ uint64_t cpt_classify(const uint4 a, const uint4 b, uint32_t slot, const fr_t &p, bool &noncanon, bool &large) {
+__device__ __forceinline__ uint64_t cpt_classify(const uint4 a, const uint4 b, uint32_t slot, const fr_t &p, bool &noncanon) {
   if ((a.z | a.w | b.x | b.y | b.z | b.w) == 0 && (a.y >> 30) == 0) {
-    large = large || (a.y >> (STG_FAST_VMAX - 32)) != 0;
     return ((uint64_t)a.y << 32) | a.x;
   }
   fr_t x, d;
@@ -37,7 +36,6 @@ __device__ __forceinline__ uint64_t cpt_classify(const uint4 a, const uint4 b, u
   const uint32_t borrow = fr_raw_sub(d, p, x);               // p - x: a small negative integer stored canonically?
   noncanon = noncanon || borrow || fr_is_zero(d);            // x >= p: not a canonical field element
   if (!borrow && (d.l[2] | d.l[3] | d.l[4] | d.l[5] | d.l[6] | d.l[7]) == 0 && (d.l[1] >> 30) == 0) {
-    large = large || (d.l[1] >> (STG_FAST_VMAX - 32)) != 0;
     return STG_TAG_NEG | ((uint64_t)d.l[1] << 32) | d.l[0];
   }
   return STG_TAG_BIG | slot;
@@ -55,8 +53,8 @@ struct CompactSrc {
     const uint32_t w = s >> 5, b = s & 31u, m = isbit[w];
     if ((m >> b) & 1u) return (bitval[w] >> b) & 1u;
     if (side_ok) return side[rank[w] + __popc(~m & ((1u << b) - 1u))];
-    bool nc = false, lg = false;             // (a non-canonical slot was already reported by the classification pass)
-    return cpt_classify(__ldg(wit + 2 * s), __ldg(wit + 2 * s + 1), s, F->p, nc, lg);
+    bool nc = false;                         // (a non-canonical slot was already reported by the classification pass)
+    return cpt_classify(__ldg(wit + 2 * s), __ldg(wit + 2 * s + 1), s, F->p, nc);
   }
   __device__ __forceinline__ bool small(uint32_t s, i128 &v) const {
     const uint64_t x = get(s);
@@ -141,23 +139,22 @@ k_r1cs_check_compact(const uint8_t *__restrict__ wit, uint64_t n, uint32_t ws, c
     const bool side_ok = n_side <= CPT_SIDE_MAX;
     // ---- pass B: the non-bit slots again (3 % of the witness, L2 hits): classify, fill the side table ----
     if (CPT_EXP < 2) {
-      bool noncanon = false, large = false;
+      bool noncanon = false;
       for (uint32_t wd = warp; wd < words; wd += CPT_THREADS / 32) {
         const uint32_t m = ~isbit[wd];
         if (!((m >> lane) & 1u)) continue;
         const uint32_t s = wd * 32 + lane;
-        const uint64_t v = cpt_classify(__ldg(w + 2 * s), __ldg(w + 2 * s + 1), s, p, noncanon, large);
+        const uint64_t v = cpt_classify(__ldg(w + 2 * s), __ldg(w + 2 * s + 1), s, p, noncanon);
         if (side_ok) side[rank[wd] + __popc(m & ((1u << lane) - 1u))] = v;
       }
       if (noncanon) atomicOr(&s_flags, 1u);
-      if (large) atomicOr(&s_flags, 2u);
     }
     __syncthreads();
     uint32_t bad = B3W_NO_ROW;
     if (!(s_flags & 1u) && CPT_EXP == 0) {
       // ---- every row from the compact copy, one block of <= 32 rows per warp step ----
       const CompactSrc src{isbit, bitval, rank, side, w, F, side_ok};
-      const bool fast_ok = !(s_flags & 2u) && src.get(0) == 1ull;
+      const bool fast_ok = src.get(0) == 1ull;
       for (uint32_t ci = 0; ci < T.n_classes; ci++) {
         const r1cs_class_dev c = T.cls[ci];
         const uint32_t nb = T.cls_blocks[ci], hw = 2u + 2u * (c.nA + c.nB + c.nC);

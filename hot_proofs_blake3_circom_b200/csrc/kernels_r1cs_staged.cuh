@@ -36,7 +36,7 @@
 #define R1CS_FLAG_XORROW 2048u /* slot-space sets: every row is  (a x)(b y) = k x + k y - k o  with  a b = 2 k: for bits, o = x xor y (set by stg_blockify) */
 #define R1CS_FLAG_BOOLROW 512u /* slot-space sets: every row of the class is  (a x) * (b x - b w0) = 0, i.e. "x is 0 or 1" (set by stg_blockify) */
 // The 64-bit fast path.  Almost every term of these systems is (small coefficient) x (word) or (power of two) x (bit).
-// With every staged value below 2^40 in magnitude (checked while staging: STG_FAST_VMAX), a term whose coefficient is at
+// With a value below 2^40 in magnitude (STG_FAST_VMAX, tested per term), a term whose coefficient is at
 // most 2^16 in magnitude is below 2^56, and a term with a larger coefficient (< 2^56: classes flagged FAST64 by the host)
 // is below 2^56 too PROVIDED its value is 0 or 1 -- which is tested per term.  A linear combination has at most
 // 64 terms, so it stays below 2^62 and plain int64 arithmetic is exact; a row that fails the per-term test (or meets a
@@ -113,7 +113,7 @@ __device__ __forceinline__ int64_t staged_term64(const Src &src, const r1cs_clas
   const uint32_t ci = (c.flags & R1CS_FLAG_ROWCOEF) ? c.coef_off + t * c.count + r : c.coef_off + t;
   const int64_t co = T.coef_lo[ci];
   const uint64_t aco = co < 0 ? (uint64_t)0 - (uint64_t)co : (uint64_t)co;
-  slow = slow || (x & STG_TAG_BIG) != 0 || ((aco >> STG_FAST_COEF) != 0 && mag > 1);
+  slow = slow || (x & STG_TAG_BIG) != 0 || (mag >> STG_FAST_VMAX) != 0 || ((aco >> STG_FAST_COEF) != 0 && mag > 1);
   return co * v;
 }
 __device__ __forceinline__ bool staged_verdict64(const r1cs_class_dev &c, int64_t L0, int64_t L1, int64_t L2) {
@@ -283,7 +283,7 @@ k_r1cs_check_staged(const uint8_t *__restrict__ wit, uint64_t n, uint32_t ws, co
   extern __shared__ __align__(16) uint8_t s_raw[];
   uint64_t *val = reinterpret_cast<uint64_t *>(s_raw);
   uint32_t *big = reinterpret_cast<uint32_t *>(s_raw + (size_t)((ws + 1) & ~1u) * 8);
-  __shared__ uint32_t s_nbig, s_bad, s_noncanon, s_large;
+  __shared__ uint32_t s_nbig, s_bad, s_noncanon;
   __shared__ r1cs_class_dev s_cls[STG_MAX_CLASSES];
   __shared__ uint32_t s_nblk[STG_MAX_CLASSES];
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -293,7 +293,7 @@ k_r1cs_check_staged(const uint8_t *__restrict__ wit, uint64_t n, uint32_t ws, co
   for (int j = 0; j < 8; j++) p.l[j] = F->p.l[j];
   for (uint64_t i = blockIdx.x; i < n; i += gridDim.x) {
     __syncthreads();                                        // the previous instance's rows are done with val / big
-    if (tid == 0) { s_nbig = 0; s_bad = B3W_NO_ROW; s_noncanon = 0; s_large = 0; }
+    if (tid == 0) { s_nbig = 0; s_bad = B3W_NO_ROW; s_noncanon = 0; }
     __syncthreads();
     // ---- phase 1: stream the witness once (4 slots per thread in flight), keep 8 bytes per slot ----
     const uint4 *w = reinterpret_cast<const uint4 *>(wit + i * (uint64_t)ws * 32);
@@ -312,7 +312,6 @@ k_r1cs_check_staged(const uint8_t *__restrict__ wit, uint64_t n, uint32_t ws, co
         uint64_t v;
         if ((a[u].z | a[u].w | b[u].x | b[u].y | b[u].z | b[u].w) == 0 && (a[u].y >> 30) == 0) {
           v = ((uint64_t)a[u].y << 32) | a[u].x;
-          if (a[u].y >> (STG_FAST_VMAX - 32)) atomicOr(&s_large, 1u);
         } else {
           fr_t x, d;
           x.l[0] = a[u].x; x.l[1] = a[u].y; x.l[2] = a[u].z; x.l[3] = a[u].w;
@@ -321,7 +320,6 @@ k_r1cs_check_staged(const uint8_t *__restrict__ wit, uint64_t n, uint32_t ws, co
           if (borrow || fr_is_zero(d)) atomicOr(&s_noncanon, 1u);      // x >= p: not a canonical field element
           if (!borrow && (d.l[2] | d.l[3] | d.l[4] | d.l[5] | d.l[6] | d.l[7]) == 0 && (d.l[1] >> 30) == 0) {
             v = STG_TAG_NEG | ((uint64_t)d.l[1] << 32) | d.l[0];
-            if (d.l[1] >> (STG_FAST_VMAX - 32)) atomicOr(&s_large, 1u);
           } else {
             const uint32_t k = atomicAdd(&s_nbig, 1u);
             v = STG_TAG_BIG | k;
@@ -341,9 +339,9 @@ k_r1cs_check_staged(const uint8_t *__restrict__ wit, uint64_t n, uint32_t ws, co
     } else if (!s_noncanon && !STG_EXP_SKIP_P2) {
       // ---- phase 2: every row from shared memory, one block of <= 32 rows per warp step ----
       const StagedSrc src{val, big, F};
-      // the 64-bit path needs every small value below 2^STG_FAST_VMAX and wire 0 to be the constant 1 (BOOLROW classes
-      // rely on it); classes with wide coefficients keep the 128-bit evaluator
-      const bool fast_ok = !s_large && val[0] == 1ull;
+      // the fast paths need wire 0 to be the constant 1 (BOOLROW classes rely on it); classes with wide coefficients keep
+      // the 128-bit evaluator
+      const bool fast_ok = val[0] == 1ull;
       for (uint32_t ci = 0; ci < T.n_classes; ci++) {
         const r1cs_class_dev c = s_cls[ci];
         const uint32_t nb = s_nblk[ci], hw = 2u + 2u * (c.nA + c.nB + c.nC);

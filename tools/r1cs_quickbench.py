@@ -32,13 +32,13 @@ for name, gen in (("blake3_compression", lcg_compression_inputs), ("blake3_nova_
     out = {"circuit": name, "n": n, "plain_ms": round(t_plain, 3), "fused_ms": round(t_fused, 3),
            "plain_wit_per_s": round(n / t_plain * 1e3), "fused_wit_per_s": round(n / t_fused * 1e3)}
     if "pasta" not in name:
-        # stand-alone check of the witnesses now resident in HBM: warp-per-instance evaluator (default for the built-in rows)
-        # and the staged evaluator (what loaded .r1cs systems use)
+        # stand-alone check of the witnesses now resident in HBM: the default evaluator of this circuit's built-in rows, then
+        # each evaluator explicitly
         t_hbm = timeit(lambda: wc.r1cs_check_device(d_out.data_ptr(), n, d_st.data_ptr(), d_bad.data_ptr(), s))
         assert int(d_st.max()) == 0
         out.update(hbm_check_ms=round(t_hbm, 3), hbm_check_wit_per_s=round(n / t_hbm * 1e3),
                    hbm_check_read_gbs=round(n * wc.witnessSize * 32 / t_hbm / 1e6))
-        for mode in ("compact", "staged"):
+        for mode in ("warp", "compact", "staged"):
             os.environ["B3W_STANDALONE_CHECK"] = mode
             wc2 = pkg.builder(name, device=0)
             t_m = timeit(lambda: wc2.r1cs_check_device(d_out.data_ptr(), n, d_st.data_ptr(), d_bad.data_ptr(), s))
