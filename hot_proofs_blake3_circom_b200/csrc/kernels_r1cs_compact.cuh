@@ -13,10 +13,9 @@
 // slots than the side table holds (not one of these circuits' witnesses, but the checker must still answer) is
 // evaluated with every non-bit value converted from HBM on the fly.
 // Measured on B200 (profiles/r01i_r1cs_check.jsonl, 2^15 witnesses): streaming + classification alone 6.3 TB/s; with the
-// rows 1.57 M witnesses/s (compression, 24 544 rows; staged 1.20) and 0.87 M/s (nova O1; staged 0.41).  The generic row
-// arithmetic (117 760 terms per witness) is now 75 % of the time and issue-bound; prefetching the block headers or keeping
-// them in L1 changes nothing.  What would: recognising the XOR rows (2xy = x + y - o over bits) the way BOOLROW
-// recognises booleanity rows.
+// rows 2.33 M witnesses/s for blake3_compression (24 544 rows; the 8-byte staged copy 1.65, the warp-per-instance evaluator
+// 1.24) and 1.18 M/s for nova O1.  The row arithmetic is what is left (issue-bound): booleanity rows and XOR rows are
+// single comparisons (BOOLROW / XORROW), the bit-recomposition rows still go term by term.
 #pragma once
 
 #ifndef CPT_EXP
