@@ -804,6 +804,8 @@ static int ensure_nova_wide(b3w_ctx *c) {
     all.insert(all.end(), lanes[l].begin(), lanes[l].end());
   }
   off[32] = (uint32_t)all.size();
+  for (void **q : {(void **)&c->d_wslots, (void **)&c->d_lane_off, (void **)&c->d_fr})       // a failed earlier attempt
+    if (*q) { cudaFree(*q); *q = nullptr; }
   CK(cudaMalloc(&c->d_wslots, all.size() * sizeof(uint2) + 16));
   CK(cudaMemcpy(c->d_wslots, all.data(), all.size() * sizeof(uint2), cudaMemcpyHostToDevice));
   CK(cudaMalloc(&c->d_lane_off, sizeof off));
@@ -903,15 +905,18 @@ static int b3w_witness_batch_fr_impl(b3w_ctx *c, const uint8_t *in_fr, uint64_t 
     // u32 inputs (what every driver of the reference produces) take the hot kernels; a batch that holds anything else
     // runs on the general kernel, which evaluates the nova-level logic on field elements
     const fr_t p = prime_of(c->def);
-    std::vector<uint8_t> canon((size_t)n * 1024);
     bool all_u32 = true;
+    for (uint64_t i = 0; i < n * 32 && all_u32; i++) {
+      const fr_t v = wd_load_reduced(in_fr + i * 32, p);
+      rows[i] = v.l[0];
+      all_u32 = wd_fits(v, 32);
+    }
+    if (all_u32) return b3w_witness_batch(c, rows.data(), n, out, status, pub);
+    std::vector<uint8_t> canon((size_t)n * 1024);           // only now: the general kernel takes canonical field elements
     for (uint64_t i = 0; i < n * 32; i++) {
       const fr_t v = wd_load_reduced(in_fr + i * 32, p);
       memcpy(canon.data() + i * 32, v.l, 32);
-      rows[i] = v.l[0];
-      all_u32 = all_u32 && wd_fits(v, 32);
     }
-    if (all_u32) return b3w_witness_batch(c, rows.data(), n, out, status, pub);
     return nova_wide_batch(c, canon.data(), n, out, status, pub);
   }
   uint64_t n_wide = 0;
