@@ -175,13 +175,26 @@ def run_own(args, rank, world, local_rank):
     wc = pkg.builder("blake3_compression", device=local_rank, chunk=2048)
     rows = lcg_compression_inputs(n, first=first)
     d_in = torch.from_numpy(rows.view(np.int32)).cuda()
-    d_out = torch.empty(n * WIT_BYTES, dtype=torch.uint8, device="cuda")
+    d_out = torch.empty(n * WIT_BYTES, dtype=torch.uint8, device="cuda")       # ordinary (cudaMalloc) memory
     d_st = torch.empty(n, dtype=torch.uint8, device="cuda")
     d_pub = torch.empty(n * 16, dtype=torch.int32, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
+    # The witnesses of the timed steps go to COMPRESSIBLE device memory (b3w_device_alloc: Blackwell's L2 compresses such
+    # lines on their way to HBM; a witness is mostly zero bytes).  Same bytes on read-back; the plain-memory rate is
+    # measured next to it.  --plain-output, or a device that does not grant compression, keeps ordinary memory.
+    out_ptr, compressible = d_out.data_ptr(), False
+    if not args.plain_output:
+        try:
+            p_c, granted = wc.device_alloc(n * WIT_BYTES, compressible=True)
+            if granted:
+                out_ptr, compressible = p_c, True
+            else:
+                wc.device_free(p_c)
+        except pkg.B3WError:
+            pass
 
-    def step():
-        wc.witness_batch_device(d_in.data_ptr(), n, d_out.data_ptr(), d_st.data_ptr(), d_pub.data_ptr(), stream)
+    def step(ptr=None):
+        wc.witness_batch_device(d_in.data_ptr(), n, ptr or out_ptr, d_st.data_ptr(), d_pub.data_ptr(), stream)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -208,6 +221,21 @@ def run_own(args, rank, world, local_rank):
     gpu_launches = world * args.steps                         # one witness kernel per step per rank
     assert int(d_st.max()) == 0
     pub0 = d_pub[:16].cpu().numpy().view(np.uint32)
+
+    # --- the same kernel into ordinary memory (what every figure before r01j was measured on) -------
+    plain_ms = None
+    if compressible:
+        for _ in range(3):
+            step(d_out.data_ptr())
+        torch.cuda.synchronize()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(5):
+            step(d_out.data_ptr())
+        p1.record()
+        torch.cuda.synchronize()
+        plain_ms = max_over_ranks(p0.elapsed_time(p1) / 5)
+        wc.device_free(out_ptr)
 
     # --- pure-store calibration on the same buffer (the write roofline of this very GPU) -----------
     for _ in range(2):
@@ -254,15 +282,16 @@ def run_own(args, rank, world, local_rank):
     C.memmove(h_in, rows.ctypes.data, n_e2e * IN_BYTES)
     e2e_steps = max(2, min(args.steps, 5))
 
-    def e2e_run(out_ptr, steps):
+    def e2e_run(out_ptr, steps, calc=None):
         from hot_proofs_blake3_circom_b200 import _lib
+        h = (calc or wc)._h
         for _ in range(1):
-            _lib.check(L.b3w_witness_batch(wc._h, h_in, n_e2e, out_ptr, h_st, h_pub))
+            _lib.check(L.b3w_witness_batch(h, h_in, n_e2e, out_ptr, h_st, h_pub))
         barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(steps):
-            _lib.check(L.b3w_witness_batch(wc._h, h_in, n_e2e, out_ptr, h_st, h_pub))   # returns after the last D2H
+            _lib.check(L.b3w_witness_batch(h, h_in, n_e2e, out_ptr, h_st, h_pub))   # returns after the last D2H
         dt = time.perf_counter() - t0
         barrier()
         return max_over_ranks(dt) / steps
@@ -271,6 +300,14 @@ def run_own(args, rank, world, local_rank):
     got0 = np.ctypeslib.as_array(C.cast(h_out, C.POINTER(C.c_uint32)), shape=(WS * 8,))
     assert got0[8] == pub0[0] and got0[0] == 1                  # slot 0 == 1, slot 1 == out[0]
     t_compact = e2e_run(None, e2e_steps)
+    # the same two calls with the library's HBM ring in compressible memory (B3W_FLAG_COMPRESSIBLE_RING)
+    t_full_c = t_compact_c = None
+    if compressible:
+        wc_ring = pkg.builder("blake3_compression", device=local_rank, chunk=2048, compressible_ring=True)
+        t_compact_c = e2e_run(None, e2e_steps, wc_ring)
+        t_full_c = e2e_run(h_out, 2, wc_ring)
+        assert got0[8] == pub0[0] and got0[0] == 1
+        wc_ring.close()
     L.b3w_host_free(h_out)
     # ... and with the witnesses returned in COMPACT form (the per-instance trace, 3 776 B: every slot is a pure function
     # of it; b3w_unpack_device expands on demand)
@@ -317,7 +354,7 @@ def run_own(args, rank, world, local_rank):
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         with open(tp) as f:
-            traffic = json.load(f).get("k_blake3_comp_witness_dram_bytes_per_launch")
+            traffic = json.load(f).get("k_blake3_comp_witness_dram_bytes_per_launch" + ("_compressible" if compressible else ""))
     value = world * n * args.steps / (total_ms / 1e3)
     line = {
         "metric": METRIC, "value": value, "unit": "witnesses/s", "n_gpus": world, "steps": args.steps,
@@ -325,13 +362,20 @@ def run_own(args, rank, world, local_rank):
         "scaling": "weak", "vs_baseline": None, "dtype": "u32 + Fr256 (BN254)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "instances_per_gpu": n, "witness_bytes": WIT_BYTES,
                    "hbm_out_bytes_per_gpu": n * WIT_BYTES, "l2": "each step writes 50.5 GB per GPU, >> 126 MB L2",
-                   "sharding": "contiguous index ranges, no collective", "out0_instance0": int(pub0[0])},
+                   "sharding": "contiguous index ranges, no collective", "out0_instance0": int(pub0[0]),
+                   "output_memory": "compressible device memory (b3w_device_alloc, CU_MEM_ALLOCATION_COMP_GENERIC): the L2 compresses "
+                                    "witness lines on their way to HBM; identical bytes on read-back" if compressible
+                                    else "ordinary device memory (cudaMalloc)"},
         "roofline": {"bound": "hbm", "kernel": "k_blake3_comp_witness", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src + " (of measured)"
                      if "MEASURED" in peak_src else peak_src + " (of fallback)",
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms,
                      "pure_store_fill_gbs_same_gpu": fill_gbs,
-                     "pure_store_same_stream_shape_gbs": fill_items_gbs, "frac_of_spec_8TBps": achieved / 8000.0},
+                     "pure_store_same_stream_shape_gbs": fill_items_gbs, "frac_of_spec_8TBps": achieved / 8000.0,
+                     "note": ("witness bytes per second INTO COMPRESSIBLE memory: the HBM interface moves fewer bytes than the "
+                              "kernel writes (traffic = ncu dram bytes per launch), so achieved can exceed the interface's peak; "
+                              "achieved_plain_memory is the same kernel into cudaMalloc memory") if compressible else None,
+                     "achieved_plain_memory": (alg_bytes / plain_ms / 1e6) if plain_ms else None},
         "e2e": {"value": world * n_e2e / t_full, "unit": "witnesses/s", "h2d_bytes_per_step": n_e2e * IN_BYTES,
                 "d2h_bytes_per_step": n_e2e * (WIT_BYTES + 1 + 64), "instances_per_step_per_gpu": n_e2e,
                 "ms_per_step": 1e3 * t_full, "d2h_gbs_per_gpu": n_e2e * WIT_BYTES / t_full / 1e9,
@@ -339,11 +383,16 @@ def run_own(args, rank, world, local_rank):
         "e2e_compact": {"value": world * n_e2e / t_compact, "unit": "witnesses/s", "h2d_bytes_per_step": n_e2e * IN_BYTES,
                         "d2h_bytes_per_step": n_e2e * (1 + 64), "ms_per_step": 1e3 * t_compact,
                         "api": "b3w_witness_batch(out=NULL): witnesses stream through the HBM ring, status + out[16] return"},
+        "e2e_compressible_ring": None if t_compact_c is None else {
+            "full_copy": world * n_e2e / t_full_c, "compact": world * n_e2e / t_compact_c, "unit": "witnesses/s",
+            "api": "the two calls above on a context created with B3W_FLAG_COMPRESSIBLE_RING"},
         "e2e_packed": {"value": world * n_e2e / t_packed, "unit": "witnesses/s", "h2d_bytes_per_step": n_e2e * IN_BYTES,
                        "d2h_bytes_per_step": n_e2e * (pk_words * 4 + 1 + 64), "ms_per_step": 1e3 * t_packed,
                        "api": "b3w_witness_batch_packed(host pinned in/out): every witness returned in compact form "
                               "(%d B trace per instance; expandable to the .wtns body with b3w_unpack_device)" % (pk_words * 4)},
         "gpu_launches": gpu_launches, "clocks": clocks}
+    if plain_ms:
+        line["value_plain_memory"] = world * n / (plain_ms / 1e3)
     if cpu:
         line["cpu_baseline"] = cpu
     print_json(json.dumps(line))
@@ -358,6 +407,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--plain-output", action="store_true", help="timed steps write ordinary (cudaMalloc) memory")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

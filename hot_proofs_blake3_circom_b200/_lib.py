@@ -11,6 +11,8 @@ B3W_R1CS_VIOLATION = 7
 B3W_NO_ROW = 0xFFFFFFFF
 B3W_FLAG_FUSED_CHECK = 1
 B3W_EXT_ASSERT = 127
+B3W_FLAG_COMPRESSIBLE_RING = 2
+B3W_MEM_COMPRESSIBLE = 1
 
 EXPORTS = ("b3w_version", "b3w_last_error", "b3w_create", "b3w_destroy", "b3w_circuit_info", "b3w_wtns_header",
            "b3w_input_signal", "b3w_witness_one", "b3w_witness_batch", "b3w_witness_batch_device",
@@ -19,7 +21,7 @@ EXPORTS = ("b3w_version", "b3w_last_error", "b3w_create", "b3w_destroy", "b3w_ci
            "b3w_nova_chain_size", "b3w_nova_chain", "b3w_debug_set_launch", "b3w_assert_trace",
            "b3w_r1cs_load", "b3w_r1cs_load_file", "b3w_inputs_from_fr", "b3w_witness_batch_fr", "b3w_packed_words", "b3w_witness_batch_packed_device", "b3w_witness_batch_packed", "b3w_unpack_device",
            "b3w_inputs_from_fr_wide", "b3w_witness_batch_wide", "b3w_witness_batch_device_wide", "b3w_assert_trace_fr",
-           "b3w_multi_create", "b3w_multi_destroy", "b3w_multi_size", "b3w_shard_range", "b3w_multi_witness_batch", "b3w_multi_nova_chain")
+           "b3w_device_alloc", "b3w_device_free", "b3w_multi_create", "b3w_multi_destroy", "b3w_multi_size", "b3w_shard_range", "b3w_multi_witness_batch", "b3w_multi_nova_chain")
 
 
 class B3WError(RuntimeError):
@@ -83,6 +85,8 @@ def lib():
     L.b3w_witness_batch_wide.argtypes = [vp, vp, vp, u64, vp, vp, vp]
     L.b3w_witness_batch_device_wide.argtypes = [vp, vp, vp, u64, vp, vp, vp, vp, vp]
     L.b3w_assert_trace_fr.argtypes = [C.c_uint32, vp, C.c_char_p, C.c_size_t]
+    L.b3w_device_alloc.argtypes = [vp, C.c_size_t, C.c_uint32, C.POINTER(vp), u32p]
+    L.b3w_device_free.argtypes = [vp, vp]
     L.b3w_packed_words.argtypes = [C.c_uint32, u32p]
     L.b3w_witness_batch_packed_device.argtypes = [vp, vp, u64, vp, vp, vp, vp]
     L.b3w_witness_batch_packed.argtypes = [vp, vp, u64, vp, vp, vp]

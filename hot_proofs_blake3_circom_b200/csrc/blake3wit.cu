@@ -77,6 +77,7 @@ static int guarded(const char *what, F &&body) {
 #include "kernels_r1cs_compact.cuh"
 #include "r1cs_load.h"
 #include "wide_domain.h"
+#include "device_mem.h"
 
 // ------------------------------------------------------------------------------------------------
 // host side
@@ -163,6 +164,9 @@ struct b3w_ctx {
   uint32_t *d_lane_off;
   uint8_t *d_fr;             // chunk x 32 x 32 bytes
   bool nw_ready;
+  // compressible device memory (device_mem.h): driver entry points + the blocks handed out by b3w_device_alloc / the ring
+  vmm_api vmm;
+  std::vector<vmm_block> *blocks;
   void *cs_ptr[8];           // chain driver scratch (grow-only)
   size_t cs_cap[8];
   // staging for host-buffer batches of PACKED witnesses: 2 slots
@@ -178,7 +182,7 @@ extern "C" const char *b3w_last_error(void) { return g_err; }
 static int b3w_create_impl(const b3w_config *cfg, b3w_ctx **out) {
   if (!cfg || !out) return fail(B3W_ERR_INVALID, "b3w_create: null argument");
   if (cfg->circuit >= (uint32_t)N_CIRCUITS) return fail(B3W_ERR_UNSUPPORTED, "b3w_create: circuit %u not built", cfg->circuit);
-  if (cfg->flags & ~(uint32_t)B3W_FLAG_FUSED_CHECK) return fail(B3W_ERR_INVALID, "b3w_create: unknown flags 0x%x", cfg->flags);
+  if (cfg->flags & ~(uint32_t)(B3W_FLAG_FUSED_CHECK | B3W_FLAG_COMPRESSIBLE_RING)) return fail(B3W_ERR_INVALID, "b3w_create: unknown flags 0x%x", cfg->flags);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -266,6 +270,50 @@ extern "C" int b3w_create(const b3w_config *cfg, b3w_ctx **out) {
   return guarded("b3w_create", [&]() { return b3w_create_impl(cfg, out); });
 }
 
+// ---- device memory for witness buffers: ordinary or compressible (device_mem.h) ------------------------------------
+static int device_alloc(b3w_ctx *c, size_t bytes, uint32_t flags, void **out) {
+  *out = nullptr;
+  if (flags & ~(uint32_t)B3W_MEM_COMPRESSIBLE) return fail(B3W_ERR_INVALID, "b3w_device_alloc: unknown flags 0x%x", flags);
+  if (bytes == 0) return fail(B3W_ERR_INVALID, "b3w_device_alloc: zero bytes");
+  if (!c->vmm.ok && !vmm_load(c->vmm)) return fail(B3W_ERR_UNSUPPORTED, "b3w_device_alloc: the driver's virtual-memory entry points are not available");
+  if (!c->blocks) c->blocks = new std::vector<vmm_block>();
+  vmm_block blk;
+  const char *err;
+  void *p = vmm_alloc(c->vmm, c->device, bytes, (flags & B3W_MEM_COMPRESSIBLE) != 0, blk, &err);
+  if (!p) return fail(B3W_ERR_NOMEM, "b3w_device_alloc(%zu bytes): %s", bytes, err);
+  c->blocks->push_back(blk);
+  *out = p;
+  return B3W_OK;
+}
+// B3W_OK when p was one of this context's blocks (and is now released), B3W_ERR_INVALID otherwise
+static int device_free(b3w_ctx *c, void *p) {
+  if (c->blocks)
+    for (size_t i = 0; i < c->blocks->size(); i++)
+      if ((void *)(*c->blocks)[i].va == p) {
+        vmm_free(c->vmm, (*c->blocks)[i]);
+        c->blocks->erase(c->blocks->begin() + i);
+        return B3W_OK;
+      }
+  return B3W_ERR_INVALID;
+}
+extern "C" int b3w_device_alloc(b3w_ctx *c, size_t bytes, uint32_t flags, void **out, uint32_t *granted) {
+  if (!c || !out) return fail(B3W_ERR_INVALID, "b3w_device_alloc: null argument");
+  CK(cudaSetDevice(c->device));
+  return guarded("b3w_device_alloc", [&]() {
+    const int rc = device_alloc(c, bytes, flags, out);
+    if (rc == B3W_OK && granted) *granted = c->blocks->back().compressed ? B3W_MEM_COMPRESSIBLE : 0u;
+    return rc;
+  });
+}
+extern "C" int b3w_device_free(b3w_ctx *c, void *p) {
+  if (!c) return fail(B3W_ERR_INVALID, "b3w_device_free: null argument");
+  if (!p) return B3W_OK;
+  CK(cudaSetDevice(c->device));
+  CK(cudaDeviceSynchronize());                               // nothing may still be using the mapping
+  if (device_free(c, p) != B3W_OK) return fail(B3W_ERR_INVALID, "b3w_device_free: %p was not allocated by b3w_device_alloc of this context", p);
+  return B3W_OK;
+}
+
 static void free_packed_ring(b3w_ctx *c);
 static void free_r1cs_dev(b3w_ctx::r1cs_dev *r) {
   if (r->cls) cudaFree(r->cls);
@@ -279,7 +327,7 @@ static void free_r1cs_dev(b3w_ctx::r1cs_dev *r) {
 }
 static void free_ring(b3w_ctx *c) {
   for (int k = 0; k < 2; k++) {
-    if (c->d_ring[k]) cudaFree(c->d_ring[k]);
+    if (c->d_ring[k] && device_free(c, c->d_ring[k]) != B3W_OK) cudaFree(c->d_ring[k]);
     if (c->d_in[k]) cudaFree(c->d_in[k]);
     if (c->d_status[k]) cudaFree(c->d_status[k]);
     if (c->d_pub[k]) cudaFree(c->d_pub[k]);
@@ -303,6 +351,10 @@ extern "C" void b3w_destroy(b3w_ctx *c) {
   if (c->d_field) cudaFree(c->d_field);
   if (c->d_fslots) cudaFree(c->d_fslots);
   if (c->d_counters) cudaFree(c->d_counters);
+  if (c->blocks) {
+    for (const vmm_block &b : *c->blocks) vmm_free(c->vmm, b);
+    delete c->blocks;
+  }
   if (c->d_wslots) cudaFree(c->d_wslots);
   if (c->d_lane_off) cudaFree(c->d_lane_off);
   if (c->d_fr) cudaFree(c->d_fr);
@@ -680,7 +732,12 @@ static int alloc_ring(b3w_ctx *c) {
   for (int k = 0; k < 2; k++) {
     CK(cudaStreamCreateWithFlags(&c->st[k], cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->ev[k], cudaEventDisableTiming));
-    CK(cudaMalloc(&c->d_ring[k], (size_t)c->chunk * d->ws * 32));
+    if (c->flags & B3W_FLAG_COMPRESSIBLE_RING) {
+      int rc = device_alloc(c, (size_t)c->chunk * d->ws * 32, B3W_MEM_COMPRESSIBLE, (void **)&c->d_ring[k]);
+      if (rc) return rc;
+    } else {
+      CK(cudaMalloc(&c->d_ring[k], (size_t)c->chunk * d->ws * 32));
+    }
     CK(cudaMalloc(&c->d_in[k], (size_t)c->chunk * d->n_inputs * 4));
     CK(cudaMalloc(&c->d_status[k], (size_t)c->chunk));
     CK(cudaMalloc(&c->d_pub[k], (size_t)c->chunk * d->n_public * 4));

@@ -46,18 +46,20 @@ def circuit_from_wasm(code):
     return CIRCUITS[h][0]
 
 
-def builder(code, options=None, device=-1, chunk=0, lazy=False, fused_check=False):
+def builder(code, options=None, device=-1, chunk=0, lazy=False, fused_check=False, compressible_ring=False):
     """builder(code, options) -> WitnessCalculator   (witness_calculator.js:1).
     `code`: bytes of one of the reference's .wasm files, or a circuit name / id.
     lazy=True defers the creation of the GPU context to the first witness call (host-logic tests).
-    fused_check=True makes every batch call also run the fused on-device R1CS check (status 7 = violation)."""
+    fused_check=True makes every batch call also run the fused on-device R1CS check (status 7 = violation).
+    compressible_ring=True puts the internal HBM ring of the host-buffer calls into compressible device memory."""
     if isinstance(code, int):
         cid = code
     elif isinstance(code, str):
         cid = CIRCUIT_IDS[code]
     else:
         cid = circuit_from_wasm(code)
-    return WitnessCalculator(cid, options or {}, device=device, chunk=chunk, lazy=lazy, fused_check=fused_check)
+    return WitnessCalculator(cid, options or {}, device=device, chunk=chunk, lazy=lazy, fused_check=fused_check,
+                             compressible_ring=compressible_ring)
 
 
 def _flat_array(a):
@@ -135,10 +137,11 @@ def _nova_chain(L, call, handle, witness_size, data, want_witness):
 
 
 class WitnessCalculator:
-    def __init__(self, circuit, sanity_check, device=-1, chunk=0, lazy=False, fused_check=False):
+    def __init__(self, circuit, sanity_check, device=-1, chunk=0, lazy=False, fused_check=False, compressible_ring=False):
         L = _lib.lib()
         self._L, self._ctx = L, None
-        self._cfg = _lib.Config(circuit, device, chunk, _lib.B3W_FLAG_FUSED_CHECK if fused_check else 0)
+        self._cfg = _lib.Config(circuit, device, chunk, (_lib.B3W_FLAG_FUSED_CHECK if fused_check else 0) |
+                                (_lib.B3W_FLAG_COMPRESSIBLE_RING if compressible_ring else 0))
         info = _lib.Info()
         _lib.check(L.b3w_circuit_info(circuit, C.byref(info)))
         if not lazy:
@@ -379,6 +382,17 @@ class WitnessCalculator:
         """data: bytes.  Returns dict(n_chunks, total_steps, step_off=u64[n_chunks+1], rows=(steps,32) u32 step inputs,
         status=u8[steps], pub=(steps,15) u32 = z_{i+1}, witness=(steps, witnessSize*32) u8 | None, root=32 bytes)."""
         return _nova_chain(self._L, self._L.b3w_nova_chain, self._h, self.witnessSize, data, want_witness)
+
+    # ---- NEW: compressible device memory for witness buffers (b3w_device_alloc) ----
+    def device_alloc(self, nbytes, compressible=True):
+        """-> (device pointer, granted): device memory of this context; `granted` tells whether the driver made it
+        compressible (Blackwell compresses such lines between L2 and HBM: witnesses are mostly zero bytes)."""
+        p, g = C.c_void_p(), C.c_uint32()
+        _lib.check(self._L.b3w_device_alloc(self._h, int(nbytes), _lib.B3W_MEM_COMPRESSIBLE if compressible else 0, C.byref(p), C.byref(g)))
+        return p.value, bool(g.value)
+
+    def device_free(self, ptr):
+        _lib.check(self._L.b3w_device_free(self._h, ptr))
 
     # ---- device-pointer plumbing used by bench.py / tests (torch supplies memory and streams) ----
     def witness_batch_device(self, d_in, n, d_out, d_status=0, d_pub=0, stream=0):

@@ -33,6 +33,8 @@ extern "C" {
 #define B3W_NO_ROW 0xFFFFFFFFu   /* "no violated row" in first_bad[] */
 
 #define B3W_FLAG_FUSED_CHECK 1u  /* b3w_config.flags: every batch call also runs the fused R1CS check */
+#define B3W_FLAG_COMPRESSIBLE_RING 2u /* b3w_config.flags: the internal HBM ring of the host-buffer calls is compressible memory */
+#define B3W_MEM_COMPRESSIBLE 1u  /* b3w_device_alloc flags */
 
 /* Circuit variants = the reference's committed witness programs:
  *   COMPRESSION   build/blake3_compression/blake3_compression_js/blake3_compression.wasm (BN254, O1)
@@ -242,6 +244,16 @@ int b3w_multi_witness_batch(b3w_multi *m, const uint32_t *in, uint64_t n, uint8_
  * ranges balanced by step count, each writing its slice of the caller's arrays.  Same arguments as b3w_nova_chain. */
 int b3w_multi_nova_chain(b3w_multi *m, const uint8_t *data, uint64_t len, uint8_t *out, uint8_t *status, uint32_t *pub,
                          uint32_t *rows, uint64_t *step_off, uint8_t root[32]);
+
+/* Device memory for witness buffers, optionally COMPRESSIBLE (B3W_MEM_COMPRESSIBLE): Blackwell's L2 compresses lines on
+ * their way to HBM when the memory was allocated for it, which cudaMalloc never does.  A witness (a bit or a word plus 24+
+ * zero bytes per 32-byte slot) is the ideal payload: on B200 the blake3_compression kernel writes 2^16 witnesses into such
+ * a buffer in 6.18 ms instead of 6.99 ms (10.6 M witnesses/s), and wide coalesced reads of it run at 8.9 TB/s instead of
+ * 6.6 TB/s (narrow reads, 8 bytes per lane, are slower than on ordinary memory).  The bytes read back are identical.
+ * *granted (may be NULL) tells whether the driver really made the block compressible; a device without the feature gets
+ * ordinary memory.  Blocks belong to the context and are released by b3w_device_free or b3w_destroy. */
+int b3w_device_alloc(b3w_ctx *ctx, size_t bytes, uint32_t flags, void **out, uint32_t *granted);
+int b3w_device_free(b3w_ctx *ctx, void *p);
 
 /* pinned host memory for batch buffers */
 void *b3w_host_alloc(size_t bytes);

@@ -203,3 +203,39 @@ def test_field_element_inputs_entry_point(wc):
     _lib.check(pkg.lib().b3w_witness_batch_fr(wc._h, fr.ctypes.data, 9, out.ctypes.data, st.ctypes.data, None))
     assert not st.any()
     assert np.array_equal(out, port.witness_batch("compression", rows, nthreads=2))
+
+
+# ---- compressible device memory (b3w_device_alloc): same bytes, hardware-compressed between L2 and HBM --------------
+def test_compressible_output_buffer_and_ring(wc):
+    n = 4096
+    rows = gen.splitmix_compression_inputs(n, first=21)
+    want = wc.calculateWitnessBatch(rows)
+    ptr, granted = wc.device_alloc(n * WS * 32, compressible=True)
+    assert ptr and ptr % 32 == 0
+    assert granted, "B200 grants CU_MEM_ALLOCATION_COMP_GENERIC"
+    d_in = torch.from_numpy(rows.view(np.int32)).cuda()
+    d_st = torch.full((n,), 255, dtype=torch.uint8, device="cuda")
+    d_sums = torch.zeros(n, dtype=torch.int64, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    wc.witness_batch_device(d_in.data_ptr(), n, ptr, d_st.data_ptr(), 0, s)
+    wc.checksum_device(ptr, n, d_sums.data_ptr(), s)
+    torch.cuda.synchronize()
+    assert int(d_st.max()) == 0
+    assert np.array_equal(d_sums.cpu().numpy().view(np.uint64), checksum_np(want["witness"], WS))
+    # bytes come back identical through an ordinary device-to-host copy
+    import ctypes as C
+    host = np.empty(64 * WS * 32, np.uint8)
+    cudart = torch.cuda.cudart()
+    assert int(cudart.cudaMemcpy(host.ctypes.data, ptr + 1000 * WS * 32, host.nbytes, 2)) == 0      # cudaMemcpyDeviceToHost
+    assert np.array_equal(host.reshape(64, WS * 32), want["witness"][1000:1064])
+    wc.device_free(ptr)
+    with pytest.raises(pkg.B3WError):
+        wc.device_free(ptr)                                            # not (any more) one of this context's blocks
+    plain, g2 = wc.device_alloc(1 << 20, compressible=False)
+    assert plain and not g2
+    wc.device_free(plain)
+    # the host-buffer calls with the ring in compressible memory
+    wcr = pkg.builder("blake3_compression", device=0, chunk=1024, compressible_ring=True)
+    got = wcr.calculateWitnessBatch(rows)
+    assert np.array_equal(got["witness"], want["witness"]) and np.array_equal(got["pub"], want["pub"])
+    wcr.close()

@@ -1,5 +1,5 @@
 """prof_run.py -- minimal driver for ncu captures of the witness kernel (no timing claims).
-usage: python tools/prof_run.py [log2_n] [launches] [circuit] [checked]"""
+usage: python tools/prof_run.py [log2_n] [launches] [circuit] [checked|plain] [compressible]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -20,14 +20,19 @@ else:
     from hot_proofs_blake3_circom_b200.inputs import splitmix_nova_inputs
     rows = splitmix_nova_inputs(n)
 d_in = torch.from_numpy(rows.view(np.int32)).cuda()
-d_out = torch.empty(n * wc.witnessSize * 32, dtype=torch.uint8, device="cuda")
+if len(sys.argv) > 5 and sys.argv[5] == "compressible":
+    out_ptr, granted = wc.device_alloc(n * wc.witnessSize * 32, compressible=True)
+    assert granted
+else:
+    d_out = torch.empty(n * wc.witnessSize * 32, dtype=torch.uint8, device="cuda")
+    out_ptr = d_out.data_ptr()
 d_st = torch.empty(n, dtype=torch.uint8, device="cuda")
 d_pub = torch.empty(n * wc.nPublic, dtype=torch.int32, device="cuda")
 s = torch.cuda.current_stream().cuda_stream
 for _ in range(launches):
     if checked:
-        wc.witness_batch_device_checked(d_in.data_ptr(), n, d_out.data_ptr(), d_st.data_ptr(), d_pub.data_ptr(), 0, s)
+        wc.witness_batch_device_checked(d_in.data_ptr(), n, out_ptr, d_st.data_ptr(), d_pub.data_ptr(), 0, s)
     else:
-        wc.witness_batch_device(d_in.data_ptr(), n, d_out.data_ptr(), d_st.data_ptr(), d_pub.data_ptr(), s)
+        wc.witness_batch_device(d_in.data_ptr(), n, out_ptr, d_st.data_ptr(), d_pub.data_ptr(), s)
 torch.cuda.synchronize()
 print("prof_run done", n, launches)
