@@ -86,9 +86,21 @@ __global__ void __launch_bounds__(256) k_checksum(const uint64_t *__restrict__ w
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   for (uint64_t i = warp; i < n; i += nwarps) {
-    const uint64_t *w = wit + i * (uint64_t)ws * 4;
+    // 16 bytes per lane, four loads in flight: wide requests are what compressible memory (device_mem.h) rewards --
+    // 8-byte lane loads read such a buffer at 2 TB/s, these at the full rate
+    const ulonglong2 *w = reinterpret_cast<const ulonglong2 *>(wit + i * (uint64_t)ws * 4);
+    const uint32_t nq = ws * 2;
     uint64_t acc = 0;
-    for (uint32_t e = lane; e < ws * 4; e += 32) acc += (w[e] + 1) * mix64(e);
+    for (uint32_t q0 = lane; q0 < nq; q0 += 128) {
+      ulonglong2 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) v[u] = __ldg(w + min(q0 + 32u * u, nq - 1));
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const uint32_t q = q0 + 32u * u;
+        if (q < nq) acc += (v[u].x + 1) * mix64(2 * q) + (v[u].y + 1) * mix64(2 * q + 1);
+      }
+    }
 #pragma unroll
     for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) sums[i] = acc;

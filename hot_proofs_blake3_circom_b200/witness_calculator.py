@@ -448,14 +448,15 @@ class MultiGpuCalculator:
     """NEW: the batched entry point over several GPUs of one node (b3w_multi_*, include/blake3wit.h): contiguous index
     ranges, one context and host thread per device, no collective.  devices=None takes every visible device."""
 
-    def __init__(self, circuit, devices=None, chunk=0, fused_check=False):
+    def __init__(self, circuit, devices=None, chunk=0, fused_check=False, compressible_ring=False):
         L = _lib.lib()
         self._L = L
         cid = circuit if isinstance(circuit, int) else (CIRCUIT_IDS[circuit] if isinstance(circuit, str) else circuit_from_wasm(circuit))
         info = _lib.Info()
         _lib.check(L.b3w_circuit_info(cid, C.byref(info)))
         self.circuit, self.witnessSize, self.nInputs, self.nPublic = cid, info.witness_size, info.n_inputs, info.n_public
-        cfg = _lib.Config(cid, -1, chunk, _lib.B3W_FLAG_FUSED_CHECK if fused_check else 0)
+        cfg = _lib.Config(cid, -1, chunk, (_lib.B3W_FLAG_FUSED_CHECK if fused_check else 0) |
+                          (_lib.B3W_FLAG_COMPRESSIBLE_RING if compressible_ring else 0))
         devs = (C.c_int32 * len(devices))(*devices) if devices else None
         h = C.c_void_p()
         _lib.check(L.b3w_multi_create(C.byref(cfg), devs, len(devices) if devices else 0, C.byref(h)))

@@ -223,10 +223,10 @@ def test_compressible_output_buffer_and_ring(wc):
     assert int(d_st.max()) == 0
     assert np.array_equal(d_sums.cpu().numpy().view(np.uint64), checksum_np(want["witness"], WS))
     # bytes come back identical through an ordinary device-to-host copy
-    import ctypes as C
+    from cuda.bindings import runtime as cudart
     host = np.empty(64 * WS * 32, np.uint8)
-    cudart = torch.cuda.cudart()
-    assert int(cudart.cudaMemcpy(host.ctypes.data, ptr + 1000 * WS * 32, host.nbytes, 2)) == 0      # cudaMemcpyDeviceToHost
+    err, = cudart.cudaMemcpy(host.ctypes.data, ptr + 1000 * WS * 32, host.nbytes, cudart.cudaMemcpyKind.cudaMemcpyDeviceToHost)
+    assert int(err) == 0
     assert np.array_equal(host.reshape(64, WS * 32), want["witness"][1000:1064])
     wc.device_free(ptr)
     with pytest.raises(pkg.B3WError):

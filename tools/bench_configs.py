@@ -100,9 +100,9 @@ def config3():
     wc.close()
 
 
-def config4():
+def config4(ring=False):
     n = 1 << 20
-    wc = pkg.builder("blake3_nova_pasta", device=0, chunk=32768)
+    wc = pkg.builder("blake3_nova_pasta", device=0, chunk=32768, compressible_ring=ring)
     rows = gen.splitmix_nova_inputs(n)
     h_in = pinned(rows)
     h_st = L.b3w_host_alloc(n)
@@ -111,7 +111,8 @@ def config4():
     dt = timed(f, reps=3)
     st = np.ctypeslib.as_array(C.cast(h_st, C.POINTER(C.c_uint8)), shape=(n,))
     assert not st.any()
-    print(json.dumps({"config": "configs[3]: blake3_nova_pasta (Pallas Fr) batch 2^20, streamed through the HBM ring",
+    print(json.dumps({"config": "configs[3]: blake3_nova_pasta (Pallas Fr) batch 2^20, streamed through the HBM ring" +
+                      (" (ring in compressible memory)" if ring else ""),
                       "instances": n, "witness_bytes": wc.witnessSize * 32, "seconds": dt, "witnesses_per_s": n / dt,
                       "GB_generated": n * wc.witnessSize * 32 / 1e9, "hbm_write_GBps": n * wc.witnessSize * 32 / dt / 1e9,
                       "note": "b3w_witness_batch(out=NULL): host pinned inputs H2D, 781 GB of witnesses written to a 2-slot HBM ring, "
@@ -121,12 +122,12 @@ def config4():
     wc.close()
 
 
-def config5():
+def config5(ring=False):
     """BASELINE configs[4]: 2^24 compression instances sharded by contiguous index range over every visible GPU through
     the C ABI's multi-GPU entry point (one host thread + context per device, no collective), without / with the fused check."""
     n = 1 << 24
     for fused in (False, True):
-        m = pkg.MultiGpuCalculator("blake3_compression", devices=None, chunk=32768, fused_check=fused)
+        m = pkg.MultiGpuCalculator("blake3_compression", devices=None, chunk=32768, fused_check=fused, compressible_ring=ring)
         rows = gen.splitmix_compression_inputs(n)
         h_in = pinned(rows)
         del rows
@@ -137,8 +138,9 @@ def config5():
         st = np.ctypeslib.as_array(C.cast(h_st, C.POINTER(C.c_uint8)), shape=(n,))
         assert not st.any()
         pub = np.ctypeslib.as_array(C.cast(h_pub, C.POINTER(C.c_uint32)), shape=(n, 16))
-        print(json.dumps({"config": "configs[4]: blake3_compression 2^24 instances, %s, %d B200 (contiguous shards, no collective)"
-                          % ("fused on-device R1CS check" if fused else "no check", m.nDevices),
+        print(json.dumps({"config": "configs[4]: blake3_compression 2^24 instances, %s, %d B200 (contiguous shards, no collective)%s"
+                          % ("fused on-device R1CS check" if fused else "no check", m.nDevices,
+                             ", rings in compressible memory" if ring else ""),
                           "n_gpus": m.nDevices, "instances": n, "seconds": dt, "witnesses_per_s": n / dt,
                           "TB_generated": n * 770976 / 1e12, "hbm_write_GBps_per_gpu": n * 770976 / dt / 1e9 / m.nDevices,
                           "xor_of_out0": int(np.bitwise_xor.reduce(pub[:, 0])),
@@ -159,3 +161,7 @@ if __name__ == "__main__":
         config4()
     if "5" in which:
         config5()
+    if "4c" in which:
+        config4(ring=True)
+    if "5c" in which:
+        config5(ring=True)
