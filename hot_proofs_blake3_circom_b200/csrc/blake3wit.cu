@@ -533,7 +533,14 @@ static int launch_witness(b3w_ctx *c, const uint32_t *d_in, uint64_t n, uint8_t 
   // Persistent grid, work items handed out dynamically (see sched_args).  Defaults from sweeps on B200 (profiles/):
   // fastest with only 2 CTAs per SM (16 expansion warps) and 24 items per witness (32 KiB each: the GPU-wide write front
   // stays compact).  The checked kernels have the same expansion shape plus CHECK_WARPS checker warps per CTA.
-  const uint32_t parts = c->sched_parts ? c->sched_parts : 24u;
+  // ... unless the witnesses go to COMPRESSIBLE memory (one of this context's b3w_device_alloc blocks): HBM is then no
+  // longer the limit, the SM-side store path and the per-item trace recomputation are, and 12 items per witness measured
+  // best across the four kernels (profiles/r01j_compressible.jsonl: nova + fused check 7.44 -> 6.49 ms per 2^16).
+  bool compressed_out = false;
+  if (c->blocks)
+    for (const vmm_block &b : *c->blocks)
+      compressed_out = compressed_out || (b.compressed && (CUdeviceptr)d_out >= b.va && (CUdeviceptr)d_out < b.va + b.size);
+  const uint32_t parts = c->sched_parts ? c->sched_parts : compressed_out ? 12u : 24u;
   uint64_t ctas_needed = (n * parts + WARPS_PER_CTA - 1) / WARPS_PER_CTA;      // one warp per work item
   int per_sm = check ? c->ctas_per_sm_checked : c->ctas_per_sm;
   const int cap = c->ctas_limit > 0 ? c->ctas_limit : 2;
