@@ -739,12 +739,10 @@ static int alloc_ring(b3w_ctx *c) {
   for (int k = 0; k < 2; k++) {
     CK(cudaStreamCreateWithFlags(&c->st[k], cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->ev[k], cudaEventDisableTiming));
-    if (c->flags & B3W_FLAG_COMPRESSIBLE_RING) {
-      int rc = device_alloc(c, (size_t)c->chunk * d->ws * 32, B3W_MEM_COMPRESSIBLE, (void **)&c->d_ring[k]);
-      if (rc) return rc;
-    } else {
+    // compressible when asked for and obtainable; a driver without the virtual-memory entry points gets ordinary memory
+    if (!(c->flags & B3W_FLAG_COMPRESSIBLE_RING) ||
+        device_alloc(c, (size_t)c->chunk * d->ws * 32, B3W_MEM_COMPRESSIBLE, (void **)&c->d_ring[k]) != B3W_OK)
       CK(cudaMalloc(&c->d_ring[k], (size_t)c->chunk * d->ws * 32));
-    }
     CK(cudaMalloc(&c->d_in[k], (size_t)c->chunk * d->n_inputs * 4));
     CK(cudaMalloc(&c->d_status[k], (size_t)c->chunk));
     CK(cudaMalloc(&c->d_pub[k], (size_t)c->chunk * d->n_public * 4));
