@@ -26,7 +26,8 @@ static napi_value Create(napi_env env, napi_callback_info info) {
   uint32_t circuit; int32_t device;
   NAPI_OK(napi_get_value_uint32(env, argv[0], &circuit));
   NAPI_OK(napi_get_value_int32(env, argv[1], &device));
-  b3w_config cfg = {circuit, device, 0, 0};
+  // the HBM ring of the host-buffer calls in compressible memory where the GPU offers it (falls back by itself)
+  b3w_config cfg = {circuit, device, 0, B3W_FLAG_COMPRESSIBLE_RING};
   b3w_ctx *ctx = NULL;
   int rc = b3w_create(&cfg, &ctx);
   if (rc) return throw_b3w(env, rc);
