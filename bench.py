@@ -193,6 +193,13 @@ def run_own(args, rank, world, local_rank):
         except pkg.B3WError:
             pass
 
+    if world > 1:                                               # every rank takes the same path (collectives follow)
+        flag = torch.tensor([1 if compressible else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if compressible and int(flag.item()) == 0:
+            wc.device_free(out_ptr)
+            out_ptr, compressible = d_out.data_ptr(), False
+
     def step(ptr=None):
         wc.witness_batch_device(d_in.data_ptr(), n, ptr or out_ptr, d_st.data_ptr(), d_pub.data_ptr(), stream)
 
