@@ -226,3 +226,46 @@ def test_nova_assert_trace_against_reference_wasm_live(built, variant, cid):
                                 "leaf_depth": v[12], "total_depth": v[13], "depth": v[14], "m": v[15:31], "b": v[31]})
         assert (rca, ref.err_msg()) == (rc, buf.value.decode()), (it, v)
     assert n_assert >= 30
+
+
+# ---- properties (hypothesis) ---------------------------------------------------------------------------------------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+_word = st.one_of(st.integers(0, 2**32 - 1), st.integers(2**32, 2**34 + 5), st.integers(1, 2**33 + 5).map(lambda k: P - k),
+                  st.integers(0, 2**256 - 1))
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.lists(_word, min_size=16, max_size=16), st.integers(0, 15))
+def test_conversion_reconstructs_every_message_word(built_once, m, j):
+    """ext * 2^32 + lo == m (mod p) for every instance the conversion lets through; refused ones are outside the window"""
+    v = list(range(100, 128))
+    v[8:24] = m
+    rows, ext, nw = convert([v])
+    if ext[0, 0] == _lib.B3W_EXT_ASSERT:
+        assert any(not (x % P < 2**34 or P - (x % P) <= 2**33) for x in m)
+        return
+    for k in range(16):
+        assert (int(ext[0, k]) * 2**32 + int(rows[0, 8 + k])) % P == m[k] % P
+        assert -2 <= int(ext[0, k]) <= 3
+    assert nw == (1 if any(int(e) for e in ext[0]) else 0)
+
+
+@settings(max_examples=150, deadline=None)
+@given(st.binary(min_size=32 * 32, max_size=32 * 32), st.integers(0, 3))
+def test_assert_trace_total_on_arbitrary_bytes(built_once, blob, cid):
+    """any 256-bit values (also >= p) are inputs: the replay answers 0 or 4 with a well-formed text, never anything else"""
+    buf = C.create_string_buffer(1024)
+    data = np.frombuffer(blob, np.uint8).copy()
+    rc = pkg.lib().b3w_assert_trace_fr(cid, data.ctypes.data, buf, len(buf))
+    assert rc in (0, 4)
+    txt = buf.value.decode()
+    assert (txt == "") == (rc == 0)
+    if rc == 4:
+        assert txt.endswith("\n") and all(line.startswith("Error in template ") for line in txt.strip().split("\n"))
+        assert ("Blake3Nova_54" in txt) == (cid != 0)
+
+
+@pytest.fixture(scope="module")
+def built_once(built):
+    return built
