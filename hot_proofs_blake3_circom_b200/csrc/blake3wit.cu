@@ -343,6 +343,7 @@ static void free_ring(b3w_ctx *c) {
 extern "C" void b3w_destroy(b3w_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  cudaDeviceSynchronize();                         // nothing of this context may still run (mapped blocks are unmapped below)
   free_ring(c);
   free_packed_ring(c);
   for (int i = 0; i < 8; i++)
