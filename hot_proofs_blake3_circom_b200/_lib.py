@@ -12,7 +12,11 @@ B3W_NO_ROW = 0xFFFFFFFF
 B3W_FLAG_FUSED_CHECK = 1
 B3W_EXT_ASSERT = 127
 B3W_FLAG_COMPRESSIBLE_RING = 2
+B3W_FLAG_PLAIN_RING = 4
+B3W_FLAG_REFERENCE_SIBLINGS = 8
 B3W_MEM_COMPRESSIBLE = 1
+B3W_MAX_SAMPLES = 1024
+B3W_VERSION = 0x000200
 
 EXPORTS = ("b3w_version", "b3w_last_error", "b3w_create", "b3w_destroy", "b3w_circuit_info", "b3w_wtns_header",
            "b3w_input_signal", "b3w_witness_one", "b3w_witness_batch", "b3w_witness_batch_device",
@@ -21,6 +25,9 @@ EXPORTS = ("b3w_version", "b3w_last_error", "b3w_create", "b3w_destroy", "b3w_ci
            "b3w_nova_chain_size", "b3w_nova_chain", "b3w_debug_set_launch", "b3w_assert_trace",
            "b3w_r1cs_load", "b3w_r1cs_load_file", "b3w_inputs_from_fr", "b3w_witness_batch_fr", "b3w_packed_words", "b3w_witness_batch_packed_device", "b3w_witness_batch_packed", "b3w_unpack_device",
            "b3w_inputs_from_fr_wide", "b3w_witness_batch_wide", "b3w_witness_batch_device_wide", "b3w_assert_trace_fr",
+           "b3w_witness_batch_ex", "b3w_witness_batch_fr_ex", "b3w_witness_batch_device_ex", "b3w_last_timing", "b3w_r1cs_program_info",
+           "b3w_r1cs_compile_stats", "b3w_nova_chain_device", "b3w_unpack_host", "b3w_witness_batch_hybrid", "b3w_multi_witness_batch_ex",
+           "b3w_debug_set_store_mode",
            "b3w_device_alloc", "b3w_device_free", "b3w_multi_create", "b3w_multi_destroy", "b3w_multi_size", "b3w_shard_range", "b3w_multi_witness_batch", "b3w_multi_nova_chain")
 
 
@@ -32,6 +39,18 @@ class B3WError(RuntimeError):
 
 class Config(C.Structure):
     _fields_ = [("circuit", C.c_uint32), ("device", C.c_int32), ("chunk", C.c_uint32), ("flags", C.c_uint32)]
+
+
+class BatchExtras(C.Structure):
+    """b3w_batch_extras (include/blake3wit.h)"""
+    _fields_ = [("sums", C.c_void_p), ("sample_idx", C.c_void_p), ("n_samples", C.c_uint32), ("sample_out", C.c_void_p),
+                ("first_bad", C.c_void_p)]
+
+
+class Timing(C.Structure):
+    """b3w_timing (include/blake3wit.h)"""
+    _fields_ = [("total_ms", C.c_double), ("kernel_ms", C.c_double), ("host_ms", C.c_double), ("launches", C.c_uint64),
+                ("instances", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
 
 class Info(C.Structure):
@@ -99,6 +118,18 @@ def lib():
     L.b3w_shard_range.argtypes = [u64, C.c_uint32, C.c_uint32, C.POINTER(u64), C.POINTER(u64)]
     L.b3w_multi_witness_batch.argtypes = [vp, vp, u64, vp, vp, vp]
     L.b3w_multi_nova_chain.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp, vp]
+    ex = C.POINTER(BatchExtras)
+    L.b3w_witness_batch_ex.argtypes = [vp, vp, u64, vp, vp, vp, ex]
+    L.b3w_witness_batch_fr_ex.argtypes = [vp, vp, u64, vp, vp, vp, ex]
+    L.b3w_witness_batch_device_ex.argtypes = [vp, vp, vp, u64, vp, vp, vp, vp, vp, C.c_int, vp]
+    L.b3w_multi_witness_batch_ex.argtypes = [vp, vp, u64, vp, vp, vp, ex]
+    L.b3w_last_timing.argtypes = [vp, C.POINTER(Timing)]
+    L.b3w_r1cs_program_info.argtypes = [vp, u32p, u32p, u32p, u32p]
+    L.b3w_r1cs_compile_stats.argtypes = [C.c_uint32, u32p, u32p, u32p, u32p, u32p]
+    L.b3w_nova_chain_device.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp, vp]
+    L.b3w_unpack_host.argtypes = [vp, vp, u64, vp, C.c_uint32]
+    L.b3w_witness_batch_hybrid.argtypes = [vp, vp, u64, vp, vp, vp, C.c_uint32]
+    L.b3w_debug_set_store_mode.argtypes = [vp, C.c_int]
     L.b3w_host_alloc.argtypes = [C.c_size_t]
     L.b3w_host_alloc.restype = vp
     L.b3w_host_alloc_near.argtypes = [C.c_size_t, C.c_int]

@@ -23,7 +23,11 @@
 #include <string>
 #include <algorithm>
 #include <thread>
+#include <mutex>
+#include <chrono>
 #include <ctype.h>
+#include <emmintrin.h>
+#include <nvtx3/nvToolsExt.h>
 #ifdef __linux__
 #include <unistd.h>
 #include <sys/syscall.h>
@@ -73,8 +77,9 @@ static int guarded(const char *what, F &&body) {
 #include "kernels_nova_wide.cuh"
 #include "kernels_chain.cuh"
 #include "kernels_aux.cuh"
-#include "kernels_r1cs_staged.cuh"
-#include "kernels_r1cs_compact.cuh"
+#include "r1cs_rows.cuh"
+#include "kernels_r1cs_fast.cuh"
+#include "kernels_fr_input.cuh"
 #include "r1cs_load.h"
 #include "wide_domain.h"
 #include "device_mem.h"
@@ -94,7 +99,7 @@ struct circuit_def {
     const uint64_t (*coef)[2]; size_t ncoef;
     const b3w_seg *cols; size_t ncols;
     uint32_t rows, terms;
-  } r_fused, r_slots;    // reduced trace-space set (fused check) / all rows in witness-slot space (O1 builds; else empty)
+  } r_fused, r_slots;    // reduced trace-space set (fused check) / all rows in witness-slot space (O1 builds: template level; O2 builds: the O2-form system)
   int n_sig;
   struct { const char *name; uint32_t off, size; } sig[12];
 };
@@ -112,69 +117,124 @@ static const uint8_t PRIME_PALLAS_SCALAR[32] = {0x01, 0x00, 0x00, 0x00, 0x21, 0x
 #define R1CS1(v)                                                                                                  \
   {R1CS_CLASSES_##v, sizeof(R1CS_CLASSES_##v) / sizeof(b3w_r1cs_class), R1CS_COEFS_##v, sizeof(R1CS_COEFS_##v) / 16, \
    R1CS_COLS_##v, sizeof(R1CS_COLS_##v) / sizeof(b3w_seg), R1CS_ROWS_##v, R1CS_TERMS_##v}
-#define R1CS_NONE {nullptr, 0, nullptr, 0, nullptr, 0, 0, 0}
 
 static const circuit_def CIRCUITS[] = {
     {"blake3_compression", false, B3W_WS_COMPRESSION, 28, 16, B3W_TRACE_WORDS_COMPRESSION, SEGS(COMPRESSION), PRIME_BN254, R1CS1(COMPRESSION_FUSED), R1CS1(COMPRESSION_SLOTS), 5,
      {{"h", 0, 8}, {"m", 8, 16}, {"t", 24, 2}, {"b", 26, 1}, {"d", 27, 1}}},
-    {"blake3_nova (bn128, O2)", true, B3W_WS_NOVA_BN_O2, 32, 15, B3W_TRACE_WORDS_NOVA_BN_O2, SEGS(NOVA_BN_O2), PRIME_BN254, R1CS1(NOVA_FUSED), R1CS_NONE, NOVA_SIGS},
+    {"blake3_nova (bn128, O2)", true, B3W_WS_NOVA_BN_O2, 32, 15, B3W_TRACE_WORDS_NOVA_BN_O2, SEGS(NOVA_BN_O2), PRIME_BN254, R1CS1(NOVA_FUSED), R1CS1(NOVA_O2_SLOTS), NOVA_SIGS},
     {"blake3_nova_pasta (vesta prime = Pallas scalar, O2)", true, B3W_WS_NOVA_PASTA_O2, 32, 15, B3W_TRACE_WORDS_NOVA_PASTA_O2,
-     SEGS(NOVA_PASTA_O2), PRIME_PALLAS_SCALAR, R1CS1(NOVA_FUSED), R1CS_NONE, NOVA_SIGS},
+     SEGS(NOVA_PASTA_O2), PRIME_PALLAS_SCALAR, R1CS1(NOVA_FUSED), R1CS1(NOVA_O2_SLOTS), NOVA_SIGS},
     {"blake3_nova (bn128, O1)", true, B3W_WS_NOVA_BN_O1, 32, 15, B3W_TRACE_WORDS_NOVA_BN_O1, SEGS(NOVA_BN_O1), PRIME_BN254, R1CS1(NOVA_FUSED), R1CS1(NOVA_BN_O1_SLOTS), NOVA_SIGS},
 };
 static const int N_CIRCUITS = sizeof(CIRCUITS) / sizeof(CIRCUITS[0]);
 
 #define N_SCHED_COUNTERS 64       // launches in flight on different streams each need their own counter set
 #define SCHED_SET_U64 (SCHED_LANES * SCHED_STRIDE)
+#define B3W_RING_SLOTS 2
 struct b3w_ctx {
-  const circuit_def *def;
-  int device;
-  int sm_count;
-  uint32_t chunk;
-  int ctas_per_sm;          // resident CTAs of this circuit's kernel (occupancy query)
-  int ctas_per_sm_checked;  // ... of its *_checked variant
-  uint32_t *d_desc;
-  field_consts *d_field;
-  uint2 *d_fslots;          // {slot, descriptor} of every slot that holds a true field element (nova)
-  uint32_t n_fslots;
-  uint32_t *h_desc;         // host copy of the per-slot descriptors
-  uint32_t flags;
+  const circuit_def *def = nullptr;
+  int device = 0;
+  int sm_count = 0;
+  uint32_t chunk = 0;
+  int ctas_per_sm = 0;          // resident CTAs of this circuit's kernel (occupancy query)
+  int ctas_per_sm_checked = 0;  // ... of its *_checked variant
+  uint32_t *d_desc = nullptr;
+  field_consts *d_field = nullptr;
+  uint2 *d_fslots = nullptr;    // {slot, descriptor} of every slot that holds a true field element (nova)
+  uint32_t n_fslots = 0;
+  uint32_t *h_desc = nullptr;   // host copy of the per-slot descriptors
+  field_consts *h_field = nullptr;   // host copy of the field constants (b3w_unpack_host)
+  uint32_t flags = 0;
+  // One host-buffer call at a time per context (include/blake3wit.h, "Ownership / threading"): the ring slots, streams and
+  // scratch below are shared mutable state, so every entry point that touches them holds this lock for its duration.
+  std::mutex mu;
   // R1CS tables (built on first use)
-  bool r1cs_ready;
-  struct r1cs_dev { r1cs_class_dev *cls; int64_t *lo, *hi; uint32_t *terms; uint32_t ncls; fr_t *coef_fr; uint32_t *row_ids, *nblk; uint32_t rows; } r_fused, r_slots;
-  bool r1cs_loaded;          // r_slots comes from b3w_r1cs_load, not from the built-in tables
-  bool slots_staged;         // r_slots is in row-block form: evaluated by k_r1cs_check_compact / _staged (always true for loaded sets)
-  uint32_t fault_word, fault_mask;
-  int ctas_limit;           // tuning hook: cap on resident CTAs per SM (0 = occupancy limit)
-  uint32_t sched_parts;     // work items per instance (0 = default)
-  unsigned long long *d_counters;   // rotating pool of work-item counters (launches on different streams may overlap)
-  uint32_t next_counter;
+  bool r1cs_ready = false;
+  struct r1cs_dev { r1cs_class_dev *cls; int64_t *lo, *hi; uint32_t *terms; uint32_t ncls; fr_t *coef_fr; uint32_t *row_ids, *nblk; uint32_t rows; };
+  r1cs_dev r_fused = {}, r_slots = {};
+  bool r1cs_loaded = false;     // r_slots comes from b3w_r1cs_load, not from the built-in tables
+  fastprog_dev fp = {};         // compiled form of the slot-space rows (kernels_r1cs_fast.cuh); r_slots holds the residual rows only
+  uint32_t slot_rows = 0;       // rows of the slot-space system (compiled + residual); 0 = none installed
+  uint32_t fault_word = B3W_NO_ROW, fault_mask = 0;
+  int ctas_limit = 0;           // tuning hook: cap on resident CTAs per SM (0 = occupancy limit)
+  uint32_t sched_parts = 0;     // work items per instance (0 = default)
+  int store_mode = 0;           // tuning hook: 0 = direct 256-bit stores, 1 = shared-memory tiles + TMA bulk stores
+  // rotating pool of work-item counters: launches on different streams may overlap, so a counter pair is only handed out
+  // again once the launch that used it last has finished (the new launch's stream waits on that launch's event)
+  unsigned long long *d_counters = nullptr;
+  uint32_t next_counter = 0;
+  cudaEvent_t ctr_ev[N_SCHED_COUNTERS / 2] = {};
   // staging for host-buffer batches: 2 ring slots
-  cudaStream_t st[2];
-  cudaEvent_t ev[2];
-  uint8_t *d_ring[2];
-  uint32_t *d_in[2];
-  uint8_t *d_status[2];
-  uint32_t *d_pub[2];
-  int8_t *d_ext[2];          // compression only: m_ext of the chunk (wide batches)
-  bool ring_ready;
-  uint32_t m_slot0;          // compression only: witness slot of m[0] (the 16 m slots are consecutive)
-  // nova only, built on first use: the wide (field-element input) kernel's override list and input staging
-  uint2 *d_wslots;
-  uint32_t *d_lane_off;
-  uint8_t *d_fr;             // chunk x 32 x 32 bytes
-  bool nw_ready;
+  cudaStream_t st[2] = {};
+  cudaEvent_t ev[2] = {};
+  cudaEvent_t ev_k0[2] = {}, ev_k1[2] = {};    // timing: around the witness kernel of the chunk in flight on each slot
+  bool ev_pending[2] = {};
+  uint8_t *d_ring[2] = {};
+  uint32_t *d_in[2] = {};
+  uint8_t *d_status[2] = {};
+  uint32_t *d_pub[2] = {};
+  int8_t *d_ext[2] = {};         // compression only: m_ext of the chunk (wide batches)
+  uint64_t *d_sums[2] = {};      // per-instance witness checksums of the chunk (b3w_batch_extras.sums)
+  uint32_t *d_fbad[2] = {};      // fused check: first violated row of the chunk's instances
+  uint8_t *d_fr[2] = {};         // Fr256 input rows of the chunk (b3w_witness_batch_fr), chunk x n_inputs x 32 bytes
+  uint32_t *d_wlist[2] = {};     // nova: indices (inside the chunk) of the instances that hold a field-valued input; [0] = count
+  bool ring_ready = false, fr_ready = false;
+  uint32_t m_slot0 = 0;          // compression only: witness slot of m[0] (the 16 m slots are consecutive)
+  // nova only, built on first use: the wide (field-element input) kernel's override list
+  uint2 *d_wslots = nullptr;
+  uint32_t *d_lane_off = nullptr;
+  bool nw_ready = false;
   // compressible device memory (device_mem.h): driver entry points + the blocks handed out by b3w_device_alloc / the ring
-  vmm_api vmm;
-  std::vector<vmm_block> *blocks;
-  void *cs_ptr[8];           // chain driver scratch (grow-only)
-  size_t cs_cap[8];
+  vmm_api vmm = {};
+  std::vector<vmm_block> *blocks = nullptr;
+  void *cs_ptr[12] = {};         // chain driver scratch (grow-only)
+  size_t cs_cap[12] = {};
   // staging for host-buffer batches of PACKED witnesses: 2 slots
-  cudaStream_t pk_st[2];
-  uint32_t *pk_in[2], *pk_buf[2], *pk_pub[2];
-  uint8_t *pk_status[2];
-  bool pk_ready;
+  cudaStream_t pk_st[2] = {};
+  uint32_t *pk_in[2] = {}, *pk_buf[2] = {}, *pk_pub[2] = {};
+  uint8_t *pk_status[2] = {};
+  bool pk_ready = false;
+  uint32_t *hy_host[2] = {};     // hybrid export: pinned host staging of the packed chunks
+  bool hy_ready = false;
+  b3w_timing timing = {};        // what b3w_last_timing() reports: the last host-buffer call of this context
 };
+
+// Every entry point runs on the context's device and leaves the CALLER's current device as it found it.
+struct dev_guard {
+  int prev = -1;
+  bool switched = false;
+  cudaError_t err = cudaSuccess;
+  explicit dev_guard(int dev) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) {
+      err = cudaSetDevice(dev);
+      switched = err == cudaSuccess;
+    }
+  }
+  ~dev_guard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+#define ON_DEVICE(c)                                                                                         \
+  dev_guard dev_guard_(c->device);                                                                           \
+  if (dev_guard_.err != cudaSuccess) return fail(B3W_ERR_CUDA, "cudaSetDevice(%d): %s", c->device, cudaGetErrorString(dev_guard_.err))
+#define LOCKED(c) std::lock_guard<std::mutex> lock_guard_(c->mu)
+
+// NVTX ranges around the stages of the host-buffer calls (tracing): visible in nsys / ncu timelines,
+// free when no tool is attached.
+struct nvtx_range {
+  explicit nvtx_range(const char *name) { nvtxRangePushA(name); }
+  ~nvtx_range() { nvtxRangePop(); }
+};
+// joins on every path out of the scope: a std::thread that is destroyed while joinable terminates the process
+struct thread_group {
+  std::vector<std::thread> th;
+  void join() { for (auto &t : th) if (t.joinable()) t.join(); }
+  ~thread_group() { join(); }
+};
+static double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 extern "C" int b3w_version(void) { return B3W_VERSION; }
 extern "C" const char *b3w_last_error(void) { return g_err; }
@@ -182,7 +242,8 @@ extern "C" const char *b3w_last_error(void) { return g_err; }
 static int b3w_create_impl(const b3w_config *cfg, b3w_ctx **out) {
   if (!cfg || !out) return fail(B3W_ERR_INVALID, "b3w_create: null argument");
   if (cfg->circuit >= (uint32_t)N_CIRCUITS) return fail(B3W_ERR_UNSUPPORTED, "b3w_create: circuit %u not built", cfg->circuit);
-  if (cfg->flags & ~(uint32_t)(B3W_FLAG_FUSED_CHECK | B3W_FLAG_COMPRESSIBLE_RING)) return fail(B3W_ERR_INVALID, "b3w_create: unknown flags 0x%x", cfg->flags);
+  if (cfg->flags & ~(uint32_t)(B3W_FLAG_FUSED_CHECK | B3W_FLAG_COMPRESSIBLE_RING | B3W_FLAG_PLAIN_RING | B3W_FLAG_REFERENCE_SIBLINGS))
+    return fail(B3W_ERR_INVALID, "b3w_create: unknown flags 0x%x", cfg->flags);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -190,12 +251,12 @@ static int b3w_create_impl(const b3w_config *cfg, b3w_ctx **out) {
   int dev = cfg->device;
   if (dev < 0) CK(cudaGetDevice(&dev));
   if (dev >= ndev) return fail(B3W_ERR_INVALID, "device %d out of range (%d devices)", dev, ndev);
-  CK(cudaSetDevice(dev));
   b3w_ctx *c = new (std::nothrow) b3w_ctx();
   if (!c) return fail(B3W_ERR_NOMEM, "out of host memory");
-  memset(c, 0, sizeof *c);
   c->def = &CIRCUITS[cfg->circuit];
   c->device = dev;
+  dev_guard dg(dev);                              // the caller's current device is restored on every path out
+  if (dg.err != cudaSuccess) { delete c; return fail(B3W_ERR_CUDA, "cudaSetDevice(%d): %s", dev, cudaGetErrorString(dg.err)); }
   c->chunk = cfg->chunk ? cfg->chunk : 1024;
   c->flags = cfg->flags;
   c->fault_word = B3W_NO_ROW;
@@ -246,21 +307,23 @@ static int b3w_create_impl(const b3w_config *cfg, b3w_ctx **out) {
     field_consts_init(*F, pl);
     e1 = cudaMalloc(&c->d_field, sizeof(field_consts));
     if (e1 == cudaSuccess) e1 = cudaMemcpy(c->d_field, F, sizeof(field_consts), cudaMemcpyHostToDevice);
-    delete F;
+    c->h_field = F;
     if (e1 != cudaSuccess) { b3w_destroy(c); return fail(B3W_ERR_CUDA, "field table upload: %s", cudaGetErrorString(e1)); }
   }
   const int bs_plain = WARPS_PER_CTA * 32, bs_checked = (WARPS_PER_CTA + (d->nova ? NOVA_CHECK_WARPS : CHECK_WARPS)) * 32;
   if (d->nova) {
-    e1 = cudaFuncSetAttribute(k_blake3_nova_witness<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NOVA_SMEM(WARPS_PER_CTA + NOVA_CHECK_WARPS));
+    e1 = cudaFuncSetAttribute(k_blake3_nova_witness<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NOVA_SMEM(WARPS_PER_CTA + NOVA_CHECK_WARPS));
     if (e1 == cudaSuccess)
-      e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, k_blake3_nova_witness<false>, bs_plain, NOVA_SMEM(WARPS_PER_CTA));
+      e1 = cudaFuncSetAttribute(k_blake3_nova_witness<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NOVA_SMEM(WARPS_PER_CTA + NOVA_CHECK_WARPS));
     if (e1 == cudaSuccess)
-      e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm_checked, k_blake3_nova_witness<true>, bs_checked,
+      e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, k_blake3_nova_witness<false, true>, bs_plain, NOVA_SMEM(WARPS_PER_CTA));
+    if (e1 == cudaSuccess)
+      e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm_checked, k_blake3_nova_witness<true, true>, bs_checked,
                                                          NOVA_SMEM(WARPS_PER_CTA + NOVA_CHECK_WARPS));
   } else {
-    e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, k_blake3_comp_witness<false, false>, bs_plain, 0);
+    e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, k_blake3_comp_witness<false, false, true>, bs_plain, 0);
     if (e1 == cudaSuccess)
-      e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm_checked, k_blake3_comp_witness<true, false>, bs_checked, 0);
+      e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm_checked, k_blake3_comp_witness<true, false, true>, bs_checked, 0);
   }
   if (e1 != cudaSuccess || c->ctas_per_sm < 1 || c->ctas_per_sm_checked < 1) { b3w_destroy(c); return fail(B3W_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e1)); }
   *out = c;
@@ -298,7 +361,8 @@ static int device_free(b3w_ctx *c, void *p) {
 }
 extern "C" int b3w_device_alloc(b3w_ctx *c, size_t bytes, uint32_t flags, void **out, uint32_t *granted) {
   if (!c || !out) return fail(B3W_ERR_INVALID, "b3w_device_alloc: null argument");
-  CK(cudaSetDevice(c->device));
+  ON_DEVICE(c);
+  LOCKED(c);
   return guarded("b3w_device_alloc", [&]() {
     const int rc = device_alloc(c, bytes, flags, out);
     if (rc == B3W_OK && granted) *granted = c->blocks->back().compressed ? B3W_MEM_COMPRESSIBLE : 0u;
@@ -308,7 +372,8 @@ extern "C" int b3w_device_alloc(b3w_ctx *c, size_t bytes, uint32_t flags, void *
 extern "C" int b3w_device_free(b3w_ctx *c, void *p) {
   if (!c) return fail(B3W_ERR_INVALID, "b3w_device_free: null argument");
   if (!p) return B3W_OK;
-  CK(cudaSetDevice(c->device));
+  ON_DEVICE(c);
+  LOCKED(c);
   CK(cudaDeviceSynchronize());                               // nothing may still be using the mapping
   if (device_free(c, p) != B3W_OK) return fail(B3W_ERR_INVALID, "b3w_device_free: %p was not allocated by b3w_device_alloc of this context", p);
   return B3W_OK;
@@ -328,39 +393,51 @@ static void free_r1cs_dev(b3w_ctx::r1cs_dev *r) {
 static void free_ring(b3w_ctx *c) {
   for (int k = 0; k < 2; k++) {
     if (c->d_ring[k] && device_free(c, c->d_ring[k]) != B3W_OK) cudaFree(c->d_ring[k]);
-    if (c->d_in[k]) cudaFree(c->d_in[k]);
-    if (c->d_status[k]) cudaFree(c->d_status[k]);
-    if (c->d_pub[k]) cudaFree(c->d_pub[k]);
-    if (c->d_ext[k]) cudaFree(c->d_ext[k]);
+    for (void **q : {(void **)&c->d_in[k], (void **)&c->d_status[k], (void **)&c->d_pub[k], (void **)&c->d_ext[k], (void **)&c->d_sums[k],
+                     (void **)&c->d_fbad[k], (void **)&c->d_fr[k], (void **)&c->d_wlist[k]}) {
+      if (*q) cudaFree(*q);
+      *q = nullptr;
+    }
     if (c->st[k]) cudaStreamDestroy(c->st[k]);
-    if (c->ev[k]) cudaEventDestroy(c->ev[k]);
-    c->d_ring[k] = nullptr; c->d_in[k] = nullptr; c->d_status[k] = nullptr; c->d_pub[k] = nullptr; c->d_ext[k] = nullptr;
-    c->st[k] = nullptr; c->ev[k] = nullptr;
+    for (cudaEvent_t *e : {&c->ev[k], &c->ev_k0[k], &c->ev_k1[k]}) {
+      if (*e) cudaEventDestroy(*e);
+      *e = nullptr;
+    }
+    c->d_ring[k] = nullptr;
+    c->st[k] = nullptr;
+    c->ev_pending[k] = false;
   }
   c->ring_ready = false;
+  c->fr_ready = false;
 }
 
+static void free_fastprog(fastprog_dev *p);
 extern "C" void b3w_destroy(b3w_ctx *c) {
   if (!c) return;
-  cudaSetDevice(c->device);
-  cudaDeviceSynchronize();                         // nothing of this context may still run (mapped blocks are unmapped below)
-  free_ring(c);
-  free_packed_ring(c);
-  for (int i = 0; i < 8; i++)
-    if (c->cs_ptr[i]) cudaFree(c->cs_ptr[i]);
-  if (c->d_desc) cudaFree(c->d_desc);
-  if (c->d_field) cudaFree(c->d_field);
-  if (c->d_fslots) cudaFree(c->d_fslots);
-  if (c->d_counters) cudaFree(c->d_counters);
-  if (c->blocks) {
-    for (const vmm_block &b : *c->blocks) vmm_free(c->vmm, b);
-    delete c->blocks;
+  {
+    dev_guard dg(c->device);
+    cudaDeviceSynchronize();                         // nothing of this context may still run (mapped blocks are unmapped below)
+    free_ring(c);
+    free_packed_ring(c);
+    for (int i = 0; i < 12; i++)
+      if (c->cs_ptr[i]) cudaFree(c->cs_ptr[i]);
+    if (c->d_desc) cudaFree(c->d_desc);
+    if (c->d_field) cudaFree(c->d_field);
+    if (c->d_fslots) cudaFree(c->d_fslots);
+    if (c->d_counters) cudaFree(c->d_counters);
+    for (cudaEvent_t e : c->ctr_ev)
+      if (e) cudaEventDestroy(e);
+    if (c->blocks) {
+      for (const vmm_block &b : *c->blocks) vmm_free(c->vmm, b);
+      delete c->blocks;
+    }
+    if (c->d_wslots) cudaFree(c->d_wslots);
+    if (c->d_lane_off) cudaFree(c->d_lane_off);
+    for (b3w_ctx::r1cs_dev *r : {&c->r_slots, &c->r_fused}) free_r1cs_dev(r);
+    free_fastprog(&c->fp);
+    free(c->h_desc);
+    delete c->h_field;
   }
-  if (c->d_wslots) cudaFree(c->d_wslots);
-  if (c->d_lane_off) cudaFree(c->d_lane_off);
-  if (c->d_fr) cudaFree(c->d_fr);
-  for (b3w_ctx::r1cs_dev *r : {&c->r_slots, &c->r_fused}) free_r1cs_dev(r);
-  free(c->h_desc);
   delete c;
 }
 
@@ -450,9 +527,9 @@ extern "C" int b3w_assert_trace(uint32_t circuit, const uint32_t *in, char *buf,
 struct r1cs_expanded {
   std::vector<r1cs_class_dev> cls;
   std::vector<int64_t> lo, hi;
-  std::vector<uint32_t> terms, nblk;     // terms: [class][term][row] matrices, or row blocks after stg_blockify (then nblk is set)
+  std::vector<uint32_t> terms;           // [class][term][row] matrices
 };
-static bool expand_r1cs_set(const circuit_def::r1cs_set &set, r1cs_expanded &x, bool as_blocks) {
+static bool expand_r1cs_set(const circuit_def::r1cs_set &set, r1cs_expanded &x) {
   const size_t ncls = set.ncls;
   x.cls.resize(ncls);
   x.lo.resize(set.ncoef);
@@ -477,70 +554,188 @@ static bool expand_r1cs_set(const circuit_def::r1cs_set &set, r1cs_expanded &x, 
     }
     row_off += s.count;
   }
-  if (term_off != set.terms || row_off != set.rows) return false;
-  // slot-space sets are evaluated block-wise by the staged checker: replace the term matrices by row blocks
-  if (as_blocks) {
-    std::vector<uint32_t> blocks;
-    stg_blockify(x.cls, x.terms, blocks, x.nblk, x.lo, x.hi);
-    x.terms.swap(blocks);
-  }
-  return true;
+  return term_off == set.terms && row_off == set.rows;
 }
 
-static int upload_r1cs_set(b3w_ctx *c, const circuit_def::r1cs_set &set, b3w_ctx::r1cs_dev *out, bool as_blocks = false) {
+// the fused (trace-space) set: class matrices as they are
+static int upload_fused_set(b3w_ctx *c, const circuit_def::r1cs_set &set, b3w_ctx::r1cs_dev *out) {
   if (set.ncls == 0) return B3W_OK;
   r1cs_expanded x;
-  if (!expand_r1cs_set(set, x, as_blocks)) return fail(B3W_ERR_INVALID, "R1CS tables of %s are corrupt", c->def->name);
+  if (!expand_r1cs_set(set, x)) return fail(B3W_ERR_INVALID, "R1CS tables of %s are corrupt", c->def->name);
   const size_t ncls = x.cls.size();
   cudaError_t e = cudaMalloc(&out->cls, ncls * sizeof(r1cs_class_dev));
   if (e == cudaSuccess) e = cudaMalloc(&out->lo, x.lo.size() * 8);
   if (e == cudaSuccess) e = cudaMalloc(&out->hi, x.hi.size() * 8);
   if (e == cudaSuccess) e = cudaMalloc(&out->terms, x.terms.size() * 4 + 16);
-  if (e == cudaSuccess && as_blocks) e = cudaMalloc(&out->nblk, x.nblk.size() * 4);
   if (e == cudaSuccess) e = cudaMemcpy(out->cls, x.cls.data(), ncls * sizeof(r1cs_class_dev), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(out->lo, x.lo.data(), x.lo.size() * 8, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(out->hi, x.hi.data(), x.hi.size() * 8, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(out->terms, x.terms.data(), x.terms.size() * 4, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess && as_blocks) e = cudaMemcpy(out->nblk, x.nblk.data(), x.nblk.size() * 4, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) return fail(B3W_ERR_CUDA, "R1CS table upload: %s", cudaGetErrorString(e));
   out->ncls = (uint32_t)ncls;
   return B3W_OK;
 }
 
-#ifndef B3W_BUILTIN_COMPACT
-#define B3W_BUILTIN_COMPACT(def) (!(def)->nova)
-#endif
+template <class T>
+static cudaError_t upload_vec(T **dst, const std::vector<T> &v) {
+  cudaError_t e = cudaMalloc((void **)dst, v.size() * sizeof(T) + 16);
+  if (e == cudaSuccess && !v.empty()) e = cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+  return e;
+}
+static void free_fastprog(fastprog_dev *p) {
+  for (void *q : {(void *)p->bool_mask, (void *)p->bool_row, (void *)p->xors, (void *)p->xor_ids, (void *)p->tiles, (void *)p->items, (void *)p->row_ids})
+    if (q) cudaFree(q);
+  memset(p, 0, sizeof *p);
+}
+
+// The slot-space system of the stand-alone check (built-in rows, or the rows of a loaded .r1cs file): compile what
+// compiles (fp_compile), keep the rest as a residual class/block set for the general evaluator, upload both.
+static int install_slot_rows(b3w_ctx *c, std::vector<r1cs_load_detail::row> &rows, uint32_t *n_compiled) {
+  fastprog_host fp;
+  std::vector<char> taken;
+  fp_compile(rows, c->def->ws, fp, taken);
+  std::vector<r1cs_load_detail::row> rest;
+  for (size_t i = 0; i < rows.size(); i++)
+    if (!taken[i]) rest.push_back(std::move(rows[i]));
+  r1cs_host_set h;
+  r1cs_group(rest, h);
+  std::vector<uint32_t> blocks, nblk;
+  stg_blockify(h.cls, h.terms, blocks, nblk, h.lo, h.hi);
+  h.terms.swap(blocks);
+  b3w_ctx::r1cs_dev d;
+  memset(&d, 0, sizeof d);
+  fastprog_dev P;
+  memset(&P, 0, sizeof P);
+  cudaError_t e = upload_vec(&d.cls, h.cls);
+  if (e == cudaSuccess) e = upload_vec(&d.nblk, nblk);
+  if (e == cudaSuccess) e = upload_vec(&d.lo, h.lo);
+  if (e == cudaSuccess) e = upload_vec(&d.hi, h.hi);
+  if (e == cudaSuccess) e = upload_vec(&d.terms, h.terms);
+  if (e == cudaSuccess) e = upload_vec(&d.coef_fr, h.coef_fr);
+  if (e == cudaSuccess) e = upload_vec(&d.row_ids, h.row_ids);
+  if (e == cudaSuccess) e = upload_vec(&P.bool_mask, fp.bool_mask);
+  if (e == cudaSuccess) e = upload_vec(&P.bool_row, fp.bool_row);
+  if (e == cudaSuccess) e = upload_vec(&P.xors, fp.xors);
+  if (e == cudaSuccess) e = upload_vec(&P.xor_ids, fp.xor_ids);
+  if (e == cudaSuccess) e = upload_vec(&P.tiles, fp.tiles);
+  if (e == cudaSuccess) e = upload_vec(&P.items, fp.items);
+  if (e == cudaSuccess) e = upload_vec(&P.row_ids, fp.row_ids);
+  if (e != cudaSuccess) {
+    free_r1cs_dev(&d);
+    free_fastprog(&P);
+    return fail(B3W_ERR_CUDA, "R1CS table upload: %s", cudaGetErrorString(e));
+  }
+  d.ncls = (uint32_t)h.cls.size();
+  d.rows = h.rows;
+  P.n_xors = (uint32_t)fp.xors.size();
+  P.n_tiles = (uint32_t)fp.tiles.size();
+  P.n_rows = fp.n_rows;
+  free_r1cs_dev(&c->r_slots);
+  free_fastprog(&c->fp);
+  c->r_slots = d;
+  c->fp = P;
+  c->slot_rows = (uint32_t)rows.size();
+  if (n_compiled) *n_compiled = fp.n_rows;
+  return B3W_OK;
+}
+
+// built-in slot-space rows (r1cs_tables.h) -> the row list install_slot_rows takes; row id = position in class order
+static bool rows_from_builtin(const circuit_def::r1cs_set &set, std::vector<r1cs_load_detail::row> &rows) {
+  r1cs_expanded x;
+  if (!expand_r1cs_set(set, x)) return false;
+  rows.clear();
+  rows.reserve(set.rows);
+  for (const r1cs_class_dev &k : x.cls) {
+    const uint32_t n[3] = {k.nA, k.nB, k.nC};
+    for (uint32_t r = 0; r < k.count; r++) {
+      r1cs_load_detail::row R;
+      R.id = k.row_off + r;
+      R.big = false;
+      uint32_t t = 0;
+      for (int part = 0; part < 3; part++)
+        for (uint32_t j = 0; j < n[part]; j++, t++) {
+          const uint32_t ci = (k.flags & R1CS_FLAG_ROWCOEF) ? k.coef_off + t * k.count + r : k.coef_off + t;
+          r1cs_load_detail::term T;
+          T.wire = x.terms[k.term_off + (size_t)t * k.count + r];
+          T.small = true;
+          T.c = (__int128)(((unsigned __int128)(uint64_t)x.hi[ci] << 64) | (unsigned __int128)(uint64_t)x.lo[ci]);
+          T.f = fr_zero();                                  // built-in coefficients are small integers: never read
+          R.part[part].push_back(T);
+        }
+      if (R.part[0].empty() || R.part[1].empty()) { R.part[0].clear(); R.part[1].clear(); }
+      rows.push_back(std::move(R));
+    }
+  }
+  return true;
+}
+
 static int ensure_r1cs(b3w_ctx *c) {
   if (c->r1cs_ready) return B3W_OK;
-  int rc = upload_r1cs_set(c, c->def->r_fused, &c->r_fused);
-  if (rc == B3W_OK && !c->r1cs_loaded) {
-    // Built-in slot-space rows: two evaluators.  "warp" = one warp per instance reading the witness in place (value kinds
-    // known offline, IsZero rows as two Montgomery products); "compact" = the general evaluator of loaded systems on a
-    // compact shared-memory copy (kernels_r1cs_compact.cuh).  Default = whichever measured faster on B200
-    // (profiles/r01i_r1cs_check.jsonl); B3W_STANDALONE_CHECK=warp|compact|staged overrides.
-    const char *e = getenv("B3W_STANDALONE_CHECK");
-    c->slots_staged = e ? (strcmp(e, "staged") == 0 || strcmp(e, "compact") == 0) : B3W_BUILTIN_COMPACT(c->def);
-    rc = upload_r1cs_set(c, c->def->r_slots, &c->r_slots, c->slots_staged);
+  int rc = c->r_fused.ncls ? B3W_OK : upload_fused_set(c, c->def->r_fused, &c->r_fused);
+  if (rc == B3W_OK && !c->r1cs_loaded && c->def->r_slots.ncls) {
+    std::vector<r1cs_load_detail::row> rows;
+    if (!rows_from_builtin(c->def->r_slots, rows)) return fail(B3W_ERR_INVALID, "R1CS tables of %s are corrupt", c->def->name);
+    rc = install_slot_rows(c, rows, nullptr);
   }
   if (rc == B3W_OK) c->r1cs_ready = true;
   return rc;
 }
 
+// where the witnesses of a launch go decides the work split (see launch_witness)
+static bool in_compressible_block(b3w_ctx *c, const void *p) {
+  if (c->blocks)
+    for (const vmm_block &b : *c->blocks)
+      if (b.compressed && (CUdeviceptr)p >= b.va && (CUdeviceptr)p < b.va + b.size) return true;
+  return false;
+}
+
+// A pair of work-item counter sets for one launch on stream s.  The pool rotates; before a pair is handed out again the
+// new launch's stream is made to wait for the launch that used it last (an event per pair), so more launches in flight
+// than the pool holds are serialised instead of corrupting each other's counters.
+static int take_counters(b3w_ctx *c, cudaStream_t s, unsigned long long **out, uint32_t *pair_out) {
+  if (!c->d_counters) CK(cudaMalloc(&c->d_counters, (size_t)N_SCHED_COUNTERS * SCHED_SET_U64 * sizeof(unsigned long long)));
+  const uint32_t pair = c->next_counter % (N_SCHED_COUNTERS / 2);
+  c->next_counter++;
+  if (!c->ctr_ev[pair]) CK(cudaEventCreateWithFlags(&c->ctr_ev[pair], cudaEventDisableTiming));
+  else CK(cudaStreamWaitEvent(s, c->ctr_ev[pair], 0));
+  *out = c->d_counters + (size_t)pair * 2 * SCHED_SET_U64;
+  *pair_out = pair;
+  CK(cudaMemsetAsync(*out, 0, 2 * SCHED_SET_U64 * sizeof(unsigned long long), s));
+  return B3W_OK;
+}
+
+struct launch_opts {
+  bool check = false;
+  uint32_t *d_first_bad = nullptr;
+  const int8_t *d_m_ext = nullptr;       // compression: the wide-domain kernel
+  unsigned long long *d_sums = nullptr;  // per-instance checksums (zeroed here)
+};
+
+template <bool CHECK, bool SUMS>
+static void launch_nova(b3w_ctx *c, unsigned grid, unsigned bs, cudaStream_t s, const uint32_t *d_in, uint64_t n, uint8_t *d_out,
+                        uint8_t *d_status, uint32_t *d_pub, const check_args &ck, const sched_args &sc, const sched_args &sck) {
+  k_blake3_nova_witness<CHECK, SUMS><<<grid, bs, NOVA_SMEM(WARPS_PER_CTA + (CHECK ? NOVA_CHECK_WARPS : 0)), s>>>(
+      d_in, n, c->d_desc, c->def->ws, c->d_field, c->d_fslots, c->n_fslots, d_out, d_status, d_pub, ck, sc, sck);
+}
+template <bool CHECK, bool WIDE, bool SUMS>
+static void launch_comp(b3w_ctx *c, unsigned grid, unsigned bs, cudaStream_t s, const uint32_t *d_in, uint64_t n, uint8_t *d_out,
+                        uint8_t *d_status, uint32_t *d_pub, const check_args &ck, const sched_args &sc, const sched_args &sck,
+                        const wide_args &wd) {
+  k_blake3_comp_witness<CHECK, WIDE, SUMS><<<grid, bs, 0, s>>>(d_in, n, c->d_desc, c->def->ws, d_out, d_status, d_pub, ck, sc, sck, wd);
+}
+
 static int launch_witness(b3w_ctx *c, const uint32_t *d_in, uint64_t n, uint8_t *d_out, uint8_t *d_status,
-                          uint32_t *d_pub, cudaStream_t s, bool check = false, uint32_t *d_first_bad = nullptr,
-                          const int8_t *d_m_ext = nullptr) {
+                          uint32_t *d_pub, cudaStream_t s, const launch_opts &o = launch_opts()) {
   if (n == 0) return B3W_OK;
-  if (d_m_ext && c->def->nova) return fail(B3W_ERR_UNSUPPORTED, "%s: only blake3_compression has a wide-domain kernel", c->def->name);
+  const bool check = o.check;
+  if (o.d_m_ext && c->def->nova) return fail(B3W_ERR_UNSUPPORTED, "%s: only blake3_compression has a wide-domain kernel", c->def->name);
   // Persistent grid, work items handed out dynamically (see sched_args).  Defaults from sweeps on B200 (profiles/):
   // fastest with only 2 CTAs per SM (16 expansion warps) and 24 items per witness (32 KiB each: the GPU-wide write front
   // stays compact).  The checked kernels have the same expansion shape plus CHECK_WARPS checker warps per CTA.
   // ... unless the witnesses go to COMPRESSIBLE memory (one of this context's b3w_device_alloc blocks): HBM is then no
   // longer the limit, the SM-side store path and the per-item trace recomputation are, and 12 items per witness measured
   // best across the four kernels (profiles/r01j_compressible.jsonl: nova + fused check 7.44 -> 6.49 ms per 2^16).
-  bool compressed_out = false;
-  if (c->blocks)
-    for (const vmm_block &b : *c->blocks)
-      compressed_out = compressed_out || (b.compressed && (CUdeviceptr)d_out >= b.va && (CUdeviceptr)d_out < b.va + b.size);
+  const bool compressed_out = in_compressible_block(c, d_out);
   const uint32_t parts = c->sched_parts ? c->sched_parts : compressed_out ? 12u : 24u;
   uint64_t ctas_needed = (n * parts + WARPS_PER_CTA - 1) / WARPS_PER_CTA;      // one warp per work item
   int per_sm = check ? c->ctas_per_sm_checked : c->ctas_per_sm;
@@ -551,59 +746,92 @@ static int launch_witness(b3w_ctx *c, const uint32_t *d_in, uint64_t n, uint8_t 
   check_args ck;
   memset(&ck, 0, sizeof ck);
   ck.fault_word = B3W_NO_ROW;
+  ck.sums = o.d_sums;
   if (check) {
     int rc = ensure_r1cs(c);
     if (rc) return rc;
     ck.T = r1cs_tables_dev{c->r_fused.cls, c->r_fused.lo, c->r_fused.hi, c->r_fused.terms, c->r_fused.ncls};
     ck.F = c->d_field;
-    ck.first_bad = d_first_bad;
+    ck.first_bad = o.d_first_bad;
     ck.fault_word = c->fault_word;
     ck.fault_mask = c->fault_mask;
   }
   const unsigned bs = (WARPS_PER_CTA + (check ? (c->def->nova ? NOVA_CHECK_WARPS : CHECK_WARPS) : 0)) * 32;
   // work distribution (see sched_args): expansion items, and -- checked kernels -- one check item per instance
   sched_args sc, sck;
-  if (!c->d_counters) CK(cudaMalloc(&c->d_counters, (size_t)N_SCHED_COUNTERS * SCHED_SET_U64 * sizeof(unsigned long long)));
-  const uint32_t set0 = c->next_counter % N_SCHED_COUNTERS;         // two consecutive counter sets (N_SCHED_COUNTERS is even)
-  c->next_counter += 2;
-  sc.counter = c->d_counters + (size_t)set0 * SCHED_SET_U64;
+  uint32_t pair;
+  int rc = take_counters(c, s, &sc.counter, &pair);
+  if (rc) return rc;
   sc.parts = parts;
   sc.part_len = ((c->def->ws + sc.parts - 1) / sc.parts + 31) / 32 * 32;
   sck.counter = sc.counter + SCHED_SET_U64;
   sck.parts = 1;
   sck.part_len = 0;
-  CK(cudaMemsetAsync(sc.counter, 0, 2 * SCHED_SET_U64 * sizeof(unsigned long long), s));
+  if (o.d_sums) CK(cudaMemsetAsync(o.d_sums, 0, n * sizeof(unsigned long long), s));
+  const bool sums = o.d_sums != nullptr;
   if (c->def->nova) {
-    if (check) k_blake3_nova_witness<true><<<grid, bs, NOVA_SMEM(WARPS_PER_CTA + NOVA_CHECK_WARPS), s>>>(d_in, n, c->d_desc, c->def->ws, c->d_field, c->d_fslots, c->n_fslots, d_out, d_status, d_pub, ck, sc, sck);
-    else k_blake3_nova_witness<false><<<grid, bs, NOVA_SMEM(WARPS_PER_CTA), s>>>(d_in, n, c->d_desc, c->def->ws, c->d_field, c->d_fslots, c->n_fslots, d_out, d_status, d_pub, ck, sc, sck);
+    if (check) { if (sums) launch_nova<true, true>(c, grid, bs, s, d_in, n, d_out, d_status, d_pub, ck, sc, sck); else launch_nova<true, false>(c, grid, bs, s, d_in, n, d_out, d_status, d_pub, ck, sc, sck); }
+    else { if (sums) launch_nova<false, true>(c, grid, bs, s, d_in, n, d_out, d_status, d_pub, ck, sc, sck); else launch_nova<false, false>(c, grid, bs, s, d_in, n, d_out, d_status, d_pub, ck, sc, sck); }
   } else {
-    const wide_args wd{d_m_ext, c->d_field, c->m_slot0};
-    if (d_m_ext) {
-      if (check) k_blake3_comp_witness<true, true><<<grid, bs, 0, s>>>(d_in, n, c->d_desc, c->def->ws, d_out, d_status, d_pub, ck, sc, sck, wd);
-      else k_blake3_comp_witness<false, true><<<grid, bs, 0, s>>>(d_in, n, c->d_desc, c->def->ws, d_out, d_status, d_pub, ck, sc, sck, wd);
+    const wide_args wd{o.d_m_ext, c->d_field, c->m_slot0};
+#define B3W_COMP(CH, WI, SU) launch_comp<CH, WI, SU>(c, grid, bs, s, d_in, n, d_out, d_status, d_pub, ck, sc, sck, wd)
+    if (o.d_m_ext) {
+      if (check) { if (sums) B3W_COMP(true, true, true); else B3W_COMP(true, true, false); }
+      else { if (sums) B3W_COMP(false, true, true); else B3W_COMP(false, true, false); }
     } else {
-      if (check) k_blake3_comp_witness<true, false><<<grid, bs, 0, s>>>(d_in, n, c->d_desc, c->def->ws, d_out, d_status, d_pub, ck, sc, sck, wd);
-      else k_blake3_comp_witness<false, false><<<grid, bs, 0, s>>>(d_in, n, c->d_desc, c->def->ws, d_out, d_status, d_pub, ck, sc, sck, wd);
+      if (check) { if (sums) B3W_COMP(true, false, true); else B3W_COMP(true, false, false); }
+      else { if (sums) B3W_COMP(false, false, true); else B3W_COMP(false, false, false); }
     }
+#undef B3W_COMP
   }
   CK(cudaGetLastError());
+  CK(cudaEventRecord(c->ctr_ev[pair], s));
+  return B3W_OK;
+}
+
+static int check_device_args(const char *who, b3w_ctx *c, const void *d_in, const void *d_out) {
+  if (!c || !d_in || !d_out) return fail(B3W_ERR_INVALID, "%s: null argument", who);
+  if (((uintptr_t)d_out & 31) != 0) return fail(B3W_ERR_INVALID, "d_out must be 32-byte aligned");
   return B3W_OK;
 }
 
 extern "C" int b3w_witness_batch_device(b3w_ctx *c, const uint32_t *d_in, uint64_t n, uint8_t *d_out,
                                         uint8_t *d_status, uint32_t *d_pub, void *stream) {
-  if (!c || !d_in || !d_out) return fail(B3W_ERR_INVALID, "b3w_witness_batch_device: null argument");
-  if (((uintptr_t)d_out & 31) != 0) return fail(B3W_ERR_INVALID, "d_out must be 32-byte aligned");
-  CK(cudaSetDevice(c->device));
-  return launch_witness(c, d_in, n, d_out, d_status, d_pub, (cudaStream_t)stream, (c->flags & B3W_FLAG_FUSED_CHECK) != 0);
+  int rc = check_device_args("b3w_witness_batch_device", c, d_in, d_out);
+  if (rc) return rc;
+  ON_DEVICE(c);
+  LOCKED(c);
+  launch_opts o;
+  o.check = (c->flags & B3W_FLAG_FUSED_CHECK) != 0;
+  return launch_witness(c, d_in, n, d_out, d_status, d_pub, (cudaStream_t)stream, o);
 }
 
 extern "C" int b3w_witness_batch_device_checked(b3w_ctx *c, const uint32_t *d_in, uint64_t n, uint8_t *d_out,
                                                 uint8_t *d_status, uint32_t *d_pub, uint32_t *d_first_bad, void *stream) {
-  if (!c || !d_in || !d_out) return fail(B3W_ERR_INVALID, "b3w_witness_batch_device_checked: null argument");
-  if (((uintptr_t)d_out & 31) != 0) return fail(B3W_ERR_INVALID, "d_out must be 32-byte aligned");
-  CK(cudaSetDevice(c->device));
-  return launch_witness(c, d_in, n, d_out, d_status, d_pub, (cudaStream_t)stream, true, d_first_bad);
+  int rc = check_device_args("b3w_witness_batch_device_checked", c, d_in, d_out);
+  if (rc) return rc;
+  ON_DEVICE(c);
+  LOCKED(c);
+  launch_opts o;
+  o.check = true;
+  o.d_first_bad = d_first_bad;
+  return launch_witness(c, d_in, n, d_out, d_status, d_pub, (cudaStream_t)stream, o);
+}
+
+extern "C" int b3w_witness_batch_device_ex(b3w_ctx *c, const uint32_t *d_in, const int8_t *d_m_ext, uint64_t n, uint8_t *d_out,
+                                           uint8_t *d_status, uint32_t *d_pub, uint32_t *d_first_bad, uint64_t *d_sums, int check,
+                                           void *stream) {
+  int rc = check_device_args("b3w_witness_batch_device_ex", c, d_in, d_out);
+  if (rc) return rc;
+  if (d_sums && ((uintptr_t)d_sums & 7) != 0) return fail(B3W_ERR_INVALID, "d_sums must be 8-byte aligned");
+  ON_DEVICE(c);
+  LOCKED(c);
+  launch_opts o;
+  o.check = check != 0 || d_first_bad != nullptr || (c->flags & B3W_FLAG_FUSED_CHECK) != 0;
+  o.d_first_bad = d_first_bad;
+  o.d_m_ext = d_m_ext;
+  o.d_sums = (unsigned long long *)d_sums;
+  return launch_witness(c, d_in, n, d_out, d_status, d_pub, (cudaStream_t)stream, o);
 }
 
 extern "C" int b3w_r1cs_info(uint32_t circuit, uint32_t *n_rows, uint32_t *n_terms) {
@@ -614,90 +842,86 @@ extern "C" int b3w_r1cs_info(uint32_t circuit, uint32_t *n_rows, uint32_t *n_ter
   return B3W_OK;
 }
 
+// instances [0, n) of d_wit; or -- listed -- the instances d_list[1 .. d_list[0]] (a device-side list: the count is read by
+// the kernel), skipping those whose status says "Assert Failed." (no witness was written for them)
+static int r1cs_check_launch(b3w_ctx *c, const uint8_t *d_wit, const uint32_t *d_list, uint64_t n, uint8_t *d_status, uint32_t *d_first_bad,
+                             cudaStream_t s, bool listed = false) {
+  int rc = ensure_r1cs(c);
+  if (rc) return rc;
+  if (c->slot_rows == 0) return fail(B3W_ERR_UNSUPPORTED, "%s: no constraint system for the stand-alone check", c->def->name);
+  if (n == 0) return B3W_OK;
+  const r1cs_tables_dev T{c->r_slots.cls, c->r_slots.lo, c->r_slots.hi, c->r_slots.terms, c->r_slots.ncls, c->r_slots.coef_fr, c->r_slots.row_ids, c->r_slots.nblk};
+  const uint32_t mw = ((c->def->ws + 31u) >> 5) + 1u;
+  const size_t smem = (size_t)((3 * mw + 1) & ~1u) * 4 + (size_t)FPK_SIDE_MAX * 8;
+  CK(cudaFuncSetAttribute(k_r1cs_check_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int per_sm = c->ctas_limit > 0 ? c->ctas_limit : FPK_CTAS_PER_SM;
+  const uint64_t cap = (uint64_t)c->sm_count * per_sm;
+  k_r1cs_check_fast<<<(unsigned)(n < cap ? n : cap), FPK_THREADS, smem, s>>>(d_wit, listed ? d_list : nullptr, n, c->def->ws, c->fp, T, c->d_field, d_status,
+                                                                             d_first_bad);
+  CK(cudaGetLastError());
+  return B3W_OK;
+}
+
 extern "C" int b3w_r1cs_check_device(b3w_ctx *c, const uint8_t *d_wit, uint64_t n, uint8_t *d_status,
                                      uint32_t *d_first_bad, void *stream) {
   if (!c || !d_wit) return fail(B3W_ERR_INVALID, "b3w_r1cs_check_device: null argument");
-  if (((uintptr_t)d_wit & 15) != 0) return fail(B3W_ERR_INVALID, "d_wit must be 16-byte aligned");
-  CK(cudaSetDevice(c->device));
+  if (((uintptr_t)d_wit & 31) != 0) return fail(B3W_ERR_INVALID, "d_wit must be 32-byte aligned");
+  ON_DEVICE(c);
+  LOCKED(c);
+  return r1cs_check_launch(c, d_wit, nullptr, n, d_status, d_first_bad, (cudaStream_t)stream);
+}
+
+// how the loaded / built-in system was split: rows the compiled program covers, rows left to the general evaluator
+extern "C" int b3w_r1cs_program_info(b3w_ctx *c, uint32_t *n_rows, uint32_t *n_compiled, uint32_t *n_xor_runs, uint32_t *n_tiles) {
+  if (!c) return fail(B3W_ERR_INVALID, "b3w_r1cs_program_info: null argument");
+  ON_DEVICE(c);
+  LOCKED(c);
   int rc = ensure_r1cs(c);
   if (rc) return rc;
-  if (c->r_slots.ncls == 0)
-    return fail(B3W_ERR_UNSUPPORTED, "%s: circom's O2 pass removed signals that the built-in template-level rows refer to; load the "
-                "O2-form system with b3w_r1cs_load (tools/export_r1cs.py writes it) or use the fused check", c->def->name);
-  if (n == 0) return B3W_OK;
-  r1cs_tables_dev T{c->r_slots.cls, c->r_slots.lo, c->r_slots.hi, c->r_slots.terms, c->r_slots.ncls, c->r_slots.coef_fr, c->r_slots.row_ids, c->r_slots.nblk};
-  if (!c->slots_staged) {
-    // built-in rows (value kinds known offline: exact 64/128-bit integer classes + IsZero rows in Fr): one warp per instance
-    uint64_t ctas = (n + 7) / 8, cap8 = (uint64_t)c->sm_count * 8;
-    k_r1cs_check_witness<<<(unsigned)(ctas < cap8 ? ctas : cap8), 256, 0, (cudaStream_t)stream>>>(d_wit, n, c->def->ws, T, c->d_field,
-                                                                                                d_status, d_first_bad);
-    CK(cudaGetLastError());
-    return B3W_OK;
-  }
-  // a loaded system: the general evaluators (one CTA per instance, Fr fallback)
-  const char *mode = getenv("B3W_STANDALONE_CHECK");
-  if (!(mode && strcmp(mode, "staged") == 0)) {
-    // compact shared-memory copy of the witness (2 bits per slot + a side table): several CTAs per SM
-    const uint32_t words = (c->def->ws + 31u) >> 5;
-    const size_t smem_c = (size_t)((3 * words + 2) & ~1u) * 4 + (size_t)CPT_SIDE_MAX * 8;
-    CK(cudaFuncSetAttribute(k_r1cs_check_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
-    const uint64_t cap_c = (uint64_t)c->sm_count * CPT_CTAS_PER_SM;
-    k_r1cs_check_compact<<<(unsigned)(n < cap_c ? n : cap_c), CPT_THREADS, smem_c, (cudaStream_t)stream>>>(d_wit, n, c->def->ws, T, c->d_field,
-                                                                                                           d_status, d_first_bad);
-    CK(cudaGetLastError());
-    return B3W_OK;
-  }
-  // B3W_STANDALONE_CHECK=staged: witness staged with 8 bytes per slot, one CTA per SM (kept for comparison)
-  const size_t smem = (size_t)((c->def->ws + 1) & ~1u) * 8 + (size_t)STG_MAX_BIG * 32;
-  CK(cudaFuncSetAttribute(k_r1cs_check_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const uint64_t cap = (uint64_t)c->sm_count;
-  k_r1cs_check_staged<<<(unsigned)(n < cap ? n : cap), STG_THREADS, smem, (cudaStream_t)stream>>>(d_wit, n, c->def->ws, T, c->d_field,
-                                                                                                 d_status, d_first_bad);
-  CK(cudaGetLastError());
+  if (n_rows) *n_rows = c->slot_rows;
+  if (n_compiled) *n_compiled = c->fp.n_rows;
+  if (n_xor_runs) *n_xor_runs = c->fp.n_xors;
+  if (n_tiles) *n_tiles = c->fp.n_tiles;
   return B3W_OK;
+}
+
+// host-only: what fp_compile makes of a circuit's built-in system (needs no GPU; tests/test_abi.py pins the numbers)
+static int b3w_r1cs_compile_stats_impl(uint32_t circuit, uint32_t *n_rows, uint32_t *n_compiled, uint32_t *n_xor_runs, uint32_t *n_tiles, uint32_t *n_items) {
+  const circuit_def *d = find_def(circuit);
+  if (!d) return B3W_ERR_UNSUPPORTED;
+  std::vector<r1cs_load_detail::row> rows;
+  if (!rows_from_builtin(d->r_slots, rows)) return fail(B3W_ERR_INVALID, "R1CS tables of %s are corrupt", d->name);
+  fastprog_host fp;
+  std::vector<char> taken;
+  fp_compile(rows, d->ws, fp, taken);
+  if (n_rows) *n_rows = (uint32_t)rows.size();
+  if (n_compiled) *n_compiled = fp.n_rows;
+  if (n_xor_runs) *n_xor_runs = (uint32_t)fp.xors.size();
+  if (n_tiles) *n_tiles = (uint32_t)fp.tiles.size();
+  if (n_items) *n_items = (uint32_t)fp.items.size();
+  return B3W_OK;
+}
+extern "C" int b3w_r1cs_compile_stats(uint32_t circuit, uint32_t *n_rows, uint32_t *n_compiled, uint32_t *n_xor_runs, uint32_t *n_tiles, uint32_t *n_items) {
+  return guarded("b3w_r1cs_compile_stats", [&]() { return b3w_r1cs_compile_stats_impl(circuit, n_rows, n_compiled, n_xor_runs, n_tiles, n_items); });
 }
 
 // Replace the built-in slot-space row set of this context by the constraint system of an iden3 `.r1cs` file: the
 // reference's own build/*.r1cs where the user has them, or the equivalents written by tools/export_r1cs.py.
 static int b3w_r1cs_load_impl(b3w_ctx *c, const uint8_t *data, size_t len, uint32_t *n_rows) {
   if (!c || !data) return fail(B3W_ERR_INVALID, "b3w_r1cs_load: null argument");
-  CK(cudaSetDevice(c->device));
-  r1cs_host_set h;
+  ON_DEVICE(c);
+  LOCKED(c);
+  r1cs_host_set hdr;
+  std::vector<r1cs_load_detail::row> rows;
   std::string err;
-  int rc = r1cs_parse(data, len, c->def->prime, c->def->ws, h, err);
+  int rc = r1cs_parse_rows(data, len, c->def->prime, c->def->ws, rows, hdr, err);
   if (rc) return fail(rc, "b3w_r1cs_load: %s", err.c_str());
-  if (h.cls.size() > STG_MAX_CLASSES)
-    return fail(B3W_ERR_UNSUPPORTED, "b3w_r1cs_load: %zu shape classes (the checker holds %d)", h.cls.size(), STG_MAX_CLASSES);
-  std::vector<uint32_t> blocks, nblk;
-  stg_blockify(h.cls, h.terms, blocks, nblk, h.lo, h.hi);
-  h.terms.swap(blocks);
-  b3w_ctx::r1cs_dev d;
-  memset(&d, 0, sizeof d);
-  cudaError_t e = cudaMalloc(&d.cls, h.cls.size() * sizeof(r1cs_class_dev) + 16);
-  if (e == cudaSuccess) e = cudaMalloc(&d.nblk, nblk.size() * 4 + 16);
-  if (e == cudaSuccess && !nblk.empty()) e = cudaMemcpy(d.nblk, nblk.data(), nblk.size() * 4, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMalloc(&d.lo, h.lo.size() * 8);
-  if (e == cudaSuccess) e = cudaMalloc(&d.hi, h.hi.size() * 8);
-  if (e == cudaSuccess) e = cudaMalloc(&d.terms, h.terms.size() * 4 + 16);
-  if (e == cudaSuccess) e = cudaMalloc(&d.coef_fr, h.coef_fr.size() * sizeof(fr_t));
-  if (e == cudaSuccess) e = cudaMalloc(&d.row_ids, h.row_ids.size() * 4 + 16);
-  if (e == cudaSuccess && !h.cls.empty()) e = cudaMemcpy(d.cls, h.cls.data(), h.cls.size() * sizeof(r1cs_class_dev), cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(d.lo, h.lo.data(), h.lo.size() * 8, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(d.hi, h.hi.data(), h.hi.size() * 8, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess && !h.terms.empty()) e = cudaMemcpy(d.terms, h.terms.data(), h.terms.size() * 4, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(d.coef_fr, h.coef_fr.data(), h.coef_fr.size() * sizeof(fr_t), cudaMemcpyHostToDevice);
-  if (e == cudaSuccess && !h.row_ids.empty()) e = cudaMemcpy(d.row_ids, h.row_ids.data(), h.row_ids.size() * 4, cudaMemcpyHostToDevice);
-  if (e != cudaSuccess) {
-    free_r1cs_dev(&d);
-    return fail(B3W_ERR_CUDA, "b3w_r1cs_load: %s", cudaGetErrorString(e));
-  }
-  d.ncls = (uint32_t)h.cls.size();
-  d.rows = h.rows;
-  free_r1cs_dev(&c->r_slots);
-  c->r_slots = d;
+  const uint32_t m = (uint32_t)rows.size();
+  CK(cudaDeviceSynchronize());                       // no check kernel may still be reading the tables that are replaced
+  rc = install_slot_rows(c, rows, nullptr);
+  if (rc) return rc;
   c->r1cs_loaded = true;
-  c->slots_staged = true;
-  if (n_rows) *n_rows = h.rows;
+  if (n_rows) *n_rows = m;
   return B3W_OK;
 }
 extern "C" int b3w_r1cs_load(b3w_ctx *c, const uint8_t *data, size_t len, uint32_t *n_rows) {
@@ -735,18 +959,30 @@ extern "C" int b3w_debug_set_launch(b3w_ctx *c, int ctas_per_sm, uint32_t parts)
   return B3W_OK;
 }
 
+extern "C" int b3w_debug_set_store_mode(b3w_ctx *c, int mode) {
+  if (!c || mode < 0 || mode > 1) return fail(B3W_ERR_INVALID, "b3w_debug_set_store_mode: bad argument");
+  LOCKED(c);
+  c->store_mode = mode;
+  return B3W_OK;
+}
+
 static int alloc_ring(b3w_ctx *c) {
   const circuit_def *d = c->def;
   for (int k = 0; k < 2; k++) {
     CK(cudaStreamCreateWithFlags(&c->st[k], cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->ev[k], cudaEventDisableTiming));
-    // compressible when asked for and obtainable; a driver without the virtual-memory entry points gets ordinary memory
-    if (!(c->flags & B3W_FLAG_COMPRESSIBLE_RING) ||
+    CK(cudaEventCreate(&c->ev_k0[k]));
+    CK(cudaEventCreate(&c->ev_k1[k]));
+    // compressible unless the caller asked for ordinary memory; a driver without the virtual-memory entry points (or a
+    // device that does not grant compression) silently gets ordinary memory -- one default in C, Python and the N-API addon
+    if ((c->flags & B3W_FLAG_PLAIN_RING) ||
         device_alloc(c, (size_t)c->chunk * d->ws * 32, B3W_MEM_COMPRESSIBLE, (void **)&c->d_ring[k]) != B3W_OK)
       CK(cudaMalloc(&c->d_ring[k], (size_t)c->chunk * d->ws * 32));
     CK(cudaMalloc(&c->d_in[k], (size_t)c->chunk * d->n_inputs * 4));
     CK(cudaMalloc(&c->d_status[k], (size_t)c->chunk));
     CK(cudaMalloc(&c->d_pub[k], (size_t)c->chunk * d->n_public * 4));
+    CK(cudaMalloc(&c->d_sums[k], (size_t)c->chunk * 8));
+    CK(cudaMalloc(&c->d_fbad[k], (size_t)c->chunk * 4));
     if (!d->nova) CK(cudaMalloc(&c->d_ext[k], (size_t)c->chunk * 16));
   }
   return B3W_OK;
@@ -759,53 +995,227 @@ static int ensure_ring(b3w_ctx *c) {
   c->ring_ready = true;
   return B3W_OK;
 }
+// staging of Fr256 input rows (b3w_witness_batch_fr): allocated on first use
+static int ensure_fr_staging(b3w_ctx *c) {
+  if (c->fr_ready) return B3W_OK;
+  for (int k = 0; k < 2; k++) {
+    CK(cudaMalloc(&c->d_fr[k], (size_t)c->chunk * c->def->n_inputs * 32));
+    if (c->def->nova) CK(cudaMalloc(&c->d_wlist[k], ((size_t)c->chunk + 1) * 4));
+  }
+  c->fr_ready = true;
+  return B3W_OK;
+}
+
+// ---- per-call timing (b3w_last_timing) ---------------------------------------------------------------------------------
+static void timing_begin(b3w_ctx *c) {
+  memset(&c->timing, 0, sizeof c->timing);
+  c->timing.total_ms = -now_ms();
+}
+// the kernel events of slot k have been recorded and their stream has drained: add the launch to the call's total
+static void timing_collect(b3w_ctx *c, int k) {
+  if (!c->ev_pending[k]) return;
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, c->ev_k0[k], c->ev_k1[k]) == cudaSuccess) c->timing.kernel_ms += ms;
+  c->ev_pending[k] = false;
+}
+static void timing_end(b3w_ctx *c) {
+  for (int k = 0; k < 2; k++) timing_collect(c, k);
+  c->timing.total_ms += now_ms();
+}
+extern "C" int b3w_last_timing(b3w_ctx *c, b3w_timing *out) {
+  if (!c || !out) return fail(B3W_ERR_INVALID, "b3w_last_timing: null argument");
+  LOCKED(c);
+  *out = c->timing;
+  return B3W_OK;
+}
+
+// ---- nova step circuits on field-element inputs (kernels_nova_wide.cuh) ---------------------------------------------
+// trace words whose value is a function of a possibly field-valued input: the slots that read them through a W32 / W64 /
+// S64 / INV descriptor are rewritten by the wide kernel's override pass
+static bool nova_field_word(uint32_t t) {
+  return (t >= NV_IN && t < NV_IN + 32) || t == NV_LDM1 || t == NV_DP1 || t == NV_DEPTH_OUT || (t >= NV_NEG_DEPTH && t < NV_BC_OUT + 2) ||
+         (t >= NV_TMP_DOWN && t < NV_EQ_D + 128) || (t >= TR_IN + 8 && t < TR_IN + 24);
+}
+static int ensure_nova_wide(b3w_ctx *c) {
+  if (c->nw_ready) return B3W_OK;
+  const circuit_def *d = c->def;
+  std::vector<uint2> lanes[32];
+  for (uint32_t sl = 0; sl < d->ws; sl++) {
+    const uint32_t dsc = c->h_desc[sl], kind = dsc >> 24, t = dsc & 0xFFFFu;
+    if (kind >= DK_W32 && nova_field_word(t)) lanes[sl & 31].push_back(make_uint2(sl, dsc));
+    else if (kind >= DK_S64) return fail(B3W_ERR_INVALID, "slot table of %s: field slot %u is not covered by the wide kernel", d->name, sl);
+    // Num2Bits(65).out[64]: constant 0 for u32 inputs; present in the O1 build only, right after out[63]
+    if (dsc == ((DK_BIT << 24) | (31u << 16) | (NV_IN + 11)) && sl + 1 < d->ws && c->h_desc[sl + 1] == ((DK_W32 << 24) | TR_ZERO))
+      lanes[(sl + 1) & 31].push_back(make_uint2(sl + 1, DK_WIDE_BIT64 << 24));
+  }
+  std::vector<uint2> all;
+  uint32_t off[33];
+  for (int l = 0; l < 32; l++) {
+    off[l] = (uint32_t)all.size();
+    all.insert(all.end(), lanes[l].begin(), lanes[l].end());
+  }
+  off[32] = (uint32_t)all.size();
+  for (void **q : {(void **)&c->d_wslots, (void **)&c->d_lane_off})       // a failed earlier attempt
+    if (*q) { cudaFree(*q); *q = nullptr; }
+  CK(cudaMalloc(&c->d_wslots, all.size() * sizeof(uint2) + 16));
+  CK(cudaMemcpy(c->d_wslots, all.data(), all.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&c->d_lane_off, sizeof off));
+  CK(cudaMemcpy(c->d_lane_off, off, sizeof off, cudaMemcpyHostToDevice));
+  CK(cudaFuncSetAttribute(k_blake3_nova_witness_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, NW_WARPS * NW_STRIDE * 4));
+  c->nw_ready = true;
+  return B3W_OK;
+}
+
+// What one host-buffer batch call is made of.  Exactly one of `in` (u32 rows) / `in_fr` (Fr256 rows) is set.
+struct batch_job {
+  const uint32_t *in = nullptr;
+  const uint8_t *in_fr = nullptr;
+  const int8_t *m_ext = nullptr;      // with `in`, compression only: the wide-domain kernel
+  uint64_t n = 0;
+  uint8_t *out = nullptr;
+  uint8_t *status = nullptr;
+  uint32_t *pub = nullptr;
+  b3w_batch_extras ex = {};
+};
 
 // Host-buffer batches: chunks of c->chunk instances through the two ring slots; chunk j runs on stream j & 1 and its D2H
-// overlaps the next chunk's kernel.  m_ext != NULL selects the wide-domain kernel (compression only).
-static int batch_chunks(b3w_ctx *c, const uint32_t *in, const int8_t *m_ext, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub) {
+// overlaps the next chunk's kernel.
+static int batch_chunks(b3w_ctx *c, const batch_job &J) {
   const circuit_def *d = c->def;
   const size_t wbytes = (size_t)d->ws * 32;
+  const bool check = (c->flags & B3W_FLAG_FUSED_CHECK) != 0;
+  // the sample instances in index order: every chunk copies the ones it holds out of its ring slot
+  std::vector<std::pair<uint64_t, uint32_t>> samples;
+  for (uint32_t j = 0; j < J.ex.n_samples; j++) samples.push_back({J.ex.sample_idx[j], j});
+  std::sort(samples.begin(), samples.end());
+  size_t sp = 0;
   uint64_t done = 0;
   int k = 0;
-  while (done < n) {
-    uint64_t m = n - done < c->chunk ? n - done : c->chunk;
+  while (done < J.n) {
+    const uint64_t m = J.n - done < c->chunk ? J.n - done : c->chunk;
     cudaStream_t s = c->st[k];
-    CK(cudaMemcpyAsync(c->d_in[k], in + done * d->n_inputs, (size_t)m * d->n_inputs * 4, cudaMemcpyHostToDevice, s));
-    if (m_ext) CK(cudaMemcpyAsync(c->d_ext[k], m_ext + done * 16, (size_t)m * 16, cudaMemcpyHostToDevice, s));
-    int rc = launch_witness(c, c->d_in[k], m, c->d_ring[k], c->d_status[k], c->d_pub[k], s, (c->flags & B3W_FLAG_FUSED_CHECK) != 0,
-                            nullptr, m_ext ? c->d_ext[k] : nullptr);
-    if (rc) return rc;
-    if (out) CK(cudaMemcpyAsync(out + done * wbytes, c->d_ring[k], (size_t)m * wbytes, cudaMemcpyDeviceToHost, s));
-    if (status) CK(cudaMemcpyAsync(status + done, c->d_status[k], (size_t)m, cudaMemcpyDeviceToHost, s));
-    if (pub) CK(cudaMemcpyAsync(pub + done * d->n_public, c->d_pub[k], (size_t)m * d->n_public * 4, cudaMemcpyDeviceToHost, s));
+    launch_opts o;
+    o.check = check;
+    o.d_first_bad = (check && J.ex.first_bad) ? c->d_fbad[k] : nullptr;
+    o.d_sums = J.ex.sums ? (unsigned long long *)c->d_sums[k] : nullptr;
+    {
+      nvtx_range r("b3w:h2d");
+      if (J.in_fr) {
+        const size_t fb = (size_t)m * d->n_inputs * 32;
+        CK(cudaMemcpyAsync(c->d_fr[k], J.in_fr + done * d->n_inputs * 32, fb, cudaMemcpyHostToDevice, s));
+        c->timing.h2d_bytes += fb;
+        const unsigned grid = (unsigned)std::min<uint64_t>((m + 7) / 8, (uint64_t)c->sm_count * 8);
+        if (d->nova) {
+          CK(cudaMemsetAsync(c->d_wlist[k], 0, 4, s));
+          k_fr_to_rows_nova<<<grid, 256, 0, s>>>(c->d_fr[k], m, c->d_field, c->d_in[k], c->d_wlist[k]);
+        } else {
+          k_fr_to_rows_compression<<<grid, 256, 0, s>>>(c->d_fr[k], m, c->d_field, c->d_in[k], c->d_ext[k]);
+          o.d_m_ext = c->d_ext[k];
+        }
+        CK(cudaGetLastError());
+      } else {
+        CK(cudaMemcpyAsync(c->d_in[k], J.in + done * d->n_inputs, (size_t)m * d->n_inputs * 4, cudaMemcpyHostToDevice, s));
+        c->timing.h2d_bytes += (size_t)m * d->n_inputs * 4;
+        if (J.m_ext) {
+          CK(cudaMemcpyAsync(c->d_ext[k], J.m_ext + done * 16, (size_t)m * 16, cudaMemcpyHostToDevice, s));
+          c->timing.h2d_bytes += (size_t)m * 16;
+          o.d_m_ext = c->d_ext[k];
+        }
+      }
+    }
+    {
+      nvtx_range r("b3w:kernel");
+      CK(cudaEventRecord(c->ev_k0[k], s));
+      int rc = launch_witness(c, c->d_in[k], m, c->d_ring[k], c->d_status[k], c->d_pub[k], s, o);
+      if (rc) return rc;
+      if (J.in_fr && d->nova) {
+        // the instances of the wide list (field-valued inputs): the general kernel fills their places; with the fused-check
+        // flag their witnesses are then checked where they lie (the stand-alone evaluator, on the listed instances only)
+        const nova_wide_args wa{c->d_fr[k], c->d_wslots, c->d_lane_off, c->d_field};
+        k_blake3_nova_witness_wide<<<c->sm_count * 4, NW_WARPS * 32, NW_WARPS * NW_STRIDE * 4, s>>>(
+            wa, c->d_wlist[k], m, c->d_desc, d->ws, c->d_ring[k], c->d_status[k], c->d_pub[k], o.d_sums);
+        CK(cudaGetLastError());
+        if (check) {
+          rc = r1cs_check_launch(c, c->d_ring[k], c->d_wlist[k], m, c->d_status[k], o.d_first_bad, s, /*listed=*/true);
+          if (rc) return rc;
+        }
+      }
+      CK(cudaEventRecord(c->ev_k1[k], s));
+      c->ev_pending[k] = true;
+      c->timing.launches++;
+    }
+    {
+      nvtx_range r("b3w:d2h");
+      size_t bytes = 0;
+      if (J.out) { CK(cudaMemcpyAsync(J.out + done * wbytes, c->d_ring[k], (size_t)m * wbytes, cudaMemcpyDeviceToHost, s)); bytes += (size_t)m * wbytes; }
+      if (J.status) { CK(cudaMemcpyAsync(J.status + done, c->d_status[k], (size_t)m, cudaMemcpyDeviceToHost, s)); bytes += m; }
+      if (J.pub) { CK(cudaMemcpyAsync(J.pub + done * d->n_public, c->d_pub[k], (size_t)m * d->n_public * 4, cudaMemcpyDeviceToHost, s)); bytes += (size_t)m * d->n_public * 4; }
+      if (J.ex.sums) { CK(cudaMemcpyAsync(J.ex.sums + done, c->d_sums[k], (size_t)m * 8, cudaMemcpyDeviceToHost, s)); bytes += (size_t)m * 8; }
+      if (o.d_first_bad) { CK(cudaMemcpyAsync(J.ex.first_bad + done, c->d_fbad[k], (size_t)m * 4, cudaMemcpyDeviceToHost, s)); bytes += (size_t)m * 4; }
+      for (; sp < samples.size() && samples[sp].first < done + m; sp++) {
+        CK(cudaMemcpyAsync(J.ex.sample_out + (size_t)samples[sp].second * wbytes, c->d_ring[k] + (samples[sp].first - done) * wbytes, wbytes,
+                           cudaMemcpyDeviceToHost, s));
+        bytes += wbytes;
+      }
+      c->timing.d2h_bytes += bytes;
+    }
     done += m;
     k ^= 1;
     // before reusing slot k (two chunks ago) its stream must have drained
-    if (done < n) CK(cudaStreamSynchronize(c->st[k]));
+    if (done < J.n) {
+      CK(cudaStreamSynchronize(c->st[k]));
+      timing_collect(c, k);
+    }
   }
   return B3W_OK;
 }
-static int batch_host(b3w_ctx *c, const uint32_t *in, const int8_t *m_ext, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub) {
-  CK(cudaSetDevice(c->device));
+
+static int batch_host(b3w_ctx *c, const batch_job &J, const char *who) {
+  const b3w_batch_extras &ex = J.ex;
+  if (ex.n_samples > B3W_MAX_SAMPLES) return fail(B3W_ERR_INVALID, "%s: %u samples (at most %u)", who, ex.n_samples, B3W_MAX_SAMPLES);
+  if (ex.n_samples && (!ex.sample_idx || !ex.sample_out)) return fail(B3W_ERR_INVALID, "%s: samples without sample_idx / sample_out", who);
+  for (uint32_t j = 0; j < ex.n_samples; j++)
+    if (ex.sample_idx[j] >= J.n) return fail(B3W_ERR_INVALID, "%s: sample %u = instance %llu of %llu", who, j, (unsigned long long)ex.sample_idx[j], (unsigned long long)J.n);
+  ON_DEVICE(c);
+  LOCKED(c);
+  nvtx_range r(who);
+  timing_begin(c);
+  c->timing.instances = J.n;
   int rc = ensure_ring(c);
+  if (rc == B3W_OK && J.in_fr) rc = ensure_fr_staging(c);
+  if (rc == B3W_OK && J.in_fr && c->def->nova) rc = ensure_nova_wide(c);
   if (rc) return rc;
-  rc = batch_chunks(c, in, m_ext, n, out, status, pub);
+  if (ex.first_bad && !(c->flags & B3W_FLAG_FUSED_CHECK))
+    for (uint64_t i = 0; i < J.n; i++) ex.first_bad[i] = B3W_NO_ROW;          // no check ran
+  rc = guarded(who, [&]() { return batch_chunks(c, J); });
   // drain both slots on every path: after an error no copy into the caller's buffers may still be in flight
   const cudaError_t e0 = cudaStreamSynchronize(c->st[0]), e1 = cudaStreamSynchronize(c->st[1]);
+  timing_end(c);
   if (rc) return rc;
   if (e0 != cudaSuccess || e1 != cudaSuccess)
-    return fail(B3W_ERR_CUDA, "b3w_witness_batch: %s", cudaGetErrorString(e0 != cudaSuccess ? e0 : e1));
+    return fail(B3W_ERR_CUDA, "%s: %s", who, cudaGetErrorString(e0 != cudaSuccess ? e0 : e1));
   return B3W_OK;
 }
 
 extern "C" int b3w_witness_batch(b3w_ctx *c, const uint32_t *in, uint64_t n, uint8_t *out, uint8_t *status,
                                  uint32_t *pub) {
   if (!c || (!in && n)) return fail(B3W_ERR_INVALID, "b3w_witness_batch: null argument");
-  return batch_host(c, in, nullptr, n, out, status, pub);
+  batch_job J;
+  J.in = in; J.n = n; J.out = out; J.status = status; J.pub = pub;
+  return batch_host(c, J, "b3w_witness_batch");
+}
+
+extern "C" int b3w_witness_batch_ex(b3w_ctx *c, const uint32_t *in, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub,
+                                    const b3w_batch_extras *extras) {
+  if (!c || (!in && n)) return fail(B3W_ERR_INVALID, "b3w_witness_batch_ex: null argument");
+  batch_job J;
+  J.in = in; J.n = n; J.out = out; J.status = status; J.pub = pub;
+  if (extras) J.ex = *extras;
+  return batch_host(c, J, "b3w_witness_batch_ex");
 }
 
 // Inputs as field elements (canonical or not): what `normalize` (witness_calculator.js:319-323) leaves is value mod p;
-// the kernels cover the circuits' honest domain [0, 2^32), anything else is refused with B3W_ERR_DOMAIN.
+// the u32 row entry points cover the circuits' honest domain [0, 2^32), anything else is refused with B3W_ERR_DOMAIN.
 static bool ge256(const uint32_t a[8], const uint32_t b[8]) {
   for (int i = 7; i >= 0; i--)
     if (a[i] != b[i]) return a[i] > b[i];
@@ -841,78 +1251,6 @@ extern "C" int b3w_inputs_from_fr(uint32_t circuit, const uint8_t *in_fr, uint64
   return B3W_OK;
 }
 
-// ---- nova step circuits on field-element inputs (kernels_nova_wide.cuh) ---------------------------------------------
-// trace words whose value is a function of a possibly field-valued input: the slots that read them through a W32 / W64 /
-// S64 / INV descriptor are rewritten by the wide kernel's override pass
-static bool nova_field_word(uint32_t t) {
-  return (t >= NV_IN && t < NV_IN + 32) || t == NV_LDM1 || t == NV_DP1 || t == NV_DEPTH_OUT || (t >= NV_NEG_DEPTH && t < NV_BC_OUT + 2) ||
-         (t >= NV_TMP_DOWN && t < NV_EQ_D + 128) || (t >= TR_IN + 8 && t < TR_IN + 24);
-}
-static int ensure_nova_wide(b3w_ctx *c) {
-  if (c->nw_ready) return B3W_OK;
-  const circuit_def *d = c->def;
-  std::vector<uint2> lanes[32];
-  for (uint32_t sl = 0; sl < d->ws; sl++) {
-    const uint32_t dsc = c->h_desc[sl], kind = dsc >> 24, t = dsc & 0xFFFFu;
-    if (kind >= DK_W32 && nova_field_word(t)) lanes[sl & 31].push_back(make_uint2(sl, dsc));
-    else if (kind >= DK_S64) return fail(B3W_ERR_INVALID, "slot table of %s: field slot %u is not covered by the wide kernel", d->name, sl);
-    // Num2Bits(65).out[64]: constant 0 for u32 inputs; present in the O1 build only, right after out[63]
-    if (dsc == ((DK_BIT << 24) | (31u << 16) | (NV_IN + 11)) && sl + 1 < d->ws && c->h_desc[sl + 1] == ((DK_W32 << 24) | TR_ZERO))
-      lanes[(sl + 1) & 31].push_back(make_uint2(sl + 1, DK_WIDE_BIT64 << 24));
-  }
-  std::vector<uint2> all;
-  uint32_t off[33];
-  for (int l = 0; l < 32; l++) {
-    off[l] = (uint32_t)all.size();
-    all.insert(all.end(), lanes[l].begin(), lanes[l].end());
-  }
-  off[32] = (uint32_t)all.size();
-  for (void **q : {(void **)&c->d_wslots, (void **)&c->d_lane_off, (void **)&c->d_fr})       // a failed earlier attempt
-    if (*q) { cudaFree(*q); *q = nullptr; }
-  CK(cudaMalloc(&c->d_wslots, all.size() * sizeof(uint2) + 16));
-  CK(cudaMemcpy(c->d_wslots, all.data(), all.size() * sizeof(uint2), cudaMemcpyHostToDevice));
-  CK(cudaMalloc(&c->d_lane_off, sizeof off));
-  CK(cudaMemcpy(c->d_lane_off, off, sizeof off, cudaMemcpyHostToDevice));
-  CK(cudaMalloc(&c->d_fr, (size_t)c->chunk * 1024));
-  c->nw_ready = true;
-  return B3W_OK;
-}
-
-// fr: n x 32 canonical field elements (host).  One ring slot, chunk after chunk (this path is about coverage, not speed).
-static int nova_wide_chunks(b3w_ctx *c, const uint8_t *fr, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub) {
-  const circuit_def *d = c->def;
-  const size_t wbytes = (size_t)d->ws * 32;
-  cudaStream_t s = c->st[0];
-  const nova_wide_args wa{c->d_fr, c->d_wslots, c->d_lane_off, c->d_field};
-  for (uint64_t done = 0; done < n;) {
-    const uint64_t m = n - done < c->chunk ? n - done : c->chunk;
-    CK(cudaMemcpyAsync(c->d_fr, fr + done * 1024, (size_t)m * 1024, cudaMemcpyHostToDevice, s));
-    const uint64_t ctas = (m + NW_WARPS - 1) / NW_WARPS, cap = (uint64_t)c->sm_count * 8;
-    k_blake3_nova_witness_wide<<<(unsigned)(ctas < cap ? ctas : cap), NW_WARPS * 32, NW_WARPS * NW_STRIDE * 4, s>>>(
-        wa, m, c->d_desc, d->ws, c->d_ring[0], c->d_status[0], c->d_pub[0]);
-    CK(cudaGetLastError());
-    if (out) CK(cudaMemcpyAsync(out + done * wbytes, c->d_ring[0], (size_t)m * wbytes, cudaMemcpyDeviceToHost, s));
-    if (status) CK(cudaMemcpyAsync(status + done, c->d_status[0], (size_t)m, cudaMemcpyDeviceToHost, s));
-    if (pub) CK(cudaMemcpyAsync(pub + done * 15, c->d_pub[0], (size_t)m * 60, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    done += m;
-  }
-  return B3W_OK;
-}
-static int nova_wide_batch(b3w_ctx *c, const uint8_t *fr, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub) {
-  if (c->flags & B3W_FLAG_FUSED_CHECK)
-    return fail(B3W_ERR_UNSUPPORTED, "%s: the fused R1CS check covers u32 inputs; this batch holds field-valued ones", c->def->name);
-  CK(cudaSetDevice(c->device));
-  int rc = ensure_ring(c);
-  if (rc == B3W_OK) rc = ensure_nova_wide(c);
-  if (rc) return rc;
-  rc = nova_wide_chunks(c, fr, n, out, status, pub);
-  const cudaError_t e = cudaStreamSynchronize(c->st[0]);          // no copy into the caller's buffers outlives the call
-  if (rc) return rc;
-  if (e != cudaSuccess) return fail(B3W_ERR_CUDA, "b3w_witness_batch_fr: %s", cudaGetErrorString(e));
-  return B3W_OK;
-}
-
 static fr_t prime_of(const circuit_def *d) {
   fr_t p;
   memcpy(p.l, d->prime, 32);
@@ -921,12 +1259,13 @@ static fr_t prime_of(const circuit_def *d) {
 
 // The full input domain of blake3_compression (wide_domain.h): Fr256 inputs -> u32 rows + the signed high parts of the
 // message words.  Nothing is refused: an instance that cannot satisfy the circuit is marked (m_ext[i][0] = 127) and comes
-// back from the kernels with status 4, like the reference's "Assert Failed.".
+// back from the kernels with status 4, like the reference's "Assert Failed.".  (Host form of k_fr_to_rows_compression, for
+// callers that keep u32 rows; b3w_witness_batch_fr converts on the device.)
 extern "C" int b3w_inputs_from_fr_wide(uint32_t circuit, const uint8_t *in_fr, uint64_t n, uint32_t *rows, int8_t *m_ext,
                                        uint64_t *n_wide) {
   const circuit_def *d = find_def(circuit);
   if (!d) return B3W_ERR_UNSUPPORTED;
-  if (d->nova) return fail(B3W_ERR_UNSUPPORTED, "%s: only blake3_compression has the full-domain path (nova inputs must be u32)", d->name);
+  if (d->nova) return fail(B3W_ERR_UNSUPPORTED, "%s: only blake3_compression has the u32 + m_ext row form (use b3w_witness_batch_fr)", d->name);
   if ((!in_fr || !rows || !m_ext) && n) return fail(B3W_ERR_INVALID, "b3w_inputs_from_fr_wide: null argument");
   const fr_t p = prime_of(d);
   uint64_t wide = 0;
@@ -943,52 +1282,29 @@ extern "C" int b3w_witness_batch_wide(b3w_ctx *c, const uint32_t *in, const int8
                                       uint32_t *pub) {
   if (!c || ((!in || !m_ext) && n)) return fail(B3W_ERR_INVALID, "b3w_witness_batch_wide: null argument");
   if (c->def->nova) return fail(B3W_ERR_UNSUPPORTED, "%s: only blake3_compression has a wide-domain kernel", c->def->name);
-  return batch_host(c, in, m_ext, n, out, status, pub);
+  batch_job J;
+  J.in = in; J.m_ext = m_ext; J.n = n; J.out = out; J.status = status; J.pub = pub;
+  return batch_host(c, J, "b3w_witness_batch_wide");
 }
 
 extern "C" int b3w_witness_batch_device_wide(b3w_ctx *c, const uint32_t *d_in, const int8_t *d_m_ext, uint64_t n, uint8_t *d_out,
                                              uint8_t *d_status, uint32_t *d_pub, uint32_t *d_first_bad, void *stream) {
-  if (!c || !d_in || !d_m_ext || !d_out) return fail(B3W_ERR_INVALID, "b3w_witness_batch_device_wide: null argument");
-  if (((uintptr_t)d_out & 31) != 0) return fail(B3W_ERR_INVALID, "d_out must be 32-byte aligned");
-  CK(cudaSetDevice(c->device));
-  return launch_witness(c, d_in, n, d_out, d_status, d_pub, (cudaStream_t)stream, (c->flags & B3W_FLAG_FUSED_CHECK) != 0 || d_first_bad != nullptr,
-                        d_first_bad, d_m_ext);
+  if (!d_m_ext) return fail(B3W_ERR_INVALID, "b3w_witness_batch_device_wide: null argument");
+  return b3w_witness_batch_device_ex(c, d_in, d_m_ext, n, d_out, d_status, d_pub, d_first_bad, nullptr, 0, stream);
 }
 
-static int b3w_witness_batch_fr_impl(b3w_ctx *c, const uint8_t *in_fr, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub) {
+// Fr256 rows, any field elements, HOST buffers: the rows are copied to the device as they are and converted there
+// (kernels_fr_input.cuh); u32 instances run on the hot kernels, the others on the wide paths, into the same outputs.
+extern "C" int b3w_witness_batch_fr_ex(b3w_ctx *c, const uint8_t *in_fr, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub,
+                                       const b3w_batch_extras *extras) {
   if (!c || (!in_fr && n)) return fail(B3W_ERR_INVALID, "b3w_witness_batch_fr: null argument");
-  const uint32_t circuit = (uint32_t)(c->def - CIRCUITS);
-  std::vector<uint32_t> rows;
-  std::vector<int8_t> ext;
-  try {
-    rows.resize((size_t)n * c->def->n_inputs);
-    if (!c->def->nova) ext.resize((size_t)n * 16);
-  } catch (...) { return fail(B3W_ERR_NOMEM, "out of host memory"); }
-  if (c->def->nova) {
-    // u32 inputs (what every driver of the reference produces) take the hot kernels; a batch that holds anything else
-    // runs on the general kernel, which evaluates the nova-level logic on field elements
-    const fr_t p = prime_of(c->def);
-    bool all_u32 = true;
-    for (uint64_t i = 0; i < n * 32 && all_u32; i++) {
-      const fr_t v = wd_load_reduced(in_fr + i * 32, p);
-      rows[i] = v.l[0];
-      all_u32 = wd_fits(v, 32);
-    }
-    if (all_u32) return b3w_witness_batch(c, rows.data(), n, out, status, pub);
-    std::vector<uint8_t> canon((size_t)n * 1024);           // only now: the general kernel takes canonical field elements
-    for (uint64_t i = 0; i < n * 32; i++) {
-      const fr_t v = wd_load_reduced(in_fr + i * 32, p);
-      memcpy(canon.data() + i * 32, v.l, 32);
-    }
-    return nova_wide_batch(c, canon.data(), n, out, status, pub);
-  }
-  uint64_t n_wide = 0;
-  int rc = b3w_inputs_from_fr_wide(circuit, in_fr, n, rows.data(), ext.data(), &n_wide);
-  if (rc) return rc;
-  return batch_host(c, rows.data(), n_wide ? ext.data() : nullptr, n, out, status, pub);
+  batch_job J;
+  J.in_fr = in_fr; J.n = n; J.out = out; J.status = status; J.pub = pub;
+  if (extras) J.ex = *extras;
+  return batch_host(c, J, "b3w_witness_batch_fr");
 }
 extern "C" int b3w_witness_batch_fr(b3w_ctx *c, const uint8_t *in_fr, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub) {
-  return guarded("b3w_witness_batch_fr", [&]() { return b3w_witness_batch_fr_impl(c, in_fr, n, out, status, pub); });
+  return b3w_witness_batch_fr_ex(c, in_fr, n, out, status, pub, nullptr);
 }
 
 // b3w_assert_trace for field-element inputs, any values: the circuits' range constraints are replayed in the wasm's
@@ -1023,7 +1339,8 @@ extern "C" int b3w_witness_one(b3w_ctx *c, const uint32_t *in, uint8_t *out) {
 
 extern "C" int b3w_checksum_device(b3w_ctx *c, const uint8_t *d_wit, uint64_t n, uint64_t *d_sums, void *stream) {
   if (!c || !d_wit || !d_sums) return fail(B3W_ERR_INVALID, "b3w_checksum_device: null argument");
-  CK(cudaSetDevice(c->device));
+  ON_DEVICE(c);
+  LOCKED(c);
   if (n == 0) return B3W_OK;
   uint64_t ctas = (n + 7) / 8, cap = (uint64_t)c->sm_count * 8;
   k_checksum<<<(unsigned)(ctas < cap ? ctas : cap), 256, 0, (cudaStream_t)stream>>>((const uint64_t *)d_wit, n, c->def->ws, d_sums);
@@ -1034,49 +1351,50 @@ extern "C" int b3w_checksum_device(b3w_ctx *c, const uint8_t *d_wit, uint64_t n,
 extern "C" int b3w_calib_fill_items(b3w_ctx *c, uint8_t *d_buf, uint64_t bytes, void *stream) {
   if (!c || !d_buf) return fail(B3W_ERR_INVALID, "b3w_calib_fill_items: null argument");
   if (((uintptr_t)d_buf & 31) != 0) return fail(B3W_ERR_INVALID, "d_buf must be 32-byte aligned");
-  CK(cudaSetDevice(c->device));
+  ON_DEVICE(c);
+  LOCKED(c);
   const uint32_t item_slots = c->sched_parts >= 32 ? c->sched_parts / 32 * 32 : 1024;   // default 32 KiB = the witness kernels' work item (tuning hook: set_launch parts >= 32 = slots per item)
   const uint64_t n_items = bytes / (item_slots * 32ull);
   if (n_items == 0) return B3W_OK;
   sched_args sc;
-  if (!c->d_counters) CK(cudaMalloc(&c->d_counters, (size_t)N_SCHED_COUNTERS * SCHED_SET_U64 * sizeof(unsigned long long)));
-  const uint32_t set0 = c->next_counter % N_SCHED_COUNTERS;
-  c->next_counter += 2;
-  sc.counter = c->d_counters + (size_t)set0 * SCHED_SET_U64;
+  uint32_t pair;
+  int rc = take_counters(c, (cudaStream_t)stream, &sc.counter, &pair);
+  if (rc) return rc;
   sc.parts = 1;
   sc.part_len = item_slots;
-  CK(cudaMemsetAsync(sc.counter, 0, SCHED_SET_U64 * sizeof(unsigned long long), (cudaStream_t)stream));
   const int per_sm = c->ctas_limit > 0 ? c->ctas_limit : 2;
   k_fill_items<<<c->sm_count * per_sm, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(d_buf, n_items, item_slots, sc);
   CK(cudaGetLastError());
+  CK(cudaEventRecord(c->ctr_ev[pair], (cudaStream_t)stream));
   return B3W_OK;
 }
 
 extern "C" int b3w_calib_fill_bulk(b3w_ctx *c, uint8_t *d_buf, uint64_t bytes, void *stream) {
   if (!c || !d_buf) return fail(B3W_ERR_INVALID, "b3w_calib_fill_bulk: null argument");
   if (((uintptr_t)d_buf & 127) != 0) return fail(B3W_ERR_INVALID, "d_buf must be 128-byte aligned");
-  CK(cudaSetDevice(c->device));
+  ON_DEVICE(c);
+  LOCKED(c);
   const uint32_t item_bytes = (c->sched_parts >= 32 ? c->sched_parts / 32 * 32 : 1024) * 32;     // tuning hook as in b3w_calib_fill_items
   const uint64_t n_items = bytes / item_bytes;
   if (n_items == 0) return B3W_OK;
   sched_args sc;
-  if (!c->d_counters) CK(cudaMalloc(&c->d_counters, (size_t)N_SCHED_COUNTERS * SCHED_SET_U64 * sizeof(unsigned long long)));
-  const uint32_t set0 = c->next_counter % N_SCHED_COUNTERS;
-  c->next_counter += 2;
-  sc.counter = c->d_counters + (size_t)set0 * SCHED_SET_U64;
+  uint32_t pair;
+  int rc = take_counters(c, (cudaStream_t)stream, &sc.counter, &pair);
+  if (rc) return rc;
   sc.parts = 1;
   sc.part_len = item_bytes / 32;
-  CK(cudaMemsetAsync(sc.counter, 0, SCHED_SET_U64 * sizeof(unsigned long long), (cudaStream_t)stream));
   CK(cudaFuncSetAttribute(k_fill_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)item_bytes));
   const int per_sm = c->ctas_limit > 0 ? c->ctas_limit : 2;
   k_fill_bulk<<<c->sm_count * per_sm, 128, item_bytes, (cudaStream_t)stream>>>(d_buf, n_items, item_bytes, sc);
   CK(cudaGetLastError());
+  CK(cudaEventRecord(c->ctr_ev[pair], (cudaStream_t)stream));
   return B3W_OK;
 }
 
 extern "C" int b3w_calib_fill(b3w_ctx *c, uint8_t *d_buf, uint64_t bytes, void *stream) {
   if (!c || !d_buf) return fail(B3W_ERR_INVALID, "b3w_calib_fill: null argument");
-  CK(cudaSetDevice(c->device));
+  ON_DEVICE(c);
+  LOCKED(c);
   k_fill<<<c->sm_count * 8, 256, 0, (cudaStream_t)stream>>>(d_buf, bytes / 32);
   CK(cudaGetLastError());
   return B3W_OK;
@@ -1114,15 +1432,29 @@ static uint32_t build_tree(tree_plan &t, uint64_t first, uint64_t n, uint64_t n_
   t.height.push_back(h_out);
   return (uint32_t)(n_chunks + t.height.size() - 1);
 }
-static void fill_paths(tree_plan &t, uint32_t ref, uint64_t n_chunks, std::vector<uint32_t> &stack) {
+// Sibling of every parent on the way down to each chunk.  stack = the {left, right} children of those parents, root first.
+//   true siblings (default): the child the path does NOT descend into -- what a bao slice proves against the BLAKE3 root;
+//   reference_siblings: the reference's rule (rust_fold/src/blake3_hash.rs:60-78): for parent i of par_len the direction is
+//     read off the chunk index, `leaf & (1 << (par_len - i - 1)) == 0` = Left, and the sibling is the parent's OTHER half by
+//     that direction.  The two agree on every perfect (2^k-chunk) tree and wherever the bits of the chunk index spell the real
+//     path; for e.g. chunk 4 of 5 the reference picks the chunk's own subtree as its "sibling".
+static void fill_paths(tree_plan &t, uint32_t ref, uint64_t n_chunks, std::vector<std::pair<uint32_t, uint32_t>> &stack, std::vector<uint8_t> &went_left,
+                       bool reference_siblings) {
   if (ref < n_chunks) {
-    t.depth_of[ref] = (uint32_t)stack.size();
-    for (size_t i = 0; i < stack.size(); i++) t.path[(size_t)ref * t.max_depth + i] = stack[i];
+    const size_t par_len = stack.size();
+    t.depth_of[ref] = (uint32_t)par_len;
+    for (size_t i = 0; i < par_len; i++) {
+      bool left = went_left[i] != 0;
+      if (reference_siblings) left = par_len - i - 1 >= 64 ? true : (((uint64_t)ref >> (par_len - i - 1)) & 1) == 0;
+      t.path[(size_t)ref * t.max_depth + i] = left ? stack[i].second : stack[i].first;
+    }
     return;
   }
   uint32_t j = ref - (uint32_t)n_chunks, l = t.nodes[2 * j], r = t.nodes[2 * j + 1];
-  stack.push_back(r); fill_paths(t, l, n_chunks, stack); stack.pop_back();
-  stack.push_back(l); fill_paths(t, r, n_chunks, stack); stack.pop_back();
+  stack.push_back({l, r});
+  went_left.push_back(1); fill_paths(t, l, n_chunks, stack, went_left, reference_siblings); went_left.pop_back();
+  went_left.push_back(0); fill_paths(t, r, n_chunks, stack, went_left, reference_siblings); went_left.pop_back();
+  stack.pop_back();
 }
 
 // Everything the host decides about a file before the device starts: the BLAKE3 tree (parents ordered by height so that
@@ -1136,7 +1468,7 @@ struct chain_plan {
   std::vector<uint32_t> path, depth_of;
   std::vector<uint64_t> step_off;              // nc + 1
 };
-static int make_chain_plan(uint64_t len, chain_plan &p) {
+static int make_chain_plan(uint64_t len, chain_plan &p, bool reference_siblings = false) {
   const uint64_t nc = chunk_count_of(len);
   if (nc > 0x7FFFFFFFull) return fail(B3W_ERR_INVALID, "input too large for the chain driver (%llu chunks)", (unsigned long long)nc);
   tree_plan t;
@@ -1145,7 +1477,11 @@ static int make_chain_plan(uint64_t len, chain_plan &p) {
   t.max_depth = hgt ? hgt : 1;
   t.depth_of.assign(nc, 0);
   t.path.assign((size_t)nc * t.max_depth, 0);
-  { std::vector<uint32_t> st; fill_paths(t, t.root, nc, st); }
+  {
+    std::vector<std::pair<uint32_t, uint32_t>> st;
+    std::vector<uint8_t> wl;
+    fill_paths(t, t.root, nc, st, wl, reference_siblings);
+  }
   p.nc = nc;
   p.max_depth = t.max_depth;
   p.n_par = t.height.size();
@@ -1199,11 +1535,20 @@ static int chain_scratch(b3w_ctx *c, int slot, size_t need, void **out) {
   return B3W_OK;
 }
 
+// Where the step witnesses of a chain go.  Host form: through the ring into the caller's host arrays (any may be NULL).
+// Device form: straight into caller-supplied DEVICE buffers (d_out etc.), nothing crosses PCIe but the file itself.
+struct chain_sink {
+  bool device = false;
+  uint8_t *out = nullptr;
+  uint8_t *status = nullptr;
+  uint32_t *pub = nullptr;
+  uint32_t *rows = nullptr;
+  uint8_t *root = nullptr;          // host, 32 bytes, in both forms
+};
+
 // Steps of chunks [lo, hi) of the file: this device hashes the whole tree (cheap), builds the rows of its chunks and
-// generates their step witnesses; host outputs are the caller's FULL arrays, written at this range's offsets.
-static int nova_chain_range(b3w_ctx *c, const chain_plan &p, const uint8_t *data, uint64_t len, uint64_t lo, uint64_t hi, uint8_t *out,
-                            uint8_t *status, uint32_t *pub, uint32_t *rows_out, uint8_t root_out[32]) {
-  CK(cudaSetDevice(c->device));
+// generates their step witnesses; outputs are the caller's FULL arrays, written at this range's offsets.
+static int nova_chain_steps(b3w_ctx *c, const chain_plan &p, const uint8_t *data, uint64_t len, uint64_t lo, uint64_t hi, const chain_sink &K) {
   int rc = ensure_ring(c);
   if (rc) return rc;
   const uint64_t nc = p.nc, first = p.step_off[lo], total = p.step_off[hi] - first;
@@ -1215,61 +1560,121 @@ static int nova_chain_range(b3w_ctx *c, const chain_plan &p, const uint8_t *data
   if ((rc = chain_scratch(c, CS_PATH, p.path.size() * 4, (void **)&d_path))) return rc;
   if ((rc = chain_scratch(c, CS_DEPTH, nc * 4, (void **)&d_depth))) return rc;
   if ((rc = chain_scratch(c, CS_OFF, (nc + 1) * 8, (void **)&d_off))) return rc;
-  if ((rc = chain_scratch(c, CS_ROWS, (size_t)total * 128, (void **)&d_rows))) return rc;
   if ((rc = chain_scratch(c, CS_ROOT, 32, (void **)&d_root))) return rc;
+  if (K.device && K.rows) d_rows = K.rows + first * 32;                          // the caller's device array IS the row buffer
+  else if ((rc = chain_scratch(c, CS_ROWS, (size_t)total * 128, (void **)&d_rows))) return rc;
   cudaStream_t s0 = c->st[0];
-  // the tail of the last chunk is zero padding (load_block reads whole 64-byte blocks)
-  const size_t tail = len & ~(size_t)1023;
-  CK(cudaMemsetAsync(d_data + tail, 0, padded - tail, s0));
-  if (len) CK(cudaMemcpyAsync(d_data, data, len, cudaMemcpyHostToDevice, s0));
-  CK(cudaMemcpyAsync(d_nodes, p.nodes.data(), p.nodes.size() * 4, cudaMemcpyHostToDevice, s0));
-  CK(cudaMemcpyAsync(d_path, p.path.data(), p.path.size() * 4, cudaMemcpyHostToDevice, s0));
-  CK(cudaMemcpyAsync(d_depth, p.depth_of.data(), nc * 4, cudaMemcpyHostToDevice, s0));
-  CK(cudaMemcpyAsync(d_off, p.step_off.data(), (nc + 1) * 8, cudaMemcpyHostToDevice, s0));
-  k_chunk_cvs<<<(unsigned)((nc + 127) / 128), 128, 0, s0>>>(d_data, len, nc, d_cv);
-  for (const auto &lv : p.levels)                                   // one launch per tree level
-    k_parent_cvs<<<(lv.second + 127) / 128, 128, 0, s0>>>(d_nodes, lv.first, lv.second, nc, d_cv);
-  k_chain_rows<<<(unsigned)((hi - lo + 63) / 64), 64, 0, s0>>>(d_data, len, lo, hi, d_cv, d_path, d_depth, p.max_depth, d_off, d_rows, d_root);
-  CK(cudaGetLastError());
-  if (rows_out) CK(cudaMemcpyAsync(rows_out + first * 32, d_rows, (size_t)total * 128, cudaMemcpyDeviceToHost, s0));
-  if (root_out && lo == 0) CK(cudaMemcpyAsync(root_out, d_root, 32, cudaMemcpyDeviceToHost, s0));
+  {
+    nvtx_range r("b3w:h2d");
+    // the tail of the last chunk is zero padding (load_block reads whole 64-byte blocks)
+    const size_t tail = len & ~(size_t)1023;
+    CK(cudaMemsetAsync(d_data + tail, 0, padded - tail, s0));
+    if (len) CK(cudaMemcpyAsync(d_data, data, len, cudaMemcpyHostToDevice, s0));
+    CK(cudaMemcpyAsync(d_nodes, p.nodes.data(), p.nodes.size() * 4, cudaMemcpyHostToDevice, s0));
+    CK(cudaMemcpyAsync(d_path, p.path.data(), p.path.size() * 4, cudaMemcpyHostToDevice, s0));
+    CK(cudaMemcpyAsync(d_depth, p.depth_of.data(), nc * 4, cudaMemcpyHostToDevice, s0));
+    CK(cudaMemcpyAsync(d_off, p.step_off.data(), (nc + 1) * 8, cudaMemcpyHostToDevice, s0));
+    c->timing.h2d_bytes += len + p.nodes.size() * 4 + p.path.size() * 4 + nc * 4 + (nc + 1) * 8;
+  }
+  {
+    nvtx_range r("b3w:tree");
+    k_chunk_cvs<<<(unsigned)((nc + 127) / 128), 128, 0, s0>>>(d_data, len, nc, d_cv);
+    for (const auto &lv : p.levels)                                   // one launch per tree level
+      k_parent_cvs<<<(lv.second + 127) / 128, 128, 0, s0>>>(d_nodes, lv.first, lv.second, nc, d_cv);
+    k_chain_rows<<<(unsigned)((hi - lo + 63) / 64), 64, 0, s0>>>(d_data, len, lo, hi, d_cv, d_path, d_depth, p.max_depth, d_off, d_rows, d_root);
+    CK(cudaGetLastError());
+  }
+  if (K.rows && !K.device) CK(cudaMemcpyAsync(K.rows + first * 32, d_rows, (size_t)total * 128, cudaMemcpyDeviceToHost, s0));
+  if (K.root && lo == 0) CK(cudaMemcpyAsync(K.root, d_root, 32, cudaMemcpyDeviceToHost, s0));
+  const bool check = (c->flags & B3W_FLAG_FUSED_CHECK) != 0;
+  const size_t wbytes = (size_t)c->def->ws * 32;
+  if (K.device) {
+    // every step witness of the range in ONE launch, straight into the caller's device buffers
+    nvtx_range r("b3w:kernel");
+    launch_opts o;
+    o.check = check;
+    CK(cudaEventRecord(c->ev_k0[0], s0));
+    rc = launch_witness(c, d_rows, total, K.out + first * wbytes, K.status ? K.status + first : nullptr, K.pub ? K.pub + first * 15 : nullptr, s0, o);
+    if (rc) return rc;
+    CK(cudaEventRecord(c->ev_k1[0], s0));
+    c->ev_pending[0] = true;
+    c->timing.launches++;
+    return B3W_OK;
+  }
   CK(cudaEventRecord(c->ev[0], s0));
   CK(cudaStreamWaitEvent(c->st[1], c->ev[0], 0));                   // the rows exist before slot 1's first launch
-  // all step witnesses of the range, ring chunk by ring chunk (or straight to `out`)
-  const size_t wbytes = (size_t)c->def->ws * 32;
+  // all step witnesses of the range, ring chunk by ring chunk
   uint64_t done = 0;
   int k = 0;
   while (done < total) {
     const uint64_t m = total - done < c->chunk ? total - done : c->chunk;
     cudaStream_t s = c->st[k];
-    rc = launch_witness(c, d_rows + done * 32, m, c->d_ring[k], c->d_status[k], c->d_pub[k], s, (c->flags & B3W_FLAG_FUSED_CHECK) != 0);
-    if (rc) return rc;
+    launch_opts o;
+    o.check = check;
+    {
+      nvtx_range r("b3w:kernel");
+      CK(cudaEventRecord(c->ev_k0[k], s));
+      rc = launch_witness(c, d_rows + done * 32, m, c->d_ring[k], c->d_status[k], c->d_pub[k], s, o);
+      if (rc) return rc;
+      CK(cudaEventRecord(c->ev_k1[k], s));
+      c->ev_pending[k] = true;
+      c->timing.launches++;
+    }
     const uint64_t g = first + done;
-    if (out) CK(cudaMemcpyAsync(out + g * wbytes, c->d_ring[k], (size_t)m * wbytes, cudaMemcpyDeviceToHost, s));
-    if (status) CK(cudaMemcpyAsync(status + g, c->d_status[k], (size_t)m, cudaMemcpyDeviceToHost, s));
-    if (pub) CK(cudaMemcpyAsync(pub + g * 15, c->d_pub[k], (size_t)m * 60, cudaMemcpyDeviceToHost, s));
+    {
+      nvtx_range r("b3w:d2h");
+      if (K.out) { CK(cudaMemcpyAsync(K.out + g * wbytes, c->d_ring[k], (size_t)m * wbytes, cudaMemcpyDeviceToHost, s)); c->timing.d2h_bytes += (size_t)m * wbytes; }
+      if (K.status) CK(cudaMemcpyAsync(K.status + g, c->d_status[k], (size_t)m, cudaMemcpyDeviceToHost, s));
+      if (K.pub) CK(cudaMemcpyAsync(K.pub + g * 15, c->d_pub[k], (size_t)m * 60, cudaMemcpyDeviceToHost, s));
+      c->timing.d2h_bytes += (size_t)m * 61;
+    }
     done += m;
     k ^= 1;
-    if (done < total) CK(cudaStreamSynchronize(c->st[k]));          // before reusing slot k its stream must have drained
+    if (done < total) {                                              // before reusing slot k its stream must have drained
+      CK(cudaStreamSynchronize(c->st[k]));
+      timing_collect(c, k);
+    }
   }
-  CK(cudaStreamSynchronize(c->st[0]));
-  CK(cudaStreamSynchronize(c->st[1]));
+  return B3W_OK;
+}
+static int nova_chain_range(b3w_ctx *c, const chain_plan &p, const uint8_t *data, uint64_t len, uint64_t lo, uint64_t hi, const chain_sink &K) {
+  ON_DEVICE(c);
+  LOCKED(c);
+  nvtx_range r("b3w_nova_chain");
+  timing_begin(c);
+  c->timing.instances = p.step_off[hi] - p.step_off[lo];
+  const int rc = guarded("b3w_nova_chain", [&]() { return nova_chain_steps(c, p, data, len, lo, hi, K); });
+  // drain on every path: after an error no copy into the caller's buffers may still be in flight
+  cudaError_t e0 = cudaSuccess, e1 = cudaSuccess;
+  if (c->ring_ready) { e0 = cudaStreamSynchronize(c->st[0]); e1 = cudaStreamSynchronize(c->st[1]); }
+  timing_end(c);
+  if (rc) return rc;
+  if (e0 != cudaSuccess || e1 != cudaSuccess) return fail(B3W_ERR_CUDA, "b3w_nova_chain: %s", cudaGetErrorString(e0 != cudaSuccess ? e0 : e1));
   return B3W_OK;
 }
 
-static int b3w_nova_chain_impl(b3w_ctx *c, const uint8_t *data, uint64_t len, uint8_t *out, uint8_t *status, uint32_t *pub,
-                              uint32_t *rows_out, uint64_t *step_off_out, uint8_t root_out[32]) {
+static int b3w_nova_chain_impl(b3w_ctx *c, const uint8_t *data, uint64_t len, const chain_sink &K, uint64_t *step_off_out) {
   if (!c || (!data && len)) return fail(B3W_ERR_INVALID, "b3w_nova_chain: null argument");
   if (!c->def->nova) return fail(B3W_ERR_INVALID, "b3w_nova_chain needs a nova circuit context");
+  if (K.device && (!K.out || ((uintptr_t)K.out & 31) != 0)) return fail(B3W_ERR_INVALID, "b3w_nova_chain_device: d_out must be a 32-byte aligned device buffer");
   chain_plan p;
-  int rc = make_chain_plan(len, p);
+  int rc = make_chain_plan(len, p, (c->flags & B3W_FLAG_REFERENCE_SIBLINGS) != 0);
   if (rc) return rc;
   if (step_off_out) memcpy(step_off_out, p.step_off.data(), (p.nc + 1) * 8);
-  return nova_chain_range(c, p, data, len, 0, p.nc, out, status, pub, rows_out, root_out);
+  return nova_chain_range(c, p, data, len, 0, p.nc, K);
 }
 extern "C" int b3w_nova_chain(b3w_ctx *c, const uint8_t *data, uint64_t len, uint8_t *out, uint8_t *status, uint32_t *pub,
                               uint32_t *rows_out, uint64_t *step_off_out, uint8_t root_out[32]) {
-  return guarded("b3w_nova_chain", [&]() { return b3w_nova_chain_impl(c, data, len, out, status, pub, rows_out, step_off_out, root_out); });
+  chain_sink K;
+  K.out = out; K.status = status; K.pub = pub; K.rows = rows_out; K.root = root_out;
+  return guarded("b3w_nova_chain", [&]() { return b3w_nova_chain_impl(c, data, len, K, step_off_out); });
+}
+extern "C" int b3w_nova_chain_device(b3w_ctx *c, const uint8_t *data, uint64_t len, uint8_t *d_out, uint8_t *d_status, uint32_t *d_pub,
+                                     uint32_t *d_rows, uint64_t *step_off_out, uint8_t root_out[32]) {
+  chain_sink K;
+  K.device = true;
+  K.out = d_out; K.status = d_status; K.pub = d_pub; K.rows = d_rows; K.root = root_out;
+  return guarded("b3w_nova_chain_device", [&]() { return b3w_nova_chain_impl(c, data, len, K, step_off_out); });
 }
 
 // (the multi-GPU form, b3w_multi_nova_chain, is with the other b3w_multi_* entry points below: the unit of sharding is a
@@ -1289,28 +1694,30 @@ extern "C" int b3w_packed_words(uint32_t circuit, uint32_t *words) {
   return B3W_OK;
 }
 
-extern "C" int b3w_witness_batch_packed_device(b3w_ctx *c, const uint32_t *d_in, uint64_t n, uint32_t *d_packed, uint8_t *d_status,
-                                               uint32_t *d_pub, void *stream) {
-  if (!c || !d_in || !d_packed) return fail(B3W_ERR_INVALID, "b3w_witness_batch_packed_device: null argument");
-  if (((uintptr_t)d_packed & 15) != 0) return fail(B3W_ERR_INVALID, "d_packed must be 16-byte aligned");
-  CK(cudaSetDevice(c->device));
+static int packed_launch(b3w_ctx *c, const uint32_t *d_in, uint64_t n, uint32_t *d_packed, uint8_t *d_status, uint32_t *d_pub, cudaStream_t s) {
   if (n == 0) return B3W_OK;
   const uint64_t ctas = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA, cap = (uint64_t)c->sm_count * 6;
   const unsigned grid = (unsigned)(ctas < cap ? ctas : cap);
   const uint32_t sw = packed_words_of(c->def);
-  if (c->def->nova) {
-    k_witness_packed<true><<<grid, WARPS_PER_CTA * 32, trace_smem_of(c->def), (cudaStream_t)stream>>>(d_in, n, sw, d_packed, d_status, d_pub);
-  } else {
-    k_witness_packed<false><<<grid, WARPS_PER_CTA * 32, trace_smem_of(c->def), (cudaStream_t)stream>>>(d_in, n, sw, d_packed, d_status, d_pub);
-  }
+  if (c->def->nova) k_witness_packed<true><<<grid, WARPS_PER_CTA * 32, trace_smem_of(c->def), s>>>(d_in, n, sw, d_packed, d_status, d_pub);
+  else k_witness_packed<false><<<grid, WARPS_PER_CTA * 32, trace_smem_of(c->def), s>>>(d_in, n, sw, d_packed, d_status, d_pub);
   CK(cudaGetLastError());
   return B3W_OK;
+}
+extern "C" int b3w_witness_batch_packed_device(b3w_ctx *c, const uint32_t *d_in, uint64_t n, uint32_t *d_packed, uint8_t *d_status,
+                                               uint32_t *d_pub, void *stream) {
+  if (!c || !d_in || !d_packed) return fail(B3W_ERR_INVALID, "b3w_witness_batch_packed_device: null argument");
+  if (((uintptr_t)d_packed & 15) != 0) return fail(B3W_ERR_INVALID, "d_packed must be 16-byte aligned");
+  ON_DEVICE(c);
+  LOCKED(c);
+  return packed_launch(c, d_in, n, d_packed, d_status, d_pub, (cudaStream_t)stream);
 }
 
 extern "C" int b3w_unpack_device(b3w_ctx *c, const uint32_t *d_packed, uint64_t n, uint8_t *d_out, void *stream) {
   if (!c || !d_packed || !d_out) return fail(B3W_ERR_INVALID, "b3w_unpack_device: null argument");
   if (((uintptr_t)d_packed & 15) != 0 || ((uintptr_t)d_out & 31) != 0) return fail(B3W_ERR_INVALID, "d_packed must be 16-byte, d_out 32-byte aligned");
-  CK(cudaSetDevice(c->device));
+  ON_DEVICE(c);
+  LOCKED(c);
   if (n == 0) return B3W_OK;
   const uint32_t parts = 8, part_len = ((c->def->ws + parts - 1) / parts + 31) / 32 * 32;
   const uint64_t ctas = (n * parts + WARPS_PER_CTA - 1) / WARPS_PER_CTA, cap = (uint64_t)c->sm_count * 2;
@@ -1327,7 +1734,7 @@ extern "C" int b3w_unpack_device(b3w_ctx *c, const uint32_t *d_packed, uint64_t 
 
 // host buffers: chunks of PACKED_CHUNK instances through two device slots (allocated on first use, kept in the context), so
 // that the D2H of chunk j overlaps the kernel and H2D of chunk j+1
-#define PACKED_CHUNK (1u << 17)
+#define PACKED_CHUNK (1u << 15)
 static int ensure_packed_ring(b3w_ctx *c) {
   if (c->pk_ready) return B3W_OK;
   const circuit_def *d = c->def;
@@ -1348,37 +1755,149 @@ static void free_packed_ring(b3w_ctx *c) {
     if (c->pk_status[k]) cudaFree(c->pk_status[k]);
     if (c->pk_pub[k]) cudaFree(c->pk_pub[k]);
     if (c->pk_st[k]) cudaStreamDestroy(c->pk_st[k]);
-    c->pk_in[k] = nullptr; c->pk_buf[k] = nullptr; c->pk_status[k] = nullptr; c->pk_pub[k] = nullptr; c->pk_st[k] = nullptr;
+    if (c->hy_host[k]) cudaFreeHost(c->hy_host[k]);
+    c->pk_in[k] = nullptr; c->pk_buf[k] = nullptr; c->pk_status[k] = nullptr; c->pk_pub[k] = nullptr; c->pk_st[k] = nullptr; c->hy_host[k] = nullptr;
   }
   c->pk_ready = false;
+  c->hy_ready = false;
+}
+
+// ---- host-side expansion of packed witnesses -----------------------------------------------------------------------------
+// The .wtns body of an instance is a pure function of its packed record (the trace) and the static slot table, so the
+// expansion can also run on the HOST: the format conversion the reference's writer does slot by slot
+// (witness_calculator.js:263-269), here for records the GPU computed.  One thread per contiguous range of instances;
+// every slot is written with two non-temporal 16-byte stores (the witness is written once and not read back by this code).
+// This is what b3w_witness_batch_hybrid uses to keep the 770 KB-per-witness expansion off PCIe.
+static void unpack_host_range(const circuit_def *d, const uint32_t *desc, const field_consts *F, const uint32_t *packed, uint32_t sw,
+                              uint64_t first, uint64_t count, uint8_t *out) {
+  const uint32_t ws = d->ws;
+  const bool aligned = ((uintptr_t)out & 15) == 0;
+  for (uint64_t i = first; i < first + count; i++) {
+    const uint32_t *trace = packed + i * sw;
+    uint8_t *dst = out + i * (size_t)ws * 32;
+    for (uint32_t s = 0; s < ws; s++) {
+      const uint32_t dsc = desc[s], t = dsc & 0xFFFFu, k = (dsc >> 16) & 31u, kind = dsc >> 24;
+      uint32_t l[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (kind == DK_BIT) l[0] = (trace[t] >> k) & 1u;
+      else if (kind == DK_W32) l[0] = trace[t];
+      else if (kind == DK_W64) { l[0] = trace[t]; l[1] = trace[t + 1]; }
+      else {
+        const int64_t x = (int64_t)(((uint64_t)trace[t + 1] << 32) | trace[t]);
+        const fr_t v = kind == DK_S64 ? fr_from_s64(x, F->p) : fr_inv_s64(x, *F);
+        memcpy(l, v.l, 32);
+      }
+      if (aligned) {
+        _mm_stream_si128((__m128i *)(dst + (size_t)s * 32), _mm_set_epi32((int)l[3], (int)l[2], (int)l[1], (int)l[0]));
+        _mm_stream_si128((__m128i *)(dst + (size_t)s * 32 + 16), _mm_set_epi32((int)l[7], (int)l[6], (int)l[5], (int)l[4]));
+      } else {
+        memcpy(dst + (size_t)s * 32, l, 32);
+      }
+    }
+  }
+  _mm_sfence();
+}
+static void unpack_host_mt(const circuit_def *d, const uint32_t *desc, const field_consts *F, const uint32_t *packed, uint32_t sw, uint64_t n,
+                           uint8_t *out, uint32_t threads) {
+  if (threads == 0) threads = std::max(1u, std::thread::hardware_concurrency());
+  if (threads > n) threads = (uint32_t)(n ? n : 1);
+  thread_group tg;
+  for (uint32_t g = 0; g < threads; g++) {
+    const uint64_t base = n / threads, extra = n % threads;
+    const uint64_t first = g * base + (g < extra ? g : extra), count = base + (g < extra ? 1 : 0);
+    if (count == 0) continue;
+    if (threads == 1) unpack_host_range(d, desc, F, packed, sw, first, count, out);
+    else tg.th.emplace_back([=]() { unpack_host_range(d, desc, F, packed, sw, first, count, out); });
+  }
+  tg.join();
+}
+extern "C" int b3w_unpack_host(b3w_ctx *c, const uint32_t *packed, uint64_t n, uint8_t *out, uint32_t threads) {
+  if (!c || ((!packed || !out) && n)) return fail(B3W_ERR_INVALID, "b3w_unpack_host: null argument");
+  return guarded("b3w_unpack_host", [&]() {
+    unpack_host_mt(c->def, c->h_desc, c->h_field, packed, packed_words_of(c->def), n, out, threads);
+    return B3W_OK;
+  });
+}
+
+// packed batch from host rows; with `expand_out` the chunks are expanded on the host into .wtns bodies as they arrive
+// (b3w_witness_batch_hybrid), `packed` may then be NULL
+static int packed_chunks(b3w_ctx *c, const uint32_t *in, uint64_t n, uint32_t *packed, uint8_t *status, uint32_t *pub, uint8_t *expand_out,
+                         uint32_t threads) {
+  const circuit_def *d = c->def;
+  const uint32_t sw = packed_words_of(d);
+  uint64_t done = 0, pend_first[2] = {0, 0}, pend_count[2] = {0, 0};
+  int k = 0;
+  auto retire = [&](int q) -> int {            // chunk in slot q has left the device: expand it on the host
+    CK(cudaStreamSynchronize(c->pk_st[q]));
+    if (expand_out && pend_count[q]) {
+      nvtx_range r("b3w:host_unpack");
+      const double t0 = now_ms();
+      const uint32_t *src = packed ? packed + pend_first[q] * sw : c->hy_host[q];
+      unpack_host_mt(d, c->h_desc, c->h_field, src, sw, pend_count[q], expand_out + pend_first[q] * (size_t)d->ws * 32, threads);
+      c->timing.host_ms += now_ms() - t0;
+    }
+    pend_count[q] = 0;
+    return B3W_OK;
+  };
+  while (done < n) {
+    const uint64_t m = n - done < PACKED_CHUNK ? n - done : PACKED_CHUNK;
+    cudaStream_t s = c->pk_st[k];
+    int rc = retire(k);                                    // slot k's previous chunk has left the device (and is expanded)
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(c->pk_in[k], in + done * d->n_inputs, m * d->n_inputs * 4, cudaMemcpyHostToDevice, s));
+    rc = packed_launch(c, c->pk_in[k], m, c->pk_buf[k], c->pk_status[k], c->pk_pub[k], s);
+    if (rc) return rc;
+    c->timing.launches++;
+    uint32_t *dst = packed ? packed + done * sw : c->hy_host[k];
+    CK(cudaMemcpyAsync(dst, c->pk_buf[k], m * sw * 4, cudaMemcpyDeviceToHost, s));
+    if (status) CK(cudaMemcpyAsync(status + done, c->pk_status[k], m, cudaMemcpyDeviceToHost, s));
+    if (pub) CK(cudaMemcpyAsync(pub + done * d->n_public, c->pk_pub[k], m * d->n_public * 4, cudaMemcpyDeviceToHost, s));
+    c->timing.h2d_bytes += m * d->n_inputs * 4;
+    c->timing.d2h_bytes += m * (sw * 4 + 1 + d->n_public * 4);
+    pend_first[k] = done;
+    pend_count[k] = m;
+    done += m;
+    k ^= 1;
+  }
+  int rc = retire(k);
+  if (rc) return rc;
+  return retire(k ^ 1);
+}
+static int packed_host(b3w_ctx *c, const uint32_t *in, uint64_t n, uint32_t *packed, uint8_t *status, uint32_t *pub, uint8_t *expand_out,
+                       uint32_t threads, const char *who) {
+  ON_DEVICE(c);
+  LOCKED(c);
+  nvtx_range r(who);
+  timing_begin(c);
+  c->timing.instances = n;
+  if (n == 0) { timing_end(c); return B3W_OK; }
+  int rc = ensure_packed_ring(c);
+  if (rc) { free_packed_ring(c); return rc; }
+  if (expand_out && !packed && !c->hy_ready) {
+    for (int k = 0; k < 2; k++)
+      if (cudaHostAlloc((void **)&c->hy_host[k], (size_t)PACKED_CHUNK * packed_words_of(c->def) * 4, cudaHostAllocPortable) != cudaSuccess) {
+        free_packed_ring(c);
+        return fail(B3W_ERR_NOMEM, "%s: pinned staging allocation failed", who);
+      }
+    c->hy_ready = true;
+  }
+  rc = guarded(who, [&]() { return packed_chunks(c, in, n, packed, status, pub, expand_out, threads); });
+  // drain on every path: after an error no copy into the caller's buffers may still be in flight
+  const cudaError_t e0 = cudaStreamSynchronize(c->pk_st[0]), e1 = cudaStreamSynchronize(c->pk_st[1]);
+  timing_end(c);
+  if (rc) return rc;
+  if (e0 != cudaSuccess || e1 != cudaSuccess) return fail(B3W_ERR_CUDA, "%s: %s", who, cudaGetErrorString(e0 != cudaSuccess ? e0 : e1));
+  return B3W_OK;
 }
 
 extern "C" int b3w_witness_batch_packed(b3w_ctx *c, const uint32_t *in, uint64_t n, uint32_t *packed, uint8_t *status, uint32_t *pub) {
   if (!c || (!in && n) || (!packed && n)) return fail(B3W_ERR_INVALID, "b3w_witness_batch_packed: null argument");
-  CK(cudaSetDevice(c->device));
-  if (n == 0) return B3W_OK;
-  int rc = ensure_packed_ring(c);
-  if (rc) { free_packed_ring(c); return rc; }
-  const circuit_def *d = c->def;
-  const uint32_t sw = packed_words_of(d);
-  uint64_t done = 0;
-  int k = 0;
-  while (done < n) {
-    const uint64_t m = n - done < PACKED_CHUNK ? n - done : PACKED_CHUNK;
-    cudaStream_t s = c->pk_st[k];
-    CK(cudaStreamSynchronize(s));                          // slot k's previous chunk has left the device
-    CK(cudaMemcpyAsync(c->pk_in[k], in + done * d->n_inputs, m * d->n_inputs * 4, cudaMemcpyHostToDevice, s));
-    rc = b3w_witness_batch_packed_device(c, c->pk_in[k], m, c->pk_buf[k], c->pk_status[k], c->pk_pub[k], s);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(packed + done * sw, c->pk_buf[k], m * sw * 4, cudaMemcpyDeviceToHost, s));
-    if (status) CK(cudaMemcpyAsync(status + done, c->pk_status[k], m, cudaMemcpyDeviceToHost, s));
-    if (pub) CK(cudaMemcpyAsync(pub + done * d->n_public, c->pk_pub[k], m * d->n_public * 4, cudaMemcpyDeviceToHost, s));
-    done += m;
-    k ^= 1;
-  }
-  CK(cudaStreamSynchronize(c->pk_st[0]));
-  CK(cudaStreamSynchronize(c->pk_st[1]));
-  return B3W_OK;
+  return packed_host(c, in, n, packed, status, pub, nullptr, 0, "b3w_witness_batch_packed");
+}
+
+extern "C" int b3w_witness_batch_hybrid(b3w_ctx *c, const uint32_t *in, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub,
+                                        uint32_t threads) {
+  if (!c || (!in && n) || (!out && n)) return fail(B3W_ERR_INVALID, "b3w_witness_batch_hybrid: null argument");
+  return packed_host(c, in, n, nullptr, status, pub, out, threads, "b3w_witness_batch_hybrid");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1386,12 +1905,6 @@ extern "C" int b3w_witness_batch_packed(b3w_ctx *c, const uint32_t *in, uint64_t
 // ------------------------------------------------------------------------------------------------
 struct b3w_multi {
   std::vector<b3w_ctx *> ctx;
-};
-// joins on every path out of the scope: a std::thread that is destroyed while joinable terminates the process
-struct thread_group {
-  std::vector<std::thread> th;
-  void join() { for (auto &t : th) if (t.joinable()) t.join(); }
-  ~thread_group() { join(); }
 };
 
 static int b3w_multi_create_impl(const b3w_config *cfg, const int32_t *devices, uint32_t n_devices, b3w_multi **out) {
@@ -1443,10 +1956,18 @@ extern "C" int b3w_shard_range(uint64_t n, uint32_t g, uint32_t n_shards, uint64
   return B3W_OK;
 }
 
-static int b3w_multi_witness_batch_impl(b3w_multi *m, const uint32_t *in, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub) {
+// `ex` (may be NULL): sums / first_bad are sliced like status; every sample is fetched by the device that owns its instance
+static int b3w_multi_witness_batch_impl(b3w_multi *m, const uint32_t *in, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub,
+                                        const b3w_batch_extras *ex) {
   if (!m || m->ctx.empty() || (!in && n)) return fail(B3W_ERR_INVALID, "b3w_multi_witness_batch: null argument");
   const uint32_t G = (uint32_t)m->ctx.size();
   const circuit_def *d = m->ctx[0]->def;
+  if (ex && ex->n_samples > B3W_MAX_SAMPLES) return fail(B3W_ERR_INVALID, "b3w_multi_witness_batch_ex: %u samples (at most %u)", ex->n_samples, B3W_MAX_SAMPLES);
+  if (ex && ex->n_samples && (!ex->sample_idx || !ex->sample_out)) return fail(B3W_ERR_INVALID, "b3w_multi_witness_batch_ex: samples without sample_idx / sample_out");
+  if (ex)
+    for (uint32_t j = 0; j < ex->n_samples; j++)
+      if (ex->sample_idx[j] >= n) return fail(B3W_ERR_INVALID, "b3w_multi_witness_batch_ex: sample %u = instance %llu of %llu", j, (unsigned long long)ex->sample_idx[j], (unsigned long long)n);
+  const size_t wbytes = (size_t)d->ws * 32;
   std::vector<int> rc(G, B3W_OK);
   std::vector<std::string> err(G);
   thread_group tg;
@@ -1455,9 +1976,25 @@ static int b3w_multi_witness_batch_impl(b3w_multi *m, const uint32_t *in, uint64
       uint64_t first, count;
       shard_of(n, g, G, &first, &count);
       if (count == 0) return;
-      rc[g] = b3w_witness_batch(m->ctx[g], in + first * d->n_inputs, count, out ? out + first * (size_t)d->ws * 32 : nullptr,
-                                status ? status + first : nullptr, pub ? pub + first * d->n_public : nullptr);
-      if (rc[g]) err[g] = g_err;                       // g_err is thread-local: carry the text over to the caller
+      b3w_batch_extras e = {};
+      std::vector<uint64_t> idx;                       // this shard's samples, relative to its range ...
+      std::vector<uint32_t> pos;                       // ... and where each goes in the caller's sample_out
+      std::vector<uint8_t> tmp;
+      if (ex) {
+        if (ex->sums) e.sums = ex->sums + first;
+        if (ex->first_bad) e.first_bad = ex->first_bad + first;
+        for (uint32_t j = 0; j < ex->n_samples; j++)
+          if (ex->sample_idx[j] >= first && ex->sample_idx[j] < first + count) { idx.push_back(ex->sample_idx[j] - first); pos.push_back(j); }
+      }
+      // the shard's samples arrive in a contiguous scratch and are then put in the caller's order
+      if (!idx.empty()) {
+        try { tmp.resize(idx.size() * wbytes); } catch (...) { rc[g] = B3W_ERR_NOMEM; err[g] = "out of host memory"; return; }
+        e.sample_idx = idx.data(); e.n_samples = (uint32_t)idx.size(); e.sample_out = tmp.data();
+      }
+      rc[g] = b3w_witness_batch_ex(m->ctx[g], in + first * d->n_inputs, count, out ? out + first * wbytes : nullptr,
+                                   status ? status + first : nullptr, pub ? pub + first * d->n_public : nullptr, &e);
+      if (rc[g]) { err[g] = g_err; return; }            // g_err is thread-local: carry the text over to the caller
+      for (size_t k = 0; k < idx.size(); k++) memcpy(ex->sample_out + (size_t)pos[k] * wbytes, tmp.data() + k * wbytes, wbytes);
     });
   }
   tg.join();
@@ -1466,7 +2003,11 @@ static int b3w_multi_witness_batch_impl(b3w_multi *m, const uint32_t *in, uint64
   return B3W_OK;
 }
 extern "C" int b3w_multi_witness_batch(b3w_multi *m, const uint32_t *in, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub) {
-  return guarded("b3w_multi_witness_batch", [&]() { return b3w_multi_witness_batch_impl(m, in, n, out, status, pub); });
+  return guarded("b3w_multi_witness_batch", [&]() { return b3w_multi_witness_batch_impl(m, in, n, out, status, pub, nullptr); });
+}
+extern "C" int b3w_multi_witness_batch_ex(b3w_multi *m, const uint32_t *in, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub,
+                                          const b3w_batch_extras *extras) {
+  return guarded("b3w_multi_witness_batch_ex", [&]() { return b3w_multi_witness_batch_impl(m, in, n, out, status, pub, extras); });
 }
 
 static int b3w_multi_nova_chain_impl(b3w_multi *m, const uint8_t *data, uint64_t len, uint8_t *out, uint8_t *status, uint32_t *pub,
@@ -1474,7 +2015,7 @@ static int b3w_multi_nova_chain_impl(b3w_multi *m, const uint8_t *data, uint64_t
   if (!m || m->ctx.empty() || (!data && len)) return fail(B3W_ERR_INVALID, "b3w_multi_nova_chain: null argument");
   if (!m->ctx[0]->def->nova) return fail(B3W_ERR_INVALID, "b3w_multi_nova_chain needs a nova circuit context");
   chain_plan p;
-  int rc0 = make_chain_plan(len, p);
+  int rc0 = make_chain_plan(len, p, (m->ctx[0]->flags & B3W_FLAG_REFERENCE_SIBLINGS) != 0);
   if (rc0) return rc0;
   if (step_off_out) memcpy(step_off_out, p.step_off.data(), (p.nc + 1) * 8);
   const uint32_t G = (uint32_t)m->ctx.size();
@@ -1487,13 +2028,15 @@ static int b3w_multi_nova_chain_impl(b3w_multi *m, const uint8_t *data, uint64_t
     if (cut[g] > p.nc) cut[g] = p.nc;
     if (cut[g] < cut[g - 1]) cut[g] = cut[g - 1];
   }
+  chain_sink K;
+  K.out = out; K.status = status; K.pub = pub; K.rows = rows_out; K.root = root_out;
   std::vector<int> rc(G, B3W_OK);
   std::vector<std::string> err(G);
   thread_group tg;
   for (uint32_t g = 0; g < G; g++) {
     if (cut[g] == cut[g + 1]) continue;
     tg.th.emplace_back([&, g]() {
-      rc[g] = nova_chain_range(m->ctx[g], p, data, len, cut[g], cut[g + 1], out, status, pub, rows_out, root_out);
+      rc[g] = nova_chain_range(m->ctx[g], p, data, len, cut[g], cut[g + 1], K);
       if (rc[g]) err[g] = g_err;
     });
   }

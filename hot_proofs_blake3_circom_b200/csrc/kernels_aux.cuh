@@ -1,5 +1,4 @@
-// kernels_aux.cuh -- compact witnesses (pack / unpack), the stand-alone R1CS check of witnesses in HBM, checksums and
-// the pure-store calibration kernels.  Included by blake3wit.cu only, after kernels_witness.cuh.
+// kernels_aux.cuh -- compact witnesses (pack / unpack), checksums and the pure-store calibration kernels.  Included by blake3wit.cu only, after kernels_witness.cuh.
 #pragma once
 // ---- compact ("packed") witnesses: SURVEY.md 8(f) rank 3 --------------------------------------------------------
 // Every slot of a witness is a pure function of the instance's trace (<= 1 324 u32) and the static slot table, so the
@@ -58,23 +57,6 @@ k_unpack(const uint32_t *__restrict__ packed, uint64_t n, uint32_t stride_words,
     for (uint32_t q = lane; q < stride_words / 4; q += 32) dst[q] = __ldg(src + q);
     __syncwarp();
     expand_slots<HAS_FIELD>(trace, desc, a, b, out + i * (uint64_t)ws * 32, lane, F, fslots, n_fslots);
-  }
-}
-
-// k_r1cs_check_witness: stand-alone check of witnesses resident in HBM (one warp per instance).
-__global__ void __launch_bounds__(256)
-k_r1cs_check_witness(const uint8_t *__restrict__ wit, uint64_t n, uint32_t ws, const r1cs_tables_dev T,
-                     const field_consts *__restrict__ F, uint8_t *__restrict__ status, uint32_t *__restrict__ first_bad) {
-  const int lane = threadIdx.x & 31;
-  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-  for (uint64_t i = warp; i < n; i += nwarps) {
-    SlotSrc src{reinterpret_cast<const uint32_t *>(wit + i * (uint64_t)ws * 32), F};
-    const uint32_t bad = r1cs_check_instance(src, T, lane);
-    if (lane == 0) {
-      if (status) status[i] = bad == B3W_NO_ROW ? 0 : B3W_R1CS_VIOLATION;
-      if (first_bad) first_bad[i] = bad;
-    }
   }
 }
 

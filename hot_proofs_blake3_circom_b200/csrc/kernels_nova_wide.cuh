@@ -166,9 +166,13 @@ __device__ __forceinline__ uint32_t nova_wide_public_output(const nw_view &w, in
   return w.fin[8 * 12];
 }
 
+// list == NULL: instances [0, n) of in_fr.  list != NULL: the instances list[1 .. list[0]] (k_fr_to_rows_nova's wide list; n is
+// ignored) -- in_fr, out, status, pub, sums are indexed by the INSTANCE, so the listed witnesses land where the hot kernel
+// left their places empty.  sums (may be NULL): per-instance witness checksum, written (not accumulated) here.
 __global__ void __launch_bounds__(NW_WARPS * 32)
-k_blake3_nova_witness_wide(const nova_wide_args wa, uint64_t n, const uint32_t *__restrict__ desc, uint32_t ws,
-                           uint8_t *__restrict__ out, uint8_t *__restrict__ status, uint32_t *__restrict__ pub) {
+k_blake3_nova_witness_wide(const nova_wide_args wa, const uint32_t *__restrict__ list, uint64_t n, const uint32_t *__restrict__ desc, uint32_t ws,
+                           uint8_t *__restrict__ out, uint8_t *__restrict__ status, uint32_t *__restrict__ pub,
+                           unsigned long long *__restrict__ sums) {
   extern __shared__ __align__(16) uint32_t s_dyn[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   nw_view w;
@@ -180,7 +184,9 @@ k_blake3_nova_witness_wide(const nova_wide_args wa, uint64_t n, const uint32_t *
   const field_consts &F = *wa.F;
   const lane_sched ls = load_lane_sched(lane);
   const uint64_t warp = (uint64_t)blockIdx.x * NW_WARPS + wib, nwarps = (uint64_t)gridDim.x * NW_WARPS;
-  for (uint64_t i = warp; i < n; i += nwarps) {
+  const uint64_t count = list ? (uint64_t)list[0] : n;
+  for (uint64_t it = warp; it < count; it += nwarps) {
+    const uint64_t i = list ? (uint64_t)list[1 + it] : it;
     __syncwarp();
     for (uint32_t k = lane; k < NOVA_TRACE_STRIDE; k += 32) w.trace[k] = 0u;
     const uint32_t *src = reinterpret_cast<const uint32_t *>(wa.in_fr + i * 1024);
@@ -197,9 +203,12 @@ k_blake3_nova_witness_wide(const nova_wide_args wa, uint64_t n, const uint32_t *
     }
     if (status && lane == 0) status[i] = ok ? 0 : B3W_CIRCOM_ASSERT;
     if (pub && lane < 15) pub[i * 15 + lane] = ok ? nova_wide_public_output(w, lane) : 0u;
-    if (!ok) continue;                                       // the reference throws "Assert Failed.": no witness exists
+    if (!ok) {                                               // the reference throws "Assert Failed.": no witness exists
+      if (sums && lane == 0) sums[i] = 0ull;
+      continue;
+    }
     uint8_t *dst = out + i * (uint64_t)ws * 32;
-    expand_slots<true>(w.trace, desc, 0, ws, dst, lane, wa.F, nullptr, 0);     // S64 / INV slots: left to the override pass
+    uint64_t acc = expand_slots<true, true>(w.trace, desc, 0, ws, dst, lane, wa.F, nullptr, 0);     // S64 / INV slots: left to the override pass
     __syncwarp();
     // override pass: lane l rewrites the slots with slot % 32 == l -- the lane that wrote them above (expand_slots starts
     // at slot 0), so both stores to an address come from one thread, in program order
@@ -207,6 +216,16 @@ k_blake3_nova_witness_wide(const nova_wide_args wa, uint64_t n, const uint32_t *
       const uint2 e = __ldg(wa.wslots + j);
       const fr_t v = nova_wide_value(w, e.y, F);
       st_slot_fr(dst + (size_t)e.x * 32, v.l);
+      // checksum: take back what expand_slots accounted for this slot (nothing for the S64 / INV kinds it skips)
+      const uint32_t kind = e.y >> 24, t = e.y & 0xFFFFu;
+      if (kind == DK_WIDE_BIT64) acc -= sum_small_slot(e.x, 0u, 0u);
+      else if (kind < DK_S64) acc -= sum_small_slot(e.x, w.trace[t], kind == DK_W64 ? w.trace[t + 1] : 0u);
+      acc += sum_field_slot(e.x, v);
+    }
+    if (sums) {
+#pragma unroll
+      for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) sums[i] = (unsigned long long)(acc * B3W_SUM_K);
     }
   }
 }

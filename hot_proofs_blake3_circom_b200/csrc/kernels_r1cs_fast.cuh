@@ -1,0 +1,358 @@
+// kernels_r1cs_fast.cuh -- the stand-alone R1CS check of witnesses RESIDENT IN HBM (b3w_r1cs_check_device):
+//   (A.z) * (B.z) == C.z  for every row of the constraint system, exact over Fr, at the speed the witnesses can be read.
+// What the reference's consumers do on the CPU with the vector they are handed: bellpepper's enforce of every row
+// (rust_fold/src/utils.rs:78-85) and circom_tester's expectPass (test/blake3_hash.test.ts:36).
+// Included by blake3wit.cu only, after r1cs_rows.cuh.
+//
+// One CTA per instance, several CTAs per SM.  The instance's witness (771 KB) is streamed from HBM exactly once with
+// 256-bit loads into a COMPACT shared-memory copy: per slot one bit "holds 0 or 1" and one bit "its value", plus the
+// tagged 8-byte value of every other slot in a side table found by rank -- 21 KB instead of 771 KB, because 97 % of the
+// slots of these witnesses are bits.  The rows are then evaluated from that copy by a program COMPILED on the host from
+// the constraint system (fp_compile, r1cs_load.h), in which the system's regularity is spent once instead of per row:
+//   * booleanity rows  (a x)(b x - b w0) = 0  -> a mask of slots that must be bits: 32 rows = one AND with the is-bit map;
+//   * XOR rows  (a x)(b y) = k x + k y - k o, a b = 2 k  -> runs of consecutive (x, y, o) triples: up to 32 rows = three
+//     bit-field extractions from the value map and one compare;
+//   * every other row -> a short list of ITEMS per linear combination: a scalar wire, or a RUN of up to 32 consecutive
+//     bit wires whose coefficients double (sum 2^i b_i: a Num2Bits / Bits34 recomposition is one or two items instead of
+//     33-35 terms), stored item-major in tiles of 32 rows so that a warp's loads coalesce and its trip counts are uniform.
+// Arithmetic is exact: signed 128-bit integers with a bit-length bound per term and per product; a row that cannot be
+// decided that way (a genuine field element such as IsZero's inverse, a run over slots that are not all bits, a bound
+// exceeded) is re-evaluated in Fr (Montgomery) by the same lane.  Rows the compiler does not take (coefficients that are
+// arbitrary field elements) stay with the general class/block evaluator of r1cs_rows.cuh as a RESIDUAL set; the built-in
+// systems compile completely.  Any satisfied system is accepted and the smallest violated row id reported, whatever the
+// witness holds; a slot >= p is reported as B3W_NOT_CANONICAL.
+// History (profiles/): 8 bytes per slot, one CTA per SM 1.65 M witnesses/s (compression, 24 544 rows) -> compact copy +
+// row blocks 2.33 M/s (0.27 of the read roofline; row arithmetic issue-bound) -> this file.
+#pragma once
+
+#ifndef FPK_EXP
+#define FPK_EXP 0                 /* experiment builds only: 1 = stream + classify, no rows */
+#endif
+#define FPK_THREADS 256
+#define FPK_CTAS_PER_SM 4
+#define FPK_SIDE_MAX 1536u        /* non-bit slots per witness in the side table (compression 713, nova O1 ~1 250) */
+
+struct fp_item {                  // 16 bytes
+  uint32_t wire;                  // scalar: the wire; run: its first wire
+  uint32_t meta;                  // bits 0..5 run length (0 = scalar, 2..32 = run) | 8..15 shift | 16..23 bit length of |coef| + shift
+  long long coef;                 // value contributes  (coef * v) << shift;  a run's v = sum 2^j bit_j
+};
+struct fp_tile {                  // 32 rows of identical item counts; lane = row
+  uint32_t item_off;              // items at item_off + k * 32 + lane, k < nA + nB + nC
+  uint32_t row_off;               // row ids at row_ids[row_off + lane]
+  uint16_t nA, nB, nC, rows;
+};
+struct fp_xor { uint32_t x, y, o, len_id; };      // len = len_id & 63 rows (x + j, y + j, o + j); ids at xor_ids[(len_id >> 6) + j]
+struct fastprog_dev {
+  uint32_t *bool_mask;            // (ws + 31) / 32 + 1 words: slots with a booleanity row
+  uint32_t *bool_row;             // per slot: id of that row (read on failure only)
+  fp_xor *xors;
+  uint32_t *xor_ids;
+  fp_tile *tiles;
+  fp_item *items;
+  uint32_t *row_ids;
+  uint32_t n_xors, n_tiles, n_rows;      // n_rows: rows the program covers (all three kinds)
+};
+
+// 32-byte slot -> tagged 8-byte value; BIG = "genuine field element", payload = slot index
+__device__ __forceinline__ uint64_t cpt_classify(const uint32_t x[8], uint32_t slot, const fr_t &p, bool &noncanon) {
+  if ((x[2] | x[3] | x[4] | x[5] | x[6] | x[7]) == 0 && (x[1] >> 30) == 0) return ((uint64_t)x[1] << 32) | x[0];
+  fr_t v, d;
+#pragma unroll
+  for (int j = 0; j < 8; j++) v.l[j] = x[j];
+  const uint32_t borrow = fr_raw_sub(d, p, v);               // p - x: a small negative integer stored canonically?
+  noncanon = noncanon || borrow || fr_is_zero(d);            // x >= p: not a canonical field element
+  if (!borrow && (d.l[2] | d.l[3] | d.l[4] | d.l[5] | d.l[6] | d.l[7]) == 0 && (d.l[1] >> 30) == 0)
+    return STG_TAG_NEG | ((uint64_t)d.l[1] << 32) | d.l[0];
+  return STG_TAG_BIG | slot;
+}
+// one witness slot with a single 256-bit load (SASS LDG.E.256); streamed: read once, kept out of L1
+__device__ __forceinline__ void ld_slot_stream(const uint8_t *p, uint32_t x[8]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7]) : "l"(p));
+}
+__device__ __forceinline__ void ld_slot(const uint8_t *p, uint32_t x[8]) {
+  const uint4 a = __ldg(reinterpret_cast<const uint4 *>(p)), b = __ldg(reinterpret_cast<const uint4 *>(p) + 1);
+  x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+}
+
+struct CompactSrc {
+  // several CTAs per SM walk the same tables: let them live in L1
+  static __device__ __forceinline__ uint32_t ld_table(const uint32_t *p) { return __ldg(p); }
+  const uint32_t *isbit, *bitval, *rank;     // shared: one bit per slot (x2), side-table base of each 32-slot word
+  const uint64_t *side;                      // shared: tagged values of the non-bit slots
+  const uint8_t *wit;                        // this instance's witness in HBM
+  const field_consts *F;
+  bool side_ok;                              // false: more non-bit slots than the side table holds
+  __device__ __forceinline__ uint64_t get(uint32_t s) const {
+    const uint32_t w = s >> 5, b = s & 31u, m = isbit[w];
+    if ((m >> b) & 1u) return (bitval[w] >> b) & 1u;
+    if (side_ok) return side[rank[w] + __popc(~m & ((1u << b) - 1u))];
+    bool nc = false;                         // (a non-canonical slot was already reported by the streaming pass)
+    uint32_t x[8];
+    ld_slot(wit + (size_t)s * 32, x);
+    return cpt_classify(x, s, F->p, nc);
+  }
+  __device__ __forceinline__ bool small(uint32_t s, i128 &v) const {
+    const uint64_t x = get(s);
+    if (x & STG_TAG_BIG) return false;
+    v = (x & STG_TAG_NEG) ? -(i128)(x & STG_PAYLOAD) : (i128)x;
+    return true;
+  }
+  __device__ __forceinline__ fr_t field(uint32_t s) const {
+    const uint64_t x = get(s);
+    fr_t r;
+    if (x & STG_TAG_BIG) {
+      ld_slot(wit + (size_t)s * 32, r.l);
+      return r;
+    }
+    r = fr_from_u64(x & STG_PAYLOAD);
+    return (x & STG_TAG_NEG) ? fr_neg(r, F->p) : r;
+  }
+  // `len` (1..32) consecutive bits of a bitmap starting at slot s (the maps carry one padding word)
+  static __device__ __forceinline__ uint32_t field_of(const uint32_t *map, uint32_t s, uint32_t len) {
+    const uint32_t w = s >> 5, v = __funnelshift_r(map[w], map[w + 1], s & 31u);
+    return len >= 32u ? v : v & ((1u << len) - 1u);
+  }
+  __device__ __forceinline__ bool run_is_bits(uint32_t s, uint32_t len) const {
+    return field_of(isbit, s, len) == (len >= 32u ? 0xFFFFFFFFu : (1u << len) - 1u);
+  }
+  __device__ __forceinline__ uint32_t run_value(uint32_t s, uint32_t len) const { return field_of(bitval, s, len); }
+};
+
+__device__ __forceinline__ int fp_bitlen64(uint64_t x) { return 64 - __clzll((long long)x); }
+__device__ __forceinline__ int fp_bitlen128(i128 x) {
+  const unsigned __int128 m = x < 0 ? (unsigned __int128)(-x) : (unsigned __int128)x;
+  const uint64_t hi = (uint64_t)(m >> 64);
+  return hi ? 64 + fp_bitlen64(hi) : fp_bitlen64((uint64_t)m);
+}
+
+// (coef << shift) as a field element; |coef| < 2^62 and bit length + shift <= 250 (guaranteed by fp_compile)
+__device__ __forceinline__ fr_t fp_coef_fr(long long coef, uint32_t shift, const fr_t &p) {
+  const uint64_t m = coef < 0 ? (uint64_t)0 - (uint64_t)coef : (uint64_t)coef;
+  fr_t r = fr_zero();
+  const uint32_t q = shift >> 5, b = shift & 31u;
+  const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
+  const uint32_t w0 = lo << b, w1 = b ? (hi << b) | (lo >> (32 - b)) : hi, w2 = b ? hi >> (32 - b) : 0u;
+#pragma unroll
+  for (int j = 0; j < 8; j++) r.l[j] = (uint32_t)j == q ? w0 : (uint32_t)j == q + 1 ? w1 : (uint32_t)j == q + 2 ? w2 : 0u;
+  return coef < 0 ? fr_neg(r, p) : r;
+}
+
+// exact evaluation of one compiled row in Fr (slow path)
+__device__ __noinline__ bool fp_row_fr(const CompactSrc &src, const fp_item *__restrict__ items, uint32_t item_off, uint32_t lane,
+                                       uint32_t nA, uint32_t nB, uint32_t nC) {
+  const field_consts &F = *src.F;
+  const uint32_t n[3] = {nA, nB, nC};
+  fr_t L[3];
+  uint32_t k = 0;
+  for (int part = 0; part < 3; part++) {
+    fr_t acc = fr_zero();
+    for (uint32_t j = 0; j < n[part]; j++, k++) {
+      const fp_item it = items[item_off + k * 32u + lane];
+      const uint32_t len = it.meta & 63u, shift = (it.meta >> 8) & 255u;
+      if (it.coef == 0) continue;
+      const uint32_t cnt = len ? len : 1u;
+      for (uint32_t e = 0; e < cnt; e++) {                    // a run is taken wire by wire here: its slots may hold anything
+        const fr_t v = src.field(it.wire + e);
+        const fr_t co = fp_coef_fr(it.coef, shift + e, F.p);
+        acc = fr_add(acc, fr_montmul(fr_montmul(co, F.r2, F.p, F.n0), v, F.p, F.n0), F.p);
+      }
+    }
+    L[part] = acc;
+  }
+  fr_t lhs = fr_zero();
+  if (nA && nB) lhs = fr_montmul(fr_montmul(L[0], L[1], F.p, F.n0), F.r2, F.p, F.n0);
+  bool eq = true;
+#pragma unroll
+  for (int j = 0; j < 8; j++) eq = eq && (lhs.l[j] == L[2].l[j]);
+  return eq;
+}
+
+// 2 x y == x + y - o in Fr (an XOR row whose slots are not all bits)
+__device__ __noinline__ bool fp_xor_fr(const CompactSrc &src, uint32_t x, uint32_t y, uint32_t o) {
+  const field_consts &F = *src.F;
+  const fr_t vx = src.field(x), vy = src.field(y), vo = src.field(o);
+  fr_t xy = fr_montmul(fr_montmul(vx, vy, F.p, F.n0), F.r2, F.p, F.n0);
+  xy = fr_add(xy, xy, F.p);
+  const fr_t rhs = fr_add(fr_add(vx, vy, F.p), fr_neg(vo, F.p), F.p);
+  bool eq = true;
+#pragma unroll
+  for (int j = 0; j < 8; j++) eq = eq && (xy.l[j] == rhs.l[j]);
+  return eq;
+}
+
+// x (x - w0) == 0 in Fr (a booleanity row when wire 0 does not hold 1, or x is not a bit)
+__device__ __noinline__ bool fp_bool_fr(const CompactSrc &src, uint32_t x) {
+  const field_consts &F = *src.F;
+  const fr_t vx = src.field(x), w0 = src.field(0);
+  const fr_t d = fr_add(vx, fr_neg(w0, F.p), F.p);
+  return fr_is_zero(fr_montmul(vx, d, F.p, F.n0));
+}
+
+// one tile: lane = row.  Returns the lane's violated row id or B3W_NO_ROW.
+__device__ __forceinline__ uint32_t fp_eval_tile(const CompactSrc &src, const fastprog_dev &P, const fp_tile t, uint32_t lane) {
+  const bool active = lane < t.rows;
+  const fp_item *__restrict__ it0 = P.items + t.item_off + lane;
+  i128 L[3] = {0, 0, 0};
+  bool undecided = false;
+  uint32_t k = 0;
+  const uint32_t n[3] = {t.nA, t.nB, t.nC};
+#pragma unroll
+  for (int part = 0; part < 3; part++) {
+    i128 acc = 0;
+    for (uint32_t j = 0; j < n[part]; j++, k++) {
+      const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(it0 + k * 32u));
+      const uint32_t wire = raw.x, meta = raw.y, len = meta & 63u, shift = (meta >> 8) & 255u, cbits = (meta >> 16) & 255u;
+      const long long coef = (long long)(((uint64_t)raw.w << 32) | raw.z);
+      long long v;
+      int vbits;
+      if (len) {
+        undecided = undecided || !src.run_is_bits(wire, len);
+        v = (long long)src.run_value(wire, len);
+        vbits = 32;
+      } else {
+        const uint64_t x = src.get(wire);
+        undecided = undecided || (x & STG_TAG_BIG) != 0;
+        const uint64_t mag = x & STG_PAYLOAD;
+        v = (x & STG_TAG_NEG) ? -(long long)mag : (long long)mag;
+        vbits = fp_bitlen64(mag);
+      }
+      undecided = undecided || (int)cbits + vbits > 118;      // <= 255 items of < 2^118 each stay below 2^126
+      acc += ((i128)coef * (i128)v) << shift;
+    }
+    L[part] = acc;
+  }
+  if (!active) return B3W_NO_ROW;
+  bool holds;
+  if (t.nA == 0 || t.nB == 0) {
+    holds = !undecided && L[2] == 0;
+  } else {
+    undecided = undecided || fp_bitlen128(L[0]) + fp_bitlen128(L[1]) > 125;
+    holds = !undecided && L[0] * L[1] == L[2];
+  }
+  if (undecided) holds = fp_row_fr(src, P.items, t.item_off, lane, t.nA, t.nB, t.nC);
+  return holds ? B3W_NO_ROW : P.row_ids[t.row_off + lane];
+}
+
+__global__ void __launch_bounds__(FPK_THREADS, FPK_CTAS_PER_SM)
+k_r1cs_check_fast(const uint8_t *__restrict__ wit, const uint32_t *__restrict__ list /* NULL, or {count, instances...}: see below */, uint64_t n,
+                  uint32_t ws, const fastprog_dev P, const r1cs_tables_dev T /* residual rows */, const field_consts *__restrict__ F,
+                  uint8_t *__restrict__ status, uint32_t *__restrict__ first_bad) {
+  extern __shared__ __align__(16) uint8_t s_raw[];
+  const uint32_t words = (ws + 31u) >> 5, mw = words + 1u;                  // one padding word per map (field_of reads w + 1)
+  uint32_t *isbit = reinterpret_cast<uint32_t *>(s_raw), *bitval = isbit + mw, *rank = bitval + mw;
+  uint64_t *side = reinterpret_cast<uint64_t *>(s_raw + (size_t)((3 * mw + 1) & ~1u) * 4);
+  __shared__ uint32_t s_bad, s_flags, s_nside;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  constexpr uint32_t NW = FPK_THREADS / 32;
+  fr_t p;
+#pragma unroll
+  for (int j = 0; j < 8; j++) p.l[j] = F->p.l[j];
+  // list != NULL: check the instances list[1 .. list[0]] (n is ignored), except those whose status says "Assert Failed."
+  const uint64_t count = list ? (uint64_t)list[0] : n;
+  for (uint64_t it = blockIdx.x; it < count; it += gridDim.x) {
+    const uint64_t i = list ? (uint64_t)list[1 + it] : it;
+    if (list && status && status[i] == B3W_CIRCOM_ASSERT) {   // CTA-uniform: no witness exists for this instance
+      if (first_bad && tid == 0) first_bad[i] = B3W_NO_ROW;
+      continue;
+    }
+    __syncthreads();                                          // the previous instance's rows are done with the copy
+    if (tid == 0) { s_bad = B3W_NO_ROW; s_flags = 0; s_nside = 0; isbit[words] = 0xFFFFFFFFu; bitval[words] = 0u; }
+    __syncthreads();
+    const uint8_t *w = wit + i * (uint64_t)ws * 32;
+    // ---- stream the witness once: lane = slot inside a 32-slot word, two words per warp step in flight ----
+    {
+      bool noncanon = false;
+      for (uint32_t wd = warp; wd < words; wd += 2 * NW) {
+        uint32_t x[2][8];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          const uint32_t s = min((wd + u * NW) * 32u + lane, ws - 1u);
+          ld_slot_stream(w + (size_t)s * 32, x[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          const uint32_t wu = wd + u * NW;
+          if (wu >= words) break;                               // warp-uniform
+          const uint32_t s = wu * 32u + lane;
+          const bool in = s < ws;
+          const bool bit = in && (x[u][1] | x[u][2] | x[u][3] | x[u][4] | x[u][5] | x[u][6] | x[u][7]) == 0 && x[u][0] < 2u;
+          const uint32_t mb = __ballot_sync(0xffffffffu, bit || !in);      // slots past the end count as bits (value 0)
+          const uint32_t mv = __ballot_sync(0xffffffffu, bit && x[u][0] == 1u);
+          uint32_t base = 0;
+          if (~mb) {                                            // warp-uniform: the word holds non-bit slots
+            if (lane == 0) base = atomicAdd(&s_nside, (uint32_t)__popc(~mb));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (!((mb >> lane) & 1u)) {
+              const uint32_t idx = base + __popc(~mb & ((1u << lane) - 1u));
+              const uint64_t v = cpt_classify(x[u], s, p, noncanon);
+              if (idx < FPK_SIDE_MAX) side[idx] = v;
+            }
+          }
+          if (lane == 0) { isbit[wu] = mb; bitval[wu] = mv; rank[wu] = base; }
+        }
+      }
+      if (noncanon) atomicOr(&s_flags, 1u);
+    }
+    __syncthreads();
+    uint32_t bad = B3W_NO_ROW;
+    if (!(s_flags & 1u) && FPK_EXP == 0) {
+      const CompactSrc src{isbit, bitval, rank, side, w, F, s_nside <= FPK_SIDE_MAX};
+      const bool one_ok = src.get(0) == 1ull;                 // wire 0 holds the constant 1
+      // ---- booleanity rows: the slots of the mask must be bits ----
+      for (uint32_t wd = tid; wd < words; wd += FPK_THREADS) {
+        const uint32_t need = __ldg(P.bool_mask + wd);
+        uint32_t viol = need & ~isbit[wd];
+        if (!one_ok) viol = need;                               // x (x - w0) = 0 with w0 != 1: decide every row exactly
+        while (viol) {
+          const uint32_t s = wd * 32u + (uint32_t)__ffs((int)viol) - 1u;
+          viol &= viol - 1u;
+          if (one_ok || !fp_bool_fr(src, s)) bad = min(bad, __ldg(P.bool_row + s));
+        }
+      }
+      // ---- XOR rows: runs of consecutive (x, y, o) triples ----
+      for (uint32_t b = tid; b < P.n_xors; b += FPK_THREADS) {
+        const uint4 e = __ldg(reinterpret_cast<const uint4 *>(P.xors) + b);
+        const uint32_t len = e.w & 63u;
+        const bool bits = src.run_is_bits(e.x, len) && src.run_is_bits(e.y, len) && src.run_is_bits(e.z, len);
+        if (bits && (src.run_value(e.x, len) ^ src.run_value(e.y, len)) == src.run_value(e.z, len)) continue;
+        for (uint32_t j = 0; j < len; j++) {                    // some row of the run is violated or holds non-bits: row by row
+          const uint64_t vx = src.get(e.x + j), vy = src.get(e.y + j), vo = src.get(e.z + j);
+          const bool holds = (vx | vy | vo) < 2ull ? vo == (vx ^ vy) : fp_xor_fr(src, e.x + j, e.y + j, e.z + j);
+          if (!holds) bad = min(bad, __ldg(P.xor_ids + (e.w >> 6) + j));
+        }
+      }
+      // ---- every other compiled row: tiles of 32 rows, one per warp step ----
+      for (uint32_t t = warp; t < P.n_tiles; t += NW) {
+        const uint4 h = __ldg(reinterpret_cast<const uint4 *>(P.tiles) + t);
+        fp_tile tl;
+        tl.item_off = h.x; tl.row_off = h.y;
+        tl.nA = (uint16_t)(h.z & 0xFFFFu); tl.nB = (uint16_t)(h.z >> 16); tl.nC = (uint16_t)(h.w & 0xFFFFu); tl.rows = (uint16_t)(h.w >> 16);
+        bad = min(bad, fp_eval_tile(src, P, tl, lane));
+      }
+      // ---- residual rows (not compiled): the general class / block evaluator ----
+      for (uint32_t ci = 0; ci < T.n_classes; ci++) {
+        const r1cs_class_dev c = T.cls[ci];
+        const uint32_t nb = T.cls_blocks[ci], hw = 2u + 2u * (c.nA + c.nB + c.nC);
+        const bool fast = one_ok && (c.flags & R1CS_FLAG_FAST64);
+        if (c.flags & R1CS_FLAG_MATRIX) {
+          for (uint32_t r = tid; r < ((c.count + 31u) & ~31u); r += FPK_THREADS)
+            bad = min(bad, fast ? staged_matrix_row<true>(src, c, T, r) : staged_matrix_row<false>(src, c, T, r));
+        } else {
+          for (uint32_t b = warp; b < nb; b += NW) {
+            const uint32_t *hdr = T.terms + c.term_off + (size_t)b * hw;
+            bad = min(bad, fast ? staged_block<true>(src, c, T, hdr, lane) : staged_block<false>(src, c, T, hdr, lane));
+          }
+        }
+      }
+    }
+    if (bad != B3W_NO_ROW) atomicMin(&s_bad, bad);
+    __syncthreads();
+    if (tid == 0) {
+      const uint32_t verdict = (s_flags & 1u) ? B3W_NOT_CANONICAL : s_bad;
+      if (status) status[i] = verdict == B3W_NO_ROW ? 0 : B3W_R1CS_VIOLATION;
+      if (first_bad) first_bad[i] = verdict;
+    }
+  }
+}

@@ -205,13 +205,36 @@ __device__ __forceinline__ bool nova_trace(uint32_t *trace, int lane) {
 
 // Slow path of phase 2 (nova only): a slot that holds a true field element.  Kept out of line so that the hot
 // loop keeps its small register footprint.
-__device__ __forceinline__ void store_field_slot(uint8_t *p, uint32_t kind, uint32_t lo, uint32_t hi,
+__device__ __forceinline__ fr_t store_field_slot(uint8_t *p, uint32_t kind, uint32_t lo, uint32_t hi,
                                               const field_consts *__restrict__ F) {
   const int64_t x = (int64_t)(((uint64_t)hi << 32) | lo);
   fr_t v;
   if (kind == DK_S64) v = fr_from_s64(x, F->p);
   else v = fr_inv_s64(x, *F);
   st_slot_fr(p, v.l);
+  return v;
+}
+
+// ---- per-instance witness checksum, computed from the values on their way to HBM (b3w_batch_extras.sums) -----------------
+// b3w_checksum_device's definition: sum over slots s and 64-bit limbs j of (limb[s][j] + 1) * mix(4 s + j) mod 2^64 with
+// mix(x) = (x + 1) * K.  K factors out, so a lane accumulates sum (limb + 1) * (4 s + j + 1) and the warp multiplies once.
+// A hot-path slot is {v, 0, 0, 0} (v = lo | hi << 32): (v + 1)(4 s + 1) + (4 s + 2) + (4 s + 3) + (4 s + 4).
+#define B3W_SUM_K 0x9E3779B97F4A7C15ull
+__device__ __forceinline__ uint64_t sum_small_slot(uint32_t s, uint32_t lo, uint32_t hi) {
+  const uint64_t v = ((uint64_t)hi << 32) | lo;
+  return (v + 1) * (4ull * s + 1) + 12ull * s + 9;
+}
+__device__ __forceinline__ uint64_t sum_field_slot(uint32_t s, const fr_t &v) {
+  uint64_t acc = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) acc += ((((uint64_t)v.l[2 * j + 1] << 32) | v.l[2 * j]) + 1) * (4ull * s + j + 1);
+  return acc;
+}
+// adds the warp's partial sum to sums[i] (zeroed before the launch; the parts of one witness are expanded by different warps)
+__device__ __forceinline__ void sum_commit(unsigned long long *sums, uint64_t i, uint64_t acc, int lane) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) atomicAdd(sums + i, (unsigned long long)(acc * B3W_SUM_K));
 }
 
 // Phase 2: expand the trace into witness slots [s0, s1) at `dst` (32 B per slot).
@@ -219,10 +242,12 @@ __device__ __forceinline__ void store_field_slot(uint8_t *p, uint32_t kind, uint
 // (kinds S64 / INV; 67 .. 260 slots per witness) are skipped here and written by a second pass over the list of field
 // slots (`fslots`: {slot, descriptor} pairs), in which all 32 lanes do field arithmetic together instead of one lane
 // diverging inside the hot loop.
-template <bool HAS_FIELD>
-__device__ __forceinline__ void expand_slots(const uint32_t *trace, const uint32_t *__restrict__ desc, uint32_t s0, uint32_t s1,
-                                             uint8_t *dst, int lane, const field_consts *__restrict__ F,
-                                             const uint2 *__restrict__ fslots, uint32_t n_fslots) {
+// SUMS: also returns this lane's share of the checksum of what it stored (see sum_small_slot), else 0.
+template <bool HAS_FIELD, bool SUMS = false>
+__device__ __forceinline__ uint64_t expand_slots(const uint32_t *trace, const uint32_t *__restrict__ desc, uint32_t s0, uint32_t s1,
+                                                 uint8_t *dst, int lane, const field_consts *__restrict__ F,
+                                                 const uint2 *__restrict__ fslots, uint32_t n_fslots) {
+  uint64_t acc = 0;
 #pragma unroll 4
   for (uint32_t s = s0 + lane; s < s1; s += 32) {
     const uint32_t dsc = __ldg(desc + s);
@@ -230,15 +255,22 @@ __device__ __forceinline__ void expand_slots(const uint32_t *trace, const uint32
     const uint32_t w = trace[t];
     uint32_t lo = kind == DK_BIT ? ((w >> k) & 1u) : w;
     uint32_t hi = kind == DK_W64 ? trace[t + 1] : 0u;
-    if (!HAS_FIELD || kind < DK_S64) st_slot(dst + (size_t)s * 32, lo, hi, 0u, 0u, 0u, 0u, 0u, 0u);
+    if (!HAS_FIELD || kind < DK_S64) {
+      st_slot(dst + (size_t)s * 32, lo, hi, 0u, 0u, 0u, 0u, 0u, 0u);
+      if (SUMS) acc += sum_small_slot(s, lo, hi);
+    }
   }
   if (HAS_FIELD) {
     for (uint32_t j = lane; j < n_fslots; j += 32) {
       const uint2 fs = __ldg(fslots + j);
       const uint32_t t = fs.y & 0xFFFFu;
-      if (fs.x >= s0 && fs.x < s1) store_field_slot(dst + (size_t)fs.x * 32, fs.y >> 24, trace[t], trace[t + 1], F);
+      if (fs.x >= s0 && fs.x < s1) {
+        const fr_t v = store_field_slot(dst + (size_t)fs.x * 32, fs.y >> 24, trace[t], trace[t + 1], F);
+        if (SUMS) acc += sum_field_slot(fs.x, v);
+      }
     }
   }
+  return acc;
 }
 
 #define WARPS_PER_CTA 8
@@ -255,6 +287,7 @@ struct check_args {
   uint32_t *first_bad;       // per instance: smallest violated row id or B3W_NO_ROW (may be NULL)
   uint32_t fault_word;       // trace word to corrupt (B3W_NO_ROW = none) ...
   uint32_t fault_mask;       // ... by xor with this mask, after the trace phase
+  unsigned long long *sums;  // SUMS kernel variants: per-instance witness checksum, zeroed before the launch (else unused)
 };
 
 // Work distribution.  A work item is one PART of one instance: slots [part * part_len, (part + 1) * part_len) of its
@@ -381,21 +414,26 @@ __device__ __forceinline__ bool wide_carries(uint32_t *trace, int lane) { return
 
 // The m slots of a wide instance inside [a, b): m mod p.  Each is rewritten by the lane that expand_slots used for it
 // (a is a multiple of 32), so the two stores to one address are ordered by program order.
-__device__ __forceinline__ void wide_patch_m(const uint32_t *trace, const wide_args &wd, uint32_t a, uint32_t b, uint8_t *dst, int lane) {
+// Returns the change of this lane's checksum share (new slot content minus what expand_slots accounted for).
+__device__ __forceinline__ uint64_t wide_patch_m(const uint32_t *trace, const wide_args &wd, uint32_t a, uint32_t b, uint8_t *dst, int lane) {
   const uint32_t j = ((uint32_t)lane - wd.m_slot0) & 31u, s = wd.m_slot0 + j;
   if (j < 16u && s >= a && s < b) {
     const int e = (int)trace[TR_EXT + j];
     const uint32_t lo = trace[TR_IN + 8 + j];
-    if (e > 0) st_slot(dst + (size_t)s * 32, lo, (uint32_t)e, 0u, 0u, 0u, 0u, 0u, 0u);
-    else if (e < 0) {
+    if (e > 0) {
+      st_slot(dst + (size_t)s * 32, lo, (uint32_t)e, 0u, 0u, 0u, 0u, 0u, 0u);
+      return sum_small_slot(s, lo, (uint32_t)e) - sum_small_slot(s, lo, 0u);
+    } else if (e < 0) {
       const fr_t v = fr_from_s64((int64_t)(((uint64_t)(uint32_t)e << 32) | lo), wd.F->p);
       st_slot_fr(dst + (size_t)s * 32, v.l);
+      return sum_field_slot(s, v) - sum_small_slot(s, lo, 0u);
     }
   }
+  return 0;
 }
 
 // k_blake3_comp_witness: compression circuit, one warp per work item (see above).
-template <bool CHECK, bool WIDE>
+template <bool CHECK, bool WIDE, bool SUMS>
 __global__ void __launch_bounds__((WARPS_PER_CTA + (CHECK ? CHECK_WARPS : 0)) * 32, CHECK ? 2 : 4)
 k_blake3_comp_witness(const uint32_t *__restrict__ in, uint64_t n, const uint32_t *__restrict__ desc, uint32_t ws,
                       uint8_t *__restrict__ out, uint8_t *__restrict__ status, uint32_t *__restrict__ pub,
@@ -463,8 +501,9 @@ k_blake3_comp_witness(const uint32_t *__restrict__ in, uint64_t n, const uint32_
           if (lane == 0) trace[ck.fault_word] ^= ck.fault_mask;
           __syncwarp();
         }
-        expand_slots<false>(trace, desc, a, b, out + i * (uint64_t)ws * 32, lane, nullptr, nullptr, 0);
-        if (WIDE) wide_patch_m(trace, wd, a, b, out + i * (uint64_t)ws * 32, lane);
+        uint64_t acc = expand_slots<false, SUMS>(trace, desc, a, b, out + i * (uint64_t)ws * 32, lane, nullptr, nullptr, 0);
+        if (WIDE) acc += wide_patch_m(trace, wd, a, b, out + i * (uint64_t)ws * 32, lane);
+        if (SUMS) sum_commit(ck.sums, i, acc, lane);
       }
     }
   }
@@ -485,7 +524,7 @@ __device__ __forceinline__ uint32_t nova_public_output(const uint32_t *trace, in
 
 // k_blake3_nova_witness: the nova step circuit (all three committed builds share it; they differ in the
 // slot table and the prime).  pub = z_{i+1} = the 15 outputs (low 32 bits each).
-template <bool CHECK>
+template <bool CHECK, bool SUMS>
 __global__ void __launch_bounds__((WARPS_PER_CTA + (CHECK ? NOVA_CHECK_WARPS : 0)) * 32, CHECK ? 2 : 3)
 k_blake3_nova_witness(const uint32_t *__restrict__ in, uint64_t n, const uint32_t *__restrict__ desc, uint32_t ws,
                       const field_consts *__restrict__ F, const uint2 *__restrict__ fslots, uint32_t n_fslots,
@@ -550,7 +589,8 @@ k_blake3_nova_witness(const uint32_t *__restrict__ in, uint64_t n, const uint32_
           if (lane == 0) trace[ck.fault_word] ^= ck.fault_mask;
           __syncwarp();
         }
-        expand_slots<true>(trace, desc, a, b, out + i * (uint64_t)ws * 32, lane, F, fslots, n_fslots);
+        const uint64_t acc = expand_slots<true, SUMS>(trace, desc, a, b, out + i * (uint64_t)ws * 32, lane, F, fslots, n_fslots);
+        if (SUMS) sum_commit(ck.sums, i, acc, lane);
       }
     }
   }

@@ -6,8 +6,9 @@
 // by tools/gen_r1cs.py (r1cs_tables.h), grouped into shape classes: the 32 lanes of a warp evaluate 32 rows of
 // identical shape, term columns are term-major so that lane loads coalesce.
 //
-// This file holds the FUSED check (value source TraceSrc); the stand-alone check of witnesses resident in HBM shares the
-// class tables and lives in kernels_r1cs_staged.cuh (value source StagedSrc: a compact shared-memory copy of the witness).
+// This file holds the FUSED check (value source TraceSrc); the stand-alone check of witnesses resident in HBM lives in
+// kernels_r1cs_fast.cuh (a program compiled from the rows, evaluated on a compact shared-memory copy of the witness) with
+// r1cs_rows.cuh for the rows that program does not take.
 //   TraceSrc  -- the fused check: a term is a slot DESCRIPTOR and its value is taken from the shared-memory trace
 //                that the expansion is about to read (nothing is re-read from HBM).  In trace space the rows that are
 //                identities for ANY trace content (booleanity of a bit extracted by shift-and-mask; w == sum 2^i
@@ -86,35 +87,6 @@ __device__ __forceinline__ bool r1cs_xorw_row(const uint32_t *trace, const r1cs_
   const uint32_t X = trace[dx & 0xFFFFu], Y = trace[dy & 0xFFFFu], O = trace[dz & 0xFFFFu];
   return (X ^ __funnelshift_r(Y, Y, (dy >> 16) & 31u)) == __funnelshift_r(O, O, (dz >> 16) & 31u);
 }
-
-// SlotSrc -- the stand-alone check of witnesses resident in HBM against the BUILT-IN slot-space rows: a term is a
-// witness slot index and its value is the 32-byte field element found there (kernels_aux.cuh, k_r1cs_check_witness).
-struct SlotSrc {
-  const uint32_t *wit;          // this instance's witness, 8 u32 per slot
-  const field_consts *F;
-  __device__ __forceinline__ fr_t load(uint32_t s) const {
-    fr_t v;
-    const uint4 a = *reinterpret_cast<const uint4 *>(wit + 8 * (size_t)s);
-    const uint4 b = *reinterpret_cast<const uint4 *>(wit + 8 * (size_t)s + 4);
-    v.l[0] = a.x; v.l[1] = a.y; v.l[2] = a.z; v.l[3] = a.w; v.l[4] = b.x; v.l[5] = b.y; v.l[6] = b.z; v.l[7] = b.w;
-    return v;
-  }
-  __device__ __forceinline__ bool small(uint32_t s, i128 &v) const {
-    fr_t x = load(s);
-    if ((x.l[2] | x.l[3] | x.l[4] | x.l[5] | x.l[6] | x.l[7]) == 0) {
-      v = (i128)(((uint64_t)x.l[1] << 32) | x.l[0]);
-      return true;
-    }
-    fr_t n;                     // p - x: a small negative integer stored canonically?
-    if (fr_raw_sub(n, F->p, x)) return false;          // x > p: not canonical
-    if ((n.l[2] | n.l[3] | n.l[4] | n.l[5] | n.l[6] | n.l[7]) != 0 || (n.l[1] >> 31)) return false;
-    v = -(i128)(((uint64_t)n.l[1] << 32) | n.l[0]);
-    return true;
-  }
-  __device__ __forceinline__ fr_t field(uint32_t s) const { return load(s); }
-  __device__ __forceinline__ bool xorw(const r1cs_class_dev &, const r1cs_tables_dev &, uint32_t) const { return false; }
-  __device__ __forceinline__ bool zmask(const r1cs_class_dev &, const r1cs_tables_dev &, uint32_t) const { return false; }
-};
 
 __device__ __forceinline__ bool TraceSrc::xorw(const r1cs_class_dev &c, const r1cs_tables_dev &T, uint32_t r) const {
   return r1cs_xorw_row(trace, c, T, r);

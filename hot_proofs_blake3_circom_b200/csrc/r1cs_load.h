@@ -4,6 +4,8 @@
 // evaluator works on (r1cs.cuh): rows with the same (nA, nB, nC) and the same small coefficients share a coefficient
 // vector; small groups are merged into per-row-coefficient classes; rows whose coefficients do not fit 56 bits (e.g.
 // 2^-31 mod p after circom's O2 substitution) keep full field-element coefficients (BIGCOEF) and are evaluated in Fr.
+// Also here: fp_compile(), which turns a row list (from a file or from the built-in tables) into the compiled program of
+// kernels_r1cs_fast.cuh; only the rows it does not take go through the class grouping.
 // Included by blake3wit.cu only.
 #pragma once
 #include <map>
@@ -19,7 +21,7 @@ struct r1cs_host_set {
 };
 
 namespace r1cs_load_detail {
-struct term { uint32_t wire; bool small; __int128 c; fr_t f; };
+struct term { uint32_t wire; bool small; __int128 c; fr_t f; };      // small: the coefficient is the signed integer c (|c| < 2^120)
 struct row { std::vector<term> part[3]; uint32_t id; bool big; };
 
 static bool rd32(const uint8_t *p, size_t len, size_t &pos, uint32_t &v) {
@@ -36,8 +38,9 @@ static bool rd64(const uint8_t *p, size_t len, size_t &pos, uint64_t &v) {
 }
 }  // namespace r1cs_load_detail
 
-// returns 0 or a B3W_ERR_* code with the text in `err`
-static int r1cs_parse(const uint8_t *data, size_t len, const uint8_t prime[32], uint32_t ws, r1cs_host_set &out, std::string &err) {
+// returns 0 or a B3W_ERR_* code with the text in `err`.  Rows come back in file order with R.id = constraint index.
+static int r1cs_parse_rows(const uint8_t *data, size_t len, const uint8_t prime[32], uint32_t ws, std::vector<r1cs_load_detail::row> &rows,
+                           r1cs_host_set &out, std::string &err) {
   using namespace r1cs_load_detail;
   size_t pos = 0;
   uint32_t version, nsec;
@@ -71,7 +74,7 @@ static int r1cs_parse(const uint8_t *data, size_t len, const uint8_t prime[32], 
   pos = sec_off[2];
   const size_t cend = sec_off[2] + sec_len[2];
   if ((uint64_t)m * 12 > (uint64_t)(cend - pos)) { err = "the header announces more constraints than the file holds"; return B3W_ERR_INVALID; }
-  std::vector<row> rows(m);
+  rows.assign(m, row());
   for (uint32_t i = 0; i < m; i++) {
     row &R = rows[i];
     R.id = i;
@@ -88,24 +91,40 @@ static int r1cs_parse(const uint8_t *data, size_t len, const uint8_t prime[32], 
         pos += 36;
         if (T.wire >= n_wires) { err = "constraint " + std::to_string(i) + " refers to wire " + std::to_string(T.wire); return B3W_ERR_INVALID; }
         if (fr_gte(T.f, P)) { err = "constraint " + std::to_string(i) + " has a coefficient >= p"; return B3W_ERR_INVALID; }
-        // small signed form: c < 2^56 or p - c < 2^56
+        // small signed form: c < 2^120 or p - c < 2^120 (the class grouping keeps only < 2^56 as "small")
         fr_t neg;
         fr_raw_sub(neg, P, T.f);
-        auto fits = [](const fr_t &x) { return (x.l[2] | x.l[3] | x.l[4] | x.l[5] | x.l[6] | x.l[7]) == 0 && (x.l[1] >> 24) == 0; };
-        if (fits(T.f)) { T.small = true; T.c = (__int128)(((uint64_t)T.f.l[1] << 32) | T.f.l[0]); }
-        else if (fits(neg)) { T.small = true; T.c = -(__int128)(((uint64_t)neg.l[1] << 32) | neg.l[0]); }
-        else { T.small = false; T.c = 0; R.big = true; }
+        auto fits = [](const fr_t &x) { return (x.l[4] | x.l[5] | x.l[6] | x.l[7]) == 0 && (x.l[3] >> 24) == 0; };
+        auto val = [](const fr_t &x) {
+          return (__int128)(((unsigned __int128)(((uint64_t)x.l[3] << 32) | x.l[2]) << 64) | (unsigned __int128)(((uint64_t)x.l[1] << 32) | x.l[0]));
+        };
+        if (fits(T.f)) { T.small = true; T.c = val(T.f); }
+        else if (fits(neg)) { T.small = true; T.c = -val(neg); }
+        else { T.small = false; T.c = 0; }
       }
-      if (k > 64) R.big = true;                            // keeps the 128-bit accumulators of the integer path exact
     }
     if (R.part[0].empty() || R.part[1].empty()) { R.part[0].clear(); R.part[1].clear(); }      // 0 * B = C  <=>  C = 0
+  }
+  return B3W_OK;
+}
+
+// Group rows into the shape classes of the general evaluator (r1cs_rows.cuh).  `rows` is consumed (terms get sorted).
+static void r1cs_group(std::vector<r1cs_load_detail::row> &rows, r1cs_host_set &out) {
+  using namespace r1cs_load_detail;
+  const __int128 lim56 = (__int128)1 << 56;
+  for (row &R : rows) {
+    R.big = false;
+    for (int part = 0; part < 3; part++) {
+      for (const term &T : R.part[part]) R.big = R.big || !T.small || T.c >= lim56 || T.c <= -lim56;
+      if (R.part[part].size() > 64) R.big = true;          // keeps the 128-bit accumulators of the integer path exact
+    }
     for (int part = 0; part < 3; part++)
       std::sort(R.part[part].begin(), R.part[part].end(), [&](const term &a, const term &b) {
         if (!R.big && a.c != b.c) return a.c < b.c;
         return a.wire < b.wire;
       });
   }
-  // group
+  const uint32_t m = (uint32_t)rows.size();
   typedef std::vector<long long> key_t;                    // nA, nB, nC, big?, then (hi, lo) of every coefficient
   std::map<key_t, std::vector<uint32_t>> groups;
   for (uint32_t i = 0; i < m; i++) {
@@ -164,10 +183,161 @@ static int r1cs_parse(const uint8_t *data, size_t len, const uint8_t prime[32], 
   // hi/lo are indexed together; BIGCOEF classes index coef_fr instead
   if (out.lo.empty()) { out.lo.push_back(0); out.hi.push_back(0); }
   if (out.coef_fr.empty()) out.coef_fr.push_back(fr_zero());
-  return B3W_OK;
 }
 
-// Prepare a slot-space set for the staged checker (kernels_r1cs_staged.cuh).  Every class is cut into row blocks: <= 32
+// ---- fp_compile: rows -> the compiled program of kernels_r1cs_fast.cuh ---------------------------------------------------
+struct fastprog_host {
+  std::vector<uint32_t> bool_mask, bool_row, xor_ids, row_ids;
+  std::vector<fp_xor> xors;
+  std::vector<fp_tile> tiles;
+  std::vector<fp_item> items;
+  uint32_t n_rows = 0;
+};
+
+namespace r1cs_load_detail {
+static int bitlen128(__int128 x) {
+  unsigned __int128 m = x < 0 ? (unsigned __int128)(-x) : (unsigned __int128)x;
+  int n = 0;
+  while (m) { n++; m >>= 1; }
+  return n;
+}
+// booleanity  (a x)(b x - b w0) = 0, either factor order
+static bool is_bool_row(const row &R, uint32_t &x) {
+  if (!R.part[2].empty()) return false;
+  for (int sw = 0; sw < 2; sw++) {
+    const std::vector<term> &P = R.part[sw], &Q = R.part[1 - sw];
+    if (P.size() != 1 || Q.size() != 2 || !P[0].small || !Q[0].small || !Q[1].small) continue;
+    const uint32_t w = P[0].wire;
+    if (w == 0 || P[0].c == 0) continue;
+    const term &qx = Q[0].wire == w ? Q[0] : Q[1], &q1 = Q[0].wire == w ? Q[1] : Q[0];
+    if (qx.wire != w || q1.wire != 0 || qx.c == 0 || qx.c != -q1.c) continue;
+    x = w;
+    return true;
+  }
+  return false;
+}
+// XOR  (a x)(b y) = k x + k y - k o  with  a b = 2 k  (circom's 2 x y = x + y - out, any scaling or term order)
+static bool is_xor_row(const row &R, uint32_t &x, uint32_t &y, uint32_t &o) {
+  if (R.part[0].size() != 1 || R.part[1].size() != 1 || R.part[2].size() != 3) return false;
+  const term &A = R.part[0][0], &B = R.part[1][0];
+  if (!A.small || !B.small) return false;
+  x = A.wire; y = B.wire;
+  __int128 kx = 0, ky = 0, ko = 0;
+  uint32_t seen = 0;
+  for (const term &T : R.part[2]) {
+    if (!T.small) return false;
+    if (T.wire == x && !(seen & 1u)) { kx = T.c; seen |= 1u; }
+    else if (T.wire == y && !(seen & 2u)) { ky = T.c; seen |= 2u; }
+    else if (!(seen & 4u)) { ko = T.c; o = T.wire; seen |= 4u; }
+    else return false;
+  }
+  const __int128 lim = (__int128)1 << 60;
+  if (seen != 7u || x == y || o == x || o == y || x == 0 || y == 0 || o == 0) return false;
+  if (A.c <= -lim || A.c >= lim || B.c <= -lim || B.c >= lim || kx == 0 || kx != ky || ko != -kx) return false;
+  return A.c * B.c == 2 * kx;
+}
+// one linear combination -> items (scalars and runs of consecutive bit wires with doubling coefficients)
+static bool compile_lc(std::vector<term> lc, std::vector<fp_item> &out) {
+  std::sort(lc.begin(), lc.end(), [](const term &a, const term &b) { return a.wire < b.wire; });
+  for (size_t j = 0; j < lc.size();) {
+    if (!lc[j].small) return false;
+    __int128 c = lc[j].c;
+    if (c == 0) { j++; continue; }
+    size_t len = 1;
+    if (lc[j].wire != 0)
+      while (j + len < lc.size() && len < 32 && lc[j + len].small && lc[j + len].wire == lc[j].wire + len && bitlen128(c) + (int)len < 120 &&
+             lc[j + len].c == c * ((__int128)1 << len))
+        len++;
+    uint32_t shift = 0;
+    while (bitlen128(c) > 61) {
+      if (c & 1) return false;                             // does not fit  (62-bit mantissa) << shift
+      c /= 2;
+      shift++;
+    }
+    const int cbits = bitlen128(c) + (int)shift;
+    if (cbits + 32 > 250 || shift > 200) return false;
+    fp_item it;
+    it.wire = lc[j].wire;
+    it.meta = (uint32_t)(len >= 2 ? len : 0) | (shift << 8) | ((uint32_t)cbits << 16);
+    it.coef = (long long)c;
+    out.push_back(it);
+    j += len;
+  }
+  return out.size() <= 255;
+}
+}  // namespace r1cs_load_detail
+
+// Compiles what it can; taken[i] tells which rows are now covered by the program (the others go to r1cs_group).
+static void fp_compile(const std::vector<r1cs_load_detail::row> &rows, uint32_t ws, fastprog_host &fp, std::vector<char> &taken) {
+  using namespace r1cs_load_detail;
+  const uint32_t words = (ws + 31u) >> 5;
+  fp.bool_mask.assign(words + 1, 0u);
+  fp.bool_row.assign((size_t)words * 32, 0xFFFFFFFFu);
+  taken.assign(rows.size(), 0);
+  struct xr { uint32_t x, y, o, id; };
+  std::vector<xr> xs;
+  struct gen { std::vector<fp_item> it; uint32_t n[3]; uint32_t id; };
+  std::vector<gen> gens;
+  for (size_t i = 0; i < rows.size(); i++) {
+    const row &R = rows[i];
+    uint32_t x = 0, y = 0, o = 0;
+    if (is_bool_row(R, x)) {
+      fp.bool_mask[x >> 5] |= 1u << (x & 31u);
+      fp.bool_row[x] = std::min(fp.bool_row[x], R.id);
+      taken[i] = 1;
+    } else if (is_xor_row(R, x, y, o)) {
+      xs.push_back(xr{x, y, o, R.id});
+      taken[i] = 1;
+    } else {
+      gen g;
+      g.id = R.id;
+      bool ok = true;
+      for (int part = 0; part < 3 && ok; part++) {
+        std::vector<fp_item> tmp;
+        ok = compile_lc(R.part[part], tmp);
+        g.it.insert(g.it.end(), tmp.begin(), tmp.end());
+        g.n[part] = (uint32_t)tmp.size();
+      }
+      if (ok) { gens.push_back(std::move(g)); taken[i] = 1; }
+    }
+  }
+  // XOR rows -> runs
+  std::sort(xs.begin(), xs.end(), [](const xr &a, const xr &b) { return a.x != b.x ? a.x < b.x : a.id < b.id; });
+  for (size_t j = 0; j < xs.size();) {
+    size_t len = 1;
+    while (j + len < xs.size() && len < 32 && xs[j + len].x == xs[j].x + len && xs[j + len].y == xs[j].y + len && xs[j + len].o == xs[j].o + len) len++;
+    fp_xor e;
+    e.x = xs[j].x; e.y = xs[j].y; e.o = xs[j].o;
+    e.len_id = (uint32_t)len | ((uint32_t)fp.xor_ids.size() << 6);
+    for (size_t k = 0; k < len; k++) fp.xor_ids.push_back(xs[j + k].id);
+    fp.xors.push_back(e);
+    j += len;
+  }
+  // general rows -> tiles of 32 rows with identical item counts, items item-major
+  std::stable_sort(gens.begin(), gens.end(), [](const gen &a, const gen &b) {
+    if (a.n[0] != b.n[0]) return a.n[0] < b.n[0];
+    if (a.n[1] != b.n[1]) return a.n[1] < b.n[1];
+    return a.n[2] < b.n[2];
+  });
+  for (size_t j = 0; j < gens.size();) {
+    size_t cnt = 1;
+    while (j + cnt < gens.size() && cnt < 32 && gens[j + cnt].n[0] == gens[j].n[0] && gens[j + cnt].n[1] == gens[j].n[1] && gens[j + cnt].n[2] == gens[j].n[2]) cnt++;
+    fp_tile t;
+    t.item_off = (uint32_t)fp.items.size();
+    t.row_off = (uint32_t)fp.row_ids.size();
+    t.nA = (uint16_t)gens[j].n[0]; t.nB = (uint16_t)gens[j].n[1]; t.nC = (uint16_t)gens[j].n[2]; t.rows = (uint16_t)cnt;
+    const uint32_t ni = gens[j].n[0] + gens[j].n[1] + gens[j].n[2];
+    const fp_item pad = {0u, 0u, 0ll};
+    for (uint32_t k = 0; k < ni; k++)
+      for (uint32_t l = 0; l < 32; l++) fp.items.push_back(l < cnt ? gens[j + l].it[k] : pad);
+    for (uint32_t l = 0; l < 32; l++) fp.row_ids.push_back(l < cnt ? gens[j + l].id : 0xFFFFFFFFu);
+    fp.tiles.push_back(t);
+    j += cnt;
+  }
+  for (char c : taken) fp.n_rows += c ? 1u : 0u;
+}
+
+// Prepare a slot-space set for the general evaluator (r1cs_rows.cuh).  Every class is cut into row blocks: <= 32
 // consecutive rows in which each term column is an arithmetic progression; a class whose blocks would average fewer
 // than 8 rows keeps its [term][row] matrix instead (flag MATRIX).  In: cls[k].term_off = start of the class's matrix in
 // `terms`.  Out: `blocks` = the new term store (per block: first row, rows, then {first wire, wire step} per term; or
@@ -190,7 +360,7 @@ static void stg_blockify(std::vector<r1cs_class_dev> &cls, const std::vector<uin
         fits56 = fits56 && fits && l > -(1ll << 56) && l < (1ll << 56);
       }
       if (fits) c.flags |= R1CS_FLAG_COEF64;
-      // the 64-bit evaluator (kernels_r1cs_staged.cuh, STG_FAST_*): <= 64 terms of < 2^56 each stay below 2^62
+      // the 64-bit evaluator (r1cs_rows.cuh, STG_FAST_*): <= 64 terms of < 2^56 each stay below 2^62
       if (fits && fits56 && c.nA <= 64 && c.nB <= 64 && c.nC <= 64) c.flags |= R1CS_FLAG_FAST64;
       // booleanity rows  (a x) * (b x - b w0) = 0  with w0 = wire 0, the constant 1:  "x is 0 or 1"
       if (fits && c.nA == 1 && c.nB == 2 && c.nC == 0 && c.count) {

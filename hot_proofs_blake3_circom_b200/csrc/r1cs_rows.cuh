@@ -1,30 +1,12 @@
-// kernels_r1cs_staged.cuh -- the GENERAL stand-alone R1CS check:  (A.z) * (B.z) == C.z  for every row of a constraint
-// system loaded at run time from an iden3 `.r1cs` file (b3w_r1cs_load: the artefact format of the reference's build/,
-// e.g. rust_fold/src/blake3_circuit.rs:71-81 `CircomConfig::new(wasm, r1cs)`), over witnesses resident in HBM.
-// (The built-in template-derived rows, whose value kinds are known offline, keep the lighter one-warp-per-instance
-// evaluator k_r1cs_check_witness in kernels_aux.cuh / r1cs.cuh.)
-//
-// One CTA per instance.  Phase 1 streams the instance's witness (771 KB) from HBM exactly once, coalesced, and keeps
-// a compact copy in shared memory: 8 bytes per slot (62-bit magnitude + tag: small non-negative / small negative,
-// i.e. the slot holds p - k / genuine field element = index into a side table of full 256-bit values); a slot >= p
-// is reported as non-canonical.  Phase 2 evaluates the rows from shared memory: exact signed 128-bit integers whenever
-// every term is small, Montgomery arithmetic in Fr otherwise (field-valued slots, coefficients that are not small
-// integers, products that could overflow) -- so ANY satisfied row is accepted and any violated row rejected, whatever
-// the values and coefficients are.  Measured on B200 (profiles/): phase 1 alone 6.9 M witnesses/s (5.4 TB/s of reads);
-// with phase 2, 0.9 M/s with 128-bit row arithmetic throughout, 1.22 M/s (compression, 24 544 rows) since rows of small
-// coefficients run in 64-bit arithmetic and booleanity rows are a single comparison (STG_FAST_*, BOOLROW).  What is left
-// is latency: the witness copy takes 209 KB of shared memory, so one CTA per SM has to hide the L2 latency of the block
-// headers / term matrices (~1 200 warp steps per instance over 32 warps) by itself; rows that touch genuine field
-// elements (nova: ~200 slots) pay the generic Fr fallback (nova O1: 0.41 M/s).
+// r1cs_rows.cuh -- GENERAL row evaluators of the stand-alone R1CS check:  (A.z) * (B.z) == C.z  for rows whose shape the
+// compiled fast program (kernels_r1cs_fast.cuh) does not cover -- in practice rows of a loaded iden3 `.r1cs` file
+// (b3w_r1cs_load) with coefficients that are arbitrary field elements (e.g. circom's own O2 output: 2^-31 mod p).
+// Rows are grouped in shape classes (r1cs.cuh) and cut into row BLOCKS by the host (stg_blockify, r1cs_load.h); a value
+// source (CompactSrc, kernels_r1cs_fast.cuh) hands out the witness values as tagged 8-byte words.  Exact for ANY values
+// and coefficients: signed 64/128-bit integers whenever every term is small, Montgomery arithmetic in Fr otherwise.
 // Included by blake3wit.cu only, after r1cs.cuh.
 #pragma once
 
-#define STG_THREADS 1024
-#ifndef STG_EXP_SKIP_P2
-#define STG_EXP_SKIP_P2 0          /* experiment builds only */
-#endif
-#define STG_MAX_BIG 512       /* field-valued slots per witness the side table holds (nova O1: < 200) */
-#define STG_MAX_CLASSES 96    /* shape classes per set (built-in: <= 27); more -> b3w_r1cs_load refuses */
 #define STG_TAG_NEG (1ull << 62)
 #define STG_TAG_BIG (2ull << 62)
 #define STG_PAYLOAD ((1ull << 62) - 1)
@@ -50,32 +32,6 @@ __device__ __forceinline__ uint32_t stg_ld_stream(const uint32_t *p) {
   asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
-
-struct StagedSrc {
-  static __device__ __forceinline__ uint32_t ld_table(const uint32_t *p) { return stg_ld_stream(p); }     // row-block headers / term matrices
-  const uint64_t *val;       // shared: tag | payload per slot
-  const uint32_t *big;       // shared: 8 limbs per big value
-  const field_consts *F;
-  __device__ __forceinline__ uint64_t get(uint32_t s) const { return val[s]; }      // tag | payload
-  __device__ __forceinline__ bool small(uint32_t s, i128 &v) const {
-    const uint64_t x = val[s];
-    if (x & STG_TAG_BIG) return false;
-    v = (x & STG_TAG_NEG) ? -(i128)(x & STG_PAYLOAD) : (i128)x;
-    return true;
-  }
-  __device__ __forceinline__ fr_t field(uint32_t s) const {
-    const uint64_t x = val[s];
-    fr_t r;
-    if (x & STG_TAG_BIG) {
-      const uint32_t *b = big + 8 * (uint32_t)(x & 0xFFFFFFFFu);
-#pragma unroll
-      for (int j = 0; j < 8; j++) r.l[j] = b[j];
-      return r;
-    }
-    r = fr_from_u64(x & STG_PAYLOAD);
-    return (x & STG_TAG_NEG) ? fr_neg(r, F->p) : r;
-  }
-};
 
 __device__ __forceinline__ fr_t fr_from_i128(i128 x, const fr_t &p) {
   const bool neg = x < 0;
@@ -275,94 +231,4 @@ __device__ __forceinline__ uint32_t staged_matrix_row(const Src &src, const r1cs
   if (need_fr && active) holds = staged_row_fr(src, c, T, nullptr, 0, r);
   if (holds || !active) return B3W_NO_ROW;
   return T.row_ids ? T.row_ids[c.row_off + r] : c.row_off + r;
-}
-
-__global__ void __launch_bounds__(STG_THREADS, 1)
-k_r1cs_check_staged(const uint8_t *__restrict__ wit, uint64_t n, uint32_t ws, const r1cs_tables_dev T, const field_consts *__restrict__ F,
-                    uint8_t *__restrict__ status, uint32_t *__restrict__ first_bad) {
-  extern __shared__ __align__(16) uint8_t s_raw[];
-  uint64_t *val = reinterpret_cast<uint64_t *>(s_raw);
-  uint32_t *big = reinterpret_cast<uint32_t *>(s_raw + (size_t)((ws + 1) & ~1u) * 8);
-  __shared__ uint32_t s_nbig, s_bad, s_noncanon;
-  __shared__ r1cs_class_dev s_cls[STG_MAX_CLASSES];
-  __shared__ uint32_t s_nblk[STG_MAX_CLASSES];
-  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  for (uint32_t k = tid; k < T.n_classes; k += STG_THREADS) { s_cls[k] = T.cls[k]; s_nblk[k] = T.cls_blocks[k]; }
-  fr_t p;
-#pragma unroll
-  for (int j = 0; j < 8; j++) p.l[j] = F->p.l[j];
-  for (uint64_t i = blockIdx.x; i < n; i += gridDim.x) {
-    __syncthreads();                                        // the previous instance's rows are done with val / big
-    if (tid == 0) { s_nbig = 0; s_bad = B3W_NO_ROW; s_noncanon = 0; }
-    __syncthreads();
-    // ---- phase 1: stream the witness once (4 slots per thread in flight), keep 8 bytes per slot ----
-    const uint4 *w = reinterpret_cast<const uint4 *>(wit + i * (uint64_t)ws * 32);
-    for (uint32_t s0 = tid; s0 < ws; s0 += 4 * STG_THREADS) {
-      uint4 a[4], b[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const uint32_t s = min(s0 + u * STG_THREADS, ws - 1);
-        a[u] = __ldcs(w + 2 * s);
-        b[u] = __ldcs(w + 2 * s + 1);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const uint32_t s = s0 + u * STG_THREADS;
-        if (s >= ws) break;
-        uint64_t v;
-        if ((a[u].z | a[u].w | b[u].x | b[u].y | b[u].z | b[u].w) == 0 && (a[u].y >> 30) == 0) {
-          v = ((uint64_t)a[u].y << 32) | a[u].x;
-        } else {
-          fr_t x, d;
-          x.l[0] = a[u].x; x.l[1] = a[u].y; x.l[2] = a[u].z; x.l[3] = a[u].w;
-          x.l[4] = b[u].x; x.l[5] = b[u].y; x.l[6] = b[u].z; x.l[7] = b[u].w;
-          const uint32_t borrow = fr_raw_sub(d, p, x);       // p - x: a small negative integer stored canonically?
-          if (borrow || fr_is_zero(d)) atomicOr(&s_noncanon, 1u);      // x >= p: not a canonical field element
-          if (!borrow && (d.l[2] | d.l[3] | d.l[4] | d.l[5] | d.l[6] | d.l[7]) == 0 && (d.l[1] >> 30) == 0) {
-            v = STG_TAG_NEG | ((uint64_t)d.l[1] << 32) | d.l[0];
-          } else {
-            const uint32_t k = atomicAdd(&s_nbig, 1u);
-            v = STG_TAG_BIG | k;
-            if (k < STG_MAX_BIG) {
-#pragma unroll
-              for (int j = 0; j < 8; j++) big[8 * k + j] = x.l[j];
-            }
-          }
-        }
-        val[s] = v;
-      }
-    }
-    __syncthreads();
-    uint32_t bad = B3W_NO_ROW;
-    if (s_nbig > STG_MAX_BIG) {
-      bad = 0;                                               // more field-valued slots than any witness of these circuits holds
-    } else if (!s_noncanon && !STG_EXP_SKIP_P2) {
-      // ---- phase 2: every row from shared memory, one block of <= 32 rows per warp step ----
-      const StagedSrc src{val, big, F};
-      // the fast paths need wire 0 to be the constant 1 (BOOLROW classes rely on it); classes with wide coefficients keep
-      // the 128-bit evaluator
-      const bool fast_ok = val[0] == 1ull;
-      for (uint32_t ci = 0; ci < T.n_classes; ci++) {
-        const r1cs_class_dev c = s_cls[ci];
-        const uint32_t nb = s_nblk[ci], hw = 2u + 2u * (c.nA + c.nB + c.nC);
-        const bool fast = fast_ok && (c.flags & R1CS_FLAG_FAST64);
-        if (c.flags & R1CS_FLAG_MATRIX) {
-          for (uint32_t r = tid; r < ((c.count + 31u) & ~31u); r += STG_THREADS)
-            bad = min(bad, fast ? staged_matrix_row<true>(src, c, T, r) : staged_matrix_row<false>(src, c, T, r));
-        } else {
-          for (uint32_t b = warp; b < nb; b += STG_THREADS / 32) {
-            const uint32_t *hdr = T.terms + c.term_off + (size_t)b * hw;
-            bad = min(bad, fast ? staged_block<true>(src, c, T, hdr, lane) : staged_block<false>(src, c, T, hdr, lane));
-          }
-        }
-      }
-    }
-    if (bad != B3W_NO_ROW) atomicMin(&s_bad, bad);
-    __syncthreads();
-    if (tid == 0) {
-      const uint32_t verdict = s_noncanon ? B3W_NOT_CANONICAL : s_bad;
-      if (status) status[i] = verdict == B3W_NO_ROW ? 0 : B3W_R1CS_VIOLATION;
-      if (first_bad) first_bad[i] = verdict;
-    }
-  }
 }

@@ -46,12 +46,14 @@ def circuit_from_wasm(code):
     return CIRCUITS[h][0]
 
 
-def builder(code, options=None, device=-1, chunk=0, lazy=False, fused_check=False, compressible_ring=False):
+def builder(code, options=None, device=-1, chunk=0, lazy=False, fused_check=False, compressible_ring=True, reference_siblings=False):
     """builder(code, options) -> WitnessCalculator   (witness_calculator.js:1).
     `code`: bytes of one of the reference's .wasm files, or a circuit name / id.
     lazy=True defers the creation of the GPU context to the first witness call (host-logic tests).
     fused_check=True makes every batch call also run the fused on-device R1CS check (status 7 = violation).
-    compressible_ring=True puts the internal HBM ring of the host-buffer calls into compressible device memory."""
+    compressible_ring=False keeps the internal HBM ring of the host-buffer calls in ordinary memory (B3W_FLAG_PLAIN_RING); the
+    default -- here, in C and in the N-API addon -- is compressible memory with a silent fall-back to ordinary memory.
+    reference_siblings=True makes novaChain pick parent-step siblings by the reference's rule (rust_fold/src/blake3_hash.rs:60-78)."""
     if isinstance(code, int):
         cid = code
     elif isinstance(code, str):
@@ -59,7 +61,7 @@ def builder(code, options=None, device=-1, chunk=0, lazy=False, fused_check=Fals
     else:
         cid = circuit_from_wasm(code)
     return WitnessCalculator(cid, options or {}, device=device, chunk=chunk, lazy=lazy, fused_check=fused_check,
-                             compressible_ring=compressible_ring)
+                             compressible_ring=compressible_ring, reference_siblings=reference_siblings)
 
 
 def _flat_array(a):
@@ -137,11 +139,13 @@ def _nova_chain(L, call, handle, witness_size, data, want_witness):
 
 
 class WitnessCalculator:
-    def __init__(self, circuit, sanity_check, device=-1, chunk=0, lazy=False, fused_check=False, compressible_ring=False):
+    def __init__(self, circuit, sanity_check, device=-1, chunk=0, lazy=False, fused_check=False, compressible_ring=True,
+                 reference_siblings=False):
         L = _lib.lib()
         self._L, self._ctx = L, None
         self._cfg = _lib.Config(circuit, device, chunk, (_lib.B3W_FLAG_FUSED_CHECK if fused_check else 0) |
-                                (_lib.B3W_FLAG_COMPRESSIBLE_RING if compressible_ring else 0))
+                                (0 if compressible_ring else _lib.B3W_FLAG_PLAIN_RING) |
+                                (_lib.B3W_FLAG_REFERENCE_SIBLINGS if reference_siblings else 0))
         info = _lib.Info()
         _lib.check(L.b3w_circuit_info(circuit, C.byref(info)))
         if not lazy:
@@ -289,10 +293,30 @@ class WitnessCalculator:
         return np.concatenate([hdr, body])
 
     # ---- NEW: batched entry point ----
-    def calculateWitnessBatch(self, inputs, want_witness=True, out=None):
+    def _extras(self, n, sums, samples, first_bad):
+        """-> (BatchExtras or None, dict of the arrays it points into)"""
+        if not (sums or first_bad or samples is not None):
+            return None, {}
+        ex, keep = _lib.BatchExtras(), {}
+        if sums:
+            keep["sums"] = np.zeros(n, np.uint64)
+            ex.sums = keep["sums"].ctypes.data
+        if first_bad:
+            keep["first_bad"] = np.zeros(n, np.uint32)
+            ex.first_bad = keep["first_bad"].ctypes.data
+        if samples is not None:
+            idx = np.ascontiguousarray(samples, np.uint64)
+            keep["sample_idx"] = idx
+            keep["samples"] = np.zeros((idx.size, self.witnessSize * 32), np.uint8)
+            ex.sample_idx, ex.n_samples, ex.sample_out = idx.ctypes.data, idx.size, keep["samples"].ctypes.data
+        return ex, keep
+
+    def calculateWitnessBatch(self, inputs, want_witness=True, out=None, sums=False, samples=None, first_bad=False):
         """inputs: list of input objects (as for calculateWitness) or an (n, nInputs) uint32 array in
         circuit declaration order.  Returns dict(witness=(n, witnessSize*32) u8 | None, status=u8[n],
-        pub=(n, nPublic) u32)."""
+        pub=(n, nPublic) u32).  Extra results (b3w_batch_extras): sums=True adds "sums" (u64[n], the witness checksum the
+        expansion warps compute from what they store), samples=<indices> adds "samples" (their full witnesses, also when
+        want_witness=False), first_bad=True adds "first_bad" (fused check: smallest violated row)."""
         fr = None
         if isinstance(inputs, np.ndarray):
             rows = np.ascontiguousarray(inputs, np.uint32)
@@ -310,18 +334,19 @@ class WitnessCalculator:
             out = _witness_buffer(n, self.witnessSize * 32)
         status = np.zeros(n, np.uint8)
         pub = np.zeros((n, self.nPublic), np.uint32)
-        if fr is not None:
-            _lib.check(self._L.b3w_witness_batch_fr(self._h, fr.ctypes.data, n, out.ctypes.data if want_witness else None,
-                                                    status.ctypes.data, pub.ctypes.data))
-        else:
-            _lib.check(self._L.b3w_witness_batch(self._h, rows.ctypes.data, n,
-                                                 out.ctypes.data if want_witness else None,
-                                                 status.ctypes.data, pub.ctypes.data))
-        return {"witness": out if want_witness else None, "status": status, "pub": pub}
+        ex, keep = self._extras(n, sums, samples, first_bad)
+        call = self._L.b3w_witness_batch_fr_ex if fr is not None else self._L.b3w_witness_batch_ex
+        src = fr if fr is not None else rows
+        _lib.check(call(self._h, src.ctypes.data, n, out.ctypes.data if want_witness else None, status.ctypes.data, pub.ctypes.data,
+                        C.byref(ex) if ex is not None else None))
+        res = {"witness": out if want_witness else None, "status": status, "pub": pub}
+        res.update({k: v for k, v in keep.items() if k != "sample_idx"})
+        return res
 
-    def calculateWitnessBatchFr(self, values, want_witness=True):
+    def calculateWitnessBatchFr(self, values, want_witness=True, sums=False, samples=None, first_bad=False):
         """values: (n, nInputs) Python ints / an (n, nInputs, 32) uint8 array of little-endian field elements.
-        Every input the reference accepts; a nova batch that holds a value outside u32 runs on the general (slower) kernel."""
+        Every input the reference accepts.  The rows are converted on the device; u32 instances run on the hot kernels,
+        only the instances that hold a field-valued input take the general path (into the same outputs)."""
         if isinstance(values, np.ndarray) and values.dtype == np.uint8:
             fr = np.ascontiguousarray(values).reshape(-1)
             n = values.shape[0]
@@ -331,9 +356,18 @@ class WitnessCalculator:
         out = _witness_buffer(n, self.witnessSize * 32) if want_witness else None
         status = np.zeros(n, np.uint8)
         pub = np.zeros((n, self.nPublic), np.uint32)
-        _lib.check(self._L.b3w_witness_batch_fr(self._h, fr.ctypes.data, n, out.ctypes.data if want_witness else None,
-                                                status.ctypes.data, pub.ctypes.data))
-        return {"witness": out, "status": status, "pub": pub}
+        ex, keep = self._extras(n, sums, samples, first_bad)
+        _lib.check(self._L.b3w_witness_batch_fr_ex(self._h, fr.ctypes.data, n, out.ctypes.data if want_witness else None,
+                                                   status.ctypes.data, pub.ctypes.data, C.byref(ex) if ex is not None else None))
+        res = {"witness": out, "status": status, "pub": pub}
+        res.update({k: v for k, v in keep.items() if k != "sample_idx"})
+        return res
+
+    def lastTiming(self):
+        """b3w_last_timing: dict(total_ms, kernel_ms, host_ms, launches, instances, h2d_bytes, d2h_bytes) of the last host-buffer call"""
+        t = _lib.Timing()
+        _lib.check(self._L.b3w_last_timing(self._h, C.byref(t)))
+        return {k: getattr(t, k) for k, _ in _lib.Timing._fields_}
 
     # ---- NEW: compact witnesses (the per-instance trace; ~200x smaller than the .wtns body) ----
     @property
@@ -370,6 +404,27 @@ class WitnessCalculator:
             torch.cuda.synchronize()
             return d_o.cpu().numpy()
 
+    def unpackWitnessesHost(self, packed, threads=0):
+        """(n, packedWords) u32 -> (n, witnessSize*32) u8, expanded on the HOST (b3w_unpack_host): the same bytes as
+        unpackWitnesses(); needs no GPU work."""
+        packed = np.ascontiguousarray(packed, np.uint32)
+        n = packed.shape[0]
+        out = np.empty((n, self.witnessSize * 32), np.uint8)
+        _lib.check(self._L.b3w_unpack_host(self._h, packed.ctypes.data, n, out.ctypes.data, threads))
+        return out
+
+    def calculateWitnessBatchHybrid(self, rows, out=None, threads=0):
+        """b3w_witness_batch_hybrid: every .wtns body in host memory, but only the packed records cross PCIe; the expansion
+        runs on host threads.  rows: (n, nInputs) u32."""
+        rows = np.ascontiguousarray(rows, np.uint32)
+        n = rows.shape[0]
+        if out is None:
+            out = np.empty((n, self.witnessSize * 32), np.uint8)
+        status = np.zeros(n, np.uint8)
+        pub = np.zeros((n, self.nPublic), np.uint32)
+        _lib.check(self._L.b3w_witness_batch_hybrid(self._h, rows.ctypes.data, n, out.ctypes.data, status.ctypes.data, pub.ctypes.data, threads))
+        return {"witness": out, "status": status, "pub": pub}
+
     def witness_batch_packed_device(self, d_in, n, d_packed, d_status=0, d_pub=0, stream=0):
         _lib.check(self._L.b3w_witness_batch_packed_device(self._h, d_in, n, d_packed, d_status or None, d_pub or None,
                                                            stream or None))
@@ -382,6 +437,19 @@ class WitnessCalculator:
         """data: bytes.  Returns dict(n_chunks, total_steps, step_off=u64[n_chunks+1], rows=(steps,32) u32 step inputs,
         status=u8[steps], pub=(steps,15) u32 = z_{i+1}, witness=(steps, witnessSize*32) u8 | None, root=32 bytes)."""
         return _nova_chain(self._L, self._L.b3w_nova_chain, self._h, self.witnessSize, data, want_witness)
+
+    def novaChainDevice(self, data, d_out, d_status=0, d_pub=0, d_rows=0):
+        """b3w_nova_chain_device: the step witnesses stay in device memory (caller-supplied device pointers; d_out must hold
+        total_steps * witnessSize * 32 bytes).  Returns dict(n_chunks, total_steps, step_off, root)."""
+        data = bytes(data)
+        nc, ns = C.c_uint64(), C.c_uint64()
+        _lib.check(self._L.b3w_nova_chain_size(len(data), C.byref(nc), C.byref(ns)))
+        buf = np.frombuffer(data, np.uint8) if data else np.zeros(1, np.uint8)
+        step_off = np.zeros(nc.value + 1, np.uint64)
+        root = np.zeros(32, np.uint8)
+        _lib.check(self._L.b3w_nova_chain_device(self._h, buf.ctypes.data, len(data), d_out, d_status or None, d_pub or None,
+                                                 d_rows or None, step_off.ctypes.data, root.ctypes.data))
+        return {"n_chunks": nc.value, "total_steps": ns.value, "step_off": step_off, "root": root.tobytes()}
 
     # ---- NEW: compressible device memory for witness buffers (b3w_device_alloc) ----
     def device_alloc(self, nbytes, compressible=True):
@@ -404,13 +472,18 @@ class WitnessCalculator:
         _lib.check(self._L.b3w_witness_batch_device_checked(self._h, d_in, n, d_out, d_status or None, d_pub or None,
                                                             d_first_bad or None, stream or None))
 
+    def witness_batch_device_ex(self, d_in, n, d_out, d_status=0, d_pub=0, d_first_bad=0, d_sums=0, d_m_ext=0, check=False, stream=0):
+        """b3w_witness_batch_device_ex: everything at once (wide message words, fused check, per-instance checksums)"""
+        _lib.check(self._L.b3w_witness_batch_device_ex(self._h, d_in, d_m_ext or None, n, d_out, d_status or None, d_pub or None,
+                                                       d_first_bad or None, d_sums or None, 1 if check else 0, stream or None))
+
     def witness_batch_device_wide(self, d_in, d_m_ext, n, d_out, d_status=0, d_pub=0, d_first_bad=0, stream=0):
         """blake3_compression with wide message words (m = m_ext * 2^32 + row word); d_first_bad != 0 adds the fused check"""
         _lib.check(self._L.b3w_witness_batch_device_wide(self._h, d_in, d_m_ext, n, d_out, d_status or None, d_pub or None,
                                                          d_first_bad or None, stream or None))
 
     def r1cs_check_device(self, d_wit, n, d_status=0, d_first_bad=0, stream=0):
-        """stand-alone R1CS check of witnesses resident in device memory (O1 builds)"""
+        """stand-alone R1CS check of witnesses resident in device memory (all four circuits have a built-in system)"""
         _lib.check(self._L.b3w_r1cs_check_device(self._h, d_wit, n, d_status or None, d_first_bad or None, stream or None))
 
     def r1cs_load(self, r1cs):
@@ -423,6 +496,12 @@ class WitnessCalculator:
             _lib.check(self._L.b3w_r1cs_load_file(self._h, str(r1cs).encode(), C.byref(n)))
         return n.value
 
+    def r1cs_program_info(self):
+        """-> dict(rows, compiled, xor_runs, tiles): how the context's constraint system was split for the stand-alone check"""
+        v = [C.c_uint32() for _ in range(4)]
+        _lib.check(self._L.b3w_r1cs_program_info(self._h, *[C.byref(x) for x in v]))
+        return dict(zip(("rows", "compiled", "xor_runs", "tiles"), (x.value for x in v)))
+
     def r1cs_info(self):
         rows, terms = C.c_uint32(), C.c_uint32()
         _lib.check(self._L.b3w_r1cs_info(self.circuit, C.byref(rows), C.byref(terms)))
@@ -434,6 +513,10 @@ class WitnessCalculator:
     def set_launch(self, ctas_per_sm=0, parts=0):
         """tuning hook: cap on resident CTAs per SM, work items per instance (0 = defaults)"""
         _lib.check(self._L.b3w_debug_set_launch(self._h, int(ctas_per_sm), int(parts)))
+
+    def set_store_mode(self, mode=0):
+        """tuning hook: 0 = direct 256-bit stores, 1 = shared-memory tiles + TMA bulk stores"""
+        _lib.check(self._L.b3w_debug_set_store_mode(self._h, int(mode)))
 
     def checksum_device(self, d_wit, n, d_sums, stream=0):
         _lib.check(self._L.b3w_checksum_device(self._h, d_wit, n, d_sums, stream or None))
@@ -448,7 +531,7 @@ class MultiGpuCalculator:
     """NEW: the batched entry point over several GPUs of one node (b3w_multi_*, include/blake3wit.h): contiguous index
     ranges, one context and host thread per device, no collective.  devices=None takes every visible device."""
 
-    def __init__(self, circuit, devices=None, chunk=0, fused_check=False, compressible_ring=False):
+    def __init__(self, circuit, devices=None, chunk=0, fused_check=False, compressible_ring=True, reference_siblings=False):
         L = _lib.lib()
         self._L = L
         cid = circuit if isinstance(circuit, int) else (CIRCUIT_IDS[circuit] if isinstance(circuit, str) else circuit_from_wasm(circuit))
@@ -456,7 +539,8 @@ class MultiGpuCalculator:
         _lib.check(L.b3w_circuit_info(cid, C.byref(info)))
         self.circuit, self.witnessSize, self.nInputs, self.nPublic = cid, info.witness_size, info.n_inputs, info.n_public
         cfg = _lib.Config(cid, -1, chunk, (_lib.B3W_FLAG_FUSED_CHECK if fused_check else 0) |
-                          (_lib.B3W_FLAG_COMPRESSIBLE_RING if compressible_ring else 0))
+                          (0 if compressible_ring else _lib.B3W_FLAG_PLAIN_RING) |
+                          (_lib.B3W_FLAG_REFERENCE_SIBLINGS if reference_siblings else 0))
         devs = (C.c_int32 * len(devices))(*devices) if devices else None
         h = C.c_void_p()
         _lib.check(L.b3w_multi_create(C.byref(cfg), devs, len(devices) if devices else 0, C.byref(h)))
@@ -480,7 +564,7 @@ class MultiGpuCalculator:
         _lib.check(self._L.b3w_shard_range(n, g, self.nDevices, C.byref(first), C.byref(count)))
         return first.value, count.value
 
-    def calculateWitnessBatch(self, rows, want_witness=True, out=None):
+    def calculateWitnessBatch(self, rows, want_witness=True, out=None, sums=False, samples=None, first_bad=False):
         rows = np.ascontiguousarray(rows, np.uint32)
         if rows.ndim != 2 or rows.shape[1] != self.nInputs:
             raise ValueError("expected an (n, %d) uint32 array" % self.nInputs)
@@ -489,14 +573,17 @@ class MultiGpuCalculator:
             out = _witness_buffer(n, self.witnessSize * 32)
         status = np.zeros(n, np.uint8)
         pub = np.zeros((n, self.nPublic), np.uint32)
-        _lib.check(self._L.b3w_multi_witness_batch(self._m, rows.ctypes.data, n, out.ctypes.data if want_witness else None,
-                                                   status.ctypes.data, pub.ctypes.data))
-        return {"witness": out if want_witness else None, "status": status, "pub": pub}
+        ex, keep = WitnessCalculator._extras(self, n, sums, samples, first_bad)
+        _lib.check(self._L.b3w_multi_witness_batch_ex(self._m, rows.ctypes.data, n, out.ctypes.data if want_witness else None,
+                                                      status.ctypes.data, pub.ctypes.data, C.byref(ex) if ex is not None else None))
+        res = {"witness": out if want_witness else None, "status": status, "pub": pub}
+        res.update({k: v for k, v in keep.items() if k != "sample_idx"})
+        return res
 
     def novaChain(self, data, want_witness=False):
         """WitnessCalculator.novaChain over all devices: chunks are sharded (balanced by step count), no collective."""
         return _nova_chain(self._L, self._L.b3w_multi_nova_chain, self._m, self.witnessSize, data, want_witness)
 
-    def witness_batch_host(self, h_in, n, h_out=None, h_status=None, h_pub=None):
-        """raw host pointers (e.g. from b3w_host_alloc); used by the benches"""
-        _lib.check(self._L.b3w_multi_witness_batch(self._m, h_in, n, h_out, h_status, h_pub))
+    def witness_batch_host(self, h_in, n, h_out=None, h_status=None, h_pub=None, extras=None):
+        """raw host pointers (e.g. from b3w_host_alloc); used by the benches.  extras: a _lib.BatchExtras or None"""
+        _lib.check(self._L.b3w_multi_witness_batch_ex(self._m, h_in, n, h_out, h_status, h_pub, C.byref(extras) if extras is not None else None))

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define B3W_VERSION 0x000100
+#define B3W_VERSION 0x000200
 
 #define B3W_OK 0
 #define B3W_ERR_INVALID (-1)     /* bad argument */
@@ -33,8 +33,15 @@ extern "C" {
 #define B3W_NO_ROW 0xFFFFFFFFu   /* "no violated row" in first_bad[] */
 
 #define B3W_FLAG_FUSED_CHECK 1u  /* b3w_config.flags: every batch call also runs the fused R1CS check */
-#define B3W_FLAG_COMPRESSIBLE_RING 2u /* b3w_config.flags: the internal HBM ring of the host-buffer calls is compressible memory */
+#define B3W_FLAG_COMPRESSIBLE_RING 2u /* accepted for compatibility: the ring IS compressible by default since 0x000200 */
+#define B3W_FLAG_PLAIN_RING 4u   /* b3w_config.flags: keep the internal HBM ring of the host-buffer calls in ordinary (cudaMalloc) memory.
+                                    Default everywhere (C, Python, N-API): compressible memory when the driver grants it, silently
+                                    ordinary memory otherwise */
+#define B3W_FLAG_REFERENCE_SIBLINGS 8u /* b3w_config.flags, b3w_nova_chain*: pick the sibling of every parent step exactly as the
+                                    reference does (rust_fold/src/blake3_hash.rs:60-78, by bit of the chunk index) instead of the
+                                    BLAKE3 tree's true sibling; see b3w_nova_chain */
 #define B3W_MEM_COMPRESSIBLE 1u  /* b3w_device_alloc flags */
+#define B3W_MAX_SAMPLES 1024u    /* b3w_batch_extras.n_samples */
 
 /* Circuit variants = the reference's committed witness programs:
  *   COMPRESSION   build/blake3_compression/blake3_compression_js/blake3_compression.wasm (BN254, O1)
@@ -52,7 +59,7 @@ typedef struct {
   uint32_t circuit;        /* b3w_circuit */
   int32_t device;          /* CUDA device ordinal; -1 = current device */
   uint32_t chunk;          /* instances per internal HBM ring slot for host-buffer batches; 0 = default */
-  uint32_t flags;          /* 0 or B3W_FLAG_FUSED_CHECK */
+  uint32_t flags;          /* 0 or an OR of B3W_FLAG_* */
 } b3w_config;
 
 /* What the WitnessCalculator constructor caches (witness_calculator.js:108-125). */
@@ -70,7 +77,14 @@ typedef struct b3w_ctx b3w_ctx;
 int b3w_version(void);
 const char *b3w_last_error(void);                       /* thread-local text of the last failure */
 
-/* replaces builder() + new WitnessCalculator (witness_calculator.js:1-125): one ctx per GPU, not re-entrant */
+/* replaces builder() + new WitnessCalculator (witness_calculator.js:1-125): one ctx per GPU.
+ * Ownership / threading: a b3w_ctx takes ONE call at a time.  The host-buffer entry points share the context's HBM ring,
+ * streams and scratch; each of them holds the context's internal lock for its whole duration, so calls made concurrently
+ * from several threads (e.g. overlapping `await`s of one calculator through the N-API addon's worker threads) are
+ * serialised, never interleaved -- the reference's wasm calculator runs each call to completion too.  For parallelism use
+ * one context per thread, or b3w_multi_*.  Every entry point runs on the context's device and restores the calling
+ * thread's current CUDA device before it returns.  The *_device entry points are asynchronous on the caller's stream; at
+ * most 32 of their launches may be in flight per context before a new launch waits for the oldest one. */
 int b3w_create(const b3w_config *cfg, b3w_ctx **out);
 void b3w_destroy(b3w_ctx *ctx);
 
@@ -101,6 +115,40 @@ int b3w_witness_one(b3w_ctx *ctx, const uint32_t *in, uint8_t *out);
  * Host buffers from b3w_host_alloc() are pinned and copy at full PCIe rate. */
 int b3w_witness_batch(b3w_ctx *ctx, const uint32_t *in, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub);
 
+/* Optional extra results of a batch call (BASELINE config 5's compact-result contract, SURVEY.md 8(d): per instance the
+ * public outputs, a status byte and a 64-bit checksum of the witness bytes, plus full witnesses for a <= 1 024-instance
+ * sample).  Every pointer may be NULL.
+ *   sums       n u64: the checksum b3w_checksum_device defines, computed by the kernel's expansion warps from the very
+ *              values they store (no re-read of HBM); 0 for an instance that asserts (no witness exists).  What a consumer
+ *              needs to know that the witness it later reads is the one that was generated and checked
+ *              (rust_fold/src/utils.rs:78-85 enforces every row on the vector it was handed).
+ *   sample_idx n_samples instance indices in [0, n), any order, n_samples <= B3W_MAX_SAMPLES: their full witnesses are
+ *              copied out of the HBM ring into sample_out (n_samples * witness_size * 32 bytes), also when out == NULL.
+ *   first_bad  n u32: with the fused check, the smallest violated row id or B3W_NO_ROW. */
+typedef struct {
+  uint64_t *sums;
+  const uint64_t *sample_idx;
+  uint32_t n_samples;
+  uint8_t *sample_out;
+  uint32_t *first_bad;
+} b3w_batch_extras;
+int b3w_witness_batch_ex(b3w_ctx *ctx, const uint32_t *in, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub,
+                         const b3w_batch_extras *extras);
+
+/* Per-call timing of the LAST host-buffer call of this context (b3w_witness_batch*, b3w_nova_chain, b3w_witness_batch_packed,
+ * b3w_witness_batch_hybrid): the reference prints per-stage wall times (test/witness_gen.test.ts:43-50,
+ * rust_fold/src/main.rs:167-178).  kernel_ms is measured with CUDA events around every witness-kernel launch of the call;
+ * the stages also carry NVTX ranges ("b3w:h2d", "b3w:kernel", "b3w:d2h", "b3w:host_unpack"). */
+typedef struct {
+  double total_ms;         /* wall clock of the call */
+  double kernel_ms;        /* sum over the call's witness-kernel launches (device time) */
+  double host_ms;          /* host-side work inside the call (Fr conversion set-up, host unpack) */
+  uint64_t launches;       /* witness-kernel launches */
+  uint64_t instances;
+  uint64_t h2d_bytes, d2h_bytes;
+} b3w_timing;
+int b3w_last_timing(b3w_ctx *ctx, b3w_timing *out);
+
 /* Field-element inputs: n rows of n_inputs Fr256 (32 bytes little-endian each, any 256-bit value: reduced mod p like
  * `normalize`, witness_calculator.js:319-323) -- the form in which rust_fold holds them (`Vec<(String, Vec<F>)>`,
  * rust_fold/src/blake3_circuit.rs:197-289).  b3w_inputs_from_fr converts to the u32 rows of the other entry points
@@ -108,6 +156,8 @@ int b3w_witness_batch(b3w_ctx *ctx, const uint32_t *in, uint64_t n, uint8_t *out
  * instance and signal.  b3w_witness_batch_fr takes ANY field elements (see "The FULL input domain" below). */
 int b3w_inputs_from_fr(uint32_t circuit, const uint8_t *in_fr, uint64_t n, uint32_t *rows);
 int b3w_witness_batch_fr(b3w_ctx *ctx, const uint8_t *in_fr, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub);
+int b3w_witness_batch_fr_ex(b3w_ctx *ctx, const uint8_t *in_fr, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub,
+                            const b3w_batch_extras *extras);
 
 /* The FULL input domain.  The reference takes any field element for every input (witness_calculator.js:319-323) and lets
  * the circuit decide.  b3w_witness_batch_fr (above) does the same for all four circuits: every input the reference accepts
@@ -124,9 +174,11 @@ int b3w_witness_batch_fr(b3w_ctx *ctx, const uint8_t *in_fr, uint64_t n, uint8_t
  *                             that leave [0, 2^34) are detected on the device (status 4, no witness, pub = 0).  With
  *                             d_first_bad != NULL or B3W_FLAG_FUSED_CHECK the fused R1CS check runs as well.
  * nova step circuits: as built they constrain little (leaf_depth - depth in [1, 256], chunk_idx_low + 2^32 chunk_idx_high
- * < 2^65, and the embedded compression's ranges); n_blocks, block_count, total_depth, depth may be ANY field elements.  A
- * batch that holds a value outside u32 runs on a general kernel that evaluates the nova-level logic on field elements
- * (pub then holds the low 32 bits of the outputs; the fused-check flag is refused for such a batch).
+ * < 2^65, and the embedded compression's ranges); n_blocks, block_count, total_depth, depth may be ANY field elements.  The
+ * Fr256 rows are converted ON THE DEVICE (one warp per instance): u32 instances run on the hot kernel, and only the instances
+ * that hold a value outside u32 run on a general kernel that evaluates the nova-level logic on field elements, into the
+ * same output buffers (pub then holds the low 32 bits of the outputs).  With B3W_FLAG_FUSED_CHECK the u32 instances get the
+ * fused check and the others the stand-alone evaluator on their finished witnesses; sums / samples work for both.
  *   b3w_assert_trace_fr       b3w_assert_trace for ONE Fr256 input row of any circuit: the reference's per-template trace of
  *                             the first failing constraint in the wasm's execution order, e.g. for b = 2^33 "Error in template
  *                             ToBits_3 line: 153\nError in template RotXorWordBits_5 line: 62\nError in template HalfFunG_18 line: 91\n...". */
@@ -151,11 +203,20 @@ int b3w_witness_batch_device(b3w_ctx *ctx, const uint32_t *d_in, uint64_t n, uin
  * (test/blake3_hash.test.ts:36) and bellpepper's enforce (rust_fold/src/utils.rs:78-85). */
 int b3w_witness_batch_device_checked(b3w_ctx *ctx, const uint32_t *d_in, uint64_t n, uint8_t *d_out, uint8_t *d_status,
                                      uint32_t *d_pub, uint32_t *d_first_bad, void *stream);
+/* Everything at once, DEVICE buffers: d_m_ext (compression only, may be NULL) selects the wide-domain kernel; check != 0 or
+ * d_first_bad != NULL adds the fused R1CS check; d_sums (n u64, may be NULL) receives the per-instance witness checksums of
+ * b3w_batch_extras.sums, computed by the expansion warps from the values they store. */
+int b3w_witness_batch_device_ex(b3w_ctx *ctx, const uint32_t *d_in, const int8_t *d_m_ext, uint64_t n, uint8_t *d_out,
+                                uint8_t *d_status, uint32_t *d_pub, uint32_t *d_first_bad, uint64_t *d_sums, int check, void *stream);
 
-/* Stand-alone R1CS check of witnesses that are RESIDENT IN DEVICE MEMORY: sparse A.z * B.z - C.z over Fr, one CTA per
- * instance (the witness is streamed from HBM once into a compact shared-memory copy, rows are evaluated from there).
- * Built-in rows exist for the O1 builds (blake3_compression, NOVA_BN_O1), whose witness still holds every value the
- * template-level rows mention; for the O2 builds load a system first (b3w_r1cs_load), else B3W_ERR_UNSUPPORTED.
+/* Stand-alone R1CS check of witnesses that are RESIDENT IN DEVICE MEMORY (e.g. from another producer, or read back later):
+ * sparse A.z * B.z - C.z over Fr, exact.  One CTA per instance streams the witness from HBM once into a compact
+ * shared-memory copy and evaluates a program compiled from the constraint system (booleanity rows as bit masks, XOR rows as
+ * bit-field compares, recompositions as runs: hot_proofs_blake3_circom_b200/csrc/kernels_r1cs_fast.cuh).  Built-in systems
+ * exist for ALL FOUR circuits: the template-level rows of the O1 builds (blake3_compression 24 544 rows, NOVA_BN_O1 25 064)
+ * and the O2-form system of NOVA_BN_O2 / NOVA_PASTA_O2 (23 743 rows over the 23 291 surviving wires; tools/gen_r1cs.py);
+ * b3w_r1cs_load replaces them by a file's.  This is the check that LOOKS AT THE EMITTED BYTES -- a wrong slot descriptor or
+ * a lost store shows here; the fused check of the *_checked kernels validates the trace the witness is expanded from.
  * d_first_bad[i] = smallest violated row, B3W_NO_ROW, or 0xFFFFFFFE when a slot is not a canonical field element. */
 int b3w_r1cs_check_device(b3w_ctx *ctx, const uint8_t *d_wit, uint64_t n, uint8_t *d_status, uint32_t *d_first_bad,
                           void *stream);
@@ -170,6 +231,12 @@ int b3w_r1cs_check_device(b3w_ctx *ctx, const uint8_t *d_wit, uint64_t n, uint8_
  * receives the number of constraints. */
 int b3w_r1cs_load(b3w_ctx *ctx, const uint8_t *r1cs, size_t len, uint32_t *n_rows);
 int b3w_r1cs_load_file(b3w_ctx *ctx, const char *path, uint32_t *n_rows);
+/* How the context's system (built-in or loaded) was split: rows in all, rows covered by the compiled program (the others
+ * stay with the general row evaluator), XOR runs and row tiles of the program.  Any pointer may be NULL. */
+int b3w_r1cs_program_info(b3w_ctx *ctx, uint32_t *n_rows, uint32_t *n_compiled, uint32_t *n_xor_runs, uint32_t *n_tiles);
+/* ditto for a circuit's BUILT-IN system, host-only (needs no GPU); n_items = 16-byte items of the row tiles. */
+int b3w_r1cs_compile_stats(uint32_t circuit, uint32_t *n_rows, uint32_t *n_compiled, uint32_t *n_xor_runs, uint32_t *n_tiles,
+                           uint32_t *n_items);
 
 /* rows / non-zero terms of the circuit's template-level constraint system in O1 form
  * (blake3_compression: 24 544 rows = 23 376 quadratic + 1 168 linear; nova: 25 064) */
@@ -182,6 +249,10 @@ int b3w_debug_inject_fault(b3w_ctx *ctx, uint32_t trace_word, uint32_t xor_mask)
 /* Tuning hook: cap the persistent grid at `ctas_per_sm` resident CTAs per SM (0 = the per-kernel default) and set the
  * number of work items an instance's witness is split into (0 = default; the items are scheduled dynamically). */
 int b3w_debug_set_launch(b3w_ctx *ctx, int ctas_per_sm, uint32_t parts);
+/* Tuning hook: how the expansion writes witness bytes.  0 = one 256-bit store per slot straight from registers (default);
+ * 1 = expanded tiles staged in shared memory and written by the TMA engine (cp.async.bulk shared -> global), plain
+ * u32-input kernels only. */
+int b3w_debug_set_store_mode(b3w_ctx *ctx, int mode);
 
 /* Per-instance 64-bit checksum of witnesses resident in device memory (reads them back from HBM):
  *   sum_i = SUM over slots s, limbs j of  (limb64[s][j] + 1) * mix(4*s + j)   (mod 2^64),
@@ -209,10 +280,24 @@ int b3w_calib_fill_bulk(b3w_ctx *ctx, uint8_t *d_buf, uint64_t bytes, void *stre
  *   rows     total_steps * 32 u32: the step inputs in circuit declaration order, or NULL
  *   step_off n_chunks + 1 u64: first step of each chunk, or NULL
  *   root     32 bytes: h_out of the last step of chunk 0 (= the BLAKE3 hash of the input for tree shapes on which the
- *            circuit's left/right rule, bit i of chunk_idx, agrees with the BLAKE3 tree: always for 2^k chunks). */
+ *            circuit's left/right rule, bit i of chunk_idx, agrees with the BLAKE3 tree: always for 2^k chunks).
+ * Non-power-of-two chunk counts.  The circuit orders (h, sibling) by bit `total_depth - 2 - depth` of chunk_idx, which is the
+ * real direction only where the BLAKE3 tree is perfect above the chunk.  DEFAULT here: the sibling of every parent step is the
+ * TRUE BLAKE3 sibling (what a bao slice proves); chunks on the right spine of an imperfect tree then do not fold to
+ * blake3(file) (tests/test_gpu_chain.py records which: e.g. the last chunk of 3, 5, 6, 7).  This deliberately DIFFERS from the
+ * reference, whose hash_with_path (rust_fold/src/blake3_hash.rs:60-78) also reads the direction off the chunk index and takes
+ * the parent node's other half by THAT direction -- for chunk 4 of 5 the chunk's own chaining value.
+ * B3W_FLAG_REFERENCE_SIBLINGS in b3w_config.flags restates that rule literally (pinned against oracle/nova_chain_ref.py's
+ * restatement of that file); both rules agree on every 2^k-chunk file, the only shape rust_fold's tests assert on.
+ * b3w_nova_chain_device: the same driver with the step witnesses left IN DEVICE MEMORY -- d_out (total_steps * witness_size *
+ * 32 bytes, 32-byte aligned, required), d_status / d_pub / d_rows (may be NULL) are caller-supplied DEVICE buffers, all step
+ * witnesses come from one launch and only the file crosses PCIe: the hand-off for a prover on the same GPU.  step_off and
+ * root are host arrays as above.  Returns after the device work has finished. */
 int b3w_nova_chain_size(uint64_t len, uint64_t *n_chunks, uint64_t *total_steps);
 int b3w_nova_chain(b3w_ctx *ctx, const uint8_t *data, uint64_t len, uint8_t *out, uint8_t *status, uint32_t *pub,
                    uint32_t *rows, uint64_t *step_off, uint8_t root[32]);
+int b3w_nova_chain_device(b3w_ctx *ctx, const uint8_t *data, uint64_t len, uint8_t *d_out, uint8_t *d_status, uint32_t *d_pub,
+                          uint32_t *d_rows, uint64_t *step_off, uint8_t root[32]);
 
 /* COMPACT ("packed") witnesses.  Every slot of a witness is a pure function of the instance's trace (the few hundred u32
  * values the circuit really computes: sums with carries, rotated words, step flags) and of the static slot table, so the
@@ -227,6 +312,15 @@ int b3w_witness_batch_packed_device(b3w_ctx *ctx, const uint32_t *d_in, uint64_t
                                     uint32_t *d_pub, void *stream);
 int b3w_witness_batch_packed(b3w_ctx *ctx, const uint32_t *in, uint64_t n, uint32_t *packed, uint8_t *status, uint32_t *pub);
 int b3w_unpack_device(b3w_ctx *ctx, const uint32_t *d_packed, uint64_t n, uint8_t *d_out, void *stream);
+/* The same expansion on the HOST: packed records (host memory) -> .wtns bodies (host memory), bit-identical to
+ * b3w_unpack_device; `threads` host threads (0 = all hardware threads), non-temporal stores.  A format conversion of records
+ * the GPU computed -- what witness_calculator.js:263-269 does slot by slot -- not a CPU witness path: there is none. */
+int b3w_unpack_host(b3w_ctx *ctx, const uint32_t *packed, uint64_t n, uint8_t *out, uint32_t threads);
+/* HYBRID export: as b3w_witness_batch (every .wtns body ends up in the caller's host buffer `out`, which need not be
+ * pinned), but only the 3.8 / 5.3 KB packed records cross PCIe and the 200x expansion runs on `threads` host threads while
+ * the next chunk is computed and copied.  Bound by the host's memory write bandwidth instead of PCIe. */
+int b3w_witness_batch_hybrid(b3w_ctx *ctx, const uint32_t *in, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub,
+                             uint32_t threads);
 
 /* Multi-GPU form of b3w_witness_batch (BASELINE config 5; north_star: "each GPU fills its own slice of the host-pinned
  * output").  Witnesses are independent, so the batch [0, n) is cut into contiguous index ranges, one per device, each
@@ -239,6 +333,10 @@ void b3w_multi_destroy(b3w_multi *m);
 uint32_t b3w_multi_size(const b3w_multi *m);
 int b3w_shard_range(uint64_t n, uint32_t g, uint32_t n_shards, uint64_t *first, uint64_t *count);
 int b3w_multi_witness_batch(b3w_multi *m, const uint32_t *in, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub);
+/* ditto with the extra results of b3w_witness_batch_ex (sums / first_bad are sliced like status; every sample is fetched by
+ * the device that owns its instance): BASELINE config 5's streamed form -- out == NULL, fused check, sums, <= 1 024 samples. */
+int b3w_multi_witness_batch_ex(b3w_multi *m, const uint32_t *in, uint64_t n, uint8_t *out, uint8_t *status, uint32_t *pub,
+                               const b3w_batch_extras *extras);
 /* b3w_nova_chain over several GPUs: the unit of sharding is a chunk (its steps chain into each other, chunks do not);
  * every device hashes the whole BLAKE3 tree (cheap) and generates the step witnesses of a contiguous range of chunks,
  * ranges balanced by step count, each writing its slice of the caller's arrays.  Same arguments as b3w_nova_chain. */

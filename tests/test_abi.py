@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(built):
     for s in syms:
         assert hasattr(L, s), "libblake3wit.so does not export %s" % s
     assert set(syms) == set(_lib.EXPORTS)
-    assert L.b3w_version() == 0x000100
+    assert L.b3w_version() == _lib.B3W_VERSION == 0x000200
 
 
 def test_no_torch_types_in_header():

@@ -479,10 +479,43 @@ def build(check_only=False, verbose=True):
             print("%-18s %6d rows in witness-slot space (%d quadratic), %d classes, %d terms; satisfied by the reference's witnesses"
                   % (setname, len(srows), sum(1 for r in srows if r[0]), len(sclasses), snnz))
         sets.append((setname, sclasses, len(srows), snnz))
+    # O2 builds (blake3_nova_js, blake3_nova_pasta_js): circom's O2 pass removed one signal per linear constraint, so the
+    # template-level rows above no longer fit their witnesses.  tools/export_r1cs.py re-derives the O2-form system by
+    # solving every linear row for the signal the O2 witness dropped and substituting it; the result has integer
+    # coefficients (<= 65 bits) and is THE SAME for both primes -- one built-in set serves both contexts.
+    import export_r1cs as ex
+    import numpy as np
+    o2rows = None
+    for variant in ("nova_bn_o2", "nova_pasta_o2"):
+        ref = RefWasm(variant)
+        w2s = np.frombuffer(ref.memory(gt.W2S_OFFSET[variant], 4 * ref.witness_size), np.uint32)
+        rng2 = random.Random(2024)
+        for trial in range(2):
+            inputs = gt.random_inputs(variant, rng2, edge=0)
+            mdl = gt.model_for(variant, inputs, ref.prime)
+            rows_d, _ = ex.derive(mdl, w2s)
+            r = {(tuple(sorted(A.items())), tuple(sorted(B.items())), tuple(sorted(C.items()))) for A, B, C in rows_d}
+            assert o2rows is None or r == o2rows, "the O2-form system depends on the input or the prime"
+            o2rows = r
+            d, pos = {}, 0
+            for nm, sz in ref.plan:
+                d[nm] = inputs[pos:pos + sz]
+                pos += sz
+            rc, wit = ref.calculate(d)
+            assert rc == 0
+            wi = [int.from_bytes(wit[32 * i:32 * i + 32].tobytes(), "little") for i in range(ref.witness_size)]
+            check_slot_rows(o2rows, wi, ref.prime)         # the reference's own witness satisfies every row
+    o2classes = classify_slots(o2rows, [0] * ref.witness_size)   # value kinds are not needed: the stand-alone checker classifies at run time
+    o2nnz = sum(len(a) + len(b) + len(c) for a, b, c in o2rows)
+    if verbose:
+        print("%-18s %6d rows in witness-slot space (%d quadratic), %d classes, %d terms; satisfied by the reference's witnesses (both primes)"
+              % ("NOVA_O2_SLOTS", len(o2rows), sum(1 for r in o2rows if r[0]), len(o2classes), o2nnz))
+    sets.append(("NOVA_O2_SLOTS", o2classes, len(o2rows), o2nnz))
     out = ["/* GENERATED by tools/gen_r1cs.py -- do not edit.",
            " * R1CS rows re-derived from the circom templates (the reference's .r1cs files are absent).",
            " *   *_FUSED sets: VALUE space, a term is a slot descriptor (trace_layout.h); identities dropped, XOR rows folded.",
-           " *   *_SLOTS sets: WITNESS-SLOT space of an O1 build, a term is a slot index (all 24 544 rows for compression).",
+           " *   *_SLOTS sets: WITNESS-SLOT space, a term is a slot index (all 24 544 rows for compression; NOVA_O2_SLOTS = the O2-form",
+           " *                 system of blake3_nova_js / blake3_nova_pasta_js, identical for both primes).",
            " * Grouped by shape; term columns run-length encoded. */",
            "#pragma once", "#include <stdint.h>", '#include "slot_tables.h"',
            "typedef struct { uint16_t nA, nB, nC, flags; uint32_t count, coef_off, col_off; } b3w_r1cs_class;", ""]
