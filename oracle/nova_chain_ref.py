@@ -28,13 +28,22 @@ def chunk_cv(chunk, idx):
     return h
 
 
-def tree_paths(cvs):
-    """-> per chunk: list of sibling CVs, root first (= Blake3HashProof.parent_path)."""
+def tree_paths(cvs, reference_siblings=False):
+    """-> per chunk: list of sibling CVs, root first (= Blake3HashProof.parent_path).
+    Default: the TRUE sibling of every parent on the chunk's path (the child the path does not descend into).
+    reference_siblings=True restates rust_fold/src/blake3_hash.rs:60-78 literally: the bao slice holds, root first, the
+    64-byte parent nodes (left CV || right CV) on the path; for parent i of par_len the reference computes
+    `mask = 1 << (par_len - i - 1)`, direction Left iff `leaf & mask == 0`, and keeps bytes 32..64 (the right child) when
+    descending left, bytes 0..32 (the left child) otherwise -- whatever the path really does at that node."""
     paths = [[] for _ in cvs]
 
     def rec(first, n, stack):
         if n == 1:
-            paths[first] = list(stack)
+            if reference_siblings:
+                par_len = len(stack)
+                paths[first] = [(rcv if first & (1 << (par_len - i - 1)) == 0 else lcv) for i, (lcv, rcv, _) in enumerate(stack)]
+            else:
+                paths[first] = [(rcv if went_left else lcv) for lcv, rcv, went_left in stack]
             return cvs[first]
         left = 1
         while left * 2 < n:
@@ -42,8 +51,8 @@ def tree_paths(cvs):
         # hash children first (need both CVs before descending with the sibling known)
         lcv = subtree_cv(first, left)
         rcv = subtree_cv(first + left, n - left)
-        rec(first, left, stack + [rcv])
-        rec(first + left, n - left, stack + [lcv])
+        rec(first, left, stack + [(lcv, rcv, True)])
+        rec(first + left, n - left, stack + [(lcv, rcv, False)])
         return b3.compress(b3.IV, lcv + rcv, 0, 0, 64, PARENT)[:8]
 
     memo = {}
@@ -65,11 +74,11 @@ def tree_paths(cvs):
     return paths
 
 
-def chain_rows(data):
+def chain_rows(data, reference_siblings=False):
     """-> (rows: list of 32-int step inputs in circuit declaration order, step_off, final h_out per chunk)."""
     chunks = [data[i:i + 1024] for i in range(0, len(data), 1024)] or [b""]
     cvs = [chunk_cv(c, i) for i, c in enumerate(chunks)]
-    paths = tree_paths(cvs)
+    paths = tree_paths(cvs, reference_siblings)
     rows, step_off, finals = [], [0], []
     for c, chunk in enumerate(chunks):
         parent_path = paths[c]

@@ -167,3 +167,23 @@ def test_header_is_plain_c_and_links_from_c(built, tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, r.returncode
     assert "Signal nope not found" in r.stdout
+
+
+def test_builtin_systems_compile_completely(built):
+    """fp_compile (host-only): every row of the four built-in constraint systems is covered by the compiled program of the
+    stand-alone checker -- booleanity masks, XOR runs, row tiles -- so the general evaluator has nothing left to do"""
+    L = pkg.lib()
+    want = {0: (24544, 464), 1: (23743, 464), 2: (23743, 464), 3: (25064, 464)}
+    for circuit, (rows, xor_runs) in want.items():
+        v = [C.c_uint32() for _ in range(5)]
+        assert L.b3w_r1cs_compile_stats(circuit, *[C.byref(x) for x in v]) == 0
+        n_rows, n_compiled, n_xor, n_tiles, n_items = (x.value for x in v)
+        assert (n_rows, n_compiled, n_xor) == (rows, rows, xor_runs), (circuit, n_rows, n_compiled, n_xor)
+        assert 30 < n_tiles < 100 and n_items < 20000
+
+
+def test_extras_and_timing_structs_match_the_header():
+    hdr = open(os.path.join(ROOT, "include", "blake3wit.h")).read()
+    assert "uint64_t *sums;" in hdr and "const uint64_t *sample_idx;" in hdr and "uint32_t *first_bad;" in hdr
+    assert C.sizeof(_lib.BatchExtras) == 40 and C.sizeof(_lib.Timing) == 56
+    assert _lib.B3W_MAX_SAMPLES == 1024

@@ -115,3 +115,71 @@ def test_chain_called_twice_with_shrinking_input(wc):
     res = wc.novaChain(small)
     rows, off, finals = nova_chain_ref.chain_rows(small)
     assert np.array_equal(res["rows"], np.array(rows, np.uint32)) and res["root"] == finals[0]
+
+
+# ---- non-power-of-two chunk counts: which chunks fold to blake3(file), under both sibling rules --------------------------
+# The circuit orders (h, sibling) by a bit of the chunk index, which is the real direction only under a perfect subtree.
+# Pinned so the behaviour cannot drift: for 3, 5, 6, 7, 9 chunks exactly the chunks listed here do NOT reach the file's hash,
+# with the true BLAKE3 sibling (default) and with the reference's rule (rust_fold/src/blake3_hash.rs:60-78) alike.
+NOT_FOLDING = {2: [], 3: [2], 4: [], 5: [4], 6: [4, 5], 7: [6], 8: [], 9: [8]}
+
+
+@pytest.mark.parametrize("reference_siblings", [False, True], ids=["true-sibling", "reference-rule"])
+def test_imperfect_trees_are_pinned(built, reference_siblings):
+    w = pkg.builder("blake3_nova", device=0, reference_siblings=reference_siblings)
+    differs = 0
+    for nch, bad in NOT_FOLDING.items():
+        data = synth(nch * 1024 - 5)
+        res = w.novaChain(data)
+        rows, off, finals = nova_chain_ref.chain_rows(data, reference_siblings)
+        assert res["total_steps"] == len(rows) and list(res["step_off"]) == off
+        assert np.array_equal(res["rows"], np.array(rows, np.uint32))          # the restatement of the chosen rule, row by row
+        digest = blake3.blake3(data).digest()
+        got_bad = [c for c in range(nch) if res["pub"][int(res["step_off"][c + 1]) - 1, 2:10].tobytes() != digest]
+        assert got_bad == bad, (nch, got_bad)
+        other, _, _ = nova_chain_ref.chain_rows(data, not reference_siblings)
+        differs += other != rows
+    assert differs >= 4            # the two rules really feed different siblings on the imperfect trees ...
+    w.close()
+
+
+def test_reference_rule_equals_default_on_perfect_trees(built):
+    a = pkg.builder("blake3_nova", device=0)
+    b = pkg.builder("blake3_nova", device=0, reference_siblings=True)
+    for n in (1024, 2048, 4096, 8192, 16384):
+        data = synth(n)
+        ra, rb = a.novaChain(data), b.novaChain(data)
+        assert np.array_equal(ra["rows"], rb["rows"]) and ra["root"] == rb["root"] == blake3.blake3(data).digest()
+    a.close()
+    b.close()
+
+
+@pytest.mark.parametrize("name,variant", [("blake3_nova", "nova_bn_o2"), ("blake3_nova_pasta", "nova_pasta_o2")])
+def test_chain_device_form(built, name, variant):
+    """b3w_nova_chain_device: step witnesses left in device memory (one launch), what a prover on the same GPU consumes"""
+    import torch
+    w = pkg.builder(name, device=0)
+    data = synth(5000)
+    host = w.novaChain(data, want_witness=True)
+    ns, ws = host["total_steps"], w.witnessSize
+    d_out = torch.zeros(ns * ws * 32, dtype=torch.uint8, device="cuda")
+    d_st = torch.full((ns,), 255, dtype=torch.uint8, device="cuda")
+    d_pub = torch.zeros(ns * 15, dtype=torch.int32, device="cuda")
+    d_rows = torch.zeros(ns * 32, dtype=torch.int32, device="cuda")
+    res = w.novaChainDevice(data, d_out.data_ptr(), d_st.data_ptr(), d_pub.data_ptr(), d_rows.data_ptr())
+    torch.cuda.synchronize()
+    rows, off, finals = nova_chain_ref.chain_rows(data)
+    assert res["total_steps"] == len(rows) and list(res["step_off"]) == off and res["root"] == finals[0]
+    got_rows = d_rows.cpu().numpy().view(np.uint32).reshape(ns, 32)
+    assert np.array_equal(got_rows, np.array(rows, np.uint32))
+    want, _, st = port.witness_batch(variant, got_rows, nthreads=NCPU, want="both")
+    assert (st == 0).all() and int(d_st.max()) == 0
+    assert np.array_equal(d_out.cpu().numpy().reshape(ns, ws * 32), want)
+    assert np.array_equal(d_pub.cpu().numpy().view(np.uint32).reshape(ns, 15), host["pub"])
+    # without the optional buffers
+    d_out.zero_()
+    res2 = w.novaChainDevice(data, d_out.data_ptr())
+    assert res2["root"] == res["root"] and np.array_equal(d_out.cpu().numpy().reshape(ns, ws * 32), want)
+    t = w.lastTiming()
+    assert t["launches"] == 1 and t["instances"] == ns and t["d2h_bytes"] == 0
+    w.close()

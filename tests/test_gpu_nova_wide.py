@@ -137,13 +137,20 @@ def test_u32_batches_stay_on_the_hot_kernel_and_agree(built):
     wc.close()
 
 
-def test_fused_check_flag_is_refused_for_field_valued_batches(built):
+def test_fused_check_flag_covers_field_valued_instances(built):
+    """round 1 refused the fused-check flag for a batch with a field-valued instance; now the u32 instances get the fused
+    check and the field-valued ones the stand-alone evaluator on their finished witnesses (the built-in O2-form system)"""
     wc = pkg.builder("blake3_nova", device=0, fused_check=True)
-    rows = gen.splitmix_nova_inputs(4)
+    rows = gen.splitmix_nova_inputs(40)
     v = [[int(x) for x in r] for r in rows]
-    assert (wc.calculateWitnessBatchFr(v, want_witness=False)["status"] == 0).all()      # u32: hot kernel + fused check
-    v[1][0] = 2**40
-    with pytest.raises(pkg.B3WError) as e:
-        wc.calculateWitnessBatchFr(v, want_witness=False)
-    assert e.value.code == _lib.B3W_ERR_UNSUPPORTED
+    v[1][0] = 2**40                                                  # n_blocks: any field element is fine
+    v[2][13] = wc.prime - 5                                          # total_depth
+    v[3][12] = 2**40                                                 # leaf_depth - depth out of range: Assert Failed.
+    res = wc.calculateWitnessBatchFr(v, sums=True, first_bad=True)
+    want = [port.witness_fr("nova_bn_o2", [x % wc.prime for x in r]) for r in v]
+    assert list(res["status"]) == [rc for rc, _ in want] and res["status"][3] == 4
+    for i, (rc, w) in enumerate(want):
+        if rc == 0:
+            assert np.array_equal(res["witness"][i], w), i
+    assert (res["first_bad"] == _lib.B3W_NO_ROW).all()
     wc.close()

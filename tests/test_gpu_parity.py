@@ -209,7 +209,8 @@ def test_field_element_inputs_entry_point(wc):
 def test_compressible_output_buffer_and_ring(wc):
     n = 4096
     rows = gen.splitmix_compression_inputs(n, first=21)
-    want = wc.calculateWitnessBatch(rows)
+    w_o, _, _ = port.witness_batch("compression", rows, nthreads=NCPU, want="both")        # the checker is Oracle B, not another GPU run
+    want = {"witness": w_o, "pub": w_o.view(np.uint32).reshape(n, WS, 8)[:, 1:17, 0]}
     ptr, granted = wc.device_alloc(n * WS * 32, compressible=True)
     assert ptr and ptr % 32 == 0
     assert granted, "B200 grants CU_MEM_ALLOCATION_COMP_GENERIC"
