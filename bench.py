@@ -11,13 +11,22 @@ ranges, no collective on the data path (weak scaling; NCCL is used only for the 
 of the timings).
 
 Keys of the JSON line (rank 0):
-  value      whole-job witnesses/s, inputs resident in HBM, CUDA events on the launching stream, max over ranks
-  roofline   the witness kernel against the measured HBM peak (MEASURED_PEAKS.json); algorithmic bytes =
-             32*24093 written + 112 read per witness
+  value      whole-job witnesses/s, inputs resident in HBM, CUDA events on the launching stream, max over ranks; the
+             witnesses go to compressible device memory, the library's default (config.output_memory)
+  roofline   the HBM record: the same kernel into ORDINARY memory, timed per launch in this run, against the measured
+             HBM peak (MEASURED_PEAKS.json); algorithmic bytes = 32*24093 written + 112 read per witness
+  roofline_compressible  the timed region itself against its own bound, the SM-side store path (peak = the kernel's
+             store stream with no work, measured in this run into the same buffer)
+  value_sustained / value_checked  the timed launch for >= 1 s back to back / with the fused R1CS check
+  r1cs_check_resident  the stand-alone check of witnesses read back from HBM (all 24 544 rows)
   e2e        the same metric through the C ABI b3w_witness_batch() with HOST (pinned) buffers: H2D of the
              inputs and D2H of every witness byte + status + public outputs inside the timed region
   e2e_compact  ditto with out=NULL: witnesses only stream through the HBM ring, compact results come back
   e2e_packed   ditto with every witness returned in compact form (its 3 776-byte trace)
+  e2e_hybrid   every .wtns body in host memory like e2e, but packed records over PCIe + expansion on host threads
+  config4 / config5  BASELINE configs[3] / configs[4] through the C ABI, streamed, >= 1 s each (config 5: fused check,
+             per-instance witness checksums, a 1 024-instance sample of full witnesses verified against those checksums)
+  fr_batches   b3w_witness_batch_fr (Fr256 rows, all-u32 and 1 % field-valued) next to b3w_witness_batch (N = 1 only)
   cpu_baseline the reference's own wasm witness program (oracle/_ref, translated to C) on all host cores,
              bounded sample (rank 0, N=1 only)
 --impl reference times that CPU path as its own arm.
@@ -148,9 +157,12 @@ def run_reference(args, rank, world):
 # own arm
 # ------------------------------------------------------------------------------------------------------
 def run_own(args, rank, world, local_rank):
+    import ctypes as C
     import torch
     import torch.distributed as dist
     import hot_proofs_blake3_circom_b200 as pkg
+    from hot_proofs_blake3_circom_b200 import _lib
+    from hot_proofs_blake3_circom_b200 import inputs as gen
     from hot_proofs_blake3_circom_b200.inputs import lcg_compression_inputs
 
     if not torch.cuda.is_available():
@@ -170,6 +182,16 @@ def run_own(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def all_true(flag):
+        if world == 1:
+            return bool(flag)
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(int(t.item()))
+
+    L = pkg.lib()
+    ncpu = os.cpu_count() or 1
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
     n = 1 << LOG2_BATCH
     first = rank * n                                            # shard = contiguous index range
     wc = pkg.builder("blake3_compression", device=local_rank, chunk=2048)
@@ -178,30 +200,51 @@ def run_own(args, rank, world, local_rank):
     d_out = torch.empty(n * WIT_BYTES, dtype=torch.uint8, device="cuda")       # ordinary (cudaMalloc) memory
     d_st = torch.empty(n, dtype=torch.uint8, device="cuda")
     d_pub = torch.empty(n * 16, dtype=torch.int32, device="cuda")
+    d_bad = torch.empty(n, dtype=torch.int32, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
-    # The witnesses of the timed steps go to COMPRESSIBLE device memory (b3w_device_alloc: Blackwell's L2 compresses such
-    # lines on their way to HBM; a witness is mostly zero bytes).  Same bytes on read-back; the plain-memory rate is
-    # measured next to it.  --plain-output, or a device that does not grant compression, keeps ordinary memory.
-    out_ptr, compressible = d_out.data_ptr(), False
+    alg_bytes = n * (WIT_BYTES + IN_BYTES)
+
+    # The witnesses of the timed steps go where the library puts them by default: COMPRESSIBLE device memory
+    # (b3w_device_alloc; the default HBM ring of the host-buffer calls): Blackwell's L2 compresses such lines on their way to
+    # HBM and a witness is mostly zero bytes.  Same bytes on read-back (tests/test_gpu_compressible.py: every byte vs the
+    # oracles).  The HBM roofline record is measured on ordinary memory right after, same kernel, same batch.
+    out_c, compressible = None, False
     if not args.plain_output:
         try:
             p_c, granted = wc.device_alloc(n * WIT_BYTES, compressible=True)
             if granted:
-                out_ptr, compressible = p_c, True
+                out_c, compressible = p_c, True
             else:
                 wc.device_free(p_c)
         except pkg.B3WError:
             pass
+    agreed = all_true(compressible)                               # every rank takes the same path (collectives follow)
+    if compressible and not agreed:
+        wc.device_free(out_c)
+        out_c, compressible = None, False
+    out_ptr = out_c if compressible else d_out.data_ptr()
 
-    if world > 1:                                               # every rank takes the same path (collectives follow)
-        flag = torch.tensor([1 if compressible else 0], dtype=torch.int32, device="cuda")
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if compressible and int(flag.item()) == 0:
-            wc.device_free(out_ptr)
-            out_ptr, compressible = d_out.data_ptr(), False
+    def step(ptr=None, checked=False):
+        if checked:
+            wc.witness_batch_device_checked(d_in.data_ptr(), n, ptr or out_ptr, d_st.data_ptr(), d_pub.data_ptr(), d_bad.data_ptr(), stream)
+        else:
+            wc.witness_batch_device(d_in.data_ptr(), n, ptr or out_ptr, d_st.data_ptr(), d_pub.data_ptr(), stream)
 
-    def step(ptr=None):
-        wc.witness_batch_device(d_in.data_ptr(), n, ptr or out_ptr, d_st.data_ptr(), d_pub.data_ptr(), stream)
+    def timed_launches(count, warm=3, **kw):
+        """-> (total ms over `count` launches, mean ms per launch), CUDA events on the launching stream, max over ranks"""
+        for _ in range(warm):
+            step(**kw)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(count + 1)]
+        barrier()
+        torch.cuda.synchronize()
+        ev[0].record()
+        for k in range(count):
+            step(**kw)
+            ev[k + 1].record()
+        torch.cuda.synchronize()
+        barrier()
+        per = [ev[k].elapsed_time(ev[k + 1]) for k in range(count)]
+        return max_over_ranks(ev[0].elapsed_time(ev[-1])), max_over_ranks(sum(per) / len(per))
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -212,70 +255,84 @@ def run_own(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    barrier()
-    torch.cuda.synchronize()
-    ev[0].record()
-    for k in range(args.steps):
-        step()
-        ev[k + 1].record()
-    torch.cuda.synchronize()
-    barrier()
+    total_ms, kernel_ms = timed_launches(args.steps, warm=0)
     clocks = sampler.stop() if rank == 0 else None
-    total_ms = max_over_ranks(ev[0].elapsed_time(ev[-1]))
-    launch_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
-    kernel_ms = max_over_ranks(sum(launch_ms) / len(launch_ms))
     gpu_launches = world * args.steps                         # one witness kernel per step per rank
     assert int(d_st.max()) == 0
     pub0 = d_pub[:16].cpu().numpy().view(np.uint32)
+    # the timed buffer is looked at: per-instance checksums of the bytes in it == those of the same kernel's output in
+    # ordinary memory (identity of the two memory kinds; the oracle comparison of both is in tests/)
+    d_s1 = torch.empty(n, dtype=torch.int64, device="cuda")
+    d_s2 = torch.empty(n, dtype=torch.int64, device="cuda")
+    wc.checksum_device(out_ptr, n, d_s1.data_ptr(), stream)
+    step(d_out.data_ptr())
+    wc.checksum_device(d_out.data_ptr(), n, d_s2.data_ptr(), stream)
+    torch.cuda.synchronize()
+    assert torch.equal(d_s1, d_s2), "witness bytes differ between compressible and ordinary memory"
+    sums_xor = int(np.bitwise_xor.reduce(d_s1.cpu().numpy().view(np.uint64)))
+    del d_s1, d_s2
 
-    # --- the same kernel into ordinary memory (what every figure before r01j was measured on) -------
-    plain_ms = None
+    # --- sustained (>= 1 s of device time) and checked variants of the same launch ------------------
+    reps_1s = int(1100.0 / kernel_ms) + 1
+    sus_ms, _ = timed_launches(reps_1s, warm=1)
+    chk_total, chk_ms = timed_launches(reps_1s, warm=2, checked=True)
+    assert int(d_st.max()) == 0 and int(d_bad.min()) == -1                # B3W_NO_ROW everywhere
+    # --- the HBM roofline record: the same kernel into ordinary (cudaMalloc) memory -------------------
+    plain_total, plain_ms = (total_ms, kernel_ms)
+    chk_plain_ms = None
     if compressible:
-        for _ in range(3):
-            step(d_out.data_ptr())
-        torch.cuda.synchronize()
-        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        p0.record()
-        for _ in range(5):
-            step(d_out.data_ptr())
-        p1.record()
-        torch.cuda.synchronize()
-        plain_ms = max_over_ranks(p0.elapsed_time(p1) / 5)
-        wc.device_free(out_ptr)
+        plain_total, plain_ms = timed_launches(max(args.steps, 10), warm=3, ptr=d_out.data_ptr())
+        _, chk_plain_ms = timed_launches(10, warm=2, ptr=d_out.data_ptr(), checked=True)
 
-    # --- pure-store calibration on the same buffer (the write roofline of this very GPU) -----------
-    for _ in range(2):
-        wc.calib_fill(d_out.data_ptr(), n * WIT_BYTES, stream)
-    torch.cuda.synchronize()
-    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    c0.record()
-    for _ in range(5):
-        wc.calib_fill(d_out.data_ptr(), n * WIT_BYTES, stream)
-    c1.record()
-    torch.cuda.synchronize()
-    fill_gbs = 5 * n * WIT_BYTES / c0.elapsed_time(c1) / 1e6
-    for _ in range(2):
-        wc.calib_fill(d_out.data_ptr(), n * WIT_BYTES, stream, items=True)
-    torch.cuda.synchronize()
-    c0.record()
-    for _ in range(5):
-        wc.calib_fill(d_out.data_ptr(), n * WIT_BYTES, stream, items=True)
-    c1.record()
-    torch.cuda.synchronize()
-    fill_items_gbs = 5 * (n * WIT_BYTES // 32768 * 32768) / c0.elapsed_time(c1) / 1e6
+    # --- pure-store calibration (the write ceilings of this very GPU, same access shape) -------------
+    def fill_rate(ptr, items):
+        for _ in range(2):
+            wc.calib_fill(ptr, n * WIT_BYTES, stream, items=items)
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(5):
+            wc.calib_fill(ptr, n * WIT_BYTES, stream, items=items)
+        c1.record()
+        torch.cuda.synchronize()
+        nb = n * WIT_BYTES if not items else n * WIT_BYTES // 32768 * 32768
+        return 5 * nb / c0.elapsed_time(c1) / 1e6
+    fill_gbs = fill_rate(d_out.data_ptr(), False)
+    fill_items_gbs = fill_rate(d_out.data_ptr(), True)
+    fill_items_c_gbs = fill_rate(out_c, True) if compressible else None
+
+    # --- the stand-alone R1CS check of witnesses where they lie (reads HBM): 2^15 of the witnesses just written ---------
+    n_chk = 1 << 15
+    step(d_out.data_ptr())
+    if compressible:
+        step(out_c)
+
+    def check_rate(ptr):
+        for _ in range(2):
+            wc.r1cs_check_device(ptr, n_chk, d_st.data_ptr(), d_bad.data_ptr(), stream)
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(5):
+            wc.r1cs_check_device(ptr, n_chk, d_st.data_ptr(), d_bad.data_ptr(), stream)
+        c1.record()
+        torch.cuda.synchronize()
+        assert int(d_st[:n_chk].max()) == 0
+        return max_over_ranks(c0.elapsed_time(c1) / 5)
+    chk_hbm_ms = check_rate(d_out.data_ptr())
+    chk_hbm_c_ms = check_rate(out_c) if compressible else None
+    if compressible:
+        wc.device_free(out_c)
     del d_out
     torch.cuda.empty_cache()
 
-    # --- e2e: the C ABI host-buffer call (what the N-API addon / a user calls) ---------------------
-    L = pkg.lib()
+    # --- e2e: the C ABI host-buffer calls (what the N-API addon / a user calls) ---------------------
     avail = 0
     with open("/proc/meminfo") as f:
         for line in f:
             if line.startswith("MemAvailable"):
                 avail = int(line.split()[1]) * 1024
-    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
-    budget = int(avail * 0.5 / max(local_world, 1))
+    budget = int(avail * 0.4 / max(local_world, 1))
     n_e2e = n
     while n_e2e * WIT_BYTES > budget and n_e2e > 1024:
         n_e2e //= 2
@@ -285,66 +342,124 @@ def run_own(args, rank, world, local_rank):
     h_pub = L.b3w_host_alloc_near(n_e2e * 64, local_rank)
     if not (h_out and h_in and h_st and h_pub):
         raise SystemExit("bench.py: pinned host allocation failed: " + L.b3w_last_error().decode())
-    import ctypes as C
     C.memmove(h_in, rows.ctypes.data, n_e2e * IN_BYTES)
     e2e_steps = max(2, min(args.steps, 5))
 
-    def e2e_run(out_ptr, steps, calc=None):
-        from hot_proofs_blake3_circom_b200 import _lib
-        h = (calc or wc)._h
-        for _ in range(1):
-            _lib.check(L.b3w_witness_batch(h, h_in, n_e2e, out_ptr, h_st, h_pub))
+    def wall(call, steps, warm=1):
+        for _ in range(warm):
+            _lib.check(call())
         barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(steps):
-            _lib.check(L.b3w_witness_batch(h, h_in, n_e2e, out_ptr, h_st, h_pub))   # returns after the last D2H
+            _lib.check(call())                                   # returns after the last D2H / host store
         dt = time.perf_counter() - t0
         barrier()
         return max_over_ranks(dt) / steps
 
-    t_full = e2e_run(h_out, e2e_steps)
     got0 = np.ctypeslib.as_array(C.cast(h_out, C.POINTER(C.c_uint32)), shape=(WS * 8,))
+    t_full = wall(lambda: L.b3w_witness_batch(wc._h, h_in, n_e2e, h_out, h_st, h_pub), e2e_steps)
     assert got0[8] == pub0[0] and got0[0] == 1                  # slot 0 == 1, slot 1 == out[0]
-    t_compact = e2e_run(None, e2e_steps)
-    # the same two calls with the library's HBM ring in compressible memory (B3W_FLAG_COMPRESSIBLE_RING)
-    t_full_c = t_compact_c = None
-    if compressible:
-        wc_ring = pkg.builder("blake3_compression", device=local_rank, chunk=2048, compressible_ring=True)
-        t_compact_c = e2e_run(None, e2e_steps, wc_ring)
-        t_full_c = e2e_run(h_out, 2, wc_ring)
-        assert got0[8] == pub0[0] and got0[0] == 1
-        wc_ring.close()
+    t_compact = wall(lambda: L.b3w_witness_batch(wc._h, h_in, n_e2e, None, h_st, h_pub), e2e_steps)
+    # hybrid: the same host buffer filled with every .wtns body, but only packed records cross PCIe; host threads expand
+    got0[:] = 0
+    hy_threads = max(1, ncpu // max(local_world, 1))
+    t_hybrid = wall(lambda: L.b3w_witness_batch_hybrid(wc._h, h_in, n_e2e, h_out, h_st, h_pub, hy_threads), 2)
+    assert got0[8] == pub0[0] and got0[0] == 1
+    hy_t = wc.lastTiming()
     L.b3w_host_free(h_out)
     # ... and with the witnesses returned in COMPACT form (the per-instance trace, 3 776 B: every slot is a pure function
-    # of it; b3w_unpack_device expands on demand)
+    # of it; b3w_unpack_device / b3w_unpack_host expand on demand)
     pk_words = wc.packedWords
     h_pk = L.b3w_host_alloc_near(n_e2e * pk_words * 4, local_rank)
     if not h_pk:
         raise SystemExit("bench.py: pinned host allocation failed: " + L.b3w_last_error().decode())
-
-    def packed_run(steps):
-        from hot_proofs_blake3_circom_b200 import _lib
-        _lib.check(L.b3w_witness_batch_packed(wc._h, h_in, n_e2e, h_pk, h_st, h_pub))
-        barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            _lib.check(L.b3w_witness_batch_packed(wc._h, h_in, n_e2e, h_pk, h_st, h_pub))
-        dt = time.perf_counter() - t0
-        barrier()
-        return max_over_ranks(dt) / steps
-
-    t_packed = packed_run(e2e_steps)
+    t_packed = wall(lambda: L.b3w_witness_batch_packed(wc._h, h_in, n_e2e, h_pk, h_st, h_pub), e2e_steps)
     pk0 = np.ctypeslib.as_array(C.cast(h_pk, C.POINTER(C.c_uint32)), shape=(pk_words,))
     assert pk0[1] == 1 and pk0[30] == pub0[0]                   # trace word 1 = the constant 1, word 30 = out[0]
     for p in (h_pk, h_in, h_st, h_pub):
         L.b3w_host_free(p)
+    wc.close()
+
+    # --- BASELINE configs[3]: 2^20 blake3_nova_pasta steps, streamed through the HBM ring (whole job = 2^20: strong) ----
+    def streamed(name, rows_fn, n_total, fused, reps_target_s, n_samples, tag):
+        n_r = n_total // world
+        calc = pkg.builder(name, device=local_rank, chunk=16384, fused_check=fused)
+        r = gen.parallel_rows(rows_fn, n_r, first=rank * n_r, threads=max(2, ncpu // max(local_world, 1)))
+        hin = L.b3w_host_alloc_near(r.nbytes, local_rank)
+        C.memmove(hin, r.ctypes.data, r.nbytes)
+        del r
+        hst, hpub = L.b3w_host_alloc_near(n_r, local_rank), L.b3w_host_alloc_near(n_r * calc.nPublic * 4, local_rank)
+        hsum = L.b3w_host_alloc_near(n_r * 8, local_rank)
+        rng = np.random.default_rng(1234 + rank)
+        idx = np.unique(np.concatenate([[0, n_r - 1], rng.integers(0, n_r, n_samples - 2)])).astype(np.uint64) if n_samples else np.zeros(0, np.uint64)
+        smp = np.zeros((idx.size, calc.witnessSize * 32), np.uint8)
+        ex = _lib.BatchExtras()
+        ex.sums = hsum
+        if idx.size:
+            ex.sample_idx, ex.n_samples, ex.sample_out = idx.ctypes.data, idx.size, smp.ctypes.data
+        call = lambda: L.b3w_witness_batch_ex(calc._h, hin, n_r, None, hst, hpub, C.byref(ex))
+        t1 = wall(call, 1, warm=1)
+        reps = max(1, int(reps_target_s / t1 + 0.999))
+        dt = wall(call, reps, warm=0)
+        st = np.ctypeslib.as_array(C.cast(hst, C.POINTER(C.c_uint8)), shape=(n_r,))
+        sums = np.ctypeslib.as_array(C.cast(hsum, C.POINTER(C.c_uint64)), shape=(n_r,))
+        assert not st.any(), "%s: status != 0" % tag
+        # every sampled witness, copied out of the ring, has the checksum the kernel reported for it
+        ok = bool(np.array_equal(gen.witness_checksums(smp, calc.witnessSize), sums[idx.astype(np.int64)])) if idx.size else None
+        assert ok is not False, "%s: sample checksums differ" % tag
+        tm = calc.lastTiming()
+        res = {"value": n_total / dt, "unit": "witnesses/s", "seconds_per_pass": dt, "passes_timed": reps, "instances": n_total,
+               "instances_per_gpu": n_r, "witness_bytes": calc.witnessSize * 32, "generated_GB_per_pass": n_total * calc.witnessSize * 32 / 1e9,
+               "ring_write_GBps_per_gpu": n_r * calc.witnessSize * 32 / dt / 1e9, "fused_check": fused,
+               "kernel_ms_last_pass": tm["kernel_ms"], "d2h_bytes_per_pass_per_gpu": tm["d2h_bytes"],
+               "sums_xor_rank0": int(np.bitwise_xor.reduce(sums)), "samples_per_gpu": int(idx.size), "samples_match_their_sums": ok}
+        for p in (hin, hst, hpub, hsum):
+            L.b3w_host_free(p)
+        calc.close()
+        return res
+    cfg4 = streamed("blake3_nova_pasta", gen.splitmix_nova_inputs, 1 << 20, False, 1.0, 0, "config4")
+    cfg4["api"] = ("b3w_witness_batch_ex(out=NULL, sums): BASELINE configs[3], 2^20 blake3_nova_pasta (Pallas Fr) step witnesses streamed "
+                   "through the HBM ring; status + z_{i+1} + checksums D2H")
+    # --- BASELINE configs[4]: 2^24 blake3_compression instances over the N GPUs (2^24 / N each), fused R1CS check ------
+    cfg5 = streamed("blake3_compression", gen.splitmix_compression_inputs, 1 << args.log2_config5, True, 1.0, 1024 // world, "config5")
+    cfg5["api"] = ("b3w_witness_batch_ex(out=NULL, sums, %d samples per GPU) on a context with B3W_FLAG_FUSED_CHECK: BASELINE configs[4], "
+                   "contiguous index ranges, no collective; per instance status + out[16] + a 64-bit witness checksum come back, plus the "
+                   "full witnesses of the sample" % (1024 // world))
+
+    # --- field-element rows (b3w_witness_batch_fr) next to u32 rows: 2^20 blake3_nova_pasta, N = 1 only ------------------
+    fr_line = None
+    if world == 1 and not args.no_fr:
+        n_f = 1 << 20
+        calc = pkg.builder("blake3_nova_pasta", device=local_rank, chunk=16384)
+        r = gen.parallel_rows(gen.splitmix_nova_inputs, n_f, threads=ncpu)
+        hin = L.b3w_host_alloc(r.nbytes)
+        C.memmove(hin, r.ctypes.data, r.nbytes)
+        hfr = L.b3w_host_alloc(n_f * 1024)
+        fr = np.ctypeslib.as_array(C.cast(hfr, C.POINTER(C.c_uint8)), shape=(n_f, 32, 32))
+        fr[:] = 0
+        fr[:, :, 0:4] = r.view(np.uint8).reshape(n_f, 32, 4)
+        hst, hpub = L.b3w_host_alloc(n_f), L.b3w_host_alloc(n_f * 60)
+        t_u32 = wall(lambda: L.b3w_witness_batch(calc._h, hin, n_f, None, hst, hpub), 3)
+        t_fr = wall(lambda: L.b3w_witness_batch_fr(calc._h, hfr, n_f, None, hst, hpub), 3)
+        p = calc.prime
+        for i in range(50, n_f, 100):                                # 1 %: n_blocks becomes a genuine field element
+            fr[i, 0] = np.frombuffer(((p - 1 - i) % p).to_bytes(32, "little"), np.uint8)
+        t_mix = wall(lambda: L.b3w_witness_batch_fr(calc._h, hfr, n_f, None, hst, hpub), 3)
+        st = np.ctypeslib.as_array(C.cast(hst, C.POINTER(C.c_uint8)), shape=(n_f,))
+        assert not st.any()
+        fr_line = {"unit": "witnesses/s", "instances": n_f, "circuit": "blake3_nova_pasta", "u32_rows_b3w_witness_batch": n_f / t_u32,
+                   "fr_rows_all_u32_b3w_witness_batch_fr": n_f / t_fr, "fr_rows_1pct_field_valued": n_f / t_mix,
+                   "h2d_bytes_u32": n_f * 128, "h2d_bytes_fr": n_f * 1024,
+                   "note": "host pinned rows in, out=NULL; Fr256 rows are converted on the device, the 1 % field-valued instances run on the "
+                           "general kernel into the same ring slots"}
+        for q in (hin, hfr, hst, hpub):
+            L.b3w_host_free(q)
+        calc.close()
 
     # --- cpu baseline (rank 0, N=1 only): bounded sample on all host cores -------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ncpu = os.cpu_count() or 1
         cpu_reference_rate(ncpu, ncpu)                          # warm-up, discarded
         n_s = 6 * ncpu
         rate, secs, kind = cpu_reference_rate(n_s, ncpu, first=ncpu)
@@ -353,16 +468,21 @@ def run_own(args, rank, world, local_rank):
                          "and read-out, %.1f s wall; reference wasm translated to C (no V8 here)" % (n_s, ncpu, secs)}
 
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
     peak, peak_src = measured_peaks()
-    alg_bytes = n * (WIT_BYTES + IN_BYTES)
-    achieved = alg_bytes / kernel_ms / 1e6
-    traffic = None
+    traffic, traffic_c = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         with open(tp) as f:
-            traffic = json.load(f).get("k_blake3_comp_witness_dram_bytes_per_launch" + ("_compressible" if compressible else ""))
+            tj = json.load(f)
+        traffic = tj.get("k_blake3_comp_witness_dram_bytes_per_launch")
+        traffic_c = tj.get("k_blake3_comp_witness_dram_bytes_per_launch_compressible")
+    mem_kind = ("compressible device memory (b3w_device_alloc, CU_MEM_ALLOCATION_COMP_GENERIC; the library's default ring): the L2 compresses "
+                "witness lines on their way to HBM; identical bytes on read-back") if compressible else "ordinary device memory (cudaMalloc)"
     value = world * n * args.steps / (total_ms / 1e3)
+    achieved_plain = alg_bytes / plain_ms / 1e6
     line = {
         "metric": METRIC, "value": value, "unit": "witnesses/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -370,19 +490,17 @@ def run_own(args, rank, world, local_rank):
         "config": {"workload": WORKLOAD, "instances_per_gpu": n, "witness_bytes": WIT_BYTES,
                    "hbm_out_bytes_per_gpu": n * WIT_BYTES, "l2": "each step writes 50.5 GB per GPU, >> 126 MB L2",
                    "sharding": "contiguous index ranges, no collective", "out0_instance0": int(pub0[0]),
-                   "output_memory": "compressible device memory (b3w_device_alloc, CU_MEM_ALLOCATION_COMP_GENERIC): the L2 compresses "
-                                    "witness lines on their way to HBM; identical bytes on read-back" if compressible
-                                    else "ordinary device memory (cudaMalloc)"},
-        "roofline": {"bound": "hbm", "kernel": "k_blake3_comp_witness", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src + " (of measured)"
-                     if "MEASURED" in peak_src else peak_src + " (of fallback)",
-                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms,
-                     "pure_store_fill_gbs_same_gpu": fill_gbs,
-                     "pure_store_same_stream_shape_gbs": fill_items_gbs, "frac_of_spec_8TBps": achieved / 8000.0,
-                     "note": ("witness bytes per second INTO COMPRESSIBLE memory: the HBM interface moves fewer bytes than the "
-                              "kernel writes (traffic = ncu dram bytes per launch), so achieved can exceed the interface's peak; "
-                              "achieved_plain_memory is the same kernel into cudaMalloc memory") if compressible else None,
-                     "achieved_plain_memory": (alg_bytes / plain_ms / 1e6) if plain_ms else None},
+                   "output_memory": mem_kind, "witness_checksums_xor_rank0": sums_xor},
+        # the HBM record: the witness kernel into ORDINARY memory, where every algorithmic byte crosses the HBM interface
+        "roofline": {"bound": "hbm", "kernel": "k_blake3_comp_witness", "achieved": achieved_plain, "peak": peak,
+                     "unit": "GB/s", "frac": achieved_plain / peak, "traffic": traffic,
+                     "traffic_source": "profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture "
+                                       "of this kernel on ordinary memory (committed profile); NOT measured in this run",
+                     "peak_source": peak_src + (" (of measured)" if "MEASURED" in peak_src else " (of fallback)"),
+                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": plain_ms, "launches_timed": max(args.steps, 10),
+                     "measured_on": "ordinary (cudaMalloc) output, same kernel and batch as the timed region, CUDA events per launch in this run",
+                     "frac_of_spec_8TBps": achieved_plain / 8000.0, "pure_store_fill_gbs_same_gpu": fill_gbs,
+                     "pure_store_same_stream_shape_gbs": fill_items_gbs, "frac_of_pure_store_same_shape": achieved_plain / fill_items_gbs},
         "e2e": {"value": world * n_e2e / t_full, "unit": "witnesses/s", "h2d_bytes_per_step": n_e2e * IN_BYTES,
                 "d2h_bytes_per_step": n_e2e * (WIT_BYTES + 1 + 64), "instances_per_step_per_gpu": n_e2e,
                 "ms_per_step": 1e3 * t_full, "d2h_gbs_per_gpu": n_e2e * WIT_BYTES / t_full / 1e9,
@@ -390,16 +508,40 @@ def run_own(args, rank, world, local_rank):
         "e2e_compact": {"value": world * n_e2e / t_compact, "unit": "witnesses/s", "h2d_bytes_per_step": n_e2e * IN_BYTES,
                         "d2h_bytes_per_step": n_e2e * (1 + 64), "ms_per_step": 1e3 * t_compact,
                         "api": "b3w_witness_batch(out=NULL): witnesses stream through the HBM ring, status + out[16] return"},
-        "e2e_compressible_ring": None if t_compact_c is None else {
-            "full_copy": world * n_e2e / t_full_c, "compact": world * n_e2e / t_compact_c, "unit": "witnesses/s",
-            "api": "the two calls above on a context created with B3W_FLAG_COMPRESSIBLE_RING"},
         "e2e_packed": {"value": world * n_e2e / t_packed, "unit": "witnesses/s", "h2d_bytes_per_step": n_e2e * IN_BYTES,
                        "d2h_bytes_per_step": n_e2e * (pk_words * 4 + 1 + 64), "ms_per_step": 1e3 * t_packed,
                        "api": "b3w_witness_batch_packed(host pinned in/out): every witness returned in compact form "
-                              "(%d B trace per instance; expandable to the .wtns body with b3w_unpack_device)" % (pk_words * 4)},
+                              "(%d B trace per instance; expandable to the .wtns body with b3w_unpack_device / b3w_unpack_host)" % (pk_words * 4)},
+        "e2e_hybrid": {"value": world * n_e2e / t_hybrid, "unit": "witnesses/s", "h2d_bytes_per_step": n_e2e * IN_BYTES,
+                       "d2h_bytes_per_step": n_e2e * (pk_words * 4 + 1 + 64), "ms_per_step": 1e3 * t_hybrid, "host_threads_per_gpu": hy_threads,
+                       "host_unpack_ms_per_step": hy_t["host_ms"], "host_store_gbs_per_gpu": n_e2e * WIT_BYTES / t_hybrid / 1e9,
+                       "api": "b3w_witness_batch_hybrid: every .wtns body in the caller's host buffer like e2e, but only the packed records cross "
+                              "PCIe; the expansion runs on host threads (non-temporal stores)"},
+        "value_sustained": {"value": world * n * reps_1s / (sus_ms / 1e3), "unit": "witnesses/s", "launches": reps_1s, "device_seconds": sus_ms / 1e3,
+                            "note": "the timed region's launch repeated back to back for >= 1 s"},
+        "value_checked": {"value": world * n / (chk_ms / 1e3), "unit": "witnesses/s", "kernel": "k_blake3_comp_witness<CHECK> (fused R1CS check)",
+                          "kernel_ms": chk_ms, "launches": reps_1s, "device_seconds": chk_total / 1e3, "output_memory": "as the timed region",
+                          "value_plain_memory": world * n / (chk_plain_ms / 1e3) if chk_plain_ms else None},
+        "r1cs_check_resident": {"kernel": "k_r1cs_check_fast (b3w_r1cs_check_device): all 24 544 rows on witnesses read back from HBM",
+                                "instances": n_chk, "value": world * n_chk / (chk_hbm_ms / 1e3), "unit": "witnesses/s", "kernel_ms": chk_hbm_ms,
+                                "read_gbs": n_chk * WIT_BYTES / chk_hbm_ms / 1e6, "frac_of_measured_hbm_peak": n_chk * WIT_BYTES / chk_hbm_ms / 1e6 / peak,
+                                "compressible_buffer": None if chk_hbm_c_ms is None else {
+                                    "value": world * n_chk / (chk_hbm_c_ms / 1e3), "kernel_ms": chk_hbm_c_ms, "read_gbs": n_chk * WIT_BYTES / chk_hbm_c_ms / 1e6}},
+        "config4": cfg4, "config5": cfg5,
         "gpu_launches": gpu_launches, "clocks": clocks}
-    if plain_ms:
+    if compressible:
+        achieved_c = alg_bytes / kernel_ms / 1e6
+        line["roofline_compressible"] = {
+            "bound": "sm-store-path", "kernel": "k_blake3_comp_witness", "achieved": achieved_c, "peak": fill_items_c_gbs, "unit": "GB/s",
+            "frac": achieved_c / fill_items_c_gbs, "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
+            "peak_source": "k_fill_items into the same compressible buffer, measured in this run: the witness kernels' store stream "
+                           "(same items, same grid, 1 KiB warp stores) with none of their work",
+            "traffic": traffic_c, "traffic_source": "profiles/traffic.json (ncu capture on compressible memory, committed); NOT measured in this run",
+            "note": "the timed region: witness bytes per second INTO COMPRESSIBLE memory.  The HBM interface carries about a third of them "
+                    "(traffic), so this is not an HBM fraction: the SM-side store path is what bounds it"}
         line["value_plain_memory"] = world * n / (plain_ms / 1e3)
+    if fr_line:
+        line["fr_batches"] = fr_line
     if cpu:
         line["cpu_baseline"] = cpu
     print_json(json.dumps(line))
@@ -415,6 +557,8 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--plain-output", action="store_true", help="timed steps write ordinary (cudaMalloc) memory")
+    ap.add_argument("--no-fr", action="store_true", help="skip the field-element-row comparison (N = 1 only)")
+    ap.add_argument("--log2-config5", type=int, default=24, help="log2 of config 5's whole-job instance count")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -769,7 +769,12 @@ static int launch_witness(b3w_ctx *c, const uint32_t *d_in, uint64_t n, uint8_t 
   sck.part_len = 0;
   if (o.d_sums) CK(cudaMemsetAsync(o.d_sums, 0, n * sizeof(unsigned long long), s));
   const bool sums = o.d_sums != nullptr;
-  if (c->def->nova) {
+  if (c->store_mode == 1 && !c->def->nova && !check && !o.d_m_ext && !sums) {
+    // experiment: shared-memory tiles + TMA bulk stores (kernels_witness.cuh, k_blake3_comp_witness_tma)
+    const int smem = WARPS_PER_CTA * TMA_NBUF * TMA_TILE_BYTES;
+    CK(cudaFuncSetAttribute(k_blake3_comp_witness_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k_blake3_comp_witness_tma<<<grid, WARPS_PER_CTA * 32, smem, s>>>(d_in, n, c->d_desc, c->def->ws, d_out, d_status, d_pub, sc);
+  } else if (c->def->nova) {
     if (check) { if (sums) launch_nova<true, true>(c, grid, bs, s, d_in, n, d_out, d_status, d_pub, ck, sc, sck); else launch_nova<true, false>(c, grid, bs, s, d_in, n, d_out, d_status, d_pub, ck, sc, sck); }
     else { if (sums) launch_nova<false, true>(c, grid, bs, s, d_in, n, d_out, d_status, d_pub, ck, sc, sck); else launch_nova<false, false>(c, grid, bs, s, d_in, n, d_out, d_status, d_pub, ck, sc, sck); }
   } else {

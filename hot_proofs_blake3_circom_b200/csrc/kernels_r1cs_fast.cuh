@@ -139,6 +139,14 @@ __device__ __forceinline__ fr_t fp_coef_fr(long long coef, uint32_t shift, const
   return coef < 0 ? fr_neg(r, p) : r;
 }
 
+// acc += (coef << shift) * v in Fr; unit coefficients (most rows that end up here: IsZero's in * inv = 1 - out) cost no product
+__device__ __forceinline__ fr_t fp_acc_fr(const fr_t &acc, long long coef, uint32_t shift, const fr_t &v, const field_consts &F) {
+  if (shift == 0 && coef == 1) return fr_add(acc, v, F.p);
+  if (shift == 0 && coef == -1) return fr_add(acc, fr_neg(v, F.p), F.p);
+  const fr_t co = fp_coef_fr(coef, shift, F.p);
+  return fr_add(acc, fr_montmul(fr_montmul(co, F.r2, F.p, F.n0), v, F.p, F.n0), F.p);
+}
+
 // exact evaluation of one compiled row in Fr (slow path)
 __device__ __noinline__ bool fp_row_fr(const CompactSrc &src, const fp_item *__restrict__ items, uint32_t item_off, uint32_t lane,
                                        uint32_t nA, uint32_t nB, uint32_t nC) {
@@ -152,12 +160,13 @@ __device__ __noinline__ bool fp_row_fr(const CompactSrc &src, const fp_item *__r
       const fp_item it = items[item_off + k * 32u + lane];
       const uint32_t len = it.meta & 63u, shift = (it.meta >> 8) & 255u;
       if (it.coef == 0) continue;
-      const uint32_t cnt = len ? len : 1u;
-      for (uint32_t e = 0; e < cnt; e++) {                    // a run is taken wire by wire here: its slots may hold anything
-        const fr_t v = src.field(it.wire + e);
-        const fr_t co = fp_coef_fr(it.coef, shift + e, F.p);
-        acc = fr_add(acc, fr_montmul(fr_montmul(co, F.r2, F.p, F.n0), v, F.p, F.n0), F.p);
+      if (len && src.run_is_bits(it.wire, len)) {               // a run over bits is one value
+        acc = fp_acc_fr(acc, it.coef, shift, fr_from_u64(src.run_value(it.wire, len)), F);
+        continue;
       }
+      const uint32_t cnt = len ? len : 1u;
+      for (uint32_t e = 0; e < cnt; e++)                        // else wire by wire: its slots may hold anything
+        acc = fp_acc_fr(acc, it.coef, shift + e, src.field(it.wire + e), F);
     }
     L[part] = acc;
   }
@@ -191,6 +200,8 @@ __device__ __noinline__ bool fp_bool_fr(const CompactSrc &src, uint32_t x) {
 }
 
 // one tile: lane = row.  Returns the lane's violated row id or B3W_NO_ROW.
+// A term (coef * v) << shift whose bit-length bound stays <= 54 goes into a 64-bit accumulator (<= 255 of them stay below
+// 2^62); the others -- 2^32.. coefficients on wide values, Num2Bits(65)'s top run -- into a 128-bit one.
 __device__ __forceinline__ uint32_t fp_eval_tile(const CompactSrc &src, const fastprog_dev &P, const fp_tile t, uint32_t lane) {
   const bool active = lane < t.rows;
   const fp_item *__restrict__ it0 = P.items + t.item_off + lane;
@@ -200,7 +211,8 @@ __device__ __forceinline__ uint32_t fp_eval_tile(const CompactSrc &src, const fa
   const uint32_t n[3] = {t.nA, t.nB, t.nC};
 #pragma unroll
   for (int part = 0; part < 3; part++) {
-    i128 acc = 0;
+    long long acc64 = 0;
+    i128 acc128 = 0;
     for (uint32_t j = 0; j < n[part]; j++, k++) {
       const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(it0 + k * 32u));
       const uint32_t wire = raw.x, meta = raw.y, len = meta & 63u, shift = (meta >> 8) & 255u, cbits = (meta >> 16) & 255u;
@@ -210,7 +222,7 @@ __device__ __forceinline__ uint32_t fp_eval_tile(const CompactSrc &src, const fa
       if (len) {
         undecided = undecided || !src.run_is_bits(wire, len);
         v = (long long)src.run_value(wire, len);
-        vbits = 32;
+        vbits = (int)len;
       } else {
         const uint64_t x = src.get(wire);
         undecided = undecided || (x & STG_TAG_BIG) != 0;
@@ -218,10 +230,15 @@ __device__ __forceinline__ uint32_t fp_eval_tile(const CompactSrc &src, const fa
         v = (x & STG_TAG_NEG) ? -(long long)mag : (long long)mag;
         vbits = fp_bitlen64(mag);
       }
-      undecided = undecided || (int)cbits + vbits > 118;      // <= 255 items of < 2^118 each stay below 2^126
-      acc += ((i128)coef * (i128)v) << shift;
+      const int bits = (int)cbits + vbits;
+      if (bits <= 54) {
+        acc64 += (coef * v) << shift;
+      } else {
+        undecided = undecided || bits > 118;                    // <= 255 items of < 2^118 each stay below 2^126
+        acc128 += ((i128)coef * (i128)v) << shift;
+      }
     }
-    L[part] = acc;
+    L[part] = acc128 + (i128)acc64;
   }
   if (!active) return B3W_NO_ROW;
   bool holds;

@@ -509,6 +509,76 @@ k_blake3_comp_witness(const uint32_t *__restrict__ in, uint64_t n, const uint32_
   }
 }
 
+// ---- experiment (b3w_debug_set_store_mode(ctx, 1)): expanded tiles staged in shared memory, written by the TMA engine -------
+// What BASELINE's north_star sketches ("stage each instance's witness in shared memory and write it back with ... TMA bulk
+// stores").  Each warp expands 128 slots (4 KiB) at a time into one of TMA_NBUF private shared-memory tiles and one elected
+// lane hands the tile to the TMA engine (cp.async.bulk.global.shared::cta, SASS UBLKCP); the next tile is expanded while
+// that copy drains.  The two 16-byte halves of a slot are written in an order that keeps the shared-memory stores free of
+// bank conflicts (lanes 0-3 / 4-7 of every quarter-warp start with opposite halves).  blake3_compression, plain u32 inputs
+// only: a nova witness has field slots that a second generic-proxy store would race the async-proxy copy for.
+// Measured against the direct 256-bit stores in profiles/r02_store_mode.jsonl; the default stays whichever is faster there.
+#define TMA_TILE_SLOTS 128u
+#define TMA_TILE_BYTES (TMA_TILE_SLOTS * 32u)
+#define TMA_NBUF 2
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2)
+k_blake3_comp_witness_tma(const uint32_t *__restrict__ in, uint64_t n, const uint32_t *__restrict__ desc, uint32_t ws,
+                          uint8_t *__restrict__ out, uint8_t *__restrict__ status, uint32_t *__restrict__ pub, const sched_args sc) {
+  __shared__ __align__(16) uint32_t s_trace[WARPS_PER_CTA][TRACE_STRIDE];
+  extern __shared__ __align__(128) uint8_t s_tiles[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  uint32_t *trace = s_trace[wib];
+  uint8_t *tiles = s_tiles + (size_t)wib * TMA_NBUF * TMA_TILE_BYTES;
+  if (lane == 0) { trace[TR_ZERO] = 0u; trace[TR_ONE] = 1u; }
+  const lane_sched ls = load_lane_sched(lane);
+  const bool flip = (lane >> 2) & 1;               // which half of its slot this lane writes first
+  uint32_t buf = 0;
+  for (item_pipe<28> pipe(sc, in, n, lane, (uint64_t)blockIdx.x * WARPS_PER_CTA + wib); pipe.valid();) {
+    const uint64_t i = pipe.inst();
+    const uint32_t part = pipe.part();
+    const uint32_t a = part * sc.part_len, b = a + sc.part_len < ws ? a + sc.part_len : ws;
+    __syncwarp();
+    if (lane < 28) trace[TR_IN + lane] = pipe.cur_in;
+    pipe.advance();
+    __syncwarp();
+    compression_trace(trace, lane, ls);
+    __syncwarp();
+    if (part == 0) {
+      if (pub && lane < 16) pub[i * 16 + lane] = trace[TR_OUT + lane];
+      if (status && lane == 0) status[i] = 0;
+    }
+    uint8_t *dst = out + i * (uint64_t)ws * 32;
+    for (uint32_t s0 = a; s0 < b; s0 += TMA_TILE_SLOTS) {
+      const uint32_t cnt = min(TMA_TILE_SLOTS, b - s0);
+      // the copy that read this buffer TMA_NBUF tiles ago has finished reading it
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(TMA_NBUF - 1) : "memory");
+      __syncwarp();
+      uint8_t *tile = tiles + (size_t)buf * TMA_TILE_BYTES;
+#pragma unroll 4
+      for (uint32_t s = s0 + lane; s < s0 + cnt; s += 32) {
+        const uint32_t dsc = __ldg(desc + s);
+        const uint32_t t = dsc & 0xFFFFu, k = (dsc >> 16) & 31u, kind = dsc >> 24;
+        const uint32_t w = trace[t];
+        const uint32_t lo = kind == DK_BIT ? ((w >> k) & 1u) : w;
+        const uint32_t hi = kind == DK_W64 ? trace[t + 1] : 0u;
+        uint4 *p = reinterpret_cast<uint4 *>(tile + (size_t)(s - s0) * 32);
+        const uint4 h0 = make_uint4(lo, hi, 0u, 0u), h1 = make_uint4(0u, 0u, 0u, 0u);
+        p[flip ? 1 : 0] = flip ? h1 : h0;
+        p[flip ? 0 : 1] = flip ? h0 : h1;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // this thread's tile writes -> visible to the TMA engine
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + (size_t)s0 * 32),
+                     "r"((uint32_t)__cvta_generic_to_shared(tile)), "r"(cnt * 32u)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      buf = (buf + 1) % TMA_NBUF;
+    }
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the tiles stay valid until the engine is done with them
+}
+
 // The 15 outputs z_{i+1} of a nova step, one per lane < 15: n_blocks_out, block_count_out, h_out[8], total_depth_out,
 // depth_out, chunk_idx_low/high_out, leaf_depth_out (circuits/blake3_nova.circom:195-202).
 __device__ __forceinline__ uint32_t nova_public_output(const uint32_t *trace, int lane) {

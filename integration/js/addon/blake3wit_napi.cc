@@ -4,6 +4,11 @@
 //                                                  libraries: [-L<repo>/hot_proofs_blake3_circom_b200 -lblake3wit] }
 // Every compute call runs in napi_async_work so that `await` keeps the event loop free, as the async methods of the
 // reference's WitnessCalculator promise (witness_calculator.js:171,190,208).
+// Thread safety: libuv runs the work items of overlapping awaits (Promise.all over one calculator) on several worker
+// threads at once.  A b3w_ctx takes one host-buffer call at a time and SERIALISES concurrent callers itself (an internal
+// lock held for the whole call, include/blake3wit.h "Ownership / threading"), so two jobs on one calculator run one
+// after the other and never see each other's ring slots -- like the reference's wasm calculator, which runs each call to
+// completion on the JS thread.  tests/test_gpu_extras.py::test_one_context_serialises_concurrent_callers pins it.
 #include <node_api.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -26,8 +31,9 @@ static napi_value Create(napi_env env, napi_callback_info info) {
   uint32_t circuit; int32_t device;
   NAPI_OK(napi_get_value_uint32(env, argv[0], &circuit));
   NAPI_OK(napi_get_value_int32(env, argv[1], &device));
-  // the HBM ring of the host-buffer calls in compressible memory where the GPU offers it (falls back by itself)
-  b3w_config cfg = {circuit, device, 0, B3W_FLAG_COMPRESSIBLE_RING};
+  // flags 0 = the library's one default everywhere: the HBM ring of the host-buffer calls is compressible memory where the
+  // GPU offers it and silently ordinary memory otherwise (B3W_FLAG_PLAIN_RING opts out)
+  b3w_config cfg = {circuit, device, 0, 0};
   b3w_ctx *ctx = NULL;
   int rc = b3w_create(&cfg, &ctx);
   if (rc) return throw_b3w(env, rc);

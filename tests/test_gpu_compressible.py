@@ -111,3 +111,27 @@ def test_plain_ring_flag_gives_the_same_bytes(built, oracle_cache):
     wc = pkg.builder("blake3_compression", device=0, chunk=512, compressible_ring=False)
     assert np.array_equal(wc.calculateWitnessBatch(rows)["witness"], want)
     wc.close()
+
+
+def test_tma_store_mode_gives_the_same_bytes(built, oracle_cache):
+    """b3w_debug_set_store_mode(1): expanded tiles staged in shared memory and written by the TMA engine (the store path
+    BASELINE's north_star sketches; an experiment switch, see profiles/r02_store_mode.jsonl) -- every byte vs Oracle B"""
+    rows = rows_for("compression", N, 31)
+    want, _, _ = oracle(oracle_cache, "compression", rows)
+    wc = pkg.builder("blake3_compression", device=0)
+    ws = wc.witnessSize
+    wc.set_store_mode(1)
+    d_in = torch.from_numpy(rows.view(np.int32)).cuda()
+    d_st = torch.full((N,), 255, dtype=torch.uint8, device="cuda")
+    d_pub = torch.zeros(N * 16, dtype=torch.int32, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    for compressible in (False, True):
+        for parts in (0, 7):                                      # 7 items per witness: ragged tile tails
+            wc.set_launch(0, parts)
+            ptr, granted = wc.device_alloc(N * ws * 32, compressible=compressible)
+            wc.witness_batch_device(d_in.data_ptr(), N, ptr, d_st.data_ptr(), d_pub.data_ptr(), s)
+            torch.cuda.synchronize()
+            assert int(d_st.max()) == 0
+            assert np.array_equal(d2h(ptr, N * ws * 32).reshape(N, ws * 32), want), (compressible, parts)
+            wc.device_free(ptr)
+    wc.close()

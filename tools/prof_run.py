@@ -1,5 +1,6 @@
 """prof_run.py -- minimal driver for ncu captures of the witness kernel (no timing claims).
-usage: python tools/prof_run.py [log2_n] [launches] [circuit] [checked|plain] [compressible]"""
+usage: python tools/prof_run.py [log2_n] [launches] [circuit] [checked|plain|r1cs] [compressible]
+`r1cs`: one witness launch, then `launches` launches of the stand-alone checker k_r1cs_check_fast on those witnesses."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -29,6 +30,14 @@ else:
 d_st = torch.empty(n, dtype=torch.uint8, device="cuda")
 d_pub = torch.empty(n * wc.nPublic, dtype=torch.int32, device="cuda")
 s = torch.cuda.current_stream().cuda_stream
+if len(sys.argv) > 4 and sys.argv[4] == "r1cs":
+    wc.witness_batch_device(d_in.data_ptr(), n, out_ptr, d_st.data_ptr(), d_pub.data_ptr(), s)
+    d_bad = torch.empty(n, dtype=torch.int32, device="cuda")
+    for _ in range(launches):
+        wc.r1cs_check_device(out_ptr, n, d_st.data_ptr(), d_bad.data_ptr(), s)
+    torch.cuda.synchronize()
+    assert int(d_st.max()) == 0
+    launches = 0
 for _ in range(launches):
     if checked:
         wc.witness_batch_device_checked(d_in.data_ptr(), n, out_ptr, d_st.data_ptr(), d_pub.data_ptr(), 0, s)
