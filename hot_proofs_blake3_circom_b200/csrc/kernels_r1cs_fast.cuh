@@ -29,7 +29,12 @@
 #define FPK_EXP 0                 /* experiment builds only: 1 = stream + classify, no rows */
 #endif
 #define FPK_THREADS 256
+#ifndef FPK_CTAS_PER_SM
 #define FPK_CTAS_PER_SM 4
+#endif
+#ifndef FPK_INFLIGHT
+#define FPK_INFLIGHT 4            /* 256-bit loads per lane in flight in the streaming loop */
+#endif
 #define FPK_SIDE_MAX 1536u        /* non-bit slots per witness in the side table (compression 713, nova O1 ~1 250) */
 
 struct fp_item {                  // 16 bytes
@@ -65,6 +70,16 @@ __device__ __forceinline__ uint64_t cpt_classify(const uint32_t x[8], uint32_t s
   if (!borrow && (d.l[2] | d.l[3] | d.l[4] | d.l[5] | d.l[6] | d.l[7]) == 0 && (d.l[1] >> 30) == 0)
     return STG_TAG_NEG | ((uint64_t)d.l[1] << 32) | d.l[0];
   return STG_TAG_BIG | slot;
+}
+// out-of-line form for the streaming loop (3 % of the slots take it): keeps the loop's register footprint small, so that
+// several 256-bit loads per lane can be in flight.  Returns the tagged value; bit 0 of *flags is set for a slot >= p.
+__device__ __noinline__ uint64_t cpt_classify_slow(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t x4, uint32_t x5, uint32_t x6,
+                                                   uint32_t x7, uint32_t slot, const field_consts *__restrict__ F, uint32_t *flags) {
+  const uint32_t x[8] = {x0, x1, x2, x3, x4, x5, x6, x7};
+  bool noncanon = false;
+  const uint64_t v = cpt_classify(x, slot, F->p, noncanon);
+  if (noncanon) atomicOr(flags, 1u);
+  return v;
 }
 // one witness slot with a single 256-bit load (SASS LDG.E.256); streamed: read once, kept out of L1
 __device__ __forceinline__ void ld_slot_stream(const uint8_t *p, uint32_t x[8]) {
@@ -252,6 +267,71 @@ __device__ __forceinline__ uint32_t fp_eval_tile(const CompactSrc &src, const fa
   return holds ? B3W_NO_ROW : P.row_ids[t.row_off + lane];
 }
 
+// rows the compiler did not take (coefficients that are arbitrary field elements): the general class / block evaluator
+__device__ __noinline__ uint32_t fp_eval_residual(const CompactSrc &src, const r1cs_tables_dev &T, bool one_ok) {
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  constexpr uint32_t NW = FPK_THREADS / 32;
+  uint32_t bad = B3W_NO_ROW;
+  for (uint32_t ci = 0; ci < T.n_classes; ci++) {
+    const r1cs_class_dev c = T.cls[ci];
+    const uint32_t nb = T.cls_blocks[ci], hw = 2u + 2u * (c.nA + c.nB + c.nC);
+    const bool fast = one_ok && (c.flags & R1CS_FLAG_FAST64);
+    if (c.flags & R1CS_FLAG_MATRIX) {
+      for (uint32_t r = tid; r < ((c.count + 31u) & ~31u); r += FPK_THREADS)
+        bad = min(bad, fast ? staged_matrix_row<true>(src, c, T, r) : staged_matrix_row<false>(src, c, T, r));
+    } else {
+      for (uint32_t b = warp; b < nb; b += NW) {
+        const uint32_t *hdr = T.terms + c.term_off + (size_t)b * hw;
+        bad = min(bad, fast ? staged_block<true>(src, c, T, hdr, lane) : staged_block<false>(src, c, T, hdr, lane));
+      }
+    }
+  }
+  return bad;
+}
+
+// every row of one instance from the compact copy (all threads of the CTA; each returns its own smallest violated row id).
+// Out of line: the streaming loop of the kernel keeps its registers for loads in flight.
+__device__ __noinline__ uint32_t fp_eval_rows(const CompactSrc &src, const fastprog_dev &P, const r1cs_tables_dev &T, uint32_t words) {
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  constexpr uint32_t NW = FPK_THREADS / 32;
+  const uint32_t *isbit = src.isbit;
+  uint32_t bad = B3W_NO_ROW;
+  const bool one_ok = src.get(0) == 1ull;                 // wire 0 holds the constant 1
+  // ---- booleanity rows: the slots of the mask must be bits ----
+  for (uint32_t wd = tid; wd < words; wd += FPK_THREADS) {
+    const uint32_t need = __ldg(P.bool_mask + wd);
+    uint32_t viol = need & ~isbit[wd];
+    if (!one_ok) viol = need;                               // x (x - w0) = 0 with w0 != 1: decide every row exactly
+    while (viol) {
+      const uint32_t s = wd * 32u + (uint32_t)__ffs((int)viol) - 1u;
+      viol &= viol - 1u;
+      if (one_ok || !fp_bool_fr(src, s)) bad = min(bad, __ldg(P.bool_row + s));
+    }
+  }
+  // ---- XOR rows: runs of consecutive (x, y, o) triples ----
+  for (uint32_t b = tid; b < P.n_xors; b += FPK_THREADS) {
+    const uint4 e = __ldg(reinterpret_cast<const uint4 *>(P.xors) + b);
+    const uint32_t len = e.w & 63u;
+    const bool bits = src.run_is_bits(e.x, len) && src.run_is_bits(e.y, len) && src.run_is_bits(e.z, len);
+    if (bits && (src.run_value(e.x, len) ^ src.run_value(e.y, len)) == src.run_value(e.z, len)) continue;
+    for (uint32_t j = 0; j < len; j++) {                    // some row of the run is violated or holds non-bits: row by row
+      const uint64_t vx = src.get(e.x + j), vy = src.get(e.y + j), vo = src.get(e.z + j);
+      const bool holds = (vx | vy | vo) < 2ull ? vo == (vx ^ vy) : fp_xor_fr(src, e.x + j, e.y + j, e.z + j);
+      if (!holds) bad = min(bad, __ldg(P.xor_ids + (e.w >> 6) + j));
+    }
+  }
+  // ---- every other compiled row: tiles of 32 rows, one per warp step ----
+  for (uint32_t t = warp; t < P.n_tiles; t += NW) {
+    const uint4 h = __ldg(reinterpret_cast<const uint4 *>(P.tiles) + t);
+    fp_tile tl;
+    tl.item_off = h.x; tl.row_off = h.y;
+    tl.nA = (uint16_t)(h.z & 0xFFFFu); tl.nB = (uint16_t)(h.z >> 16); tl.nC = (uint16_t)(h.w & 0xFFFFu); tl.rows = (uint16_t)(h.w >> 16);
+    bad = min(bad, fp_eval_tile(src, P, tl, lane));
+  }
+  if (T.n_classes) bad = min(bad, fp_eval_residual(src, T, one_ok));
+  return bad;
+}
+
 __global__ void __launch_bounds__(FPK_THREADS, FPK_CTAS_PER_SM)
 k_r1cs_check_fast(const uint8_t *__restrict__ wit, const uint32_t *__restrict__ list /* NULL, or {count, instances...}: see below */, uint64_t n,
                   uint32_t ws, const fastprog_dev P, const r1cs_tables_dev T /* residual rows */, const field_consts *__restrict__ F,
@@ -263,9 +343,6 @@ k_r1cs_check_fast(const uint8_t *__restrict__ wit, const uint32_t *__restrict__ 
   __shared__ uint32_t s_bad, s_flags, s_nside;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   constexpr uint32_t NW = FPK_THREADS / 32;
-  fr_t p;
-#pragma unroll
-  for (int j = 0; j < 8; j++) p.l[j] = F->p.l[j];
   // list != NULL: check the instances list[1 .. list[0]] (n is ignored), except those whose status says "Assert Failed."
   const uint64_t count = list ? (uint64_t)list[0] : n;
   for (uint64_t it = blockIdx.x; it < count; it += gridDim.x) {
@@ -278,91 +355,46 @@ k_r1cs_check_fast(const uint8_t *__restrict__ wit, const uint32_t *__restrict__ 
     if (tid == 0) { s_bad = B3W_NO_ROW; s_flags = 0; s_nside = 0; isbit[words] = 0xFFFFFFFFu; bitval[words] = 0u; }
     __syncthreads();
     const uint8_t *w = wit + i * (uint64_t)ws * 32;
-    // ---- stream the witness once: lane = slot inside a 32-slot word, two words per warp step in flight ----
-    {
-      bool noncanon = false;
-      for (uint32_t wd = warp; wd < words; wd += 2 * NW) {
-        uint32_t x[2][8];
+    // ---- stream the witness once: lane = slot inside a 32-slot word, FPK_INFLIGHT words (1 KiB each) per warp in flight ----
+    // The loop is latency-bound (ncu: half of all stall samples sit on the first use of the loaded slot), so what counts is
+    // bytes in flight per SM: 32 warps x FPK_INFLIGHT KiB.
+    for (uint32_t wd = warp; wd < words; wd += FPK_INFLIGHT * NW) {
+      uint32_t x[FPK_INFLIGHT][8];
 #pragma unroll
-        for (int u = 0; u < 2; u++) {
-          const uint32_t s = min((wd + u * NW) * 32u + lane, ws - 1u);
-          ld_slot_stream(w + (size_t)s * 32, x[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-          const uint32_t wu = wd + u * NW;
-          if (wu >= words) break;                               // warp-uniform
-          const uint32_t s = wu * 32u + lane;
-          const bool in = s < ws;
-          const bool bit = in && (x[u][1] | x[u][2] | x[u][3] | x[u][4] | x[u][5] | x[u][6] | x[u][7]) == 0 && x[u][0] < 2u;
-          const uint32_t mb = __ballot_sync(0xffffffffu, bit || !in);      // slots past the end count as bits (value 0)
-          const uint32_t mv = __ballot_sync(0xffffffffu, bit && x[u][0] == 1u);
-          uint32_t base = 0;
-          if (~mb) {                                            // warp-uniform: the word holds non-bit slots
-            if (lane == 0) base = atomicAdd(&s_nside, (uint32_t)__popc(~mb));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (!((mb >> lane) & 1u)) {
-              const uint32_t idx = base + __popc(~mb & ((1u << lane) - 1u));
-              const uint64_t v = cpt_classify(x[u], s, p, noncanon);
-              if (idx < FPK_SIDE_MAX) side[idx] = v;
-            }
-          }
-          if (lane == 0) { isbit[wu] = mb; bitval[wu] = mv; rank[wu] = base; }
-        }
+      for (int u = 0; u < FPK_INFLIGHT; u++) {
+        const uint32_t s = min((wd + u * NW) * 32u + lane, ws - 1u);
+        ld_slot_stream(w + (size_t)s * 32, x[u]);
       }
-      if (noncanon) atomicOr(&s_flags, 1u);
+#pragma unroll
+      for (int u = 0; u < FPK_INFLIGHT; u++) {
+        const uint32_t wu = wd + u * NW;
+        if (wu >= words) break;                               // warp-uniform
+        const uint32_t s = wu * 32u + lane;
+        const bool in = s < ws;
+        const bool bit = in && (x[u][1] | x[u][2] | x[u][3] | x[u][4] | x[u][5] | x[u][6] | x[u][7]) == 0 && x[u][0] < 2u;
+        const uint32_t mb = __ballot_sync(0xffffffffu, bit || !in);      // slots past the end count as bits (value 0)
+        const uint32_t mv = __ballot_sync(0xffffffffu, bit && x[u][0] == 1u);
+        uint32_t base = 0;
+        if (~mb) {                                            // warp-uniform: the word holds non-bit slots
+          if (lane == 0) base = atomicAdd(&s_nside, (uint32_t)__popc(~mb));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (!((mb >> lane) & 1u)) {
+            const uint32_t idx = base + __popc(~mb & ((1u << lane) - 1u));
+            // small non-negative integers (every word, sum and carry of these circuits) need no field arithmetic
+            uint64_t v;
+            if ((x[u][2] | x[u][3] | x[u][4] | x[u][5] | x[u][6] | x[u][7]) == 0 && (x[u][1] >> 30) == 0) v = ((uint64_t)x[u][1] << 32) | x[u][0];
+            else v = cpt_classify_slow(x[u][0], x[u][1], x[u][2], x[u][3], x[u][4], x[u][5], x[u][6], x[u][7], s, F, &s_flags);
+            if (idx < FPK_SIDE_MAX) side[idx] = v;
+          }
+        }
+        if (lane == 0) { isbit[wu] = mb; bitval[wu] = mv; rank[wu] = base; }
+      }
     }
     __syncthreads();
     uint32_t bad = B3W_NO_ROW;
     if (!(s_flags & 1u) && FPK_EXP == 0) {
       const CompactSrc src{isbit, bitval, rank, side, w, F, s_nside <= FPK_SIDE_MAX};
-      const bool one_ok = src.get(0) == 1ull;                 // wire 0 holds the constant 1
-      // ---- booleanity rows: the slots of the mask must be bits ----
-      for (uint32_t wd = tid; wd < words; wd += FPK_THREADS) {
-        const uint32_t need = __ldg(P.bool_mask + wd);
-        uint32_t viol = need & ~isbit[wd];
-        if (!one_ok) viol = need;                               // x (x - w0) = 0 with w0 != 1: decide every row exactly
-        while (viol) {
-          const uint32_t s = wd * 32u + (uint32_t)__ffs((int)viol) - 1u;
-          viol &= viol - 1u;
-          if (one_ok || !fp_bool_fr(src, s)) bad = min(bad, __ldg(P.bool_row + s));
-        }
-      }
-      // ---- XOR rows: runs of consecutive (x, y, o) triples ----
-      for (uint32_t b = tid; b < P.n_xors; b += FPK_THREADS) {
-        const uint4 e = __ldg(reinterpret_cast<const uint4 *>(P.xors) + b);
-        const uint32_t len = e.w & 63u;
-        const bool bits = src.run_is_bits(e.x, len) && src.run_is_bits(e.y, len) && src.run_is_bits(e.z, len);
-        if (bits && (src.run_value(e.x, len) ^ src.run_value(e.y, len)) == src.run_value(e.z, len)) continue;
-        for (uint32_t j = 0; j < len; j++) {                    // some row of the run is violated or holds non-bits: row by row
-          const uint64_t vx = src.get(e.x + j), vy = src.get(e.y + j), vo = src.get(e.z + j);
-          const bool holds = (vx | vy | vo) < 2ull ? vo == (vx ^ vy) : fp_xor_fr(src, e.x + j, e.y + j, e.z + j);
-          if (!holds) bad = min(bad, __ldg(P.xor_ids + (e.w >> 6) + j));
-        }
-      }
-      // ---- every other compiled row: tiles of 32 rows, one per warp step ----
-      for (uint32_t t = warp; t < P.n_tiles; t += NW) {
-        const uint4 h = __ldg(reinterpret_cast<const uint4 *>(P.tiles) + t);
-        fp_tile tl;
-        tl.item_off = h.x; tl.row_off = h.y;
-        tl.nA = (uint16_t)(h.z & 0xFFFFu); tl.nB = (uint16_t)(h.z >> 16); tl.nC = (uint16_t)(h.w & 0xFFFFu); tl.rows = (uint16_t)(h.w >> 16);
-        bad = min(bad, fp_eval_tile(src, P, tl, lane));
-      }
-      // ---- residual rows (not compiled): the general class / block evaluator ----
-      for (uint32_t ci = 0; ci < T.n_classes; ci++) {
-        const r1cs_class_dev c = T.cls[ci];
-        const uint32_t nb = T.cls_blocks[ci], hw = 2u + 2u * (c.nA + c.nB + c.nC);
-        const bool fast = one_ok && (c.flags & R1CS_FLAG_FAST64);
-        if (c.flags & R1CS_FLAG_MATRIX) {
-          for (uint32_t r = tid; r < ((c.count + 31u) & ~31u); r += FPK_THREADS)
-            bad = min(bad, fast ? staged_matrix_row<true>(src, c, T, r) : staged_matrix_row<false>(src, c, T, r));
-        } else {
-          for (uint32_t b = warp; b < nb; b += NW) {
-            const uint32_t *hdr = T.terms + c.term_off + (size_t)b * hw;
-            bad = min(bad, fast ? staged_block<true>(src, c, T, hdr, lane) : staged_block<false>(src, c, T, hdr, lane));
-          }
-        }
-      }
+      bad = fp_eval_rows(src, P, T, words);
     }
     if (bad != B3W_NO_ROW) atomicMin(&s_bad, bad);
     __syncthreads();

@@ -101,19 +101,24 @@ static napi_value WtnsHeader(napi_env env, napi_callback_info info) {
   return v;
 }
 
-// witnessBatch(ctx, rows: Uint32Array, n, wantWitness) -> Promise<{witness: Uint8Array|null, status: Uint8Array, pub: Uint32Array}>
+// witnessBatch(ctx, rows: Uint32Array, n, wantWitness[, wantSums]) -> Promise<{witness: Uint8Array|null, status: Uint8Array,
+//   pub: Uint32Array[, sums: BigUint64Array]}>; sums = the per-instance 64-bit witness checksums of b3w_batch_extras (computed by
+//   the kernel from the values it stores): what lets a caller that streams (wantWitness = false) account for every witness
 // witnessOne(ctx, row) -> Promise<Uint8Array>
 // witnessBatchFr(ctx, fr: Uint8Array(n * nInputs * 32), n, wantWitness) / witnessOneFr(ctx, fr): the same with inputs as
 // little-endian field elements (b3w_witness_batch_fr: blake3_compression takes every value the reference takes)
 struct job {
   napi_async_work work; napi_deferred deferred;
   b3w_ctx *ctx; uint32_t circuit; uint32_t *rows; uint8_t *fr; uint64_t n; b3w_info bi;
-  uint8_t *out, *status; uint32_t *pub; bool one, out_pinned; int rc; char err[512];
+  uint8_t *out, *status; uint32_t *pub; uint64_t *sums; bool one, out_pinned; int rc; char err[512];
 };
 static void job_run(napi_env, void *data) {
   job *j = (job *)data;
-  j->rc = j->fr ? b3w_witness_batch_fr(j->ctx, j->fr, j->n, j->out, j->status, j->pub)
-                : b3w_witness_batch(j->ctx, j->rows, j->n, j->out, j->status, j->pub);
+  b3w_batch_extras ex;
+  memset(&ex, 0, sizeof ex);
+  ex.sums = j->sums;
+  j->rc = j->fr ? b3w_witness_batch_fr_ex(j->ctx, j->fr, j->n, j->out, j->status, j->pub, &ex)
+                : b3w_witness_batch_ex(j->ctx, j->rows, j->n, j->out, j->status, j->pub, &ex);
   if (j->rc == B3W_OK && j->one && j->status[0]) j->rc = j->status[0];
   if (j->rc == B3W_CIRCOM_ASSERT) {
     // witness_calculator.js:21-43,159-162: Error("Assert Failed.\n" + the printErrorMessage lines), re-wrapped
@@ -148,7 +153,7 @@ static void job_done(napi_env env, napi_status, void *data) {
     napi_create_error(env, NULL, msg, &res);
     napi_reject_deferred(env, j->deferred, res);
     if (j->out_pinned) b3w_host_free(j->out); else free(j->out);
-    free(j->status); free(j->pub);
+    free(j->status); free(j->pub); free(j->sums);
   } else if (j->one) {
     size_t wb = (size_t)j->bi.witness_size * 32;
     napi_create_external_arraybuffer(env, j->out, wb, j->out_pinned ? job_free_pinned : job_free_buf, NULL, &ab);
@@ -169,6 +174,11 @@ static void job_done(napi_env env, napi_status, void *data) {
     napi_create_external_arraybuffer(env, j->pub, j->n * j->bi.n_public * 4, job_free_buf, NULL, &ab);
     napi_create_typedarray(env, napi_uint32_array, j->n * j->bi.n_public, ab, 0, &v);
     napi_set_named_property(env, res, "pub", v);
+    if (j->sums) {
+      napi_create_external_arraybuffer(env, j->sums, j->n * 8, job_free_buf, NULL, &ab);
+      napi_create_typedarray(env, napi_biguint64_array, j->n, ab, 0, &v);
+      napi_set_named_property(env, res, "sums", v);
+    }
     napi_resolve_deferred(env, j->deferred, res);
   }
   napi_delete_async_work(env, j->work);
@@ -177,7 +187,7 @@ static void job_done(napi_env env, napi_status, void *data) {
   free(j);
 }
 static napi_value start_job(napi_env env, napi_callback_info info, bool one, bool fr = false) {
-  size_t argc = 4; napi_value argv[4];
+  size_t argc = 5; napi_value argv[5];
   NAPI_OK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
   job *j = (job *)calloc(1, sizeof(job));
   handle *h = NULL;
@@ -187,11 +197,12 @@ static napi_value start_job(napi_env env, napi_callback_info info, bool one, boo
   b3w_circuit_info(h->circuit, &j->bi);
   napi_typedarray_type tt; size_t len; void *data; napi_value ab; size_t off;
   NAPI_OK(napi_get_typedarray_info(env, argv[1], &tt, &len, &data, &ab, &off));
-  bool want = true;
+  bool want = true, want_sums = false;
   if (one) j->n = 1;
   else {
     uint32_t n32; NAPI_OK(napi_get_value_uint32(env, argv[2], &n32)); j->n = n32;
     NAPI_OK(napi_get_value_bool(env, argv[3], &want));
+    if (argc >= 5) NAPI_OK(napi_get_value_bool(env, argv[4], &want_sums));
   }
   if (len != (size_t)j->n * j->bi.n_inputs * (fr ? 32 : 1) || tt != (fr ? napi_uint8_array : napi_uint32_array)) {
     free(j);
@@ -208,9 +219,10 @@ static napi_value start_job(napi_env env, napi_callback_info info, bool one, boo
   }
   j->status = (uint8_t *)calloc(j->n ? j->n : 1, 1);
   j->pub = (uint32_t *)calloc((j->n ? j->n : 1) * 16, 4);
+  j->sums = want_sums ? (uint64_t *)calloc(j->n ? j->n : 1, 8) : NULL;
   j->out = want ? out_alloc((size_t)(j->n ? j->n : 1) * j->bi.witness_size * 32, &j->out_pinned) : NULL;
   if (want && !j->out) {
-    free(j->rows); free(j->fr); free(j->status); free(j->pub); free(j);
+    free(j->rows); free(j->fr); free(j->status); free(j->pub); free(j->sums); free(j);
     napi_throw_error(env, NULL, "out of host memory for the witness buffer");
     return NULL;
   }

@@ -119,16 +119,17 @@ class WitnessCalculator {
     // opts.witness === false keeps the witnesses on the GPU and returns only status + public outputs.
     async calculateWitnessBatch(inputs, opts) {
         opts = opts || {};
+        // opts.witness === false: stream only (status + pub come back); opts.sums: per-instance 64-bit witness checksums too
         if (!Array.isArray(inputs)) {
-            return await this.addon.witnessBatch(this.instance, inputs.rows, inputs.n, opts.witness !== false);   // {witness, status, pub}
+            return await this.addon.witnessBatch(this.instance, inputs.rows, inputs.n, opts.witness !== false, !!opts.sums);   // {witness, status, pub[, sums]}
         }
         const n = inputs.length;
         const vals = inputs.map((inp) => this._values(inp));
         const u32 = vals.every((v) => v.every((x) => x >> 32n === 0n));
-        if (!u32) return await this.addon.witnessBatchFr(this.instance, this._fr(vals.flat()), n, opts.witness !== false);
+        if (!u32) return await this.addon.witnessBatchFr(this.instance, this._fr(vals.flat()), n, opts.witness !== false, !!opts.sums);
         const rows = new Uint32Array(n * this.nInputs);
         vals.forEach((v, i) => rows.set(this._row(v), i * this.nInputs));
-        return await this.addon.witnessBatch(this.instance, rows, n, opts.witness !== false);
+        return await this.addon.witnessBatch(this.instance, rows, n, opts.witness !== false, !!opts.sums);
     }
 }
 

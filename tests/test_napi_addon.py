@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 MOCK = os.path.join(ROOT, "tests", "napi_mock")
 ADDON = os.path.join(ROOT, "integration", "js", "addon", "blake3wit_napi.cc")
 K_NULL, K_U32, K_STRING, K_OBJECT, K_ARRAY, K_TYPEDARRAY, K_EXTERNAL, K_ERROR, K_PROMISE = 0, 1, 4, 5, 6, 8, 9, 10, 11
-U8, U32 = 1, 6                                            # napi_uint8_array, napi_uint32_array
+U8, U32, U64 = 1, 6, 10                                   # napi_uint8_array, napi_uint32_array, napi_biguint64_array
 P = 21888242871839275222246405745257275088548364400416034343698204186575808495617
 
 
@@ -71,10 +71,11 @@ class Napi:
     def array_of(self, ta):
         t, n, p = C.c_int(), C.c_size_t(), C.c_void_p()
         assert self.L.mk_typed_info(ta, C.byref(t), C.byref(n), C.byref(p)) == 0
-        dt = {U8: np.uint8, U32: np.uint32}[t.value]
+        dt = {U8: np.uint8, U32: np.uint32, U64: np.uint64}[t.value]
         if n.value == 0:
             return np.zeros(0, dt)
-        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8 if t.value == U8 else C.c_uint32)), (n.value,)).copy()
+        ct = {U8: C.c_uint8, U32: C.c_uint32, U64: C.c_uint64}[t.value]
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(ct)), (n.value,)).copy()
 
     def await_(self, promise):
         """-> the resolution handle; raises RuntimeError(message) for a rejection (what `await` does in JS)"""
@@ -163,6 +164,12 @@ def test_witness_batch_through_the_addon(napi, ctx, cases):
     assert np.array_equal(pub, want.view(np.uint32).reshape(n, 24093, 8)[:, 1:17, 0])
     res = napi.await_(napi.call("witnessBatch", ctx, napi.typed(rows.reshape(-1)), L.mk_u32(n), L.mk_bool(0)))
     assert L.mk_kind(napi.get(res, "witness")) == K_NULL and np.array_equal(napi.array_of(napi.get(res, "pub")).reshape(n, 16), pub)
+    assert napi.get(res, "sums") is None
+    # streamed, with the per-instance witness checksums (BigUint64Array): equal to the checksum of the fixture's witnesses
+    from conftest import checksum_np
+    res = napi.await_(napi.call("witnessBatch", ctx, napi.typed(rows.reshape(-1)), L.mk_u32(n), L.mk_bool(0), L.mk_bool(1)))
+    assert L.mk_kind(napi.get(res, "witness")) == K_NULL
+    assert np.array_equal(napi.array_of(napi.get(res, "sums")), checksum_np(want, 24093))
 
 
 @pytest.mark.gpu

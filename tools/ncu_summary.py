@@ -28,6 +28,11 @@ FULL_METRICS = [
     "launch__block_size", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers",
     "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum",
     "l1tex__t_sector_pipe_lsu_mem_global_op_ld_hit_rate.pct", "sm__cycles_elapsed.avg.per_second",
+    "dram__bytes_read.sum.per_second", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+    "lts__t_sectors_srcunit_tex_op_read.sum", "lts__t_sector_hit_rate.pct", "launch__occupancy_limit_warps", "sm__maximum_warps_per_active_cycle_pct",
+    "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_barrier_per_warp_active.pct",
+    "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct",
+    "smsp__inst_executed_op_local_ld.sum", "smsp__inst_executed_op_local_st.sum", "launch__shared_mem_per_block_dynamic",
 ]
 
 
