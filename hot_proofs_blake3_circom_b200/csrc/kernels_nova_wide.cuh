@@ -75,7 +75,14 @@ __device__ __noinline__ fr_t nova_wide_value(const nw_view &w, uint32_t dsc, con
     else if (t >= TR_IN + 8 && t < TR_IN + 24) s = w.sel[48 + t - (TR_IN + 8)];
     if (s != NW_SEL_ZERO) v = w.in(s);
   }
-  if (kind == DK_INV && !fr_is_zero(v)) v = fr_inv(v, F.p, F.r2, F.n0);
+  if (kind == DK_INV && !fr_is_zero(v)) {
+    // IsZero.inv.  Most of these differences stay small integers even when one input is a genuine field element (e.g. only
+    // n_blocks is): +-k with k < 256 comes from the table, like on the hot path; only the rest pays a Fermat inversion
+    const fr_t neg = fr_neg(v, p);
+    if (nw_fits(v, 8)) v = F.inv_small[v.l[0]];
+    else if (nw_fits(neg, 8)) v = fr_neg(F.inv_small[neg.l[0]], p);
+    else v = fr_inv(v, F.p, F.r2, F.n0);
+  }
   return v;
 }
 
