@@ -857,12 +857,18 @@ static int r1cs_check_launch(b3w_ctx *c, const uint8_t *d_wit, const uint32_t *d
   if (n == 0) return B3W_OK;
   const r1cs_tables_dev T{c->r_slots.cls, c->r_slots.lo, c->r_slots.hi, c->r_slots.terms, c->r_slots.ncls, c->r_slots.coef_fr, c->r_slots.row_ids, c->r_slots.nblk};
   const uint32_t mw = ((c->def->ws + 31u) >> 5) + 1u;
-  const size_t smem = (size_t)((3 * mw + 1) & ~1u) * 4 + (size_t)FPK_SIDE_MAX * 8;
+  // the side table holds the non-bit slots: sized from the circuit's own slot kinds (+ margin) rather than for the worst
+  // case, which leaves more of the SM's L1 to the program tables; a witness with more non-bit slots than that (not one of
+  // this circuit's) is still checked, its values are then re-read from HBM on demand
+  uint32_t non_bits = 0;
+  for (uint32_t sl = 0; sl < c->def->ws; sl++) non_bits += (c->h_desc[sl] >> 24) != DK_BIT;
+  const uint32_t side_max = std::min<uint32_t>(FPK_SIDE_MAX, (non_bits + 128u + 63u) & ~63u);
+  const size_t smem = (size_t)((3 * mw + 1) & ~1u) * 4 + (size_t)side_max * 8;
   CK(cudaFuncSetAttribute(k_r1cs_check_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int per_sm = c->ctas_limit > 0 ? c->ctas_limit : FPK_CTAS_PER_SM;
   const uint64_t cap = (uint64_t)c->sm_count * per_sm;
-  k_r1cs_check_fast<<<(unsigned)(n < cap ? n : cap), FPK_THREADS, smem, s>>>(d_wit, listed ? d_list : nullptr, n, c->def->ws, c->fp, T, c->d_field, d_status,
-                                                                             d_first_bad);
+  k_r1cs_check_fast<<<(unsigned)(n < cap ? n : cap), FPK_THREADS, smem, s>>>(d_wit, listed ? d_list : nullptr, n, c->def->ws, side_max, c->fp, T, c->d_field,
+                                                                             d_status, d_first_bad);
   CK(cudaGetLastError());
   return B3W_OK;
 }

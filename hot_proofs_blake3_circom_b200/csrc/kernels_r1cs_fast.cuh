@@ -223,13 +223,15 @@ __device__ __forceinline__ uint32_t fp_eval_tile(const CompactSrc &src, const fa
   i128 L[3] = {0, 0, 0};
   bool undecided = false;
   uint32_t k = 0;
-  const uint32_t n[3] = {t.nA, t.nB, t.nC};
+  const uint32_t n[3] = {t.nA, t.nB, t.nC}, nt = (uint32_t)t.nA + t.nB + t.nC;
+  uint4 nxt = nt ? __ldg(reinterpret_cast<const uint4 *>(it0)) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
   for (int part = 0; part < 3; part++) {
     long long acc64 = 0;
     i128 acc128 = 0;
     for (uint32_t j = 0; j < n[part]; j++, k++) {
-      const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(it0 + k * 32u));
+      const uint4 raw = nxt;
+      if (k + 1 < nt) nxt = __ldg(reinterpret_cast<const uint4 *>(it0 + (k + 1) * 32u));      // next item in flight (the tables live in L1 / L2)
       const uint32_t wire = raw.x, meta = raw.y, len = meta & 63u, shift = (meta >> 8) & 255u, cbits = (meta >> 16) & 255u;
       const long long coef = (long long)(((uint64_t)raw.w << 32) | raw.z);
       long long v;
@@ -334,8 +336,9 @@ __device__ __noinline__ uint32_t fp_eval_rows(const CompactSrc &src, const fastp
 
 __global__ void __launch_bounds__(FPK_THREADS, FPK_CTAS_PER_SM)
 k_r1cs_check_fast(const uint8_t *__restrict__ wit, const uint32_t *__restrict__ list /* NULL, or {count, instances...}: see below */, uint64_t n,
-                  uint32_t ws, const fastprog_dev P, const r1cs_tables_dev T /* residual rows */, const field_consts *__restrict__ F,
-                  uint8_t *__restrict__ status, uint32_t *__restrict__ first_bad) {
+                  uint32_t ws, uint32_t side_max /* entries of the side table in this launch's shared memory */, const fastprog_dev P,
+                  const r1cs_tables_dev T /* residual rows */, const field_consts *__restrict__ F, uint8_t *__restrict__ status,
+                  uint32_t *__restrict__ first_bad) {
   extern __shared__ __align__(16) uint8_t s_raw[];
   const uint32_t words = (ws + 31u) >> 5, mw = words + 1u;                  // one padding word per map (field_of reads w + 1)
   uint32_t *isbit = reinterpret_cast<uint32_t *>(s_raw), *bitval = isbit + mw, *rank = bitval + mw;
@@ -384,7 +387,7 @@ k_r1cs_check_fast(const uint8_t *__restrict__ wit, const uint32_t *__restrict__ 
             uint64_t v;
             if ((x[u][2] | x[u][3] | x[u][4] | x[u][5] | x[u][6] | x[u][7]) == 0 && (x[u][1] >> 30) == 0) v = ((uint64_t)x[u][1] << 32) | x[u][0];
             else v = cpt_classify_slow(x[u][0], x[u][1], x[u][2], x[u][3], x[u][4], x[u][5], x[u][6], x[u][7], s, F, &s_flags);
-            if (idx < FPK_SIDE_MAX) side[idx] = v;
+            if (idx < side_max) side[idx] = v;
           }
         }
         if (lane == 0) { isbit[wu] = mb; bitval[wu] = mv; rank[wu] = base; }
@@ -393,7 +396,7 @@ k_r1cs_check_fast(const uint8_t *__restrict__ wit, const uint32_t *__restrict__ 
     __syncthreads();
     uint32_t bad = B3W_NO_ROW;
     if (!(s_flags & 1u) && FPK_EXP == 0) {
-      const CompactSrc src{isbit, bitval, rank, side, w, F, s_nside <= FPK_SIDE_MAX};
+      const CompactSrc src{isbit, bitval, rank, side, w, F, s_nside <= side_max};
       bad = fp_eval_rows(src, P, T, words);
     }
     if (bad != B3W_NO_ROW) atomicMin(&s_bad, bad);
