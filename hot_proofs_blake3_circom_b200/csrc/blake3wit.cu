@@ -154,6 +154,7 @@ struct b3w_ctx {
   r1cs_dev r_fused = {}, r_slots = {};
   bool r1cs_loaded = false;     // r_slots comes from b3w_r1cs_load, not from the built-in tables
   fastprog_dev fp = {};         // compiled form of the slot-space rows (kernels_r1cs_fast.cuh); r_slots holds the residual rows only
+  fastprog_dev fp0 = {};        // the same rows compiled without virtual bits (all-zero when fp has none: fp is then used for both)
   uint32_t slot_rows = 0;       // rows of the slot-space system (compiled + residual); 0 = none installed
   uint32_t fault_word = B3W_NO_ROW, fault_mask = 0;
   int ctas_limit = 0;           // tuning hook: cap on resident CTAs per SM (0 = occupancy limit)
@@ -435,6 +436,7 @@ extern "C" void b3w_destroy(b3w_ctx *c) {
     if (c->d_lane_off) cudaFree(c->d_lane_off);
     for (b3w_ctx::r1cs_dev *r : {&c->r_slots, &c->r_fused}) free_r1cs_dev(r);
     free_fastprog(&c->fp);
+    free_fastprog(&c->fp0);
     free(c->h_desc);
     delete c->h_field;
   }
@@ -583,17 +585,46 @@ static cudaError_t upload_vec(T **dst, const std::vector<T> &v) {
   return e;
 }
 static void free_fastprog(fastprog_dev *p) {
-  for (void *q : {(void *)p->bool_mask, (void *)p->bool_row, (void *)p->xors, (void *)p->xor_ids, (void *)p->tiles, (void *)p->items, (void *)p->row_ids})
+  for (void *q : {(void *)p->bool_mask, (void *)p->bool_row, (void *)p->xors, (void *)p->xor_ids, (void *)p->tiles, (void *)p->vtiles, (void *)p->items, (void *)p->row_ids})
     if (q) cudaFree(q);
   memset(p, 0, sizeof *p);
 }
 
 // The slot-space system of the stand-alone check (built-in rows, or the rows of a loaded .r1cs file): compile what
 // compiles (fp_compile), keep the rest as a residual class/block set for the general evaluator, upload both.
+static cudaError_t upload_fastprog(fastprog_dev *P, const fastprog_host &fp) {
+  memset(P, 0, sizeof *P);
+  cudaError_t e = upload_vec(&P->bool_mask, fp.bool_mask);
+  if (e == cudaSuccess) e = upload_vec(&P->bool_row, fp.bool_row);
+  if (e == cudaSuccess) e = upload_vec(&P->xors, fp.xors);
+  if (e == cudaSuccess) e = upload_vec(&P->xor_ids, fp.xor_ids);
+  if (e == cudaSuccess) e = upload_vec(&P->tiles, fp.tiles);
+  if (e == cudaSuccess) e = upload_vec(&P->vtiles, fp.vtiles);
+  if (e == cudaSuccess) e = upload_vec(&P->items, fp.items);
+  if (e == cudaSuccess) e = upload_vec(&P->row_ids, fp.row_ids);
+  P->n_xors = (uint32_t)fp.xors.size();
+  P->n_tiles = (uint32_t)fp.tiles.size();
+  P->n_vtiles = (uint32_t)fp.vtiles.size();
+  P->n_rows = fp.n_rows;
+  return e;
+}
+// fp_compile with virtual bits where the system has them, plus the plain compilation the kernel falls back to for a
+// witness whose virtual bits are not bits; both cover the same rows (fp0 stays empty when there are no virtual bits)
+static void compile_programs(const std::vector<r1cs_load_detail::row> &rows, uint32_t ws, fastprog_host &fp, fastprog_host &fp0, std::vector<char> &taken) {
+  fp_compile(rows, ws, fp, taken, /*with_virtuals=*/true);
+  if (fp.n_virtual == 0) return;
+  std::vector<char> taken0;
+  fp_compile(rows, ws, fp0, taken0, false);
+  if (taken0 != taken) {                                      // cannot happen (fp_compile keeps the two in step); be safe
+    fp = std::move(fp0);
+    fp0 = fastprog_host();
+    taken.swap(taken0);
+  }
+}
 static int install_slot_rows(b3w_ctx *c, std::vector<r1cs_load_detail::row> &rows, uint32_t *n_compiled) {
-  fastprog_host fp;
+  fastprog_host fp, fp0;
   std::vector<char> taken;
-  fp_compile(rows, c->def->ws, fp, taken);
+  compile_programs(rows, c->def->ws, fp, fp0, taken);
   std::vector<r1cs_load_detail::row> rest;
   for (size_t i = 0; i < rows.size(); i++)
     if (!taken[i]) rest.push_back(std::move(rows[i]));
@@ -604,8 +635,8 @@ static int install_slot_rows(b3w_ctx *c, std::vector<r1cs_load_detail::row> &row
   h.terms.swap(blocks);
   b3w_ctx::r1cs_dev d;
   memset(&d, 0, sizeof d);
-  fastprog_dev P;
-  memset(&P, 0, sizeof P);
+  fastprog_dev P, P0;
+  memset(&P0, 0, sizeof P0);
   cudaError_t e = upload_vec(&d.cls, h.cls);
   if (e == cudaSuccess) e = upload_vec(&d.nblk, nblk);
   if (e == cudaSuccess) e = upload_vec(&d.lo, h.lo);
@@ -613,27 +644,22 @@ static int install_slot_rows(b3w_ctx *c, std::vector<r1cs_load_detail::row> &row
   if (e == cudaSuccess) e = upload_vec(&d.terms, h.terms);
   if (e == cudaSuccess) e = upload_vec(&d.coef_fr, h.coef_fr);
   if (e == cudaSuccess) e = upload_vec(&d.row_ids, h.row_ids);
-  if (e == cudaSuccess) e = upload_vec(&P.bool_mask, fp.bool_mask);
-  if (e == cudaSuccess) e = upload_vec(&P.bool_row, fp.bool_row);
-  if (e == cudaSuccess) e = upload_vec(&P.xors, fp.xors);
-  if (e == cudaSuccess) e = upload_vec(&P.xor_ids, fp.xor_ids);
-  if (e == cudaSuccess) e = upload_vec(&P.tiles, fp.tiles);
-  if (e == cudaSuccess) e = upload_vec(&P.items, fp.items);
-  if (e == cudaSuccess) e = upload_vec(&P.row_ids, fp.row_ids);
+  if (e == cudaSuccess) e = upload_fastprog(&P, fp);
+  if (e == cudaSuccess && fp.n_virtual) e = upload_fastprog(&P0, fp0);
   if (e != cudaSuccess) {
     free_r1cs_dev(&d);
     free_fastprog(&P);
+    free_fastprog(&P0);
     return fail(B3W_ERR_CUDA, "R1CS table upload: %s", cudaGetErrorString(e));
   }
   d.ncls = (uint32_t)h.cls.size();
   d.rows = h.rows;
-  P.n_xors = (uint32_t)fp.xors.size();
-  P.n_tiles = (uint32_t)fp.tiles.size();
-  P.n_rows = fp.n_rows;
   free_r1cs_dev(&c->r_slots);
   free_fastprog(&c->fp);
+  free_fastprog(&c->fp0);
   c->r_slots = d;
   c->fp = P;
+  c->fp0 = P0;
   c->slot_rows = (uint32_t)rows.size();
   if (n_compiled) *n_compiled = fp.n_rows;
   return B3W_OK;
@@ -856,7 +882,7 @@ static int r1cs_check_launch(b3w_ctx *c, const uint8_t *d_wit, const uint32_t *d
   if (c->slot_rows == 0) return fail(B3W_ERR_UNSUPPORTED, "%s: no constraint system for the stand-alone check", c->def->name);
   if (n == 0) return B3W_OK;
   const r1cs_tables_dev T{c->r_slots.cls, c->r_slots.lo, c->r_slots.hi, c->r_slots.terms, c->r_slots.ncls, c->r_slots.coef_fr, c->r_slots.row_ids, c->r_slots.nblk};
-  const uint32_t mw = ((c->def->ws + 31u) >> 5) + 1u;
+  const uint32_t mw = ((c->def->ws + 31u) >> 5) + c->fp.n_vtiles + 1u;
   // the side table holds the non-bit slots: sized from the circuit's own slot kinds (+ margin) rather than for the worst
   // case, which leaves more of the SM's L1 to the program tables; a witness with more non-bit slots than that (not one of
   // this circuit's) is still checked, its values are then re-read from HBM on demand
@@ -867,7 +893,8 @@ static int r1cs_check_launch(b3w_ctx *c, const uint8_t *d_wit, const uint32_t *d
   CK(cudaFuncSetAttribute(k_r1cs_check_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int per_sm = c->ctas_limit > 0 ? c->ctas_limit : FPK_CTAS_PER_SM;
   const uint64_t cap = (uint64_t)c->sm_count * per_sm;
-  k_r1cs_check_fast<<<(unsigned)(n < cap ? n : cap), FPK_THREADS, smem, s>>>(d_wit, listed ? d_list : nullptr, n, c->def->ws, side_max, c->fp, T, c->d_field,
+  k_r1cs_check_fast<<<(unsigned)(n < cap ? n : cap), FPK_THREADS, smem, s>>>(d_wit, listed ? d_list : nullptr, n, c->def->ws, side_max, c->fp,
+                                                                             c->fp.n_vtiles ? c->fp0 : c->fp, T, c->d_field,
                                                                              d_status, d_first_bad);
   CK(cudaGetLastError());
   return B3W_OK;
@@ -902,9 +929,9 @@ static int b3w_r1cs_compile_stats_impl(uint32_t circuit, uint32_t *n_rows, uint3
   if (!d) return B3W_ERR_UNSUPPORTED;
   std::vector<r1cs_load_detail::row> rows;
   if (!rows_from_builtin(d->r_slots, rows)) return fail(B3W_ERR_INVALID, "R1CS tables of %s are corrupt", d->name);
-  fastprog_host fp;
+  fastprog_host fp, fp0;
   std::vector<char> taken;
-  fp_compile(rows, d->ws, fp, taken);
+  compile_programs(rows, d->ws, fp, fp0, taken);
   if (n_rows) *n_rows = (uint32_t)rows.size();
   if (n_compiled) *n_compiled = fp.n_rows;
   if (n_xor_runs) *n_xor_runs = (uint32_t)fp.xors.size();

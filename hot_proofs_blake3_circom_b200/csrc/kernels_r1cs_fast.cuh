@@ -28,7 +28,9 @@
 #ifndef FPK_EXP
 #define FPK_EXP 0                 /* experiment builds only: 1 = stream + classify, no rows */
 #endif
+#ifndef FPK_THREADS
 #define FPK_THREADS 256
+#endif
 #ifndef FPK_CTAS_PER_SM
 #define FPK_CTAS_PER_SM 4
 #endif
@@ -45,8 +47,12 @@ struct fp_item {                  // 16 bytes
 struct fp_tile {                  // 32 rows of identical item counts; lane = row
   uint32_t item_off;              // items at item_off + k * 32 + lane, k < nA + nB + nC
   uint32_t row_off;               // row ids at row_ids[row_off + lane]
-  uint16_t nA, nB, nC, rows;
+  uint16_t nA, nB, nC, rows;      // rows: 1..32 | FP_TILE_FAST
 };
+// FP_TILE_FAST (set by fp_compile): with every scalar below 2^FP_FAST_VBITS and every run over bits, no term of any row of
+// the tile reaches 2^57 and no linear combination has more than 16 items -- plain 64-bit sums are exact, no bounds tracked
+#define FP_TILE_FAST 0x8000u
+#define FP_FAST_VBITS 36
 struct fp_xor { uint32_t x, y, o, len_id; };      // len = len_id & 63 rows (x + j, y + j, o + j); ids at xor_ids[(len_id >> 6) + j]
 struct fastprog_dev {
   uint32_t *bool_mask;            // (ws + 31) / 32 + 1 words: slots with a booleanity row
@@ -54,9 +60,10 @@ struct fastprog_dev {
   fp_xor *xors;
   uint32_t *xor_ids;
   fp_tile *tiles;
+  fp_tile *vtiles;                // virtual-bit definitions, 32 per group: nA items each, then one item holding the unit (r1cs_load.h)
   fp_item *items;
   uint32_t *row_ids;
-  uint32_t n_xors, n_tiles, n_rows;      // n_rows: rows the program covers (all three kinds)
+  uint32_t n_xors, n_tiles, n_vtiles, n_rows;      // n_rows: rows the program covers (all kinds)
 };
 
 // 32-byte slot -> tagged 8-byte value; BIG = "genuine field element", payload = slot index
@@ -154,39 +161,45 @@ __device__ __forceinline__ fr_t fp_coef_fr(long long coef, uint32_t shift, const
   return coef < 0 ? fr_neg(r, p) : r;
 }
 
-// acc += (coef << shift) * v in Fr; unit coefficients (most rows that end up here: IsZero's in * inv = 1 - out) cost no product
-__device__ __forceinline__ fr_t fp_acc_fr(const fr_t &acc, long long coef, uint32_t shift, const fr_t &v, const field_consts &F) {
+// acc + (coef << shift) * v in Fr; unit coefficients (most rows that end up here: IsZero's in * inv = 1 - out) cost no product.
+// Out of line, like everything on the Fr path: the instruction cache (32 KB before L2) has to hold the streaming loop and
+// the row pass of the four CTAs of an SM at the same time -- ncu showed the kernel stalled on instruction fetch
+// (no_instruction 6.6 warps per issue) when these bodies were inlined at every call site.
+__device__ __noinline__ fr_t fp_montmul(const fr_t &a, const fr_t &b, const field_consts &F) { return fr_montmul(a, b, F.p, F.n0); }
+__device__ __noinline__ fr_t fp_acc_fr(const fr_t &acc, long long coef, uint32_t shift, const fr_t &v, const field_consts &F) {
   if (shift == 0 && coef == 1) return fr_add(acc, v, F.p);
   if (shift == 0 && coef == -1) return fr_add(acc, fr_neg(v, F.p), F.p);
   const fr_t co = fp_coef_fr(coef, shift, F.p);
-  return fr_add(acc, fr_montmul(fr_montmul(co, F.r2, F.p, F.n0), v, F.p, F.n0), F.p);
+  return fr_add(acc, fp_montmul(fp_montmul(co, F.r2, F), v, F), F.p);
+}
+// a * b in Fr for canonical (non-Montgomery) operands
+__device__ __forceinline__ fr_t fp_mul_fr(const fr_t &a, const fr_t &b, const field_consts &F) {
+  return fp_montmul(fp_montmul(a, b, F), F.r2, F);
 }
 
 // exact evaluation of one compiled row in Fr (slow path)
 __device__ __noinline__ bool fp_row_fr(const CompactSrc &src, const fp_item *__restrict__ items, uint32_t item_off, uint32_t lane,
                                        uint32_t nA, uint32_t nB, uint32_t nC) {
   const field_consts &F = *src.F;
-  const uint32_t n[3] = {nA, nB, nC};
-  fr_t L[3];
-  uint32_t k = 0;
-  for (int part = 0; part < 3; part++) {
-    fr_t acc = fr_zero();
-    for (uint32_t j = 0; j < n[part]; j++, k++) {
-      const fp_item it = items[item_off + k * 32u + lane];
-      const uint32_t len = it.meta & 63u, shift = (it.meta >> 8) & 255u;
-      if (it.coef == 0) continue;
-      if (len && src.run_is_bits(it.wire, len)) {               // a run over bits is one value
-        acc = fp_acc_fr(acc, it.coef, shift, fr_from_u64(src.run_value(it.wire, len)), F);
-        continue;
-      }
-      const uint32_t cnt = len ? len : 1u;
-      for (uint32_t e = 0; e < cnt; e++)                        // else wire by wire: its slots may hold anything
-        acc = fp_acc_fr(acc, it.coef, shift + e, src.field(it.wire + e), F);
+  const uint32_t nt = nA + nB + nC;
+  fr_t L[3] = {fr_zero(), fr_zero(), fr_zero()};
+#pragma unroll 1
+  for (uint32_t k = 0; k < nt; k++) {
+    const fp_item it = items[item_off + k * 32u + lane];
+    const uint32_t len = it.meta & 63u, shift = (it.meta >> 8) & 255u;
+    if (it.coef == 0) continue;
+    const bool as_run = len && src.run_is_bits(it.wire, len);   // a run over bits is one value; else wire by wire: its slots may hold anything
+    const uint32_t cnt = (len && !as_run) ? len : 1u;
+    const int part = k < nA ? 0 : k < nA + nB ? 1 : 2;
+#pragma unroll 1
+    for (uint32_t e = 0; e < cnt; e++) {
+      const fr_t v = as_run ? fr_from_u64(src.run_value(it.wire, len)) : src.field(it.wire + e);
+      const fr_t acc = fp_acc_fr(part == 0 ? L[0] : part == 1 ? L[1] : L[2], it.coef, shift + e, v, F);
+      if (part == 0) L[0] = acc; else if (part == 1) L[1] = acc; else L[2] = acc;
     }
-    L[part] = acc;
   }
   fr_t lhs = fr_zero();
-  if (nA && nB) lhs = fr_montmul(fr_montmul(L[0], L[1], F.p, F.n0), F.r2, F.p, F.n0);
+  if (nA && nB) lhs = fp_mul_fr(L[0], L[1], F);
   bool eq = true;
 #pragma unroll
   for (int j = 0; j < 8; j++) eq = eq && (lhs.l[j] == L[2].l[j]);
@@ -197,7 +210,7 @@ __device__ __noinline__ bool fp_row_fr(const CompactSrc &src, const fp_item *__r
 __device__ __noinline__ bool fp_xor_fr(const CompactSrc &src, uint32_t x, uint32_t y, uint32_t o) {
   const field_consts &F = *src.F;
   const fr_t vx = src.field(x), vy = src.field(y), vo = src.field(o);
-  fr_t xy = fr_montmul(fr_montmul(vx, vy, F.p, F.n0), F.r2, F.p, F.n0);
+  fr_t xy = fp_mul_fr(vx, vy, F);
   xy = fr_add(xy, xy, F.p);
   const fr_t rhs = fr_add(fr_add(vx, vy, F.p), fr_neg(vo, F.p), F.p);
   bool eq = true;
@@ -211,54 +224,201 @@ __device__ __noinline__ bool fp_bool_fr(const CompactSrc &src, uint32_t x) {
   const field_consts &F = *src.F;
   const fr_t vx = src.field(x), w0 = src.field(0);
   const fr_t d = fr_add(vx, fr_neg(w0, F.p), F.p);
-  return fr_is_zero(fr_montmul(vx, d, F.p, F.n0));
+  return fr_is_zero(fp_montmul(vx, d, F));
+}
+
+// the exact integer value of one item, (coef * v) << shift; `undecided` is raised when it has none in 128 bits (a run over
+// non-bits, a bound past 2^118); a scalar that holds a genuine field element gives 0 and is reported in `big` as
+// 1 + (coef == 1 ? 0 : coef == -1 ? 1 : 2) -- the caller may know what to do with a lone unit-coefficient one
+__device__ __forceinline__ i128 fp_term(const CompactSrc &src, const uint4 raw, bool &undecided, uint32_t &big) {
+  const uint32_t wire = raw.x, meta = raw.y, len = meta & 63u, shift = (meta >> 8) & 255u, cbits = (meta >> 16) & 255u;
+  const long long coef = (long long)(((uint64_t)raw.w << 32) | raw.z);
+  long long v;
+  int vbits;
+  big = 0;
+  if (len) {
+    undecided = undecided || !src.run_is_bits(wire, len);
+    v = (long long)src.run_value(wire, len);
+    vbits = (int)len;
+  } else {
+    const uint64_t x = src.get(wire);
+    if (x & STG_TAG_BIG) {
+      big = (shift == 0 && coef == 1) ? 1u : (shift == 0 && coef == -1) ? 2u : 3u;
+      return 0;
+    }
+    const uint64_t mag = x & STG_PAYLOAD;
+    v = (x & STG_TAG_NEG) ? -(long long)mag : (long long)mag;
+    vbits = fp_bitlen64(mag);
+  }
+  const int bits = (int)cbits + vbits;
+  if (bits <= 62) return (i128)((coef * v) << shift);
+  undecided = undecided || bits > 118;                          // <= 255 items of < 2^118 each stay below 2^126
+  return ((i128)coef * (i128)v) << shift;
+}
+
+// The virtual bits of one instance (r1cs_load.h: fp_find_virtuals): every definition's linear combination L is evaluated
+// exactly and must be 0 or its unit u; the bit goes into the maps at slot 32 * words + index, where the rewritten rows
+// read it like any other bit.  A definition that is neither (or cannot be decided in integers), or a witness whose slot 0
+// is not 1, raises bit 1 of *flags: the caller then evaluates the instance with the program compiled without virtual bits.
+__device__ __noinline__ void fp_eval_virtuals(const CompactSrc &src, const fastprog_dev &P, uint32_t words, uint32_t *isbit, uint32_t *bitval,
+                                              uint32_t *flags) {
+  const uint32_t tid = threadIdx.x, lane = tid & 31u;
+  if (tid == 0 && src.get(0) != 1ull) atomicOr(flags, 2u);
+  for (uint32_t g = tid >> 5; g < P.n_vtiles; g += FPK_THREADS / 32) {
+    const uint4 h = __ldg(reinterpret_cast<const uint4 *>(P.vtiles) + g);
+    const uint32_t n = h.z & 0xFFFFu, rows = h.w >> 16;
+    const fp_item *__restrict__ it0 = P.items + h.x + lane;
+    i128 acc = 0;
+    bool undecided = false;
+#pragma unroll 1
+    for (uint32_t k = 0; k < n; k++) {
+      uint32_t big;
+      acc += fp_term(src, __ldg(reinterpret_cast<const uint4 *>(it0 + k * 32u)), undecided, big);
+      undecided = undecided || big != 0;
+    }
+    const uint4 ur = __ldg(reinterpret_cast<const uint4 *>(it0 + n * 32u));
+    const i128 unit = (i128)(long long)(((uint64_t)ur.w << 32) | ur.z) << ((ur.y >> 8) & 255u);
+    const bool in = lane < rows, one = in && !undecided && acc == unit, zero = !undecided && acc == 0;
+    const uint32_t mv = __ballot_sync(0xffffffffu, one);
+    const bool valid = __all_sync(0xffffffffu, !in || one || zero);
+    if (lane == 0) {
+      isbit[words + g] = 0xFFFFFFFFu;
+      bitval[words + g] = mv;
+      if (!valid) atomicOr(flags, 2u);
+    }
+  }
+}
+
+// an XOR run in which some row is violated or holds non-bits, row by row (cold: kept out of the row pass's code)
+__device__ __noinline__ uint32_t fp_xor_run_slow(const CompactSrc &src, const fastprog_dev &P, const uint4 e) {
+  const uint32_t len = e.w & 63u;
+  uint32_t bad = B3W_NO_ROW;
+  for (uint32_t j = 0; j < len; j++) {
+    const uint64_t vx = src.get(e.x + j), vy = src.get(e.y + j), vo = src.get(e.z + j);
+    const bool holds = (vx | vy | vo) < 2ull ? vo == (vx ^ vy) : fp_xor_fr(src, e.x + j, e.y + j, e.z + j);
+    if (!holds) bad = min(bad, __ldg(P.xor_ids + (e.w >> 6) + j));
+  }
+  return bad;
+}
+// the booleanity rows of one mask word that the bit map does not settle (cold)
+__device__ __noinline__ uint32_t fp_bool_word_slow(const CompactSrc &src, const fastprog_dev &P, uint32_t wd, uint32_t viol, bool one_ok) {
+  uint32_t bad = B3W_NO_ROW;
+  while (viol) {
+    const uint32_t s = wd * 32u + (uint32_t)__ffs((int)viol) - 1u;
+    viol &= viol - 1u;
+    if (one_ok || !fp_bool_fr(src, s)) bad = min(bad, __ldg(P.bool_row + s));
+  }
+  return bad;
+}
+
+// A FP_TILE_FAST tile in 64-bit arithmetic.  *ok = false when some value of the lane's row is not what the flag assumes (a
+// scalar >= 2^36 or tagged negative / field-valued, a run over non-bits): the caller then re-evaluates the tile exactly.
+__device__ __forceinline__ uint32_t fp_eval_tile_fast(const CompactSrc &src, const fastprog_dev &P, const fp_tile t, uint32_t lane, bool *ok_out) {
+  const fp_item *__restrict__ it0 = P.items + t.item_off + lane;
+  const uint32_t nA = t.nA, nAB = (uint32_t)t.nA + t.nB, nt = nAB + t.nC;
+  long long L[3] = {0, 0, 0};
+  bool ok = true;
+  uint4 nxt = nt ? __ldg(reinterpret_cast<const uint4 *>(it0)) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll 1
+  for (uint32_t k = 0; k < nt; k++) {                           // one loop body for the three linear combinations (code size)
+    const uint4 raw = nxt;
+    if (k + 1 < nt) nxt = __ldg(reinterpret_cast<const uint4 *>(it0 + (k + 1) * 32u));
+    const uint32_t wire = raw.x, len = raw.y & 63u, shift = (raw.y >> 8) & 255u;
+    const long long coef = (long long)((((uint64_t)raw.w << 32) | raw.z) << shift);
+    uint64_t v;
+    if (len) {
+      ok = ok && src.run_is_bits(wire, len);
+      v = src.run_value(wire, len);
+    } else {
+      v = src.get(wire);
+      ok = ok && (v >> FP_FAST_VBITS) == 0;                     // the tags are high bits: covers them too
+    }
+    const long long term = coef * (long long)v;
+    if (k < nA) L[0] += term; else if (k < nAB) L[1] += term; else L[2] += term;
+  }
+  *ok_out = ok;
+  const bool holds = (t.nA && t.nB) ? (i128)L[0] * (i128)L[1] == (i128)L[2] : L[2] == 0;
+  return (holds || lane >= (t.rows & 63u)) ? B3W_NO_ROW : P.row_ids[t.row_off + lane];
+}
+
+// a * W == c (mod p) for the field element W in witness slot `wire` (canonical: the streaming pass has checked) and small
+// integers a, c:  T = |a| W + E with E = -+c mod p is a multiple of p  <=>  two Montgomery steps leave 0 or p.
+// 40 multiply-adds instead of the two full Montgomery products of the general Fr evaluator.
+__device__ __noinline__ bool fp_small_times_big(const CompactSrc &src, uint32_t wire, long long a, long long c) {
+  const field_consts &F = *src.F;
+  uint32_t w[8];
+  ld_slot(src.wit + (size_t)wire * 32, w);
+  const uint64_t ma = a < 0 ? (uint64_t)0 - (uint64_t)a : (uint64_t)a;
+  const long long e = a < 0 ? c : -c;                         // a W = c  <=>  |a| W + e = 0  (a > 0: e = -c;  a < 0: e = c)
+  fr_t E = fr_from_u64(e < 0 ? (uint64_t)0 - (uint64_t)e : (uint64_t)e);
+  if (e < 0) E = fr_neg(E, F.p);
+  uint32_t t[11];
+#pragma unroll
+  for (int j = 0; j < 8; j++) t[j] = E.l[j];
+  t[8] = t[9] = t[10] = 0;
+#pragma unroll
+  for (int i = 0; i < 2; i++) {                                 // T += |a| W
+    const uint32_t ai = (uint32_t)(ma >> (32 * i));
+    uint64_t cy = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { cy += (uint64_t)ai * w[j] + t[i + j]; t[i + j] = (uint32_t)cy; cy >>= 32; }
+#pragma unroll
+    for (int j = i + 8; j < 11; j++) { cy += t[j]; t[j] = (uint32_t)cy; cy >>= 32; }
+  }
+#pragma unroll
+  for (int i = 0; i < 2; i++) {                                 // T += m p 2^(32 i), clearing limb i
+    const uint32_t m = t[i] * F.n0;
+    uint64_t cy = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { cy += (uint64_t)m * F.p.l[j] + t[i + j]; t[i + j] = (uint32_t)cy; cy >>= 32; }
+#pragma unroll
+    for (int j = i + 8; j < 11; j++) { cy += t[j]; t[j] = (uint32_t)cy; cy >>= 32; }
+  }
+  // T / 2^64 < 2 p: a multiple of p is 0 or p
+  uint32_t any = t[10], diff = t[10];
+#pragma unroll
+  for (int j = 0; j < 8; j++) { any |= t[2 + j]; diff |= t[2 + j] ^ F.p.l[j]; }
+  return any == 0 || diff == 0;
 }
 
 // one tile: lane = row.  Returns the lane's violated row id or B3W_NO_ROW.
-// A term (coef * v) << shift whose bit-length bound stays <= 54 goes into a 64-bit accumulator (<= 255 of them stay below
-// 2^62); the others -- 2^32.. coefficients on wide values, Num2Bits(65)'s top run -- into a 128-bit one.
-__device__ __forceinline__ uint32_t fp_eval_tile(const CompactSrc &src, const fastprog_dev &P, const fp_tile t, uint32_t lane) {
-  const bool active = lane < t.rows;
+// A term (coef * v) << shift whose bit-length bound stays <= 62 is formed in 64 bits, the others -- 2^32.. coefficients
+// on wide values, Num2Bits(65)'s top run -- in 128; the sums are 128-bit.
+__device__ __noinline__ uint32_t fp_eval_tile(const CompactSrc &src, const fastprog_dev &P, const fp_tile t, uint32_t lane) {
+  const bool active = lane < (t.rows & 63u);
   const fp_item *__restrict__ it0 = P.items + t.item_off + lane;
   i128 L[3] = {0, 0, 0};
   bool undecided = false;
-  uint32_t k = 0;
-  const uint32_t n[3] = {t.nA, t.nB, t.nC}, nt = (uint32_t)t.nA + t.nB + t.nC;
+  uint32_t nbig = 0, big_wire = 0, big_kind = 0;
+  const uint32_t nA = t.nA, nAB = (uint32_t)t.nA + t.nB, nt = nAB + t.nC;
   uint4 nxt = nt ? __ldg(reinterpret_cast<const uint4 *>(it0)) : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-  for (int part = 0; part < 3; part++) {
-    long long acc64 = 0;
-    i128 acc128 = 0;
-    for (uint32_t j = 0; j < n[part]; j++, k++) {
-      const uint4 raw = nxt;
-      if (k + 1 < nt) nxt = __ldg(reinterpret_cast<const uint4 *>(it0 + (k + 1) * 32u));      // next item in flight (the tables live in L1 / L2)
-      const uint32_t wire = raw.x, meta = raw.y, len = meta & 63u, shift = (meta >> 8) & 255u, cbits = (meta >> 16) & 255u;
-      const long long coef = (long long)(((uint64_t)raw.w << 32) | raw.z);
-      long long v;
-      int vbits;
-      if (len) {
-        undecided = undecided || !src.run_is_bits(wire, len);
-        v = (long long)src.run_value(wire, len);
-        vbits = (int)len;
-      } else {
-        const uint64_t x = src.get(wire);
-        undecided = undecided || (x & STG_TAG_BIG) != 0;
-        const uint64_t mag = x & STG_PAYLOAD;
-        v = (x & STG_TAG_NEG) ? -(long long)mag : (long long)mag;
-        vbits = fp_bitlen64(mag);
-      }
-      const int bits = (int)cbits + vbits;
-      if (bits <= 54) {
-        acc64 += (coef * v) << shift;
-      } else {
-        undecided = undecided || bits > 118;                    // <= 255 items of < 2^118 each stay below 2^126
-        acc128 += ((i128)coef * (i128)v) << shift;
-      }
+#pragma unroll 1
+  for (uint32_t k = 0; k < nt; k++) {                           // one loop body for the three linear combinations (code size)
+    const uint4 raw = nxt;
+    if (k + 1 < nt) nxt = __ldg(reinterpret_cast<const uint4 *>(it0 + (k + 1) * 32u));      // next item in flight (the tables live in L1 / L2)
+    uint32_t big;
+    const i128 term = fp_term(src, raw, undecided, big);
+    const uint32_t part = k < nA ? 0u : k < nAB ? 1u : 2u;
+    if (big) {                                                  // remember one field-valued operand: wire, sign, which side
+      nbig++;
+      big_wire = raw.x;
+      big_kind = big | (part << 4);
     }
-    L[part] = acc128 + (i128)acc64;
+    if (part == 0) L[0] += term; else if (part == 1) L[1] += term; else L[2] += term;
   }
   if (!active) return B3W_NO_ROW;
   bool holds;
+  if (nbig) {
+    // IsZero's  in * inv = 1 - out  and its kin: one factor IS a field-valued slot (unit coefficient, nothing else on its
+    // side), the other factor and the right-hand side are small integers -> one 64 x 256-bit product (fp_small_times_big)
+    const uint32_t side = big_kind >> 4;
+    const i128 other = side == 0 ? L[1] : L[0];
+    const bool lone = !undecided && nbig == 1 && (big_kind & 15u) <= 2u && side <= 1u && t.nA && t.nB && (side == 0 ? L[0] : L[1]) == 0 &&
+                      fp_bitlen128(other) <= 62 && fp_bitlen128(L[2]) <= 62;
+    if (lone) return fp_small_times_big(src, big_wire, (big_kind & 15u) == 2u ? -(long long)other : (long long)other, (long long)L[2])
+                         ? B3W_NO_ROW : P.row_ids[t.row_off + lane];
+    undecided = true;
+  }
   if (t.nA == 0 || t.nB == 0) {
     holds = !undecided && L[2] == 0;
   } else {
@@ -293,22 +453,18 @@ __device__ __noinline__ uint32_t fp_eval_residual(const CompactSrc &src, const r
 
 // every row of one instance from the compact copy (all threads of the CTA; each returns its own smallest violated row id).
 // Out of line: the streaming loop of the kernel keeps its registers for loads in flight.
-__device__ __noinline__ uint32_t fp_eval_rows(const CompactSrc &src, const fastprog_dev &P, const r1cs_tables_dev &T, uint32_t words) {
-  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  constexpr uint32_t NW = FPK_THREADS / 32;
+__device__ __noinline__ uint32_t fp_eval_rows(const CompactSrc &src, const fastprog_dev &P, const r1cs_tables_dev &T, uint32_t words,
+                                               uint32_t *next_tile /* shared, 0 at entry */) {
+  const uint32_t tid = threadIdx.x, lane = tid & 31u;
   const uint32_t *isbit = src.isbit;
   uint32_t bad = B3W_NO_ROW;
   const bool one_ok = src.get(0) == 1ull;                 // wire 0 holds the constant 1
   // ---- booleanity rows: the slots of the mask must be bits ----
-  for (uint32_t wd = tid; wd < words; wd += FPK_THREADS) {
+  for (uint32_t wd = tid; wd < words + P.n_vtiles; wd += FPK_THREADS) {     // (virtual bits: a word per group of definitions)
     const uint32_t need = __ldg(P.bool_mask + wd);
     uint32_t viol = need & ~isbit[wd];
     if (!one_ok) viol = need;                               // x (x - w0) = 0 with w0 != 1: decide every row exactly
-    while (viol) {
-      const uint32_t s = wd * 32u + (uint32_t)__ffs((int)viol) - 1u;
-      viol &= viol - 1u;
-      if (one_ok || !fp_bool_fr(src, s)) bad = min(bad, __ldg(P.bool_row + s));
-    }
+    if (viol) bad = min(bad, fp_bool_word_slow(src, P, wd, viol, one_ok));
   }
   // ---- XOR rows: runs of consecutive (x, y, o) triples ----
   for (uint32_t b = tid; b < P.n_xors; b += FPK_THREADS) {
@@ -316,18 +472,24 @@ __device__ __noinline__ uint32_t fp_eval_rows(const CompactSrc &src, const fastp
     const uint32_t len = e.w & 63u;
     const bool bits = src.run_is_bits(e.x, len) && src.run_is_bits(e.y, len) && src.run_is_bits(e.z, len);
     if (bits && (src.run_value(e.x, len) ^ src.run_value(e.y, len)) == src.run_value(e.z, len)) continue;
-    for (uint32_t j = 0; j < len; j++) {                    // some row of the run is violated or holds non-bits: row by row
-      const uint64_t vx = src.get(e.x + j), vy = src.get(e.y + j), vo = src.get(e.z + j);
-      const bool holds = (vx | vy | vo) < 2ull ? vo == (vx ^ vy) : fp_xor_fr(src, e.x + j, e.y + j, e.z + j);
-      if (!holds) bad = min(bad, __ldg(P.xor_ids + (e.w >> 6) + j));
-    }
+    bad = min(bad, fp_xor_run_slow(src, P, e));             // some row of the run is violated or holds non-bits: row by row
   }
-  // ---- every other compiled row: tiles of 32 rows, one per warp step ----
-  for (uint32_t t = warp; t < P.n_tiles; t += NW) {
+  // ---- every other compiled row: tiles of 32 rows, one per warp step, handed out dynamically (fp_compile orders them
+  // by decreasing cost: a warp that meets rows for the Fr path does not end up holding the CTA's barrier alone) ----
+  for (;;) {
+    uint32_t t = 0;
+    if (lane == 0) t = atomicAdd(next_tile, 1u);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= P.n_tiles) break;
     const uint4 h = __ldg(reinterpret_cast<const uint4 *>(P.tiles) + t);
     fp_tile tl;
     tl.item_off = h.x; tl.row_off = h.y;
     tl.nA = (uint16_t)(h.z & 0xFFFFu); tl.nB = (uint16_t)(h.z >> 16); tl.nC = (uint16_t)(h.w & 0xFFFFu); tl.rows = (uint16_t)(h.w >> 16);
+    if (tl.rows & FP_TILE_FAST) {
+      bool ok;
+      const uint32_t r = fp_eval_tile_fast(src, P, tl, lane, &ok);
+      if (__all_sync(0xffffffffu, ok)) { bad = min(bad, r); continue; }
+    }
     bad = min(bad, fp_eval_tile(src, P, tl, lane));
   }
   if (T.n_classes) bad = min(bad, fp_eval_residual(src, T, one_ok));
@@ -337,13 +499,14 @@ __device__ __noinline__ uint32_t fp_eval_rows(const CompactSrc &src, const fastp
 __global__ void __launch_bounds__(FPK_THREADS, FPK_CTAS_PER_SM)
 k_r1cs_check_fast(const uint8_t *__restrict__ wit, const uint32_t *__restrict__ list /* NULL, or {count, instances...}: see below */, uint64_t n,
                   uint32_t ws, uint32_t side_max /* entries of the side table in this launch's shared memory */, const fastprog_dev P,
+                  const fastprog_dev P0 /* the same rows compiled without virtual bits (= P when P has none) */,
                   const r1cs_tables_dev T /* residual rows */, const field_consts *__restrict__ F, uint8_t *__restrict__ status,
                   uint32_t *__restrict__ first_bad) {
   extern __shared__ __align__(16) uint8_t s_raw[];
-  const uint32_t words = (ws + 31u) >> 5, mw = words + 1u;                  // one padding word per map (field_of reads w + 1)
+  const uint32_t words = (ws + 31u) >> 5, mw = words + P.n_vtiles + 1u;      // virtual-bit words, one padding word per map (field_of reads w + 1)
   uint32_t *isbit = reinterpret_cast<uint32_t *>(s_raw), *bitval = isbit + mw, *rank = bitval + mw;
   uint64_t *side = reinterpret_cast<uint64_t *>(s_raw + (size_t)((3 * mw + 1) & ~1u) * 4);
-  __shared__ uint32_t s_bad, s_flags, s_nside;
+  __shared__ uint32_t s_bad, s_flags, s_nside, s_tile;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   constexpr uint32_t NW = FPK_THREADS / 32;
   // list != NULL: check the instances list[1 .. list[0]] (n is ignored), except those whose status says "Assert Failed."
@@ -355,7 +518,7 @@ k_r1cs_check_fast(const uint8_t *__restrict__ wit, const uint32_t *__restrict__ 
       continue;
     }
     __syncthreads();                                          // the previous instance's rows are done with the copy
-    if (tid == 0) { s_bad = B3W_NO_ROW; s_flags = 0; s_nside = 0; isbit[words] = 0xFFFFFFFFu; bitval[words] = 0u; }
+    if (tid == 0) { s_bad = B3W_NO_ROW; s_flags = 0; s_nside = 0; s_tile = 0; isbit[mw - 1u] = 0xFFFFFFFFu; bitval[mw - 1u] = 0u; }
     __syncthreads();
     const uint8_t *w = wit + i * (uint64_t)ws * 32;
     // ---- stream the witness once: lane = slot inside a 32-slot word, FPK_INFLIGHT words (1 KiB each) per warp in flight ----
@@ -397,7 +560,11 @@ k_r1cs_check_fast(const uint8_t *__restrict__ wit, const uint32_t *__restrict__ 
     uint32_t bad = B3W_NO_ROW;
     if (!(s_flags & 1u) && FPK_EXP == 0) {
       const CompactSrc src{isbit, bitval, rank, side, w, F, s_nside <= side_max};
-      bad = fp_eval_rows(src, P, T, words);
+      if (P.n_vtiles) {                                       // CTA-uniform
+        fp_eval_virtuals(src, P, words, isbit, bitval, &s_flags);
+        __syncthreads();
+      }
+      bad = (s_flags & 2u) ? fp_eval_rows(src, P0, T, words, &s_tile) : fp_eval_rows(src, P, T, words, &s_tile);
     }
     if (bad != B3W_NO_ROW) atomicMin(&s_bad, bad);
     __syncthreads();

@@ -189,9 +189,9 @@ static void r1cs_group(std::vector<r1cs_load_detail::row> &rows, r1cs_host_set &
 struct fastprog_host {
   std::vector<uint32_t> bool_mask, bool_row, xor_ids, row_ids;
   std::vector<fp_xor> xors;
-  std::vector<fp_tile> tiles;
+  std::vector<fp_tile> tiles, vtiles;    // vtiles: groups of 32 virtual-bit definitions (see fp_find_virtuals)
   std::vector<fp_item> items;
-  uint32_t n_rows = 0;
+  uint32_t n_rows = 0, n_fast_tiles = 0, n_virtual = 0;
 };
 
 namespace r1cs_load_detail {
@@ -267,19 +267,169 @@ static bool compile_lc(std::vector<term> lc, std::vector<fp_item> &out) {
 }
 }  // namespace r1cs_load_detail
 
+// ---- virtual bits ----------------------------------------------------------------------------------------------------
+// circom's O2 pass removes a signal per linear constraint: a bit b_k of a Num2Bits / Bits34 decomposition disappears and
+// every row that used it carries the linear combination  L = w - sum_{i != k} 2^i b_i  (= 2^k b_k) in its place -- a
+// booleanity row becomes  (L)(L - u) = 0  with 32 terms a side, an XOR row drags one or two copies of L along.  Evaluated
+// as they stand those rows are most of the stand-alone check's arithmetic for the O2 builds (and all of its 128-bit part).
+// fp_find_virtuals recognises the rows  (L + a0)(s L + b0) = 0, s = +-1, one root zero  ->  L is 0 or u: V = L / u is a
+// VIRTUAL BIT, evaluated once per witness into a bit slot past the witness's own (kernels_r1cs_fast.cuh, fp_eval_virtuals);
+// fp_reduce_lc then rewrites  mu L + rest  ->  (mu u) V + rest  in every other row, after which those rows are booleanity /
+// XOR / short rows like the rest of the system.  The rewriting is an identity whenever every L really is 0 or u; a witness
+// for which one is not (a violated row) is evaluated by the program compiled WITHOUT virtual bits, so the verdict and the
+// smallest violated row id never depend on this pass.
+namespace r1cs_load_detail {
+struct virt_def {
+  std::vector<term> L;      // sorted by wire, no wire 0, powers of two divided out, first coefficient positive
+  __int128 u;               // L is 0 or u
+  uint32_t row;             // index (not id) of the defining row
+  uint32_t anchor;          // position in L of a term with an odd coefficient
+};
+static int tz128(__int128 x) {
+  unsigned __int128 m = x < 0 ? (unsigned __int128)(-x) : (unsigned __int128)x;
+  int n = 0;
+  while (m && !(m & 1)) { n++; m >>= 1; }
+  return n;
+}
+static bool lc_small_sorted(const std::vector<term> &in, std::vector<term> &out, __int128 &c0) {
+  out.clear();
+  c0 = 0;
+  for (const term &T : in) {
+    if (!T.small) return false;
+    if (T.wire == 0) c0 += T.c;
+    else if (T.c != 0) out.push_back(T);
+  }
+  std::sort(out.begin(), out.end(), [](const term &a, const term &b) { return a.wire < b.wire; });
+  for (size_t i = 1; i < out.size(); i++)
+    if (out[i].wire == out[i - 1].wire) return false;        // a wire twice in one combination: not a form this pass meets
+  return true;
+}
+static bool find_virtual(const row &R, uint32_t row_index, virt_def &V) {
+  if (!R.part[2].empty() || R.part[0].size() < 3 || R.part[1].size() < 3) return false;
+  std::vector<term> A, B;
+  __int128 a0, b0;
+  if (!lc_small_sorted(R.part[0], A, a0) || !lc_small_sorted(R.part[1], B, b0) || A.size() != B.size() || A.size() < 2) return false;
+  const int sgn = B[0].c == A[0].c ? 1 : B[0].c == -A[0].c ? -1 : 0;
+  if (!sgn) return false;
+  for (size_t i = 0; i < A.size(); i++)
+    if (A[i].wire != B[i].wire || B[i].c != sgn * A[i].c) return false;
+  // (L + a0)(sgn L + b0) = 0:  L = -a0  or  L = -sgn b0
+  __int128 u;
+  if (a0 == 0 && b0 != 0) u = -sgn * b0;
+  else if (b0 == 0 && a0 != 0) u = -a0;
+  else return false;
+  int g = 127;
+  for (const term &T : A) g = std::min(g, tz128(T.c));
+  if (tz128(u) < g) return false;                              // L is a multiple of 2^g and u is not: L = 0 always; leave the row alone
+  const __int128 d = ((__int128)1 << g) * (A[0].c < 0 ? -1 : 1);
+  V.L = A;
+  for (term &T : V.L) T.c /= d;
+  V.u = u / d;
+  V.row = row_index;
+  V.anchor = 0;
+  while (V.anchor < V.L.size() && !(V.L[V.anchor].c & 1)) V.anchor++;
+  return V.anchor < V.L.size();
+}
+// rewrite every  mu * L_j  inside `lc` as  (mu u_j) * V_j  (V_j = wire vbase + j); returns true when something changed
+static bool reduce_lc(std::vector<term> &lc, const std::vector<virt_def> &virt, const std::multimap<uint32_t, uint32_t> &by_anchor, uint32_t vbase) {
+  bool changed = false;
+  for (bool again = true; again;) {
+    again = false;
+    std::map<uint32_t, __int128> m;
+    for (const term &T : lc) {
+      if (!T.small) return changed;
+      m[T.wire] += T.c;
+    }
+    for (const auto &kv : m) {
+      auto range = by_anchor.equal_range(kv.first);
+      for (auto it = range.first; it != range.second && !again; ++it) {
+        const virt_def &V = virt[it->second];
+        const __int128 ca = V.L[V.anchor].c, mu = kv.second / ca;
+        if (mu == 0 || mu * ca != kv.second || bitlen128(mu) + bitlen128(V.u) > 118) continue;
+        bool all = true;
+        for (const term &T : V.L) {
+          auto f = m.find(T.wire);
+          all = all && f != m.end() && bitlen128(mu) + bitlen128(T.c) < 120 && f->second == mu * T.c;
+        }
+        if (!all) continue;
+        for (const term &T : V.L) m.erase(T.wire);
+        m[vbase + it->second] += mu * V.u;
+        lc.clear();
+        for (const auto &e : m)
+          if (e.second != 0) {
+            term T;
+            T.wire = e.first; T.small = true; T.c = e.second; T.f = fr_zero();
+            lc.push_back(T);
+          }
+        changed = again = true;
+      }
+      if (again) break;
+    }
+  }
+  return changed;
+}
+}  // namespace r1cs_load_detail
+
 // Compiles what it can; taken[i] tells which rows are now covered by the program (the others go to r1cs_group).
-static void fp_compile(const std::vector<r1cs_load_detail::row> &rows, uint32_t ws, fastprog_host &fp, std::vector<char> &taken) {
+static void fp_compile(const std::vector<r1cs_load_detail::row> &rows, uint32_t ws, fastprog_host &fp, std::vector<char> &taken,
+                       bool with_virtuals = false) {
   using namespace r1cs_load_detail;
-  const uint32_t words = (ws + 31u) >> 5;
-  fp.bool_mask.assign(words + 1, 0u);
-  fp.bool_row.assign((size_t)words * 32, 0xFFFFFFFFu);
+  const uint32_t words = (ws + 31u) >> 5, vbase = words * 32u;
   taken.assign(rows.size(), 0);
+  auto compile_row = [](const row &R, std::vector<fp_item> &it, uint32_t n[3]) {
+    it.clear();
+    for (int part = 0; part < 3; part++) {
+      std::vector<fp_item> tmp;
+      if (!compile_lc(R.part[part], tmp)) return false;
+      it.insert(it.end(), tmp.begin(), tmp.end());
+      n[part] = (uint32_t)tmp.size();
+    }
+    return true;
+  };
+  // virtual bits: the rows that define them, and their compiled linear combinations
+  std::vector<virt_def> virt;
+  std::vector<std::vector<fp_item>> virt_items;
+  std::vector<int> def_of(rows.size(), -1);
+  std::multimap<uint32_t, uint32_t> by_anchor;
+  if (with_virtuals)
+    for (size_t i = 0; i < rows.size(); i++) {
+      virt_def V;
+      std::vector<fp_item> it, li;
+      uint32_t n[3];
+      uint32_t x;
+      if (is_bool_row(rows[i], x) || !find_virtual(rows[i], (uint32_t)i, V)) continue;
+      if (!compile_row(rows[i], it, n) || !compile_lc(V.L, li) || li.empty() || li.size() > 16 || bitlen128(V.u) > 118) continue;
+      if (bitlen128(V.u) - tz128(V.u) > 61) continue;            // the unit is stored as (62-bit mantissa) << shift
+      def_of[i] = (int)virt.size();
+      by_anchor.insert({V.L[V.anchor].wire, (uint32_t)virt.size()});
+      virt.push_back(std::move(V));
+      virt_items.push_back(std::move(li));
+    }
+  const uint32_t nvw = ((uint32_t)virt.size() + 31u) >> 5;
+  fp.n_virtual = (uint32_t)virt.size();
+  fp.bool_mask.assign(words + nvw + 1, 0u);
+  fp.bool_row.assign((size_t)(words + nvw) * 32, 0xFFFFFFFFu);
   struct xr { uint32_t x, y, o, id; };
   std::vector<xr> xs;
   struct gen { std::vector<fp_item> it; uint32_t n[3]; uint32_t id; };
   std::vector<gen> gens;
   for (size_t i = 0; i < rows.size(); i++) {
-    const row &R = rows[i];
+    if (def_of[i] >= 0) { taken[i] = 1; continue; }            // holds by construction once the virtual bit is valid
+    const row *Rp = &rows[i];
+    row reduced;
+    if (!virt.empty() && (rows[i].part[0].size() > 2 || rows[i].part[1].size() > 2 || rows[i].part[2].size() > 2)) {
+      reduced = rows[i];
+      bool changed = false;
+      for (int part = 0; part < 3; part++) changed = reduce_lc(reduced.part[part], virt, by_anchor, vbase) || changed;
+      if (changed) {
+        std::vector<fp_item> it;
+        uint32_t n[3];
+        if (!compile_row(rows[i], it, n)) continue;            // the fallback program must cover the same rows: leave it to the general evaluator
+        if (reduced.part[0].empty() || reduced.part[1].empty()) { reduced.part[0].clear(); reduced.part[1].clear(); }
+        Rp = &reduced;
+      }
+    }
+    const row &R = *Rp;
     uint32_t x = 0, y = 0, o = 0;
     if (is_bool_row(R, x)) {
       fp.bool_mask[x >> 5] |= 1u << (x & 31u);
@@ -291,15 +441,36 @@ static void fp_compile(const std::vector<r1cs_load_detail::row> &rows, uint32_t 
     } else {
       gen g;
       g.id = R.id;
-      bool ok = true;
-      for (int part = 0; part < 3 && ok; part++) {
-        std::vector<fp_item> tmp;
-        ok = compile_lc(R.part[part], tmp);
-        g.it.insert(g.it.end(), tmp.begin(), tmp.end());
-        g.n[part] = (uint32_t)tmp.size();
-      }
+      bool ok = compile_row(R, g.it, g.n);
+      if (!ok && Rp == &reduced) ok = compile_row(rows[i], g.it, g.n);
       if (ok) { gens.push_back(std::move(g)); taken[i] = 1; }
     }
+  }
+  // virtual-bit definitions -> groups of 32 (lane = definition): its items, item-major, padded to the group's longest, then
+  // one more item holding the unit u as coef << shift
+  for (size_t j = 0; j < virt.size(); j += 32) {
+    const size_t cnt = std::min<size_t>(32, virt.size() - j);
+    size_t ni = 0;
+    for (size_t l = 0; l < cnt; l++) ni = std::max(ni, virt_items[j + l].size());
+    fp_tile t;
+    t.item_off = (uint32_t)fp.items.size();
+    t.row_off = (uint32_t)fp.row_ids.size();
+    t.nA = (uint16_t)ni; t.nB = 0; t.nC = 0; t.rows = (uint16_t)cnt;
+    const fp_item pad = {0u, 0u, 0ll};
+    for (size_t k = 0; k < ni; k++)
+      for (size_t l = 0; l < 32; l++) fp.items.push_back(l < cnt && k < virt_items[j + l].size() ? virt_items[j + l][k] : pad);
+    for (size_t l = 0; l < 32; l++) {
+      fp_item ui = pad;
+      if (l < cnt) {
+        __int128 u = virt[j + l].u;                            // (62-bit mantissa) << shift, exactly: checked when the row was picked
+        uint32_t shift = 0;
+        while (bitlen128(u) > 61) { u /= 2; shift++; }
+        ui.wire = 0; ui.meta = shift << 8; ui.coef = (long long)u;
+      }
+      fp.items.push_back(ui);
+    }
+    for (size_t l = 0; l < 32; l++) fp.row_ids.push_back(l < cnt ? rows[virt[j + l].row].id : 0xFFFFFFFFu);
+    fp.vtiles.push_back(t);
   }
   // XOR rows -> runs
   std::sort(xs.begin(), xs.end(), [](const xr &a, const xr &b) { return a.x != b.x ? a.x < b.x : a.id < b.id; });
@@ -319,20 +490,40 @@ static void fp_compile(const std::vector<r1cs_load_detail::row> &rows, uint32_t 
     if (a.n[1] != b.n[1]) return a.n[1] < b.n[1];
     return a.n[2] < b.n[2];
   });
+  struct tile_plan { size_t first, cnt; bool fast; uint32_t cost; };
+  std::vector<tile_plan> plan;
   for (size_t j = 0; j < gens.size();) {
     size_t cnt = 1;
     while (j + cnt < gens.size() && cnt < 32 && gens[j + cnt].n[0] == gens[j].n[0] && gens[j + cnt].n[1] == gens[j].n[1] && gens[j + cnt].n[2] == gens[j].n[2]) cnt++;
+    // FP_TILE_FAST: 64-bit sums are exact when every scalar is below 2^FP_FAST_VBITS and every run lies over bits
+    bool fast = gens[j].n[0] <= 16 && gens[j].n[1] <= 16 && gens[j].n[2] <= 16, scalar_product = gens[j].n[0] && gens[j].n[1];
+    for (size_t l = 0; l < cnt; l++)
+      for (const fp_item &it : gens[j + l].it) {
+        const uint32_t len = it.meta & 63u, cbits = (it.meta >> 16) & 255u;
+        fast = fast && cbits + (len ? len : it.wire >= vbase ? 1u : (uint32_t)FP_FAST_VBITS) <= 57;      // a virtual wire holds a bit
+      }
+    for (uint32_t k = 0; k < gens[j].n[0] + gens[j].n[1]; k++) scalar_product = scalar_product && (gens[j].it[k].meta & 63u) == 0;
+    // cost estimate for the hand-out order: items, dearer on the bounds-tracking path; products of plain wires are where
+    // field-valued operands turn up (IsZero's in * inv), i.e. rows that may need the Fr evaluator
+    const uint32_t ni = gens[j].n[0] + gens[j].n[1] + gens[j].n[2];
+    plan.push_back(tile_plan{j, cnt, fast, ni * (fast ? 2u : 5u) + (scalar_product ? 64u : 0u)});
+    j += cnt;
+  }
+  std::stable_sort(plan.begin(), plan.end(), [](const tile_plan &a, const tile_plan &b) { return a.cost > b.cost; });
+  for (const tile_plan &tp : plan) {
+    const size_t j = tp.first, cnt = tp.cnt;
     fp_tile t;
     t.item_off = (uint32_t)fp.items.size();
     t.row_off = (uint32_t)fp.row_ids.size();
-    t.nA = (uint16_t)gens[j].n[0]; t.nB = (uint16_t)gens[j].n[1]; t.nC = (uint16_t)gens[j].n[2]; t.rows = (uint16_t)cnt;
+    t.nA = (uint16_t)gens[j].n[0]; t.nB = (uint16_t)gens[j].n[1]; t.nC = (uint16_t)gens[j].n[2];
+    t.rows = (uint16_t)(cnt | (tp.fast ? FP_TILE_FAST : 0u));
     const uint32_t ni = gens[j].n[0] + gens[j].n[1] + gens[j].n[2];
     const fp_item pad = {0u, 0u, 0ll};
     for (uint32_t k = 0; k < ni; k++)
       for (uint32_t l = 0; l < 32; l++) fp.items.push_back(l < cnt ? gens[j + l].it[k] : pad);
     for (uint32_t l = 0; l < 32; l++) fp.row_ids.push_back(l < cnt ? gens[j + l].id : 0xFFFFFFFFu);
     fp.tiles.push_back(t);
-    j += cnt;
+    fp.n_fast_tiles += tp.fast ? 1u : 0u;
   }
   for (char c : taken) fp.n_rows += c ? 1u : 0u;
 }

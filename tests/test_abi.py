@@ -173,7 +173,7 @@ def test_builtin_systems_compile_completely(built):
     """fp_compile (host-only): every row of the four built-in constraint systems is covered by the compiled program of the
     stand-alone checker -- booleanity masks, XOR runs, row tiles -- so the general evaluator has nothing left to do"""
     L = pkg.lib()
-    want = {0: (24544, 464), 1: (23743, 464), 2: (23743, 464), 3: (25064, 464)}
+    want = {0: (24544, 464), 1: (23743, 812), 2: (23743, 812), 3: (25064, 464)}      # O2: XOR rows over virtual bits split runs
     for circuit, (rows, xor_runs) in want.items():
         v = [C.c_uint32() for _ in range(5)]
         assert L.b3w_r1cs_compile_stats(circuit, *[C.byref(x) for x in v]) == 0

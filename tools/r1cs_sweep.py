@@ -37,7 +37,7 @@ for name, gen in (("blake3_compression", lcg_compression_inputs), ("blake3_nova_
     wc.device_free(ptr); del d_out; wc.close()
 print(json.dumps(out), flush=True)
 ''' % ROOT
-libs = [None] + sorted(glob.glob(os.path.join(ROOT, "build_exp", "libb3w_inf*.so")))
+libs = [None] + sorted(glob.glob(os.path.join(ROOT, "build_exp", "libb3w_*.so")))
 for lib in libs:
     env = dict(os.environ)
     if lib:
