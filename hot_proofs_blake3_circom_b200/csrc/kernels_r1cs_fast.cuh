@@ -14,25 +14,34 @@
 //     bit-field extractions from the value map and one compare;
 //   * every other row -> a short list of ITEMS per linear combination: a scalar wire, or a RUN of up to 32 consecutive
 //     bit wires whose coefficients double (sum 2^i b_i: a Num2Bits / Bits34 recomposition is one or two items instead of
-//     33-35 terms), stored item-major in tiles of 32 rows so that a warp's loads coalesce and its trip counts are uniform.
+//     33-35 terms), stored item-major in tiles of 32 rows so that a warp's loads coalesce and its trip counts are uniform;
+//     tiles whose terms provably stay below 2^57 (FP_TILE_FAST) are summed in plain 64-bit arithmetic; warps take tiles
+//     from a shared counter, dearest first;
+//   * VIRTUAL BITS: where circom's O2 pass substituted a bit by w - sum 2^i b_i, that combination is evaluated once per
+//     witness into a bit slot of its own and the rows that carried it become booleanity / XOR / short rows (r1cs_load.h);
+//   * a product with ONE field-valued factor (IsZero's in * inv = 1 - out) is one 64 x 256-bit multiply-reduce.
 // Arithmetic is exact: signed 128-bit integers with a bit-length bound per term and per product; a row that cannot be
 // decided that way (a genuine field element such as IsZero's inverse, a run over slots that are not all bits, a bound
 // exceeded) is re-evaluated in Fr (Montgomery) by the same lane.  Rows the compiler does not take (coefficients that are
 // arbitrary field elements) stay with the general class/block evaluator of r1cs_rows.cuh as a RESIDUAL set; the built-in
 // systems compile completely.  Any satisfied system is accepted and the smallest violated row id reported, whatever the
 // witness holds; a slot >= p is reported as B3W_NOT_CANONICAL.
+// The kernel's code is kept SMALL on purpose (cold paths out of line, one loop body for A, B and C): the four-to-eight
+// CTAs of an SM are in different phases, and once their hot code exceeded the 32 KB instruction cache ncu showed 6.6
+// warps per issue waiting for instructions (profiles/r02m).
 // History (profiles/): 8 bytes per slot, one CTA per SM 1.65 M witnesses/s (compression, 24 544 rows) -> compact copy +
-// row blocks 2.33 M/s (0.27 of the read roofline; row arithmetic issue-bound) -> this file.
+// row blocks 2.33 M/s (0.27 of the read roofline; row arithmetic issue-bound) -> compiled program 7.8 M/s (nova O2 5.1)
+// -> virtual bits, fast tiles, dynamic hand-out, 128-thread CTAs: 8.2 M/s (0.96), nova O2 7.9 M/s (0.90), O1 6.8 (0.82).
 #pragma once
 
 #ifndef FPK_EXP
 #define FPK_EXP 0                 /* experiment builds only: 1 = stream + classify, no rows */
 #endif
 #ifndef FPK_THREADS
-#define FPK_THREADS 256
+#define FPK_THREADS 128           /* 128 x 8 CTAs per SM: same warps as 256 x 4, the phases of more instances interleave (profiles/r02t) */
 #endif
 #ifndef FPK_CTAS_PER_SM
-#define FPK_CTAS_PER_SM 4
+#define FPK_CTAS_PER_SM 8
 #endif
 #ifndef FPK_INFLIGHT
 #define FPK_INFLIGHT 4            /* 256-bit loads per lane in flight in the streaming loop */

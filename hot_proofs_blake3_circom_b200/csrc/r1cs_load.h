@@ -490,38 +490,67 @@ static void fp_compile(const std::vector<r1cs_load_detail::row> &rows, uint32_t 
     if (a.n[1] != b.n[1]) return a.n[1] < b.n[1];
     return a.n[2] < b.n[2];
   });
-  struct tile_plan { size_t first, cnt; bool fast; uint32_t cost; };
-  std::vector<tile_plan> plan;
+  struct tile_plan { std::vector<size_t> rows; uint32_t n[3]; bool fast; uint32_t cost; };
+  std::vector<tile_plan> plan, small;
   for (size_t j = 0; j < gens.size();) {
     size_t cnt = 1;
     while (j + cnt < gens.size() && cnt < 32 && gens[j + cnt].n[0] == gens[j].n[0] && gens[j + cnt].n[1] == gens[j].n[1] && gens[j + cnt].n[2] == gens[j].n[2]) cnt++;
+    tile_plan tp;
+    for (size_t l = 0; l < cnt; l++) tp.rows.push_back(j + l);
+    for (int q = 0; q < 3; q++) tp.n[q] = gens[j].n[q];
+    (cnt <= 4 ? small : plan).push_back(std::move(tp));
+    j += cnt;
+  }
+  // shapes with a handful of rows (the one-off rows of the nova step logic) would cost a warp pass each: they share
+  // tiles, every row padded with zero items to the tile's longest A, B and C
+  std::stable_sort(small.begin(), small.end(), [](const tile_plan &a, const tile_plan &b) { return a.n[0] + a.n[1] + a.n[2] > b.n[0] + b.n[1] + b.n[2]; });
+  for (size_t j = 0; j < small.size();) {
+    tile_plan tp = small[j++];
+    while (j < small.size() && tp.rows.size() + small[j].rows.size() <= 32) {
+      for (int q = 0; q < 3; q++) tp.n[q] = std::max(tp.n[q], small[j].n[q]);
+      tp.rows.insert(tp.rows.end(), small[j].rows.begin(), small[j].rows.end());
+      j++;
+    }
+    plan.push_back(std::move(tp));
+  }
+  for (tile_plan &tp : plan) {
     // FP_TILE_FAST: 64-bit sums are exact when every scalar is below 2^FP_FAST_VBITS and every run lies over bits
-    bool fast = gens[j].n[0] <= 16 && gens[j].n[1] <= 16 && gens[j].n[2] <= 16, scalar_product = gens[j].n[0] && gens[j].n[1];
-    for (size_t l = 0; l < cnt; l++)
-      for (const fp_item &it : gens[j + l].it) {
+    bool fast = tp.n[0] <= 16 && tp.n[1] <= 16 && tp.n[2] <= 16, scalar_product = false;
+    for (size_t r : tp.rows) {
+      for (const fp_item &it : gens[r].it) {
         const uint32_t len = it.meta & 63u, cbits = (it.meta >> 16) & 255u;
         fast = fast && cbits + (len ? len : it.wire >= vbase ? 1u : (uint32_t)FP_FAST_VBITS) <= 57;      // a virtual wire holds a bit
       }
-    for (uint32_t k = 0; k < gens[j].n[0] + gens[j].n[1]; k++) scalar_product = scalar_product && (gens[j].it[k].meta & 63u) == 0;
+      bool sp = gens[r].n[0] && gens[r].n[1];
+      for (uint32_t k = 0; k < gens[r].n[0] + gens[r].n[1]; k++) sp = sp && (gens[r].it[k].meta & 63u) == 0;
+      scalar_product = scalar_product || sp;
+    }
     // cost estimate for the hand-out order: items, dearer on the bounds-tracking path; products of plain wires are where
     // field-valued operands turn up (IsZero's in * inv), i.e. rows that may need the Fr evaluator
-    const uint32_t ni = gens[j].n[0] + gens[j].n[1] + gens[j].n[2];
-    plan.push_back(tile_plan{j, cnt, fast, ni * (fast ? 2u : 5u) + (scalar_product ? 64u : 0u)});
-    j += cnt;
+    tp.fast = fast;
+    tp.cost = (tp.n[0] + tp.n[1] + tp.n[2]) * (fast ? 2u : 5u) + (scalar_product ? 64u : 0u);
   }
   std::stable_sort(plan.begin(), plan.end(), [](const tile_plan &a, const tile_plan &b) { return a.cost > b.cost; });
   for (const tile_plan &tp : plan) {
-    const size_t j = tp.first, cnt = tp.cnt;
+    const size_t cnt = tp.rows.size();
     fp_tile t;
     t.item_off = (uint32_t)fp.items.size();
     t.row_off = (uint32_t)fp.row_ids.size();
-    t.nA = (uint16_t)gens[j].n[0]; t.nB = (uint16_t)gens[j].n[1]; t.nC = (uint16_t)gens[j].n[2];
+    t.nA = (uint16_t)tp.n[0]; t.nB = (uint16_t)tp.n[1]; t.nC = (uint16_t)tp.n[2];
     t.rows = (uint16_t)(cnt | (tp.fast ? FP_TILE_FAST : 0u));
-    const uint32_t ni = gens[j].n[0] + gens[j].n[1] + gens[j].n[2];
     const fp_item pad = {0u, 0u, 0ll};
-    for (uint32_t k = 0; k < ni; k++)
-      for (uint32_t l = 0; l < 32; l++) fp.items.push_back(l < cnt ? gens[j + l].it[k] : pad);
-    for (uint32_t l = 0; l < 32; l++) fp.row_ids.push_back(l < cnt ? gens[j + l].id : 0xFFFFFFFFu);
+    for (int q = 0; q < 3; q++)
+      for (uint32_t k = 0; k < tp.n[q]; k++)
+        for (uint32_t l = 0; l < 32; l++) {
+          fp_item it = pad;
+          if (l < cnt) {
+            const gen &g = gens[tp.rows[l]];
+            const uint32_t base = q == 0 ? 0u : q == 1 ? g.n[0] : g.n[0] + g.n[1];
+            if (k < g.n[q]) it = g.it[base + k];
+          }
+          fp.items.push_back(it);
+        }
+    for (uint32_t l = 0; l < 32; l++) fp.row_ids.push_back(l < cnt ? gens[tp.rows[l]].id : 0xFFFFFFFFu);
     fp.tiles.push_back(t);
     fp.n_fast_tiles += tp.fast ? 1u : 0u;
   }

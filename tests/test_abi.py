@@ -179,7 +179,7 @@ def test_builtin_systems_compile_completely(built):
         assert L.b3w_r1cs_compile_stats(circuit, *[C.byref(x) for x in v]) == 0
         n_rows, n_compiled, n_xor, n_tiles, n_items = (x.value for x in v)
         assert (n_rows, n_compiled, n_xor) == (rows, rows, xor_runs), (circuit, n_rows, n_compiled, n_xor)
-        assert 30 < n_tiles < 100 and n_items < 20000
+        assert 15 < n_tiles < 100 and n_items < 20000
 
 
 def test_extras_and_timing_structs_match_the_header():

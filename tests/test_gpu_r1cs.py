@@ -204,10 +204,13 @@ def test_loaded_r1cs_accepts_valid_and_rejects_corruption(built, exported, name,
     # the reported row really is violated by that witness (host re-evaluation of the file's row)
     import export_r1cs as ex
     r = ex.read_r1cs(exported[variant])
-    for i in (0, 1, 2, 3, 100):
+    # ... and it is the FIRST violated row of the file (the O2 system is evaluated through virtual bits, a corrupted
+    # witness through the plainly compiled program: the verdict must not depend on which)
+    for i in (0, 1, 2, 3, 100, 101, 102, 200, 255):
         body = d_out.view(n, ws * 32)[i].cpu().numpy().tobytes()
         wi = [int.from_bytes(body[32 * k:32 * k + 32], "little") for k in range(ws)]
         assert ex.check_rows([r["rows"][int(bad[i])]], wi, r["prime"]) is not None
+        assert ex.check_rows(r["rows"][:int(bad[i])], wi, r["prime"]) is None, "row %d is not the first violated row of instance %d" % (bad[i], i)
     # a non-canonical slot (>= p) is reported as such
     w[idx, sl, 0] -= 1
     w[7, 5, :] = 0xFF
