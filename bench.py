@@ -307,14 +307,15 @@ def run_own(args, rank, world, local_rank):
     if compressible:
         step(out_c)
 
-    def check_rate(ptr):
+    def check_rate(ptr, calc=None):
+        calc = calc or wc
         for _ in range(2):
-            wc.r1cs_check_device(ptr, n_chk, d_st.data_ptr(), d_bad.data_ptr(), stream)
+            calc.r1cs_check_device(ptr, n_chk, d_st.data_ptr(), d_bad.data_ptr(), stream)
         torch.cuda.synchronize()
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         c0.record()
         for _ in range(5):
-            wc.r1cs_check_device(ptr, n_chk, d_st.data_ptr(), d_bad.data_ptr(), stream)
+            calc.r1cs_check_device(ptr, n_chk, d_st.data_ptr(), d_bad.data_ptr(), stream)
         c1.record()
         torch.cuda.synchronize()
         assert int(d_st[:n_chk].max()) == 0
@@ -325,6 +326,22 @@ def run_own(args, rank, world, local_rank):
         wc.device_free(out_c)
     del d_out
     torch.cuda.empty_cache()
+    # ... and of the nova step circuits' witnesses: the O2 build rust_fold loads (blake3_nova_pasta, Pallas Fr) and the O1 build
+    chk_nova = {}
+    from hot_proofs_blake3_circom_b200.inputs import splitmix_nova_inputs
+    for nm in ("blake3_nova_pasta", "blake3_nova_o1"):
+        wn = pkg.builder(nm, device=local_rank)
+        dn_in = torch.from_numpy(splitmix_nova_inputs(n_chk, first=rank * n_chk).view(np.int32)).cuda()
+        dn_out = torch.empty(n_chk * wn.witnessSize * 32, dtype=torch.uint8, device="cuda")
+        wn.witness_batch_device(dn_in.data_ptr(), n_chk, dn_out.data_ptr(), d_st.data_ptr(), 0, stream)
+        ms = check_rate(dn_out.data_ptr(), wn)
+        nb = n_chk * wn.witnessSize * 32
+        info = wn.r1cs_program_info()
+        chk_nova[nm] = {"value": world * n_chk / (ms / 1e3), "unit": "witnesses/s", "kernel_ms": ms, "rows": info["rows"], "witness_bytes": wn.witnessSize * 32,
+                        "read_gbs": nb / ms / 1e6, "frac_of_measured_hbm_peak": nb / ms / 1e6 / measured_peaks()[0]}
+        del dn_out, dn_in
+        wn.close()
+        torch.cuda.empty_cache()
 
     # --- e2e: the C ABI host-buffer calls (what the N-API addon / a user calls) ---------------------
     avail = 0
@@ -531,7 +548,8 @@ def run_own(args, rank, world, local_rank):
                                 "instances": n_chk, "value": world * n_chk / (chk_hbm_ms / 1e3), "unit": "witnesses/s", "kernel_ms": chk_hbm_ms,
                                 "read_gbs": n_chk * WIT_BYTES / chk_hbm_ms / 1e6, "frac_of_measured_hbm_peak": n_chk * WIT_BYTES / chk_hbm_ms / 1e6 / peak,
                                 "compressible_buffer": None if chk_hbm_c_ms is None else {
-                                    "value": world * n_chk / (chk_hbm_c_ms / 1e3), "kernel_ms": chk_hbm_c_ms, "read_gbs": n_chk * WIT_BYTES / chk_hbm_c_ms / 1e6}},
+                                    "value": world * n_chk / (chk_hbm_c_ms / 1e3), "kernel_ms": chk_hbm_c_ms, "read_gbs": n_chk * WIT_BYTES / chk_hbm_c_ms / 1e6},
+                                "nova": chk_nova},
         "config4": cfg4, "config5": cfg5,
         "gpu_launches": gpu_launches, "clocks": clocks}
     if compressible:

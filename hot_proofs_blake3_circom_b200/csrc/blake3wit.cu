@@ -924,7 +924,7 @@ extern "C" int b3w_r1cs_program_info(b3w_ctx *c, uint32_t *n_rows, uint32_t *n_c
 }
 
 // host-only: what fp_compile makes of a circuit's built-in system (needs no GPU; tests/test_abi.py pins the numbers)
-static int b3w_r1cs_compile_stats_impl(uint32_t circuit, uint32_t *n_rows, uint32_t *n_compiled, uint32_t *n_xor_runs, uint32_t *n_tiles, uint32_t *n_items) {
+static int b3w_r1cs_compile_stats_impl(uint32_t circuit, uint32_t *out, uint32_t n_out) {
   const circuit_def *d = find_def(circuit);
   if (!d) return B3W_ERR_UNSUPPORTED;
   std::vector<r1cs_load_detail::row> rows;
@@ -932,15 +932,24 @@ static int b3w_r1cs_compile_stats_impl(uint32_t circuit, uint32_t *n_rows, uint3
   fastprog_host fp, fp0;
   std::vector<char> taken;
   compile_programs(rows, d->ws, fp, fp0, taken);
-  if (n_rows) *n_rows = (uint32_t)rows.size();
-  if (n_compiled) *n_compiled = fp.n_rows;
-  if (n_xor_runs) *n_xor_runs = (uint32_t)fp.xors.size();
-  if (n_tiles) *n_tiles = (uint32_t)fp.tiles.size();
-  if (n_items) *n_items = (uint32_t)fp.items.size();
+  const uint32_t v[9] = {(uint32_t)rows.size(), fp.n_rows, (uint32_t)fp.xors.size(), (uint32_t)fp.tiles.size(), (uint32_t)fp.items.size(),
+                         fp.n_virtual, fp.n_fast_tiles, (uint32_t)fp0.tiles.size(), (uint32_t)fp0.items.size()};
+  for (uint32_t i = 0; i < n_out && i < 9; i++) out[i] = v[i];
   return B3W_OK;
 }
 extern "C" int b3w_r1cs_compile_stats(uint32_t circuit, uint32_t *n_rows, uint32_t *n_compiled, uint32_t *n_xor_runs, uint32_t *n_tiles, uint32_t *n_items) {
-  return guarded("b3w_r1cs_compile_stats", [&]() { return b3w_r1cs_compile_stats_impl(circuit, n_rows, n_compiled, n_xor_runs, n_tiles, n_items); });
+  uint32_t v[5] = {0, 0, 0, 0, 0};
+  const int rc = guarded("b3w_r1cs_compile_stats", [&]() { return b3w_r1cs_compile_stats_impl(circuit, v, 5); });
+  if (n_rows) *n_rows = v[0];
+  if (n_compiled) *n_compiled = v[1];
+  if (n_xor_runs) *n_xor_runs = v[2];
+  if (n_tiles) *n_tiles = v[3];
+  if (n_items) *n_items = v[4];
+  return rc;
+}
+extern "C" int b3w_r1cs_compile_stats_ex(uint32_t circuit, uint32_t *out, uint32_t n_out) {
+  if (!out) return fail(B3W_ERR_INVALID, "b3w_r1cs_compile_stats_ex: null argument");
+  return guarded("b3w_r1cs_compile_stats_ex", [&]() { return b3w_r1cs_compile_stats_impl(circuit, out, n_out); });
 }
 
 // Replace the built-in slot-space row set of this context by the constraint system of an iden3 `.r1cs` file: the

@@ -241,6 +241,11 @@ int b3w_r1cs_program_info(b3w_ctx *ctx, uint32_t *n_rows, uint32_t *n_compiled, 
 /* ditto for a circuit's BUILT-IN system, host-only (needs no GPU); n_items = 16-byte items of the row tiles. */
 int b3w_r1cs_compile_stats(uint32_t circuit, uint32_t *n_rows, uint32_t *n_compiled, uint32_t *n_xor_runs, uint32_t *n_tiles,
                            uint32_t *n_items);
+/* the same and more, as an array (the first n_out of): rows, compiled rows, XOR runs, row tiles, items, VIRTUAL BITS (linear
+ * combinations that circom's O2 pass put in place of a bit, evaluated once per witness into a bit slot of their own --
+ * 0 for the O1-form systems), tiles summed in plain 64-bit arithmetic, and tiles / items of the program compiled without
+ * virtual bits, which a witness whose virtual bits are not bits is evaluated with (0 / 0 when there are none). */
+int b3w_r1cs_compile_stats_ex(uint32_t circuit, uint32_t *out, uint32_t n_out);
 
 /* rows / non-zero terms of the circuit's template-level constraint system in O1 form
  * (blake3_compression: 24 544 rows = 23 376 quadratic + 1 168 linear; nova: 25 064) */

@@ -180,6 +180,17 @@ def test_builtin_systems_compile_completely(built):
         n_rows, n_compiled, n_xor, n_tiles, n_items = (x.value for x in v)
         assert (n_rows, n_compiled, n_xor) == (rows, rows, xor_runs), (circuit, n_rows, n_compiled, n_xor)
         assert 15 < n_tiles < 100 and n_items < 20000
+        ex = (C.c_uint32 * 9)()
+        assert L.b3w_r1cs_compile_stats_ex(circuit, ex, 9) == 0
+        assert list(ex[:5]) == [n_rows, n_compiled, n_xor, n_tiles, n_items]
+        n_virtual, n_fast, plain_tiles, plain_items = ex[5:9]
+        if circuit in (1, 2):
+            # the O2-form system: every bit circom substituted by a linear combination is a virtual bit; the rows that carried
+            # them are booleanity / XOR / short rows now, and nearly every tile sums in 64 bits; the plainly compiled program
+            # (the fall-back for witnesses whose virtual bits are not bits) has 2.6 times the tiles
+            assert n_virtual == 701 and plain_tiles == 55 and plain_items > 1.5 * n_items and n_fast >= n_tiles - 8
+        else:
+            assert (n_virtual, plain_tiles, plain_items) == (0, 0, 0) and n_fast >= n_tiles - 8
 
 
 def test_extras_and_timing_structs_match_the_header():
