@@ -51,6 +51,7 @@
 struct fp_item {                  // 16 bytes
   uint32_t wire;                  // scalar: the wire; run: its first wire
   uint32_t meta;                  // bits 0..5 run length (0 = scalar, 2..32 = run) | 8..15 shift | 16..23 bit length of |coef| + shift
+                                  // | 24..29 scalars: log2 bound of the value the 64-bit tile path assumes (1 or FP_FAST_VBITS)
   long long coef;                 // value contributes  (coef * v) << shift;  a run's v = sum 2^j bit_j
 };
 struct fp_tile {                  // 32 rows of identical item counts; lane = row
@@ -340,7 +341,7 @@ __device__ __forceinline__ uint32_t fp_eval_tile_fast(const CompactSrc &src, con
       v = src.run_value(wire, len);
     } else {
       v = src.get(wire);
-      ok = ok && (v >> FP_FAST_VBITS) == 0;                     // the tags are high bits: covers them too
+      ok = ok && (v >> ((raw.y >> 24) & 63u)) == 0;             // the bound fp_compile assumed for this wire; the tags are high bits: covers them too
     }
     const long long term = coef * (long long)v;
     if (k < nA) L[0] += term; else if (k < nAB) L[1] += term; else L[2] += term;

@@ -456,7 +456,7 @@ static void fp_compile(const std::vector<r1cs_load_detail::row> &rows, uint32_t 
     t.item_off = (uint32_t)fp.items.size();
     t.row_off = (uint32_t)fp.row_ids.size();
     t.nA = (uint16_t)ni; t.nB = 0; t.nC = 0; t.rows = (uint16_t)cnt;
-    const fp_item pad = {0u, 0u, 0ll};
+    const fp_item pad = {0u, 1u << 24, 0ll};                 // wire 0 times 0 (its value bound: one bit)
     for (size_t k = 0; k < ni; k++)
       for (size_t l = 0; l < 32; l++) fp.items.push_back(l < cnt && k < virt_items[j + l].size() ? virt_items[j + l][k] : pad);
     for (size_t l = 0; l < 32; l++) {
@@ -513,13 +513,21 @@ static void fp_compile(const std::vector<r1cs_load_detail::row> &rows, uint32_t 
     }
     plan.push_back(std::move(tp));
   }
+  // what the 64-bit path may assume of a scalar (and checks at run time): a wire with a booleanity row, a virtual bit and
+  // wire 0 stay below 2^1, anything else below 2^FP_FAST_VBITS; kept in bits 24..29 of the item's meta word
+  for (gen &g : gens)
+    for (fp_item &it : g.it)
+      if ((it.meta & 63u) == 0) {
+        const bool bit = it.wire == 0 || it.wire >= vbase || ((fp.bool_mask[it.wire >> 5] >> (it.wire & 31u)) & 1u);
+        it.meta |= (bit ? 1u : (uint32_t)FP_FAST_VBITS) << 24;
+      }
   for (tile_plan &tp : plan) {
-    // FP_TILE_FAST: 64-bit sums are exact when every scalar is below 2^FP_FAST_VBITS and every run lies over bits
+    // FP_TILE_FAST: 64-bit sums are exact when every scalar is below its bound and every run lies over bits
     bool fast = tp.n[0] <= 16 && tp.n[1] <= 16 && tp.n[2] <= 16, scalar_product = false;
     for (size_t r : tp.rows) {
       for (const fp_item &it : gens[r].it) {
         const uint32_t len = it.meta & 63u, cbits = (it.meta >> 16) & 255u;
-        fast = fast && cbits + (len ? len : it.wire >= vbase ? 1u : (uint32_t)FP_FAST_VBITS) <= 57;      // a virtual wire holds a bit
+        fast = fast && cbits + (len ? len : (it.meta >> 24) & 63u) <= 57;
       }
       bool sp = gens[r].n[0] && gens[r].n[1];
       for (uint32_t k = 0; k < gens[r].n[0] + gens[r].n[1]; k++) sp = sp && (gens[r].it[k].meta & 63u) == 0;
@@ -538,7 +546,7 @@ static void fp_compile(const std::vector<r1cs_load_detail::row> &rows, uint32_t 
     t.row_off = (uint32_t)fp.row_ids.size();
     t.nA = (uint16_t)tp.n[0]; t.nB = (uint16_t)tp.n[1]; t.nC = (uint16_t)tp.n[2];
     t.rows = (uint16_t)(cnt | (tp.fast ? FP_TILE_FAST : 0u));
-    const fp_item pad = {0u, 0u, 0ll};
+    const fp_item pad = {0u, 1u << 24, 0ll};                 // wire 0 times 0 (its value bound: one bit)
     for (int q = 0; q < 3; q++)
       for (uint32_t k = 0; k < tp.n[q]; k++)
         for (uint32_t l = 0; l < 32; l++) {
