@@ -12,5 +12,6 @@ for c in blake3_compression blake3_nova_pasta blake3_nova_o1; do
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_r1cs_check_fast -s 1 -c 1 -f -o gpurun_out/r2w_prof_r1cs_$c python tools/prof_run.py 15 3 $c r1cs > gpurun_out/r2w_ncu_r1cs_$c.log 2>&1; tail -1 gpurun_out/r2w_ncu_r1cs_$c.log
 done
 python tools/r1cs_sweep.py 2>&1 | tee gpurun_out/r2w_r1cs_sweep.jsonl
+timeout 600 python tools/bench_configs.py 1 3 2>&1 | tee gpurun_out/r2w_configs_0_2.jsonl
 timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -6 | tee gpurun_out/r2w_pytest.log
 ls -la gpurun_out | tail -12
