@@ -990,6 +990,44 @@ extern "C" int b3w_r1cs_load_file(b3w_ctx *c, const char *path, uint32_t *n_rows
   return guarded("b3w_r1cs_load_file", [&]() { return b3w_r1cs_load_file_impl(c, path, n_rows); });
 }
 
+// host-only (no GPU, no context): compile the rows of an `.r1cs` file the way b3w_r1cs_load does and copy one table of the
+// program out -- what tests/test_r1cs_program.py evaluates with Python integers against the file's own rows.
+// section: 0 bool_mask, 1 bool_row, 2 xors, 3 xor_ids, 4 tiles, 5 virtual-bit groups, 6 items, 7 row_ids, 8 taken[] (u8 per row)
+static int b3w_debug_r1cs_program_impl(const uint8_t *r1cs, size_t len, const uint8_t prime[32], uint32_t n_wires, int plain, uint32_t section,
+                                       void *out, size_t cap, size_t *n_bytes) {
+  if (!r1cs || !prime || !n_bytes) return fail(B3W_ERR_INVALID, "b3w_debug_r1cs_program: null argument");
+  r1cs_host_set hdr;
+  std::vector<r1cs_load_detail::row> rows;
+  std::string err;
+  int rc = r1cs_parse_rows(r1cs, len, prime, n_wires, rows, hdr, err);
+  if (rc) return fail(rc, "b3w_debug_r1cs_program: %s", err.c_str());
+  fastprog_host fp, fp0;
+  std::vector<char> taken;
+  compile_programs(rows, n_wires, fp, fp0, taken);
+  const fastprog_host &P = (plain && fp.n_virtual) ? fp0 : fp;
+  const void *src = nullptr;
+  size_t nb = 0;
+  switch (section) {
+    case 0: src = P.bool_mask.data(); nb = P.bool_mask.size() * 4; break;
+    case 1: src = P.bool_row.data(); nb = P.bool_row.size() * 4; break;
+    case 2: src = P.xors.data(); nb = P.xors.size() * sizeof(fp_xor); break;
+    case 3: src = P.xor_ids.data(); nb = P.xor_ids.size() * 4; break;
+    case 4: src = P.tiles.data(); nb = P.tiles.size() * sizeof(fp_tile); break;
+    case 5: src = P.vtiles.data(); nb = P.vtiles.size() * sizeof(fp_tile); break;
+    case 6: src = P.items.data(); nb = P.items.size() * sizeof(fp_item); break;
+    case 7: src = P.row_ids.data(); nb = P.row_ids.size() * 4; break;
+    case 8: src = taken.data(); nb = taken.size(); break;
+    default: return fail(B3W_ERR_INVALID, "b3w_debug_r1cs_program: section %u", section);
+  }
+  *n_bytes = nb;
+  if (out && nb <= cap && nb) memcpy(out, src, nb);
+  return B3W_OK;
+}
+extern "C" int b3w_debug_r1cs_program(const uint8_t *r1cs, size_t len, const uint8_t prime[32], uint32_t n_wires, int plain, uint32_t section,
+                                      void *out, size_t cap, size_t *n_bytes) {
+  return guarded("b3w_debug_r1cs_program", [&]() { return b3w_debug_r1cs_program_impl(r1cs, len, prime, n_wires, plain, section, out, cap, n_bytes); });
+}
+
 extern "C" int b3w_debug_inject_fault(b3w_ctx *c, uint32_t trace_word, uint32_t xor_mask) {
   if (!c) return fail(B3W_ERR_INVALID, "b3w_debug_inject_fault: null argument");
   if (trace_word != B3W_NO_ROW && trace_word >= (c->def->nova ? (uint32_t)NOVA_TRACE_WORDS : (uint32_t)TR_NOVA))

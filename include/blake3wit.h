@@ -251,6 +251,14 @@ int b3w_r1cs_compile_stats_ex(uint32_t circuit, uint32_t *out, uint32_t n_out);
  * (blake3_compression: 24 544 rows = 23 376 quadratic + 1 168 linear; nova: 25 064) */
 int b3w_r1cs_info(uint32_t circuit, uint32_t *n_rows, uint32_t *n_terms);
 
+/* Test hook, host-only (no GPU, no context): compile the constraint system of an `.r1cs` file exactly as b3w_r1cs_load
+ * does and copy one table of the resulting program to `out` (n_bytes receives its size; nothing is copied when cap is too
+ * small).  plain != 0: the program compiled WITHOUT virtual bits (the kernel's fall-back).  Sections: 0 booleanity mask,
+ * 1 booleanity row ids, 2 XOR runs, 3 XOR row ids, 4 row tiles, 5 virtual-bit groups, 6 items, 7 row ids of the tiles,
+ * 8 one byte per file row: covered by the program (1) or left to the general evaluator (0).  tests/test_r1cs_program.py
+ * evaluates these tables with Python integers against the file's own rows. */
+int b3w_debug_r1cs_program(const uint8_t *r1cs, size_t len, const uint8_t prime[32], uint32_t n_wires, int plain, uint32_t section,
+                           void *out, size_t cap, size_t *n_bytes);
 /* Test hook for the fused check: xor `xor_mask` into trace word `trace_word` of every instance after the trace phase
  * of the *_checked kernels (B3W_NO_ROW disables it). */
 int b3w_debug_inject_fault(b3w_ctx *ctx, uint32_t trace_word, uint32_t xor_mask);
