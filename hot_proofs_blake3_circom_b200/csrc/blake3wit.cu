@@ -893,10 +893,15 @@ static int r1cs_check_launch(b3w_ctx *c, const uint8_t *d_wit, const uint32_t *d
   CK(cudaFuncSetAttribute(k_r1cs_check_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int per_sm = c->ctas_limit > 0 ? c->ctas_limit : FPK_CTAS_PER_SM;
   const uint64_t cap = (uint64_t)c->sm_count * per_sm;
+  unsigned long long *d_counter = nullptr;                    // instances are handed out dynamically (kernels_r1cs_fast.cuh)
+  uint32_t pair = 0;
+  rc = take_counters(c, s, &d_counter, &pair);
+  if (rc) return rc;
   k_r1cs_check_fast<<<(unsigned)(n < cap ? n : cap), FPK_THREADS, smem, s>>>(d_wit, listed ? d_list : nullptr, n, c->def->ws, side_max, c->fp,
                                                                              c->fp.n_vtiles ? c->fp0 : c->fp, T, c->d_field,
-                                                                             d_status, d_first_bad);
+                                                                             d_status, d_first_bad, d_counter);
   CK(cudaGetLastError());
+  CK(cudaEventRecord(c->ctr_ev[pair], s));
   return B3W_OK;
 }
 

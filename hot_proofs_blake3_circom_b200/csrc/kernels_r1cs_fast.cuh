@@ -44,7 +44,7 @@
 #define FPK_CTAS_PER_SM 8
 #endif
 #ifndef FPK_INFLIGHT
-#define FPK_INFLIGHT 4            /* 256-bit loads per lane in flight in the streaming loop */
+#define FPK_INFLIGHT 3            /* 256-bit loads per lane kept in flight by the streaming loop (rotating registers; 3..5) */
 #endif
 #define FPK_SIDE_MAX 1536u        /* non-bit slots per witness in the side table (compression 713, nova O1 ~1 250) */
 
@@ -102,6 +102,11 @@ __device__ __noinline__ uint64_t cpt_classify_slow(uint32_t x0, uint32_t x1, uin
 __device__ __forceinline__ void ld_slot_stream(const uint8_t *p, uint32_t x[8]) {
   asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7]) : "l"(p));
+}
+// the same under a predicate (x keeps its contents when `on` is false): no branch around the load, the registers stay registers
+__device__ __forceinline__ void ld_slot_stream_if(const uint8_t *p, uint32_t (&x)[8], bool on) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %9, 0;\n\t@q ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t}"
+               : "+r"(x[0]), "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "+r"(x[6]), "+r"(x[7]) : "l"(p), "r"((uint32_t)on));
 }
 __device__ __forceinline__ void ld_slot(const uint8_t *p, uint32_t x[8]) {
   const uint4 a = __ldg(reinterpret_cast<const uint4 *>(p)), b = __ldg(reinterpret_cast<const uint4 *>(p) + 1);
@@ -506,80 +511,136 @@ __device__ __noinline__ uint32_t fp_eval_rows(const CompactSrc &src, const fastp
   return bad;
 }
 
+// ---- the kernel's shared memory: the compact copy (dynamic) and five control words ----
+extern __shared__ __align__(16) uint8_t fp_smem[];
+__shared__ uint32_t fp_s_bad, fp_s_flags, fp_s_nside, fp_s_tile;
+__shared__ unsigned long long fp_s_it;
+struct fp_copy {                  // isbit | bitval | rank (mw words each) | side (8-byte entries)
+  uint32_t *isbit, *bitval, *rank;
+  uint64_t *side;
+  __device__ __forceinline__ explicit fp_copy(uint32_t mw) {
+    isbit = reinterpret_cast<uint32_t *>(fp_smem);
+    bitval = isbit + mw;
+    rank = bitval + mw;
+    side = reinterpret_cast<uint64_t *>(fp_smem + (size_t)((3 * mw + 1) & ~1u) * 4);
+  }
+};
+
+struct fp_stream_args {
+  const uint8_t *w;               // this instance's witness in HBM
+  const field_consts *F;
+  uint32_t ws, words, mw, side_max;
+};
+// one 32-slot word of the streaming pass from the registers x (lane = slot); then the load of word wu + ahead goes into x
+__device__ __forceinline__ void fp_stream_word(const fp_stream_args &c, const fp_copy &m, uint32_t lane, uint32_t (&x)[8], uint32_t wu,
+                                               uint32_t ahead) {
+  if (wu >= c.words) return;                                  // warp-uniform
+  const uint32_t x0 = x[0], x1 = x[1], hi = x[2] | x[3] | x[4] | x[5] | x[6] | x[7];
+  const uint32_t s = wu * 32u + lane;
+  const bool in = s < c.ws;
+  const bool bit = in && (x1 | hi) == 0 && x0 < 2u;
+  const uint32_t mb = __ballot_sync(0xffffffffu, bit || !in);  // slots past the end count as bits (value 0)
+  const uint32_t mv = __ballot_sync(0xffffffffu, bit && x0 == 1u);
+  uint32_t base = 0;
+  if (~mb) {                                                  // warp-uniform: the word holds non-bit slots
+    if (lane == 0) base = atomicAdd(&fp_s_nside, (uint32_t)__popc(~mb));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (!((mb >> lane) & 1u)) {
+      const uint32_t idx = base + __popc(~mb & ((1u << lane) - 1u));
+      // small non-negative integers (every word, sum and carry of these circuits) need no field arithmetic
+      uint64_t v;
+      if (hi == 0 && (x1 >> 30) == 0) v = ((uint64_t)x1 << 32) | x0;
+      else v = cpt_classify_slow(x0, x1, x[2], x[3], x[4], x[5], x[6], x[7], s, c.F, &fp_s_flags);
+      if (idx < c.side_max) m.side[idx] = v;
+    }
+  }
+  if (lane == 0) { m.isbit[wu] = mb; m.bitval[wu] = mv; m.rank[wu] = base; }
+  const uint32_t wn = wu + ahead;                             // the registers are free: the next load goes out now
+  ld_slot_stream_if(c.w + (size_t)min(wn * 32u + lane, c.ws - 1u) * 32, x, wn < c.words);
+}
+// The streaming pass of one instance: lane = slot inside a 32-slot word (1 KiB), the CTA's warps take the words round-robin.
+// ROTATING registers: a word's slots are consumed and the load of the word FPK_INFLIGHT steps ahead goes into the same
+// registers at once, so FPK_INFLIGHT - 1 .. FPK_INFLIGHT KiB per warp stay in flight THROUGH the classification work
+// instead of draining to zero before the next burst (compressible buffers: 3.59 -> 2.95 ms per 2^15 compression witnesses,
+// ordinary memory 4.06 -> 3.87 with the dynamic hand-out; profiles/r02z).  Out of line for a register allocation of its
+// own: inside the kernel body ptxas kept the slot registers on the stack, next to the values that live across the row pass.
+__device__ __noinline__ void fp_stream(const fp_stream_args c) {
+  constexpr uint32_t NW = FPK_THREADS / 32, AH = FPK_INFLIGHT * NW;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const fp_copy m(c.mw);
+#define FPK_SLOT_REGS(x, k) \
+  uint32_t x[8] = {0, 0, 0, 0, 0, 0, 0, 0}; \
+  ld_slot_stream_if(c.w + (size_t)min((warp + (k) * NW) * 32u + lane, c.ws - 1u) * 32, x, warp + (k) * NW < c.words)
+  FPK_SLOT_REGS(xa, 0);
+  FPK_SLOT_REGS(xb, 1);
+  FPK_SLOT_REGS(xc, 2);
+#if FPK_INFLIGHT >= 4
+  FPK_SLOT_REGS(xd, 3);
+#endif
+#if FPK_INFLIGHT >= 5
+  FPK_SLOT_REGS(xe, 4);
+#endif
+#undef FPK_SLOT_REGS
+#pragma unroll 1
+  for (uint32_t wd = warp; wd < c.words; wd += AH) {
+    fp_stream_word(c, m, lane, xa, wd, AH);
+    fp_stream_word(c, m, lane, xb, wd + NW, AH);
+    fp_stream_word(c, m, lane, xc, wd + 2 * NW, AH);
+#if FPK_INFLIGHT >= 4
+    fp_stream_word(c, m, lane, xd, wd + 3 * NW, AH);
+#endif
+#if FPK_INFLIGHT >= 5
+    fp_stream_word(c, m, lane, xe, wd + 4 * NW, AH);
+#endif
+  }
+}
+
 __global__ void __launch_bounds__(FPK_THREADS, FPK_CTAS_PER_SM)
 k_r1cs_check_fast(const uint8_t *__restrict__ wit, const uint32_t *__restrict__ list /* NULL, or {count, instances...}: see below */, uint64_t n,
                   uint32_t ws, uint32_t side_max /* entries of the side table in this launch's shared memory */, const fastprog_dev P,
                   const fastprog_dev P0 /* the same rows compiled without virtual bits (= P when P has none) */,
                   const r1cs_tables_dev T /* residual rows */, const field_consts *__restrict__ F, uint8_t *__restrict__ status,
-                  uint32_t *__restrict__ first_bad) {
-  extern __shared__ __align__(16) uint8_t s_raw[];
+                  uint32_t *__restrict__ first_bad, unsigned long long *__restrict__ counter /* NULL: static round-robin; else 0 at launch */) {
   const uint32_t words = (ws + 31u) >> 5, mw = words + P.n_vtiles + 1u;      // virtual-bit words, one padding word per map (field_of reads w + 1)
-  uint32_t *isbit = reinterpret_cast<uint32_t *>(s_raw), *bitval = isbit + mw, *rank = bitval + mw;
-  uint64_t *side = reinterpret_cast<uint64_t *>(s_raw + (size_t)((3 * mw + 1) & ~1u) * 4);
-  __shared__ uint32_t s_bad, s_flags, s_nside, s_tile;
-  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  constexpr uint32_t NW = FPK_THREADS / 32;
+  const fp_copy m(mw);
+  uint32_t *const isbit = m.isbit, *const bitval = m.bitval;
+  const uint32_t tid = threadIdx.x;
   // list != NULL: check the instances list[1 .. list[0]] (n is ignored), except those whose status says "Assert Failed."
   const uint64_t count = list ? (uint64_t)list[0] : n;
-  for (uint64_t it = blockIdx.x; it < count; it += gridDim.x) {
+  // Instances are handed out through a counter in global memory (one atomic per 770 KB read): CTAs that finish early take
+  // the remainder, and the phases of the CTAs (stream / rows) drift apart instead of staying in the step the launch put
+  // them in (-3 % on all three systems, profiles/r02z).  counter == NULL: static round-robin.
+  for (uint64_t it = blockIdx.x;; it += gridDim.x) {
+    __syncthreads();                                          // the previous instance's rows are done with the copy
+    if (tid == 0) {
+      if (counter) fp_s_it = atomicAdd(counter, 1ull);
+      fp_s_bad = B3W_NO_ROW; fp_s_flags = 0; fp_s_nside = 0; fp_s_tile = 0; isbit[mw - 1u] = 0xFFFFFFFFu; bitval[mw - 1u] = 0u;
+    }
+    __syncthreads();
+    if (counter) it = fp_s_it;
+    if (it >= count) break;
     const uint64_t i = list ? (uint64_t)list[1 + it] : it;
     if (list && status && status[i] == B3W_CIRCOM_ASSERT) {   // CTA-uniform: no witness exists for this instance
       if (first_bad && tid == 0) first_bad[i] = B3W_NO_ROW;
       continue;
     }
-    __syncthreads();                                          // the previous instance's rows are done with the copy
-    if (tid == 0) { s_bad = B3W_NO_ROW; s_flags = 0; s_nside = 0; s_tile = 0; isbit[mw - 1u] = 0xFFFFFFFFu; bitval[mw - 1u] = 0u; }
-    __syncthreads();
     const uint8_t *w = wit + i * (uint64_t)ws * 32;
-    // ---- stream the witness once: lane = slot inside a 32-slot word, FPK_INFLIGHT words (1 KiB each) per warp in flight ----
-    // The loop is latency-bound (ncu: half of all stall samples sit on the first use of the loaded slot), so what counts is
-    // bytes in flight per SM: 32 warps x FPK_INFLIGHT KiB.
-    for (uint32_t wd = warp; wd < words; wd += FPK_INFLIGHT * NW) {
-      uint32_t x[FPK_INFLIGHT][8];
-#pragma unroll
-      for (int u = 0; u < FPK_INFLIGHT; u++) {
-        const uint32_t s = min((wd + u * NW) * 32u + lane, ws - 1u);
-        ld_slot_stream(w + (size_t)s * 32, x[u]);
-      }
-#pragma unroll
-      for (int u = 0; u < FPK_INFLIGHT; u++) {
-        const uint32_t wu = wd + u * NW;
-        if (wu >= words) break;                               // warp-uniform
-        const uint32_t s = wu * 32u + lane;
-        const bool in = s < ws;
-        const bool bit = in && (x[u][1] | x[u][2] | x[u][3] | x[u][4] | x[u][5] | x[u][6] | x[u][7]) == 0 && x[u][0] < 2u;
-        const uint32_t mb = __ballot_sync(0xffffffffu, bit || !in);      // slots past the end count as bits (value 0)
-        const uint32_t mv = __ballot_sync(0xffffffffu, bit && x[u][0] == 1u);
-        uint32_t base = 0;
-        if (~mb) {                                            // warp-uniform: the word holds non-bit slots
-          if (lane == 0) base = atomicAdd(&s_nside, (uint32_t)__popc(~mb));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (!((mb >> lane) & 1u)) {
-            const uint32_t idx = base + __popc(~mb & ((1u << lane) - 1u));
-            // small non-negative integers (every word, sum and carry of these circuits) need no field arithmetic
-            uint64_t v;
-            if ((x[u][2] | x[u][3] | x[u][4] | x[u][5] | x[u][6] | x[u][7]) == 0 && (x[u][1] >> 30) == 0) v = ((uint64_t)x[u][1] << 32) | x[u][0];
-            else v = cpt_classify_slow(x[u][0], x[u][1], x[u][2], x[u][3], x[u][4], x[u][5], x[u][6], x[u][7], s, F, &s_flags);
-            if (idx < side_max) side[idx] = v;
-          }
-        }
-        if (lane == 0) { isbit[wu] = mb; bitval[wu] = mv; rank[wu] = base; }
-      }
-    }
+    // ---- stream the witness once into the compact copy ----
+    fp_stream(fp_stream_args{w, F, ws, words, mw, side_max});
     __syncthreads();
     uint32_t bad = B3W_NO_ROW;
-    if (!(s_flags & 1u) && FPK_EXP == 0) {
-      const CompactSrc src{isbit, bitval, rank, side, w, F, s_nside <= side_max};
+    if (!(fp_s_flags & 1u) && FPK_EXP == 0) {
+      const CompactSrc src{isbit, bitval, m.rank, m.side, w, F, fp_s_nside <= side_max};
       if (P.n_vtiles) {                                       // CTA-uniform
-        fp_eval_virtuals(src, P, words, isbit, bitval, &s_flags);
+        fp_eval_virtuals(src, P, words, isbit, bitval, &fp_s_flags);
         __syncthreads();
       }
-      bad = (s_flags & 2u) ? fp_eval_rows(src, P0, T, words, &s_tile) : fp_eval_rows(src, P, T, words, &s_tile);
+      bad = (fp_s_flags & 2u) ? fp_eval_rows(src, P0, T, words, &fp_s_tile) : fp_eval_rows(src, P, T, words, &fp_s_tile);
     }
-    if (bad != B3W_NO_ROW) atomicMin(&s_bad, bad);
+    if (bad != B3W_NO_ROW) atomicMin(&fp_s_bad, bad);
     __syncthreads();
     if (tid == 0) {
-      const uint32_t verdict = (s_flags & 1u) ? B3W_NOT_CANONICAL : s_bad;
+      const uint32_t verdict = (fp_s_flags & 1u) ? B3W_NOT_CANONICAL : fp_s_bad;
       if (status) status[i] = verdict == B3W_NO_ROW ? 0 : B3W_R1CS_VIOLATION;
       if (first_bad) first_bad[i] = verdict;
     }
