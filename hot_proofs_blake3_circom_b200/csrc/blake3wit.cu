@@ -585,7 +585,7 @@ static cudaError_t upload_vec(T **dst, const std::vector<T> &v) {
   return e;
 }
 static void free_fastprog(fastprog_dev *p) {
-  for (void *q : {(void *)p->bool_mask, (void *)p->bool_row, (void *)p->xors, (void *)p->xor_ids, (void *)p->tiles, (void *)p->vtiles, (void *)p->items, (void *)p->row_ids})
+  for (void *q : {(void *)p->bool_mask, (void *)p->bool_row, (void *)p->xors, (void *)p->xor_ids, (void *)p->tiles, (void *)p->vtiles, (void *)p->items, (void *)p->row_ids, (void *)p->side_rank})
     if (q) cudaFree(q);
   memset(p, 0, sizeof *p);
 }
@@ -646,6 +646,19 @@ static int install_slot_rows(b3w_ctx *c, std::vector<r1cs_load_detail::row> &row
   if (e == cudaSuccess) e = upload_vec(&d.row_ids, h.row_ids);
   if (e == cudaSuccess) e = upload_fastprog(&P, fp);
   if (e == cudaSuccess && fp.n_virtual) e = upload_fastprog(&P0, fp0);
+  if (e == cudaSuccess) {
+    // where the kernel keeps the non-bit slots of a witness: the entries of word w start at side_rank[w] (the circuit's slot
+    // kinds decide; a slot that is not DK_BIT may still hold 0 or 1, its entry is then simply not used)
+    const uint32_t words = (c->def->ws + 31u) >> 5, mw = words + P.n_vtiles + 1u;
+    std::vector<uint32_t> rank(mw);
+    uint32_t total = 0;
+    for (uint32_t w = 0; w < mw; w++) {
+      rank[w] = total;
+      for (uint32_t sl = w * 32u; sl < std::min(c->def->ws, (w + 1u) * 32u) && w < words; sl++) total += (c->h_desc[sl] >> 24) != DK_BIT;
+    }
+    e = upload_vec(&P.side_rank, rank);
+    P.side_total = (total + 1u) & ~1u;
+  }
   if (e != cudaSuccess) {
     free_r1cs_dev(&d);
     free_fastprog(&P);
@@ -883,13 +896,9 @@ static int r1cs_check_launch(b3w_ctx *c, const uint8_t *d_wit, const uint32_t *d
   if (n == 0) return B3W_OK;
   const r1cs_tables_dev T{c->r_slots.cls, c->r_slots.lo, c->r_slots.hi, c->r_slots.terms, c->r_slots.ncls, c->r_slots.coef_fr, c->r_slots.row_ids, c->r_slots.nblk};
   const uint32_t mw = ((c->def->ws + 31u) >> 5) + c->fp.n_vtiles + 1u;
-  // the side table holds the non-bit slots: sized from the circuit's own slot kinds (+ margin) rather than for the worst
-  // case, which leaves more of the SM's L1 to the program tables; a witness with more non-bit slots than that (not one of
-  // this circuit's) is still checked, its values are then re-read from HBM on demand
-  uint32_t non_bits = 0;
-  for (uint32_t sl = 0; sl < c->def->ws; sl++) non_bits += (c->h_desc[sl] >> 24) != DK_BIT;
-  const uint32_t side_max = std::min<uint32_t>(FPK_SIDE_MAX, (non_bits + 128u + 63u) & ~63u);
-  const size_t smem = (size_t)((3 * mw + 1) & ~1u) * 4 + (size_t)side_max * 8;
+  // the side table holds the non-bit slots of the circuit's witness layout (install_slot_rows: side_rank / side_total); a
+  // witness with non-bit slots elsewhere (not one of this circuit's) is still checked, those values are re-read from HBM
+  const size_t smem = (size_t)((3 * mw + 1) & ~1u) * 4 + (size_t)c->fp.side_total * 8;
   CK(cudaFuncSetAttribute(k_r1cs_check_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int per_sm = c->ctas_limit > 0 ? c->ctas_limit : FPK_CTAS_PER_SM;
   const uint64_t cap = (uint64_t)c->sm_count * per_sm;
@@ -897,7 +906,7 @@ static int r1cs_check_launch(b3w_ctx *c, const uint8_t *d_wit, const uint32_t *d
   uint32_t pair = 0;
   rc = take_counters(c, s, &d_counter, &pair);
   if (rc) return rc;
-  k_r1cs_check_fast<<<(unsigned)(n < cap ? n : cap), FPK_THREADS, smem, s>>>(d_wit, listed ? d_list : nullptr, n, c->def->ws, side_max, c->fp,
+  k_r1cs_check_fast<<<(unsigned)(n < cap ? n : cap), FPK_THREADS, smem, s>>>(d_wit, listed ? d_list : nullptr, n, c->def->ws, c->fp,
                                                                              c->fp.n_vtiles ? c->fp0 : c->fp, T, c->d_field,
                                                                              d_status, d_first_bad, d_counter);
   CK(cudaGetLastError());

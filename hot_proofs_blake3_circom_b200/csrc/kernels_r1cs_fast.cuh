@@ -31,7 +31,11 @@
 // warps per issue waiting for instructions (profiles/r02m).
 // History (profiles/): 8 bytes per slot, one CTA per SM 1.65 M witnesses/s (compression, 24 544 rows) -> compact copy +
 // row blocks 2.33 M/s (0.27 of the read roofline; row arithmetic issue-bound) -> compiled program 7.8 M/s (nova O2 5.1)
-// -> virtual bits, fast tiles, dynamic hand-out, 128-thread CTAs: 8.2 M/s (0.96), nova O2 7.9 M/s (0.90), O1 6.8 (0.82).
+// -> virtual bits, fast tiles, dynamic hand-out, 128-thread CTAs: 8.2 M/s (0.96), nova O2 7.9 M/s (0.90), O1 6.8 (0.82)
+// -> rotating-register streaming loop, instances from a global counter, side-table places from the circuit's layout
+// instead of a shared-memory counter: 8.6 M/s (1.02; 11.9 M/s from compressible buffers), nova O2 8.0 (0.92), O1 7.0 (0.85).
+// Measured and dropped on the way (profiles/r02z_*): L2 prefetch of the next instance, staggered CTA starts, 9 and 10 CTAs
+// per SM (the program tables lose their L1), an unrolled tile loop (instruction cache).
 #pragma once
 
 #ifndef FPK_EXP
@@ -44,9 +48,8 @@
 #define FPK_CTAS_PER_SM 8
 #endif
 #ifndef FPK_INFLIGHT
-#define FPK_INFLIGHT 3            /* 256-bit loads per lane kept in flight by the streaming loop (rotating registers; 3..5) */
+#define FPK_INFLIGHT 4            /* 256-bit loads per lane kept in flight by the streaming loop (rotating registers; 3..5) */
 #endif
-#define FPK_SIDE_MAX 1536u        /* non-bit slots per witness in the side table (compression 713, nova O1 ~1 250) */
 
 struct fp_item {                  // 16 bytes
   uint32_t wire;                  // scalar: the wire; run: its first wire
@@ -73,7 +76,9 @@ struct fastprog_dev {
   fp_tile *vtiles;                // virtual-bit definitions, 32 per group: nA items each, then one item holding the unit (r1cs_load.h)
   fp_item *items;
   uint32_t *row_ids;
+  uint32_t *side_rank;            // per 32-slot word (+ virtual-bit words + 1, like the maps): side-table entries the circuit's slot kinds reserve before it
   uint32_t n_xors, n_tiles, n_vtiles, n_rows;      // n_rows: rows the program covers (all kinds)
+  uint32_t side_total;            // entries of the side table = non-bit slots of the circuit's witness layout
 };
 
 // 32-byte slot -> tagged 8-byte value; BIG = "genuine field element", payload = slot index
@@ -120,7 +125,7 @@ struct CompactSrc {
   const uint64_t *side;                      // shared: tagged values of the non-bit slots
   const uint8_t *wit;                        // this instance's witness in HBM
   const field_consts *F;
-  bool side_ok;                              // false: more non-bit slots than the side table holds
+  bool side_ok;                              // false: an irregular instance (non-bit slots where the circuit's layout has none): values from HBM
   __device__ __forceinline__ uint64_t get(uint32_t s) const {
     const uint32_t w = s >> 5, b = s & 31u, m = isbit[w];
     if ((m >> b) & 1u) return (bitval[w] >> b) & 1u;
@@ -511,11 +516,11 @@ __device__ __noinline__ uint32_t fp_eval_rows(const CompactSrc &src, const fastp
   return bad;
 }
 
-// ---- the kernel's shared memory: the compact copy (dynamic) and five control words ----
+// ---- the kernel's shared memory: the compact copy (dynamic) and four control words ----
 extern __shared__ __align__(16) uint8_t fp_smem[];
-__shared__ uint32_t fp_s_bad, fp_s_flags, fp_s_nside, fp_s_tile;
+__shared__ uint32_t fp_s_bad, fp_s_flags, fp_s_tile;
 __shared__ unsigned long long fp_s_it;
-struct fp_copy {                  // isbit | bitval | rank (mw words each) | side (8-byte entries)
+struct fp_copy {                  // isbit | bitval | rank (mw words each; rank is the launch's constant side_rank) | side (8-byte entries)
   uint32_t *isbit, *bitval, *rank;
   uint64_t *side;
   __device__ __forceinline__ explicit fp_copy(uint32_t mw) {
@@ -529,7 +534,7 @@ struct fp_copy {                  // isbit | bitval | rank (mw words each) | sid
 struct fp_stream_args {
   const uint8_t *w;               // this instance's witness in HBM
   const field_consts *F;
-  uint32_t ws, words, mw, side_max;
+  uint32_t ws, words, mw;
 };
 // one 32-slot word of the streaming pass from the registers x (lane = slot); then the load of word wu + ahead goes into x
 __device__ __forceinline__ void fp_stream_word(const fp_stream_args &c, const fp_copy &m, uint32_t lane, uint32_t (&x)[8], uint32_t wu,
@@ -541,20 +546,22 @@ __device__ __forceinline__ void fp_stream_word(const fp_stream_args &c, const fp
   const bool bit = in && (x1 | hi) == 0 && x0 < 2u;
   const uint32_t mb = __ballot_sync(0xffffffffu, bit || !in);  // slots past the end count as bits (value 0)
   const uint32_t mv = __ballot_sync(0xffffffffu, bit && x0 == 1u);
-  uint32_t base = 0;
   if (~mb) {                                                  // warp-uniform: the word holds non-bit slots
-    if (lane == 0) base = atomicAdd(&fp_s_nside, (uint32_t)__popc(~mb));
-    base = __shfl_sync(0xffffffffu, base, 0);
+    // Their side-table entries start where the CIRCUIT's slot kinds put this word's (m.rank, constant per launch): no
+    // counter, no atomic, no exchange between the warps.  A word with more non-bit slots than the circuit's layout has
+    // there (never a witness of this circuit) makes the instance IRREGULAR: its rows read such values from HBM instead.
+    const uint32_t r0 = m.rank[wu], cap = m.rank[wu + 1u] - r0;
+    const bool fits = (uint32_t)__popc(~mb) <= cap;
     if (!((mb >> lane) & 1u)) {
-      const uint32_t idx = base + __popc(~mb & ((1u << lane) - 1u));
       // small non-negative integers (every word, sum and carry of these circuits) need no field arithmetic
       uint64_t v;
       if (hi == 0 && (x1 >> 30) == 0) v = ((uint64_t)x1 << 32) | x0;
       else v = cpt_classify_slow(x0, x1, x[2], x[3], x[4], x[5], x[6], x[7], s, c.F, &fp_s_flags);
-      if (idx < c.side_max) m.side[idx] = v;
+      if (fits) m.side[r0 + __popc(~mb & ((1u << lane) - 1u))] = v;
     }
+    if (!fits && lane == 0) atomicOr(&fp_s_flags, 4u);
   }
-  if (lane == 0) { m.isbit[wu] = mb; m.bitval[wu] = mv; m.rank[wu] = base; }
+  if (lane == 0) { m.isbit[wu] = mb; m.bitval[wu] = mv; }
   const uint32_t wn = wu + ahead;                             // the registers are free: the next load goes out now
   ld_slot_stream_if(c.w + (size_t)min(wn * 32u + lane, c.ws - 1u) * 32, x, wn < c.words);
 }
@@ -597,7 +604,7 @@ __device__ __noinline__ void fp_stream(const fp_stream_args c) {
 
 __global__ void __launch_bounds__(FPK_THREADS, FPK_CTAS_PER_SM)
 k_r1cs_check_fast(const uint8_t *__restrict__ wit, const uint32_t *__restrict__ list /* NULL, or {count, instances...}: see below */, uint64_t n,
-                  uint32_t ws, uint32_t side_max /* entries of the side table in this launch's shared memory */, const fastprog_dev P,
+                  uint32_t ws, const fastprog_dev P,
                   const fastprog_dev P0 /* the same rows compiled without virtual bits (= P when P has none) */,
                   const r1cs_tables_dev T /* residual rows */, const field_consts *__restrict__ F, uint8_t *__restrict__ status,
                   uint32_t *__restrict__ first_bad, unsigned long long *__restrict__ counter /* NULL: static round-robin; else 0 at launch */) {
@@ -607,6 +614,7 @@ k_r1cs_check_fast(const uint8_t *__restrict__ wit, const uint32_t *__restrict__ 
   const uint32_t tid = threadIdx.x;
   // list != NULL: check the instances list[1 .. list[0]] (n is ignored), except those whose status says "Assert Failed."
   const uint64_t count = list ? (uint64_t)list[0] : n;
+  for (uint32_t k = tid; k < mw; k += FPK_THREADS) m.rank[k] = __ldg(P.side_rank + k);      // (the loop's first barrier publishes it)
   // Instances are handed out through a counter in global memory (one atomic per 770 KB read): CTAs that finish early take
   // the remainder, and the phases of the CTAs (stream / rows) drift apart instead of staying in the step the launch put
   // them in (-3 % on all three systems, profiles/r02z).  counter == NULL: static round-robin.
@@ -614,7 +622,7 @@ k_r1cs_check_fast(const uint8_t *__restrict__ wit, const uint32_t *__restrict__ 
     __syncthreads();                                          // the previous instance's rows are done with the copy
     if (tid == 0) {
       if (counter) fp_s_it = atomicAdd(counter, 1ull);
-      fp_s_bad = B3W_NO_ROW; fp_s_flags = 0; fp_s_nside = 0; fp_s_tile = 0; isbit[mw - 1u] = 0xFFFFFFFFu; bitval[mw - 1u] = 0u;
+      fp_s_bad = B3W_NO_ROW; fp_s_flags = 0; fp_s_tile = 0; isbit[mw - 1u] = 0xFFFFFFFFu; bitval[mw - 1u] = 0u;
     }
     __syncthreads();
     if (counter) it = fp_s_it;
@@ -626,11 +634,11 @@ k_r1cs_check_fast(const uint8_t *__restrict__ wit, const uint32_t *__restrict__ 
     }
     const uint8_t *w = wit + i * (uint64_t)ws * 32;
     // ---- stream the witness once into the compact copy ----
-    fp_stream(fp_stream_args{w, F, ws, words, mw, side_max});
+    fp_stream(fp_stream_args{w, F, ws, words, mw});
     __syncthreads();
     uint32_t bad = B3W_NO_ROW;
     if (!(fp_s_flags & 1u) && FPK_EXP == 0) {
-      const CompactSrc src{isbit, bitval, m.rank, m.side, w, F, fp_s_nside <= side_max};
+      const CompactSrc src{isbit, bitval, m.rank, m.side, w, F, (fp_s_flags & 4u) == 0};
       if (P.n_vtiles) {                                       // CTA-uniform
         fp_eval_virtuals(src, P, words, isbit, bitval, &fp_s_flags);
         __syncthreads();
