@@ -399,9 +399,9 @@ def run_own(args, rank, world, local_rank):
     wc.close()
 
     # --- BASELINE configs[3]: 2^20 blake3_nova_pasta steps, streamed through the HBM ring (whole job = 2^20: strong) ----
-    def streamed(name, rows_fn, n_total, fused, reps_target_s, n_samples, tag):
+    def streamed(name, rows_fn, n_total, fused, reps_target_s, n_samples, tag, byte_check=False):
         n_r = n_total // world
-        calc = pkg.builder(name, device=local_rank, chunk=16384, fused_check=fused)
+        calc = pkg.builder(name, device=local_rank, chunk=16384, fused_check=fused, byte_check=byte_check)
         r = gen.parallel_rows(rows_fn, n_r, first=rank * n_r, threads=max(2, ncpu // max(local_world, 1)))
         hin = L.b3w_host_alloc_near(r.nbytes, local_rank)
         C.memmove(hin, r.ctypes.data, r.nbytes)
@@ -430,7 +430,7 @@ def run_own(args, rank, world, local_rank):
         tm = calc.lastTiming()
         res = {"value": n_total / dt, "unit": "witnesses/s", "seconds_per_pass": dt, "passes_timed": reps, "instances": n_total,
                "instances_per_gpu": n_r, "witness_bytes": calc.witnessSize * 32, "generated_GB_per_pass": n_total * calc.witnessSize * 32 / 1e9,
-               "ring_write_GBps_per_gpu": n_r * calc.witnessSize * 32 / dt / 1e9, "fused_check": fused,
+               "ring_write_GBps_per_gpu": n_r * calc.witnessSize * 32 / dt / 1e9, "fused_check": fused, "byte_check": byte_check,
                "kernel_ms_sum_last_pass": tm["kernel_ms"], "launches_per_pass": tm["launches"], "d2h_bytes_per_pass_per_gpu": tm["d2h_bytes"],
                "kernel_ms_note": "b3w_last_timing: sum of the CUDA-event durations of the pass's launches; launches alternate between the two ring "
                                  "streams and overlap, so the sum exceeds the wall time of the pass",
@@ -448,6 +448,14 @@ def run_own(args, rank, world, local_rank):
     cfg5["api"] = ("b3w_witness_batch_ex(out=NULL, sums, %d samples per GPU) on a context with B3W_FLAG_FUSED_CHECK: BASELINE configs[4], "
                    "contiguous index ranges, no collective; per instance status + out[16] + a 64-bit witness checksum come back, plus the "
                    "full witnesses of the sample" % (1024 // world))
+
+    # --- the same stream with B3W_FLAG_BYTE_CHECK: every chunk is read back from the ring and all 24 544 rows are evaluated
+    # on its bytes before anything leaves the GPU (2^22 instances over the N GPUs) ------------------------------------------
+    cfg5b = streamed("blake3_compression", gen.splitmix_compression_inputs, 1 << min(22, args.log2_config5), False, 0.5, 0, "config5_byte_check",
+                     byte_check=True)
+    cfg5b["api"] = ("b3w_witness_batch_ex(out=NULL, sums) on a context with B3W_FLAG_BYTE_CHECK: like config5, but instead of the fused "
+                    "check on the trace the stand-alone checker (k_r1cs_check_fast) re-reads every witness from the HBM ring and evaluates "
+                    "every row on the bytes that were stored")
 
     # --- field-element rows (b3w_witness_batch_fr) next to u32 rows: 2^20 blake3_nova_pasta, N = 1 only ------------------
     fr_line = None
@@ -550,7 +558,7 @@ def run_own(args, rank, world, local_rank):
                                 "compressible_buffer": None if chk_hbm_c_ms is None else {
                                     "value": world * n_chk / (chk_hbm_c_ms / 1e3), "kernel_ms": chk_hbm_c_ms, "read_gbs": n_chk * WIT_BYTES / chk_hbm_c_ms / 1e6},
                                 "nova": chk_nova},
-        "config4": cfg4, "config5": cfg5,
+        "config4": cfg4, "config5": cfg5, "config5_byte_check": cfg5b,
         "gpu_launches": gpu_launches, "clocks": clocks}
     if compressible:
         achieved_c = alg_bytes / kernel_ms / 1e6

@@ -14,6 +14,7 @@ B3W_EXT_ASSERT = 127
 B3W_FLAG_COMPRESSIBLE_RING = 2
 B3W_FLAG_PLAIN_RING = 4
 B3W_FLAG_REFERENCE_SIBLINGS = 8
+B3W_FLAG_BYTE_CHECK = 16
 B3W_MEM_COMPRESSIBLE = 1
 B3W_MAX_SAMPLES = 1024
 B3W_VERSION = 0x000200

@@ -243,7 +243,7 @@ extern "C" const char *b3w_last_error(void) { return g_err; }
 static int b3w_create_impl(const b3w_config *cfg, b3w_ctx **out) {
   if (!cfg || !out) return fail(B3W_ERR_INVALID, "b3w_create: null argument");
   if (cfg->circuit >= (uint32_t)N_CIRCUITS) return fail(B3W_ERR_UNSUPPORTED, "b3w_create: circuit %u not built", cfg->circuit);
-  if (cfg->flags & ~(uint32_t)(B3W_FLAG_FUSED_CHECK | B3W_FLAG_COMPRESSIBLE_RING | B3W_FLAG_PLAIN_RING | B3W_FLAG_REFERENCE_SIBLINGS))
+  if (cfg->flags & ~(uint32_t)(B3W_FLAG_FUSED_CHECK | B3W_FLAG_COMPRESSIBLE_RING | B3W_FLAG_PLAIN_RING | B3W_FLAG_REFERENCE_SIBLINGS | B3W_FLAG_BYTE_CHECK))
     return fail(B3W_ERR_INVALID, "b3w_create: unknown flags 0x%x", cfg->flags);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -889,7 +889,7 @@ extern "C" int b3w_r1cs_info(uint32_t circuit, uint32_t *n_rows, uint32_t *n_ter
 // instances [0, n) of d_wit; or -- listed -- the instances d_list[1 .. d_list[0]] (a device-side list: the count is read by
 // the kernel), skipping those whose status says "Assert Failed." (no witness was written for them)
 static int r1cs_check_launch(b3w_ctx *c, const uint8_t *d_wit, const uint32_t *d_list, uint64_t n, uint8_t *d_status, uint32_t *d_first_bad,
-                             cudaStream_t s, bool listed = false) {
+                             cudaStream_t s, bool listed = false, bool skip_asserted = false) {
   int rc = ensure_r1cs(c);
   if (rc) return rc;
   if (c->slot_rows == 0) return fail(B3W_ERR_UNSUPPORTED, "%s: no constraint system for the stand-alone check", c->def->name);
@@ -908,7 +908,7 @@ static int r1cs_check_launch(b3w_ctx *c, const uint8_t *d_wit, const uint32_t *d
   if (rc) return rc;
   k_r1cs_check_fast<<<(unsigned)(n < cap ? n : cap), FPK_THREADS, smem, s>>>(d_wit, listed ? d_list : nullptr, n, c->def->ws, c->fp,
                                                                              c->fp.n_vtiles ? c->fp0 : c->fp, T, c->d_field,
-                                                                             d_status, d_first_bad, d_counter);
+                                                                             d_status, d_first_bad, d_counter, (listed || skip_asserted) ? 1u : 0u);
   CK(cudaGetLastError());
   CK(cudaEventRecord(c->ctr_ev[pair], s));
   return B3W_OK;
@@ -1182,7 +1182,7 @@ struct batch_job {
 static int batch_chunks(b3w_ctx *c, const batch_job &J) {
   const circuit_def *d = c->def;
   const size_t wbytes = (size_t)d->ws * 32;
-  const bool check = (c->flags & B3W_FLAG_FUSED_CHECK) != 0;
+  const bool check = (c->flags & B3W_FLAG_FUSED_CHECK) != 0, byte_check = (c->flags & B3W_FLAG_BYTE_CHECK) != 0;
   // the sample instances in index order: every chunk copies the ones it holds out of its ring slot
   std::vector<std::pair<uint64_t, uint32_t>> samples;
   for (uint32_t j = 0; j < J.ex.n_samples; j++) samples.push_back({J.ex.sample_idx[j], j});
@@ -1195,7 +1195,7 @@ static int batch_chunks(b3w_ctx *c, const batch_job &J) {
     cudaStream_t s = c->st[k];
     launch_opts o;
     o.check = check;
-    o.d_first_bad = (check && J.ex.first_bad) ? c->d_fbad[k] : nullptr;
+    o.d_first_bad = ((check || byte_check) && J.ex.first_bad) ? c->d_fbad[k] : nullptr;
     o.d_sums = J.ex.sums ? (unsigned long long *)c->d_sums[k] : nullptr;
     {
       nvtx_range r("b3w:h2d");
@@ -1238,6 +1238,14 @@ static int batch_chunks(b3w_ctx *c, const batch_job &J) {
           rc = r1cs_check_launch(c, c->d_ring[k], c->d_wlist[k], m, c->d_status[k], o.d_first_bad, s, /*listed=*/true);
           if (rc) return rc;
         }
+      }
+      if (byte_check) {
+        // every witness of the chunk is read back from the ring slot and ALL rows of the constraint system are evaluated on
+        // its bytes (what a consumer does with the vector it is handed, rust_fold/src/utils.rs:78-85): a wrong slot
+        // descriptor, a wrong split or a lost store cannot pass, which the fused check -- it sees the trace -- cannot say
+        rc = r1cs_check_launch(c, c->d_ring[k], nullptr, m, c->d_status[k], o.d_first_bad, s, false, /*skip_asserted=*/true);
+        if (rc) return rc;
+        c->timing.launches++;
       }
       CK(cudaEventRecord(c->ev_k1[k], s));
       c->ev_pending[k] = true;
@@ -1284,7 +1292,7 @@ static int batch_host(b3w_ctx *c, const batch_job &J, const char *who) {
   if (rc == B3W_OK && J.in_fr) rc = ensure_fr_staging(c);
   if (rc == B3W_OK && J.in_fr && c->def->nova) rc = ensure_nova_wide(c);
   if (rc) return rc;
-  if (ex.first_bad && !(c->flags & B3W_FLAG_FUSED_CHECK))
+  if (ex.first_bad && !(c->flags & (B3W_FLAG_FUSED_CHECK | B3W_FLAG_BYTE_CHECK)))
     for (uint64_t i = 0; i < J.n; i++) ex.first_bad[i] = B3W_NO_ROW;          // no check ran
   rc = guarded(who, [&]() { return batch_chunks(c, J); });
   // drain both slots on every path: after an error no copy into the caller's buffers may still be in flight

@@ -607,12 +607,13 @@ k_r1cs_check_fast(const uint8_t *__restrict__ wit, const uint32_t *__restrict__ 
                   uint32_t ws, const fastprog_dev P,
                   const fastprog_dev P0 /* the same rows compiled without virtual bits (= P when P has none) */,
                   const r1cs_tables_dev T /* residual rows */, const field_consts *__restrict__ F, uint8_t *__restrict__ status,
-                  uint32_t *__restrict__ first_bad, unsigned long long *__restrict__ counter /* NULL: static round-robin; else 0 at launch */) {
+                  uint32_t *__restrict__ first_bad, unsigned long long *__restrict__ counter /* NULL: static round-robin; else 0 at launch */,
+                  uint32_t skip_asserted /* leave instances whose status says "Assert Failed." alone: no witness exists for them */) {
   const uint32_t words = (ws + 31u) >> 5, mw = words + P.n_vtiles + 1u;      // virtual-bit words, one padding word per map (field_of reads w + 1)
   const fp_copy m(mw);
   uint32_t *const isbit = m.isbit, *const bitval = m.bitval;
   const uint32_t tid = threadIdx.x;
-  // list != NULL: check the instances list[1 .. list[0]] (n is ignored), except those whose status says "Assert Failed."
+  // list != NULL: check the instances list[1 .. list[0]] (n is ignored)
   const uint64_t count = list ? (uint64_t)list[0] : n;
   for (uint32_t k = tid; k < mw; k += FPK_THREADS) m.rank[k] = __ldg(P.side_rank + k);      // (the loop's first barrier publishes it)
   // Instances are handed out through a counter in global memory (one atomic per 770 KB read): CTAs that finish early take
@@ -628,7 +629,7 @@ k_r1cs_check_fast(const uint8_t *__restrict__ wit, const uint32_t *__restrict__ 
     if (counter) it = fp_s_it;
     if (it >= count) break;
     const uint64_t i = list ? (uint64_t)list[1 + it] : it;
-    if (list && status && status[i] == B3W_CIRCOM_ASSERT) {   // CTA-uniform: no witness exists for this instance
+    if (skip_asserted && status && status[i] == B3W_CIRCOM_ASSERT) {      // CTA-uniform: no witness exists for this instance
       if (first_bad && tid == 0) first_bad[i] = B3W_NO_ROW;
       continue;
     }

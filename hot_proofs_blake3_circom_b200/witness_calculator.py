@@ -46,11 +46,14 @@ def circuit_from_wasm(code):
     return CIRCUITS[h][0]
 
 
-def builder(code, options=None, device=-1, chunk=0, lazy=False, fused_check=False, compressible_ring=True, reference_siblings=False):
+def builder(code, options=None, device=-1, chunk=0, lazy=False, fused_check=False, compressible_ring=True, reference_siblings=False,
+            byte_check=False):
     """builder(code, options) -> WitnessCalculator   (witness_calculator.js:1).
     `code`: bytes of one of the reference's .wasm files, or a circuit name / id.
     lazy=True defers the creation of the GPU context to the first witness call (host-logic tests).
     fused_check=True makes every batch call also run the fused on-device R1CS check (status 7 = violation).
+    byte_check=True (B3W_FLAG_BYTE_CHECK) re-reads every chunk's witnesses from the HBM ring and evaluates every row of the
+    constraint system on those bytes before they leave the GPU (the consumer-side check of rust_fold/src/utils.rs:78-85).
     compressible_ring=False keeps the internal HBM ring of the host-buffer calls in ordinary memory (B3W_FLAG_PLAIN_RING); the
     default -- here, in C and in the N-API addon -- is compressible memory with a silent fall-back to ordinary memory.
     reference_siblings=True makes novaChain pick parent-step siblings by the reference's rule (rust_fold/src/blake3_hash.rs:60-78)."""
@@ -61,7 +64,7 @@ def builder(code, options=None, device=-1, chunk=0, lazy=False, fused_check=Fals
     else:
         cid = circuit_from_wasm(code)
     return WitnessCalculator(cid, options or {}, device=device, chunk=chunk, lazy=lazy, fused_check=fused_check,
-                             compressible_ring=compressible_ring, reference_siblings=reference_siblings)
+                             compressible_ring=compressible_ring, reference_siblings=reference_siblings, byte_check=byte_check)
 
 
 def _flat_array(a):
@@ -140,12 +143,13 @@ def _nova_chain(L, call, handle, witness_size, data, want_witness):
 
 class WitnessCalculator:
     def __init__(self, circuit, sanity_check, device=-1, chunk=0, lazy=False, fused_check=False, compressible_ring=True,
-                 reference_siblings=False):
+                 reference_siblings=False, byte_check=False):
         L = _lib.lib()
         self._L, self._ctx = L, None
         self._cfg = _lib.Config(circuit, device, chunk, (_lib.B3W_FLAG_FUSED_CHECK if fused_check else 0) |
                                 (0 if compressible_ring else _lib.B3W_FLAG_PLAIN_RING) |
-                                (_lib.B3W_FLAG_REFERENCE_SIBLINGS if reference_siblings else 0))
+                                (_lib.B3W_FLAG_REFERENCE_SIBLINGS if reference_siblings else 0) |
+                                (_lib.B3W_FLAG_BYTE_CHECK if byte_check else 0))
         info = _lib.Info()
         _lib.check(L.b3w_circuit_info(circuit, C.byref(info)))
         if not lazy:
@@ -531,7 +535,8 @@ class MultiGpuCalculator:
     """NEW: the batched entry point over several GPUs of one node (b3w_multi_*, include/blake3wit.h): contiguous index
     ranges, one context and host thread per device, no collective.  devices=None takes every visible device."""
 
-    def __init__(self, circuit, devices=None, chunk=0, fused_check=False, compressible_ring=True, reference_siblings=False):
+    def __init__(self, circuit, devices=None, chunk=0, fused_check=False, compressible_ring=True, reference_siblings=False,
+                 byte_check=False):
         L = _lib.lib()
         self._L = L
         cid = circuit if isinstance(circuit, int) else (CIRCUIT_IDS[circuit] if isinstance(circuit, str) else circuit_from_wasm(circuit))
@@ -540,7 +545,8 @@ class MultiGpuCalculator:
         self.circuit, self.witnessSize, self.nInputs, self.nPublic = cid, info.witness_size, info.n_inputs, info.n_public
         cfg = _lib.Config(cid, -1, chunk, (_lib.B3W_FLAG_FUSED_CHECK if fused_check else 0) |
                           (0 if compressible_ring else _lib.B3W_FLAG_PLAIN_RING) |
-                          (_lib.B3W_FLAG_REFERENCE_SIBLINGS if reference_siblings else 0))
+                          (_lib.B3W_FLAG_REFERENCE_SIBLINGS if reference_siblings else 0) |
+                          (_lib.B3W_FLAG_BYTE_CHECK if byte_check else 0))
         devs = (C.c_int32 * len(devices))(*devices) if devices else None
         h = C.c_void_p()
         _lib.check(L.b3w_multi_create(C.byref(cfg), devs, len(devices) if devices else 0, C.byref(h)))

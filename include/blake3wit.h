@@ -37,6 +37,13 @@ extern "C" {
 #define B3W_FLAG_PLAIN_RING 4u   /* b3w_config.flags: keep the internal HBM ring of the host-buffer calls in ordinary (cudaMalloc) memory.
                                     Default everywhere (C, Python, N-API): compressible memory when the driver grants it, silently
                                     ordinary memory otherwise */
+#define B3W_FLAG_BYTE_CHECK 16u  /* b3w_config.flags: every host-buffer batch call (b3w_witness_batch*, also with out = NULL) re-reads each
+                                    chunk's witnesses from the HBM ring right after they were written and evaluates EVERY row of the
+                                    constraint system on those bytes (the kernel of b3w_r1cs_check_device): what a consumer does
+                                    with the vector it is handed (rust_fold/src/utils.rs:78-85), before the bytes leave the GPU.
+                                    status[i] = B3W_R1CS_VIOLATION and first_bad[i] = the row (numbering of b3w_r1cs_check_device) on a
+                                    miss; instances with "Assert Failed." keep that status.  Costs one read of the ring per chunk
+                                    (about as long as writing it); needs a constraint system (built in for all four circuits). */
 #define B3W_FLAG_REFERENCE_SIBLINGS 8u /* b3w_config.flags, b3w_nova_chain*: pick the sibling of every parent step exactly as the
                                     reference does (rust_fold/src/blake3_hash.rs:60-78, by bit of the chunk index) instead of the
                                     BLAKE3 tree's true sibling; see b3w_nova_chain */
@@ -124,7 +131,8 @@ int b3w_witness_batch(b3w_ctx *ctx, const uint32_t *in, uint64_t n, uint8_t *out
  *              (rust_fold/src/utils.rs:78-85 enforces every row on the vector it was handed).
  *   sample_idx n_samples instance indices in [0, n), any order, n_samples <= B3W_MAX_SAMPLES: their full witnesses are
  *              copied out of the HBM ring into sample_out (n_samples * witness_size * 32 bytes), also when out == NULL.
- *   first_bad  n u32: with the fused check, the smallest violated row id or B3W_NO_ROW. */
+ *   first_bad  n u32: with the fused check (B3W_FLAG_FUSED_CHECK) the smallest violated row id of the fused system or B3W_NO_ROW;
+ *              with B3W_FLAG_BYTE_CHECK the verdict of the stand-alone checker on the stored bytes (its row numbering) instead. */
 typedef struct {
   uint64_t *sums;
   const uint64_t *sample_idx;

@@ -78,6 +78,9 @@ extern "C" {
 pub const B3W_NOVA_PASTA_O2: u32 = 2; // ../build/blake3_nova_pasta_js/blake3_nova_pasta.wasm (main.rs:364-365)
 pub const B3W_FLAG_FUSED_CHECK: u32 = 1;
 pub const B3W_FLAG_REFERENCE_SIBLINGS: u32 = 8;
+/// every chunk is re-read from the HBM ring and all rows are evaluated on its bytes (what `synthesize_with_vec`, utils.rs:78-85,
+/// would enforce on the vector) before the witnesses leave the GPU
+pub const B3W_FLAG_BYTE_CHECK: u32 = 16;
 pub const IO_ARITY: usize = 15; // blake3_circuit.rs:15
 
 fn last_error() -> String {

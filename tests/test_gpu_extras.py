@@ -171,3 +171,37 @@ def test_entry_points_restore_the_callers_device(built):
     assert cudart.cudaGetDevice()[1] == 0
     wc.close()
     m.close()
+
+
+def test_byte_check_flag_checks_what_lies_in_the_ring(built):
+    """B3W_FLAG_BYTE_CHECK: every chunk is read back from the HBM ring and all rows of the constraint system are evaluated on
+    its bytes (the consumer's check, rust_fold/src/utils.rs:78-85) -- valid witnesses pass, "Assert Failed." stays."""
+    n = 5000
+    rows = gen.splitmix_nova_inputs(n, first=3)
+    rows[5, 14] = rows[5, 12]                                   # asserts
+    wc = pkg.builder("blake3_nova_pasta", device=0, chunk=1024, byte_check=True)
+    res = wc.calculateWitnessBatch(rows, want_witness=False, sums=True, first_bad=True)
+    _, want_sums, st = port.witness_batch("nova_pasta_o2", rows, nthreads=NCPU, want="both")
+    ok = st == 0
+    assert np.array_equal(res["status"] == 0, ok) and res["status"][5] == _lib.B3W_CIRCOM_ASSERT
+    assert (res["first_bad"] == _lib.B3W_NO_ROW).all()
+    assert np.array_equal(res["sums"][ok], want_sums[ok])
+    assert wc.lastTiming()["launches"] == 2 * ((n + 1023) // 1024)            # generator + checker per chunk
+    wc.close()
+
+
+def test_byte_check_reports_the_rows_of_the_standalone_checker(built):
+    wc = pkg.builder("blake3_compression", device=0, fused_check=True, byte_check=True, chunk=64)
+    rows = gen.lcg_compression_inputs(200)
+    wc.inject_fault(48 + 3, 1)                                  # the stored witnesses are faulty
+    res = wc.calculateWitnessBatch(rows, want_witness=True, first_bad=True)
+    assert (res["status"] == _lib.B3W_R1CS_VIOLATION).all()
+    # the same bytes through b3w_r1cs_check_device: same verdict, same row numbering
+    d = torch.from_numpy(np.ascontiguousarray(res["witness"])).cuda()
+    d_st = torch.full((200,), 255, dtype=torch.uint8, device="cuda")
+    d_bad = torch.zeros(200, dtype=torch.int32, device="cuda")
+    wc.r1cs_check_device(d.data_ptr(), 200, d_st.data_ptr(), d_bad.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert (d_st.cpu().numpy() == _lib.B3W_R1CS_VIOLATION).all()
+    assert np.array_equal(d_bad.cpu().numpy().view(np.uint32), res["first_bad"])
+    wc.close()
