@@ -128,6 +128,7 @@ static const circuit_def CIRCUITS[] = {
 };
 static const int N_CIRCUITS = sizeof(CIRCUITS) / sizeof(CIRCUITS[0]);
 
+#define B3W_DEFAULT_CHUNK 4096u    // instances per ring slot: 8.4 M witnesses/s at 1 024, 10.5 at 2 048, 10.75 from 4 096 on (profiles/r02z_chunk_sweep.jsonl)
 #define N_SCHED_COUNTERS 64       // launches in flight on different streams each need their own counter set
 #define SCHED_SET_U64 (SCHED_LANES * SCHED_STRIDE)
 #define B3W_RING_SLOTS 2
@@ -180,6 +181,7 @@ struct b3w_ctx {
   uint8_t *d_fr[2] = {};         // Fr256 input rows of the chunk (b3w_witness_batch_fr), chunk x n_inputs x 32 bytes
   uint32_t *d_wlist[2] = {};     // nova: indices (inside the chunk) of the instances that hold a field-valued input; [0] = count
   bool ring_ready = false, fr_ready = false;
+  uint32_t ring_cap = 0;         // instances per ring slot as allocated: grows with the largest batch seen, up to `chunk`
   uint32_t m_slot0 = 0;          // compression only: witness slot of m[0] (the 16 m slots are consecutive)
   // nova only, built on first use: the wide (field-element input) kernel's override list
   uint2 *d_wslots = nullptr;
@@ -258,7 +260,7 @@ static int b3w_create_impl(const b3w_config *cfg, b3w_ctx **out) {
   c->device = dev;
   dev_guard dg(dev);                              // the caller's current device is restored on every path out
   if (dg.err != cudaSuccess) { delete c; return fail(B3W_ERR_CUDA, "cudaSetDevice(%d): %s", dev, cudaGetErrorString(dg.err)); }
-  c->chunk = cfg->chunk ? cfg->chunk : 1024;
+  c->chunk = cfg->chunk ? cfg->chunk : B3W_DEFAULT_CHUNK;
   c->flags = cfg->flags;
   c->fault_word = B3W_NO_ROW;
   cudaError_t e1 = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, dev);
@@ -410,6 +412,7 @@ static void free_ring(b3w_ctx *c) {
   }
   c->ring_ready = false;
   c->fr_ready = false;
+  c->ring_cap = 0;
 }
 
 static void free_fastprog(fastprog_dev *p);
@@ -1065,8 +1068,9 @@ extern "C" int b3w_debug_set_store_mode(b3w_ctx *c, int mode) {
   return B3W_OK;
 }
 
-static int alloc_ring(b3w_ctx *c) {
+static int alloc_ring(b3w_ctx *c, uint32_t cap) {
   const circuit_def *d = c->def;
+  c->ring_cap = cap;
   for (int k = 0; k < 2; k++) {
     CK(cudaStreamCreateWithFlags(&c->st[k], cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->ev[k], cudaEventDisableTiming));
@@ -1075,21 +1079,28 @@ static int alloc_ring(b3w_ctx *c) {
     // compressible unless the caller asked for ordinary memory; a driver without the virtual-memory entry points (or a
     // device that does not grant compression) silently gets ordinary memory -- one default in C, Python and the N-API addon
     if ((c->flags & B3W_FLAG_PLAIN_RING) ||
-        device_alloc(c, (size_t)c->chunk * d->ws * 32, B3W_MEM_COMPRESSIBLE, (void **)&c->d_ring[k]) != B3W_OK)
-      CK(cudaMalloc(&c->d_ring[k], (size_t)c->chunk * d->ws * 32));
-    CK(cudaMalloc(&c->d_in[k], (size_t)c->chunk * d->n_inputs * 4));
-    CK(cudaMalloc(&c->d_status[k], (size_t)c->chunk));
-    CK(cudaMalloc(&c->d_pub[k], (size_t)c->chunk * d->n_public * 4));
-    CK(cudaMalloc(&c->d_sums[k], (size_t)c->chunk * 8));
-    CK(cudaMalloc(&c->d_fbad[k], (size_t)c->chunk * 4));
-    if (!d->nova) CK(cudaMalloc(&c->d_ext[k], (size_t)c->chunk * 16));
+        device_alloc(c, (size_t)cap * d->ws * 32, B3W_MEM_COMPRESSIBLE, (void **)&c->d_ring[k]) != B3W_OK)
+      CK(cudaMalloc(&c->d_ring[k], (size_t)cap * d->ws * 32));
+    CK(cudaMalloc(&c->d_in[k], (size_t)cap * d->n_inputs * 4));
+    CK(cudaMalloc(&c->d_status[k], (size_t)cap));
+    CK(cudaMalloc(&c->d_pub[k], (size_t)cap * d->n_public * 4));
+    CK(cudaMalloc(&c->d_sums[k], (size_t)cap * 8));
+    CK(cudaMalloc(&c->d_fbad[k], (size_t)cap * 4));
+    if (!d->nova) CK(cudaMalloc(&c->d_ext[k], (size_t)cap * 16));
   }
   return B3W_OK;
 }
 // the two ring slots exist completely or not at all (a half-built ring is released before the error is returned)
-static int ensure_ring(b3w_ctx *c) {
-  if (c->ring_ready) return B3W_OK;
-  const int rc = alloc_ring(c);
+// Sized for the call at hand: min(chunk, n) instances per slot, rounded up to a power of two (at least 64), so that a
+// context used for single witnesses (b3w_witness_one, the CLI) never maps gigabytes; a larger batch re-creates the ring
+// (the slots are idle here: every host-buffer call drains its streams before it returns, under the context's lock).
+static int ensure_ring(b3w_ctx *c, uint64_t n) {
+  uint32_t need = 64;
+  while (need < c->chunk && need < n) need <<= 1;
+  if (need > c->chunk) need = c->chunk;
+  if (c->ring_ready && c->ring_cap >= need) return B3W_OK;
+  free_ring(c);
+  const int rc = alloc_ring(c, need);
   if (rc) { free_ring(c); return rc; }
   c->ring_ready = true;
   return B3W_OK;
@@ -1098,8 +1109,8 @@ static int ensure_ring(b3w_ctx *c) {
 static int ensure_fr_staging(b3w_ctx *c) {
   if (c->fr_ready) return B3W_OK;
   for (int k = 0; k < 2; k++) {
-    CK(cudaMalloc(&c->d_fr[k], (size_t)c->chunk * c->def->n_inputs * 32));
-    if (c->def->nova) CK(cudaMalloc(&c->d_wlist[k], ((size_t)c->chunk + 1) * 4));
+    CK(cudaMalloc(&c->d_fr[k], (size_t)c->ring_cap * c->def->n_inputs * 32));          // (free_ring releases these with the ring)
+    if (c->def->nova) CK(cudaMalloc(&c->d_wlist[k], ((size_t)c->ring_cap + 1) * 4));
   }
   c->fr_ready = true;
   return B3W_OK;
@@ -1191,7 +1202,7 @@ static int batch_chunks(b3w_ctx *c, const batch_job &J) {
   uint64_t done = 0;
   int k = 0;
   while (done < J.n) {
-    const uint64_t m = J.n - done < c->chunk ? J.n - done : c->chunk;
+    const uint64_t m = J.n - done < c->ring_cap ? J.n - done : c->ring_cap;
     cudaStream_t s = c->st[k];
     launch_opts o;
     o.check = check;
@@ -1288,7 +1299,7 @@ static int batch_host(b3w_ctx *c, const batch_job &J, const char *who) {
   nvtx_range r(who);
   timing_begin(c);
   c->timing.instances = J.n;
-  int rc = ensure_ring(c);
+  int rc = ensure_ring(c, J.n);
   if (rc == B3W_OK && J.in_fr) rc = ensure_fr_staging(c);
   if (rc == B3W_OK && J.in_fr && c->def->nova) rc = ensure_nova_wide(c);
   if (rc) return rc;
@@ -1656,9 +1667,9 @@ struct chain_sink {
 // Steps of chunks [lo, hi) of the file: this device hashes the whole tree (cheap), builds the rows of its chunks and
 // generates their step witnesses; outputs are the caller's FULL arrays, written at this range's offsets.
 static int nova_chain_steps(b3w_ctx *c, const chain_plan &p, const uint8_t *data, uint64_t len, uint64_t lo, uint64_t hi, const chain_sink &K) {
-  int rc = ensure_ring(c);
-  if (rc) return rc;
   const uint64_t nc = p.nc, first = p.step_off[lo], total = p.step_off[hi] - first;
+  int rc = ensure_ring(c, total);
+  if (rc) return rc;
   uint8_t *d_data; uint32_t *d_cv, *d_nodes, *d_path, *d_depth, *d_rows, *d_root; uint64_t *d_off;
   const size_t padded = (size_t)nc * 1024;
   if ((rc = chain_scratch(c, CS_DATA, padded, (void **)&d_data))) return rc;
@@ -1714,7 +1725,7 @@ static int nova_chain_steps(b3w_ctx *c, const chain_plan &p, const uint8_t *data
   uint64_t done = 0;
   int k = 0;
   while (done < total) {
-    const uint64_t m = total - done < c->chunk ? total - done : c->chunk;
+    const uint64_t m = total - done < c->ring_cap ? total - done : c->ring_cap;
     cudaStream_t s = c->st[k];
     launch_opts o;
     o.check = check;

@@ -65,7 +65,9 @@ typedef enum {
 typedef struct {
   uint32_t circuit;        /* b3w_circuit */
   int32_t device;          /* CUDA device ordinal; -1 = current device */
-  uint32_t chunk;          /* instances per internal HBM ring slot for host-buffer batches; 0 = default */
+  uint32_t chunk;          /* most instances per internal HBM ring slot for host-buffer batches; 0 = default (4096: two slots of
+                              3.2 GB at full size).  The ring is created at the first batch call, sized for that call (a power of
+                              two >= 64, <= chunk) and re-created when a larger batch arrives. */
   uint32_t flags;          /* 0 or an OR of B3W_FLAG_* */
 } b3w_config;
 

@@ -205,3 +205,28 @@ def test_byte_check_reports_the_rows_of_the_standalone_checker(built):
     assert (d_st.cpu().numpy() == _lib.B3W_R1CS_VIOLATION).all()
     assert np.array_equal(d_bad.cpu().numpy().view(np.uint32), res["first_bad"])
     wc.close()
+
+
+def test_ring_grows_with_the_batch(built):
+    """the HBM ring is sized for the call at hand (min(chunk, n) rounded up to a power of two) and re-created when a larger
+    batch arrives: same bytes whatever the order of the calls"""
+    wc = pkg.builder("blake3_compression", device=0)            # default chunk
+    rows = gen.lcg_compression_inputs(300)
+    want = port.witness_batch("compression", rows, nthreads=NCPU)
+    for n in (1, 70, 300, 5, 129):
+        res = wc.calculateWitnessBatch(rows[:n], sums=True)
+        assert not res["status"].any() and np.array_equal(res["witness"], want[:n]), n
+    # the Fr256 staging follows the ring: field-element rows before and after a growth
+    import ctypes as C
+    L = pkg.lib()
+    big = gen.lcg_compression_inputs(3000)
+    want_big = port.witness_batch("compression", big, nthreads=NCPU, want="sums")
+    for n in (200, 3000):
+        fr = np.zeros((n, 28, 32), np.uint8)
+        fr[:, :, :4] = big[:n].view(np.uint8).reshape(n, 28, 4)
+        st, pub, sums = np.zeros(n, np.uint8), np.zeros((n, 16), np.uint32), np.zeros(n, np.uint64)
+        ex = _lib.BatchExtras()
+        ex.sums = sums.ctypes.data
+        _lib.check(L.b3w_witness_batch_fr_ex(wc._h, fr.ctypes.data, n, None, st.ctypes.data, pub.ctypes.data, C.byref(ex)))
+        assert not st.any() and np.array_equal(sums, want_big[:n]), n
+    wc.close()
