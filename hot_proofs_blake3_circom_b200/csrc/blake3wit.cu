@@ -1253,7 +1253,9 @@ static int batch_chunks(b3w_ctx *c, const batch_job &J) {
       if (byte_check) {
         // every witness of the chunk is read back from the ring slot and ALL rows of the constraint system are evaluated on
         // its bytes (what a consumer does with the vector it is handed, rust_fold/src/utils.rs:78-85): a wrong slot
-        // descriptor, a wrong split or a lost store cannot pass, which the fused check -- it sees the trace -- cannot say
+        // descriptor, a wrong split or a lost store cannot pass, which the fused check -- it sees the trace -- cannot say.
+        // (Making chunk k + 1's generator run beside this checker, with fewer checker CTAs per SM so that both are resident,
+        // was measured: 5.65 -> 5.85 M witnesses/s at best, slower for 4 096-instance slots; profiles/r02z_byte_check_overlap_sweep.jsonl)
         rc = r1cs_check_launch(c, c->d_ring[k], nullptr, m, c->d_status[k], o.d_first_bad, s, false, /*skip_asserted=*/true);
         if (rc) return rc;
         c->timing.launches++;
