@@ -118,18 +118,38 @@ __device__ __forceinline__ void ld_slot(const uint8_t *p, uint32_t x[8]) {
   x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
 }
 
+// ---- the kernel's shared memory: the compact copy (dynamic) and four control words.  Every access goes through fp_smem
+// BY NAME: a pointer handed to an out-of-line function is a generic address to the compiler (LD.E / ST.E with 64-bit
+// address arithmetic instead of LDS / STS -- the first compiled row pass had 619 generic loads and 13 LDS) ----
+extern __shared__ __align__(16) uint8_t fp_smem[];
+__shared__ uint32_t fp_s_bad, fp_s_flags, fp_s_tile;
+__shared__ unsigned long long fp_s_it;
+struct fp_copy {                  // isbit | bitval | rank (mw words each; rank is the launch's constant side_rank) | side (8-byte entries)
+  uint32_t *isbit, *bitval, *rank;
+  uint64_t *side;
+  __device__ __forceinline__ explicit fp_copy(uint32_t mw) {
+    isbit = reinterpret_cast<uint32_t *>(fp_smem);
+    bitval = isbit + mw;
+    rank = bitval + mw;
+    side = reinterpret_cast<uint64_t *>(fp_smem + (size_t)((3 * mw + 1) & ~1u) * 4);
+  }
+};
+
 struct CompactSrc {
   // several CTAs per SM walk the same tables: let them live in L1
   static __device__ __forceinline__ uint32_t ld_table(const uint32_t *p) { return __ldg(p); }
-  const uint32_t *isbit, *bitval, *rank;     // shared: one bit per slot (x2), side-table base of each 32-slot word
-  const uint64_t *side;                      // shared: tagged values of the non-bit slots
+  uint32_t mw;                               // words per map: the copy is found in fp_smem by name (see fp_copy)
+  __device__ __forceinline__ const uint32_t *isbit() const { return reinterpret_cast<const uint32_t *>(fp_smem); }       // one bit per slot: holds 0 or 1
+  __device__ __forceinline__ const uint32_t *bitval() const { return isbit() + mw; }                                      // ... its value
+  __device__ __forceinline__ const uint32_t *rank() const { return isbit() + 2u * mw; }                                   // side-table base of each 32-slot word
+  __device__ __forceinline__ const uint64_t *side() const { return reinterpret_cast<const uint64_t *>(fp_smem + (size_t)((3 * mw + 1) & ~1u) * 4); }
   const uint8_t *wit;                        // this instance's witness in HBM
   const field_consts *F;
   bool side_ok;                              // false: an irregular instance (non-bit slots where the circuit's layout has none): values from HBM
   __device__ __forceinline__ uint64_t get(uint32_t s) const {
-    const uint32_t w = s >> 5, b = s & 31u, m = isbit[w];
-    if ((m >> b) & 1u) return (bitval[w] >> b) & 1u;
-    if (side_ok) return side[rank[w] + __popc(~m & ((1u << b) - 1u))];
+    const uint32_t w = s >> 5, b = s & 31u, m = isbit()[w];
+    if ((m >> b) & 1u) return (bitval()[w] >> b) & 1u;
+    if (side_ok) return side()[rank()[w] + __popc(~m & ((1u << b) - 1u))];
     bool nc = false;                         // (a non-canonical slot was already reported by the streaming pass)
     uint32_t x[8];
     ld_slot(wit + (size_t)s * 32, x);
@@ -157,9 +177,9 @@ struct CompactSrc {
     return len >= 32u ? v : v & ((1u << len) - 1u);
   }
   __device__ __forceinline__ bool run_is_bits(uint32_t s, uint32_t len) const {
-    return field_of(isbit, s, len) == (len >= 32u ? 0xFFFFFFFFu : (1u << len) - 1u);
+    return field_of(isbit(), s, len) == (len >= 32u ? 0xFFFFFFFFu : (1u << len) - 1u);
   }
-  __device__ __forceinline__ uint32_t run_value(uint32_t s, uint32_t len) const { return field_of(bitval, s, len); }
+  __device__ __forceinline__ uint32_t run_value(uint32_t s, uint32_t len) const { return field_of(bitval(), s, len); }
 };
 
 __device__ __forceinline__ int fp_bitlen64(uint64_t x) { return 64 - __clzll((long long)x); }
@@ -280,9 +300,10 @@ __device__ __forceinline__ i128 fp_term(const CompactSrc &src, const uint4 raw, 
 // exactly and must be 0 or its unit u; the bit goes into the maps at slot 32 * words + index, where the rewritten rows
 // read it like any other bit.  A definition that is neither (or cannot be decided in integers), or a witness whose slot 0
 // is not 1, raises bit 1 of *flags: the caller then evaluates the instance with the program compiled without virtual bits.
-__device__ __noinline__ void fp_eval_virtuals(const CompactSrc &src, const fastprog_dev &P, uint32_t words, uint32_t *isbit, uint32_t *bitval,
-                                              uint32_t *flags) {
+__device__ __noinline__ void fp_eval_virtuals(const CompactSrc &src, const fastprog_dev &P, uint32_t words) {
   const uint32_t tid = threadIdx.x, lane = tid & 31u;
+  const fp_copy m(src.mw);
+  uint32_t *const isbit = m.isbit, *const bitval = m.bitval, *const flags = &fp_s_flags;
   if (tid == 0 && src.get(0) != 1ull) atomicOr(flags, 2u);
   for (uint32_t g = tid >> 5; g < P.n_vtiles; g += FPK_THREADS / 32) {
     const uint4 h = __ldg(reinterpret_cast<const uint4 *>(P.vtiles) + g);
@@ -473,10 +494,9 @@ __device__ __noinline__ uint32_t fp_eval_residual(const CompactSrc &src, const r
 
 // every row of one instance from the compact copy (all threads of the CTA; each returns its own smallest violated row id).
 // Out of line: the streaming loop of the kernel keeps its registers for loads in flight.
-__device__ __noinline__ uint32_t fp_eval_rows(const CompactSrc &src, const fastprog_dev &P, const r1cs_tables_dev &T, uint32_t words,
-                                               uint32_t *next_tile /* shared, 0 at entry */) {
+__device__ __noinline__ uint32_t fp_eval_rows(const CompactSrc &src, const fastprog_dev &P, const r1cs_tables_dev &T, uint32_t words) {
   const uint32_t tid = threadIdx.x, lane = tid & 31u;
-  const uint32_t *isbit = src.isbit;
+  const uint32_t *isbit = src.isbit();
   uint32_t bad = B3W_NO_ROW;
   const bool one_ok = src.get(0) == 1ull;                 // wire 0 holds the constant 1
   // ---- booleanity rows: the slots of the mask must be bits ----
@@ -498,7 +518,7 @@ __device__ __noinline__ uint32_t fp_eval_rows(const CompactSrc &src, const fastp
   // by decreasing cost: a warp that meets rows for the Fr path does not end up holding the CTA's barrier alone) ----
   for (;;) {
     uint32_t t = 0;
-    if (lane == 0) t = atomicAdd(next_tile, 1u);
+    if (lane == 0) t = atomicAdd(&fp_s_tile, 1u);           // (0 at entry)
     t = __shfl_sync(0xffffffffu, t, 0);
     if (t >= P.n_tiles) break;
     const uint4 h = __ldg(reinterpret_cast<const uint4 *>(P.tiles) + t);
@@ -515,21 +535,6 @@ __device__ __noinline__ uint32_t fp_eval_rows(const CompactSrc &src, const fastp
   if (T.n_classes) bad = min(bad, fp_eval_residual(src, T, one_ok));
   return bad;
 }
-
-// ---- the kernel's shared memory: the compact copy (dynamic) and four control words ----
-extern __shared__ __align__(16) uint8_t fp_smem[];
-__shared__ uint32_t fp_s_bad, fp_s_flags, fp_s_tile;
-__shared__ unsigned long long fp_s_it;
-struct fp_copy {                  // isbit | bitval | rank (mw words each; rank is the launch's constant side_rank) | side (8-byte entries)
-  uint32_t *isbit, *bitval, *rank;
-  uint64_t *side;
-  __device__ __forceinline__ explicit fp_copy(uint32_t mw) {
-    isbit = reinterpret_cast<uint32_t *>(fp_smem);
-    bitval = isbit + mw;
-    rank = bitval + mw;
-    side = reinterpret_cast<uint64_t *>(fp_smem + (size_t)((3 * mw + 1) & ~1u) * 4);
-  }
-};
 
 struct fp_stream_args {
   const uint8_t *w;               // this instance's witness in HBM
@@ -639,12 +644,12 @@ k_r1cs_check_fast(const uint8_t *__restrict__ wit, const uint32_t *__restrict__ 
     __syncthreads();
     uint32_t bad = B3W_NO_ROW;
     if (!(fp_s_flags & 1u) && FPK_EXP == 0) {
-      const CompactSrc src{isbit, bitval, m.rank, m.side, w, F, (fp_s_flags & 4u) == 0};
+      const CompactSrc src{mw, w, F, (fp_s_flags & 4u) == 0};
       if (P.n_vtiles) {                                       // CTA-uniform
-        fp_eval_virtuals(src, P, words, isbit, bitval, &fp_s_flags);
+        fp_eval_virtuals(src, P, words);
         __syncthreads();
       }
-      bad = (fp_s_flags & 2u) ? fp_eval_rows(src, P0, T, words, &fp_s_tile) : fp_eval_rows(src, P, T, words, &fp_s_tile);
+      bad = (fp_s_flags & 2u) ? fp_eval_rows(src, P0, T, words) : fp_eval_rows(src, P, T, words);
     }
     if (bad != B3W_NO_ROW) atomicMin(&fp_s_bad, bad);
     __syncthreads();
