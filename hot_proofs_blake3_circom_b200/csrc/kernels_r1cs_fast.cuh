@@ -35,7 +35,8 @@
 // -> rotating-register streaming loop, instances from a global counter, side-table places from the circuit's layout
 // instead of a shared-memory counter: 8.6 M/s (1.02; 11.9 M/s from compressible buffers), nova O2 8.0 (0.92), O1 7.0 (0.85).
 // Measured and dropped on the way (profiles/r02z_*): L2 prefetch of the next instance, staggered CTA starts, 9 and 10 CTAs
-// per SM (the program tables lose their L1), an unrolled tile loop (instruction cache).
+// per SM (the program tables lose their L1), an unrolled tile loop (instruction cache), table entries and tile headers
+// loaded one step ahead in the row pass (the extra live registers spill: +1..2 %).
 #pragma once
 
 #ifndef FPK_EXP
