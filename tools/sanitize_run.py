@@ -93,4 +93,12 @@ for name, rows in (("blake3_compression", gen.splitmix_compression_inputs(70)), 
         d_o = torch.zeros(ns * wc.witnessSize * 32, dtype=torch.uint8, device="cuda")
         wc.novaChainDevice(data, d_o.data_ptr())
     wc.close()
+# round 2, second half: B3W_FLAG_BYTE_CHECK (the stand-alone checker -- rotating-register streaming loop, instances from a
+# global counter, side-table places from the slot layout -- chained to the generator on the ring) and the growing ring
+for name, rows in (("blake3_compression", gen.splitmix_compression_inputs(150)), ("blake3_nova_o1", gen.splitmix_nova_inputs(90))):
+    wc = pkg.builder(name, device=0, byte_check=True)
+    for n in (3, len(rows)):
+        res = wc.calculateWitnessBatch(rows[:n], want_witness=False, sums=True, first_bad=True)
+        assert not (res["status"] & 3).any()
+    wc.close()
 print("sanitize_run done")
