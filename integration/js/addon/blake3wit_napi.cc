@@ -22,18 +22,19 @@ static napi_value throw_b3w(napi_env env, int rc) {
   return NULL;
 }
 
-// create(circuit, device) -> external(handle)
+// create(circuit, device[, flags]) -> external(handle)      flags: an OR of B3W_FLAG_* (fused check 1, byte check 16, ...)
 struct handle { b3w_ctx *ctx; uint32_t circuit; };
 static void ctx_finalize(napi_env, void *data, void *) { b3w_destroy(((handle *)data)->ctx); free(data); }
 static napi_value Create(napi_env env, napi_callback_info info) {
-  size_t argc = 2; napi_value argv[2];
+  size_t argc = 3; napi_value argv[3];
   NAPI_OK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
-  uint32_t circuit; int32_t device;
+  uint32_t circuit, flags = 0; int32_t device;
   NAPI_OK(napi_get_value_uint32(env, argv[0], &circuit));
   NAPI_OK(napi_get_value_int32(env, argv[1], &device));
+  if (argc >= 3) NAPI_OK(napi_get_value_uint32(env, argv[2], &flags));
   // flags 0 = the library's one default everywhere: the HBM ring of the host-buffer calls is compressible memory where the
   // GPU offers it and silently ordinary memory otherwise (B3W_FLAG_PLAIN_RING opts out)
-  b3w_config cfg = {circuit, device, 0, 0};
+  b3w_config cfg = {circuit, device, 0, flags};
   b3w_ctx *ctx = NULL;
   int rc = b3w_create(&cfg, &ctx);
   if (rc) return throw_b3w(env, rc);

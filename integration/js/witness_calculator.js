@@ -27,7 +27,10 @@ module.exports = async function builder(code, options) {
         return require("./witness_calculator.wasm.js")(code, options);      // the reference path, untouched
     }
     const addon = require("./build/Release/blake3wit_napi.node");
-    return new WitnessCalculator(addon, addon.create(circuit, options.device === undefined ? -1 : options.device), circuit, options);
+    // options.fusedCheck: the fused on-device R1CS check with every batch (B3W_FLAG_FUSED_CHECK); options.byteCheck: every chunk
+    // is re-read from HBM and all rows are evaluated on its bytes before results leave the GPU (B3W_FLAG_BYTE_CHECK)
+    const flags = (options.fusedCheck ? 1 : 0) | (options.byteCheck ? 16 : 0);
+    return new WitnessCalculator(addon, addon.create(circuit, options.device === undefined ? -1 : options.device, flags), circuit, options);
 };
 
 class WitnessCalculator {

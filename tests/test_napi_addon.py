@@ -211,3 +211,18 @@ def test_nova_field_element_inputs_through_the_addon(napi):
                 napi.await_(call)
             assert str(e.value) == "Error: Assert Failed.\n" + bytes(text[i]).decode()
     assert seen == {0, 4}
+
+
+@pytest.mark.gpu
+def test_create_with_flags_byte_check(napi, cases):
+    """create(circuit, device, flags): a context with B3W_FLAG_BYTE_CHECK (16) checks every witness where it lies in the HBM
+    ring -- the fixture's witnesses pass and come back unchanged; unknown flags are refused with the library's text"""
+    L = napi.L
+    h = napi.call("create", L.mk_u32(0), L.mk_i32(0), L.mk_u32(16))
+    rows, want = cases["rows"], cases["witness"]
+    n = rows.shape[0]
+    res = napi.await_(napi.call("witnessBatch", h, napi.typed(rows.reshape(-1)), L.mk_u32(n), L.mk_bool(1)))
+    assert (napi.array_of(napi.get(res, "status")) == 0).all()
+    assert napi.array_of(napi.get(res, "witness")).tobytes() == want.tobytes()
+    with pytest.raises(RuntimeError, match="unknown flags"):
+        napi.call("create", L.mk_u32(0), L.mk_i32(0), L.mk_u32(1 << 20))
