@@ -457,6 +457,39 @@ def run_own(args, rank, world, local_rank):
                     "check on the trace the stand-alone checker (k_r1cs_check_fast) re-reads every witness from the HBM ring and evaluates "
                     "every row on the bytes that were stored")
 
+    # --- BASELINE configs[2]: all Nova step witnesses of a synthetic 1 MiB file through b3w_nova_chain (every rank chains its
+    # own file: weak), and a 64 MiB file for a sustained figure -------------------------------------------------------------
+    def chained(mib, reps_target_s):
+        import blake3
+        from hot_proofs_blake3_circom_b200.witness_calculator import pinned_array
+        calc = pkg.builder("blake3_nova", device=local_rank, chunk=16384)
+        data = gen.splitmix_words(0xB3B30003 + rank, np.arange(mib << 18, dtype=np.uint64), 1)[:, 0].tobytes()
+        nc, ns = C.c_uint64(), C.c_uint64()
+        _lib.check(L.b3w_nova_chain_size(len(data), C.byref(nc), C.byref(ns)))
+        ns = ns.value
+        rows, status, pubz = pinned_array((ns, 32), np.uint32), pinned_array((ns,), np.uint8), pinned_array((ns, 15), np.uint32)
+        h_data = pinned_array((len(data),), np.uint8)
+        h_data[:] = np.frombuffer(data, np.uint8)
+        step_off, root = np.zeros(nc.value + 1, np.uint64), np.zeros(32, np.uint8)
+        call = lambda: L.b3w_nova_chain(calc._h, h_data.ctypes.data, len(data), None, status.ctypes.data, pubz.ctypes.data,
+                                        rows.ctypes.data, step_off.ctypes.data, root.ctypes.data)
+        t1 = wall(call, 1, warm=2)
+        reps = max(3, int(reps_target_s / t1 + 0.999))
+        dt = wall(call, reps, warm=0)
+        digest = blake3.blake3(data).digest()
+        last = step_off[1:].astype(np.int64) - 1
+        folds = bool((pubz[last, 2:10].view(np.uint8).reshape(len(last), 32) == np.frombuffer(digest, np.uint8)).all())
+        assert root.tobytes() == digest and folds and not status.any(), "config3: chain does not fold to BLAKE3(file)"
+        res = {"value": world * ns / dt, "unit": "step witnesses/s", "file_MiB_per_gpu": mib, "chunks_per_gpu": nc.value, "step_witnesses_per_gpu": ns,
+               "seconds_per_file": dt, "files_timed": reps, "witness_bytes": calc.witnessSize * 32,
+               "ring_write_GBps_per_gpu": ns * calc.witnessSize * 32 / dt / 1e9, "root_is_blake3_of_file": True, "every_chunk_folds_to_root": folds}
+        calc.close()
+        return res
+    cfg3 = chained(1, 0.3)
+    cfg3["api"] = ("b3w_nova_chain(out=NULL): BASELINE configs[2], host bytes in -> device BLAKE3 tree, step rows, all 26 624 step witnesses "
+                   "(blake3_nova, BN254 O2 layout) through the HBM ring, z_{i+1} / status / rows back (pinned)")
+    cfg3["sustained_64MiB"] = chained(64, 0.5)
+
     # --- field-element rows (b3w_witness_batch_fr) next to u32 rows: 2^20 blake3_nova_pasta, N = 1 only ------------------
     fr_line = None
     if world == 1 and not args.no_fr:
@@ -558,7 +591,7 @@ def run_own(args, rank, world, local_rank):
                                 "compressible_buffer": None if chk_hbm_c_ms is None else {
                                     "value": world * n_chk / (chk_hbm_c_ms / 1e3), "kernel_ms": chk_hbm_c_ms, "read_gbs": n_chk * WIT_BYTES / chk_hbm_c_ms / 1e6},
                                 "nova": chk_nova},
-        "config4": cfg4, "config5": cfg5, "config5_byte_check": cfg5b,
+        "config3": cfg3, "config4": cfg4, "config5": cfg5, "config5_byte_check": cfg5b,
         "gpu_launches": gpu_launches, "clocks": clocks}
     if compressible:
         achieved_c = alg_bytes / kernel_ms / 1e6
