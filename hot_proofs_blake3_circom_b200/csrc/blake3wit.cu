@@ -628,6 +628,10 @@ static int install_slot_rows(b3w_ctx *c, std::vector<r1cs_load_detail::row> &row
   fastprog_host fp, fp0;
   std::vector<char> taken;
   compile_programs(rows, c->def->ws, fp, fp0, taken);
+  if (fp.n_virtual && ((c->def->ws + 31u) >> 5) + fp.vtiles.size() + 1u > FP_MAPW) {     // more virtual-bit words than the kernel's maps hold:
+    fp = std::move(fp0);                                                                   // the plainly compiled program alone (same rows)
+    fp0 = fastprog_host();
+  }
   std::vector<r1cs_load_detail::row> rest;
   for (size_t i = 0; i < rows.size(); i++)
     if (!taken[i]) rest.push_back(std::move(rows[i]));
@@ -901,7 +905,8 @@ static int r1cs_check_launch(b3w_ctx *c, const uint8_t *d_wit, const uint32_t *d
   const uint32_t mw = ((c->def->ws + 31u) >> 5) + c->fp.n_vtiles + 1u;
   // the side table holds the non-bit slots of the circuit's witness layout (install_slot_rows: side_rank / side_total); a
   // witness with non-bit slots elsewhere (not one of this circuit's) is still checked, those values are re-read from HBM
-  const size_t smem = (size_t)((3 * mw + 1) & ~1u) * 4 + (size_t)c->fp.side_total * 8;
+  if (mw > FP_MAPW) return fail(B3W_ERR_UNSUPPORTED, "%s: %u map words (the checker holds %u)", c->def->name, mw, FP_MAPW);
+  const size_t smem = (size_t)3 * FP_MAPW * 4 + (size_t)c->fp.side_total * 8;
   CK(cudaFuncSetAttribute(k_r1cs_check_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int per_sm = c->ctas_limit > 0 ? c->ctas_limit : FPK_CTAS_PER_SM;
   const uint64_t cap = (uint64_t)c->sm_count * per_sm;

@@ -125,32 +125,35 @@ __device__ __forceinline__ void ld_slot(const uint8_t *p, uint32_t x[8]) {
 extern __shared__ __align__(16) uint8_t fp_smem[];
 __shared__ uint32_t fp_s_bad, fp_s_flags, fp_s_tile;
 __shared__ unsigned long long fp_s_it;
-struct fp_copy {                  // isbit | bitval | rank (mw words each; rank is the launch's constant side_rank) | side (8-byte entries)
+#define FP_MAPW 784u               /* words per map: >= (slots + 31) / 32 + virtual-bit words + 1 of every system (checked on the host); a
+                                      CONSTANT so that no accessor needs a value from the (stack-resident) argument structs */
+struct fp_copy {                  // isbit | bitval | rank (FP_MAPW words each; rank is the launch's constant side_rank) | side (8-byte entries)
   uint32_t *isbit, *bitval, *rank;
   uint64_t *side;
-  __device__ __forceinline__ explicit fp_copy(uint32_t mw) {
+  __device__ __forceinline__ fp_copy() {
     isbit = reinterpret_cast<uint32_t *>(fp_smem);
-    bitval = isbit + mw;
-    rank = bitval + mw;
-    side = reinterpret_cast<uint64_t *>(fp_smem + (size_t)((3 * mw + 1) & ~1u) * 4);
+    bitval = isbit + FP_MAPW;
+    rank = bitval + FP_MAPW;
+    side = reinterpret_cast<uint64_t *>(fp_smem + 3u * FP_MAPW * 4u);
   }
 };
 
 struct CompactSrc {
   // several CTAs per SM walk the same tables: let them live in L1
   static __device__ __forceinline__ uint32_t ld_table(const uint32_t *p) { return __ldg(p); }
-  uint32_t mw;                               // words per map: the copy is found in fp_smem by name (see fp_copy)
-  __device__ __forceinline__ const uint32_t *isbit() const { return reinterpret_cast<const uint32_t *>(fp_smem); }       // one bit per slot: holds 0 or 1
-  __device__ __forceinline__ const uint32_t *bitval() const { return isbit() + mw; }                                      // ... its value
-  __device__ __forceinline__ const uint32_t *rank() const { return isbit() + 2u * mw; }                                   // side-table base of each 32-slot word
-  __device__ __forceinline__ const uint64_t *side() const { return reinterpret_cast<const uint64_t *>(fp_smem + (size_t)((3 * mw + 1) & ~1u) * 4); }
+  // the copy is found in fp_smem by name, at constant offsets (see fp_copy)
+  static __device__ __forceinline__ const uint32_t *isbit() { return reinterpret_cast<const uint32_t *>(fp_smem); }      // one bit per slot: holds 0 or 1
+  static __device__ __forceinline__ const uint32_t *bitval() { return isbit() + FP_MAPW; }                               // ... its value
+  static __device__ __forceinline__ const uint32_t *rank() { return isbit() + 2u * FP_MAPW; }                            // side-table base of each 32-slot word
+  static __device__ __forceinline__ const uint64_t *side() { return reinterpret_cast<const uint64_t *>(fp_smem + 3u * FP_MAPW * 4u); }
+  // false: an irregular instance (non-bit slots where the circuit's layout has none): such values are read from HBM
+  static __device__ __forceinline__ bool side_ok() { return (fp_s_flags & 4u) == 0; }
   const uint8_t *wit;                        // this instance's witness in HBM
   const field_consts *F;
-  bool side_ok;                              // false: an irregular instance (non-bit slots where the circuit's layout has none): values from HBM
   __device__ __forceinline__ uint64_t get(uint32_t s) const {
     const uint32_t w = s >> 5, b = s & 31u, m = isbit()[w];
     if ((m >> b) & 1u) return (bitval()[w] >> b) & 1u;
-    if (side_ok) return side()[rank()[w] + __popc(~m & ((1u << b) - 1u))];
+    if (side_ok()) return side()[rank()[w] + __popc(~m & ((1u << b) - 1u))];
     bool nc = false;                         // (a non-canonical slot was already reported by the streaming pass)
     uint32_t x[8];
     ld_slot(wit + (size_t)s * 32, x);
@@ -303,7 +306,7 @@ __device__ __forceinline__ i128 fp_term(const CompactSrc &src, const uint4 raw, 
 // is not 1, raises bit 1 of *flags: the caller then evaluates the instance with the program compiled without virtual bits.
 __device__ __noinline__ void fp_eval_virtuals(const CompactSrc &src, const fastprog_dev &P, uint32_t words) {
   const uint32_t tid = threadIdx.x, lane = tid & 31u;
-  const fp_copy m(src.mw);
+  const fp_copy m;
   uint32_t *const isbit = m.isbit, *const bitval = m.bitval, *const flags = &fp_s_flags;
   if (tid == 0 && src.get(0) != 1ull) atomicOr(flags, 2u);
   for (uint32_t g = tid >> 5; g < P.n_vtiles; g += FPK_THREADS / 32) {
@@ -540,7 +543,7 @@ __device__ __noinline__ uint32_t fp_eval_rows(const CompactSrc &src, const fastp
 struct fp_stream_args {
   const uint8_t *w;               // this instance's witness in HBM
   const field_consts *F;
-  uint32_t ws, words, mw;
+  uint32_t ws, words;
 };
 // one 32-slot word of the streaming pass from the registers x (lane = slot); then the load of word wu + ahead goes into x
 __device__ __forceinline__ void fp_stream_word(const fp_stream_args &c, const fp_copy &m, uint32_t lane, uint32_t (&x)[8], uint32_t wu,
@@ -580,7 +583,7 @@ __device__ __forceinline__ void fp_stream_word(const fp_stream_args &c, const fp
 __device__ __noinline__ void fp_stream(const fp_stream_args c) {
   constexpr uint32_t NW = FPK_THREADS / 32, AH = FPK_INFLIGHT * NW;
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const fp_copy m(c.mw);
+  const fp_copy m;
 #define FPK_SLOT_REGS(x, k) \
   uint32_t x[8] = {0, 0, 0, 0, 0, 0, 0, 0}; \
   ld_slot_stream_if(c.w + (size_t)min((warp + (k) * NW) * 32u + lane, c.ws - 1u) * 32, x, warp + (k) * NW < c.words)
@@ -616,7 +619,7 @@ k_r1cs_check_fast(const uint8_t *__restrict__ wit, const uint32_t *__restrict__ 
                   uint32_t *__restrict__ first_bad, unsigned long long *__restrict__ counter /* NULL: static round-robin; else 0 at launch */,
                   uint32_t skip_asserted /* leave instances whose status says "Assert Failed." alone: no witness exists for them */) {
   const uint32_t words = (ws + 31u) >> 5, mw = words + P.n_vtiles + 1u;      // virtual-bit words, one padding word per map (field_of reads w + 1)
-  const fp_copy m(mw);
+  const fp_copy m;
   uint32_t *const isbit = m.isbit, *const bitval = m.bitval;
   const uint32_t tid = threadIdx.x;
   // list != NULL: check the instances list[1 .. list[0]] (n is ignored)
@@ -641,11 +644,11 @@ k_r1cs_check_fast(const uint8_t *__restrict__ wit, const uint32_t *__restrict__ 
     }
     const uint8_t *w = wit + i * (uint64_t)ws * 32;
     // ---- stream the witness once into the compact copy ----
-    fp_stream(fp_stream_args{w, F, ws, words, mw});
+    fp_stream(fp_stream_args{w, F, ws, words});
     __syncthreads();
     uint32_t bad = B3W_NO_ROW;
     if (!(fp_s_flags & 1u) && FPK_EXP == 0) {
-      const CompactSrc src{mw, w, F, (fp_s_flags & 4u) == 0};
+      const CompactSrc src{w, F};
       if (P.n_vtiles) {                                       // CTA-uniform
         fp_eval_virtuals(src, P, words);
         __syncthreads();
