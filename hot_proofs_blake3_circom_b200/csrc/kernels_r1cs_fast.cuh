@@ -33,7 +33,8 @@
 // row blocks 2.33 M/s (0.27 of the read roofline; row arithmetic issue-bound) -> compiled program 7.8 M/s (nova O2 5.1)
 // -> virtual bits, fast tiles, dynamic hand-out, 128-thread CTAs: 8.2 M/s (0.96), nova O2 7.9 M/s (0.90), O1 6.8 (0.82)
 // -> rotating-register streaming loop, instances from a global counter, side-table places from the circuit's layout
-// instead of a shared-memory counter: 8.6 M/s (1.02; 11.9 M/s from compressible buffers), nova O2 8.0 (0.92), O1 7.0 (0.85).
+// instead of a shared-memory counter, the copy addressed through the shared array by name at constant offsets:
+// 8.7 M/s (1.03; 12.4 M/s from compressible buffers), nova O2 8.2 (0.94), O1 7.4 (0.89).
 // Measured and dropped on the way (profiles/r02z_*): L2 prefetch of the next instance, staggered CTA starts, 9 and 10 CTAs
 // per SM (the program tables lose their L1), an unrolled tile loop (instruction cache), table entries and tile headers
 // loaded one step ahead in the row pass (the extra live registers spill: +1..2 %).
