@@ -37,7 +37,8 @@
 // 8.7 M/s (1.03; 12.4 M/s from compressible buffers), nova O2 8.2 (0.94), O1 7.4 (0.89).
 // Measured and dropped on the way (profiles/r02z_*): L2 prefetch of the next instance, staggered CTA starts, 9 and 10 CTAs
 // per SM (the program tables lose their L1), an unrolled tile loop (instruction cache), table entries and tile headers
-// loaded one step ahead in the row pass (the extra live registers spill: +1..2 %).
+// loaded one step ahead in the row pass (the extra live registers spill: +1..2 %).  Kept: the booleanity / XOR loops without
+// a call inside (unsettled steps are noted in a mask and redone out of line afterwards): -1.5 % on the nova systems.
 #pragma once
 
 #ifndef FPK_EXP
@@ -504,20 +505,41 @@ __device__ __noinline__ uint32_t fp_eval_rows(const CompactSrc &src, const fastp
   const uint32_t *isbit = src.isbit();
   uint32_t bad = B3W_NO_ROW;
   const bool one_ok = src.get(0) == 1ull;                 // wire 0 holds the constant 1
+  // The two loops below contain NO call: a step that does not settle (a violation, or slots that are not bits) is only
+  // noted in a mask and redone out of line afterwards, so that the compiler is free to unroll and to have the table loads
+  // of several steps in flight (with the slow-path call inside, every step was a load -> use chain of an L1 / L2 latency).
   // ---- booleanity rows: the slots of the mask must be bits ----
-  for (uint32_t wd = tid; wd < words + P.n_vtiles; wd += FPK_THREADS) {     // (virtual bits: a word per group of definitions)
-    const uint32_t need = __ldg(P.bool_mask + wd);
-    uint32_t viol = need & ~isbit[wd];
-    if (!one_ok) viol = need;                               // x (x - w0) = 0 with w0 != 1: decide every row exactly
-    if (viol) bad = min(bad, fp_bool_word_slow(src, P, wd, viol, one_ok));
+  {
+    const uint32_t nw = words + P.n_vtiles;                 // (virtual bits: a word per group of definitions; <= FP_MAPW: 7 steps)
+    const uint32_t *__restrict__ bm = P.bool_mask;
+    uint32_t redo = 0;
+#pragma unroll 4
+    for (uint32_t j = 0, wd = tid; wd < nw; j++, wd += FPK_THREADS) {
+      const uint32_t need = __ldg(bm + wd);
+      const uint32_t viol = one_ok ? need & ~isbit[wd] : need;       // x (x - w0) = 0 with w0 != 1: decide every row exactly
+      if (viol) redo |= 1u << j;
+    }
+    for (; redo; redo &= redo - 1u) {                       // cold
+      const uint32_t wd = tid + ((uint32_t)__ffs((int)redo) - 1u) * FPK_THREADS, need = __ldg(bm + wd);
+      bad = min(bad, fp_bool_word_slow(src, P, wd, one_ok ? need & ~isbit[wd] : need, one_ok));
+    }
   }
   // ---- XOR rows: runs of consecutive (x, y, o) triples ----
-  for (uint32_t b = tid; b < P.n_xors; b += FPK_THREADS) {
-    const uint4 e = __ldg(reinterpret_cast<const uint4 *>(P.xors) + b);
-    const uint32_t len = e.w & 63u;
-    const bool bits = src.run_is_bits(e.x, len) && src.run_is_bits(e.y, len) && src.run_is_bits(e.z, len);
-    if (bits && (src.run_value(e.x, len) ^ src.run_value(e.y, len)) == src.run_value(e.z, len)) continue;
-    bad = min(bad, fp_xor_run_slow(src, P, e));             // some row of the run is violated or holds non-bits: row by row
+  {
+    const uint32_t nx = P.n_xors, nf = min(nx, 32u * FPK_THREADS);   // (the mask has 32 steps; the systems in use have 4 to 7)
+    const uint4 *__restrict__ xs = reinterpret_cast<const uint4 *>(P.xors);
+    uint32_t redo = 0;
+#pragma unroll 1
+    for (uint32_t j = 0, b = tid; b < nf; j++, b += FPK_THREADS) {
+      const uint4 e = __ldg(xs + b);
+      const uint32_t len = e.w & 63u;
+      const bool bits = src.run_is_bits(e.x, len) && src.run_is_bits(e.y, len) && src.run_is_bits(e.z, len);
+      if (!(bits && (src.run_value(e.x, len) ^ src.run_value(e.y, len)) == src.run_value(e.z, len))) redo |= 1u << j;
+    }
+    for (; redo; redo &= redo - 1u)                         // cold: some row of the run is violated or holds non-bits: row by row
+      bad = min(bad, fp_xor_run_slow(src, P, __ldg(xs + tid + ((uint32_t)__ffs((int)redo) - 1u) * FPK_THREADS)));
+    for (uint32_t b = tid + 32u * FPK_THREADS; b < nx; b += FPK_THREADS)      // a loaded system with more than 4 096 runs: the rest, run by run
+      bad = min(bad, fp_xor_run_slow(src, P, __ldg(xs + b)));
   }
   // ---- every other compiled row: tiles of 32 rows, one per warp step, handed out dynamically (fp_compile orders them
   // by decreasing cost: a warp that meets rows for the Fr path does not end up holding the CTA's barrier alone) ----
