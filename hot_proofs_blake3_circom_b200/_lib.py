@@ -28,7 +28,7 @@ EXPORTS = ("b3w_version", "b3w_last_error", "b3w_create", "b3w_destroy", "b3w_ci
            "b3w_inputs_from_fr_wide", "b3w_witness_batch_wide", "b3w_witness_batch_device_wide", "b3w_assert_trace_fr",
            "b3w_witness_batch_ex", "b3w_witness_batch_fr_ex", "b3w_witness_batch_device_ex", "b3w_last_timing", "b3w_r1cs_program_info",
            "b3w_r1cs_compile_stats", "b3w_r1cs_compile_stats_ex", "b3w_debug_r1cs_program", "b3w_nova_chain_device", "b3w_unpack_host", "b3w_witness_batch_hybrid", "b3w_multi_witness_batch_ex",
-           "b3w_debug_set_store_mode",
+           "b3w_debug_set_store_mode", "b3w_debug_side_layout",
            "b3w_device_alloc", "b3w_device_free", "b3w_multi_create", "b3w_multi_destroy", "b3w_multi_size", "b3w_shard_range", "b3w_multi_witness_batch", "b3w_multi_nova_chain")
 
 
@@ -133,6 +133,7 @@ def lib():
     L.b3w_unpack_host.argtypes = [vp, vp, u64, vp, C.c_uint32]
     L.b3w_witness_batch_hybrid.argtypes = [vp, vp, u64, vp, vp, vp, C.c_uint32]
     L.b3w_debug_set_store_mode.argtypes = [vp, C.c_int]
+    L.b3w_debug_side_layout.argtypes = [C.c_uint32, C.c_uint32, vp, C.c_uint32, vp, vp]
     L.b3w_host_alloc.argtypes = [C.c_size_t]
     L.b3w_host_alloc.restype = vp
     L.b3w_host_alloc_near.argtypes = [C.c_size_t, C.c_int]

@@ -624,6 +624,38 @@ static void compile_programs(const std::vector<r1cs_load_detail::row> &rows, uin
     taken.swap(taken0);
   }
 }
+// Where the stand-alone checker keeps the non-bit slots of a witness (kernels_r1cs_fast.cuh): the side-table entries of
+// 32-slot word w start at rank[w], by the CIRCUIT's slot kinds (a slot that is not DK_BIT may still hold 0 or 1: its entry
+// is then simply not used).  rank has one entry per map word (slot words + virtual-bit words + 1); returns the table size.
+static uint32_t side_layout(const uint32_t *desc, uint32_t ws, uint32_t n_vtiles, std::vector<uint32_t> &rank) {
+  const uint32_t words = (ws + 31u) >> 5, mw = words + n_vtiles + 1u;
+  rank.assign(mw, 0u);
+  uint32_t total = 0;
+  for (uint32_t w = 0; w < mw; w++) {
+    rank[w] = total;
+    for (uint32_t sl = w * 32u; w < words && sl < std::min(ws, (w + 1u) * 32u); sl++) total += (desc[sl] >> 24) != DK_BIT;
+  }
+  return (total + 1u) & ~1u;
+}
+extern "C" int b3w_debug_side_layout(uint32_t circuit, uint32_t n_vtiles, uint32_t *rank_out, uint32_t cap, uint32_t *n_words, uint32_t *total) {
+  const circuit_def *d = find_def(circuit);
+  if (!d) return fail(B3W_ERR_UNSUPPORTED, "unknown circuit %u", circuit);
+  return guarded("b3w_debug_side_layout", [&]() {
+    std::vector<uint32_t> desc, rank;
+    for (size_t i = 0; i < d->n_segs; i++)
+      for (uint32_t j = 0; j < d->segs[i].count; j++) desc.push_back(d->segs[i].desc0 + j * d->segs[i].delta);
+    if (desc.size() != d->ws) return fail(B3W_ERR_INVALID, "slot table of %s is corrupt", d->name);
+    const uint32_t t = side_layout(desc.data(), d->ws, n_vtiles, rank);
+    if (n_words) *n_words = (uint32_t)rank.size();
+    if (total) *total = t;
+    if (rank_out) {
+      if (cap < rank.size()) return fail(B3W_ERR_INVALID, "b3w_debug_side_layout: %u words, room for %u", (uint32_t)rank.size(), cap);
+      memcpy(rank_out, rank.data(), rank.size() * 4);
+    }
+    return B3W_OK;
+  });
+}
+
 static int install_slot_rows(b3w_ctx *c, std::vector<r1cs_load_detail::row> &rows, uint32_t *n_compiled) {
   fastprog_host fp, fp0;
   std::vector<char> taken;
@@ -654,17 +686,9 @@ static int install_slot_rows(b3w_ctx *c, std::vector<r1cs_load_detail::row> &row
   if (e == cudaSuccess) e = upload_fastprog(&P, fp);
   if (e == cudaSuccess && fp.n_virtual) e = upload_fastprog(&P0, fp0);
   if (e == cudaSuccess) {
-    // where the kernel keeps the non-bit slots of a witness: the entries of word w start at side_rank[w] (the circuit's slot
-    // kinds decide; a slot that is not DK_BIT may still hold 0 or 1, its entry is then simply not used)
-    const uint32_t words = (c->def->ws + 31u) >> 5, mw = words + P.n_vtiles + 1u;
-    std::vector<uint32_t> rank(mw);
-    uint32_t total = 0;
-    for (uint32_t w = 0; w < mw; w++) {
-      rank[w] = total;
-      for (uint32_t sl = w * 32u; sl < std::min(c->def->ws, (w + 1u) * 32u) && w < words; sl++) total += (c->h_desc[sl] >> 24) != DK_BIT;
-    }
+    std::vector<uint32_t> rank;
+    P.side_total = side_layout(c->h_desc, c->def->ws, P.n_vtiles, rank);
     e = upload_vec(&P.side_rank, rank);
-    P.side_total = (total + 1u) & ~1u;
   }
   if (e != cudaSuccess) {
     free_r1cs_dev(&d);

@@ -269,6 +269,10 @@ int b3w_r1cs_info(uint32_t circuit, uint32_t *n_rows, uint32_t *n_terms);
  * evaluates these tables with Python integers against the file's own rows. */
 int b3w_debug_r1cs_program(const uint8_t *r1cs, size_t len, const uint8_t prime[32], uint32_t n_wires, int plain, uint32_t section,
                            void *out, size_t cap, size_t *n_bytes);
+/* Test hook: the side-table layout of the stand-alone checker for a circuit (host only, no GPU): rank_out[w] (may be NULL;
+ * cap words of room) = entries reserved before 32-slot word w by the circuit's slot kinds, *n_words = slot words + n_vtiles + 1,
+ * *total = entries in all (even).  The kernel's shared-memory copy of a witness is laid out by this table. */
+int b3w_debug_side_layout(uint32_t circuit, uint32_t n_vtiles, uint32_t *rank_out, uint32_t cap, uint32_t *n_words, uint32_t *total);
 /* Test hook for the fused check: xor `xor_mask` into trace word `trace_word` of every instance after the trace phase
  * of the *_checked kernels (B3W_NO_ROW disables it). */
 int b3w_debug_inject_fault(b3w_ctx *ctx, uint32_t trace_word, uint32_t xor_mask);

@@ -145,3 +145,38 @@ def test_compiled_program_equals_the_files_rows(tmp_path, variant, rows_fn, n_vi
                 assert verdict(w2) == want, (variant, k, s, new)
     if n_virtual:
         assert n_fallback > 0                                                    # some corruption broke a virtual bit: both programs were exercised
+
+
+@pytest.mark.parametrize("circuit,variant,rows_fn,non_bits", [(0, "compression", gen.splitmix_compression_inputs, 717),
+                                                               (1, "nova_bn_o2", gen.splitmix_nova_inputs, None),
+                                                               (2, "nova_pasta_o2", gen.splitmix_nova_inputs, None),
+                                                               (3, "nova_bn_o1", gen.splitmix_nova_inputs, None)])
+def test_side_table_layout_holds_every_witness(circuit, variant, rows_fn, non_bits):
+    """The checker's streaming pass places the non-bit slots of a witness by the CIRCUIT's slot kinds (b3w_debug_side_layout =
+    what install_slot_rows uploads): rank[w] is a prefix count, and no 32-slot word of any oracle witness -- random inputs,
+    zeros, all-ones words -- holds more non-bit values than the layout reserves for it (such a witness would take the slow,
+    still exact, 'irregular' path)."""
+    L = pkg.lib()
+    nw, total = C.c_uint32(), C.c_uint32()
+    assert L.b3w_debug_side_layout(circuit, 3, None, 0, C.byref(nw), C.byref(total)) == 0, L.b3w_last_error()
+    rank = np.zeros(nw.value, np.uint32)
+    assert L.b3w_debug_side_layout(circuit, 3, rank.ctypes.data, nw.value, None, None) == 0
+    assert L.b3w_debug_side_layout(circuit, 3, rank.ctypes.data, nw.value - 1, None, None) != 0          # too little room
+    rows = rows_fn(48, first=5)
+    rows[1] = 0
+    rows[2, 8:24] = 0xFFFFFFFF                                  # message words all ones
+    if variant != "compression":
+        rows[1, 12], rows[1, 13] = 1, 1                         # leaf_depth = total_depth = 1, depth 0: a valid step
+    wit, _, st = port.witness_batch(variant, rows, want="both")
+    ws = wit.shape[1] // 32
+    words = (ws + 31) // 32
+    assert nw.value == words + 3 + 1 and (np.diff(rank.astype(np.int64)) >= 0).all() and (rank[words:] == rank[words]).all()
+    assert total.value == (int(rank[words]) + 1) // 2 * 2 and (non_bits is None or rank[words] == non_bits)
+    w = wit[st == 0].reshape(-1, ws, 32)
+    assert len(w) >= 40
+    isbit = (w[:, :, 1:] == 0).all(axis=2) & (w[:, :, 0] < 2)
+    pad = np.ones((len(w), words * 32 - ws), bool)
+    nonbit_per_word = (~np.concatenate([isbit, pad], axis=1)).reshape(len(w), words, 32).sum(axis=2)
+    cap = np.diff(rank.astype(np.int64))[:words]
+    assert (nonbit_per_word <= cap).all()
+    assert (nonbit_per_word.max(axis=0) == cap).mean() > 0.9    # and the layout is tight: nearly every reserved entry is used by some witness
