@@ -930,7 +930,8 @@ static int r1cs_check_launch(b3w_ctx *c, const uint8_t *d_wit, const uint32_t *d
   // the side table holds the non-bit slots of the circuit's witness layout (install_slot_rows: side_rank / side_total); a
   // witness with non-bit slots elsewhere (not one of this circuit's) is still checked, those values are re-read from HBM
   if (mw > FP_MAPW) return fail(B3W_ERR_UNSUPPORTED, "%s: %u map words (the checker holds %u)", c->def->name, mw, FP_MAPW);
-  const size_t smem = (size_t)3 * FP_MAPW * 4 + (size_t)c->fp.side_total * 8;
+  if (c->fp.side_total > 0xFFFFu) return fail(B3W_ERR_UNSUPPORTED, "%s: %u side-table entries", c->def->name, c->fp.side_total);
+  const size_t smem = (size_t)FP_SIDE_OFF + (size_t)c->fp.side_total * 8;
   CK(cudaFuncSetAttribute(k_r1cs_check_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int per_sm = c->ctas_limit > 0 ? c->ctas_limit : FPK_CTAS_PER_SM;
   const uint64_t cap = (uint64_t)c->sm_count * per_sm;

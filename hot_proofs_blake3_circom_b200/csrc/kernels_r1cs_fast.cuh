@@ -34,7 +34,8 @@
 // -> virtual bits, fast tiles, dynamic hand-out, 128-thread CTAs: 8.2 M/s (0.96), nova O2 7.9 M/s (0.90), O1 6.8 (0.82)
 // -> rotating-register streaming loop, instances from a global counter, side-table places from the circuit's layout
 // instead of a shared-memory counter, the copy addressed through the shared array by name at constant offsets:
-// 8.7 M/s (1.03; 12.4 M/s from compressible buffers), nova O2 8.2 (0.94), O1 7.4 (0.89).
+// 8.8 M/s (1.03; 12.4 M/s from compressible buffers), nova O2 8.3 (0.95), O1 7.5 (0.90); nine CTAs per SM on a 16-bit rank
+// table: nova O2 8.5 (0.97).
 // Measured and dropped on the way (profiles/r02z_*): L2 prefetch of the next instance, staggered CTA starts, 9 and 10 CTAs
 // per SM (the program tables lose their L1), an unrolled tile loop (instruction cache), table entries and tile headers
 // loaded one step ahead in the row pass (the extra live registers spill: +1..2 %).  Kept: the booleanity / XOR loops without
@@ -45,10 +46,12 @@
 #define FPK_EXP 0                 /* experiment builds only: 1 = stream + classify, no rows */
 #endif
 #ifndef FPK_THREADS
-#define FPK_THREADS 128           /* 128 x 8 CTAs per SM: same warps as 256 x 4, the phases of more instances interleave (profiles/r02t) */
+#define FPK_THREADS 128           /* 128-thread CTAs: same warps as 256-thread ones at half the count, the phases of more instances interleave (profiles/r02t) */
 #endif
 #ifndef FPK_CTAS_PER_SM
-#define FPK_CTAS_PER_SM 8
+#define FPK_CTAS_PER_SM 9         /* 56 registers per thread; with the 16-bit rank table nine copies need no larger shared-memory carve-out
+                                     than eight did (132 KB for compression / nova O2, 164 KB for O1), so the program tables keep their L1:
+                                     nova O2 -2.9 % time, the others +-0 (profiles/r02z_r1cs_sweep_9ctas.jsonl; before, 9 and 10 CTAs lost) */
 #endif
 #ifndef FPK_INFLIGHT
 #define FPK_INFLIGHT 4            /* 256-bit loads per lane kept in flight by the streaming loop (rotating registers; 3..5) */
@@ -129,14 +132,16 @@ __shared__ uint32_t fp_s_bad, fp_s_flags, fp_s_tile;
 __shared__ unsigned long long fp_s_it;
 #define FP_MAPW 784u               /* words per map: >= (slots + 31) / 32 + virtual-bit words + 1 of every system (checked on the host); a
                                       CONSTANT so that no accessor needs a value from the (stack-resident) argument structs */
-struct fp_copy {                  // isbit | bitval | rank (FP_MAPW words each; rank is the launch's constant side_rank) | side (8-byte entries)
-  uint32_t *isbit, *bitval, *rank;
+#define FP_SIDE_OFF (FP_MAPW * 10u) /* bytes: two maps of 32-bit words, one of 16-bit ranks */
+struct fp_copy {                  // isbit | bitval (FP_MAPW words each) | rank (16 bits per word: the launch's constant side_rank) | side (8-byte entries)
+  uint32_t *isbit, *bitval;
+  uint16_t *rank;
   uint64_t *side;
   __device__ __forceinline__ fp_copy() {
     isbit = reinterpret_cast<uint32_t *>(fp_smem);
     bitval = isbit + FP_MAPW;
-    rank = bitval + FP_MAPW;
-    side = reinterpret_cast<uint64_t *>(fp_smem + 3u * FP_MAPW * 4u);
+    rank = reinterpret_cast<uint16_t *>(bitval + FP_MAPW);
+    side = reinterpret_cast<uint64_t *>(fp_smem + FP_SIDE_OFF);
   }
 };
 
@@ -146,8 +151,8 @@ struct CompactSrc {
   // the copy is found in fp_smem by name, at constant offsets (see fp_copy)
   static __device__ __forceinline__ const uint32_t *isbit() { return reinterpret_cast<const uint32_t *>(fp_smem); }      // one bit per slot: holds 0 or 1
   static __device__ __forceinline__ const uint32_t *bitval() { return isbit() + FP_MAPW; }                               // ... its value
-  static __device__ __forceinline__ const uint32_t *rank() { return isbit() + 2u * FP_MAPW; }                            // side-table base of each 32-slot word
-  static __device__ __forceinline__ const uint64_t *side() { return reinterpret_cast<const uint64_t *>(fp_smem + 3u * FP_MAPW * 4u); }
+  static __device__ __forceinline__ const uint16_t *rank() { return reinterpret_cast<const uint16_t *>(isbit() + 2u * FP_MAPW); }   // side-table base of each 32-slot word
+  static __device__ __forceinline__ const uint64_t *side() { return reinterpret_cast<const uint64_t *>(fp_smem + FP_SIDE_OFF); }
   // false: an irregular instance (non-bit slots where the circuit's layout has none): such values are read from HBM
   static __device__ __forceinline__ bool side_ok() { return (fp_s_flags & 4u) == 0; }
   const uint8_t *wit;                        // this instance's witness in HBM
@@ -582,7 +587,7 @@ __device__ __forceinline__ void fp_stream_word(const fp_stream_args &c, const fp
     // Their side-table entries start where the CIRCUIT's slot kinds put this word's (m.rank, constant per launch): no
     // counter, no atomic, no exchange between the warps.  A word with more non-bit slots than the circuit's layout has
     // there (never a witness of this circuit) makes the instance IRREGULAR: its rows read such values from HBM instead.
-    const uint32_t r0 = m.rank[wu], cap = m.rank[wu + 1u] - r0;
+    const uint32_t r0 = m.rank[wu], cap = (uint32_t)m.rank[wu + 1u] - r0;
     const bool fits = (uint32_t)__popc(~mb) <= cap;
     if (!((mb >> lane) & 1u)) {
       // small non-negative integers (every word, sum and carry of these circuits) need no field arithmetic
@@ -647,7 +652,7 @@ k_r1cs_check_fast(const uint8_t *__restrict__ wit, const uint32_t *__restrict__ 
   const uint32_t tid = threadIdx.x;
   // list != NULL: check the instances list[1 .. list[0]] (n is ignored)
   const uint64_t count = list ? (uint64_t)list[0] : n;
-  for (uint32_t k = tid; k < mw; k += FPK_THREADS) m.rank[k] = __ldg(P.side_rank + k);      // (the loop's first barrier publishes it)
+  for (uint32_t k = tid; k < mw; k += FPK_THREADS) m.rank[k] = (uint16_t)__ldg(P.side_rank + k);      // (the loop's first barrier publishes it)
   // Instances are handed out through a counter in global memory (one atomic per 770 KB read): CTAs that finish early take
   // the remainder, and the phases of the CTAs (stream / rows) drift apart instead of staying in the step the launch put
   // them in (-3 % on all three systems, profiles/r02z).  counter == NULL: static round-robin.
