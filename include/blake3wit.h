@@ -214,7 +214,8 @@ int b3w_witness_batch_device(b3w_ctx *ctx, const uint32_t *d_in, uint64_t n, uin
  * WHAT IT VALIDATES: the TRACE the witness is expanded from (the circuit's arithmetic: every sum, carry, rotation, flag).  Rows
  * that hold for any trace content by construction of the expansion (booleanity of an extracted bit, word = sum of its bits)
  * are not evaluated, so a wrong slot descriptor or a lost store is invisible to it; b3w_r1cs_check_device is the check
- * that reads the emitted bytes, and b3w_batch_extras.sums ties streamed witnesses to what was stored. */
+ * that reads the emitted bytes (B3W_FLAG_BYTE_CHECK chains it to every chunk of the host-buffer batch calls), and
+ * b3w_batch_extras.sums ties streamed witnesses to what was stored. */
 int b3w_witness_batch_device_checked(b3w_ctx *ctx, const uint32_t *d_in, uint64_t n, uint8_t *d_out, uint8_t *d_status,
                                      uint32_t *d_pub, uint32_t *d_first_bad, void *stream);
 /* Everything at once, DEVICE buffers: d_m_ext (compression only, may be NULL) selects the wide-domain kernel; check != 0 or
