@@ -19,7 +19,8 @@
 //     from a shared counter, dearest first;
 //   * VIRTUAL BITS: where circom's O2 pass substituted a bit by w - sum 2^i b_i, that combination is evaluated once per
 //     witness into a bit slot of its own and the rows that carried it become booleanity / XOR / short rows (r1cs_load.h);
-//   * a product with ONE field-valued factor (IsZero's in * inv = 1 - out) is one 64 x 256-bit multiply-reduce.
+//   * a product with ONE field-valued factor (IsZero's in * inv = 1 - out) is one 64 x 256-bit multiply-reduce; ONE value
+//     beyond 2^62 alone on the right-hand side (the nova circuits' 64-bit chunk index) is eight word compares.
 // Arithmetic is exact: signed 128-bit integers with a bit-length bound per term and per product; a row that cannot be
 // decided that way (a genuine field element such as IsZero's inverse, a run over slots that are not all bits, a bound
 // exceeded) is re-evaluated in Fr (Montgomery) by the same lane.  Rows the compiler does not take (coefficients that are
@@ -35,7 +36,8 @@
 // -> rotating-register streaming loop, instances from a global counter, side-table places from the circuit's layout
 // instead of a shared-memory counter, the copy addressed through the shared array by name at constant offsets:
 // 8.8 M/s (1.03; 12.4 M/s from compressible buffers), nova O2 8.3 (0.95), O1 7.5 (0.90); nine CTAs per SM on a 16-bit rank
-// table: nova O2 8.5 (0.97).
+// table: nova O2 8.5 (0.97); the nova circuits' 64-bit chunk index decided by a compare (fp_big_equals) instead of the Fr
+// evaluator: O1 8.1 (0.97).
 // Measured and dropped on the way (profiles/r02z_*): L2 prefetch of the next instance, staggered CTA starts, 9 and 10 CTAs
 // per SM (the program tables lose their L1), an unrolled tile loop (instruction cache), table entries and tile headers
 // loaded one step ahead in the row pass (the extra live registers spill: +1..2 %).  Kept: the booleanity / XOR loops without
@@ -433,6 +435,24 @@ __device__ __noinline__ bool fp_small_times_big(const CompactSrc &src, uint32_t 
   return any == 0 || diff == 0;
 }
 
+// W == v (mod p) for the field element W in witness slot `wire` (canonical: the streaming pass has checked) and a signed
+// 128-bit integer v: eight word compares.  Decides a row whose ONE value beyond 2^62 stands alone with a unit coefficient
+// on the right-hand side -- the 64-bit chunk index of the nova circuits in `low + 2^32 high = idx` and in Num2Bits(65)'s
+// recomposition -- which the general Fr evaluator settled with two Montgomery products per item.
+__device__ __noinline__ bool fp_big_equals(const CompactSrc &src, uint32_t wire, i128 v) {
+  uint32_t w[8];
+  ld_slot(src.wit + (size_t)wire * 32, w);
+  const bool neg = v < 0;
+  const unsigned __int128 m = neg ? (unsigned __int128)(-v) : (unsigned __int128)v;
+  fr_t e = fr_zero();
+  e.l[0] = (uint32_t)m; e.l[1] = (uint32_t)(m >> 32); e.l[2] = (uint32_t)(m >> 64); e.l[3] = (uint32_t)(m >> 96);
+  if (neg && m != 0) e = fr_neg(e, src.F->p);
+  bool eq = true;
+#pragma unroll
+  for (int j = 0; j < 8; j++) eq = eq && w[j] == e.l[j];
+  return eq;
+}
+
 // one tile: lane = row.  Returns the lane's violated row id or B3W_NO_ROW.
 // A term (coef * v) << shift whose bit-length bound stays <= 62 is formed in 64 bits, the others -- 2^32.. coefficients
 // on wide values, Num2Bits(65)'s top run -- in 128; the sums are 128-bit.
@@ -469,6 +489,12 @@ __device__ __noinline__ uint32_t fp_eval_tile(const CompactSrc &src, const fastp
                       fp_bitlen128(other) <= 62 && fp_bitlen128(L[2]) <= 62;
     if (lone) return fp_small_times_big(src, big_wire, (big_kind & 15u) == 2u ? -(long long)other : (long long)other, (long long)L[2])
                          ? B3W_NO_ROW : P.row_ids[t.row_off + lane];
+    // ... or it stands on the right-hand side with a unit coefficient:  A B = C' +- W  <=>  W = +-(A B - C')
+    const bool quad = t.nA && t.nB;
+    if (!undecided && nbig == 1 && (big_kind & 15u) <= 2u && side == 2u && (!quad || fp_bitlen128(L[0]) + fp_bitlen128(L[1]) <= 125)) {
+      const i128 rest = (quad ? L[0] * L[1] : (i128)0) - L[2];
+      return fp_big_equals(src, big_wire, (big_kind & 15u) == 1u ? rest : -rest) ? B3W_NO_ROW : P.row_ids[t.row_off + lane];
+    }
     undecided = true;
   }
   if (t.nA == 0 || t.nB == 0) {

@@ -300,3 +300,39 @@ def test_r1cs_load_survives_damaged_files(built, exported):
         assert rc <= 0                                           # an error code or an (equally large) accepted system
     assert load(good) == 0
     wc.close()
+
+
+@pytest.mark.parametrize("name", ["blake3_nova_o1", "blake3_nova_pasta", "blake3_nova"])
+def test_hbm_check_decides_rows_with_a_64_bit_chunk_index(built, name):
+    """chunk_idx = low + 2^32 high beyond 2^62 does not fit the checker's tagged 8-byte values: the rows that carry it (its
+    definition, Num2Bits(65)'s recomposition) are decided by comparing the slot with the integer the rest of the row
+    demands (fp_big_equals) -- valid witnesses pass, a changed index slot is a violation, whatever bits change."""
+    wc = pkg.builder(name, device=0)
+    n, ws = 96, wc.witnessSize
+    rows = gen.splitmix_nova_inputs(n, first=1)
+    rows[:, 11] |= 0x80000000                                   # chunk_idx_high: the index is >= 2^63
+    d_out, st, _ = run(wc, rows)
+    ok = st.cpu().numpy() == 0
+    assert ok.sum() > n // 2
+    status, bad = hbm_check(wc, d_out, n)
+    assert (status[ok] == 0).all() and (bad[ok] == _lib.B3W_NO_ROW).all()
+    w64 = d_out.view(n, ws, 32).cpu().numpy().view(np.uint64).reshape(n, ws, 4)
+    idx = rows[:, 10].astype(np.uint64) | (rows[:, 11].astype(np.uint64) << np.uint64(32))
+    hit = (w64[:, :, 0] == idx[:, None]) & (w64[:, :, 1:] == 0).all(axis=2)
+    if name != "blake3_nova_o1":                                # circom's O2 pass substituted the combined index away: no such slot
+        assert not hit.any()
+        wc.close()
+        return
+    assert hit[ok].any(axis=1).all()                            # every O1 witness holds the combined index in some slot
+    slot = hit.argmax(axis=1)
+    w = d_out.view(n, ws, 32)
+    ii = torch.arange(n, device="cuda")
+    sl = torch.from_numpy(slot).cuda()
+    for byte, delta in ((0, 1), (7, 0x40), (3, 0x10)):
+        w[ii, sl, byte] ^= delta
+        status, bad = hbm_check(wc, d_out, n)
+        assert (status[ok] == _lib.B3W_R1CS_VIOLATION).all() and (bad[ok] != _lib.B3W_NO_ROW).all(), (byte, delta)
+        w[ii, sl, byte] ^= delta
+    status, _ = hbm_check(wc, d_out, n)
+    assert (status[ok] == 0).all()
+    wc.close()
