@@ -613,11 +613,12 @@ static cudaError_t upload_fastprog(fastprog_dev *P, const fastprog_host &fp) {
 }
 // fp_compile with virtual bits where the system has them, plus the plain compilation the kernel falls back to for a
 // witness whose virtual bits are not bits; both cover the same rows (fp0 stays empty when there are no virtual bits)
-static void compile_programs(const std::vector<r1cs_load_detail::row> &rows, uint32_t ws, fastprog_host &fp, fastprog_host &fp0, std::vector<char> &taken) {
-  fp_compile(rows, ws, fp, taken, /*with_virtuals=*/true);
+static void compile_programs(const std::vector<r1cs_load_detail::row> &rows, uint32_t ws, fastprog_host &fp, fastprog_host &fp0, std::vector<char> &taken,
+                             const std::vector<uint8_t> *wide_hint = nullptr) {
+  fp_compile(rows, ws, fp, taken, /*with_virtuals=*/true, wide_hint);
   if (fp.n_virtual == 0) return;
   std::vector<char> taken0;
-  fp_compile(rows, ws, fp0, taken0, false);
+  fp_compile(rows, ws, fp0, taken0, false, wide_hint);
   if (taken0 != taken) {                                      // cannot happen (fp_compile keeps the two in step); be safe
     fp = std::move(fp0);
     fp0 = fastprog_host();
@@ -659,7 +660,9 @@ extern "C" int b3w_debug_side_layout(uint32_t circuit, uint32_t n_vtiles, uint32
 static int install_slot_rows(b3w_ctx *c, std::vector<r1cs_load_detail::row> &rows, uint32_t *n_compiled) {
   fastprog_host fp, fp0;
   std::vector<char> taken;
-  compile_programs(rows, c->def->ws, fp, fp0, taken);
+  std::vector<uint8_t> wide(c->def->ws);                      // slots that hold signed / field-valued quantities by their kind
+  for (uint32_t sl = 0; sl < c->def->ws; sl++) wide[sl] = (c->h_desc[sl] >> 24) >= DK_S64;
+  compile_programs(rows, c->def->ws, fp, fp0, taken, &wide);
   if (fp.n_virtual && ((c->def->ws + 31u) >> 5) + fp.vtiles.size() + 1u > FP_MAPW) {     // more virtual-bit words than the kernel's maps hold:
     fp = std::move(fp0);                                                                   // the plainly compiled program alone (same rows)
     fp0 = fastprog_host();

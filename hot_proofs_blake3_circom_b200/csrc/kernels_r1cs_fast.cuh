@@ -37,7 +37,7 @@
 // instead of a shared-memory counter, the copy addressed through the shared array by name at constant offsets:
 // 8.8 M/s (1.03; 12.4 M/s from compressible buffers), nova O2 8.3 (0.95), O1 7.5 (0.90); nine CTAs per SM on a 16-bit rank
 // table: nova O2 8.5 (0.97); the nova circuits' 64-bit chunk index decided by a compare (fp_big_equals) instead of the Fr
-// evaluator: O1 8.1 (0.97).
+// evaluator, tiles with signed / field-valued scalars (by slot kind) compiled for the exact path at once: O2 8.6 (0.985), O1 8.2 (0.99).
 // Measured and dropped on the way (profiles/r02z_*): L2 prefetch of the next instance, staggered CTA starts, 9 and 10 CTAs
 // per SM (the program tables lose their L1), an unrolled tile loop (instruction cache), table entries and tile headers
 // loaded one step ahead in the row pass (the extra live registers spill: +1..2 %).  Kept: the booleanity / XOR loops without

@@ -371,8 +371,12 @@ static bool reduce_lc(std::vector<term> &lc, const std::vector<virt_def> &virt, 
 }  // namespace r1cs_load_detail
 
 // Compiles what it can; taken[i] tells which rows are now covered by the program (the others go to r1cs_group).
+// wide_hint (may be NULL): per wire, 1 where the circuit's slot kinds say the value is a signed or field-valued quantity
+// (IsZero's inverse, a negative difference): a tile with such a scalar is not marked FP_TILE_FAST -- at run time its 64-bit
+// pass would find the value out of bounds and the tile would be evaluated a second time.  A hint only: the verdict of a tile
+// never depends on its flag.
 static void fp_compile(const std::vector<r1cs_load_detail::row> &rows, uint32_t ws, fastprog_host &fp, std::vector<char> &taken,
-                       bool with_virtuals = false) {
+                       bool with_virtuals = false, const std::vector<uint8_t> *wide_hint = nullptr) {
   using namespace r1cs_load_detail;
   const uint32_t words = (ws + 31u) >> 5, vbase = words * 32u;
   taken.assign(rows.size(), 0);
@@ -528,6 +532,7 @@ static void fp_compile(const std::vector<r1cs_load_detail::row> &rows, uint32_t 
       for (const fp_item &it : gens[r].it) {
         const uint32_t len = it.meta & 63u, cbits = (it.meta >> 16) & 255u;
         fast = fast && cbits + (len ? len : (it.meta >> 24) & 63u) <= 57;
+        if (wide_hint && len == 0 && it.coef != 0 && it.wire < wide_hint->size() && (*wide_hint)[it.wire]) fast = false;
       }
       bool sp = gens[r].n[0] && gens[r].n[1];
       for (uint32_t k = 0; k < gens[r].n[0] + gens[r].n[1]; k++) sp = sp && (gens[r].it[k].meta & 63u) == 0;
