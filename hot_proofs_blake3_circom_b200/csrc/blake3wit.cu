@@ -660,8 +660,8 @@ extern "C" int b3w_debug_side_layout(uint32_t circuit, uint32_t n_vtiles, uint32
 static int install_slot_rows(b3w_ctx *c, std::vector<r1cs_load_detail::row> &rows, uint32_t *n_compiled) {
   fastprog_host fp, fp0;
   std::vector<char> taken;
-  std::vector<uint8_t> wide(c->def->ws);                      // slots that hold signed / field-valued quantities by their kind
-  for (uint32_t sl = 0; sl < c->def->ws; sl++) wide[sl] = (c->h_desc[sl] >> 24) >= DK_S64;
+  std::vector<uint8_t> wide(c->def->ws);                      // slots that hold field-valued quantities by their kind (IsZero's inverse)
+  for (uint32_t sl = 0; sl < c->def->ws; sl++) wide[sl] = (c->h_desc[sl] >> 24) == DK_INV;
   compile_programs(rows, c->def->ws, fp, fp0, taken, &wide);
   if (fp.n_virtual && ((c->def->ws + 31u) >> 5) + fp.vtiles.size() + 1u > FP_MAPW) {     // more virtual-bit words than the kernel's maps hold:
     fp = std::move(fp0);                                                                   // the plainly compiled program alone (same rows)

@@ -366,7 +366,7 @@ __device__ __noinline__ uint32_t fp_bool_word_slow(const CompactSrc &src, const 
 }
 
 // A FP_TILE_FAST tile in 64-bit arithmetic.  *ok = false when some value of the lane's row is not what the flag assumes (a
-// scalar >= 2^36 or tagged negative / field-valued, a run over non-bits): the caller then re-evaluates the tile exactly.
+// scalar of magnitude >= 2^36 or field-valued, a run over non-bits): the caller then re-evaluates the tile exactly.
 __device__ __forceinline__ uint32_t fp_eval_tile_fast(const CompactSrc &src, const fastprog_dev &P, const fp_tile t, uint32_t lane, bool *ok_out) {
   const fp_item *__restrict__ it0 = P.items + t.item_off + lane;
   const uint32_t nA = t.nA, nAB = (uint32_t)t.nA + t.nB, nt = nAB + t.nC;
@@ -379,15 +379,18 @@ __device__ __forceinline__ uint32_t fp_eval_tile_fast(const CompactSrc &src, con
     if (k + 1 < nt) nxt = __ldg(reinterpret_cast<const uint4 *>(it0 + (k + 1) * 32u));
     const uint32_t wire = raw.x, len = raw.y & 63u, shift = (raw.y >> 8) & 255u;
     const long long coef = (long long)((((uint64_t)raw.w << 32) | raw.z) << shift);
-    uint64_t v;
+    long long v;
     if (len) {
       ok = ok && src.run_is_bits(wire, len);
-      v = src.run_value(wire, len);
+      v = (long long)src.run_value(wire, len);
     } else {
-      v = src.get(wire);
-      ok = ok && (v >> ((raw.y >> 24) & 63u)) == 0;             // the bound fp_compile assumed for this wire; the tags are high bits: covers them too
+      // a small value of either sign (differences such as depth - leaf_depth - k are negative in every witness); its
+      // magnitude must stay below the bound fp_compile assumed for this wire, and it must not be a genuine field element
+      const uint64_t x = src.get(wire), mag = x & STG_PAYLOAD;
+      ok = ok && !(x & STG_TAG_BIG) && (mag >> ((raw.y >> 24) & 63u)) == 0;
+      v = (x & STG_TAG_NEG) ? -(long long)mag : (long long)mag;
     }
-    const long long term = coef * (long long)v;
+    const long long term = coef * v;
     if (k < nA) L[0] += term; else if (k < nAB) L[1] += term; else L[2] += term;
   }
   *ok_out = ok;

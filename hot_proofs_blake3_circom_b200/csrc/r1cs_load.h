@@ -371,8 +371,8 @@ static bool reduce_lc(std::vector<term> &lc, const std::vector<virt_def> &virt, 
 }  // namespace r1cs_load_detail
 
 // Compiles what it can; taken[i] tells which rows are now covered by the program (the others go to r1cs_group).
-// wide_hint (may be NULL): per wire, 1 where the circuit's slot kinds say the value is a signed or field-valued quantity
-// (IsZero's inverse, a negative difference): a tile with such a scalar is not marked FP_TILE_FAST -- at run time its 64-bit
+// wide_hint (may be NULL): per wire, 1 where the circuit's slot kinds say the value is a field element (IsZero's inverse):
+// a tile with such a scalar is not marked FP_TILE_FAST -- at run time its 64-bit
 // pass would find the value out of bounds and the tile would be evaluated a second time.  A hint only: the verdict of a tile
 // never depends on its flag.
 static void fp_compile(const std::vector<r1cs_load_detail::row> &rows, uint32_t ws, fastprog_host &fp, std::vector<char> &taken,
