@@ -180,3 +180,17 @@ def test_side_table_layout_holds_every_witness(circuit, variant, rows_fn, non_bi
     cap = np.diff(rank.astype(np.int64))[:words]
     assert (nonbit_per_word <= cap).all()
     assert (nonbit_per_word.max(axis=0) == cap).mean() > 0.9    # and the layout is tight: nearly every reserved entry is used by some witness
+
+
+@needs_ref
+@pytest.mark.parametrize("variant", ["compression", "nova_pasta_o2", "nova_bn_o1"])
+def test_no_row_of_a_valid_witness_needs_the_general_fr_evaluator(variant):
+    """tools/r1cs_replay.py replays the compiled program on oracle witnesses (one with a chunk index beyond 2^62, one within)
+    and names the path of every tile row: plain integers, the 64 x 256-bit product for IsZero's inverse ("lone"), the compare
+    against one large value on the right-hand side ("big_rhs").  None may be left to the general Fr evaluator -- two nova O1
+    rows were, in every instance, until round 2's last session."""
+    import r1cs_replay
+    kinds = r1cs_replay.main(variant, verbose=False)
+    assert sum(kinds.values()) > 500 and not [k for k in kinds if k.startswith("FR")], dict(kinds)
+    if variant == "nova_bn_o1":
+        assert kinds["big_rhs"] >= 2 and kinds["lone"] >= 60      # the index rows of the first witness; IsZero rows

@@ -21,7 +21,9 @@ from oracle import port
 FAST = 0x8000
 
 
-def main(variant):
+def main(variant, verbose=True):
+    """-> Counter of the path every tile row takes (int / lone / big_rhs / FR...), over two oracle witnesses"""
+    total = Counter()
     out_dir = "/tmp/r1cs_replay"
     os.makedirs(out_dir, exist_ok=True)
     path, _ = ex.export(variant, out_dir, trials=1, verbose=False)
@@ -30,6 +32,9 @@ def main(variant):
     p, ws = r["prime"], r["n_wires"]
     P = program(blob, p, ws, plain=False)
     rows_in = gen.splitmix_compression_inputs(4, first=3) if variant == "compression" else gen.splitmix_nova_inputs(4, first=3)
+    if variant != "compression":
+        rows_in[0, 11] |= 0x80000000       # chunk_idx >= 2^63: beyond the tagged 8-byte values
+        rows_in[1, 11] &= 0x0FFFFFFF       # ... and one that fits
     wit = port.witness_batch(variant, rows_in)
 
     def small(v):                      # the kernel's tagged 8-byte value: |v| < 2^62, else "BIG"
@@ -100,10 +105,13 @@ def main(variant):
                 else:
                     kinds.append("int")
             c = Counter(kinds)
-            if (fast and fast_fails) or not fast or any(k != "int" for k in c):
+            total.update(c)
+            if verbose and ((fast and fast_fails) or not fast or any(k != "int" for k in c)):
                 print("instance %d tile %2d %-5s A,B,C items %d,%d,%d  %s%s" % (inst, ti, "FAST" if fast else "exact", nA, nB, nC, dict(c),
                                                                                "   <- FAST tile evaluated twice (%s)" % ", ".join(sorted(why)) if fast and fast_fails else ""))
-    print("(the debug dump compiles WITHOUT the circuit's slot-kind hint: install_slot_rows compiles the tiles flagged 'evaluated twice' for the exact path)")
+    if verbose:
+        print("(the debug dump compiles WITHOUT the circuit's slot-kind hint: install_slot_rows compiles the tiles flagged 'evaluated twice' for the exact path)")
+    return total
 
 
 if __name__ == "__main__":
