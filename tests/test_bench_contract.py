@@ -1,0 +1,60 @@
+"""The benchmark contract, checked WITHOUT a GPU: the JSON lines bench.py printed on the B200 boxes (committed under
+profiles/) carry every key the driver reads, with coherent values; the reference arm's line has its own shape; and
+bench.py refuses to run its own arm without a GPU instead of falling back to anything."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def line(name):
+    return json.load(open(os.path.join(ROOT, "profiles", name)))
+
+
+@pytest.mark.parametrize("name,n", [("r02z_bench_own.json", 1), ("r02z_bench_n2.json", 2), ("r02z_bench_n8.json", 8)])
+def test_own_arm_line(name, n):
+    d = line(name)
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "roofline", "e2e", "gpu_launches", "clocks"):
+        assert k in d, k
+    assert d["metric"] == "blake3_compression witnesses/sec" and d["unit"] == "witnesses/s" and d["n_gpus"] == n
+    assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None and d["data"] == "synthetic"
+    assert "workload" in d["config"] and "model" not in d["config"] and d["warmup"] >= 3 and d["gpu_launches"] == d["steps"] * n   # one launch per step and GPU
+    per_gpu = d["config"]["instances_per_gpu"]
+    assert abs(d["value"] - n * per_gpu / (d["ms_per_step"] / 1e3)) / d["value"] < 1e-6       # value = whole-job units / max-over-ranks time
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert abs(r["achieved"] - r["algorithmic_bytes_per_launch"] / (r["kernel_ms"] / 1e3) / 1e9) / r["achieved"] < 1e-6
+    assert 0.9 < r["traffic"] / r["algorithmic_bytes_per_launch"] < 1.1                        # DRAM traffic ~ algorithmic bytes: nothing re-read
+    e = d["e2e"]
+    assert e["unit"] == "witnesses/s" and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] >= per_gpu * 770976
+    assert e["value"] < d["value"] / 50                                                        # PCIe-bound, not a copy of `value`
+    c = d["clocks"]
+    assert c["sm_mhz"] > 0.9 * c["sm_max_mhz"] and not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    if n == 1:
+        b = d["cpu_baseline"]
+        assert b["kind"] == "reference" and b["cores"] >= 1 and b["unit"] == "witnesses/s" and b["sample"]
+        for k in ("value_checked", "r1cs_check_resident", "config3", "config4", "config5", "config5_byte_check", "fr_batches", "e2e_hybrid"):
+            assert k in d, k
+        assert d["config5"]["samples_match_their_sums"] is True and d["config3"]["root_is_blake3_of_file"] is True
+
+
+def test_reference_arm_line():
+    d = line("r02z_bench_ref.json")
+    assert d["impl"] == "reference" and d["metric"] == "blake3_compression witnesses/sec" and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    own = line("r02z_bench_own.json")
+    assert d["config"]["workload"] == own["config"]["workload"] and d["unit"] == own["unit"]
+
+
+def test_own_arm_needs_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a box WITHOUT a GPU")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "3"], capture_output=True, text=True, timeout=300)
+    assert p.returncode != 0 and not p.stdout.strip().startswith("{")                          # no number without the CUDA path
