@@ -1749,6 +1749,11 @@ static int nova_chain_steps(b3w_ctx *c, const chain_plan &p, const uint8_t *data
     CK(cudaEventRecord(c->ev_k0[0], s0));
     rc = launch_witness(c, d_rows, total, K.out + first * wbytes, K.status ? K.status + first : nullptr, K.pub ? K.pub + first * 15 : nullptr, s0, o);
     if (rc) return rc;
+    if ((c->flags & B3W_FLAG_BYTE_CHECK) && K.status) {                 // every row on the bytes just written (see batch_chunks)
+      rc = r1cs_check_launch(c, K.out + first * wbytes, nullptr, total, K.status + first, nullptr, s0, false, /*skip_asserted=*/true);
+      if (rc) return rc;
+      c->timing.launches++;
+    }
     CK(cudaEventRecord(c->ev_k1[0], s0));
     c->ev_pending[0] = true;
     c->timing.launches++;
@@ -1769,6 +1774,11 @@ static int nova_chain_steps(b3w_ctx *c, const chain_plan &p, const uint8_t *data
       CK(cudaEventRecord(c->ev_k0[k], s));
       rc = launch_witness(c, d_rows + done * 32, m, c->d_ring[k], c->d_status[k], c->d_pub[k], s, o);
       if (rc) return rc;
+      if (c->flags & B3W_FLAG_BYTE_CHECK) {                            // every row on the bytes in the ring slot (see batch_chunks)
+        rc = r1cs_check_launch(c, c->d_ring[k], nullptr, m, c->d_status[k], nullptr, s, false, /*skip_asserted=*/true);
+        if (rc) return rc;
+        c->timing.launches++;
+      }
       CK(cudaEventRecord(c->ev_k1[k], s));
       c->ev_pending[k] = true;
       c->timing.launches++;

@@ -38,7 +38,8 @@ extern "C" {
                                     Default everywhere (C, Python, N-API): compressible memory when the driver grants it, silently
                                     ordinary memory otherwise */
 #define B3W_FLAG_BYTE_CHECK 16u  /* b3w_config.flags: every host-buffer batch call (b3w_witness_batch, _ex, _fr, _fr_ex, _wide; also with out = NULL;
-                                    NOT the packed / hybrid forms, whose witnesses are not expanded on the GPU) re-reads each
+                                    b3w_nova_chain and, where a status array is given, b3w_nova_chain_device; NOT the packed / hybrid
+                                    forms, whose witnesses are not expanded on the GPU) re-reads each
                                     chunk's witnesses from the HBM ring right after they were written and evaluates EVERY row of the
                                     constraint system on those bytes (the kernel of b3w_r1cs_check_device): what a consumer does
                                     with the vector it is handed (rust_fold/src/utils.rs:78-85), before the bytes leave the GPU.

@@ -5,8 +5,10 @@ import os
 
 import numpy as np
 import pytest
+import torch
 
 import hot_proofs_blake3_circom_b200 as pkg
+from hot_proofs_blake3_circom_b200 import _lib
 from hot_proofs_blake3_circom_b200 import inputs as gen
 from oracle import nova_chain_ref, port, ref_wasm
 
@@ -183,3 +185,30 @@ def test_chain_device_form(built, name, variant):
     t = w.lastTiming()
     assert t["launches"] == 1 and t["instances"] == ns and t["d2h_bytes"] == 0
     w.close()
+
+
+@pytest.mark.parametrize("name", ["blake3_nova", "blake3_nova_o1"])
+def test_chain_with_the_byte_check_flag(built, name):
+    """B3W_FLAG_BYTE_CHECK covers the chain driver too: every step witness is re-read from the ring (or from the caller's
+    device buffer) and all rows are evaluated on its bytes; the chain's results are unchanged, a faulty witness is flagged."""
+    data = synth(40000)
+    plain = pkg.builder(name, device=0, chunk=64)
+    ref = plain.novaChain(data)
+    plain.close()
+    w = pkg.builder(name, device=0, chunk=64, byte_check=True)
+    res = w.novaChain(data)
+    assert (res["status"] == 0).all() and np.array_equal(res["pub"], ref["pub"]) and res["root"] == ref["root"]
+    chunks = (res["total_steps"] + 63) // 64
+    assert w.lastTiming()["launches"] == 2 * chunks                 # generator + checker per ring chunk
+    ns = res["total_steps"]
+    d_out = torch.zeros(ns * w.witnessSize * 32, dtype=torch.uint8, device="cuda")
+    d_st = torch.full((ns,), 255, dtype=torch.uint8, device="cuda")
+    w.novaChainDevice(data, d_out.data_ptr(), d_st.data_ptr())
+    torch.cuda.synchronize()
+    assert int(d_st.max()) == 0
+    w.close()
+    bad = pkg.builder(name, device=0, chunk=64, fused_check=True, byte_check=True)
+    bad.inject_fault(48 + 3, 1)                                     # the stored witnesses are faulty
+    res = bad.novaChain(data)
+    assert (res["status"] == _lib.B3W_R1CS_VIOLATION).all()
+    bad.close()
