@@ -11,8 +11,9 @@ ranges, no collective on the data path (weak scaling; NCCL is used only for the 
 of the timings).
 
 Keys of the JSON line (rank 0):
+  config     the workload, identical in both arms; `run` = what this run observed (output memory kind, out[0] of instance 0)
   value      whole-job witnesses/s, inputs resident in HBM, CUDA events on the launching stream, max over ranks; the
-             witnesses go to compressible device memory, the library's default (config.output_memory)
+             witnesses go to compressible device memory, the library's default (run.output_memory)
   roofline   the HBM record: the same kernel into ORDINARY memory, timed per launch in this run, against the measured
              HBM peak (MEASURED_PEAKS.json); algorithmic bytes = 32*24093 written + 112 read per witness
   roofline_compressible  the timed region itself against its own bound, the SM-side store path (peak = the kernel's
@@ -52,6 +53,15 @@ LOG2_BATCH = 16
 METRIC = "blake3_compression witnesses/sec"
 print_json = print
 WORKLOAD = "blake3_compression batch 2^16 random 64-byte blocks, BN254 Fr (BASELINE configs[1]), per GPU"
+
+
+def workload_config(n=1 << LOG2_BATCH):
+    """`config` of the JSON line: the workload and nothing measured, so that both arms (this one and --impl reference)
+    print the SAME object; what a run found out (output memory kind, instance 0's out[0], checksums) is under `run`."""
+    return {"workload": WORKLOAD, "instances_per_gpu": n, "witness_bytes": WIT_BYTES, "input_bytes": IN_BYTES,
+            "witness_bytes_per_batch_per_gpu": n * WIT_BYTES,
+            "l2": "a batch's witnesses are 50.5 GB per GPU, >> 126 MB L2: nothing of one step survives in L2 for the next",
+            "sharding": "contiguous index ranges, no collective"}
 
 
 def measured_peaks():
@@ -146,8 +156,9 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "witnesses/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 + Fr256 (BN254)",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "note": "CPU arm: bounded sample per step; "
-                                        "the reference wasm (V8 unavailable) translated to C, all host threads"},
+        "data": "synthetic", "config": workload_config(),
+        "run": {"note": "CPU arm: a bounded sample of the workload per step; the reference wasm (V8 unavailable) translated "
+                        "to C (oracle/_ref), all host threads", "witnesses_per_step": per_step},
         "cpu_baseline": {"value": value, "unit": "witnesses/s", "cores": ncpu, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "witnesses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
@@ -550,10 +561,8 @@ def run_own(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": "witnesses/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32 + Fr256 (BN254)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "instances_per_gpu": n, "witness_bytes": WIT_BYTES,
-                   "hbm_out_bytes_per_gpu": n * WIT_BYTES, "l2": "each step writes 50.5 GB per GPU, >> 126 MB L2",
-                   "sharding": "contiguous index ranges, no collective", "out0_instance0": int(pub0[0]),
-                   "output_memory": mem_kind, "witness_checksums_xor_rank0": sums_xor},
+        "config": workload_config(n),
+        "run": {"output_memory": mem_kind, "out0_instance0": int(pub0[0]), "witness_checksums_xor_rank0": sums_xor},
         # the HBM record: the witness kernel into ORDINARY memory, where every algorithmic byte crosses the HBM interface
         "roofline": {"bound": "hbm", "kernel": "k_blake3_comp_witness", "achieved": achieved_plain, "peak": peak,
                      "unit": "GB/s", "frac": achieved_plain / peak, "traffic": traffic,

@@ -1,0 +1,65 @@
+#!/usr/bin/env python3
+"""make_golden_sums.py -- regenerates tests/golden/compression_sums_2p20.npz (run anywhere: needs the oracles only).
+
+The fixture pins the per-instance witness checksums (the b3w_checksum_device definition) of the 2^20
+blake3_compression instances splitmix_compression_inputs(2^20, first=0) -- BASELINE configs[3]'s count on the
+compression circuit, SURVEY.md section 8(d) "a checksum of checksums" -- WITHOUT shipping 8 MiB of sums:
+
+  block_digest[b] = first 8 bytes (little endian) of sha256(sums[4096 b : 4096 (b + 1)].tobytes()),  b = 0 .. 255
+  sha256          = sha256 of all 2^20 sums (u64 little endian, instance order)
+
+The sums come from Oracle B (oracle/circuit_oracle.c through oracle/port.py), the restatement that tests/test_oracle.py
+pins to the reference wasm (Oracle A); this script re-checks a spread of 256 instances (one per block) against Oracle A
+itself when oracle/_ref is built.  A GPU test that matches every block digest has matched every one of the 2^20 sums;
+it does so without the 150 s (16 host cores) of oracle time the full comparison cost inside the GPU suite, which still
+compares a random 2^15-instance subset with Oracle B live (B3W_FULL_ORACLE=1 brings the full live comparison back).
+"""
+import hashlib
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import port, ref_wasm  # noqa: E402
+from hot_proofs_blake3_circom_b200.inputs import splitmix_compression_inputs  # noqa: E402
+
+LOG2_N, BLOCK = 20, 4096
+
+
+def block_digests(sums):
+    """u64[n] -> u64[n / BLOCK]: the first 8 bytes of each block's sha256 (shared with tests/test_gpu_extras.py)."""
+    sums = np.ascontiguousarray(sums, "<u8")
+    assert sums.size % BLOCK == 0
+    return np.array([int.from_bytes(hashlib.sha256(sums[b:b + BLOCK].tobytes()).digest()[:8], "little")
+                     for b in range(0, sums.size, BLOCK)], np.uint64)
+
+
+def main():
+    n = 1 << LOG2_N
+    rows = splitmix_compression_inputs(n, first=0)
+    t = time.time()
+    sums = port.witness_batch("compression", rows, want="sums")
+    print("oracle B: %d sums in %.0f s" % (n, time.time() - t))
+    if ref_wasm.available("compression"):
+        idx = np.arange(0, n, BLOCK) + (np.arange(n // BLOCK) * 2654435761 % BLOCK)      # one instance per block
+        wit, status, _ = ref_wasm.RefWasm("compression").batch_u32(rows[idx], nthreads=os.cpu_count() or 1)
+        assert (status == 0).all()
+        wit_b, sums_b, _ = port.witness_batch("compression", rows[idx], want="both")
+        assert np.array_equal(wit, wit_b) and np.array_equal(sums_b, sums[idx])
+        print("oracle A == oracle B on %d spread instances (every byte)" % idx.size)
+    else:
+        print("oracle/_ref not built: Oracle A cross-check skipped")
+    sha = hashlib.sha256(np.ascontiguousarray(sums, "<u8").tobytes()).hexdigest()
+    np.savez_compressed(os.path.join(HERE, "compression_sums_2p20.npz"), log2_n=np.uint32(LOG2_N), block=np.uint32(BLOCK),
+                        block_digest=block_digests(sums), sha256=np.frombuffer(sha.encode(), np.uint8),
+                        first16=sums[:16].copy(), xor=np.bitwise_xor.reduce(sums))
+    print("compression_sums_2p20.npz: sha256", sha)
+
+
+if __name__ == "__main__":
+    main()

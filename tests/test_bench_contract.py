@@ -58,3 +58,24 @@ def test_own_arm_needs_a_gpu():
         pytest.skip("needs a box WITHOUT a GPU")
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "3"], capture_output=True, text=True, timeout=300)
     assert p.returncode != 0 and not p.stdout.strip().startswith("{")                          # no number without the CUDA path
+
+
+def test_both_arms_print_the_same_config():
+    """The driver compares the arms' `config` objects: both come from bench.workload_config(), which holds the workload
+    and nothing a run measured (that is under `run`).  The reference arm is run here (1 step, a few seconds of CPU)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle import ref_wasm
+    cfg = bench.workload_config()
+    assert cfg["workload"] == bench.WORKLOAD and cfg["instances_per_gpu"] == 1 << 16 and cfg["witness_bytes"] == 24093 * 32
+    assert "l2" in cfg and "model" not in cfg
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert src.count('"config": workload_config(') == 2                                        # own arm and reference arm
+    if not ref_wasm.available("compression"):
+        pytest.skip("oracle/_ref not built")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-400:]
+    d = json.loads(p.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["config"] == cfg and d["higher_is_better"] is True and d["unit"] == "witnesses/s"
+    assert d["cpu_baseline"]["cores"] == (os.cpu_count() or 1) and d["e2e"]["value"] == d["value"] > 0

@@ -1,7 +1,9 @@
 """GPU tests of the extra batch results (b3w_batch_extras, BASELINE config 5's compact-result contract):
 per-instance witness checksums computed by the expansion warps, full witnesses for a <= 1 024-instance sample out of the
 streamed HBM ring, first violated row; single GPU and the multi-GPU entry point.  Checker: Oracle B."""
+import hashlib
 import os
+import sys
 import threading
 
 import numpy as np
@@ -12,6 +14,10 @@ import hot_proofs_blake3_circom_b200 as pkg
 from hot_proofs_blake3_circom_b200 import _lib
 from hot_proofs_blake3_circom_b200 import inputs as gen
 from oracle import port
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+sys.path.insert(0, GOLDEN)
+import make_golden_sums  # noqa: E402  (block_digests: the fixture's own definition)
 
 pytestmark = pytest.mark.gpu
 NCPU = os.cpu_count() or 1
@@ -30,8 +36,17 @@ def test_streamed_2_20_sums_and_samples(built):
     res = wc.calculateWitnessBatch(rows, want_witness=False, sums=True, samples=sample, first_bad=True)
     assert res["witness"] is None and not res["status"].any()
     assert (res["first_bad"] == _lib.B3W_NO_ROW).all()
-    want_sums = port.witness_batch("compression", rows, nthreads=NCPU, want="sums")
-    assert np.array_equal(res["sums"], want_sums)
+    # every one of the 2^20 sums against Oracle B: through the committed per-4096-block digests of Oracle B's sums
+    # (tests/golden/make_golden_sums.py), and live on a random 2^15 of them (B3W_FULL_ORACLE=1: live on all, 150 s)
+    g = np.load(os.path.join(GOLDEN, "compression_sums_2p20.npz"))
+    assert int(g["log2_n"]) == 20 and np.array_equal(res["sums"][:16], g["first16"])
+    got = make_golden_sums.block_digests(res["sums"])
+    bad = np.nonzero(got != g["block_digest"])[0]
+    assert bad.size == 0, "blocks of 4096 instances whose checksums differ from Oracle B's: %s" % bad[:8]
+    assert hashlib.sha256(np.ascontiguousarray(res["sums"], "<u8").tobytes()).hexdigest() == bytes(g["sha256"]).decode()
+    live = np.arange(n) if os.environ.get("B3W_FULL_ORACLE") == "1" else np.sort(rng.choice(n, 1 << 15, replace=False))
+    want_sums = port.witness_batch("compression", rows[live], nthreads=NCPU, want="sums")
+    assert np.array_equal(res["sums"][live], want_sums)
     want = port.witness_batch("compression", rows[sample], nthreads=NCPU)
     assert np.array_equal(res["samples"], want)
     t = wc.lastTiming()
