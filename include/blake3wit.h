@@ -153,7 +153,8 @@ int b3w_witness_batch_ex(b3w_ctx *ctx, const uint32_t *in, uint64_t n, uint8_t *
  * the stages also carry NVTX ranges ("b3w:h2d", "b3w:kernel", "b3w:d2h", "b3w:host_unpack"). */
 typedef struct {
   double total_ms;         /* wall clock of the call */
-  double kernel_ms;        /* sum over the call's witness-kernel launches (device time) */
+  double kernel_ms;        /* sum over the call's witness-kernel launches (device time); launches on the two ring streams may
+                              overlap, so 0 < kernel_ms <= 2 * total_ms */
   double host_ms;          /* host-side work inside the call (Fr conversion set-up, host unpack) */
   uint64_t launches;       /* witness-kernel launches */
   uint64_t instances;

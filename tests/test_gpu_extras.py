@@ -50,7 +50,9 @@ def test_streamed_2_20_sums_and_samples(built):
     want = port.witness_batch("compression", rows[sample], nthreads=NCPU)
     assert np.array_equal(res["samples"], want)
     t = wc.lastTiming()
-    assert t["instances"] == n and t["launches"] == n // 4096 and 0 < t["kernel_ms"] <= t["total_ms"]
+    # kernel_ms sums the launches' device times; launches alternate between the two ring streams and may overlap, so the
+    # sum is bounded by twice the call's wall clock, not by the wall clock itself
+    assert t["instances"] == n and t["launches"] == n // 4096 and 0 < t["kernel_ms"] <= 2 * t["total_ms"]
     assert t["d2h_bytes"] == n * (1 + 64 + 8 + 4) + len(sample) * WS * 32
     wc.close()
 
