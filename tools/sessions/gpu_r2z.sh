@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2, last GPU session: bench (both arms), ncu launch list of the bench command, full captures of the witness kernel
 # (ordinary + compressible memory) and of the reworked stand-alone checker on the three systems, checker sweep, configs 0/2,
-# then the whole GPU suite.  (compute-sanitizer: tools/gpu_r2z_sanitize.sh, a call of its own.)
+# then the whole GPU suite.  (compute-sanitizer: tools/sessions/gpu_r2z_sanitize.sh, a call of its own.)
 mkdir -p gpurun_out
 (time python bench.py --steps 20 --warmup 5 > gpurun_out/r2z_bench_own.json 2> gpurun_out/r2z_bench_own.err) 2>&1 | tail -3 | tee gpurun_out/r2z_bench_wall.txt
 tail -5 gpurun_out/r2z_bench_own.err; cut -c1-600 gpurun_out/r2z_bench_own.json
