@@ -296,6 +296,43 @@ class WitnessCalculator:
         _lib.check(self._L.b3w_wtns_header(self.circuit, hdr.ctypes.data))
         return np.concatenate([hdr, body])
 
+    # ---- NEW: the consumer's side -- are these witnesses valid? ----
+    def checkWitnesses(self, witness):
+        """witness: (n, witnessSize*32) u8 in HOST memory (.wtns bodies, e.g. read back from files) -> (status u8[n], first_bad
+        u32[n]): every row of the circuit's constraint system evaluated on the bytes by the stand-alone GPU checker
+        (b3w_r1cs_check_device) -- what circom_tester's expectPass (test/blake3_hash.test.ts:36,57), `snarkjs wtns check` and
+        bellpepper's enforce (rust_fold/src/utils.rs:78-85) decide.  status 0 = all rows hold, 7 = B3W_R1CS_VIOLATION with
+        first_bad = the violated row (B3W_NO_ROW otherwise)."""
+        import torch
+        w = np.ascontiguousarray(witness, np.uint8).reshape(-1, self.witnessSize * 32)
+        if not w.flags.writeable:                         # a view of a bytes object: torch wants memory it may write to
+            w = w.copy()
+        n = w.shape[0]
+        with torch.cuda.device(self._cfg.device if self._cfg.device >= 0 else torch.cuda.current_device()):
+            self._h
+            d_w = torch.from_numpy(w).cuda()
+            d_st = torch.full((n,), 255, dtype=torch.uint8, device="cuda")
+            d_bad = torch.zeros(n, dtype=torch.int32, device="cuda")
+            self.r1cs_check_device(d_w.data_ptr(), n, d_st.data_ptr(), d_bad.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            return d_st.cpu().numpy(), d_bad.cpu().numpy().view(np.uint32)
+
+    def wtnsBody(self, buf):
+        """a .wtns image (what calculateWTNSBin / the CLI wrote) -> its witness section, after checking that the container is
+        THIS circuit's: same 76-byte header as b3w_wtns_header (prime, witnessSize).  Host-only."""
+        from .wtns import parse_wtns, WtnsError
+        w = parse_wtns(buf)
+        if w["prime"] != self.prime:
+            raise WtnsError("the file's prime is not this circuit's (%d bits vs %d)" % (w["prime"].bit_length(), self.prime.bit_length()))
+        if w["n8"] != 32 or w["n_witness"] != self.witnessSize:
+            raise WtnsError("the file holds %d witness values, this circuit has %d" % (w["n_witness"], self.witnessSize))
+        return w["body"]
+
+    def checkWTNSBin(self, buf):
+        """-> (ok, first_bad): the .wtns image's witness checked against every constraint on the GPU (see checkWitnesses)."""
+        status, bad = self.checkWitnesses(self.wtnsBody(buf)[None, :])
+        return bool(status[0] == 0), int(bad[0])
+
     # ---- NEW: batched entry point ----
     def _extras(self, n, sums, samples, first_bad):
         """-> (BatchExtras or None, dict of the arrays it points into)"""
