@@ -26,7 +26,8 @@ Keys of the JSON line (rank 0):
   e2e_packed   ditto with every witness returned in compact form (its 3 776-byte trace)
   e2e_hybrid   every .wtns body in host memory like e2e, but packed records over PCIe + expansion on host threads
   config4 / config5  BASELINE configs[3] / configs[4] through the C ABI, streamed, >= 1 s each (config 5: fused check,
-             per-instance witness checksums, a 1 024-instance sample of full witnesses verified against those checksums)
+             per-instance witness checksums, a 1 024-instance sample of full witnesses verified against those checksums;
+             sums_vs_oracle_b: ALL 2^24 checksums against the committed digests of Oracle B's, tests/golden/)
   fr_batches   b3w_witness_batch_fr (Fr256 rows, all-u32 and 1 % field-valued) next to b3w_witness_batch (N = 1 only)
   cpu_baseline the reference's own wasm witness program (oracle/_ref, translated to C) on all host cores,
              bounded sample (rank 0, N=1 only)
@@ -62,6 +63,31 @@ def workload_config(n=1 << LOG2_BATCH):
             "witness_bytes_per_batch_per_gpu": n * WIT_BYTES,
             "l2": "a batch's witnesses are 50.5 GB per GPU, >> 126 MB L2: nothing of one step survives in L2 for the next",
             "sharding": "contiguous index ranges, no collective"}
+
+
+def sums_vs_oracle_fixture(sums, first, fixture="compression_sums_2p24.npz"):
+    """Every per-instance witness checksum of a streamed blake3_compression run (instances first .. first + len(sums) of the
+    splitmix sequence) against Oracle B, through the per-4096-instance digests of Oracle B's checksums committed under
+    tests/golden/ (made by tests/golden/make_golden_sums.py; reading a fixture is not running the oracle).  Never raises:
+    -> {"match": bool, "blocks": k, ...} or {"skipped": why}."""
+    try:
+        import hashlib
+        path = os.path.join(ROOT, "tests", "golden", fixture)
+        if not os.path.exists(path):
+            return {"skipped": "tests/golden/%s not present" % fixture}
+        g = np.load(path)
+        blk, want = int(g["block"]), g["block_digest"]
+        n = int(sums.size)
+        if first % blk or n % blk or n == 0 or (first + n) // blk > want.size:
+            return {"skipped": "instances %d..%d are not whole blocks of the fixture (2^%d instances)" % (first, first + n, int(g["log2_n"]))}
+        s = np.ascontiguousarray(sums, "<u8")
+        got = np.array([int.from_bytes(hashlib.sha256(s[b:b + blk].tobytes()).digest()[:8], "little") for b in range(0, n, blk)], np.uint64)
+        bad = np.nonzero(got != want[first // blk:(first + n) // blk])[0]
+        return {"match": bool(bad.size == 0), "blocks": int(got.size), "instances": n, "first_instance": int(first),
+                "first_differing_block": (int(bad[0]) + first // blk) if bad.size else None, "fixture": "tests/golden/" + fixture,
+                "what": "sha256 digests of Oracle B's checksums per 4096 instances: a match pins every witness checksum of the run"}
+    except Exception as e:                                    # the verification must not take the measurement down
+        return {"skipped": "error: %r" % (e,)}
 
 
 def measured_peaks():
@@ -439,6 +465,7 @@ def run_own(args, rank, world, local_rank):
         ok = bool(np.array_equal(gen.witness_checksums(smp, calc.witnessSize), sums[idx.astype(np.int64)])) if idx.size else None
         assert ok is not False, "%s: sample checksums differ" % tag
         tm = calc.lastTiming()
+        vs_oracle = sums_vs_oracle_fixture(sums, rank * n_r) if name == "blake3_compression" else None
         res = {"value": n_total / dt, "unit": "witnesses/s", "seconds_per_pass": dt, "passes_timed": reps, "instances": n_total,
                "instances_per_gpu": n_r, "witness_bytes": calc.witnessSize * 32, "generated_GB_per_pass": n_total * calc.witnessSize * 32 / 1e9,
                "ring_write_GBps_per_gpu": n_r * calc.witnessSize * 32 / dt / 1e9, "fused_check": fused, "byte_check": byte_check,
@@ -446,6 +473,9 @@ def run_own(args, rank, world, local_rank):
                "kernel_ms_note": "b3w_last_timing: sum of the CUDA-event durations of the pass's launches; launches alternate between the two ring "
                                  "streams and overlap, so the sum exceeds the wall time of the pass",
                "sums_xor_rank0": int(np.bitwise_xor.reduce(sums)), "samples_per_gpu": int(idx.size), "samples_match_their_sums": ok}
+        if vs_oracle is not None:                                # rank 0's record + the verdict of all ranks
+            res["sums_vs_oracle_b"] = vs_oracle
+            res["sums_match_oracle_b_on_all_ranks"] = all_true(vs_oracle.get("match") is not False) and "match" in vs_oracle
         del smp
         for p in (hin, hst, hpub, hsum, hsmp):
             L.b3w_host_free(p)

@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""make_golden_sums.py -- regenerates tests/golden/compression_sums_2p20.npz (run anywhere: needs the oracles only).
+"""make_golden_sums.py [log2_n] -- regenerates tests/golden/compression_sums_2p20.npz (default) or, with 24, compression_sums_2p24.npz
+(run anywhere: needs the oracles only; 2^20 takes 3.5 min on 8 cores, 2^24 an hour).
 
 The fixture pins the per-instance witness checksums (the b3w_checksum_device definition) of the 2^20
 blake3_compression instances splitmix_compression_inputs(2^20, first=0) -- BASELINE configs[3]'s count on the
@@ -39,27 +40,34 @@ def block_digests(sums):
                      for b in range(0, sums.size, BLOCK)], np.uint64)
 
 
-def main():
-    n = 1 << LOG2_N
-    rows = splitmix_compression_inputs(n, first=0)
+def main(log2_n=LOG2_N):
+    n = 1 << log2_n
     t = time.time()
-    sums = port.witness_batch("compression", rows, want="sums")
+    step = 1 << 18                                                       # bounded memory: 2^18 instances at a time
+    sums = np.empty(n, np.uint64)
+    for lo in range(0, n, step):
+        rows = splitmix_compression_inputs(min(step, n - lo), first=lo)
+        sums[lo:lo + rows.shape[0]] = port.witness_batch("compression", rows, want="sums")
+        if log2_n > 20:
+            print("  %d / %d  (%.0f s)" % (lo + rows.shape[0], n, time.time() - t), flush=True)
     print("oracle B: %d sums in %.0f s" % (n, time.time() - t))
     if ref_wasm.available("compression"):
-        idx = np.arange(0, n, BLOCK) + (np.arange(n // BLOCK) * 2654435761 % BLOCK)      # one instance per block
-        wit, status, _ = ref_wasm.RefWasm("compression").batch_u32(rows[idx], nthreads=os.cpu_count() or 1)
+        idx = (np.arange(0, n, BLOCK) + (np.arange(n // BLOCK) * 2654435761 % BLOCK))[::max(1, n // BLOCK // 256)]   # <= 256 spread instances
+        rows = np.concatenate([splitmix_compression_inputs(1, first=int(i)) for i in idx])
+        wit, status, _ = ref_wasm.RefWasm("compression").batch_u32(rows, nthreads=os.cpu_count() or 1)
         assert (status == 0).all()
-        wit_b, sums_b, _ = port.witness_batch("compression", rows[idx], want="both")
+        wit_b, sums_b, _ = port.witness_batch("compression", rows, want="both")
         assert np.array_equal(wit, wit_b) and np.array_equal(sums_b, sums[idx])
         print("oracle A == oracle B on %d spread instances (every byte)" % idx.size)
     else:
         print("oracle/_ref not built: Oracle A cross-check skipped")
     sha = hashlib.sha256(np.ascontiguousarray(sums, "<u8").tobytes()).hexdigest()
-    np.savez_compressed(os.path.join(HERE, "compression_sums_2p20.npz"), log2_n=np.uint32(LOG2_N), block=np.uint32(BLOCK),
+    name = "compression_sums_2p%d.npz" % log2_n
+    np.savez_compressed(os.path.join(HERE, name), log2_n=np.uint32(log2_n), block=np.uint32(BLOCK),
                         block_digest=block_digests(sums), sha256=np.frombuffer(sha.encode(), np.uint8),
                         first16=sums[:16].copy(), xor=np.bitwise_xor.reduce(sums))
-    print("compression_sums_2p20.npz: sha256", sha)
+    print("%s: sha256 %s" % (name, sha))
 
 
 if __name__ == "__main__":
-    main()
+    main(int(sys.argv[1]) if len(sys.argv) > 1 else LOG2_N)

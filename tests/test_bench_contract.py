@@ -79,3 +79,30 @@ def test_both_arms_print_the_same_config():
     d = json.loads(p.stdout.strip().splitlines()[-1])
     assert d["impl"] == "reference" and d["config"] == cfg and d["higher_is_better"] is True and d["unit"] == "witnesses/s"
     assert d["cpu_baseline"]["cores"] == (os.cpu_count() or 1) and d["e2e"]["value"] == d["value"] > 0
+
+
+def test_bench_checks_streamed_checksums_against_the_oracle_fixture(built):
+    """bench.py holds every checksum of config 5's streamed run to committed digests of Oracle B's (tests/golden/); the
+    helper is exercised here with Oracle B's own sums standing in for the GPU's."""
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    import bench
+    from oracle import port
+    from hot_proofs_blake3_circom_b200.inputs import splitmix_compression_inputs
+    first = 101 * 4096
+    sums = port.witness_batch("compression", splitmix_compression_inputs(8192, first=first), want="sums")
+    for fixture in ("compression_sums_2p20.npz", "compression_sums_2p24.npz"):
+        if not os.path.exists(os.path.join(ROOT, "tests", "golden", fixture)):
+            assert "skipped" in bench.sums_vs_oracle_fixture(sums, first, fixture)
+            continue
+        r = bench.sums_vs_oracle_fixture(sums, first, fixture)
+        assert r["match"] is True and r["blocks"] == 2 and r["first_differing_block"] is None
+        bad = sums.copy()
+        bad[4096 + 7] ^= 1
+        r = bench.sums_vs_oracle_fixture(bad, first, fixture)
+        assert r["match"] is False and r["first_differing_block"] == 102
+        assert "skipped" in bench.sums_vs_oracle_fixture(sums, first + 1, fixture)              # not whole blocks
+        assert "skipped" in bench.sums_vs_oracle_fixture(sums[:100], first, fixture)
+        assert "skipped" in bench.sums_vs_oracle_fixture(sums, (1 << 24), fixture)               # beyond the fixture
+        json.dumps(r)
+    assert "skipped" in bench.sums_vs_oracle_fixture(sums, first, "no_such_fixture.npz")
