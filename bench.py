@@ -66,8 +66,8 @@ def workload_config(n=1 << LOG2_BATCH):
 
 
 def sums_vs_oracle_fixture(sums, first, fixture="compression_sums_2p24.npz"):
-    """Every per-instance witness checksum of a streamed blake3_compression run (instances first .. first + len(sums) of the
-    splitmix sequence) against Oracle B, through the per-4096-instance digests of Oracle B's checksums committed under
+    """Every per-instance witness checksum of a streamed run (instances first .. first + len(sums) of the circuit's splitmix
+    sequence: config 5's blake3_compression, config 4's blake3_nova_pasta) against Oracle B, through the per-4096-instance digests of Oracle B's checksums committed under
     tests/golden/ (made by tests/golden/make_golden_sums.py; reading a fixture is not running the oracle).  Never raises:
     -> {"match": bool, "blocks": k, ...} or {"skipped": why}."""
     try:
@@ -465,7 +465,8 @@ def run_own(args, rank, world, local_rank):
         ok = bool(np.array_equal(gen.witness_checksums(smp, calc.witnessSize), sums[idx.astype(np.int64)])) if idx.size else None
         assert ok is not False, "%s: sample checksums differ" % tag
         tm = calc.lastTiming()
-        vs_oracle = sums_vs_oracle_fixture(sums, rank * n_r) if name == "blake3_compression" else None
+        fixture = {"blake3_compression": "compression_sums_2p24.npz", "blake3_nova_pasta": "nova_pasta_o2_sums_2p20.npz"}.get(name)
+        vs_oracle = sums_vs_oracle_fixture(sums, rank * n_r, fixture) if fixture else None
         res = {"value": n_total / dt, "unit": "witnesses/s", "seconds_per_pass": dt, "passes_timed": reps, "instances": n_total,
                "instances_per_gpu": n_r, "witness_bytes": calc.witnessSize * 32, "generated_GB_per_pass": n_total * calc.witnessSize * 32 / 1e9,
                "ring_write_GBps_per_gpu": n_r * calc.witnessSize * 32 / dt / 1e9, "fused_check": fused, "byte_check": byte_check,

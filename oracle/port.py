@@ -55,7 +55,7 @@ def signals_fr(variant, values):
 
 def witness_batch(variant, rows, nthreads=None, want="witness"):
     """rows: (n, n_inputs) uint32.  want = "witness" -> (n, ws*32) u8;  "sums" -> u64[n] checksums
-    (same definition as b3w_checksum_device);  "both" -> (witness, sums, status)."""
+    (same definition as b3w_checksum_device);  "sums+status" -> (sums, status);  "both" -> (witness, sums, status)."""
     v = VARIANT_ID[variant]
     L = lib()
     rows = np.ascontiguousarray(rows, np.uint32)
@@ -63,7 +63,7 @@ def witness_batch(variant, rows, nthreads=None, want="witness"):
     assert rows.shape[1] == L.b3o_n_inputs(v)
     ws = L.b3o_witness_size(v)
     out = np.zeros((n, ws * 32), np.uint8) if want in ("witness", "both") else None
-    sums = np.zeros(n, np.uint64) if want in ("sums", "both") else None
+    sums = np.zeros(n, np.uint64) if want in ("sums", "sums+status", "both") else None
     status = np.zeros(n, np.int32)
     L.b3o_witness_batch_u32(v, rows.ctypes.data, n, out.ctypes.data if out is not None else None,
                             sums.ctypes.data if sums is not None else None, status.ctypes.data,
@@ -73,4 +73,6 @@ def witness_batch(variant, rows, nthreads=None, want="witness"):
         return out
     if want == "sums":
         return sums
+    if want == "sums+status":
+        return sums, status
     return out, sums, status

@@ -57,6 +57,50 @@ def test_streamed_2_20_sums_and_samples(built):
     wc.close()
 
 
+def test_streamed_2_24_every_checksum_against_oracle_b(built):
+    """BASELINE configs[4]'s size on one GPU (north_star: "bit-exact blake3_compression witnesses for 2^24 synthetic inputs"):
+    12.9 TB of witnesses stream through the HBM ring with the fused check; the checksum of EVERY one of them is held to
+    Oracle B's through the committed per-block digests (tests/golden/make_golden_sums.py 24: an hour of Oracle B, not
+    repeatable inside the suite), and a random 2^14 of them are re-derived live."""
+    n = 1 << 24
+    rows = gen.parallel_rows(gen.splitmix_compression_inputs, n, first=0, threads=NCPU)
+    wc = pkg.builder("blake3_compression", device=0, chunk=16384, fused_check=True)
+    res = wc.calculateWitnessBatch(rows, want_witness=False, sums=True, first_bad=True)
+    assert not res["status"].any() and (res["first_bad"] == _lib.B3W_NO_ROW).all()
+    g = np.load(os.path.join(GOLDEN, "compression_sums_2p24.npz"))
+    assert int(g["log2_n"]) == 24 and np.array_equal(res["sums"][:16], g["first16"])
+    bad = np.nonzero(make_golden_sums.block_digests(res["sums"]) != g["block_digest"])[0]
+    assert bad.size == 0, "blocks of 4096 instances whose checksums differ from Oracle B's: %s" % bad[:8]
+    assert int(np.bitwise_xor.reduce(res["sums"])) == int(g["xor"])
+    live = np.sort(np.random.default_rng(24).choice(n, 1 << 14, replace=False))
+    assert np.array_equal(res["sums"][live], port.witness_batch("compression", rows[live], nthreads=NCPU, want="sums"))
+    # out[16] of every instance is the plain BLAKE3 compression of its inputs?  checked at 2^16 in test_gpu_parity.py; here the
+    # public outputs of the live sample against the oracle's witnesses
+    w = port.witness_batch("compression", rows[live[:256]], nthreads=NCPU).view(np.uint32).reshape(256, WS, 8)
+    assert np.array_equal(res["pub"][live[:256]], w[:, 1:17, 0])
+    wc.close()
+
+
+def test_streamed_nova_pasta_2_20_every_checksum_against_oracle_b(built):
+    """BASELINE configs[3] (2^20 blake3_nova_pasta steps, Pallas scalar field, streamed): every checksum against Oracle B's
+    committed digests (tests/golden/make_golden_sums.py 20 nova_pasta_o2), a random 2^13 re-derived live."""
+    n = 1 << 20
+    rows = gen.parallel_rows(gen.splitmix_nova_inputs, n, first=0, threads=NCPU)
+    wc = pkg.builder("blake3_nova_pasta", device=0, chunk=16384)
+    res = wc.calculateWitnessBatch(rows, want_witness=False, sums=True)
+    assert not res["status"].any()
+    g = np.load(os.path.join(GOLDEN, "nova_pasta_o2_sums_2p20.npz"))
+    assert int(g["log2_n"]) == 20 and np.array_equal(res["sums"][:16], g["first16"])
+    bad = np.nonzero(make_golden_sums.block_digests(res["sums"]) != g["block_digest"])[0]
+    assert bad.size == 0, "blocks of 4096 instances whose checksums differ from Oracle B's: %s" % bad[:8]
+    live = np.sort(np.random.default_rng(20).choice(n, 1 << 13, replace=False))
+    want, want_sums, st = port.witness_batch("nova_pasta_o2", rows[live[:512]], nthreads=NCPU, want="both")
+    assert not st.any() and np.array_equal(res["sums"][live[:512]], want_sums)
+    assert np.array_equal(res["pub"][live[:512]], want.view(np.uint32).reshape(512, wc.witnessSize, 8)[:, 1:16, 0])       # z_{i+1}
+    assert np.array_equal(res["sums"][live], port.witness_batch("nova_pasta_o2", rows[live], nthreads=NCPU, want="sums"))
+    wc.close()
+
+
 @pytest.mark.parametrize("name,variant,rows_fn", [("blake3_nova_pasta", "nova_pasta_o2", gen.splitmix_nova_inputs),
                                                   ("blake3_nova_o1", "nova_bn_o1", gen.splitmix_nova_inputs)])
 def test_streamed_nova_sums_and_samples(built, name, variant, rows_fn):

@@ -112,23 +112,29 @@ def test_witness_structure_counts(golden):
     assert w[0, 0] == 1
 
 
-def test_sums_fixture_of_2p20_instances_is_oracle_b(built):
-    """tests/golden/compression_sums_2p20.npz (per-block digests of Oracle B's checksums of 2^20 instances, what the GPU's
-    streamed run is held to in test_gpu_extras.py) re-derived here for three of its 256 blocks, first and last included."""
+@pytest.mark.parametrize("fixture,variant,blocks", [("compression_sums_2p20.npz", "compression", (0, 101, 255)),
+                                                    ("compression_sums_2p24.npz", "compression", (0, 300, 4095)),
+                                                    ("nova_pasta_o2_sums_2p20.npz", "nova_pasta_o2", (0, 77, 255))])
+def test_sums_fixtures_are_oracle_b(built, fixture, variant, blocks):
+    """tests/golden/*_sums_2p*.npz (per-block digests of Oracle B's checksums of 2^20 / 2^24 instances, what the GPU's streamed
+    runs and bench.py's config 4 / 5 are held to) re-derived here for three blocks of each, first and last included."""
     import os
     import sys
     gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
     sys.path.insert(0, gdir)
     import make_golden_sums as mk
-    g = np.load(os.path.join(gdir, "compression_sums_2p20.npz"))
+    g = np.load(os.path.join(gdir, fixture))
     nblk = (1 << int(g["log2_n"])) // mk.BLOCK
     assert g["block_digest"].shape == (nblk,) and int(g["block"]) == mk.BLOCK and len(bytes(g["sha256"])) == 64
-    for b in (0, 101, nblk - 1):
-        rows = gen.splitmix_compression_inputs(mk.BLOCK, first=b * mk.BLOCK)
-        sums = port.witness_batch("compression", rows, want="sums")
-        assert mk.block_digests(sums)[0] == g["block_digest"][b]
+    assert blocks[-1] == nblk - 1
+    rows_fn = gen.splitmix_compression_inputs if variant == "compression" else gen.splitmix_nova_inputs
+    ws = port.witness_size(variant)
+    for b in blocks:
+        rows = rows_fn(mk.BLOCK, first=b * mk.BLOCK)
+        sums, status = port.witness_batch(variant, rows, want="sums+status")
+        assert not status.any() and mk.block_digests(sums)[0] == g["block_digest"][b]
         if b == 0:
             assert np.array_equal(sums[:16], g["first16"])
             # the sums are the checksum of the witness bytes (conftest.checksum_np = b3w_checksum_device's definition)
-            wit = port.witness_batch("compression", rows[:8])
-            assert np.array_equal(checksum_np(wit, WS), sums[:8])
+            wit = port.witness_batch(variant, rows[:8])
+            assert np.array_equal(checksum_np(wit, ws), sums[:8])
