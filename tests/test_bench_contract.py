@@ -106,3 +106,15 @@ def test_bench_checks_streamed_checksums_against_the_oracle_fixture(built):
         assert "skipped" in bench.sums_vs_oracle_fixture(sums, (1 << 24), fixture)               # beyond the fixture
         json.dumps(r)
     assert "skipped" in bench.sums_vs_oracle_fixture(sums, first, "no_such_fixture.npz")
+
+
+def test_committed_bench_line_agrees_with_oracle_b_on_2p24_checksums():
+    """The XOR of all per-instance witness checksums the B200 reported for config 5 (2^24 blake3_compression) and config 4
+    (2^20 blake3_nova_pasta) in the committed single-GPU bench line equals the XOR of Oracle B's checksums of the same
+    instances (tests/golden/*_sums_2p*.npz, generated AFTER that GPU run): 64 bits over 12.9 TB / 0.78 TB of witnesses."""
+    import numpy as np
+    d = line("r02z_bench_own.json")
+    g5 = np.load(os.path.join(ROOT, "tests", "golden", "compression_sums_2p24.npz"))
+    g4 = np.load(os.path.join(ROOT, "tests", "golden", "nova_pasta_o2_sums_2p20.npz"))
+    assert d["config5"]["instances"] == 1 << 24 and d["config5"]["sums_xor_rank0"] == int(g5["xor"])
+    assert d["config4"]["instances"] == 1 << 20 and d["config4"]["sums_xor_rank0"] == int(g4["xor"])
