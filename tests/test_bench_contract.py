@@ -118,3 +118,20 @@ def test_committed_bench_line_agrees_with_oracle_b_on_2p24_checksums():
     g4 = np.load(os.path.join(ROOT, "tests", "golden", "nova_pasta_o2_sums_2p20.npz"))
     assert d["config5"]["instances"] == 1 << 24 and d["config5"]["sums_xor_rank0"] == int(g5["xor"])
     assert d["config4"]["instances"] == 1 << 20 and d["config4"]["sums_xor_rank0"] == int(g4["xor"])
+
+
+@pytest.mark.parametrize("name", ["r02z_bench_own.json", "r02z_bench_n2.json", "r02z_bench_n8.json"])
+def test_committed_bench_lines_rank0_shards_agree_with_oracle_b(name):
+    """Rank 0's shard of a streamed run is a prefix of the instance sequence: the XOR of the checksums the B200s reported for
+    it (config 5: 2^24 / N instances with the fused check; the byte-check run: 2^22 / N) equals the XOR of Oracle B's
+    checksums of that prefix (tests/golden/compression_sums_prefix_xor.npz, computed after those runs)."""
+    import numpy as np
+    g = np.load(os.path.join(ROOT, "tests", "golden", "compression_sums_prefix_xor.npz"))
+    want = {1 << int(k): int(x) for k, x in zip(g["log2_n"], g["xor"])}
+    g24 = np.load(os.path.join(ROOT, "tests", "golden", "compression_sums_2p24.npz"))
+    want[1 << 24] = int(g24["xor"])
+    d = line(name)
+    for key in ("config5", "config5_byte_check"):
+        per_gpu = d[key]["instances_per_gpu"]
+        assert per_gpu * d["n_gpus"] == d[key]["instances"] and per_gpu in want, (key, per_gpu)
+        assert d[key]["sums_xor_rank0"] == want[per_gpu], (name, key, per_gpu)
