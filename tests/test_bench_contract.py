@@ -135,3 +135,9 @@ def test_committed_bench_lines_rank0_shards_agree_with_oracle_b(name):
         per_gpu = d[key]["instances_per_gpu"]
         assert per_gpu * d["n_gpus"] == d[key]["instances"] and per_gpu in want, (key, per_gpu)
         assert d[key]["sums_xor_rank0"] == want[per_gpu], (name, key, per_gpu)
+    # config 4 (2^20 blake3_nova_pasta steps, Pallas scalar field): 2^20 / N per rank
+    g = np.load(os.path.join(ROOT, "tests", "golden", "nova_pasta_o2_sums_prefix_xor.npz"))
+    want = {1 << int(k): int(x) for k, x in zip(g["log2_n"], g["xor"])}
+    want[1 << 20] = int(np.load(os.path.join(ROOT, "tests", "golden", "nova_pasta_o2_sums_2p20.npz"))["xor"])
+    per_gpu = d["config4"]["instances_per_gpu"]
+    assert per_gpu * d["n_gpus"] == 1 << 20 and d["config4"]["sums_xor_rank0"] == want[per_gpu], (name, per_gpu)
