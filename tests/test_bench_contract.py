@@ -141,3 +141,17 @@ def test_committed_bench_lines_rank0_shards_agree_with_oracle_b(name):
     want[1 << 20] = int(np.load(os.path.join(ROOT, "tests", "golden", "nova_pasta_o2_sums_2p20.npz"))["xor"])
     per_gpu = d["config4"]["instances_per_gpu"]
     assert per_gpu * d["n_gpus"] == 1 << 20 and d["config4"]["sums_xor_rank0"] == want[per_gpu], (name, per_gpu)
+
+
+def test_committed_bench_lines_headline_batch_agrees_with_oracle_b(built):
+    """The timed region's own batch (2^16 LCG(6429) instances, rank 0 = instances 0 .. 2^16): the XOR of the checksums the
+    B200 computed from the bytes in the timed COMPRESSIBLE buffer equals Oracle B's, re-derived live (14 s on 8 cores)."""
+    import numpy as np
+    from oracle import port
+    from hot_proofs_blake3_circom_b200.inputs import lcg_compression_inputs
+    sums = port.witness_batch("compression", lcg_compression_inputs(1 << 16), want="sums")
+    want = int(np.bitwise_xor.reduce(sums))
+    for name in ("r02z_bench_own.json", "r02z_bench_n2.json", "r02z_bench_n8.json"):
+        d = line(name)
+        got = d.get("run", d["config"])["witness_checksums_xor_rank0"]          # under `config` in lines printed before `run` existed
+        assert got == want, name
